@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the message-passing hot path (BASELINE.json metric: RouteNet samples/sec, with the
+message-passing edges/sec of every iteration reported beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+One "step" = one pass of the hot path over one batch of synthetic input: device adjacency build
+(CSR, length order, step tables) + T message-passing iterations + readout.
+ * ``value``  : whole-job samples/s with the batch's raw tensors already resident in HBM.
+ * ``e2e``    : the same through the public Engine API from pinned HOST buffers: H2D of the packed
+                batch, adjacency build, forward, D2H of the predictions -- all inside the timed region.
+ * ``roofline``: the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak.
+ * ``cpu_baseline`` / ``--impl reference``: the op-for-op CPU restatement of the reference (oracle/),
+   because the reference itself needs tensorflow==2.1.0 which cannot be installed.
+Weak scaling: every rank runs its own batch of the same size; no data-path collective (inference).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (golden fixture holding model json + base topology, shape, qsize, default samples per GPU)
+    "routenet_geant2_b4096": ("routenet_geant2", "geant2", False, 4096),
+    "routenet_nsfnet_b4096": ("routenet_nsfnet", "nsfnet", False, 4096),
+    "qsize_nsfnet_b4096": ("qsize_nsfnet", "nsfnet", True, 4096),
+}
+DEFAULT_WORKLOAD = "routenet_geant2_b4096"
+
+
+def load_case(name):
+    fixture, shape, qsize, n = WORKLOADS[name]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", fixture + ".json")))
+    return g, shape, qsize, n
+
+
+def feature_fns(qsize):
+    # already-normalised feature ranges (examples/*/main.py normalisations applied to the raw ranges)
+    if qsize:
+        return {"traffic": lambda r, n: (r.uniform(0.05, 0.6, n) - 0.28) / 0.15,
+                "link_capacity": lambda r, n: (r.choice([10.0, 25.0, 40.0], n) - 27.0) / 14.86,
+                "queue_sizes": lambda r, n: (r.choice([1.0, 8.0, 16.0, 32.0], n) - 16.5) / 15.5}
+    return {"traffic": lambda r, n: (r.uniform(40.0, 300.0, n) - 170.0) / 130.0,
+            "link_capacity": lambda r, n: (r.choice([10000.0, 40000.0], n) - 25000.0) / 40000.0}
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------ CPU restatement
+def _cpu_worker(args):
+    """Forward of `count` samples with the oracle (per-sample loop = the reference's model_fn loop)."""
+    workload, count, seed = args
+    import numpy as _np
+    from oracle import ignnition_oracle as orc
+    g, shape, qsize, _ = load_case(workload)
+    dims = g["reference_meta"]["dimensions"]
+    o = orc.Oracle(g["model_json"], dims, dtype=_np.float32)
+    w = o.init_weights(1234)
+    base = dict(g["reference_tensors"][0])
+    rng = _np.random.RandomState(seed)
+    fns = feature_fns(qsize)
+    ent_of = {f["name"]: e["name"] for e in g["model_json"]["entities"] for f in e.get("features", [])}
+    t0 = time.perf_counter()
+    for _ in range(count):
+        for name, fn in fns.items():
+            base[name] = fn(rng, base["num_" + ent_of[name]]).astype(_np.float32)
+        o.forward(base, w)
+    return time.perf_counter() - t0
+
+
+def cpu_samples_per_s(workload, total_samples, procs):
+    import multiprocessing as mp
+    per = max(1, total_samples // procs)
+    t0 = time.perf_counter()
+    if procs == 1:
+        _cpu_worker((workload, per, 0))
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            pool.map(_cpu_worker, [(workload, per, s) for s in range(procs)])
+    dt = time.perf_counter() - t0
+    return per * procs / dt, per * procs, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # one worker process per core, one BLAS thread each (the matmuls are tiny: [P,32]x[32,96])
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    # calibrate on one core, then size a step to ~3 s of wall time on all cores
+    _cpu_worker((args.workload, 1, 0))
+    t1 = _cpu_worker((args.workload, 2, 0)) / 2
+    import multiprocessing as mp
+    per = max(1, min(512, int(3.0 / max(t1, 1e-4))))
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, [(args.workload, max(1, per // 4), s) for s in range(cores)])
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_cpu_worker, [(args.workload, per, 100 + k * cores + s) for s in range(cores)])
+        dt = time.perf_counter() - t0
+    n = per * cores
+    val = n * args.steps / dt
+    g, shape, qsize, _ = load_case(args.workload)
+    line = {
+        "impl": "reference", "metric": "routenet_samples_per_s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "samples_per_step": n, "iterations": 8,
+                   "note": "CPU restatement of the reference (oracle port); tensorflow==2.1.0 not installable"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d samples/step of %s, one process per core, per-sample forward loop "
+                                   "(generate_model.py:712-724)" % (n, args.workload)},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ignnition_b200 import Engine, ModelDescription, _lib
+    from ignnition_b200.batching import assemble_tiled
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    g, shape, qsize, n_default = load_case(args.workload)
+    n_samples = args.batch or n_default
+    dims = g["reference_meta"]["dimensions"]
+    md = ModelDescription(g["model_json"], dims)
+    eng = Engine(md, device=dev, seed=0)
+    from oracle import ignnition_oracle as orc   # checker-side weights only (same seeded weights as the CPU leg)
+    eng.set_weights(orc.Oracle(g["model_json"], dims).init_weights(1234))
+    base = g["reference_tensors"][0]
+    batch = assemble_tiled(base, n_samples, eng.entities, eng.features, eng.adjacencies, eng.sequences,
+                           feature_fns(qsize), seed=rank)
+    pinned = batch.pack(pin=True)
+    edges_per_iter = sum(batch.n_edges[a.name] for a in eng.adjacencies)
+    out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
+    n_pred = batch.num[out_entity]
+
+    def step_resident(graph):
+        eng.build_graph(graph)
+        return eng.forward(graph)
+
+    host_pred = torch.empty(n_pred, 1, dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        graph = eng.upload(batch, pinned)
+        eng.build_graph(graph)
+        pred = eng.forward(graph)
+        host_pred.copy_(pred, non_blocking=True)
+        return graph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    graph = eng.upload(batch, pinned)
+    for _ in range(max(args.warmup, 3)):
+        step_resident(graph)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.ign_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident(graph)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.ign_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # end to end from host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+
+    # dominant kernel: per-kernel CUDA-event timing of one more pass (same stream, after the timed region)
+    kern = profile_kernels(eng, graph, torch, args.steps)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        top = max(kern.values(), key=lambda k: k["ms_total"])
+        roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": top["gbs"] / hbm_peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "algorithmic_bytes_per_launch": top["bytes"], "avg_launch_ms": top["ms_avg"],
+                "share_of_step": top["ms_total"] / max(sum(k["ms_total"] for k in kern.values()), 1e-9)}
+        cores = os.cpu_count() or 1
+        cpu_val, cpu_n, cpu_dt = cpu_samples_per_s(args.workload, args.cpu_samples, 1)
+        line = {
+            "metric": "routenet_samples_per_s", "value": n_samples * world * args.steps / (ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "samples_per_gpu": n_samples, "iterations": eng.T,
+                       "paths_per_gpu": batch.num.get("path"), "links_per_gpu": batch.num.get("link"),
+                       "mp_edges_per_iteration_per_gpu": edges_per_iter,
+                       "timing": "inputs+states per step exceed L2 (no flush needed)",
+                       "step": "device CSR build + T message-passing iterations + readout"},
+            "mp_edges_per_s": edges_per_iter * eng.T * world * args.steps / (ms / 1e3),
+            "e2e": {"value": n_samples * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(pinned[0].numel()), "d2h_bytes_per_step": int(host_pred.numel() * 4),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "kernels": sorted(kern.values(), key=lambda k: -k["ms_total"]),
+            "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": 1, "kind": "port",
+                             "host_cores": cores,
+                             "sample": "%d samples of %s through oracle/ignnition_oracle.py (NumPy fp32, "
+                                       "per-sample loop), %.1f s" % (cpu_n, args.workload, cpu_dt)},
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_kernels(eng, graph, torch, reps):
+    """CUDA-event time of every launch class in one forward (events on the launching stream)."""
+    from ignnition_b200 import ops
+    records = {}
+    orig = {}
+
+    def wrap(name, bytes_fn):
+        fn = getattr(ops, name)
+        orig[name] = fn
+
+        def timed(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            records.setdefault(name, []).append((e0, e1, bytes_fn(*a, **kw)))
+            return out
+        setattr(ops, name, timed)
+
+    def b_gru_seq(steps_rowptr, steps, order, srcs, h0, *a, **kw):
+        E, n, F, U = steps.numel(), h0.shape[0], srcs[0].shape[1], h0.shape[1]
+        return E * (4 + 4 * F) + n * (8 * U + 8)            # col + gathered row per step; h0 in, h out, rowptr, order
+
+    def b_agg(rowptr, col, src_states, h_dst, *a, **kw):
+        E, n, F, U = col.numel(), h_dst.shape[0], src_states.shape[1], h_dst.shape[1]
+        return E * (4 + 4 * F) + n * (8 * U + 4)
+
+    def b_seg(op, rowptr, col, src_states, *a, **kw):
+        n, F = rowptr.numel() - 1, src_states.shape[1]
+        E = col.numel() if col is not None else src_states.shape[0]
+        return E * (4 + 4 * F) + n * (4 * F + 4)
+
+    def b_dense(x, w, bias, act, *a, **kw):
+        return 4 * (x.numel() + x.shape[0] * w.shape[1] + w.numel())
+
+    def b_csr(dst, src, seq, num_dst, *a, **kw):
+        return dst.numel() * 8 * 2 * 3 + num_dst * 4
+
+    def b_gru_cell(x, h, *a, **kw):
+        return 4 * (x.numel() + 2 * h.numel())
+
+    for name, fn in (("gru_seq", b_gru_seq), ("agg_gru_cell", b_agg), ("segment_reduce", b_seg),
+                     ("dense", b_dense), ("csr_build", b_csr), ("gru_cell", b_gru_cell)):
+        wrap(name, fn)
+    try:
+        for _ in range(max(1, min(reps, 3))):
+            eng.build_graph(graph)
+            eng.forward(graph)
+        torch.cuda.synchronize()
+    finally:
+        for name, fn in orig.items():
+            setattr(ops, name, fn)
+    out = {}
+    n_pass = max(1, min(reps, 3))
+    for name, recs in records.items():
+        ms = [a.elapsed_time(b) for a, b, _ in recs]
+        by = [c for _, _, c in recs]
+        tot = float(sum(ms))
+        out[name] = {"name": "ign_" + name, "launches_per_step": len(recs) // n_pass, "ms_total": tot / n_pass,
+                     "ms_avg": tot / len(recs), "bytes": float(np.mean(by)),
+                     "gbs": float(sum(by)) / (tot / 1e3) / 1e9 if tot > 0 else 0.0}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--cpu-samples", type=int, default=48, help="samples of the bounded CPU-baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,361 @@
+// Dense layers y = act(x W + b) for the message / update / readout MLPs (sm_100a, fp32).
+//
+// Replaces the Keras functional Model of Dense layers the reference builds in
+// Feed_forward_model.construct_tf_model (code/utils/auxilary_classes.py:918-975) and calls at
+// code/utils/generate_model.py:468 (message), :600 (update) and :624 (readout).
+//
+// This file is the fp32 CUDA-core path: 128x128x16 shared-memory tiles, 8x8 register tiles,
+// bias + activation fused in the epilogue (the pre-activation is optionally kept for the
+// backward pass).  Layers with a handful of outputs (the 256 -> 1 readout head) use a
+// warp-per-row dot product instead, which is HBM-bound.  The same tile kernel, with transposed
+// operand reads, serves the backward products dX = dZ W^T and dW = X^T dZ.
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+
+// C[M,N] (+)= op(A) op(B);  TA: A is stored [K,M] (read transposed); TB: B is stored [N,K].
+// EPI 0: C = act(acc + bias[n]), optional pre-activation store   (forward)
+// EPI 1: C = acc                                                (dX)
+// EPI 2: atomicAdd(C, acc) over a split of the reduction dim     (dW; grid.z = splits)
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                            float* __restrict__ C, int64_t M, int N, int64_t K,
+                                                            const float* __restrict__ bias, int act,
+                                                            float* __restrict__ pre, int64_t k_per_split) {
+  __shared__ __align__(16) float As[2][BK][LDA_S];
+  __shared__ __align__(16) float Bs[2][BK][LDB_S];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t kbeg = (EPI == 2) ? (int64_t)blockIdx.z * k_per_split : 0;
+  const int64_t kend = (EPI == 2) ? min(K, kbeg + k_per_split) : K;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  // global -> register staging: 128x16 A tile and 16x128 B tile, 8 floats per thread each
+  float ra[8], rb[8];
+  auto load_tiles = [&](int64_t k0) {
+    if (!TA) {          // A[m, k] row-major, lda = K: thread reads 4 consecutive k of 2 rows
+      const int kq = (tid % 4) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t m = m0 + tid / 4 + 64 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t k = k0 + kq + j;
+          ra[i * 4 + j] = (m < M && k < kend) ? __ldg(A + m * K + k) : 0.0f;
+        }
+      }
+    } else {            // A stored [K, M]: thread reads 4 consecutive m of 2 k rows
+      const int mq = (tid % 32) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t k = k0 + tid / 32 + 8 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t m = m0 + mq + j;
+          ra[i * 4 + j] = (m < M && k < kend) ? __ldg(A + k * M + m) : 0.0f;
+        }
+      }
+    }
+    if (!TB) {          // B[k, n] row-major, ldb = N
+      const int nq = (tid % 32) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t k = k0 + tid / 32 + 8 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + nq + j;
+          rb[i * 4 + j] = (n < N && k < kend) ? __ldg(B + k * N + n) : 0.0f;
+        }
+      }
+    } else {            // B stored [N, K]
+      const int kq = (tid % 4) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n = n0 + tid / 4 + 64 * i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t k = k0 + kq + j;
+          rb[i * 4 + j] = (n < N && k < kend) ? __ldg(B + (int64_t)n * K + k) : 0.0f;
+        }
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+    if (!TA) {
+      const int kq = (tid % 4) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[buf][kq + j][tid / 4 + 64 * i] = ra[i * 4 + j];
+    } else {
+      const int mq = (tid % 32) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        *reinterpret_cast<float4*>(&As[buf][tid / 32 + 8 * i][mq]) =
+            make_float4(ra[i * 4], ra[i * 4 + 1], ra[i * 4 + 2], ra[i * 4 + 3]);
+    }
+    if (!TB) {
+      const int nq = (tid % 32) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        *reinterpret_cast<float4*>(&Bs[buf][tid / 32 + 8 * i][nq]) =
+            make_float4(rb[i * 4], rb[i * 4 + 1], rb[i * 4 + 2], rb[i * 4 + 3]);
+    } else {
+      const int kq = (tid % 4) * 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Bs[buf][kq + j][tid / 4 + 64 * i] = rb[i * 4 + j];
+    }
+  };
+
+  int buf = 0;
+  if (kbeg < kend) {
+    load_tiles(kbeg);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
+    if (more) load_tiles(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (EPI == 0) {
+        if (bias) v += bias[n];
+        if (pre) pre[m * N + n] = v;
+        C[m * N + n] = act_fwd(act, v);
+      } else if (EPI == 1) {
+        C[m * N + n] = v;
+      } else {
+        atomicAdd(C + m * N + n, v);
+      }
+    }
+  }
+}
+
+// few outputs (N <= 8): one warp per row, HBM-bound
+template <int NMAX>
+__global__ void __launch_bounds__(256) dense_small_n_kernel(const float* __restrict__ x, int64_t M, int K,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int N, int act, float* __restrict__ y,
+                                                            float* __restrict__ pre) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.0f;
+  for (int k = lane; k < K; k += 32) {
+    const float xv = __ldg(x + row * K + k);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc[n] = fmaf(xv, __ldg(w + (int64_t)k * N + n), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) {
+      if (n < N) {
+        float v = acc[n] + (bias ? bias[n] : 0.0f);
+        if (pre) pre[row * N + n] = v;
+        y[row * N + n] = act_fwd(act, v);
+      }
+    }
+  }
+}
+
+// dz = dy * act'(pre), in place; db += column sums of dz (per-CTA partial, then atomics)
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ dy, const float* __restrict__ pre,
+                                                           int64_t M, int N, int act, float* __restrict__ db) {
+  // each CTA covers 64 rows; thread t handles columns t, t+256, ...
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const int64_t r1 = min(M, r0 + 64);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float s = 0.0f;
+    for (int64_t r = r0; r < r1; ++r) {
+      float g = dy[r * N + n];
+      if (act != IGN_ACT_LINEAR) {
+        g *= act_bwd(act, pre[r * N + n]);
+        dy[r * N + n] = g;
+      }
+      s += g;
+    }
+    if (db) atomicAdd(db + n, s);
+  }
+}
+
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ label, int64_t n,
+                           float grad_scale, float* __restrict__ d_pred, double* __restrict__ sse) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double e2 = 0.0;
+  if (i < n) {
+    const float e = pred[i] - label[i];
+    if (d_pred) d_pred[i] = 2.0f * e * grad_scale;
+    e2 = (double)e * (double)e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = e2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+    atomicAdd(sse, s);
+  }
+}
+
+__global__ void l2_kernel(const float* __restrict__ w, int64_t n, float lambda, float* __restrict__ dw,
+                          double* __restrict__ reg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < n) {
+    const float v = w[i];
+    if (dw) dw[i] += 2.0f * lambda * v;
+    s = (double)v * (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += part[k];
+    if (reg) atomicAdd(reg, (double)lambda * t);
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr_t, float beta1, float beta2, float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  w[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+}  // namespace
+
+extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                         float* y, float* pre_act, void* stream) {
+  IGN_REQUIRE(m >= 0 && k > 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: dense: bad shape");
+  IGN_REQUIRE(act >= IGN_ACT_LINEAR && act <= IGN_ACT_LEAKY_RELU, IGN_ERR_INVALID,
+              "IGNNITION: dense: unknown activation %d", act);
+  if (m == 0) return IGN_OK;
+  IGN_REQUIRE(x && w && y, IGN_ERR_INVALID, "IGNNITION: dense: null pointer");
+  cudaStream_t st = ign_stream(stream);
+  if (n <= 8) {
+    dense_small_n_kernel<8><<<(unsigned)ign_cdiv(m * 32, 256), 256, 0, st>>>(x, m, k, w, bias, n, act, y, pre_act);
+    IGN_CHECK_LAUNCH("dense_small_n");
+    return IGN_OK;
+  }
+  dim3 grid((unsigned)ign_cdiv(m, BM), (unsigned)ign_cdiv(n, BN), 1);
+  gemm_kernel<false, false, 0><<<grid, GEMM_THREADS, 0, st>>>(x, w, y, m, n, k, bias, act, pre_act, 0);
+  IGN_CHECK_LAUNCH("dense");
+  return IGN_OK;
+}
+
+extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, int n, int act,
+                             const float* pre_act, float* dy, float* dx, float* dw, float* db, void* stream) {
+  IGN_REQUIRE(m >= 0 && k > 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: dense_bwd: bad shape");
+  if (m == 0) return IGN_OK;
+  IGN_REQUIRE(x && w && dy, IGN_ERR_INVALID, "IGNNITION: dense_bwd: null pointer");
+  IGN_REQUIRE(act == IGN_ACT_LINEAR || pre_act, IGN_ERR_INVALID, "IGNNITION: dense_bwd: pre-activation needed");
+  cudaStream_t st = ign_stream(stream);
+  if (act != IGN_ACT_LINEAR || db) {
+    act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db);
+    IGN_CHECK_LAUNCH("act_bwd_bias");
+  }
+  if (dx) {   // dX[m,k] = dZ[m,n] W^T : B = W stored [k,n] = [N',K'] with N'=k, K'=n
+    dim3 grid((unsigned)ign_cdiv(m, BM), (unsigned)ign_cdiv(k, BN), 1);
+    gemm_kernel<false, true, 1><<<grid, GEMM_THREADS, 0, st>>>(dy, w, dx, m, k, n, nullptr, 0, nullptr, 0);
+    IGN_CHECK_LAUNCH("dense_bwd_dx");
+  }
+  if (dw) {   // dW[k,n] += X^T[k,m] dZ[m,n] : A = X stored [m,k] = [K',M'] with M'=k, K'=m
+    int64_t splits = ign_cdiv(m, 4096);
+    if (splits > 1024) splits = 1024;
+    const int64_t per = ign_cdiv(ign_cdiv(m, splits), BK) * BK;
+    splits = ign_cdiv(m, per);
+    dim3 grid((unsigned)ign_cdiv(k, BM), (unsigned)ign_cdiv(n, BN), (unsigned)splits);
+    gemm_kernel<true, false, 2><<<grid, GEMM_THREADS, 0, st>>>(x, dy, dw, k, n, m, nullptr, 0, nullptr, per);
+    IGN_CHECK_LAUNCH("dense_bwd_dw");
+  }
+  return IGN_OK;
+}
+
+extern "C" int ign_mse_loss(const float* pred, const float* label, int64_t n, float grad_scale, float* d_pred,
+                            double* sse, void* stream) {
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: mse_loss: negative size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(pred && label && sse, IGN_ERR_INVALID, "IGNNITION: mse_loss: null pointer");
+  mse_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(pred, label, n, grad_scale, d_pred, sse);
+  IGN_CHECK_LAUNCH("mse_loss");
+  return IGN_OK;
+}
+
+extern "C" int ign_l2_reg(const float* w, int64_t n, float lambda, float* dw, double* reg, void* stream) {
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: l2_reg: negative size");
+  if (n == 0 || lambda == 0.0f) return IGN_OK;
+  IGN_REQUIRE(w, IGN_ERR_INVALID, "IGNNITION: l2_reg: null pointer");
+  l2_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(w, n, lambda, dw, reg);
+  IGN_CHECK_LAUNCH("l2_reg");
+  return IGN_OK;
+}
+
+extern "C" int ign_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int64_t step, void* stream) {
+  IGN_REQUIRE(n >= 0 && step >= 1, IGN_ERR_INVALID, "IGNNITION: adam_step: bad argument");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(w && g && m && v, IGN_ERR_INVALID, "IGNNITION: adam_step: null pointer");
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
+  adam_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(w, g, m, v, n, (float)lr_t, beta1, beta2, eps);
+  IGN_CHECK_LAUNCH("adam_step");
+  return IGN_OK;
+}

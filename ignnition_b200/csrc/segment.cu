@@ -1,0 +1,230 @@
+// Gather + segmented aggregation over a CSR-by-destination (sm_100a), plus the small layout
+// kernels around it (initial hidden state, gathered concat).
+//
+// ign_segment_reduce replaces tf.gather -> tf.scatter_nd into the padded [num_dst,max_len,F]
+// tensor -> tf.reduce_sum(axis=1)  (reference code/utils/generate_model.py:432,479-490 and
+// code/utils/auxilary_classes.py:254-262).  One sub-warp of G = F/4 lanes owns one destination,
+// walks its slots in seq order with a single accumulator (so the sum order is the reference's
+// column order: deterministic, no atomics), stages G column indices per coalesced load and
+// broadcasts them by shuffle, and keeps UNROLL independent 16-byte row loads in flight per lane.
+// HBM-bound: algorithmic bytes = E*(4 + 4F) + num_dst*(4F + 4)  (DESIGN.md).
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int SEG_THREADS = 256;
+constexpr int SEG_UNROLL = 4;
+
+template <int OP>
+__device__ __forceinline__ void seg_acc(float4& a, const float4& v) {
+  if (OP == IGN_OP_MAX) {
+    a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
+  } else {
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+}
+
+// G lanes per destination (power of two <= 32), V float4 columns per lane: F <= 4*G*V
+template <int G, int V, int OP>
+__global__ void __launch_bounds__(SEG_THREADS) segment_reduce_kernel(const int* __restrict__ rowptr,
+                                                                     const int* __restrict__ col,
+                                                                     const float* __restrict__ src, int F,
+                                                                     int64_t num_dst, float* __restrict__ out) {
+  const int64_t gid = ((int64_t)blockIdx.x * SEG_THREADS + threadIdx.x) / G;
+  if (gid >= num_dst) return;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);                                   // lane inside the group
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const int lo = rowptr[gid], hi = rowptr[gid + 1];
+  const float init = (OP == IGN_OP_MAX) ? -INFINITY : 0.0f;
+  float4 acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = make_float4(init, init, init, init);
+  bool colok[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) colok[v] = (gl + v * G) * 4 < F;
+
+  for (int e = lo; e < hi; e += G) {
+    const int mine = (e + gl < hi) ? (col ? col[e + gl] : e + gl) : -1;
+    const int cnt = min(G, hi - e);
+    for (int j = 0; j < cnt; j += SEG_UNROLL) {
+      int c[SEG_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SEG_UNROLL; ++u) c[u] = __shfl_sync(gmask, mine, (j + u) & (G - 1), G);
+      float4 val[SEG_UNROLL][V];
+#pragma unroll
+      for (int u = 0; u < SEG_UNROLL; ++u) {
+        const bool ok = (j + u < cnt);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (ok && colok[v]) val[u][v] = ldg_f4(src + (int64_t)c[u] * F + (gl + v * G) * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < SEG_UNROLL; ++u) {
+        if (j + u < cnt) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (colok[v]) seg_acc<OP>(acc[v], val[u][v]);
+        }
+      }
+    }
+  }
+  const int len = hi - lo;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if (!colok[v]) continue;
+    float4 r = acc[v];
+    if (OP == IGN_OP_MEAN) {
+      const float inv = 1.0f / (float)max(len, 1);
+      r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+    }
+    if (OP == IGN_OP_MAX && len == 0) r = make_float4(0.f, 0.f, 0.f, 0.f);
+    st_f4(out + gid * F + (gl + v * G) * 4, r);
+  }
+}
+
+template <int G, int V>
+int launch_segment(int op, const int* rowptr, const int* col, const float* src, int F, int64_t num_dst,
+                   float* out, cudaStream_t st) {
+  const int64_t threads = num_dst * G;
+  const unsigned grid = (unsigned)ign_cdiv(threads, SEG_THREADS);
+  switch (op) {
+    case IGN_OP_SUM:
+      segment_reduce_kernel<G, V, IGN_OP_SUM><<<grid, SEG_THREADS, 0, st>>>(rowptr, col, src, F, num_dst, out);
+      break;
+    case IGN_OP_MEAN:
+      segment_reduce_kernel<G, V, IGN_OP_MEAN><<<grid, SEG_THREADS, 0, st>>>(rowptr, col, src, F, num_dst, out);
+      break;
+    default:
+      segment_reduce_kernel<G, V, IGN_OP_MAX><<<grid, SEG_THREADS, 0, st>>>(rowptr, col, src, F, num_dst, out);
+      break;
+  }
+  IGN_CHECK_LAUNCH("segment_reduce");
+  return IGN_OK;
+}
+
+constexpr int MAX_FEATS = 8;
+struct FeatList {
+  const float* ptr[MAX_FEATS];
+  int size[MAX_FEATS];
+  int n;
+};
+
+__global__ void init_state_kernel(FeatList f, int64_t n, int hidden, float* __restrict__ state) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * hidden) return;
+  const int64_t row = i / hidden;
+  int c = (int)(i - row * hidden);
+  float v = 0.0f;
+  for (int k = 0; k < f.n; ++k) {
+    if (c < f.size[k]) { v = f.ptr[k][row * f.size[k] + c]; break; }
+    c -= f.size[k];
+    if (k == f.n - 1) v = 0.0f;
+  }
+  state[i] = v;
+}
+
+struct ConcatParts {
+  const float* ptr[4];
+  const int* idx[4];
+  int width[4];
+  int n;
+  int total;
+};
+
+__global__ void gather_concat_kernel(ConcatParts p, int64_t rows, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * p.total) return;
+  const int64_t row = i / p.total;
+  int c = (int)(i - row * p.total);
+  float v = 0.0f;
+  for (int k = 0; k < p.n; ++k) {
+    if (c < p.width[k]) {
+      const int64_t r = p.idx[k] ? (int64_t)p.idx[k][row] : row;
+      v = p.ptr[k][r * p.width[k] + c];
+      break;
+    }
+    c -= p.width[k];
+  }
+  out[i] = v;
+}
+
+__global__ void axpy_kernel(int64_t n, float a, const float* __restrict__ x, float* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+
+}  // namespace
+
+extern "C" int ign_segment_reduce(int op, const int32_t* rowptr, const int32_t* col, const float* src_states,
+                                  int F, int64_t num_dst, float* out, void* stream) {
+  IGN_REQUIRE(op == IGN_OP_SUM || op == IGN_OP_MEAN || op == IGN_OP_MAX, IGN_ERR_INVALID,
+              "IGNNITION: segment_reduce: unknown aggregation %d", op);
+  IGN_REQUIRE(num_dst >= 0, IGN_ERR_INVALID, "IGNNITION: segment_reduce: negative size");
+  IGN_REQUIRE(F > 0 && F % 4 == 0 && F <= 256, IGN_ERR_UNSUPPORTED,
+              "IGNNITION: segment_reduce: message width %d unsupported (multiple of 4, <= 256)", F);
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr && src_states && out, IGN_ERR_INVALID, "IGNNITION: segment_reduce: null pointer");
+  cudaStream_t st = ign_stream(stream);
+  const int q = F / 4;
+  if (q <= 1) return launch_segment<1, 1>(op, rowptr, col, src_states, F, num_dst, out, st);
+  if (q <= 2) return launch_segment<2, 1>(op, rowptr, col, src_states, F, num_dst, out, st);
+  if (q <= 4) return launch_segment<4, 1>(op, rowptr, col, src_states, F, num_dst, out, st);
+  if (q <= 8) return launch_segment<8, 1>(op, rowptr, col, src_states, F, num_dst, out, st);
+  if (q <= 16) return launch_segment<16, 1>(op, rowptr, col, src_states, F, num_dst, out, st);
+  if (q <= 32) return launch_segment<32, 1>(op, rowptr, col, src_states, F, num_dst, out, st);
+  return launch_segment<32, 2>(op, rowptr, col, src_states, F, num_dst, out, st);
+}
+
+extern "C" int ign_init_state(int n_feat, const float* const* feats, const int32_t* feat_size, int64_t n,
+                              int hidden, float* state, void* stream) {
+  IGN_REQUIRE(n_feat >= 0 && n_feat <= MAX_FEATS, IGN_ERR_UNSUPPORTED,
+              "IGNNITION: init_state: at most %d features per entity", MAX_FEATS);
+  IGN_REQUIRE(n >= 0 && hidden > 0, IGN_ERR_INVALID, "IGNNITION: init_state: bad size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(state && (n_feat == 0 || (feats && feat_size)), IGN_ERR_INVALID, "IGNNITION: init_state: null pointer");
+  FeatList f;
+  f.n = n_feat;
+  int total = 0;
+  for (int k = 0; k < MAX_FEATS; ++k) {
+    f.ptr[k] = k < n_feat ? feats[k] : nullptr;
+    f.size[k] = k < n_feat ? feat_size[k] : 0;
+    IGN_REQUIRE(k >= n_feat || (f.ptr[k] && f.size[k] > 0), IGN_ERR_INVALID, "IGNNITION: init_state: bad feature");
+    total += f.size[k];
+  }
+  IGN_REQUIRE(total <= hidden, IGN_ERR_INVALID,
+              "IGNNITION: init_state: features (%d) wider than the hidden state (%d)", total, hidden);
+  init_state_kernel<<<(unsigned)ign_cdiv(n * hidden, 256), 256, 0, ign_stream(stream)>>>(f, n, hidden, state);
+  IGN_CHECK_LAUNCH("init_state");
+  return IGN_OK;
+}
+
+extern "C" int ign_gather_concat(int n_parts, const float* const* parts, const int32_t* const* idx,
+                                 const int32_t* widths, int64_t rows, float* out, void* stream) {
+  IGN_REQUIRE(n_parts >= 1 && n_parts <= 4, IGN_ERR_UNSUPPORTED, "IGNNITION: gather_concat: 1..4 parts");
+  IGN_REQUIRE(rows >= 0 && parts && widths && out, IGN_ERR_INVALID, "IGNNITION: gather_concat: bad argument");
+  if (rows == 0) return IGN_OK;
+  ConcatParts p;
+  p.n = n_parts;
+  p.total = 0;
+  for (int k = 0; k < 4; ++k) {
+    p.ptr[k] = k < n_parts ? parts[k] : nullptr;
+    p.idx[k] = (k < n_parts && idx) ? idx[k] : nullptr;
+    p.width[k] = k < n_parts ? widths[k] : 0;
+    IGN_REQUIRE(k >= n_parts || (p.ptr[k] && p.width[k] > 0), IGN_ERR_INVALID, "IGNNITION: gather_concat: bad part");
+    p.total += p.width[k];
+  }
+  gather_concat_kernel<<<(unsigned)ign_cdiv(rows * p.total, 256), 256, 0, ign_stream(stream)>>>(p, rows, out);
+  IGN_CHECK_LAUNCH("gather_concat");
+  return IGN_OK;
+}
+
+extern "C" int ign_axpy(int64_t n, float a, const float* x, float* y, void* stream) {
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: axpy: negative size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(x && y, IGN_ERR_INVALID, "IGNNITION: axpy: null pointer");
+  axpy_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(n, a, x, y);
+  IGN_CHECK_LAUNCH("axpy");
+  return IGN_OK;
+}

@@ -1,0 +1,447 @@
+"""The B200 message-passing engine: drop-in for the model IGNNITION generates.
+
+``Engine`` mirrors ``ComnetModel`` (reference ``code/utils/generate_model.py:219-695``):
+ * ``Engine(model_description)`` creates the weights ``ComnetModel.__init__`` creates (:235-382),
+   in Keras layout, inside ONE flat fp32 device buffer (a name -> (offset, shape) table maps TF
+   checkpoint variables 1:1),
+ * ``engine(input_dict, training=False)`` is ``ComnetModel.call`` (:384-658) for one sample,
+ * ``engine.forward(graph)`` runs a block-diagonal batch of samples in one pass (what
+   ``model_fn`` does with a Python loop, :712-724).
+
+Host Python only decides WHICH kernels run; every tensor operation on the path is a hand-written
+sm_100a kernel behind the C-ABI (``ops.py`` -> ``libignnition_b200.so``).  There is no CPU path.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .batching import AdjacencySpec, Batch, SequenceSpec, assemble
+from .model_description import FeedForward, MessagePassing, ModelDescription
+
+_ALIGN = 64   # floats: every parameter starts on a 256-byte boundary (float4 / cp.async loads)
+
+
+class DeviceGraph:
+    """A batch resident in HBM: features, CSR per adjacency, step tables, per-entity counts."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None          # the packed upload
+        self.t: Dict[str, torch.Tensor] = {}             # views into buf
+        self.num: Dict[str, int] = {}
+        self.n_samples = 0
+        self.csr: Dict[str, Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]] = {}
+        self.csr_t: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}   # transposed (by source), training
+        self.steps: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.order: Dict[str, torch.Tensor] = {}
+        self.status: Dict[str, torch.Tensor] = {}
+        self.h2d_bytes = 0
+
+
+class _MPPlan:
+    """One message passing (destination + sources) compiled to kernel choices."""
+
+    def __init__(self, mp: MessagePassing, key: str):
+        self.mp = mp
+        self.key = key
+        self.dst = mp.destination_entity
+        self.adjs: List[AdjacencySpec] = []
+        self.kind = ""         # 'agg_gru' | 'seq_gru' | 'agg_ff'
+        self.op = ops.OP_SUM
+        self.seq: Optional[SequenceSpec] = None
+        self.msg_dim = 0
+
+
+class Engine:
+    def __init__(self, model: ModelDescription, device: Optional[torch.device] = None, seed: int = 0,
+                 csr_mode: int = ops.CSR_SORT, sort_by_length: bool = True):
+        self.model = model
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("IGNNITION: ignnition_b200 runs on CUDA devices only (no CPU fallback)")
+        self.csr_mode = csr_mode
+        self.sort_by_length = sort_by_length
+        self.dims = model.get_input_dimensions()
+        self.entities = [e.name for e in model.get_entities()]
+        self.hidden = {e.name: e.hidden_state_dimension for e in model.get_entities()}
+        self.T = model.get_mp_iterations()
+        self.features = [(f.name, e.name, f.size) for e in model.get_entities() for f in e.features]
+        self.adjacencies = [AdjacencySpec(a[0], a[1], a[2], a[3] == "True") for a in model.get_adjecency_info()]
+        self._adj_by_name = {a.name: a for a in self.adjacencies}
+        self._needs_perm = set()
+        self.plans: List[List[_MPPlan]] = []
+        self.sequences: List[SequenceSpec] = []
+        self.param_table: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        self._param_init: Dict[str, str] = {}
+        self._reg: Dict[str, float] = {}
+        self._n_params = 0
+        self._compile()
+        self.weights = torch.zeros(self._n_params, dtype=torch.float32, device=self.device)
+        self.reset_parameters(seed)
+
+    @property
+    def gpu_launches(self) -> int:
+        """Kernels launched by libignnition_b200.so in this process (counted inside the library)."""
+        from . import _lib
+        return int(_lib.load().ign_launch_count())
+
+    # ------------------------------------------------------------------ model compilation
+    def _add_param(self, name: str, shape: Tuple[int, ...], init: str, reg: float = 0.0):
+        if name in self.param_table:
+            return
+        off = (self._n_params + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.param_table[name] = (off, tuple(shape))
+        self._param_init[name] = init
+        if reg:
+            self._reg[name] = reg
+        self._n_params = off + int(np.prod(shape))
+
+    def _add_ff(self, prefix: str, ff: FeedForward, in_dim: int, last_units: Optional[int] = None) -> int:
+        n = len(ff.layers)
+        for j, l in enumerate(ff.layers):
+            if l.type_layer != "Dense":
+                raise RuntimeError("IGNNITION: layer type %s is not supported by the B200 engine "
+                                   "(only Dense)" % l.type_layer)
+            units = last_units if (j == n - 1 and last_units is not None) else l.units
+            if units is None:
+                raise RuntimeError("IGNNITION: Dense layer %s has no units" % l.name)
+            if l.activation not in ops.ACTIVATIONS:
+                raise RuntimeError("IGNNITION: activation %s is not supported" % l.activation)
+            self._add_param("%s/%s/kernel" % (prefix, l.name), (in_dim, units), "glorot", l.kernel_regularizer)
+            if l.use_bias:
+                self._add_param("%s/%s/bias" % (prefix, l.name), (units,), "zeros")
+            in_dim = units
+        return in_dim
+
+    def _compile(self):
+        for si, (stage_name, mps) in enumerate(self.model.get_mp_instances()):
+            stage_plans = []
+            for mi, mp in enumerate(mps):
+                p = _MPPlan(mp, "s%d_m%d" % (si, mi))
+                fd = self.hidden[p.dst]
+                msg_dims = []
+                for src in mp.source_entities:
+                    p.adjs.append(self._adj_by_name[src.adj_vector])
+                    d = self.hidden[src.name]
+                    for k, op in enumerate(src.message_formation):
+                        if op.type != "feed_forward_nn":
+                            continue
+                        self._needs_perm.add(src.adj_vector)
+                        din = 0
+                        for i in op.input:
+                            if i == "hs_source":
+                                din += self.hidden[src.name]
+                            elif i == "hs_dest":
+                                din += fd
+                            elif i == "edge_params":
+                                din += int(src.extra_parameters)
+                            else:
+                                raise RuntimeError(
+                                    "IGNNITION: named message inputs (%s) cannot run in the reference "
+                                    "either (generate_model.py:458 vs :470)" % i)
+                        d = self._add_ff("%s_to_%s_message_creation_%d" % (src.name, p.dst, k), op.model, din)
+                    msg_dims.append(d)
+                if len(set(msg_dims)) != 1:
+                    raise RuntimeError("IGNNITION: all sources of a message passing must send messages of "
+                                       "the same dimension, got %s" % msg_dims)
+                p.msg_dim = msg_dims[0]
+                agg = mp.aggregation.type
+                if agg in ("sum", "mean", "max"):
+                    p.op = {"sum": ops.OP_SUM, "mean": ops.OP_MEAN, "max": ops.OP_MAX}[agg]
+                    p.kind = "agg_gru" if mp.update.type == "recurrent_nn" else "agg_ff"
+                elif agg in ("ordered", "interleave"):
+                    if mp.update.type != "recurrent_nn":
+                        raise RuntimeError("IGNNITION: %s aggregation needs a recurrent update" % agg)
+                    p.kind = "seq_gru"
+                    if len(p.adjs) > 1 or agg == "interleave":
+                        p.seq = SequenceSpec(p.key, p.dst, p.adjs, agg == "interleave")
+                        self.sequences.append(p.seq)
+                else:
+                    raise RuntimeError("IGNNITION: aggregation '%s' is not built yet in the B200 engine "
+                                       "(SURVEY.md section 8f, next rows)" % agg)
+                if mp.update.type == "recurrent_nn":
+                    if mp.update.recurrent_type != "GRU":
+                        raise RuntimeError("IGNNITION: only GRU cells are supported (LSTM cannot run in "
+                                           "the reference: single-tensor state, auxilary_classes.py:764)")
+                    params = mp.update.cell_parameters
+                    if str(params.get("reset_after", True)) not in ("True", "true", "1"):
+                        raise RuntimeError("IGNNITION: GRU reset_after=False is not built")
+                    self._add_param(p.dst + "_update/kernel", (p.msg_dim, 3 * fd), "glorot")
+                    self._add_param(p.dst + "_update/recurrent_kernel", (fd, 3 * fd), "orthogonal")
+                    self._add_param(p.dst + "_update/bias", (2, 3 * fd), "zeros")
+                else:
+                    self._add_ff(p.dst + "_ff_update", mp.update.model, p.msg_dim + fd, last_units=fd)
+                stage_plans.append(p)
+            self.plans.append(stage_plans)
+        self.readout = []
+        dims = dict(self.hidden)
+        for k, op in enumerate(self.model.get_readout_operations()):
+            if op.type in ("predict", "neural_network"):
+                din = sum(int(dims[i]) for i in op.input)
+                dout = self._add_ff("readout_model_%d" % k, op.architecture, din)
+                if op.type == "neural_network":
+                    dims[op.output_name] = dout
+                self.readout.append((k, op))
+                if op.type == "predict":
+                    break
+            else:
+                raise RuntimeError("IGNNITION: readout operation '%s' is not built yet in the B200 engine "
+                                   "(SURVEY.md section 8f, next rows)" % op.type)
+
+    # ------------------------------------------------------------------ weights
+    def param(self, name: str) -> torch.Tensor:
+        off, shape = self.param_table[name]
+        return self.weights[off:off + int(np.prod(shape))].view(*shape)
+
+    def _pview(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        off, shape = self.param_table[name]
+        return buf[off:off + int(np.prod(shape))].view(*shape)
+
+    def reset_parameters(self, seed: int = 0):
+        """Keras default initialisers: glorot_uniform kernels, orthogonal recurrent kernels, zero biases."""
+        rng = np.random.RandomState(seed)
+        host = np.zeros(self._n_params, dtype=np.float32)
+        for name, (off, shape) in self.param_table.items():
+            kind = self._param_init[name]
+            if kind == "glorot":
+                lim = math.sqrt(6.0 / (shape[0] + shape[-1]))
+                v = rng.uniform(-lim, lim, shape)
+            elif kind == "orthogonal":
+                a = rng.normal(size=(shape[1], shape[0]))
+                q, r = np.linalg.qr(a)
+                q = q * np.sign(np.diag(r))
+                v = q.T
+            else:
+                v = np.zeros(shape)
+            host[off:off + v.size] = v.astype(np.float32).reshape(-1)
+        self.weights.copy_(torch.from_numpy(host))
+
+    def set_weights(self, w: Dict[str, np.ndarray]):
+        host = self.weights.cpu().numpy()
+        for name, v in w.items():
+            if name not in self.param_table:
+                raise RuntimeError("IGNNITION: unknown variable " + name)
+            off, shape = self.param_table[name]
+            v = np.asarray(v, dtype=np.float32)
+            if tuple(v.shape) != shape:
+                raise RuntimeError("IGNNITION: variable %s has shape %s, expected %s" % (name, v.shape, shape))
+            host[off:off + v.size] = v.reshape(-1)
+        self.weights.copy_(torch.from_numpy(host))
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        host = self.weights.cpu().numpy()
+        return {n: host[o:o + int(np.prod(s))].reshape(s).copy() for n, (o, s) in self.param_table.items()}
+
+    # ------------------------------------------------------------------ batches
+    def assemble(self, samples: Sequence[dict], labels=None) -> Batch:
+        return assemble(samples, self.entities, self.features, self.adjacencies, self.sequences, labels)
+
+    def upload(self, batch: Batch, pinned=None) -> DeviceGraph:
+        """Host -> device copy of the packed batch (one cudaMemcpyAsync) + tensor views."""
+        if pinned is None:
+            pinned = batch.pack(pin=True)
+        buf, layout = pinned
+        g = DeviceGraph()
+        g.buf = torch.empty(buf.numel(), dtype=torch.uint8, device=self.device)
+        g.buf.copy_(buf, non_blocking=True)
+        g.h2d_bytes = buf.numel()
+        for k, (off, dtype, shape) in layout.items():
+            n = int(np.prod(shape)) if len(shape) else 1
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+            g.t[k] = g.buf[off:off + n * 4].view(tdt).view(*shape) if n else torch.empty(shape, dtype=tdt, device=self.device)
+        g.num = dict(batch.num)
+        g.n_samples = batch.n_samples
+        return g
+
+    def build_graph(self, g: DeviceGraph, training: bool = False, check: bool = False) -> DeviceGraph:
+        """Device adjacency builder: CSR per adjacency, length order, step tables."""
+        for a in self.adjacencies:
+            dst, src, seq = g.t["dst_" + a.name], g.t["src_" + a.name], g.t["seq_" + a.name]
+            rowptr, col, perm, status = ops.csr_build(dst, src, seq, g.num[a.dst], self.csr_mode,
+                                                      want_perm=training or check or a.name in self._needs_perm,
+                                                      want_status=check)
+            g.csr[a.name] = (rowptr, col, perm)
+            if status is not None:
+                g.status[a.name] = status
+        for stage in self.plans:
+            for p in stage:
+                if p.kind != "seq_gru":
+                    continue
+                if p.seq is None:
+                    rowptr, col, _ = g.csr[p.adjs[0].name]
+                    g.steps[p.key] = (rowptr, col)
+                else:
+                    rps = [g.csr[a.name][0] for a in p.adjs]
+                    cols = [g.csr[a.name][1] for a in p.adjs]
+                    total = sum(int(c.numel()) for c in cols)
+                    multi = g.n_samples > 1
+                    g.steps[p.key] = ops.steps_build(
+                        rps, cols, g.t["sample_of_" + p.dst] if multi else None, g.t["pos_off_" + p.key],
+                        g.t["pos_src_" + p.key], g.t["pos_col_" + p.key], g.num[p.dst], total)
+                if self.sort_by_length and g.num[p.dst] > 0:
+                    g.order[p.key] = ops.length_order(g.steps[p.key][0])
+                return g
+
+    def prepare(self, samples_or_batch, labels=None, training: bool = False, check: bool = False) -> DeviceGraph:
+        batch = samples_or_batch if isinstance(samples_or_batch, Batch) else self.assemble(samples_or_batch, labels)
+        return self.build_graph(self.upload(batch), training=training, check=check)
+
+    # ------------------------------------------------------------------ forward
+    def _act(self, name):
+        return ops.ACTIVATIONS[name]
+
+    def _run_ff(self, prefix: str, ff: FeedForward, x: torch.Tensor, saves: Optional[list] = None) -> torch.Tensor:
+        for l in ff.layers:
+            w = self.param("%s/%s/kernel" % (prefix, l.name))
+            b = self.param("%s/%s/bias" % (prefix, l.name)) if l.use_bias else None
+            pre = None
+            if saves is not None:
+                pre = torch.empty(x.shape[0], w.shape[1], dtype=torch.float32, device=self.device)
+            y = ops.dense(x, w, b, self._act(l.activation), pre_act=pre)
+            if saves is not None:
+                saves.append((prefix, l, x, pre))
+            x = y
+        return x
+
+    def _messages(self, p: _MPPlan, k: int, g: DeviceGraph, state: Dict[str, torch.Tensor]):
+        """Per-edge messages of source k in INPUT edge order, or None for direct_assignation."""
+        src = p.mp.source_entities[k]
+        a = p.adjs[k]
+        msgs = None
+        for j, op in enumerate(src.message_formation):
+            if op.type != "feed_forward_nn":
+                continue
+            parts, idx = [], []
+            for i in op.input:
+                if i == "hs_source":
+                    parts.append(state[src.name]); idx.append(g.t["src_" + a.name])
+                elif i == "hs_dest":
+                    parts.append(state[p.dst]); idx.append(g.t["dst_" + a.name])
+                else:
+                    parts.append(g.t["params_" + a.name]); idx.append(None)
+            x = ops.gather_concat(parts, idx, g.t["src_" + a.name].numel())
+            msgs = self._run_ff("%s_to_%s_message_creation_%d" % (src.name, p.dst, j), op.model, x)
+        return msgs
+
+    def _mp_forward(self, p: _MPPlan, g: DeviceGraph, state: Dict[str, torch.Tensor], tape: Optional[list]):
+        dst = p.dst
+        h = state[dst]
+        n_dst = g.num[dst]
+        K = self.param(dst + "_update/kernel") if p.mp.update.type == "recurrent_nn" else None
+        R = self.param(dst + "_update/recurrent_kernel") if K is not None else None
+        B = self.param(dst + "_update/bias") if K is not None else None
+        out = torch.empty_like(h)
+        msgs = [self._messages(p, k, g, state) for k in range(len(p.adjs))]
+
+        if p.kind == "seq_gru":
+            rowptr_s, steps = g.steps[p.key]
+            srcs = []
+            for k, a in enumerate(p.adjs):
+                srcs.append(msgs[k] if msgs[k] is not None else state[a.src])
+            if any(m is not None for m in msgs):
+                raise RuntimeError("IGNNITION: message neural networks feeding an ordered aggregation are "
+                                   "not built yet (step table indexes source rows)")
+            h_seq = None
+            if tape is not None:
+                h_seq = torch.empty(steps.numel(), h.shape[1], dtype=torch.float32, device=self.device)
+            ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq)
+            if tape is not None:
+                tape.append(("seq_gru", p, [state[a.src] for a in p.adjs], h, h_seq))
+            return out
+
+        # aggregating kinds
+        fused = (p.kind == "agg_gru" and p.op == ops.OP_SUM and len(p.adjs) == 1 and msgs[0] is None
+                 and self._fusable(p.msg_dim, h.shape[1]))
+        if fused:
+            rowptr, col, _ = g.csr[p.adjs[0].name]
+            agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
+            ops.agg_gru_cell(rowptr, col, state[p.adjs[0].src], h, K, R, B, out=out, agg_out=agg)
+            if tape is not None:
+                tape.append(("agg_gru", p, state[p.adjs[0].src], h, agg))
+            return out
+        agg = None
+        for k, a in enumerate(p.adjs):
+            rowptr, col, perm = g.csr[a.name]
+            if msgs[k] is None:
+                part = ops.segment_reduce(ops.OP_SUM if len(p.adjs) > 1 else p.op, rowptr, col, state[a.src])
+            else:
+                part = ops.segment_reduce(ops.OP_SUM if len(p.adjs) > 1 else p.op, rowptr, perm, msgs[k])
+            if agg is None:
+                agg = part
+            else:
+                ops.axpy(1.0, part, agg)
+        if len(p.adjs) > 1 and p.op != ops.OP_SUM:
+            raise RuntimeError("IGNNITION: mean/max over several sources is not built")
+        if p.kind == "agg_gru":
+            ops.gru_cell(agg, h, K, R, B, out=out)
+            if tape is not None:
+                tape.append(("agg_gru_unfused", p, [state[a.src] for a in p.adjs], h, agg))
+            return out
+        x = ops.gather_concat([agg, h], [None, None], n_dst)          # FF update, generate_model.py:599
+        ff = p.mp.update.model
+        layers = FeedForward(list(ff.layers))
+        return self._run_ff_last_units(dst + "_ff_update", layers, x)
+
+    def _run_ff_last_units(self, prefix, ff, x):
+        return self._run_ff(prefix, ff, x)
+
+    @staticmethod
+    def _fusable(f_in: int, units: int) -> bool:
+        # weights must stay resident in shared memory next to the tiles (csrc/gru.cu)
+        return f_in in (16, 32) and units in (16, 32)
+
+    def initial_states(self, g: DeviceGraph) -> Dict[str, torch.Tensor]:
+        state = {}
+        for e in self.model.get_entities():
+            feats = [g.t["feat_" + f.name] for f in e.features]
+            sizes = [f.size for f in e.features]
+            state[e.name] = ops.init_state(feats, sizes, g.num[e.name], e.hidden_state_dimension,
+                                           out=torch.empty(g.num[e.name], e.hidden_state_dimension,
+                                                           dtype=torch.float32, device=self.device))
+        return state
+
+    def message_passing(self, g: DeviceGraph, state: Dict[str, torch.Tensor], iterations: Optional[int] = None,
+                        tape: Optional[list] = None) -> Dict[str, torch.Tensor]:
+        T = self.T if iterations is None else iterations
+        for _ in range(T):
+            for stage in self.plans:
+                for p in stage:
+                    state[p.dst] = self._mp_forward(p, g, state, tape)      # written back at once (:602)
+        return state
+
+    def readout_forward(self, state: Dict[str, torch.Tensor], tape: Optional[list] = None) -> torch.Tensor:
+        st = dict(state)
+        result = None
+        for k, op in self.readout:
+            if len(op.input) == 1:
+                x = st[op.input[0]]
+            else:
+                x = ops.gather_concat([st[i] for i in op.input], [None] * len(op.input), st[op.input[0]].shape[0])
+            saves = [] if tape is not None else None
+            y = self._run_ff("readout_model_%d" % k, op.architecture, x, saves)
+            if tape is not None:
+                tape.append(("readout", op, saves))
+            if op.type == "predict":
+                result = y
+                break
+            st[op.output_name] = y
+        return result
+
+    def forward(self, g: DeviceGraph, training: bool = False, return_states: bool = False,
+                tape: Optional[list] = None):
+        state = self.initial_states(g)
+        state = self.message_passing(g, state, tape=tape)
+        pred = self.readout_forward(state, tape=tape)
+        if return_states:
+            return pred, state
+        return pred
+
+    def __call__(self, input: dict, training: bool = False) -> torch.Tensor:
+        """ComnetModel.call for ONE sample given as the reference's tensor dict (host arrays)."""
+        g = self.prepare([input])
+        return self.forward(g, training=training)

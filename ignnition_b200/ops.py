@@ -1,0 +1,234 @@
+"""Thin torch-tensor wrappers over the C-ABI (``include/ignnition_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; every function below
+passes raw device pointers (``tensor.data_ptr()``) and the stream handle to the library and checks
+the status.  No torch op computes anything on this path and nothing falls back to the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+OP_SUM, OP_MEAN, OP_MAX = 0, 1, 2
+CSR_SORT, CSR_RANK = 0, 1
+STEP_SRC_SHIFT = 28
+ACTIVATIONS = {None: 0, "None": 0, "linear": 0, "relu": 1, "selu": 2, "sigmoid": 3, "tanh": 4,
+               "elu": 5, "softplus": 6, "leaky_relu": 7}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("IGNNITION: %s must be a CUDA tensor (no CPU path exists)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("IGNNITION: %s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("IGNNITION: %s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _f(t, name="tensor"):
+    return _ptr(t, torch.float32, name)
+
+
+def _i(t, name="tensor"):
+    return _ptr(t, torch.int32, name)
+
+
+def _ptr_array(ts: Sequence[Optional[torch.Tensor]], dtype):
+    arr = (C.c_void_p * max(len(ts), 1))()
+    for k, t in enumerate(ts):
+        arr[k] = _ptr(t, dtype, "tensor list element")
+    return arr
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------- adjacency
+def csr_build(dst: torch.Tensor, src: torch.Tensor, seq: Optional[torch.Tensor], num_dst: int,
+              mode: int = CSR_SORT, want_perm: bool = False, want_status: bool = False):
+    """(rowptr[num_dst+1], col[E], perm[E]|None, status[2]|None) -- see ign_csr_build."""
+    lib = _lib.load()
+    E = dst.numel()
+    dev = dst.device
+    rowptr = torch.empty(num_dst + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev) if want_perm else None
+    status = torch.empty(2, dtype=torch.int32, device=dev) if want_status else None
+    nbytes = lib.ign_csr_build_ws_bytes(E, num_dst)
+    ws = _workspace(nbytes, dev)
+    _lib.check(lib.ign_csr_build(_i(dst, "dst"), _i(src, "src"), _i(seq, "seq"), E, num_dst, mode,
+                                 _i(rowptr), _i(col), _i(perm), _i(status), ws.data_ptr(), ws.numel(),
+                                 _stream()), "csr_build")
+    return rowptr, col, perm, status
+
+
+def length_order(rowptr: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    n = rowptr.numel() - 1
+    order = torch.empty(n, dtype=torch.int32, device=rowptr.device)
+    ws = _workspace(lib.ign_length_order_ws_bytes(n), rowptr.device)
+    _lib.check(lib.ign_length_order(_i(rowptr), n, _i(order), ws.data_ptr(), ws.numel(), _stream()),
+               "length_order")
+    return order
+
+
+def steps_build(rowptrs: List[torch.Tensor], cols: List[torch.Tensor], dst_sample: Optional[torch.Tensor],
+                pos_off: torch.Tensor, pos_src: torch.Tensor, pos_col: torch.Tensor, num_dst: int,
+                total_steps: int):
+    """Step table of a multi-source ordered / interleave aggregation (ign_steps_build).
+    ``total_steps`` = sum of all sources' edge counts (known on the host)."""
+    lib = _lib.load()
+    dev = rowptrs[0].device
+    steps_rowptr = torch.empty(num_dst + 1, dtype=torch.int32, device=dev)
+    steps = torch.empty(max(total_steps, 1), dtype=torch.int32, device=dev)
+    ws = _workspace(lib.ign_steps_build_ws_bytes(num_dst), dev)
+    rp = _ptr_array(rowptrs, torch.int32)
+    cp = _ptr_array(cols, torch.int32)
+    _lib.check(lib.ign_steps_build(len(rowptrs), rp, cp, _i(dst_sample), _i(pos_off), _i(pos_src),
+                                   _i(pos_col), num_dst, _i(steps_rowptr), _i(steps), ws.data_ptr(),
+                                   ws.numel(), _stream()), "steps_build")
+    return steps_rowptr, steps
+
+
+# ------------------------------------------------------------------------------- forward
+def init_state(feats: List[torch.Tensor], sizes: List[int], n: int, hidden: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    dev = feats[0].device if feats else (out.device if out is not None else torch.device("cuda"))
+    if out is None:
+        out = torch.empty(n, hidden, dtype=torch.float32, device=dev)
+    fp = _ptr_array(feats, torch.float32)
+    sz = (C.c_int32 * max(len(sizes), 1))(*sizes)
+    _lib.check(lib.ign_init_state(len(feats), fp, sz, n, hidden, _f(out), _stream()), "init_state")
+    return out
+
+
+def segment_reduce(op: int, rowptr, col, src_states, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    n = rowptr.numel() - 1
+    F = src_states.shape[1]
+    if out is None:
+        out = torch.empty(n, F, dtype=torch.float32, device=src_states.device)
+    _lib.check(lib.ign_segment_reduce(op, _i(rowptr), _i(col), _f(src_states), F, n, _f(out), _stream()),
+               "segment_reduce")
+    return out
+
+
+def gru_cell(x, h, kernel, rkernel, bias, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    n, units = h.shape
+    if out is None:
+        out = torch.empty_like(h)
+    _lib.check(lib.ign_gru_cell(_f(x), _f(h), n, x.shape[1], units, _f(kernel), _f(rkernel), _f(bias),
+                                _f(out), _stream()), "gru_cell")
+    return out
+
+
+def agg_gru_cell(rowptr, col, src_states, h_dst, kernel, rkernel, bias, out=None, agg_out=None):
+    lib = _lib.load()
+    n, units = h_dst.shape
+    if out is None:
+        out = torch.empty_like(h_dst)
+    _lib.check(lib.ign_agg_gru_cell(_i(rowptr), _i(col), _f(src_states), src_states.shape[1], _f(h_dst), n,
+                                    units, _f(kernel), _f(rkernel), _f(bias), _f(out), _f(agg_out),
+                                    _stream()), "agg_gru_cell")
+    return out
+
+
+def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rkernel, bias, out=None,
+            h_seq=None):
+    lib = _lib.load()
+    n, units = h0.shape
+    if out is None:
+        out = torch.empty_like(h0)
+    sp = _ptr_array(srcs, torch.float32)
+    _lib.check(lib.ign_gru_seq(_i(steps_rowptr), _i(steps), _i(order), len(srcs), sp, srcs[0].shape[1],
+                               _f(h0), n, units, _f(kernel), _f(rkernel), _f(bias), _f(out), _f(h_seq),
+                               _stream()), "gru_seq")
+    return out
+
+
+def dense(x, w, bias, act: int, out=None, pre_act=None):
+    lib = _lib.load()
+    m, k = x.shape
+    n = w.shape[1]
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    _lib.check(lib.ign_dense(_f(x), m, k, _f(w), _f(bias), n, act, _f(out), _f(pre_act), _stream()), "dense")
+    return out
+
+
+def gather_concat(parts: List[torch.Tensor], idx: List[Optional[torch.Tensor]], rows: int, out=None):
+    lib = _lib.load()
+    widths = [p.shape[1] for p in parts]
+    if out is None:
+        out = torch.empty(rows, sum(widths), dtype=torch.float32, device=parts[0].device)
+    pp = _ptr_array(parts, torch.float32)
+    ip = _ptr_array(idx, torch.int32)
+    wd = (C.c_int32 * len(widths))(*widths)
+    _lib.check(lib.ign_gather_concat(len(parts), pp, ip, wd, rows, _f(out), _stream()), "gather_concat")
+    return out
+
+
+# ------------------------------------------------------------------------------- train step
+def mse_loss(pred, label, grad_scale: float, d_pred, sse):
+    lib = _lib.load()
+    _lib.check(lib.ign_mse_loss(_f(pred), _f(label), pred.numel(), grad_scale, _f(d_pred),
+                                _ptr(sse, torch.float64, "sse"), _stream()), "mse_loss")
+
+
+def dense_bwd(x, w, act: int, pre_act, dy, dx, dw, db):
+    lib = _lib.load()
+    m, k = x.shape
+    n = w.shape[1]
+    _lib.check(lib.ign_dense_bwd(_f(x), m, k, _f(w), n, act, _f(pre_act), _f(dy), _f(dx), _f(dw), _f(db),
+                                 _stream()), "dense_bwd")
+
+
+def gru_cell_bwd(x, h, kernel, rkernel, bias, d_out, dx, dh, dk, drk, db):
+    lib = _lib.load()
+    n, units = h.shape
+    _lib.check(lib.ign_gru_cell_bwd(_f(x), _f(h), n, x.shape[1], units, _f(kernel), _f(rkernel), _f(bias),
+                                    _f(d_out), _f(dx), _f(dh), _f(dk), _f(drk), _f(db), _stream()),
+               "gru_cell_bwd")
+
+
+def gru_seq_bwd(steps_rowptr, steps, order, srcs, h0, h_seq, kernel, rkernel, bias, d_out, d_steps, dh0,
+                dk, drk, db):
+    lib = _lib.load()
+    n, units = h0.shape
+    sp = _ptr_array(srcs, torch.float32)
+    _lib.check(lib.ign_gru_seq_bwd(_i(steps_rowptr), _i(steps), _i(order), len(srcs), sp, srcs[0].shape[1],
+                                   _f(h0), _f(h_seq), n, units, _f(kernel), _f(rkernel), _f(bias),
+                                   _f(d_out), _f(d_steps), _f(dh0), _f(dk), _f(drk), _f(db), _stream()),
+               "gru_seq_bwd")
+
+
+def l2_reg(w, lam: float, dw, reg):
+    lib = _lib.load()
+    _lib.check(lib.ign_l2_reg(_f(w), w.numel(), lam, _f(dw), _ptr(reg, torch.float64, "reg"), _stream()),
+               "l2_reg")
+
+
+def adam_step(w, g, m, v, lr: float, beta1: float, beta2: float, eps: float, step: int):
+    lib = _lib.load()
+    _lib.check(lib.ign_adam_step(_f(w), _f(g), _f(m), _f(v), w.numel(), lr, beta1, beta2, eps, step,
+                                 _stream()), "adam_step")
+
+
+def axpy(a: float, x, y):
+    lib = _lib.load()
+    _lib.check(lib.ign_axpy(x.numel(), a, _f(x), _f(y), _stream()), "axpy")

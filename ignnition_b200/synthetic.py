@@ -152,15 +152,3 @@ def write_dataset(directory: str, samples: Sequence[dict], per_file: int = 25) -
             tar.addfile(info, io.BytesIO(payload))
         out.append(path)
     return out
-
-
-def tiled_batch(base: dict, n_samples: int, feature_fns: Dict[str, callable], seed: int = 0) -> dict:
-    """Block-diagonal batch of ``n_samples`` copies of one sample's tensor dict, new features each.
-
-    ``base`` is the tensor dict of ONE sample (``generator.sample_to_tensors``); index arrays are
-    replicated with per-sample entity offsets in vectorised numpy (what ``batching.assemble`` does
-    sample by sample), features are drawn by ``feature_fns[name](rng, count)``.
-    Returns a dict in ``batching.Batch`` input form (see ``batching.assemble``).
-    """
-    from .batching import assemble_tiled
-    return assemble_tiled(base, n_samples, feature_fns, seed)

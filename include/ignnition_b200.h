@@ -1,0 +1,204 @@
+/*
+ * ignnition_b200 -- C-ABI of the B200-native message-passing engine.
+ *
+ * The reference (zhangbiqiong/ignnition) has no FFI: its generated model calls TensorFlow ops from
+ * Python.  Each entry point below replaces the TF op sequence named in its comment (reference
+ * file:line, relative to the reference root) and is what a ctypes binding in the reference's
+ * ComnetModel.call would bind.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.
+ *  - every pointer is a DEVICE pointer owned by the caller unless the comment says "host".
+ *    The library never allocates or frees device memory: scratch is passed in, its size is
+ *    queried with the matching *_ws_bytes function.
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does no host
+ *    synchronisation and no allocation, so it can be captured in a CUDA graph.
+ *  - return value: 0 = OK, <0 = invalid argument (checked on the host before any launch),
+ *    >0 = cudaError_t of the failed launch.  ign_last_error() returns the thread-local message.
+ *  - states / messages / weights are fp32 row-major; indices are int32; weights are in Keras
+ *    layout: Dense kernel[in,out], bias[out]; GRUCell (v2, reset_after=True) kernel[in,3u],
+ *    recurrent_kernel[u,3u], bias[2,3u], gate order z|r|h.
+ */
+#ifndef IGNNITION_B200_H
+#define IGNNITION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGN_OK 0
+#define IGN_ERR_INVALID (-1)
+#define IGN_ERR_UNSUPPORTED (-2)
+#define IGN_ERR_WORKSPACE (-3)
+
+/* aggregation operators of ign_segment_reduce */
+#define IGN_OP_SUM 0
+#define IGN_OP_MEAN 1
+#define IGN_OP_MAX 2
+
+/* activations (tf.keras.activations names, auxilary_classes.py:839-865) */
+#define IGN_ACT_LINEAR 0
+#define IGN_ACT_RELU 1
+#define IGN_ACT_SELU 2
+#define IGN_ACT_SIGMOID 3
+#define IGN_ACT_TANH 4
+#define IGN_ACT_ELU 5
+#define IGN_ACT_SOFTPLUS 6
+#define IGN_ACT_LEAKY_RELU 7
+
+/* step-table entries of ign_gru_seq: (source id << 28) | row, or IGN_STEP_ZERO for a zero message */
+#define IGN_STEP_SRC_SHIFT 28
+#define IGN_STEP_ROW_MASK 0x0FFFFFFF
+#define IGN_STEP_ZERO (-1)
+#define IGN_MAX_SOURCES 4
+
+int ign_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int ign_last_error(char* buf, size_t n);
+/* number of CUDA kernels this library has launched in the process so far (for bench.py's gpu_launches) */
+int64_t ign_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Adjacency -> CSR by destination.
+ * Replaces the per-edge host loop + padded scatter of the reference:
+ *   generator_std_to_framework.py:134-185 (src_idx/dst_idx/seq), generate_model.py:479-490
+ *   (lens = unsorted_segment_sum(1, dst), scatter_nd into [num_dst, max_len, F]).
+ * Output: rowptr[num_dst+1] (exclusive scan of in-degrees), col[E] = src of the edge at slot
+ * rowptr[d]+seq, perm[E] = position of that edge in the input arrays (nullable).
+ * seq == NULL : stable LSD radix sort of the edges by dst (seq is then the rank in input order).
+ * seq != NULL and mode == IGN_CSR_RANK: histogram + scan + placement at rowptr[dst]+seq.
+ * seq != NULL and mode == IGN_CSR_SORT: radix sort as above (edges of one destination must appear
+ *   in ascending seq order, which the reference generator guarantees, :153).
+ * status (nullable, int32[2] device): [0] = number of slots whose seq disagrees with its slot
+ *   (0 for valid input), [1] = max in-degree.
+ */
+#define IGN_CSR_SORT 0
+#define IGN_CSR_RANK 1
+size_t ign_csr_build_ws_bytes(int64_t n_edges, int64_t num_dst);
+int ign_csr_build(const int32_t* dst, const int32_t* src, const int32_t* seq, int64_t n_edges,
+                  int64_t num_dst, int mode, int32_t* rowptr, int32_t* col, int32_t* perm,
+                  int32_t* status, void* ws, size_t ws_bytes, void* stream);
+
+/* Destinations ordered by descending in-degree (stable), so that one CTA of ign_gru_seq walks
+ * sequences of equal length (replaces the dense right-padding + tf.sequence_mask of
+ * generate_model.py:484-490 / auxilary_classes.py:785-790).  order[num_dst]. */
+size_t ign_length_order_ws_bytes(int64_t num_dst);
+int ign_length_order(const int32_t* rowptr, int64_t num_dst, int32_t* order, void* ws,
+                     size_t ws_bytes, void* stream);
+
+/* Step table for multi-source ordered / interleave aggregation (generate_model.py:507-543,
+ * auxilary_classes.py:421-440).  For destination d of sample s = dst_sample[d], position t of the
+ * reference's padded sequence is source pos_src[pos_off[s]+t], column pos_col[pos_off[s]+t];
+ * it holds a real message iff column < in-degree of d in that source's CSR, else zeros.
+ * final_len(d) = sum of in-degrees.  Outputs: steps_rowptr[num_dst+1], steps[sum final_len]
+ * (entries as IGN_STEP_*).  Call with steps == NULL to compute only steps_rowptr. */
+size_t ign_steps_build_ws_bytes(int64_t num_dst);
+int ign_steps_build(int n_src, const int32_t* const* rowptrs /*host array of device ptrs*/,
+                    const int32_t* const* cols /*host array of device ptrs*/,
+                    const int32_t* dst_sample, const int32_t* pos_off, const int32_t* pos_src,
+                    const int32_t* pos_col, int64_t num_dst, int32_t* steps_rowptr, int32_t* steps,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Entity.calculate_hs (auxilary_classes.py:128-160): state[n, hidden] = [features | zeros].
+ * feats: host array of n_feat device pointers, each [n, feat_size[i]] fp32. */
+int ign_init_state(int n_feat, const float* const* feats, const int32_t* feat_size /*host*/,
+                   int64_t n, int hidden, float* state, void* stream);
+
+/* gather + aggregation: out[d] = op_{e in [rowptr[d], rowptr[d+1])} src_states[col[e]]  in slot order.
+ * Replaces tf.gather (generate_model.py:432) + scatter_nd (:490) + reduce_sum(axis=1)
+ * (auxilary_classes.py:254-262).  col == NULL means identity (messages already in slot order).
+ * mean / max are north-star extensions (empty destination -> 0). F % 4 == 0, F <= 256. */
+int ign_segment_reduce(int op, const int32_t* rowptr, const int32_t* col, const float* src_states,
+                       int F, int64_t num_dst, float* out, void* stream);
+
+/* One GRU step for every destination, x = aggregated messages, h = old state:
+ * Recurrent_Cell.perform_unsorted_update (auxilary_classes.py:752-765).  out may alias h. */
+int ign_gru_cell(const float* x, const float* h, int64_t n, int f_in, int units,
+                 const float* kernel, const float* recurrent_kernel, const float* bias,
+                 float* out, void* stream);
+
+/* Fused gather + sum aggregation + GRU update (RouteNet stage 2, Q-size step 2, config 5):
+ * generate_model.py:432,490 + Sum_aggr (auxilary_classes.py:254-262) + perform_unsorted_update
+ * (:752-765).  The aggregated message never leaves the SM.  agg_out (nullable) receives the
+ * aggregated messages [num_dst, f_in] (saved for the backward pass).  out must not alias h_dst
+ * when src_states == h_dst. */
+int ign_agg_gru_cell(const int32_t* rowptr, const int32_t* col, const float* src_states, int f_in,
+                     const float* h_dst, int64_t num_dst, int units, const float* kernel,
+                     const float* recurrent_kernel, const float* bias, float* out, float* agg_out,
+                     void* stream);
+
+/* Ordered / interleave aggregation + recurrent update: for every destination d,
+ *   h <- h0[d]; for t in 0..len(d)-1: h <- GRU(x = message(steps[steps_rowptr[d]+t]), h); out[d] = h
+ * Replaces keras RNN(GRUCell)(padded, initial_state, mask=sequence_mask(len)) + gather_nd
+ * (auxilary_classes.py:767-796) and Interleave_aggr (:421-440).  A destination with len 0 keeps
+ * its state.  srcs: host array of n_src device pointers [*, f_in].  order (nullable) = output of
+ * ign_length_order.  h_seq (nullable): [sum len, units] hidden state after every step (saved for
+ * the backward pass).  out must not alias h0 unless no source aliases h0. */
+int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* order, int n_src,
+                const float* const* srcs, int f_in, const float* h0, int64_t num_dst, int units,
+                const float* kernel, const float* recurrent_kernel, const float* bias, float* out,
+                float* h_seq, void* stream);
+
+/* Dense layer y = act(x W + b): Feed_forward_Layer (auxilary_classes.py:800-866), used by the
+ * message MLP (generate_model.py:448-473), the FF update (:594-600) and the readout (:607-629).
+ * bias nullable.  pre_act (nullable) receives x W + b (saved for the backward pass). */
+int ign_dense(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+              float* y, float* pre_act, void* stream);
+
+/* Row-wise concatenation of up to 4 blocks, each optionally gathered by an index:
+ * tf.concat([hs_source, hs_dest, edge_params], axis=1) after tf.gather (generate_model.py:432-465)
+ * and tf.concat([agg, old_state], 1) of the FF update (:599).  idx[i] nullable = identity. */
+int ign_gather_concat(int n_parts, const float* const* parts, const int32_t* const* idx,
+                      const int32_t* widths /*host*/, int64_t rows, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Train step (model_fn, generate_model.py:697-830): backward twins + loss + Adam.
+ */
+/* loss = mean((y - pred)^2) over all n predictions (MeanSquaredError, :745-751).
+ * Writes d_pred = 2 (pred - y) * grad_scale  (grad_scale = 1/global_n for data-parallel runs) and
+ * accumulates sum of squared errors into sse[0] (fp64, caller zeroes it). */
+int ign_mse_loss(const float* pred, const float* label, int64_t n, float grad_scale, float* d_pred,
+                 double* sse, void* stream);
+
+/* dx = (dy * act'(pre)) W^T ; dW += x^T (dy*act') ; db += colsum(dy*act').
+ * dx nullable.  dy is overwritten with dy*act'(pre).  dW/db are ACCUMULATED (caller zeroes). */
+int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, int n, int act,
+                  const float* pre_act, float* dy, float* dx, float* dw, float* db, void* stream);
+
+/* backward of ign_gru_cell: given d_out [n,units] computes dx [n,f_in], dh [n,units] (both nullable)
+ * and ACCUMULATES d_kernel, d_recurrent_kernel, d_bias. */
+int ign_gru_cell_bwd(const float* x, const float* h, int64_t n, int f_in, int units,
+                     const float* kernel, const float* recurrent_kernel, const float* bias,
+                     const float* d_out, float* dx, float* dh, float* d_kernel,
+                     float* d_recurrent_kernel, float* d_bias, void* stream);
+
+/* backward of ign_gru_seq (BPTT over every destination's sequence).  h_seq is the saved output of
+ * the forward call.  d_steps [sum len, f_in] receives the gradient w.r.t. each step's message
+ * (the caller reduces it per source row with ign_segment_reduce over the transposed CSR);
+ * dh0 [num_dst, units] the gradient w.r.t. the initial state.  Weight gradients are ACCUMULATED. */
+int ign_gru_seq_bwd(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* order,
+                    int n_src, const float* const* srcs, int f_in, const float* h0,
+                    const float* h_seq, int64_t num_dst, int units, const float* kernel,
+                    const float* recurrent_kernel, const float* bias, const float* d_out,
+                    float* d_steps, float* dh0, float* d_kernel, float* d_recurrent_kernel,
+                    float* d_bias, void* stream);
+
+/* l2 regulariser: reg[0] += lambda * sum(w^2) (fp64), dw += 2 lambda w (auxilary_classes.py:834). */
+int ign_l2_reg(const float* w, int64_t n, float lambda, float* dw, double* reg, void* stream);
+
+/* Keras Adam step on a flat parameter buffer (generate_model.py:796-818) [TF-2.1 semantics]:
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v moments; w -= lr_t*m/(sqrt(v)+eps).  step is 1-based. */
+int ign_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, void* stream);
+
+/* y[i] += x[idx[i]] row-wise helper and elementwise utilities used by the backward pass */
+int ign_axpy(int64_t n, float a, const float* x, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGNNITION_B200_H */

@@ -384,7 +384,7 @@ class Oracle:
             lens = np.bincount(dst_idx, minlength=num_dst).astype(np.int64)     # :481
             max_len = int(seq.max()) + 1 if len(seq) else 0                       # :484
             s = np.zeros((num_dst, max_len, final_messages.shape[1]), dtype=dt)   # scatter_nd :490
-            np.add.at(s, (dst_idx, seq), final_messages)
+            s[dst_idx, seq] = final_messages          # (dst, seq) pairs are unique: no duplicate-sum
             if agg["type"] == "concat":                                           # :496-505
                 if first:
                     src_input, final_len, first = s, lens.copy(), False
@@ -426,7 +426,7 @@ class Oracle:
         elif t == "interleave":                                                   # auxilary_classes.py:421-440
             tr = np.transpose(src_input, (1, 0, 2))
             out = np.zeros_like(tr)
-            np.add.at(out, indices.reshape(-1), tr)
+            out[indices.reshape(-1)] = tr             # scatter_nd with unique indices
             src_input = np.transpose(out, (1, 0, 2))
         elif t == "attention":                                                    # auxilary_classes.py:278-344
             k1, k2, ak = (w[dst + "_attention/kernel1"], w[dst + "_attention/kernel2"],

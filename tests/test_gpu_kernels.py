@@ -1,0 +1,293 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (ops.py -> libignnition_b200.so) against the
+CPU oracle on the same seeded inputs.  Integer outputs are bit-exact; float outputs are compared
+with the north-star tolerance (1e-5 relative, fp32)."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ignnition_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5          # north-star tolerance (BASELINE.json): 1e-5 relative, fp32
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def rel_err(got, want):
+    want = np.asarray(want, dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def random_edges(rng, n_dst, n_src, max_len, shuffle=True, empty_frac=0.2):
+    lens = rng.randint(0, max_len + 1, n_dst)
+    lens[rng.rand(n_dst) < empty_frac] = 0
+    dst = np.repeat(np.arange(n_dst), lens)
+    seq = np.concatenate([np.arange(l) for l in lens]) if lens.sum() else np.zeros(0, np.int64)
+    src = rng.randint(0, n_src, len(dst))
+    if shuffle:      # groups in arbitrary order, seq ascending inside each destination (reference :145-153)
+        order = np.argsort(rng.permutation(n_dst)[dst], kind="stable")
+        dst, seq, src = dst[order], seq[order], src[order]
+    return src, dst, seq
+
+
+# ------------------------------------------------------------------ CSR builder (bit-exact)
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n_dst,n_src,max_len", [(1, 1, 1), (7, 5, 3), (1000, 300, 9), (70000, 5000, 40), (5, 3, 0)])
+def test_csr_build_bit_exact(mode, n_dst, n_src, max_len):
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(n_dst + max_len)
+    src, dst, seq = random_edges(rng, n_dst, n_src, max_len)
+    rowptr, col, perm, status = ops.csr_build(dev(dst, torch.int32), dev(src, torch.int32), dev(seq, torch.int32),
+                                              n_dst, mode, want_perm=True, want_status=True)
+    r, c, p = orc.csr_from_edges(src, dst, seq, n_dst)
+    assert np.array_equal(rowptr.cpu().numpy(), r)
+    assert np.array_equal(col.cpu().numpy(), c)
+    assert np.array_equal(perm.cpu().numpy(), p)
+    st = status.cpu().numpy()
+    assert st[0] == 0 and st[1] == (np.diff(r).max() if n_dst else 0)
+
+
+def test_csr_build_sort_without_seq_and_large():
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(3)
+    n_dst, E = 3_000_000, 5_000_000          # 22-bit keys: 3 radix passes, multi-level scan
+    dst = rng.randint(0, n_dst, E)
+    src = rng.randint(0, 1 << 20, E)
+    rowptr, col, perm, _ = ops.csr_build(dev(dst, torch.int32), dev(src, torch.int32), None, n_dst, 0, want_perm=True)
+    r, c, p = orc.stable_sort_csr(src, dst, n_dst)
+    assert np.array_equal(rowptr.cpu().numpy(), r)
+    assert np.array_equal(perm.cpu().numpy(), p)
+    assert np.array_equal(col.cpu().numpy(), c)
+
+
+def test_csr_build_golden_and_status_flags_bad_seq(golden):
+    from ignnition_b200 import ops
+    g = golden("routenet_geant2")
+    ref = g["reference_tensors"][0]
+    for adj, s_e, d_e, _ in g["reference_meta"]["adjacency_info"]:
+        src, dst, seq = (np.array(ref["src_" + adj]), np.array(ref["dst_" + adj]),
+                         np.array(ref["seq_%s_%s" % (s_e, d_e)]))
+        n = ref["num_" + d_e]
+        for mode in (0, 1):
+            rowptr, col, perm, st = ops.csr_build(dev(dst, torch.int32), dev(src, torch.int32),
+                                                  dev(seq, torch.int32), n, mode, True, True)
+            r, c, p = orc.csr_from_edges(src, dst, seq, n)
+            assert np.array_equal(rowptr.cpu().numpy(), r) and np.array_equal(col.cpu().numpy(), c)
+            assert np.array_equal(perm.cpu().numpy(), p) and st.cpu().numpy()[0] == 0
+        bad = seq.copy()
+        bad[0], bad[1] = bad[1], bad[0]
+        if bad[0] != seq[0]:
+            _, _, _, st = ops.csr_build(dev(dst, torch.int32), dev(src, torch.int32), dev(bad, torch.int32), n, 0,
+                                        True, True)
+            assert st.cpu().numpy()[0] > 0
+
+
+def test_length_order_is_stable_descending():
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(5)
+    lens = rng.randint(0, 9, 100_000)
+    rowptr = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=rowptr[1:])
+    order = ops.length_order(dev(rowptr, torch.int32)).cpu().numpy()
+    want = np.argsort(-lens, kind="stable")
+    assert np.array_equal(order, want)
+
+
+# ------------------------------------------------------------------ gather + segmented aggregation
+@pytest.mark.parametrize("F", [4, 8, 32, 64, 100, 256])
+@pytest.mark.parametrize("op", [0, 1, 2])
+def test_segment_reduce(F, op):
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(F + op)
+    n_dst, n_src = 3001, 777
+    src, dst, seq = random_edges(rng, n_dst, n_src, 37)
+    states = rng.randn(n_src, F).astype(np.float32)
+    r, c, _ = orc.csr_from_edges(src, dst, seq, n_dst)
+    got = ops.segment_reduce(op, dev(r, torch.int32), dev(c, torch.int32), dev(states)).cpu().numpy()
+    want = np.zeros((n_dst, F), np.float64)
+    for d in range(n_dst):
+        rows = states[c[r[d]:r[d + 1]]].astype(np.float64)
+        if len(rows):
+            want[d] = rows.sum(0) if op == 0 else rows.mean(0) if op == 1 else rows.max(0)
+    if op == 2:
+        assert np.array_equal(got, want.astype(np.float32))          # max is exact
+    else:
+        assert rel_err(got, want) < RTOL
+    if op == 0:   # slot-order single-accumulator sum == sequential fp32 sum, bit for bit
+        seqsum = np.zeros((n_dst, F), np.float32)
+        for d in range(n_dst):
+            acc = np.zeros(F, np.float32)
+            for e in range(r[d], r[d + 1]):
+                acc = acc + states[c[e]]
+            seqsum[d] = acc
+        assert np.array_equal(got, seqsum)
+
+
+def test_segment_reduce_identity_col_and_errors():
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(9)
+    msgs = rng.randn(50, 32).astype(np.float32)
+    rowptr = np.array([0, 10, 10, 50], np.int32)
+    got = ops.segment_reduce(0, dev(rowptr), None, dev(msgs)).cpu().numpy()
+    assert rel_err(got[0], msgs[:10].sum(0)) < RTOL and np.all(got[1] == 0)
+    with pytest.raises(RuntimeError, match="IGNNITION"):
+        ops.segment_reduce(0, dev(rowptr), None, dev(rng.randn(50, 30).astype(np.float32)))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.segment_reduce(0, torch.from_numpy(rowptr), None, dev(msgs))
+
+
+# ------------------------------------------------------------------ GRU kernels
+def gru_weights(rng, fi, u):
+    lim = np.sqrt(6.0 / (fi + 3 * u))
+    return (rng.uniform(-lim, lim, (fi, 3 * u)).astype(np.float32),
+            rng.uniform(-lim, lim, (u, 3 * u)).astype(np.float32),
+            rng.uniform(-0.1, 0.1, (2, 3 * u)).astype(np.float32))
+
+
+@pytest.mark.parametrize("fi,u", [(32, 32), (64, 64), (16, 16), (16, 32), (64, 32), (32, 64), (32, 16)])
+@pytest.mark.parametrize("n", [1, 129, 5000])
+def test_gru_cell(fi, u, n):
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(fi + u + n)
+    K, R, b = gru_weights(rng, fi, u)
+    x = rng.randn(n, fi).astype(np.float32)
+    h = rng.randn(n, u).astype(np.float32)
+    got = ops.gru_cell(dev(x), dev(h), dev(K), dev(R), dev(b)).cpu().numpy()
+    want = orc.gru_cell(x.astype(np.float64), h.astype(np.float64), K.astype(np.float64), R.astype(np.float64),
+                        b.astype(np.float64))
+    assert rel_err(got, want) < RTOL
+
+
+def test_gru_unsupported_width_fails_loudly():
+    from ignnition_b200 import ops
+    z = torch.zeros(4, 48, device="cuda")
+    w = torch.zeros(48, 144, device="cuda")
+    b = torch.zeros(2, 144, device="cuda")
+    with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
+        ops.gru_cell(z, z, w, w, b)
+
+
+@pytest.mark.parametrize("fi,u", [(32, 32), (64, 64), (16, 32)])
+def test_agg_gru_cell(fi, u):
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(fi * u)
+    n_dst, n_src = 2500, 900
+    src, dst, seq = random_edges(rng, n_dst, n_src, 45)
+    states = (rng.randn(n_src, fi) * 0.3).astype(np.float32)
+    h = rng.randn(n_dst, u).astype(np.float32)
+    K, R, b = gru_weights(rng, fi, u)
+    r, c, _ = orc.csr_from_edges(src, dst, seq, n_dst)
+    agg_out = torch.empty(n_dst, fi, device="cuda")
+    got = ops.agg_gru_cell(dev(r, torch.int32), dev(c, torch.int32), dev(states), dev(h), dev(K), dev(R), dev(b),
+                           agg_out=agg_out).cpu().numpy()
+    agg = np.zeros((n_dst, fi), np.float64)
+    np.add.at(agg, dst, states[src].astype(np.float64))
+    want = orc.gru_cell(agg, h.astype(np.float64), K.astype(np.float64), R.astype(np.float64), b.astype(np.float64))
+    assert rel_err(agg_out.cpu().numpy(), agg) < RTOL
+    assert rel_err(got, want) < RTOL
+
+
+@pytest.mark.parametrize("fi,u", [(32, 32), (64, 64)])
+@pytest.mark.parametrize("use_order", [False, True])
+def test_gru_seq_vs_masked_rnn(fi, u, use_order):
+    """ordered aggregation: CSR walk == keras RNN over the dense right-padded tensor + mask."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(fi + 7 * use_order)
+    n_dst, n_src, max_len = 1500, 400, 7
+    lens = rng.randint(0, max_len + 1, n_dst)      # includes empty destinations (state carried)
+    dst = np.repeat(np.arange(n_dst), lens)
+    seq = np.concatenate([np.arange(l) for l in lens])
+    src = rng.randint(0, n_src, len(dst))
+    states = (rng.randn(n_src, fi) * 0.5).astype(np.float32)
+    h0 = rng.randn(n_dst, u).astype(np.float32)
+    K, R, b = gru_weights(rng, fi, u)
+    r, c, _ = orc.csr_from_edges(src, dst, seq, n_dst)
+    rp, cc = dev(r, torch.int32), dev(c, torch.int32)
+    order = ops.length_order(rp) if use_order else None
+    h_seq = torch.zeros(len(dst), u, device="cuda")
+    got = ops.gru_seq(rp, cc, order, [dev(states)], dev(h0), dev(K), dev(R), dev(b), h_seq=h_seq).cpu().numpy()
+    padded = np.zeros((n_dst, max_len, fi), np.float64)
+    padded[dst, seq] = states[src]
+    K64, R64, b64 = K.astype(np.float64), R.astype(np.float64), b.astype(np.float64)
+    cell = lambda a, h: orc.gru_cell(a, h, K64, R64, b64)
+    nz = lens > 0
+    want = h0.astype(np.float64).copy()
+    want[nz] = orc.masked_rnn_last(cell, padded[nz], h0[nz].astype(np.float64), lens[nz])
+    assert rel_err(got, want) < RTOL
+    assert np.array_equal(got[~nz], h0[~nz])
+    # saved per-step states: last step of every non-empty destination equals its new state
+    hs = h_seq.cpu().numpy()
+    assert np.array_equal(hs[r[1:][nz] - 1], got[nz])
+
+
+def test_gru_seq_interleave_step_table(golden):
+    """Q-size step 1: step table from ign_steps_build == reference interleave of the padded tensors."""
+    from ignnition_b200 import ops
+    from ignnition_b200.batching import AdjacencySpec, SequenceSpec, position_table
+    g = golden("qsize_nsfnet")
+    ref = g["reference_tensors"][0]
+    adjs = [AdjacencySpec("adj_links_paths", "link", "path"), AdjacencySpec("adj_nodes_paths", "node", "path")]
+    spec = SequenceSpec("k", "path", adjs, True)
+    ps, pc = position_table(ref, spec)
+    n = ref["num_path"]
+    rps, cols, np_csr = [], [], []
+    for a in adjs:
+        r, c, _ = orc.csr_from_edges(ref["src_" + a.name], ref["dst_" + a.name], ref[a.seq_key], n)
+        np_csr.append((r, c))
+        rps.append(dev(r, torch.int32)); cols.append(dev(c, torch.int32))
+    total = sum(len(c) for _, c in np_csr)
+    srp, steps = ops.steps_build(rps, cols, None, dev(np.array([0, len(ps)], np.int32)), dev(ps), dev(pc), n, total)
+    srp, steps = srp.cpu().numpy(), steps.cpu().numpy()
+    # reference: concat padded blocks, scatter columns to `indices`, first final_len columns are the sequence
+    idx = np.concatenate([ref["indices_link_to_path"], ref["indices_node_to_path"]])
+    lens = [np.diff(r) for r, _ in np_csr]
+    maxl = [int(l.max()) for l in lens]
+    for d in range(n):
+        cols_d = []
+        for k, (r, c) in enumerate(np_csr):
+            row = [(k << 28) | int(x) for x in c[r[d]:r[d + 1]]] + [-1] * (maxl[k] - lens[k][d])
+            cols_d += row
+        seq_d = [-1] * len(idx)
+        for cpos, p in enumerate(idx):
+            seq_d[p] = cols_d[cpos]
+        fl = lens[0][d] + lens[1][d]
+        assert srp[d + 1] - srp[d] == fl
+        assert steps[srp[d]:srp[d + 1]].tolist() == seq_d[:fl]
+
+
+# ------------------------------------------------------------------ dense layers
+@pytest.mark.parametrize("m,k,n,act", [(1, 32, 256, "selu"), (1000, 32, 256, "selu"), (777, 256, 256, "relu"),
+                                       (5000, 256, 1, None), (130, 65, 20, "tanh"), (300, 7, 3, "sigmoid")])
+def test_dense(m, k, n, act):
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(m + k + n)
+    x = rng.randn(m, k).astype(np.float32)
+    w = (rng.randn(k, n) / np.sqrt(k)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+    pre = torch.empty(m, n, device="cuda")
+    got = ops.dense(dev(x), dev(w), dev(b), ops.ACTIVATIONS[act], pre_act=pre).cpu().numpy()
+    z = x.astype(np.float64) @ w.astype(np.float64) + b
+    assert rel_err(pre.cpu().numpy(), z) < RTOL
+    assert rel_err(got, orc.activation(act, z)) < RTOL
+
+
+def test_init_state_and_gather_concat():
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(0)
+    a = rng.randn(100, 1).astype(np.float32)
+    b = rng.randn(100, 3).astype(np.float32)
+    st = ops.init_state([dev(a), dev(b)], [1, 3], 100, 32).cpu().numpy()
+    assert np.array_equal(st[:, :1], a) and np.array_equal(st[:, 1:4], b) and np.all(st[:, 4:] == 0)
+    idx = rng.randint(0, 100, 250).astype(np.int32)
+    p = rng.randn(250, 2).astype(np.float32)
+    out = ops.gather_concat([dev(st), dev(p)], [dev(idx), None], 250).cpu().numpy()
+    assert np.array_equal(out[:, :32], st[idx]) and np.array_equal(out[:, 32:], p)

@@ -1,0 +1,197 @@
+"""GPU parity tests of the whole generated model (Engine == ComnetModel) against the CPU oracle and
+the committed golden fixtures."""
+
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from ignnition_b200 import synthetic
+from ignnition_b200.generator import sample_dimensions, sample_to_tensors
+from ignnition_b200.model_description import ModelDescription
+from oracle import ignnition_oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5          # BASELINE.json north star: 1e-5 relative (fp32) on states and predictions
+
+
+def rel_err(got, want):
+    want = np.asarray(want, dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def make(model_json, dims, seed=1234):
+    from ignnition_b200 import Engine
+    md = ModelDescription(model_json, dims)
+    o64 = orc.Oracle(model_json, dims, dtype=np.float64)
+    w = {k: v.astype(np.float32) for k, v in o64.init_weights(seed).items()}
+    eng = Engine(md, device="cuda:0")
+    assert set(eng.param_table) == set(w), set(eng.param_table) ^ set(w)
+    eng.set_weights(w)
+    return md, eng, o64, w
+
+
+def tensors_of(md, sample):
+    feats = [f.name for f in md.get_all_features()]
+    out, _, _ = md.get_output_info()
+    return sample_to_tensors(sample, feats, out, md.get_adjecency_info(), md.get_interleave_tensors(),
+                             md.get_additional_input_names(), True)
+
+
+@pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet"])
+def test_forward_matches_golden_and_oracle(case):
+    g = load_golden(case)
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    for ref, fl in zip(g["reference_tensors"], g["oracle_float"]):
+        tens = orc.normalize_inputs(g["model_json"], ref)
+        graph = eng.prepare([tens], check=True)
+        for st in graph.status.values():
+            assert st.cpu().numpy()[0] == 0
+        pred, state = eng.forward(graph, return_states=True)
+        p64, s64 = o64.forward(tens, w, return_states=True)
+        assert rel_err(pred.cpu().numpy().reshape(-1), fl["predictions_fp64"]) < RTOL     # committed fixture
+        assert rel_err(pred.cpu().numpy(), p64) < RTOL
+        for e, v in s64.items():
+            assert rel_err(state[e].cpu().numpy(), v) < RTOL, e
+        # __call__ == ComnetModel.call contract: dict in, [P, 1] out
+        assert eng(tens).shape == (ref["num_path"], 1)
+
+
+@pytest.mark.parametrize("csr_mode", [0, 1])
+@pytest.mark.parametrize("sort_by_length", [False, True])
+def test_batch_equals_per_sample(csr_mode, sort_by_length):
+    """model_fn loops over samples (generate_model.py:712-724); the block-diagonal batch must give the
+    same predictions, for ragged batches (different topologies / sizes) too."""
+    from ignnition_b200 import Engine
+    g = load_golden("routenet_nsfnet")
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    eng = Engine(md, device="cuda:0", csr_mode=csr_mode, sort_by_length=sort_by_length)
+    eng.set_weights(w)
+    samples = [synthetic.routenet_sample("nsfnet", 0, 0), synthetic.routenet_sample("geant2", 3, 1),
+               synthetic.routenet_sample("nsfnet", 5, 2)]
+    tens = [orc.normalize_inputs(g["model_json"], tensors_of(md, s)[0]) for s in samples]
+    pred = eng.forward(eng.prepare(tens)).cpu().numpy().reshape(-1)
+    want = np.concatenate([o64.forward(t, w).reshape(-1) for t in tens])
+    assert pred.shape == want.shape
+    assert rel_err(pred, want) < RTOL
+
+
+def test_qsize_batch_interleave():
+    g = load_golden("qsize_nsfnet")
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    samples = [synthetic.routenet_sample("nsfnet", s, s, qsize=True) for s in (0, 2)] + [g["samples"][0]]
+    tens = [orc.normalize_inputs(g["model_json"], tensors_of(md, s)[0]) for s in samples]
+    pred = eng.forward(eng.prepare(tens)).cpu().numpy().reshape(-1)
+    want = np.concatenate([o64.forward(t, w).reshape(-1) for t in tens])
+    assert rel_err(pred, want) < RTOL
+
+
+def _mpnn_json(agg="sum", hidden=64, update="gru", message_nn=False):
+    """generic single-entity MPNN (BASELINE config 5 shape) in the reference's JSON keywords."""
+    msg = [{"type": "direct_assignation"}]
+    nns = [{"nn_name": "rec", "nn_type": "recurrent_neural_network", "recurrent_type": "GRU"},
+           {"nn_name": "ro", "nn_type": "feed_forward", "nn_architecture": [
+               {"type_layer": "Dense", "units": 16, "activation": "relu"},
+               {"type_layer": "Dense", "units": 1, "activation": "None"}]}]
+    if message_nn:
+        msg = [{"type": "neural_network", "nn_name": "msg", "input": ["hs_source", "hs_dest", "edge_params"]}]
+        nns.append({"nn_name": "msg", "nn_type": "feed_forward", "nn_architecture": [
+            {"type_layer": "Dense", "units": 24, "activation": "tanh", "kernel_regularizer": 0.01},
+            {"type_layer": "Dense", "units": hidden, "activation": "None"}]})
+    upd = {"type": "recurrent_neural_network", "nn_name": "rec"}
+    if update == "ff":
+        upd = {"type": "neural_network", "nn_name": "upd"}
+        nns.append({"nn_name": "upd", "nn_type": "feed_forward", "nn_architecture": [
+            {"type_layer": "Dense", "units": 40, "activation": "selu"},
+            {"type_layer": "Dense", "units": 999, "activation": "sigmoid"}]})   # units forced to hidden
+    return {
+        "entities": [{"name": "node", "hidden_state_dimension": hidden,
+                      "features": [{"name": "x", "normalization": "None"}]}],
+        "message_passing": {"num_iterations": 3, "stages": [{"stage_name": "s", "stage_mp": [{
+            "destination_entity": "node",
+            "source_entities": [{"name": "node", "adj_vector": "adj", "message": msg}],
+            "aggregation": {"type": agg}, "update": upd}]}]},
+        "readout": [{"type": "predict", "input": ["node"], "label": "y", "nn_name": "ro"}],
+        "neural_networks": nns,
+        "learning_options": {"loss": "MeanSquaredError", "optimizer": {"type": "Adam"}},
+    }
+
+
+def _mpnn_sample(rng, n, max_deg, feat=3, params=False):
+    ent = {"v%d" % i: "node" for i in range(n)}
+    adj = {}
+    order = rng.permutation(n)
+    for d in order:
+        k = rng.randint(0, max_deg + 1)
+        if k:
+            nb = rng.randint(0, n, k)
+            adj["v%d" % d] = [["v%d" % s, [float(rng.randint(0, 5)), float(rng.randint(0, 5))]] for s in nb] \
+                if params else ["v%d" % s for s in nb]
+    return {"entities": ent, "adj": adj, "x": rng.randn(n, feat).tolist(), "y": rng.randn(n).tolist()}
+
+
+@pytest.mark.parametrize("agg,hidden,update,message_nn", [
+    ("sum", 64, "gru", False),      # config 5 shape: unfused segment_reduce + gru_cell (64-wide weights)
+    ("sum", 32, "gru", False),      # fused agg_gru_cell with source entity == destination entity
+    ("mean", 32, "gru", False), ("max", 32, "gru", False),
+    ("sum", 32, "ff", False),       # feed-forward update (semantics of call; crashes in the reference)
+    ("sum", 32, "gru", True),       # message MLP on [hs_source | hs_dest | edge_params]
+    ("ordered", 32, "gru", False),
+])
+def test_generic_mpnn(agg, hidden, update, message_nn):
+    rng = np.random.RandomState(len(agg) + hidden)
+    model_json = _mpnn_json(agg, hidden, update, message_nn)
+    samples = [_mpnn_sample(rng, n, 6, params=message_nn) for n in (40, 1, 300)]
+    if agg == "ordered":           # ordered needs >= 1 message per destination in the reference
+        for s in samples:
+            for v in s["entities"]:
+                s["adj"].setdefault(v, [v])
+    dims = sample_dimensions(samples[0])
+    md, eng, o64, w = make(model_json, dims)
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    want, wstate = [], []
+    for t in tens:
+        p, s = o64.forward(t, w, return_states=True)
+        want.append(p.reshape(-1)); wstate.append(s["node"])
+    assert rel_err(state["node"].cpu().numpy(), np.concatenate(wstate)) < RTOL
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate(want)) < RTOL
+
+
+def test_unsupported_keywords_fail_loudly():
+    from ignnition_b200 import Engine
+    mj = _mpnn_json("attention")
+    with pytest.raises(RuntimeError, match="IGNNITION.*not built yet"):
+        Engine(ModelDescription(mj, {"x": 3, "adj": 0}), device="cuda:0")
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        Engine(ModelDescription(_mpnn_json(), {"x": 3, "adj": 0}), device="cpu")
+
+
+def test_full_size_properties_geant2_batch():
+    """BASELINE config 3 at full size (GEANT2-shaped x 4096): size-independent properties --
+    every sample of a tiled batch with identical features gives identical predictions, the CSR is a
+    permutation (status == 0), and a 2-sample slice matches the oracle."""
+    from ignnition_b200.batching import assemble_tiled
+    g = load_golden("routenet_geant2")
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    base = g["reference_tensors"][0]
+    n = 4096
+    P, L = base["num_path"], base["num_link"]
+    tr = orc.normalization_routenet(np.asarray(base["traffic"], np.float32), "traffic")
+    cap = orc.normalization_routenet(np.asarray(base["link_capacity"], np.float32), "link_capacity")
+    fns = {"traffic": lambda r, c: np.tile(tr, c // P), "link_capacity": lambda r, c: np.tile(cap, c // L)}
+    batch = assemble_tiled(base, n, eng.entities, eng.features, eng.adjacencies, eng.sequences, fns)
+    graph = eng.prepare(batch, check=True)
+    for st in graph.status.values():
+        assert st.cpu().numpy()[0] == 0
+    pred = eng.forward(graph).cpu().numpy().reshape(n, P)
+    assert np.array_equal(pred, np.broadcast_to(pred[0], pred.shape))        # idempotent across replicas
+    want = o64.forward(orc.normalize_inputs(g["model_json"], base), w).reshape(-1)
+    assert rel_err(pred[0], want) < RTOL and rel_err(pred[-1], want) < RTOL

@@ -1,0 +1,304 @@
+"""CPU tests: host logic and the oracle against the golden vectors produced by the reference's own
+generator / parser (``oracle/make_golden.py``), and the C-ABI export check."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from ignnition_b200 import synthetic
+from ignnition_b200.batching import AdjacencySpec, SequenceSpec, assemble, assemble_tiled, position_table
+from ignnition_b200.generator import interleave_indices, make_indices, sample_dimensions, sample_to_tensors
+from ignnition_b200.model_description import ModelDescription, ModelDescriptionError
+from oracle import ignnition_oracle as orc
+
+CASES = ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet", "routenet_geant2"]
+
+
+def _samples(g):
+    if g["samples"] is not None:
+        return g["samples"]
+    shape, ts, fs = g["sample_recipe"]
+    return [synthetic.routenet_sample(shape, ts, fs)]
+
+
+def _tensors(g, sample, md):
+    feats = [f.name for f in md.get_all_features()]
+    out, _, _ = md.get_output_info()
+    return sample_to_tensors(sample, feats, out, md.get_adjecency_info(), md.get_interleave_tensors(),
+                             md.get_additional_input_names(), True)
+
+
+# ------------------------------------------------------------------ parser vs the reference parser
+@pytest.mark.parametrize("case", CASES)
+def test_parser_matches_reference(case):
+    g = load_golden(case)
+    meta = g["reference_meta"]
+    md = ModelDescription(g["model_json"], meta["dimensions"])
+    assert md.get_adjecency_info() == meta["adjacency_info"]
+    assert md.get_interleave_tensors() == meta["interleave_tensors"]
+    assert md.get_interleave_sources() == meta["interleave_sources"]
+    assert [[f.name, f.size, f.normalization] for f in md.get_all_features()] == meta["features"]
+    assert list(md.get_output_info()) == meta["output_info"]
+    assert md.get_mp_iterations() == meta["mp_iterations"]
+    assert md.get_input_dimensions() == meta["input_dimensions"]
+    assert md.get_additional_input_names() == meta["additional_input"]
+    assert md.get_loss() == meta["loss"]
+    assert md.get_optimizer() == meta["optimizer"]
+    stages = [[name, [[mp.destination_entity, [s.name for s in mp.source_entities], mp.aggregation.type,
+                       mp.update.type] for mp in mps]] for name, mps in md.get_mp_instances()]
+    assert stages == meta["stages"]
+
+
+def test_parser_rejects_bad_models():
+    g = load_golden("qsize_hand")
+    bad = dict(g["model_json"])
+    bad = {k: v for k, v in bad.items() if k != "readout"}
+    with pytest.raises(ModelDescriptionError, match="IGNNITION"):
+        ModelDescription(bad)
+    import copy
+    bad = copy.deepcopy(g["model_json"])
+    bad["message_passing"]["stages"][0]["stage_mp"][0]["destination_entity"] = "nope"
+    with pytest.raises(ModelDescriptionError, match="destination entity nope"):
+        ModelDescription(bad)
+    bad = copy.deepcopy(g["model_json"])
+    bad["message_passing"]["stages"][0]["stage_mp"][0]["update"]["nn_name"] = "missing_nn"
+    with pytest.raises(ModelDescriptionError, match="missing_nn"):
+        ModelDescription(bad)
+
+
+# ------------------------------------------------------------------ generator vs the reference generator
+@pytest.mark.parametrize("case", CASES)
+def test_generator_bit_exact(case):
+    g = load_golden(case)
+    md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
+    for sample, ref, ref_y in zip(_samples(g), g["reference_tensors"], g["reference_labels"]):
+        assert sample_dimensions(sample) == g["reference_meta"]["dimensions"]
+        got, y = _tensors(g, sample, md)
+        assert set(got) == set(ref)
+        for k, v in ref.items():
+            if k.startswith(("src_", "dst_", "seq_", "indices_", "num_")):
+                assert np.array_equal(np.asarray(got[k], dtype=np.int64), np.asarray(v, dtype=np.int64)), k
+            else:
+                assert np.array_equal(np.asarray(got[k], dtype=np.float64), np.asarray(v, dtype=np.float64)), k
+        assert np.allclose(y, ref_y, rtol=0, atol=0)
+
+
+def test_make_indices_order_of_appearance():
+    cnt, idx = make_indices({"a": "x", "b": "y", "c": "x", "d": "y", "e": "x"})
+    assert cnt == {"x": 3, "y": 2}
+    assert idx == {"a": 0, "b": 0, "c": 1, "d": 1, "e": 2}
+
+
+def test_interleave_hand_example():
+    # pattern [node, link], max lens 3/3 -> node [0,2,4], link [1,3,5]
+    assert interleave_indices(["node", "link"], {"node": 3, "link": 3}) == {"node": [0, 2, 4], "link": [1, 3, 5]}
+    assert interleave_indices(["node", "link"], {"node": 4, "link": 3}) == {"node": [0, 2, 4, 6], "link": [1, 3, 5]}
+
+
+def test_generator_errors():
+    g = load_golden("qsize_hand")
+    md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
+    s = dict(g["samples"][0])
+    del s["traffic"]
+    with pytest.raises(Exception, match='feature named "traffic"'):
+        _tensors(g, s, md)
+    s = dict(g["samples"][0])
+    s["entities"] = dict(s["entities"], p0="link")
+    with pytest.raises(Exception, match="adjecency list"):
+        _tensors(g, s, md)
+
+
+# ------------------------------------------------------------------ oracle: integer side
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_csr_roundtrip(case):
+    g = load_golden(case)
+    for ref in g["reference_tensors"]:
+        for adj, src_e, dst_e, _ in g["reference_meta"]["adjacency_info"]:
+            src, dst = np.array(ref["src_" + adj]), np.array(ref["dst_" + adj])
+            seq = np.array(ref["seq_%s_%s" % (src_e, dst_e)])
+            n = ref["num_" + dst_e]
+            rowptr, col, perm = orc.csr_from_edges(src, dst, seq, n)
+            assert rowptr[-1] == len(src) and np.all(col >= 0)
+            # CSR -> (dst, seq, src) round trip
+            d2 = np.repeat(np.arange(n), np.diff(rowptr))
+            s2 = np.arange(len(src)) - rowptr[d2]
+            assert np.array_equal(d2, dst[perm]) and np.array_equal(s2, seq[perm]) and np.array_equal(col, src[perm])
+            # stable sort by destination gives the same CSR (seq is the rank in input order)
+            r2, c2, p2 = orc.stable_sort_csr(src, dst, n)
+            assert np.array_equal(r2, rowptr) and np.array_equal(c2, col) and np.array_equal(p2, perm)
+
+
+def test_oracle_segment_sum_equals_padded_reduce_sum():
+    rng = np.random.RandomState(0)
+    n_dst, n_src, F = 17, 11, 8
+    lens = rng.randint(0, 6, n_dst)
+    dst = np.repeat(np.arange(n_dst), lens)
+    seq = np.concatenate([np.arange(l) for l in lens])
+    p = rng.permutation(len(dst))
+    dst, seq = dst[p], seq[p]
+    src = rng.randint(0, n_src, len(dst))
+    states = rng.randn(n_src, F).astype(np.float32)
+    padded = np.zeros((n_dst, lens.max(), F), np.float32)
+    padded[dst, seq] = states[src]
+    rowptr, col, _ = orc.csr_from_edges(src, dst, seq, n_dst)
+    seg = np.stack([states[col[rowptr[d]:rowptr[d + 1]]].sum(axis=0) if lens[d] else np.zeros(F, np.float32)
+                    for d in range(n_dst)])
+    assert np.allclose(seg, padded.sum(axis=1), rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------ oracle: float side cross-checks
+def test_oracle_gru_matches_torch_grucell():
+    rng = np.random.RandomState(1)
+    u, fi, n = 32, 32, 50
+    K = rng.uniform(-0.3, 0.3, (fi, 3 * u)).astype(np.float32)
+    R = rng.uniform(-0.3, 0.3, (u, 3 * u)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (2, 3 * u)).astype(np.float32)
+    x = rng.randn(n, fi).astype(np.float32)
+    h = rng.randn(n, u).astype(np.float32)
+    got = orc.gru_cell(x, h, K, R, b)
+    cell = torch.nn.GRUCell(fi, u)
+    perm = np.concatenate([np.arange(u, 2 * u), np.arange(0, u), np.arange(2 * u, 3 * u)])   # z|r|h -> r|z|n
+    with torch.no_grad():
+        cell.weight_ih.copy_(torch.from_numpy(K[:, perm].T.copy()))
+        cell.weight_hh.copy_(torch.from_numpy(R[:, perm].T.copy()))
+        cell.bias_ih.copy_(torch.from_numpy(b[0, perm].copy()))
+        cell.bias_hh.copy_(torch.from_numpy(b[1, perm].copy()))
+        ref = cell(torch.from_numpy(x), torch.from_numpy(h)).numpy()
+    assert np.abs(got - ref).max() < 2e-6
+
+
+def test_oracle_selu_matches_torch():
+    x = np.linspace(-6, 6, 101).astype(np.float32)
+    ref = torch.nn.functional.selu(torch.from_numpy(x)).numpy()
+    assert np.abs(orc.activation("selu", x) - ref).max() < 1e-6
+
+
+def test_oracle_masked_rnn_is_per_destination_walk():
+    rng = np.random.RandomState(2)
+    n, L, F = 9, 5, 8
+    lens = rng.randint(1, L + 1, n)
+    x = rng.randn(n, L, F).astype(np.float32)
+    h0 = rng.randn(n, F).astype(np.float32)
+    K = rng.uniform(-0.4, 0.4, (F, 3 * F)).astype(np.float32)
+    R = rng.uniform(-0.4, 0.4, (F, 3 * F)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (2, 3 * F)).astype(np.float32)
+    cell = lambda a, h: orc.gru_cell(a, h, K, R, b)
+    got = orc.masked_rnn_last(cell, x, h0, lens)
+    for i in range(n):
+        h = h0[i:i + 1]
+        for t in range(lens[i]):
+            h = cell(x[i:i + 1, t], h)
+        assert np.allclose(got[i], h[0], rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        orc.masked_rnn_last(cell, x, h0, np.zeros(n, dtype=np.int64))
+
+
+@pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet"])
+def test_oracle_float_golden(case):
+    g = load_golden(case)
+    dims = g["reference_meta"]["dimensions"]
+    for ref, fl in zip(g["reference_tensors"], g["oracle_float"]):
+        o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
+        w = {k: v.astype(np.float32) for k, v in o64.init_weights(fl["weight_seed"]).items()}
+        tens = orc.normalize_inputs(g["model_json"], ref)
+        p64, st = o64.forward(tens, w, return_states=True)
+        assert np.allclose(p64.reshape(-1), fl["predictions_fp64"], rtol=1e-12, atol=1e-12)
+        for k, v in fl["state_checksums_fp64"].items():
+            assert abs(st[k].sum() - v) <= 1e-9 * max(1.0, abs(v))
+        # fp32 run of the same program stays within the north-star tolerance of the fp64 shadow
+        p32 = orc.Oracle(g["model_json"], dims, dtype=np.float32).forward(tens, w)
+        err = np.abs(p32.reshape(-1) - p64.reshape(-1)).max() / np.abs(p64).max()
+        assert err < 1e-5, err
+
+
+def test_oracle_weight_count_routenet():
+    g = load_golden("routenet_nsfnet")
+    o = orc.Oracle(g["model_json"], g["reference_meta"]["dimensions"])
+    total = sum(int(np.prod(s)) for s in o.weight_shapes().values())
+    assert total == 87169           # 2 x 6336 GRU + 8448 + 65792 + 257
+
+
+def test_exponential_decay_and_adam():
+    assert orc.exponential_decay(80000, 1e-3, 80000, 0.6) == pytest.approx(6e-4)
+    assert orc.exponential_decay(81999, 1e-3, 82000, 0.8, staircase="True") == pytest.approx(1e-3)
+    w, g = np.ones(3), np.full(3, 0.5)
+    w1, m, v = orc.adam_step(w, g, np.zeros(3), np.zeros(3), 1, 1e-3)
+    assert np.allclose(w1, 1 - 1e-3 * 0.5 / (0.5 + 1e-7 * np.sqrt(1 - 0.999) / 1.0) , rtol=1e-5)
+
+
+# ------------------------------------------------------------------ batching
+def _specs(md):
+    ents = [e.name for e in md.get_entities()]
+    feats = [(f.name, e.name, f.size) for e in md.get_entities() for f in e.features]
+    adjs = [AdjacencySpec(a[0], a[1], a[2], a[3] == "True") for a in md.get_adjecency_info()]
+    by = {a.name: a for a in adjs}
+    seqs = []
+    for si, (_, mps) in enumerate(md.get_mp_instances()):
+        for mi, mp in enumerate(mps):
+            if mp.aggregation.type == "interleave" or (mp.aggregation.type == "ordered" and len(mp.source_entities) > 1):
+                seqs.append(SequenceSpec("s%d_m%d" % (si, mi), mp.destination_entity,
+                                         [by[s.adj_vector] for s in mp.source_entities],
+                                         mp.aggregation.type == "interleave"))
+    return ents, feats, adjs, seqs
+
+
+def test_batch_is_block_diagonal():
+    g = load_golden("routenet_nsfnet")
+    md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
+    ents, feats, adjs, seqs = _specs(md)
+    samples = g["reference_tensors"]
+    b = assemble(samples, ents, feats, adjs, seqs, g["reference_labels"])
+    assert b.num["path"] == sum(s["num_path"] for s in samples)
+    off = 0
+    for s in samples:
+        n = len(s["src_adj_links_paths"])
+        assert np.array_equal(b.arrays["src_adj_links_paths"][off:off + n] - b.offsets["link"][samples.index(s)],
+                              s["src_adj_links_paths"])
+        off += n
+    assert b.arrays["labels"].size == b.num["path"]
+    # tiled assembly == assembling copies
+    t = assemble_tiled(samples[0], 3, ents, feats, adjs, seqs,
+                       {"traffic": lambda r, n: np.zeros(n), "link_capacity": lambda r, n: np.zeros(n)})
+    c = assemble([samples[0]] * 3, ents, feats, adjs, seqs)
+    for k in ("src_adj_links_paths", "dst_adj_links_paths", "seq_adj_links_paths", "src_adj_paths_links",
+              "dst_adj_paths_links", "sample_of_path"):
+        assert np.array_equal(t.arrays[k], c.arrays[k]), k
+
+
+def test_position_table_interleave():
+    g = load_golden("qsize_hand")
+    md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
+    _, _, _, seqs = _specs(md)
+    ps, pc = position_table(g["reference_tensors"][0], seqs[0])
+    # sources in model order: link (k=0), node (k=1); pattern [node, link] -> n0 l0 n1 l1 n2 l2
+    assert ps.tolist() == [1, 0, 1, 0, 1, 0]
+    assert pc.tolist() == [0, 0, 1, 1, 2, 2]
+
+
+# ------------------------------------------------------------------ the C-ABI library
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ignnition_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ign_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    from ignnition_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared
+    path = _lib.LIB_PATH
+    if not os.path.exists(path):
+        import __graft_entry__ as ge
+        ge.build()
+    lib = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ign_version() >= 100
+    # host-side argument validation works without a GPU: invalid calls return <0 and set the message
+    lib.ign_segment_reduce.restype = ctypes.c_int
+    rc = lib.ign_segment_reduce(99, None, None, None, 32, ctypes.c_int64(1), None, None)
+    assert rc < 0
+    buf = ctypes.create_string_buffer(256)
+    lib.ign_last_error(buf, ctypes.c_size_t(256))
+    assert buf.value.decode().startswith("IGNNITION:")
