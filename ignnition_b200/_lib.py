@@ -31,6 +31,7 @@ SIGNATURES = {
     "ign_length_order": (_int, [_p, _i64, _p, _p, _sz, _p]),
     "ign_steps_build_ws_bytes": (_sz, [_i64]),
     "ign_steps_build": (_int, [_int, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "ign_steps_keys": (_int, [_p, _i64, _int, _i64, _p, _p]),
     "ign_init_state": (_int, [_int, _p, _p, _i64, _int, _p, _p]),
     "ign_segment_reduce": (_int, [_int, _p, _p, _p, _int, _i64, _p, _p]),
     "ign_gru_cell": (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p]),

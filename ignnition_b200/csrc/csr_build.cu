@@ -365,6 +365,16 @@ __global__ void steps_fill_kernel(StepSources s, const int* __restrict__ dst_sam
   }
 }
 
+// key of step i for the transposed (by source row) CSR of source `src_id`; foreign / zero steps go to
+// the dummy bucket n_rows
+__global__ void steps_keys_kernel(const int* __restrict__ steps, int64_t n, int src_id, int n_rows,
+                                  int* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int e = steps[i];
+  keys[i] = (e >= 0 && (e >> IGN_STEP_SRC_SHIFT) == src_id) ? (e & IGN_STEP_ROW_MASK) : n_rows;
+}
+
 inline unsigned grid1d(int64_t n, int threads = 256) { return (unsigned)ign_cdiv(n > 0 ? n : 1, threads); }
 
 }  // namespace
@@ -389,7 +399,8 @@ extern "C" int ign_csr_build(const int32_t* dst, const int32_t* src, const int32
   IGN_REQUIRE(rowptr && (n_edges == 0 || (dst && src && col)), IGN_ERR_INVALID,
               "IGNNITION: csr_build: null pointer");
   IGN_REQUIRE(mode == IGN_CSR_SORT || mode == IGN_CSR_RANK, IGN_ERR_INVALID, "IGNNITION: csr_build: bad mode");
-  IGN_REQUIRE(mode == IGN_CSR_SORT || seq, IGN_ERR_INVALID, "IGNNITION: csr_build: IGN_CSR_RANK needs seq");
+  IGN_REQUIRE(mode == IGN_CSR_SORT || seq || n_edges == 0, IGN_ERR_INVALID,
+              "IGNNITION: csr_build: IGN_CSR_RANK needs seq");
   IGN_REQUIRE(ws && ws_bytes >= ign_csr_build_ws_bytes(n_edges, num_dst), IGN_ERR_WORKSPACE,
               "IGNNITION: csr_build: workspace too small (%zu < %zu)", ws_bytes,
               ign_csr_build_ws_bytes(n_edges, num_dst));
@@ -497,5 +508,16 @@ extern "C" int ign_steps_build(int n_src, const int32_t* const* rowptrs, const i
                                                         steps_rowptr, steps);
     IGN_CHECK_LAUNCH("steps_fill");
   }
+  return IGN_OK;
+}
+
+extern "C" int ign_steps_keys(const int32_t* steps, int64_t n, int src_id, int64_t n_rows, int32_t* keys,
+                              void* stream) {
+  IGN_REQUIRE(n >= 0 && n_rows >= 0 && src_id >= 0 && src_id < IGN_MAX_SOURCES, IGN_ERR_INVALID,
+              "IGNNITION: steps_keys: bad argument");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(steps && keys, IGN_ERR_INVALID, "IGNNITION: steps_keys: null pointer");
+  steps_keys_kernel<<<grid1d(n), 256, 0, ign_stream(stream)>>>(steps, n, src_id, (int)n_rows, keys);
+  IGN_CHECK_LAUNCH("steps_keys");
   return IGN_OK;
 }

@@ -103,6 +103,13 @@ def steps_build(rowptrs: List[torch.Tensor], cols: List[torch.Tensor], dst_sampl
     return steps_rowptr, steps
 
 
+def steps_keys(steps: torch.Tensor, src_id: int, n_rows: int) -> torch.Tensor:
+    lib = _lib.load()
+    keys = torch.empty_like(steps)
+    _lib.check(lib.ign_steps_keys(_i(steps), steps.numel(), src_id, n_rows, _i(keys), _stream()), "steps_keys")
+    return keys
+
+
 # ------------------------------------------------------------------------------- forward
 def init_state(feats: List[torch.Tensor], sizes: List[int], n: int, hidden: int,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -1,0 +1,207 @@
+"""Train step of the generated model: loss, backward, optimiser.
+
+Mirrors ``model_fn`` (reference ``code/utils/generate_model.py:697-830``):
+  loss = MeanSquaredError()(labels, predictions) over ALL predictions of the batch (:745-751)
+         + sum(model.losses)  (l2(lambda) = lambda * sum(w^2) per regularised Dense kernel, :749)
+  grads = tf.gradients(total_loss, variables) (:791);  Adam(ExponentialDecay(...)) (:796-818).
+
+The backward pass walks the forward tape in reverse and calls the backward twins of the kernels
+(``ign_dense_bwd``, ``ign_gru_cell_bwd``, ``ign_gru_seq_bwd``); gradients w.r.t. source states are
+reduced per source row with ``ign_segment_reduce`` over the TRANSPOSED adjacency (built once per
+batch by the same device radix sort), so no atomics touch state gradients.  Data-parallel runs
+all-reduce the flat gradient buffer over NCCL and divide by the GLOBAL prediction count, which
+reproduces the reference's mean over all predictions.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+
+class LearningRate:
+    """tf.keras.optimizers.schedules by name (generate_model.py:802-809) [TF-2.1 semantics]."""
+
+    def __init__(self, optimizer: dict):
+        self.const = float(optimizer.get("learning_rate", 0.001))
+        self.schedule = optimizer.get("schedule")
+        if self.schedule is not None:
+            t = self.schedule.get("type")
+            if t not in ("ExponentialDecay", "InverseTimeDecay"):
+                raise RuntimeError("IGNNITION: learning-rate schedule %s is not built" % t)
+
+    def __call__(self, step: int) -> float:
+        s = self.schedule
+        if s is None:
+            return self.const
+        lr0, ds, dr = float(s["initial_learning_rate"]), float(s["decay_steps"]), float(s["decay_rate"])
+        p = step / ds
+        if s.get("staircase"):            # any truthy value, e.g. the string "True" of the Q-size example
+            p = math.floor(p)
+        if s["type"] == "ExponentialDecay":
+            return lr0 * dr ** p
+        return lr0 / (1.0 + dr * p)
+
+
+class Trainer:
+    """Owns gradients, Adam moments and the step counter of one Engine."""
+
+    def __init__(self, engine, world_size: int = 1, process_group=None):
+        self.e = engine
+        self.world = world_size
+        self.pg = process_group
+        opt = engine.model.get_optimizer()
+        kind = opt.get("type", "Adam")
+        if kind != "Adam":
+            raise RuntimeError("IGNNITION: optimizer %s is not built in the B200 engine (Adam only)" % kind)
+        if engine.model.get_loss() != "MeanSquaredError":
+            raise RuntimeError("IGNNITION: loss %s is not built in the B200 engine (MeanSquaredError only)"
+                               % engine.model.get_loss())
+        self.beta1 = float(opt.get("beta_1", 0.9))
+        self.beta2 = float(opt.get("beta_2", 0.999))
+        self.eps = float(opt.get("epsilon", 1e-7))
+        self.lr = LearningRate(opt)
+        n = engine.weights.numel()
+        dev = engine.device
+        self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.scalars = torch.zeros(4, dtype=torch.float64, device=dev)    # [sse, reg, n_pred, unused]
+        self.step = 0
+
+    def g(self, name: str) -> torch.Tensor:
+        return self.e._pview(self.grads, name)
+
+    # ------------------------------------------------------------------ transposed adjacencies
+    def build_transposed(self, graph):
+        e = self.e
+        for stage in e.plans:
+            for p in stage:
+                if p.kind == "seq_gru":
+                    rowptr_s, steps = graph.steps[p.key]
+                    for k, a in enumerate(p.adjs):
+                        key = "%s/%d" % (p.key, k)
+                        if key in graph.csr_t:
+                            continue
+                        n_rows = graph.num[a.src]
+                        keys = ops.steps_keys(steps, k, n_rows)
+                        rp, _, perm, _ = ops.csr_build(keys, keys, None, n_rows + 1, ops.CSR_SORT, want_perm=True)
+                        graph.csr_t[key] = (rp[:n_rows + 1], perm)
+                else:
+                    for a in p.adjs:
+                        if a.name in graph.csr_t:
+                            continue
+                        rp, col_t, _, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name], None,
+                                                        graph.num[a.src], ops.CSR_SORT)
+                        graph.csr_t[a.name] = (rp, col_t)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, graph, tape: list, d_pred: torch.Tensor):
+        e = self.e
+        dev = e.device
+        gstate: Dict[str, Optional[torch.Tensor]] = {n: None for n in e.entities}
+
+        def add_grad(ent: str, contrib: torch.Tensor):
+            if gstate[ent] is None:
+                gstate[ent] = contrib
+            else:
+                ops.axpy(1.0, contrib, gstate[ent])
+
+        for entry in reversed(tape):
+            kind = entry[0]
+            if kind == "readout":
+                _, op, saves = entry
+                dy = d_pred
+                for prefix, layer, x, pre in reversed(saves):
+                    w = e.param("%s/%s/kernel" % (prefix, layer.name))
+                    dw = self.g("%s/%s/kernel" % (prefix, layer.name))
+                    db = self.g("%s/%s/bias" % (prefix, layer.name)) if layer.use_bias else None
+                    dx = torch.empty_like(x)
+                    ops.dense_bwd(x, w, e._act(layer.activation), pre, dy, dx, dw, db)
+                    dy = dx
+                if len(op.input) != 1:
+                    raise RuntimeError("IGNNITION: training with a multi-input readout is not built")
+                add_grad(op.input[0], dy)
+            elif kind == "seq_gru":
+                _, p, src_states, h_old, h_seq = entry
+                g_new = gstate[p.dst]
+                if g_new is None:                       # state never reaches the loss
+                    continue
+                rowptr_s, steps = graph.steps[p.key]
+                d_steps = torch.empty(steps.numel(), p.msg_dim, dtype=torch.float32, device=dev)
+                dh0 = torch.empty_like(h_old)
+                ops.gru_seq_bwd(rowptr_s, steps, graph.order.get(p.key), src_states, h_old, h_seq,
+                                e.param(p.dst + "_update/kernel"), e.param(p.dst + "_update/recurrent_kernel"),
+                                e.param(p.dst + "_update/bias"), g_new, d_steps, dh0,
+                                self.g(p.dst + "_update/kernel"), self.g(p.dst + "_update/recurrent_kernel"),
+                                self.g(p.dst + "_update/bias"))
+                gstate[p.dst] = dh0
+                for k, a in enumerate(p.adjs):
+                    rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]
+                    add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_steps))
+            elif kind in ("agg_gru", "agg_gru_unfused"):
+                _, p, src_state, h_old, agg = entry
+                if p.op != ops.OP_SUM:
+                    raise RuntimeError("IGNNITION: training through mean/max aggregation is not built")
+                g_new = gstate[p.dst]
+                if g_new is None:
+                    continue
+                d_agg = torch.empty_like(agg)
+                dh = torch.empty_like(h_old)
+                ops.gru_cell_bwd(agg, h_old, e.param(p.dst + "_update/kernel"),
+                                 e.param(p.dst + "_update/recurrent_kernel"), e.param(p.dst + "_update/bias"),
+                                 g_new, d_agg, dh, self.g(p.dst + "_update/kernel"),
+                                 self.g(p.dst + "_update/recurrent_kernel"), self.g(p.dst + "_update/bias"))
+                gstate[p.dst] = dh
+                for a in p.adjs:
+                    rp_t, col_t = graph.csr_t[a.name]
+                    add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, col_t, d_agg))
+            else:
+                raise RuntimeError("IGNNITION: training through '%s' is not built" % kind)
+
+    # ------------------------------------------------------------------ one step
+    def loss_and_grads(self, graph, global_n: Optional[int] = None):
+        """Forward + backward.  Returns (pred, local sum of squared errors tensor[fp64], n_local)."""
+        e = self.e
+        if "labels" not in graph.t:
+            raise RuntimeError("IGNNITION: the batch has no labels")
+        self.build_transposed(graph)
+        self.grads.zero_()
+        self.scalars.zero_()
+        tape: list = []
+        pred = e.forward(graph, training=True, tape=tape)
+        n_local = pred.numel()
+        n_glob = global_n if global_n is not None else n_local * self.world
+        d_pred = torch.empty_like(pred)
+        ops.mse_loss(pred, graph.t["labels"], 1.0 / float(n_glob), d_pred, self.scalars[0:1])
+        self.backward(graph, tape, d_pred)
+        return pred, n_local
+
+    def apply(self):
+        e = self.e
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, group=self.pg)              # NCCL over NVLink: sum of rank gradients
+            dist.all_reduce(self.scalars[0:1], group=self.pg)
+        for name, lam in e._reg.items():                            # added once, identical on every rank
+            ops.l2_reg(e.param(name), lam, self.g(name), self.scalars[1:2])
+        self.step += 1
+        ops.adam_step(e.weights, self.grads, self.m, self.v, self.lr(self.step - 1), self.beta1, self.beta2,
+                      self.eps, self.step)
+
+    def train_step(self, graph, global_n: Optional[int] = None):
+        """One optimiser step on a prepared batch.  Returns (loss, regularisation) as device scalars
+        in ``self.scalars`` -- read them with ``losses()`` (a host sync)."""
+        pred, n_local = self.loss_and_grads(graph, global_n)
+        self._n_glob = global_n if global_n is not None else n_local * self.world
+        self.apply()
+        return pred
+
+    def losses(self):
+        s = self.scalars.cpu().numpy()
+        mse = float(s[0]) / float(self._n_glob)
+        return {"loss": mse, "regularization_loss": float(s[1]), "total_loss": mse + float(s[1])}

@@ -102,6 +102,12 @@ int ign_steps_build(int n_src, const int32_t* const* rowptrs /*host array of dev
                     const int32_t* pos_col, int64_t num_dst, int32_t* steps_rowptr, int32_t* steps,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* Sort keys for the transposed (by source row) view of a step table, used by the backward pass to
+ * reduce d_steps per source row without atomics: keys[i] = row of step i if it belongs to source
+ * src_id, else n_rows (a dummy bucket).  Feed keys to ign_csr_build(seq = NULL, num_dst = n_rows+1). */
+int ign_steps_keys(const int32_t* steps, int64_t n, int src_id, int64_t n_rows, int32_t* keys,
+                   void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Entity.calculate_hs (auxilary_classes.py:128-160): state[n, hidden] = [features | zeros].
  * feats: host array of n_feat device pointers, each [n, feat_size[i]] fp32. */

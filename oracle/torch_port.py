@@ -1,0 +1,131 @@
+"""CPU ORACLE, differentiable twin (test infrastructure, not product code).
+
+The same op-for-op restatement of ``ComnetModel.call`` as ``oracle/ignnition_oracle.py`` (dense
+right-padded message tensor, masked RNN, Keras GRU / Dense / SELU formulas), written on torch CPU
+tensors so that ``torch.autograd`` gives the reference for ``tf.gradients(total_loss, variables)``
+(``code/utils/generate_model.py:791``).  Covers what the BASELINE configs train: direct_assignation
+messages, sum / ordered / interleave aggregation, GRU update, Dense readout.  Cross-checked against
+the NumPy oracle in ``tests/test_host.py``.  float parity vs TensorFlow itself is unpinned (see the
+NumPy oracle's header).
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from .ignnition_oracle import SELU_ALPHA, SELU_SCALE, Oracle
+
+
+def _act(name, x):
+    if name is None or name in ("None", "linear"):
+        return x
+    if name == "relu":
+        return torch.relu(x)
+    if name == "selu":
+        return SELU_SCALE * torch.where(x > 0, x, SELU_ALPHA * (torch.exp(torch.clamp(x, max=0)) - 1))
+    if name == "sigmoid":
+        return torch.sigmoid(x)
+    if name == "tanh":
+        return torch.tanh(x)
+    raise ValueError("torch oracle: unsupported activation " + str(name))
+
+
+def gru_cell(x, h, K, R, b):
+    u = h.shape[1]
+    mx = x @ K + b[0]
+    mh = h @ R + b[1]
+    z = torch.sigmoid(mx[:, :u] + mh[:, :u])
+    r = torch.sigmoid(mx[:, u:2 * u] + mh[:, u:2 * u])
+    hh = torch.tanh(mx[:, 2 * u:] + r * mh[:, 2 * u:])
+    return z * h + (1 - z) * hh
+
+
+class TorchOracle:
+    def __init__(self, model_json: dict, dims: Dict[str, int], dtype=torch.float64):
+        self.np_oracle = Oracle(model_json, dims, dtype=np.float64)
+        self.m = self.np_oracle.m
+        self.dtype = dtype
+
+    def params(self, w: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
+        return {k: torch.tensor(np.asarray(v, dtype=np.float64), dtype=self.dtype, requires_grad=True)
+                for k, v in w.items()}
+
+    def forward(self, inp: dict, w: Dict[str, torch.Tensor]) -> torch.Tensor:
+        o = self.np_oracle
+        dt = self.dtype
+        state = {e["name"]: torch.tensor(o.initial_state(e, inp), dtype=dt) for e in self.m["entities"]}
+        for _ in range(o.T):
+            for st in self.m["message_passing"]["stages"]:
+                for mp in st["stage_mp"]:
+                    dst = mp["destination_entity"]
+                    state[dst] = self._mp(mp, dst, state, inp, w)
+        for k, op in enumerate(self.m["readout"]):
+            if op["type"] == "predict":
+                x = torch.cat([state[i] for i in op["input"]], dim=1)
+                for l in o.layer_names(op["nn_name"], "readout"):
+                    x = x @ w["readout_model_%d/%s/kernel" % (k, l["name"])] + w["readout_model_%d/%s/bias" % (k, l["name"])]
+                    a = l.get("activation")
+                    x = _act(None if a == "None" else a, x)
+                return x
+        raise ValueError("torch oracle: no predict operation")
+
+    def _mp(self, mp, dst, state, inp, w):
+        dt = self.dtype
+        num_dst = int(inp["num_" + dst])
+        agg = mp["aggregation"]["type"]
+        blocks, lens_all, idx_all = [], [], []
+        for src in mp["source_entities"]:
+            if any(op["type"] != "direct_assignation" for op in src["message"]):
+                raise ValueError("torch oracle: message neural networks are not restated here")
+            src_idx = torch.as_tensor(np.asarray(inp["src_" + src["adj_vector"]], dtype=np.int64))
+            dst_idx = torch.as_tensor(np.asarray(inp["dst_" + src["adj_vector"]], dtype=np.int64))
+            seq = torch.as_tensor(np.asarray(inp["seq_" + src["name"] + "_" + dst], dtype=np.int64))
+            msgs = state[src["name"]][src_idx]                                   # tf.gather
+            max_len = int(seq.max()) + 1
+            s = torch.zeros(num_dst, max_len, msgs.shape[1], dtype=dt).index_put((dst_idx, seq), msgs)  # scatter_nd
+            blocks.append(s)
+            lens_all.append(torch.bincount(dst_idx, minlength=num_dst))
+            if agg == "interleave":
+                idx_all.append(np.asarray(inp["indices_" + src["name"] + "_to_" + dst], dtype=np.int64))
+        src_input = torch.cat(blocks, dim=1)
+        final_len = sum(lens_all)
+        K, R, b = w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"], w[dst + "_update/bias"]
+        h = state[dst]
+        if agg == "sum":
+            return gru_cell(src_input.sum(dim=1), h, K, R, b)
+        if agg == "interleave":
+            idx = torch.as_tensor(np.concatenate(idx_all))
+            tr = src_input.transpose(0, 1)
+            src_input = torch.zeros_like(tr).index_put((idx,), tr).transpose(0, 1)
+        elif agg != "ordered":
+            raise ValueError("torch oracle: aggregation " + agg + " is not restated here")
+        out_prev = torch.zeros_like(h)
+        outs = []
+        for t in range(src_input.shape[1]):                                      # masked K.rnn
+            m = (t < final_len)[:, None]
+            nh = gru_cell(src_input[:, t], h, K, R, b)
+            out_prev = torch.where(m, nh, out_prev)
+            h = torch.where(m, nh, h)
+            outs.append(out_prev)
+        outputs = torch.stack(outs, dim=1)
+        return outputs[torch.arange(num_dst), final_len - 1]                     # gather_nd
+
+    def loss_and_grads(self, samples: List[dict], labels: List[np.ndarray], w_np: Dict[str, np.ndarray]):
+        """model_fn: MSE over all predictions of all samples + sum of l2 regularisers; gradients."""
+        w = self.params(w_np)
+        preds = torch.cat([self.forward(s, w).reshape(-1) for s in samples])
+        y = torch.tensor(np.concatenate([np.asarray(l, dtype=np.float64).reshape(-1) for l in labels]), dtype=self.dtype)
+        mse = torch.mean((y - preds) ** 2)
+        reg = torch.zeros((), dtype=self.dtype)
+        for prefix, layers in self.np_oracle._regularized_layers():
+            for l in layers:
+                lam = float(l.get("kernel_regularizer", 0.0) or 0.0)
+                if lam:
+                    reg = reg + lam * (w[prefix + "/" + l["name"] + "/kernel"] ** 2).sum()
+        total = mse + reg
+        total.backward()
+        grads = {k: (v.grad.numpy().copy() if v.grad is not None else np.zeros(v.shape)) for k, v in w.items()}
+        return float(mse), float(reg), preds.detach().numpy(), grads

@@ -302,3 +302,29 @@ def test_cabi_exports_every_declared_symbol():
     buf = ctypes.create_string_buffer(256)
     lib.ign_last_error(buf, ctypes.c_size_t(256))
     assert buf.value.decode().startswith("IGNNITION:")
+
+
+# ------------------------------------------------------------------ the differentiable oracle twin
+@pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_hand"])
+def test_torch_oracle_matches_numpy_oracle(case):
+    from oracle.torch_port import TorchOracle
+    g = load_golden(case)
+    dims = g["reference_meta"]["dimensions"]
+    o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
+    w = {k: v.astype(np.float32) for k, v in o64.init_weights(1234).items()}
+    tens = orc.normalize_inputs(g["model_json"], g["reference_tensors"][0])
+    to = TorchOracle(g["model_json"], dims)
+    p_t = to.forward(tens, to.params(w)).detach().numpy()
+    p_n = o64.forward(tens, w)
+    assert np.abs(p_t - p_n).max() < 1e-12
+
+
+def test_learning_rate_schedules():
+    from ignnition_b200.train import LearningRate
+    lr = LearningRate({"type": "Adam", "schedule": {"type": "ExponentialDecay", "initial_learning_rate": 0.001,
+                                                   "decay_steps": 82000, "decay_rate": 0.8, "staircase": "True"}})
+    assert lr(0) == pytest.approx(1e-3) and lr(81999) == pytest.approx(1e-3) and lr(82000) == pytest.approx(8e-4)
+    lr = LearningRate({"type": "Adam", "schedule": {"type": "ExponentialDecay", "initial_learning_rate": 0.001,
+                                                   "decay_steps": 80000, "decay_rate": 0.6}})
+    assert lr(40000) == pytest.approx(orc.exponential_decay(40000, 1e-3, 80000, 0.6))
+    assert LearningRate({"type": "Adam", "learning_rate": 0.01})(5) == 0.01
