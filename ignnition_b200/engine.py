@@ -285,7 +285,7 @@ class Engine:
                         g.t["pos_src_" + p.key], g.t["pos_col_" + p.key], g.num[p.dst], total)
                 if self.sort_by_length and g.num[p.dst] > 0:
                     g.order[p.key] = ops.length_order(g.steps[p.key][0])
-                return g
+        return g
 
     def prepare(self, samples_or_batch, labels=None, training: bool = False, check: bool = False) -> DeviceGraph:
         batch = samples_or_batch if isinstance(samples_or_batch, Batch) else self.assemble(samples_or_batch, labels)
