@@ -283,14 +283,26 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
 
 }  // namespace
 
+// tensor-core path (dense_tc.cu)
+bool ign_dense_tc_supported(int k, int n);
+size_t ign_dense_tc_ws(int k, int n);
+int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                        float* y, float* pre_act, void* ws, cudaStream_t st);
+
+extern "C" size_t ign_dense_ws_bytes(int k, int n) {
+  return (k > 0 && n > 0 && ign_dense_tc_supported(k, n)) ? ign_dense_tc_ws(k, n) : 0;
+}
+
 extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
-                         float* y, float* pre_act, void* stream) {
+                         float* y, float* pre_act, void* ws, size_t ws_bytes, void* stream) {
   IGN_REQUIRE(m >= 0 && k > 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: dense: bad shape");
   IGN_REQUIRE(act >= IGN_ACT_LINEAR && act <= IGN_ACT_LEAKY_RELU, IGN_ERR_INVALID,
               "IGNNITION: dense: unknown activation %d", act);
   if (m == 0) return IGN_OK;
   IGN_REQUIRE(x && w && y, IGN_ERR_INVALID, "IGNNITION: dense: null pointer");
   cudaStream_t st = ign_stream(stream);
+  if (ws && ign_dense_tc_supported(k, n) && ws_bytes >= ign_dense_tc_ws(k, n) && m >= 128)
+    return ign_dense_tc_launch(x, m, k, w, bias, n, act, y, pre_act, ws, st);
   if (n <= 8) {
     dense_small_n_kernel<8><<<(unsigned)ign_cdiv(m * 32, 256), 256, 0, st>>>(x, m, k, w, bias, n, act, y, pre_act);
     IGN_CHECK_LAUNCH("dense_small_n");

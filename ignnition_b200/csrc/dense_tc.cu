@@ -1,0 +1,262 @@
+// Dense layer on the 5th-generation tensor cores (tcgen05 + TMEM), fp32 in / fp32 out, sm_100a.
+//
+// y[M,N] = act(x[M,K] W[K,N] + b) for the readout / message / update MLPs of the generated model
+// (reference code/utils/auxilary_classes.py:918-975, called at code/utils/generate_model.py:468,
+// :600, :624).  The reference computes in fp32 and the parity bar is 1e-5 relative, so the GEMM
+// runs as 3xTF32: every fp32 operand is split into hi (top 19 bits, exact as TF32) and
+// lo = x - hi, and  D = A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulates in fp32 in TMEM
+// (the dropped lo*lo term is ~2^-22 relative).
+//
+// Layout: one CTA owns a 128-row tile of x and all N <= 256 output columns; the accumulator is
+// 128 TMEM lanes x N columns.  K is walked in chunks of 32 floats (= one 128-byte swizzle row):
+//   * W is split and laid out ONCE per call by dense_tc_prep into the exact shared-memory image
+//     of each chunk ([N rows][32 k] K-major, SWIZZLE_128B, hi image then lo image), so the main
+//     kernel fetches B chunks with plain 16-byte cp.async;
+//   * the x chunk is loaded with coalesced float4 loads, split in registers and stored into the
+//     swizzled A_hi / A_lo images;
+//   * one elected thread issues 12 tcgen05.mma (kind::tf32, M=128, N, K=8) per chunk and commits
+//     to the stage's mbarrier; two shared-memory stages let the loads of chunk c+1 overlap the
+//     MMAs of chunk c;
+//   * epilogue: 8 warps read the accumulator with tcgen05.ld (32 lanes x 16 columns), add the
+//     bias, apply the activation and write 64-byte row segments.
+// Shapes outside (K % 32 == 0, N % 16 == 0, 16 <= N <= 256) use the fp32 CUDA-core path (dense.cu).
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_M = 128;
+constexpr int TC_KC = 32;                       // floats per K chunk = 128 bytes per row
+constexpr int A_IMG = TC_M * 128;               // bytes of one A image (hi or lo) of a chunk
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of float (row r, k) inside a [rows][32] K-major SWIZZLE_128B image
+__host__ __device__ __forceinline__ int sw128_off(int r, int k) {
+  return r * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4;
+}
+
+// W[K,N] -> per chunk c: [hi image: N rows x 128 B][lo image]  (the shared-memory layout of B)
+__global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * N) return;
+  const int k = i / N, n = i % N;
+  const float v = w[i];
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const float lo = v - hi;
+  const int c = k / TC_KC, kk = k % TC_KC;
+  char* base = reinterpret_cast<char*>(img) + (size_t)c * (2 * N * 128);
+  *reinterpret_cast<float*>(base + sw128_off(n, kk)) = hi;
+  *reinterpret_cast<float*>(base + N * 128 + sw128_off(n, kk)) = lo;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __restrict__ x, int64_t M, int K,
+                                                                 const float* __restrict__ wimg,
+                                                                 const float* __restrict__ bias, int N, int act,
+                                                                 float* __restrict__ y, float* __restrict__ pre,
+                                                                 int tmem_cols) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve-up (1024-byte aligned images): stage s: A_hi | A_lo | B_hi | B_lo
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_img = N * 128;
+  const int stage_bytes = 2 * A_IMG + 2 * b_img;
+  __shared__ uint64_t bar_stage[2];
+  __shared__ uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar_stage[0], 1);
+    mbar_init(&bar_stage[1], 1);
+    mbar_init(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t idesc = umma_idesc(N);
+  const int nchunks = K / TC_KC;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  uint32_t use[2] = {0, 0};        // how many times each stage has been committed
+  uint32_t acc_uses = 0;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t m0 = tile * TC_M;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1;
+      unsigned char* st = smem + s * stage_bytes;
+      // the MMAs that last read this stage must have completed
+      if (use[s] > 0) mbar_wait(&bar_stage[s], (use[s] - 1) & 1);
+      // B chunk: straight copy of the prepared image (hi + lo)
+      {
+        const char* src = reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * b_img);
+        unsigned char* dst = st + 2 * A_IMG;
+        for (int i = tid * 16; i < 2 * b_img; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
+        cp_async_commit();
+      }
+      // A chunk: 128 rows x 32 floats, split into hi / lo, swizzled store
+      {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = tid + j * TC_THREADS;        // 0..1023 : (row, 16-byte column)
+          const int r = idx >> 3, c4 = idx & 7;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + r < M) v = ldg_f4(x + (m0 + r) * K + c * TC_KC + c4 * 4);
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+          hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+          hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+          hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+          const int off = r * 128 + ((c4 ^ (r & 7)) << 4);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + A_IMG + off) = lo;
+        }
+      }
+      cp_async_wait<0>();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG;
+        const uint32_t b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + b_img;
+#pragma unroll
+        for (int kk = 0; kk < TC_KC / 8; ++kk) {
+          const uint32_t ko = kk * 32;                 // 8 tf32 = 32 bytes along K inside the swizzle row
+          const uint32_t first = (c == 0 && kk == 0) ? 0u : 1u;
+          umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, first);
+          umma_tf32(tmem_d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
+          umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+        }
+        umma_commit(&bar_stage[s]);
+        if (c == nchunks - 1) umma_commit(&bar_acc);
+      }
+      use[s] += 1;
+    }
+    // epilogue: accumulator -> registers -> bias / activation -> global
+    mbar_wait(&bar_acc, acc_uses & 1);
+    acc_uses += 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int64_t row = m0 + q * 32 + lane;
+      const int ncol_half = N / 2;
+      for (int cb = 0; cb < ncol_half; cb += 16) {
+        const int col = half * ncol_half + cb;
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+        if (row < M) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += bias ? __ldg(bias + col + i) : 0.0f;
+          if (pre) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) st_f4(pre + row * N + col + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = act_fwd(act, v[i]);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) st_f4(y + row * N + col + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                 // accumulator drained before the next tile's MMAs
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)tmem_cols));
+  }
+}
+
+}  // namespace
+
+// true when the tensor-core path is built for this shape
+bool ign_dense_tc_supported(int k, int n) { return k % TC_KC == 0 && k >= TC_KC && n % 32 == 0 && n >= 32 && n <= 256; }
+
+size_t ign_dense_tc_ws(int k, int n) { return (size_t)(k / TC_KC) * 2 * n * 128; }
+
+int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                        float* y, float* pre_act, void* ws, cudaStream_t st) {
+  float* img = reinterpret_cast<float*>(ws);
+  dense_tc_prep_kernel<<<(unsigned)ign_cdiv((int64_t)k * n, 256), 256, 0, st>>>(w, k, n, img);
+  IGN_CHECK_LAUNCH("dense_tc_prep");
+  const size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * n * 128);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    IGN_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int cols = 32;
+  while (cols < n) cols <<= 1;
+  int sms = IGN_NUM_SMS, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ign_cdiv(m, TC_M);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  dense_tc_kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols);
+  IGN_CHECK_LAUNCH("dense_tc");
+  return IGN_OK;
+}

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) gru_seq_kernel(const int* __restrict_
 // ---------------------------------------------------------------------------------------------
 // MODE 0: x = segment sum over CSR (fused aggregation); MODE 1: x given as dense rows
 template <int FI, int U, int MODE>
-__global__ void __launch_bounds__(THREADS) gru_cell_kernel(const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(THREADS, (U <= 32 && FI <= 32) ? 2 : 1) gru_cell_kernel(const int* __restrict__ rowptr,
                                                            const int* __restrict__ col,
                                                            const float* __restrict__ src,   // states (MODE 0) / x (MODE 1)
                                                            const float* __restrict__ h, int64_t num_dst,

@@ -168,13 +168,21 @@ def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rk
     return out
 
 
-def dense(x, w, bias, act: int, out=None, pre_act=None):
+def dense(x, w, bias, act: int, out=None, pre_act=None, tensor_cores: bool = True):
+    """y = act(x w + b).  With ``tensor_cores`` the layer runs as 3xTF32 on tcgen05 when the shape is
+    built for it (a workspace for the split / swizzled weight image is passed), else fp32 FMA."""
     lib = _lib.load()
     m, k = x.shape
     n = w.shape[1]
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device=x.device)
-    _lib.check(lib.ign_dense(_f(x), m, k, _f(w), _f(bias), n, act, _f(out), _f(pre_act), _stream()), "dense")
+    ws, nbytes = None, 0
+    if tensor_cores:
+        nbytes = lib.ign_dense_ws_bytes(k, n)
+        if nbytes:
+            ws = _workspace(nbytes, x.device)
+    _lib.check(lib.ign_dense(_f(x), m, k, _f(w), _f(bias), n, act, _f(out), _f(pre_act),
+                             ws.data_ptr() if ws is not None else None, nbytes, _stream()), "dense")
     return out
 
 

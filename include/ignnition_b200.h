@@ -151,9 +151,13 @@ int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, const int32_t
 
 /* Dense layer y = act(x W + b): Feed_forward_Layer (auxilary_classes.py:800-866), used by the
  * message MLP (generate_model.py:448-473), the FF update (:594-600) and the readout (:607-629).
- * bias nullable.  pre_act (nullable) receives x W + b (saved for the backward pass). */
+ * bias nullable.  pre_act (nullable) receives x W + b (saved for the backward pass).
+ * When ws holds at least ign_dense_ws_bytes(k, n) > 0 bytes the layer runs on the tcgen05 tensor
+ * cores as 3xTF32 (fp32-accurate split products, fp32 accumulation in TMEM); otherwise, or for
+ * shapes the tensor-core path is not built for (ign_dense_ws_bytes == 0), on the fp32 CUDA cores. */
+size_t ign_dense_ws_bytes(int k, int n);
 int ign_dense(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
-              float* y, float* pre_act, void* stream);
+              float* y, float* pre_act, void* ws, size_t ws_bytes, void* stream);
 
 /* Row-wise concatenation of up to 4 blocks, each optionally gathered by an index:
  * tf.concat([hs_source, hs_dest, edge_params], axis=1) after tf.gather (generate_model.py:432-465)

@@ -265,16 +265,21 @@ def test_gru_seq_interleave_step_table(golden):
 
 
 # ------------------------------------------------------------------ dense layers
+@pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("m,k,n,act", [(1, 32, 256, "selu"), (1000, 32, 256, "selu"), (777, 256, 256, "relu"),
-                                       (5000, 256, 1, None), (130, 65, 20, "tanh"), (300, 7, 3, "sigmoid")])
-def test_dense(m, k, n, act):
+                                       (5000, 256, 1, None), (130, 65, 20, "tanh"), (300, 7, 3, "sigmoid"),
+                                       (128, 32, 32, None), (40000, 64, 96, "selu"), (2049, 256, 128, "tanh")])
+def test_dense(m, k, n, act, tensor_cores):
+    """tensor_cores=True: 3xTF32 on tcgen05 where the shape is built (K % 32 == 0, N % 32 == 0, M >= 128),
+    else the fp32 CUDA-core kernel; both must meet the fp32 parity bar."""
     from ignnition_b200 import ops
     rng = np.random.RandomState(m + k + n)
     x = rng.randn(m, k).astype(np.float32)
     w = (rng.randn(k, n) / np.sqrt(k)).astype(np.float32)
     b = rng.uniform(-0.1, 0.1, n).astype(np.float32)
     pre = torch.empty(m, n, device="cuda")
-    got = ops.dense(dev(x), dev(w), dev(b), ops.ACTIVATIONS[act], pre_act=pre).cpu().numpy()
+    got = ops.dense(dev(x), dev(w), dev(b), ops.ACTIVATIONS[act], pre_act=pre,
+                    tensor_cores=tensor_cores).cpu().numpy()
     z = x.astype(np.float64) @ w.astype(np.float64) + b
     assert rel_err(pre.cpu().numpy(), z) < RTOL
     assert rel_err(got, orc.activation(act, z)) < RTOL
