@@ -25,6 +25,7 @@ SIGNATURES = {
     "ign_version": (_int, []),
     "ign_last_error": (_int, [C.c_char_p, _sz]),
     "ign_launch_count": (_i64, []),
+    "ign_set_tensor_cores": (_int, [_int]),
     "ign_csr_build_ws_bytes": (_sz, [_i64, _i64]),
     "ign_csr_build": (_int, [_p, _p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_length_order_ws_bytes": (_sz, [_i64]),

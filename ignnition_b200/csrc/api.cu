@@ -29,3 +29,10 @@ extern "C" int ign_last_error(char* buf, size_t n) {
 static std::atomic<long long> g_launches{0};
 void ign_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" int64_t ign_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
+
+// process-wide switch between the tcgen05 (3xTF32) kernels and their fp32 CUDA-core twins
+static std::atomic<int> g_tensor_cores{1};
+bool ign_tensor_cores_enabled() { return g_tensor_cores.load(std::memory_order_relaxed) != 0; }
+extern "C" int ign_set_tensor_cores(int enable) {
+  return g_tensor_cores.exchange(enable ? 1 : 0, std::memory_order_relaxed);
+}

@@ -104,3 +104,16 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// 3xTF32 operand split: hi = round-to-nearest TF32 of v, lo = round-to-nearest TF32 of (v - hi).
+// |v - (hi + lo)| <= 2^-24 |v|, i.e. the pair carries v to fp32 precision; the tensor core reads
+// both exactly (their low 13 mantissa bits are zero).
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
+  hi = tf32_rna(v);
+  lo = tf32_rna(v - hi);
+}

@@ -283,6 +283,7 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
 
 }  // namespace
 
+bool ign_tensor_cores_enabled();
 // tensor-core path (dense_tc.cu)
 bool ign_dense_tc_supported(int k, int n);
 size_t ign_dense_tc_ws(int k, int n);
@@ -301,7 +302,8 @@ extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const
   if (m == 0) return IGN_OK;
   IGN_REQUIRE(x && w && y, IGN_ERR_INVALID, "IGNNITION: dense: null pointer");
   cudaStream_t st = ign_stream(stream);
-  if (ws && ign_dense_tc_supported(k, n) && ws_bytes >= ign_dense_tc_ws(k, n) && m >= 128)
+  if (ws && ign_tensor_cores_enabled() && ign_dense_tc_supported(k, n) && ws_bytes >= ign_dense_tc_ws(k, n) &&
+      m >= 128)
     return ign_dense_tc_launch(x, m, k, w, bias, n, act, y, pre_act, ws, st);
   if (n <= 8) {
     dense_small_n_kernel<8><<<(unsigned)ign_cdiv(m * 32, 256), 256, 0, st>>>(x, m, k, w, bias, n, act, y, pre_act);

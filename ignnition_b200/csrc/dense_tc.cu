@@ -3,8 +3,8 @@
 // y[M,N] = act(x[M,K] W[K,N] + b) for the readout / message / update MLPs of the generated model
 // (reference code/utils/auxilary_classes.py:918-975, called at code/utils/generate_model.py:468,
 // :600, :624).  The reference computes in fp32 and the parity bar is 1e-5 relative, so the GEMM
-// runs as 3xTF32: every fp32 operand is split into hi (top 19 bits, exact as TF32) and
-// lo = x - hi, and  D = A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulates in fp32 in TMEM
+// runs as 3xTF32: every fp32 operand is split into hi = rna_tf32(x) and
+// lo = rna_tf32(x - hi) (so hi + lo carries x to 2^-24), and  D = A_hi B_hi + A_lo B_hi + A_hi B_lo  accumulates in fp32 in TMEM
 // (the dropped lo*lo term is ~2^-22 relative).
 //
 // Layout: one CTA owns a 128-row tile of x and all N <= 256 output columns; the accumulator is
@@ -100,8 +100,8 @@ __global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, 
   if (i >= K * N) return;
   const int k = i / N, n = i % N;
   const float v = w[i];
-  const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  const float lo = v - hi;
+  float hi, lo;
+  tf32_split(v, hi, lo);
   const int c = k / TC_KC, kk = k % TC_KC;
   char* base = reinterpret_cast<char*>(img) + (size_t)c * (2 * N * 128);
   *reinterpret_cast<float*>(base + sw128_off(n, kk)) = hi;
@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m0 + r < M) v = ldg_f4(x + (m0 + r) * K + c * TC_KC + c4 * 4);
           float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
-          hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
-          hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
-          hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+          tf32_split(v.x, hi.x, lo.x);
+          tf32_split(v.y, hi.y, lo.y);
+          tf32_split(v.z, hi.z, lo.z);
+          tf32_split(v.w, hi.w, lo.w);
           const int off = r * 128 + ((c4 ^ (r & 7)) << 4);
           *reinterpret_cast<float4*>(st + off) = hi;
           *reinterpret_cast<float4*>(st + A_IMG + off) = lo;

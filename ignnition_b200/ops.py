@@ -21,6 +21,11 @@ ACTIVATIONS = {None: 0, "None": 0, "linear": 0, "relu": 1, "selu": 2, "sigmoid":
                "elu": 5, "softplus": 6, "leaky_relu": 7}
 
 
+def set_tensor_cores(enable: bool) -> bool:
+    """Process-wide switch between the tcgen05 (3xTF32) kernels and their fp32 CUDA-core twins."""
+    return bool(_lib.load().ign_set_tensor_cores(1 if enable else 0))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 

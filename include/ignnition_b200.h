@@ -60,6 +60,10 @@ int ign_version(void);
 int ign_last_error(char* buf, size_t n);
 /* number of CUDA kernels this library has launched in the process so far (for bench.py's gpu_launches) */
 int64_t ign_launch_count(void);
+/* Process-wide switch: 1 (default) = kernels that have a tcgen05 3xTF32 variant use it (ign_gru_seq
+ * for 32-wide states, ign_dense when given a workspace); 0 = always the fp32 CUDA-core twins.
+ * Returns the previous setting.  Both variants meet the 1e-5 fp32 parity bar. */
+int ign_set_tensor_cores(int enable);
 
 /* ---------------------------------------------------------------------------------------------
  * Adjacency -> CSR by destination.

@@ -196,10 +196,24 @@ def test_agg_gru_cell(fi, u):
     assert rel_err(got, want) < RTOL
 
 
+@pytest.fixture
+def fp32_kernels():
+    """Run a test on the fp32 CUDA-core twins instead of the tcgen05 (3xTF32) kernels."""
+    from ignnition_b200 import ops
+    prev = ops.set_tensor_cores(False)
+    yield
+    ops.set_tensor_cores(prev)
+
+
+def test_gru_seq_fp32_twin(fp32_kernels):
+    test_gru_seq_vs_masked_rnn(32, 32, True)
+
+
 @pytest.mark.parametrize("fi,u", [(32, 32), (64, 64)])
 @pytest.mark.parametrize("use_order", [False, True])
 def test_gru_seq_vs_masked_rnn(fi, u, use_order):
-    """ordered aggregation: CSR walk == keras RNN over the dense right-padded tensor + mask."""
+    """ordered aggregation: CSR walk == keras RNN over the dense right-padded tensor + mask.
+    (32, 32) runs the tcgen05 3xTF32 kernel by default."""
     from ignnition_b200 import ops
     rng = np.random.RandomState(fi + 7 * use_order)
     n_dst, n_src, max_len = 1500, 400, 7
@@ -227,6 +241,18 @@ def test_gru_seq_vs_masked_rnn(fi, u, use_order):
     # saved per-step states: last step of every non-empty destination equals its new state
     hs = h_seq.cpu().numpy()
     assert np.array_equal(hs[r[1:][nz] - 1], got[nz])
+    # a long-sequence case (link-like fan-in) through the same kernel
+    lens2 = rng.randint(1, 60, 300)
+    dst2 = np.repeat(np.arange(300), lens2)
+    seq2 = np.concatenate([np.arange(l) for l in lens2])
+    src2 = rng.randint(0, n_src, len(dst2))
+    r2, c2, _ = orc.csr_from_edges(src2, dst2, seq2, 300)
+    got2 = ops.gru_seq(dev(r2, torch.int32), dev(c2, torch.int32), None, [dev(states)], dev(h0[:300]), dev(K), dev(R),
+                       dev(b)).cpu().numpy()
+    pad2 = np.zeros((300, 59, fi), np.float64)
+    pad2[dst2, seq2] = states[src2]
+    want2 = orc.masked_rnn_last(cell, pad2, h0[:300].astype(np.float64), lens2)
+    assert rel_err(got2, want2) < RTOL
 
 
 def test_gru_seq_interleave_step_table(golden):
