@@ -375,6 +375,16 @@ __global__ void steps_keys_kernel(const int* __restrict__ steps, int64_t n, int 
   keys[i] = (e >= 0 && (e >> IGN_STEP_SRC_SHIFT) == src_id) ? (e & IGN_STEP_ROW_MASK) : n_rows;
 }
 
+// per sorted position i: (destination, first step, number of steps, first step entry)
+__global__ void seq_meta_kernel(const int* __restrict__ steps_rowptr, const int* __restrict__ steps,
+                                const int* __restrict__ order, int64_t n, int4* __restrict__ meta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = order ? order[i] : (int)i;
+  const int lo = steps_rowptr[d], len = steps_rowptr[d + 1] - lo;
+  meta[i] = make_int4(d, lo, len, len > 0 ? steps[lo] : IGN_STEP_ZERO);
+}
+
 inline unsigned grid1d(int64_t n, int threads = 256) { return (unsigned)ign_cdiv(n > 0 ? n : 1, threads); }
 
 }  // namespace
@@ -519,5 +529,16 @@ extern "C" int ign_steps_keys(const int32_t* steps, int64_t n, int src_id, int64
   IGN_REQUIRE(steps && keys, IGN_ERR_INVALID, "IGNNITION: steps_keys: null pointer");
   steps_keys_kernel<<<grid1d(n), 256, 0, ign_stream(stream)>>>(steps, n, src_id, (int)n_rows, keys);
   IGN_CHECK_LAUNCH("steps_keys");
+  return IGN_OK;
+}
+
+extern "C" int ign_seq_meta(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* order, int64_t num_dst,
+                            int32_t* meta, void* stream) {
+  IGN_REQUIRE(num_dst >= 0, IGN_ERR_INVALID, "IGNNITION: seq_meta: negative size");
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(steps_rowptr && steps && meta, IGN_ERR_INVALID, "IGNNITION: seq_meta: null pointer");
+  seq_meta_kernel<<<grid1d(num_dst), 256, 0, ign_stream(stream)>>>(steps_rowptr, steps, order, num_dst,
+                                                                    reinterpret_cast<int4*>(meta));
+  IGN_CHECK_LAUNCH("seq_meta");
   return IGN_OK;
 }

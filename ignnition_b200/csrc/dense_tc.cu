@@ -77,16 +77,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// activation in the epilogue: SELU / ELU use ex2.approx with a Taylor branch near zero instead of
+// expm1f (the epilogue is instruction-bound); everything else as act_fwd
+__device__ __forceinline__ float fast_expm1(float x) {       // x <= 0
+  const float p = x * (1.0f + x * (0.5f + x * (0.16666667f + x * (0.041666668f + x * 0.0083333338f))));
+  return x > -0.125f ? p : __expf(x) - 1.0f;
+}
+__device__ __forceinline__ float act_epi(int act, float x) {
+  if (act == IGN_ACT_SELU) return x > 0.0f ? IGN_SELU_SCALE * x : (IGN_SELU_SCALE * IGN_SELU_ALPHA) * fast_expm1(x);
+  if (act == IGN_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == IGN_ACT_LINEAR) return x;
+  if (act == IGN_ACT_ELU) return x > 0.0f ? x : fast_expm1(x);
+  return act_fwd(act, x);
 }
 
 // byte offset of float (row r, k) inside a [rows][32] K-major SWIZZLE_128B image
@@ -121,6 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
   __shared__ uint64_t bar_stage[2];
   __shared__ uint64_t bar_acc;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -134,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
                  "r"((uint32_t)tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  if (tid < N) s_bias[tid] = bias ? bias[tid] : 0.0f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -204,21 +216,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
       const int q = warp & 3, half = warp >> 2;
       const int64_t row = m0 + q * 32 + lane;
       const int ncol_half = N / 2;
-      for (int cb = 0; cb < ncol_half; cb += 16) {
+      for (int cb = 0; cb < ncol_half; cb += 32) {       // two 16-column TMEM loads in flight per wait
         const int col = half * ncol_half + cb;
-        float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+        const bool second = cb + 16 < ncol_half;
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nowait(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col, ra);
+        if (second) tmem_ld16_nowait(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(col + 16), rb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row < M) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += bias ? __ldg(bias + col + i) : 0.0f;
-          if (pre) {
+          for (int hblk = 0; hblk < 2; ++hblk) {
+            if (hblk == 1 && !second) break;
+            const int c0 = col + hblk * 16;
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) st_f4(pre + row * N + col + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + i);
+              float4 v;
+              v.x = __uint_as_float(hblk ? rb[i] : ra[i]) + bv.x;
+              v.y = __uint_as_float(hblk ? rb[i + 1] : ra[i + 1]) + bv.y;
+              v.z = __uint_as_float(hblk ? rb[i + 2] : ra[i + 2]) + bv.z;
+              v.w = __uint_as_float(hblk ? rb[i + 3] : ra[i + 3]) + bv.w;
+              if (pre) st_f4(pre + row * N + c0 + i, v);
+              v.x = act_epi(act, v.x); v.y = act_epi(act, v.y); v.z = act_epi(act, v.z); v.w = act_epi(act, v.w);
+              st_f4(y + row * N + c0 + i, v);
+            }
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = act_fwd(act, v[i]);
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) st_f4(y + row * N + col + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
       }
     }

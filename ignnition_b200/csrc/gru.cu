@@ -325,13 +325,14 @@ int check_gru_args(const char* who, int f_in, int units, const float* k, const f
 // tensor-core variant (gru_seq_tc.cu), 32-wide messages and states
 int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* order, int n_src,
                           const float* const* srcs, const float* h0, int64_t num_dst, const float* kernel,
-                          const float* rkernel, const float* bias, float* out, float* h_seq, cudaStream_t st);
+                          const float* rkernel, const float* bias, float* out, float* h_seq, const int* meta,
+                          cudaStream_t st);
 bool ign_tensor_cores_enabled();
 
 extern "C" int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* order, int n_src,
                            const float* const* srcs, int f_in, const float* h0, int64_t num_dst, int units,
                            const float* kernel, const float* recurrent_kernel, const float* bias, float* out,
-                           float* h_seq, void* stream) {
+                           float* h_seq, const int32_t* meta, void* stream) {
   IGN_REQUIRE(num_dst >= 0, IGN_ERR_INVALID, "IGNNITION: gru_seq: negative size");
   IGN_REQUIRE(n_src >= 1 && n_src <= IGN_MAX_SOURCES && srcs, IGN_ERR_INVALID,
               "IGNNITION: gru_seq: between 1 and %d sources", IGN_MAX_SOURCES);
@@ -347,7 +348,7 @@ extern "C" int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, co
   cudaStream_t st = ign_stream(stream);
   if (f_in == 32 && units == 32 && ign_tensor_cores_enabled())
     return ign_gru_seq_tc_launch(steps_rowptr, steps, order, n_src, srcs, h0, num_dst, kernel, recurrent_kernel,
-                                 bias, out, h_seq, st);
+                                 bias, out, h_seq, meta, st);
   IGN_GRU_DISPATCH(f_in, units, return (launch_gru_seq<FI, U>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
                                                                recurrent_kernel, bias, out, h_seq, st)));
   return IGN_ERR_UNSUPPORTED;

@@ -108,6 +108,7 @@ struct Slot {
   int d;        // destination of this thread's row (-1: none)
   int lo;       // first step
   int len;      // number of steps
+  int entry;    // step-table entry of the next message to gather (one step of lookahead)
   float h[16];  // running state, this thread's 16 units
 };
 
@@ -115,7 +116,8 @@ template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     const int* __restrict__ steps_rowptr, const int* __restrict__ steps, const int* __restrict__ order, SrcPtrs srcs,
     const float* __restrict__ h0, int64_t num_dst, const float* __restrict__ kernel, const float* __restrict__ rkernel,
-    const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ h_seq) {
+    const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ h_seq,
+    const int4* __restrict__ meta) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* bx_hi = smem;
@@ -176,17 +178,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
   const int64_t npairs = (ntiles + 1) / 2;
   uint32_t uses[2] = {0, 0};
 
-  // gather this thread's 64 bytes of the message of step t (row's entry), returns 4 float4
-  auto load_x = [&](const Slot& s, int t, float4 (&x)[4]) {
+  // gather this thread's 64 bytes of the message of step t (its entry was fetched one step earlier,
+  // so the row load does not wait on an index load), then fetch the entry of step t + 1
+  auto load_x = [&](Slot& s, int t, float4 (&x)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < s.len) {
-      const int entry = __ldg(steps + s.lo + t);
-      if (entry >= 0) {
-        const float* p = pick_src(srcs, entry >> IGN_STEP_SRC_SHIFT) + (int64_t)(entry & IGN_STEP_ROW_MASK) * U + u0;
+    const int entry = s.entry;
+    s.entry = (t + 1 < s.len) ? __ldg(steps + s.lo + t + 1) : IGN_STEP_ZERO;
+    if (t < s.len && entry >= 0) {
+      const float* p = pick_src(srcs, entry >> IGN_STEP_SRC_SHIFT) + (int64_t)(entry & IGN_STEP_ROW_MASK) * U + u0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = ldg_f4(p + 4 * j);
-      }
+      for (int j = 0; j < 4; ++j) x[j] = ldg_f4(p + 4 * j);
     }
   };
   auto store_x = [&](int slot, const float4 (&x)[4]) {
@@ -226,6 +228,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     umma_commit(&bar[slot]);
   };
 
+  // walk plan of this thread's rows in the NEXT pair of tiles (prefetched one pair ahead)
+  int4 nmeta[2];
+  auto fetch_meta = [&](int64_t pr) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int64_t didx = (pr * 2 + s) * ROWS + row;
+      nmeta[s] = make_int4(-1, 0, 0, IGN_STEP_ZERO);
+      if (pr < npairs && didx < num_dst) {
+        if (meta) {
+          nmeta[s] = __ldg(meta + didx);
+        } else {
+          const int d = order ? __ldg(order + didx) : (int)didx;
+          const int lo = __ldg(steps_rowptr + d), len = __ldg(steps_rowptr + d + 1) - lo;
+          nmeta[s] = make_int4(d, lo, len, len > 0 ? __ldg(steps + lo) : IGN_STEP_ZERO);
+        }
+      }
+    }
+  };
+  fetch_meta(blockIdx.x);
+
   for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
     Slot sl[2];
     if (tid < 2) s_maxlen[tid] = 0;
@@ -233,13 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     // ---- tile set-up: meta, h0 -> registers + image, x_0 -> image
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const int64_t didx = (pair * 2 + s) * ROWS + row;
-      sl[s].d = -1; sl[s].lo = 0; sl[s].len = 0;
-      if (didx < num_dst) {
-        sl[s].d = order ? __ldg(order + didx) : (int)didx;
-        sl[s].lo = __ldg(steps_rowptr + sl[s].d);
-        sl[s].len = __ldg(steps_rowptr + sl[s].d + 1) - sl[s].lo;
-      }
+      sl[s].d = nmeta[s].x; sl[s].lo = nmeta[s].y; sl[s].len = nmeta[s].z; sl[s].entry = nmeta[s].w;
 #pragma unroll
       for (int j = 0; j < 16; ++j) sl[s].h[j] = 0.f;
       if (sl[s].d >= 0) {
@@ -255,6 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
       store_x(s, x);
       store_h(s, sl[s]);
     }
+    fetch_meta(pair + gridDim.x);                        // lands while this pair is being walked
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const int maxlen0 = s_maxlen[0], maxlen1 = s_maxlen[1];
@@ -344,7 +361,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
 
 int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* order, int n_src,
                           const float* const* srcs, const float* h0, int64_t num_dst, const float* kernel,
-                          const float* rkernel, const float* bias, float* out, float* h_seq, cudaStream_t st) {
+                          const float* rkernel, const float* bias, float* out, float* h_seq, const int* meta,
+                          cudaStream_t st) {
   SrcPtrs sp;
   for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
   const size_t smem = 1024 + 4 * (size_t)BIMG + 2 * (size_t)SLOT_BYTES;
@@ -361,10 +379,12 @@ int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* 
   const int grid = (int)(npairs < sms ? npairs : sms);
   if (fast)
     gru_seq_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
-                                                             rkernel, bias, out, h_seq);
+                                                             rkernel, bias, out, h_seq,
+                                                             reinterpret_cast<const int4*>(meta));
   else
     gru_seq_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
-                                                              rkernel, bias, out, h_seq);
+                                                              rkernel, bias, out, h_seq,
+                                                              reinterpret_cast<const int4*>(meta));
   IGN_CHECK_LAUNCH("gru_seq_tc");
   return IGN_OK;
 }

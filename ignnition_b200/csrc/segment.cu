@@ -111,18 +111,34 @@ struct FeatList {
   int n;
 };
 
-__global__ void init_state_kernel(FeatList f, int64_t n, int hidden, float* __restrict__ state) {
+__device__ __forceinline__ float init_state_value(const FeatList& f, int64_t row, int c) {
+  for (int k = 0; k < f.n; ++k) {
+    if (c < f.size[k]) return f.ptr[k][row * f.size[k] + c];
+    c -= f.size[k];
+  }
+  return 0.0f;
+}
+// one thread per 4 consecutive columns (hidden % 4 == 0), 16-byte stores
+__global__ void init_state_kernel(FeatList f, int64_t n, int hidden, int total_feat, float* __restrict__ state) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = hidden / 4;
+  if (i >= n * q) return;
+  const int64_t row = i / q;
+  const int c = (int)(i - row * q) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < total_feat) {
+    v.x = init_state_value(f, row, c);
+    v.y = init_state_value(f, row, c + 1);
+    v.z = init_state_value(f, row, c + 2);
+    v.w = init_state_value(f, row, c + 3);
+  }
+  st_f4(state + row * hidden + c, v);
+}
+__global__ void init_state_scalar_kernel(FeatList f, int64_t n, int hidden, float* __restrict__ state) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * hidden) return;
   const int64_t row = i / hidden;
-  int c = (int)(i - row * hidden);
-  float v = 0.0f;
-  for (int k = 0; k < f.n; ++k) {
-    if (c < f.size[k]) { v = f.ptr[k][row * f.size[k] + c]; break; }
-    c -= f.size[k];
-    if (k == f.n - 1) v = 0.0f;
-  }
-  state[i] = v;
+  state[i] = init_state_value(f, row, (int)(i - row * hidden));
 }
 
 struct ConcatParts {
@@ -195,7 +211,11 @@ extern "C" int ign_init_state(int n_feat, const float* const* feats, const int32
   }
   IGN_REQUIRE(total <= hidden, IGN_ERR_INVALID,
               "IGNNITION: init_state: features (%d) wider than the hidden state (%d)", total, hidden);
-  init_state_kernel<<<(unsigned)ign_cdiv(n * hidden, 256), 256, 0, ign_stream(stream)>>>(f, n, hidden, state);
+  if (hidden % 4 == 0)
+    init_state_kernel<<<(unsigned)ign_cdiv(n * (hidden / 4), 256), 256, 0, ign_stream(stream)>>>(f, n, hidden, total,
+                                                                                                 state);
+  else
+    init_state_scalar_kernel<<<(unsigned)ign_cdiv(n * hidden, 256), 256, 0, ign_stream(stream)>>>(f, n, hidden, state);
   IGN_CHECK_LAUNCH("init_state");
   return IGN_OK;
 }

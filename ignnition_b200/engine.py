@@ -39,6 +39,7 @@ class DeviceGraph:
         self.csr_t: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}   # transposed (by source), training
         self.steps: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.order: Dict[str, torch.Tensor] = {}
+        self.meta: Dict[str, torch.Tensor] = {}
         self.status: Dict[str, torch.Tensor] = {}
         self.h2d_bytes = 0
 
@@ -285,6 +286,8 @@ class Engine:
                         g.t["pos_src_" + p.key], g.t["pos_col_" + p.key], g.num[p.dst], total)
                 if self.sort_by_length and g.num[p.dst] > 0:
                     g.order[p.key] = ops.length_order(g.steps[p.key][0])
+                if g.num[p.dst] > 0:
+                    g.meta[p.key] = ops.seq_meta(g.steps[p.key][0], g.steps[p.key][1], g.order.get(p.key))
         return g
 
     def prepare(self, samples_or_batch, labels=None, training: bool = False, check: bool = False) -> DeviceGraph:
@@ -349,7 +352,8 @@ class Engine:
             h_seq = None
             if tape is not None:
                 h_seq = torch.empty(steps.numel(), h.shape[1], dtype=torch.float32, device=self.device)
-            ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq)
+            ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq,
+                        meta=g.meta.get(p.key))
             if tape is not None:
                 tape.append(("seq_gru", p, [state[a.src] for a in p.adjs], h, h_seq))
             return out

@@ -160,8 +160,16 @@ def agg_gru_cell(rowptr, col, src_states, h_dst, kernel, rkernel, bias, out=None
     return out
 
 
+def seq_meta(steps_rowptr, steps, order) -> torch.Tensor:
+    lib = _lib.load()
+    n = steps_rowptr.numel() - 1
+    meta = torch.empty(max(n, 1), 4, dtype=torch.int32, device=steps_rowptr.device)
+    _lib.check(lib.ign_seq_meta(_i(steps_rowptr), _i(steps), _i(order), n, _i(meta), _stream()), "seq_meta")
+    return meta
+
+
 def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rkernel, bias, out=None,
-            h_seq=None):
+            h_seq=None, meta=None):
     lib = _lib.load()
     n, units = h0.shape
     if out is None:
@@ -169,7 +177,7 @@ def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rk
     sp = _ptr_array(srcs, torch.float32)
     _lib.check(lib.ign_gru_seq(_i(steps_rowptr), _i(steps), _i(order), len(srcs), sp, srcs[0].shape[1],
                                _f(h0), n, units, _f(kernel), _f(rkernel), _f(bias), _f(out), _f(h_seq),
-                               _stream()), "gru_seq")
+                               _i(meta), _stream()), "gru_seq")
     return out
 
 

@@ -93,6 +93,12 @@ size_t ign_length_order_ws_bytes(int64_t num_dst);
 int ign_length_order(const int32_t* rowptr, int64_t num_dst, int32_t* order, void* ws,
                      size_t ws_bytes, void* stream);
 
+/* Walk plan of ign_gru_seq: meta[4*i .. 4*i+3] = (destination, first step, number of steps, first
+ * step entry) of the i-th destination in `order` (identity when order == NULL).  One 16-byte load per
+ * destination replaces the order -> rowptr -> steps pointer chase at the start of every tile. */
+int ign_seq_meta(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* order,
+                 int64_t num_dst, int32_t* meta, void* stream);
+
 /* Step table for multi-source ordered / interleave aggregation (generate_model.py:507-543,
  * auxilary_classes.py:421-440).  For destination d of sample s = dst_sample[d], position t of the
  * reference's padded sequence is source pos_src[pos_off[s]+t], column pos_col[pos_off[s]+t];
@@ -151,7 +157,8 @@ int ign_agg_gru_cell(const int32_t* rowptr, const int32_t* col, const float* src
 int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* order, int n_src,
                 const float* const* srcs, int f_in, const float* h0, int64_t num_dst, int units,
                 const float* kernel, const float* recurrent_kernel, const float* bias, float* out,
-                float* h_seq, void* stream);
+                float* h_seq, const int32_t* meta /* nullable: output of ign_seq_meta for this order */,
+                void* stream);
 
 /* Dense layer y = act(x W + b): Feed_forward_Layer (auxilary_classes.py:800-866), used by the
  * message MLP (generate_model.py:448-473), the FF update (:594-600) and the readout (:607-629).
