@@ -249,6 +249,31 @@ def run_ours(args):
     # dominant kernel: per-kernel CUDA-event timing of one more pass (same stream, after the timed region)
     kern = profile_kernels(eng, graph, torch, args.steps)
 
+    # parity of the timed configuration: first 2 samples of this rank's batch vs the CPU oracle
+    parity = None
+    if rank == 0:
+        pred = eng.forward(graph).cpu().numpy().reshape(n_samples, -1)
+        o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
+        w64 = o64.init_weights(1234)
+        worst = 0.0
+        for k in range(2):
+            t = dict(base)
+            for name, ent, size in eng.features:
+                n_e = int(base["num_" + ent])
+                t[name] = batch.arrays["feat_" + name][k * n_e * size:(k + 1) * n_e * size]
+            want = o64.forward(t, {a: b.astype(np.float32) for a, b in w64.items()}).reshape(-1)
+            worst = max(worst, float(np.abs(pred[k] - want).max() / np.abs(want).max()))
+        parity = {"max_rel_err_vs_fp64_oracle": worst, "samples_checked": 2, "tolerance": 1e-5}
+
+    also = None
+    if rank == 0 and not args.no_also:
+        del graph
+        torch.cuda.empty_cache()
+        try:
+            also = [run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "uniform")]
+        except Exception as exc:   # e.g. not enough free memory on a shared box: report, do not hide
+            also = [{"workload": "mpnn_uniform", "error": str(exc)[:200]}]
+
     if rank == 0:
         peaks = {}
         try:
@@ -286,7 +311,15 @@ def run_ours(args):
                              "sample": "%d samples of %s through oracle/ignnition_oracle.py (NumPy fp32, "
                                        "per-sample loop), %.1f s" % (cpu_n, args.workload, cpu_dt)},
             "clocks": clocks,
+            "parity": parity,
+            "also": also,
         }
+        if also and "segment_reduce" in also[0]:
+            sr = also[0]["segment_reduce"]
+            line["roofline_gather_segment"] = {
+                "bound": "hbm", "kernel": "ign_segment_reduce (config 5: 10M nodes / 200M edges, F=64)",
+                "achieved": sr["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": sr["achieved_gbs"] / hbm_peak,
+                "traffic": None}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -356,6 +389,101 @@ def profile_kernels(eng, graph, torch, reps):
     return out
 
 
+# ------------------------------------------------------------------------------ config 5: big graph
+def mpnn_model_json(hidden=64, iterations=8):
+    """generic sum-aggregation MPNN (BASELINE config 5) in the reference's JSON keywords"""
+    return {
+        "entities": [{"name": "node", "hidden_state_dimension": hidden,
+                      "features": [{"name": "x", "normalization": "None"}]}],
+        "message_passing": {"num_iterations": iterations, "stages": [{"stage_name": "s", "stage_mp": [{
+            "destination_entity": "node",
+            "source_entities": [{"name": "node", "adj_vector": "adj", "message": [{"type": "direct_assignation"}]}],
+            "aggregation": {"type": "sum"},
+            "update": {"type": "recurrent_neural_network", "nn_name": "rec"}}]}]},
+        "readout": [{"type": "predict", "input": ["node"], "label": "y", "nn_name": "ro"}],
+        "neural_networks": [
+            {"nn_name": "rec", "nn_type": "recurrent_neural_network", "recurrent_type": "GRU"},
+            {"nn_name": "ro", "nn_type": "feed_forward", "nn_architecture": [
+                {"type_layer": "Dense", "units": 1, "activation": "None"}]}],
+        "learning_options": {"loss": "MeanSquaredError", "optimizer": {"type": "Adam"}},
+    }
+
+
+def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="uniform"):
+    """Message-passing iterations of the generic MPNN on ONE large synthetic graph resident in HBM.
+    Returns a dict with edges/s per iteration and the roofline of the gather + segment-sum kernel."""
+    from ignnition_b200 import Engine, ModelDescription, ops
+    from ignnition_b200.engine import DeviceGraph
+    md = ModelDescription(mpnn_model_json(hidden), {"x": hidden, "adj": 0})
+    eng = Engine(md, device=dev, seed=0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    src = torch.randint(0, n_nodes, (n_edges,), device=dev, dtype=torch.int32, generator=gen)
+    if variant == "uniform":
+        dst = torch.randint(0, n_nodes, (n_edges,), device=dev, dtype=torch.int32, generator=gen)
+    else:                                   # skewed in-degrees (power-law-like): dst = floor(N * u^3)
+        u = torch.rand(n_edges, device=dev, generator=gen)
+        dst = (u * u * u * n_nodes).to(torch.int32).clamp_(0, n_nodes - 1)
+    g = DeviceGraph()
+    g.num = {"node": n_nodes}
+    g.n_samples = 1
+    g.t = {"feat_x": torch.randn(n_nodes, hidden, device=dev, generator=gen), "src_adj": src, "dst_adj": dst}
+    # adjacency build: no seq in a raw edge list -> stable radix sort by destination (timed separately)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rowptr, col, _, _ = ops.csr_build(dst, src, None, n_nodes, ops.CSR_SORT)
+    e1.record()
+    torch.cuda.synchronize()
+    csr_ms = e0.elapsed_time(e1)
+    g.csr["adj"] = (rowptr, col, None)
+    del src, dst
+    g.t.pop("src_adj"); g.t.pop("dst_adj")
+    state = eng.initial_states(g)
+    K = eng.param("node_update/kernel"); R = eng.param("node_update/recurrent_kernel"); B = eng.param("node_update/bias")
+    agg = torch.empty(n_nodes, hidden, device=dev)
+    h = state["node"]
+    h2 = torch.empty_like(h)
+
+    def iteration():
+        nonlocal h, h2
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, h, out=agg)
+        ops.gru_cell(agg, h, K, R, B, out=h2)
+        h, h2 = h2, h
+
+    for _ in range(max(warmup, 3)):
+        iteration()
+    torch.cuda.synchronize()
+    seg_ms, cell_ms = [], []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(steps):
+        ev[3 * k].record()
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, h, out=agg)
+        ev[3 * k + 1].record()
+        ops.gru_cell(agg, h, K, R, B, out=h2)
+        ev[3 * k + 2].record()
+        h, h2 = h2, h
+    t1.record()
+    torch.cuda.synchronize()
+    total_ms = t0.elapsed_time(t1)
+    for k in range(steps):
+        seg_ms.append(ev[3 * k].elapsed_time(ev[3 * k + 1]))
+        cell_ms.append(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]))
+    seg_bytes = n_edges * (4 + 4 * hidden) + n_nodes * (4 * hidden + 4)
+    seg_avg = float(np.mean(seg_ms))
+    return {"workload": "mpnn_%s_n%d_e%d_h%d" % (variant, n_nodes, n_edges, hidden),
+            "mp_edges_per_s_per_iteration": n_edges * steps / (total_ms / 1e3),
+            "ms_per_iteration": total_ms / steps, "iterations_timed": steps,
+            "csr_build_ms": csr_ms, "csr_build_edges_per_s": n_edges / (csr_ms / 1e3),
+            "segment_reduce": {"avg_launch_ms": seg_avg, "algorithmic_bytes_per_launch": seg_bytes,
+                               "achieved_gbs": seg_bytes / (seg_avg / 1e3) / 1e9},
+            "gru_cell": {"avg_launch_ms": float(np.mean(cell_ms)),
+                         "algorithmic_bytes_per_launch": 3 * 4 * hidden * n_nodes,
+                         "tflops_fp32": 2.0 * n_nodes * 3 * hidden * 2 * hidden / (np.mean(cell_ms) / 1e3) / 1e12}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,6 +493,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--cpu-samples", type=int, default=48, help="samples of the bounded CPU-baseline leg")
+    ap.add_argument("--no-also", action="store_true", help="skip the config-5 big-graph leg of the default run")
+    ap.add_argument("--mpnn-nodes", type=int, default=10_000_000)
+    ap.add_argument("--mpnn-edges", type=int, default=200_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
