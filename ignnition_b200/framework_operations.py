@@ -1,0 +1,270 @@
+"""The reference's public entry points on the B200 engine: ``create_model``, ``train_and_evaluate``,
+``predict``, ``debug`` (reference ``code/utils/framework_operations.py:42-268``, ``readme.md:77-95``).
+
+Same files drive it: ``./train_options.ini`` ([PATHS] train_dataset, eval_dataset, predict_dataset,
+warm_start_path, json_path, model_dir; [TRAINING_OPTIONS] batch_size, train_steps, shuffle_*,
+eval_samples, save_checkpoints_secs, keep_checkpoint_max, throttle_secs, execute_gpu -- reference
+``code/train_options.ini:1-50``), the same ``model_description.json`` and the user's ``main.py`` with
+its normalisation functions (looked up by name, ``generate_model.py:68,77``).  This is host glue:
+the tf.estimator / tf.data plumbing of the reference is NOT rebuilt; checkpoints are ``.npz`` files
+of the named variables (Keras layouts), written every ``save_checkpoints_secs``.
+"""
+
+from __future__ import annotations
+
+import configparser
+import glob
+import itertools
+import os
+import sys
+import time
+from typing import Callable, Dict, Iterator, List, Optional
+
+import numpy as np
+
+from .generator import find_dataset_dimensions, read_dataset, sample_to_tensors
+from .model_description import ModelDescription
+
+CONFIG: Optional[configparser.ConfigParser] = None
+
+
+def _log(msg: str):
+    print("IGNNITION: " + msg, file=sys.stderr, flush=True)
+
+
+def load_config(path: str = "./train_options.ini") -> configparser.ConfigParser:
+    """ExtendedInterpolation ini, read relative to the CWD like the reference (:34-36)."""
+    global CONFIG
+    cfg = configparser.ConfigParser()
+    cfg._interpolation = configparser.ExtendedInterpolation()
+    if not cfg.read(path):
+        raise RuntimeError("IGNNITION: the configuration file %s was not found" % path)
+    CONFIG = cfg
+    return cfg
+
+
+def _cfg() -> configparser.ConfigParser:
+    return CONFIG if CONFIG is not None else load_config()
+
+
+def create_model(config_path: Optional[str] = None) -> ModelDescription:
+    cfg = load_config(config_path) if config_path else _cfg()
+    dims = find_dataset_dimensions(cfg["PATHS"]["train_dataset"])
+    return ModelDescription(cfg["PATHS"]["json_path"], dims)
+
+
+# ------------------------------------------------------------------ normalisation (generate_model.py:46-86)
+def _resolve(name: Optional[str], namespace: Optional[dict]) -> Optional[Callable]:
+    if name is None or str(name) == "None":
+        return None
+    for ns in (namespace, getattr(sys.modules.get("__main__"), "__dict__", None),
+               getattr(sys.modules.get("main"), "__dict__", None)):
+        if ns and name in ns and callable(ns[name]):
+            return ns[name]
+    return None
+
+
+def normalize(model: ModelDescription, x: dict, y=None, namespace: Optional[dict] = None):
+    for f in model.get_all_features():
+        fn = _resolve(f.normalization, namespace)
+        v = np.asarray(x[f.name], dtype=np.float32)
+        if str(f.normalization) != "None":
+            if fn is None:
+                raise RuntimeError("IGNNITION: The normalization function %s is not defined in the main file."
+                                   % f.normalization)
+            v = np.asarray(fn(v, f.name), dtype=np.float32)
+        x[f.name] = v
+    if y is None:
+        return x
+    out_name, out_norm, _ = model.get_output_info()
+    y = np.asarray(y, dtype=np.float32)
+    if str(out_norm) != "None":
+        fn = _resolve(out_norm, namespace)
+        if fn is None:
+            raise RuntimeError("IGNNITION: The normalization function %s is not defined in the main file." % out_norm)
+        y = np.asarray(fn(y, out_name), dtype=np.float32)
+    return x, y
+
+
+def samples_of(model: ModelDescription, directory: str, training: bool, shuffle: bool = False,
+               namespace: Optional[dict] = None, repeat: bool = False) -> Iterator:
+    """The reference's input_fn as a Python iterator of normalised tensor dicts (+ labels)."""
+    feats = [f.name for f in model.get_all_features()]
+    out_name, _, _ = model.get_output_info()
+    adj, inter = model.get_adjecency_info(), model.get_interleave_tensors()
+    extra = [a for a in model.get_additional_input_names() if a not in feats]
+    while True:
+        n = 0
+        for sample in read_dataset(directory, shuffle):
+            n += 1
+            if training:
+                x, y = sample_to_tensors(sample, feats, out_name, adj, inter, extra, True)
+                yield normalize(model, x, y, namespace)
+            else:
+                yield normalize(model, sample_to_tensors(sample, feats, out_name, adj, inter, extra, False),
+                                namespace=namespace)
+        if not repeat or n == 0:
+            return
+
+
+def eval_metrics(labels: np.ndarray, preds: np.ndarray) -> Dict[str, float]:
+    """label/prediction mean, MAE, MRE, R^2 (generate_model.py:770-787, 201-216)."""
+    y, p = labels.astype(np.float64).reshape(-1), preds.astype(np.float64).reshape(-1)
+    return {"label/mean": float(y.mean()), "prediction/mean": float(p.mean()),
+            "mae": float(np.abs(y - p).mean()), "mre": float((np.abs(y - p) / np.abs(y)).mean()),
+            "r-squared": float(1.0 - ((y - p) ** 2).sum() / ((y - y.mean()) ** 2).sum())}
+
+
+def save_checkpoint(engine, trainer, model_dir: str, keep_max: int) -> str:
+    os.makedirs(model_dir, exist_ok=True)
+    path = os.path.join(model_dir, "model.ckpt-%d.npz" % trainer.step)
+    np.savez(path, __step__=np.int64(trainer.step), **engine.get_weights())
+    old = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.npz")), key=os.path.getmtime)
+    for p in old[:-keep_max] if keep_max > 0 else []:
+        os.remove(p)
+    return path
+
+
+def load_checkpoint(engine, path: str) -> int:
+    """Warm start: every stored kernel / recurrent_kernel / bias variable (framework_operations.py:126-129)."""
+    if os.path.isdir(path):
+        files = sorted(glob.glob(os.path.join(path, "model.ckpt-*.npz")), key=os.path.getmtime)
+        if not files:
+            raise RuntimeError("IGNNITION: no checkpoint found in " + path)
+        path = files[-1]
+    data = np.load(path)
+    engine.set_weights({k: data[k] for k in data.files if k != "__step__"})
+    return int(data["__step__"]) if "__step__" in data.files else 0
+
+
+def evaluate(model: ModelDescription, engine, directory: str, n_samples: int, shuffle: bool = False,
+             namespace: Optional[dict] = None) -> Dict[str, float]:
+    out_name, _, out_denorm = model.get_output_info()
+    ys, ps = [], []
+    it = samples_of(model, directory, True, shuffle, namespace)
+    while True:
+        chunk = list(itertools.islice(it, min(64, n_samples - len(ys)) if n_samples else 64))
+        if not chunk:
+            break
+        pred = engine.forward(engine.prepare([c[0] for c in chunk])).cpu().numpy().reshape(-1)
+        ps.append(pred)
+        ys += [c[1].reshape(-1) for c in chunk]
+        if n_samples and len(ys) >= n_samples:
+            break
+    y, p = np.concatenate(ys), np.concatenate(ps)
+    loss = float(np.mean((y - p) ** 2))
+    fn = _resolve(out_denorm, namespace)
+    if fn is not None:
+        y, p = np.asarray(fn(y, out_name)), np.asarray(fn(p, out_name))
+    else:
+        _log("A denormalization function for output %s was not defined. The output (and statistics) will "
+             "use the normalized values." % out_name)
+    return dict(eval_metrics(y, p), loss=loss)
+
+
+def train_and_evaluate(model: ModelDescription, namespace: Optional[dict] = None, max_steps: Optional[int] = None,
+                       engine=None):
+    """tf.estimator.train_and_evaluate of the reference (:108-166) on Engine + Trainer."""
+    import datetime
+
+    import torch
+
+    from .engine import Engine
+    from .parallel import rank_world
+    from .train import Trainer
+    cfg = _cfg()
+    opt = cfg["TRAINING_OPTIONS"]
+    rank, world, local = rank_world()
+    _log("Starting the training and evaluation process...")
+    torch.cuda.set_device(local)
+    engine = engine or Engine(model, device=torch.device("cuda", local))
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl", device_id=engine.device)
+    trainer = Trainer(engine, world_size=world)
+    if cfg.has_option("PATHS", "warm_start_path") and cfg["PATHS"]["warm_start_path"].strip():
+        load_checkpoint(engine, cfg["PATHS"]["warm_start_path"])
+    model_dir = os.path.join(cfg["PATHS"]["model_dir"], "experiment_" + str(datetime.datetime.now()).replace(" ", "_"))
+    batch = int(opt["batch_size"])
+    steps = int(opt["train_steps"]) if max_steps is None else max_steps
+    keep = int(opt.get("keep_checkpoint_max", 20))
+    ckpt_secs, eval_secs = float(opt.get("save_checkpoints_secs", 300)), float(opt.get("throttle_secs", 300))
+    it = samples_of(model, cfg["PATHS"]["train_dataset"], True, opt.get("shuffle_train_samples", "True") == "True",
+                    namespace, repeat=True)
+    # every rank reads the same stream and keeps its slice of each global batch
+    t_ckpt = t_eval = time.time()
+    history = []
+    for step in range(steps):
+        chunk = list(itertools.islice(it, batch * world))
+        if not chunk:
+            break
+        mine = chunk[rank::world] if world > 1 else chunk
+        n_glob = sum(c[1].size for c in chunk)
+        graph = engine.prepare([c[0] for c in mine], labels=[c[1] for c in mine], training=True)
+        trainer.train_step(graph, global_n=n_glob)
+        if step % 10 == 0:                        # LoggingTensorHook every 10 iterations (:820-824)
+            l = trainer.losses()
+            history.append((step, l["loss"]))
+            if rank == 0:
+                _log("step %d  Loss = %.6g, Regularization loss = %.6g, Total loss = %.6g"
+                     % (step, l["loss"], l["regularization_loss"], l["total_loss"]))
+        now = time.time()
+        if rank == 0 and (now - t_ckpt >= ckpt_secs or step == steps - 1):
+            save_checkpoint(engine, trainer, model_dir, keep)
+            t_ckpt = now
+        if rank == 0 and (now - t_eval >= eval_secs or step == steps - 1) and cfg["PATHS"].get("eval_dataset", "").strip():
+            m = evaluate(model, engine, cfg["PATHS"]["eval_dataset"], int(opt.get("eval_samples", 100)),
+                         opt.get("shuffle_eval_samples", "False") == "True", namespace)
+            _log("evaluation at step %d: %s" % (step, ", ".join("%s = %.6g" % kv for kv in m.items())))
+            t_eval = now
+    return engine, trainer, history
+
+
+def predict(model: ModelDescription, namespace: Optional[dict] = None, engine=None) -> List[np.ndarray]:
+    """One pass over predict_dataset with the warm-start weights (:169-236); the reference's loop never
+    terminates on a finite dataset, this one stops at the end."""
+    import torch
+
+    from .engine import Engine
+    cfg = _cfg()
+    _log("Starting to make the predictions...")
+    if not cfg.has_option("PATHS", "warm_start_path"):
+        _log("The path of the model to use for the predictions is unspecified. Please add a field "
+             "warm_start_path in the train_options.ini with the corresponding path to the model you want to restore.")
+        sys.exit(0)
+    if not cfg.has_option("PATHS", "predict_dataset"):
+        _log("The path of dataset to use for the prediction is unspecified. Please add a field predict_dataset "
+             "in the train_config.ini file with the corresponding path to the dataset you want to predict.")
+        sys.exit(0)
+    engine = engine or Engine(model, device=torch.device("cuda", torch.cuda.current_device()))
+    load_checkpoint(engine, cfg["PATHS"]["warm_start_path"])
+    out_name, _, out_denorm = model.get_output_info()
+    fn = _resolve(out_denorm, namespace)
+    if fn is None:
+        _log("A denormalization function for output %s was not defined. The output will be normalized." % out_name)
+    result = []
+    for x in samples_of(model, cfg["PATHS"]["predict_dataset"], False, False, namespace):
+        p = engine(x).cpu().numpy().reshape(-1)
+        result.append(np.asarray(fn(p, out_name)) if fn is not None else p)
+    return result
+
+
+def debug(model: ModelDescription, engine=None) -> str:
+    """The reference dumps the TF graph for TensorBoard (:239-268); here: the compiled kernel plan."""
+    import torch
+
+    from .engine import Engine
+    cfg = _cfg()
+    engine = engine or Engine(model, device=torch.device("cuda", torch.cuda.current_device()))
+    lines = ["ignnition_b200 kernel plan", "T = %d" % engine.T]
+    for stage in engine.plans:
+        for p in stage:
+            lines.append("  %s <- %s : %s (%s)" % (p.dst, [a.src for a in p.adjs], p.kind, p.mp.aggregation.type))
+    for name, (off, shape) in engine.param_table.items():
+        lines.append("  var %-60s %s @%d" % (name, shape, off))
+    text = "\n".join(lines)
+    out = os.path.join(cfg["PATHS"].get("debug_dir", "../"), "debug_model")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "plan.txt"), "w") as fh:
+        fh.write(text + "\n")
+    _log("The debug model has been generated.")
+    return text
