@@ -266,11 +266,11 @@ def run_ours(args):
         parity = {"max_rel_err_vs_fp64_oracle": worst, "samples_checked": 2, "tolerance": 1e-5}
 
     also = None
-    if rank == 0 and not args.no_also:
+    if not args.no_also:                 # every rank takes part: the big graph is partitioned across them
         del graph
         torch.cuda.empty_cache()
         try:
-            also = [run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "uniform")]
+            also = [run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "uniform", rank, world)]
         except Exception as exc:   # e.g. not enough free memory on a shared box: report, do not hide
             also = [{"workload": "mpnn_uniform", "error": str(exc)[:200]}]
 
@@ -409,79 +409,99 @@ def mpnn_model_json(hidden=64, iterations=8):
     }
 
 
-def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="uniform"):
-    """Message-passing iterations of the generic MPNN on ONE large synthetic graph resident in HBM.
-    Returns a dict with edges/s per iteration and the roofline of the gather + segment-sum kernel."""
+def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="uniform", rank=0, world=1):
+    """Message-passing iterations of the generic MPNN on ONE large synthetic graph (strong scaling).
+
+    The graph is partitioned by destination-node range: rank r owns the rows
+    [r N/W, (r+1) N/W) of the CSR (all their in-edges) and the authoritative state of those nodes.
+    Every iteration all-gathers the owned states over NCCL / NVLink into the full source-state
+    buffer, then runs gather + segment-sum and the GRU update on the owned rows.  world == 1: no
+    collective.  Returns edges/s per iteration (whole graph, max over ranks) and the roofline of the
+    gather + segment-sum kernel."""
+    import torch.distributed as dist
     from ignnition_b200 import Engine, ModelDescription, ops
     from ignnition_b200.engine import DeviceGraph
     md = ModelDescription(mpnn_model_json(hidden), {"x": hidden, "adj": 0})
     eng = Engine(md, device=dev, seed=0)
+    own = n_nodes // world
+    n_nodes = own * world
+    e_own = n_edges // world
     gen = torch.Generator(device=dev)
-    gen.manual_seed(0)
-    src = torch.randint(0, n_nodes, (n_edges,), device=dev, dtype=torch.int32, generator=gen)
+    gen.manual_seed(1000 + rank)
+    src = torch.randint(0, n_nodes, (e_own,), device=dev, dtype=torch.int32, generator=gen)
     if variant == "uniform":
-        dst = torch.randint(0, n_nodes, (n_edges,), device=dev, dtype=torch.int32, generator=gen)
-    else:                                   # skewed in-degrees (power-law-like): dst = floor(N * u^3)
-        u = torch.rand(n_edges, device=dev, generator=gen)
-        dst = (u * u * u * n_nodes).to(torch.int32).clamp_(0, n_nodes - 1)
+        dst = torch.randint(0, own, (e_own,), device=dev, dtype=torch.int32, generator=gen)   # local row ids
+    else:                                   # skewed in-degrees (power-law-like): dst = floor(own * u^3)
+        u = torch.rand(e_own, device=dev, generator=gen)
+        dst = (u * u * u * own).to(torch.int32).clamp_(0, own - 1)
     g = DeviceGraph()
-    g.num = {"node": n_nodes}
+    g.num = {"node": own}
     g.n_samples = 1
-    g.t = {"feat_x": torch.randn(n_nodes, hidden, device=dev, generator=gen), "src_adj": src, "dst_adj": dst}
+    g.t = {"feat_x": torch.randn(own, hidden, device=dev, generator=gen)}
     # adjacency build: no seq in a raw edge list -> stable radix sort by destination (timed separately)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    rowptr, col, _, _ = ops.csr_build(dst, src, None, n_nodes, ops.CSR_SORT)
+    rowptr, col, _, _ = ops.csr_build(dst, src, None, own, ops.CSR_SORT)
     e1.record()
     torch.cuda.synchronize()
     csr_ms = e0.elapsed_time(e1)
-    g.csr["adj"] = (rowptr, col, None)
     del src, dst
-    g.t.pop("src_adj"); g.t.pop("dst_adj")
-    state = eng.initial_states(g)
+    h = eng.initial_states(g)["node"]                     # owned states
+    full = torch.empty(n_nodes, hidden, device=dev) if world > 1 else None
     K = eng.param("node_update/kernel"); R = eng.param("node_update/recurrent_kernel"); B = eng.param("node_update/bias")
-    agg = torch.empty(n_nodes, hidden, device=dev)
-    h = state["node"]
+    agg = torch.empty(own, hidden, device=dev)
     h2 = torch.empty_like(h)
 
-    def iteration():
-        nonlocal h, h2
-        ops.segment_reduce(ops.OP_SUM, rowptr, col, h, out=agg)
-        ops.gru_cell(agg, h, K, R, B, out=h2)
-        h, h2 = h2, h
+    def gather_states():
+        if world > 1:
+            dist.all_gather_into_tensor(full, h)          # NCCL over NVLink: every rank's owned states
+            return full
+        return h
 
     for _ in range(max(warmup, 3)):
-        iteration()
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, gather_states(), out=agg)
+        ops.gru_cell(agg, h, K, R, B, out=h2)
+        h, h2 = h2, h
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
-    seg_ms, cell_ms = [], []
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for k in range(steps):
-        ev[3 * k].record()
-        ops.segment_reduce(ops.OP_SUM, rowptr, col, h, out=agg)
-        ev[3 * k + 1].record()
+        ev[4 * k].record()
+        srcs = gather_states()
+        ev[4 * k + 1].record()
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, srcs, out=agg)
+        ev[4 * k + 2].record()
         ops.gru_cell(agg, h, K, R, B, out=h2)
-        ev[3 * k + 2].record()
+        ev[4 * k + 3].record()
         h, h2 = h2, h
     t1.record()
     torch.cuda.synchronize()
-    total_ms = t0.elapsed_time(t1)
-    for k in range(steps):
-        seg_ms.append(ev[3 * k].elapsed_time(ev[3 * k + 1]))
-        cell_ms.append(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]))
-    seg_bytes = n_edges * (4 + 4 * hidden) + n_nodes * (4 * hidden + 4)
-    seg_avg = float(np.mean(seg_ms))
-    return {"workload": "mpnn_%s_n%d_e%d_h%d" % (variant, n_nodes, n_edges, hidden),
-            "mp_edges_per_s_per_iteration": n_edges * steps / (total_ms / 1e3),
-            "ms_per_iteration": total_ms / steps, "iterations_timed": steps,
-            "csr_build_ms": csr_ms, "csr_build_edges_per_s": n_edges / (csr_ms / 1e3),
-            "segment_reduce": {"avg_launch_ms": seg_avg, "algorithmic_bytes_per_launch": seg_bytes,
-                               "achieved_gbs": seg_bytes / (seg_avg / 1e3) / 1e9},
-            "gru_cell": {"avg_launch_ms": float(np.mean(cell_ms)),
-                         "algorithmic_bytes_per_launch": 3 * 4 * hidden * n_nodes,
-                         "tflops_fp32": 2.0 * n_nodes * 3 * hidden * 2 * hidden / (np.mean(cell_ms) / 1e3) / 1e12}}
+    t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ag_ms = float(np.mean([ev[4 * k].elapsed_time(ev[4 * k + 1]) for k in range(steps)]))
+    seg_avg = float(np.mean([ev[4 * k + 1].elapsed_time(ev[4 * k + 2]) for k in range(steps)]))
+    cell_avg = float(np.mean([ev[4 * k + 2].elapsed_time(ev[4 * k + 3]) for k in range(steps)]))
+    seg_bytes = e_own * (4 + 4 * hidden) + own * (4 * hidden + 4)
+    out = {"workload": "mpnn_%s_n%d_e%d_h%d" % (variant, n_nodes, e_own * world, hidden), "n_gpus": world,
+           "partition": "destination-node range, %d nodes / %d edges per GPU" % (own, e_own),
+           "mp_edges_per_s_per_iteration": e_own * world * steps / (total_ms / 1e3),
+           "ms_per_iteration": total_ms / steps, "iterations_timed": steps,
+           "csr_build_ms": csr_ms, "csr_build_edges_per_s": e_own / (csr_ms / 1e3),
+           "segment_reduce": {"avg_launch_ms": seg_avg, "algorithmic_bytes_per_launch": seg_bytes,
+                              "achieved_gbs": seg_bytes / (seg_avg / 1e3) / 1e9},
+           "gru_cell": {"avg_launch_ms": cell_avg,
+                        "tflops_fp32": 2.0 * own * 3 * hidden * 2 * hidden / (cell_avg / 1e3) / 1e12}}
+    if world > 1:
+        recv = (world - 1) * own * hidden * 4
+        out["all_gather"] = {"avg_ms": ag_ms, "bytes_received_per_gpu": recv,
+                             "achieved_gbs_per_gpu": recv / (ag_ms / 1e3) / 1e9, "nvlink_peer_peak_gbs": 770.0}
+    return out
 
 
 def main():

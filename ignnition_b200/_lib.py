@@ -35,7 +35,8 @@ SIGNATURES = {
     "ign_steps_keys": (_int, [_p, _i64, _int, _i64, _p, _p]),
     "ign_init_state": (_int, [_int, _p, _p, _i64, _int, _p, _p]),
     "ign_segment_reduce": (_int, [_int, _p, _p, _p, _int, _i64, _p, _p]),
-    "ign_gru_cell": (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p]),
+    "ign_gru_cell_ws_bytes": (_sz, [_int, _int]),
+    "ign_gru_cell": (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_agg_gru_cell": (_int, [_p, _p, _p, _int, _p, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "ign_gru_seq": (_int, [_p, _p, _p, _int, _p, _int, _p, _i64, _int, _p, _p, _p, _p, _p, _p, _p]),
     "ign_seq_meta": (_int, [_p, _p, _p, _i64, _p, _p]),

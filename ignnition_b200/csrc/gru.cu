@@ -369,14 +369,30 @@ extern "C" int ign_agg_gru_cell(const int32_t* rowptr, const int32_t* col, const
   return IGN_ERR_UNSUPPORTED;
 }
 
+// tensor-core variant (gru_cell_tc.cu)
+bool ign_gru_cell_tc_supported(int f_in, int units);
+size_t ign_gru_cell_tc_ws(int units);
+int ign_gru_cell_tc_launch(const float* x, const float* h, int64_t n, int units, const float* kernel,
+                           const float* rkernel, const float* bias, float* out, void* ws, cudaStream_t st);
+
+extern "C" size_t ign_gru_cell_ws_bytes(int f_in, int units) {
+  return ign_gru_cell_tc_supported(f_in, units) ? ign_gru_cell_tc_ws(units) : 0;
+}
+
 extern "C" int ign_gru_cell(const float* x, const float* h, int64_t n, int f_in, int units, const float* kernel,
-                            const float* recurrent_kernel, const float* bias, float* out, void* stream) {
+                            const float* recurrent_kernel, const float* bias, float* out, void* ws, size_t ws_bytes,
+                            void* stream) {
   IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: gru_cell: negative size");
   int rc = check_gru_args("gru_cell", f_in, units, kernel, recurrent_kernel, bias);
   if (rc) return rc;
   if (n == 0) return IGN_OK;
   IGN_REQUIRE(x && h && out, IGN_ERR_INVALID, "IGNNITION: gru_cell: null pointer");
   cudaStream_t st = ign_stream(stream);
+  if (ws && ign_tensor_cores_enabled() && ign_gru_cell_tc_supported(f_in, units) &&
+      ws_bytes >= ign_gru_cell_tc_ws(units) && n >= 128) {
+    IGN_REQUIRE(out != h, IGN_ERR_INVALID, "IGNNITION: gru_cell: out must not alias h on the tensor-core path");
+    return ign_gru_cell_tc_launch(x, h, n, units, kernel, recurrent_kernel, bias, out, ws, st);
+  }
   IGN_GRU_DISPATCH(f_in, units, return (launch_gru_cell<FI, U, 1>(nullptr, nullptr, x, h, n, kernel,
                                                                    recurrent_kernel, bias, out, nullptr, st)));
   return IGN_ERR_UNSUPPORTED;

@@ -1,0 +1,108 @@
+// tcgen05 / TMEM / mbarrier helpers shared by the tensor-core kernels (sm_100a only).
+//
+// Operand images are [rows][32 fp32] blocks in the canonical K-major SWIZZLE_128B layout
+// (8-row groups of 1024 bytes, 16-byte chunks XOR-swizzled by row & 7); every fp32 operand is
+// stored twice, as hi = rna_tf32(v) and lo = rna_tf32(v - hi), and every product is issued as
+// A_hi B_hi + A_lo B_hi + A_hi B_lo (3xTF32) so results keep fp32 accuracy.
+#pragma once
+
+#include "common.cuh"
+
+namespace ign_tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[128, n] (+)= A[128, 32] B[n, 32]^T as 3xTF32 over the 4 K = 8 steps of one 32-float chunk
+__device__ __forceinline__ void umma_chunk_3x(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                              uint32_t b_lo, int n, bool accumulate_first) {
+  const uint32_t idesc = umma_idesc(n);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t ko = kk * 32;                      // 8 tf32 = 32 bytes along K inside the swizzle row
+    umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), idesc, (accumulate_first || kk > 0) ? 1u : 0u);
+    umma_tf32(tmem_d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), idesc, 1u);
+    umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), idesc, 1u);
+  }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {     // one warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {        // one warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// byte offset of float (row r, k) inside a [rows][32] K-major SWIZZLE_128B image
+__host__ __device__ __forceinline__ int sw128_off(int r, int k) {
+  return r * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4;
+}
+// store 4 consecutive floats (16-byte chunk c4 of row r) as hi / lo into two swizzled images
+__device__ __forceinline__ void store_split(unsigned char* img_hi, unsigned char* img_lo, int r, int c4, float4 v) {
+  float4 hi, lo;
+  tf32_split(v.x, hi.x, lo.x);
+  tf32_split(v.y, hi.y, lo.y);
+  tf32_split(v.z, hi.z, lo.z);
+  tf32_split(v.w, hi.w, lo.w);
+  const int off = r * 128 + ((c4 ^ (r & 7)) << 4);
+  *reinterpret_cast<float4*>(img_hi + off) = hi;
+  *reinterpret_cast<float4*>(img_lo + off) = lo;
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
+
+}  // namespace ign_tc

@@ -139,13 +139,20 @@ def segment_reduce(op: int, rowptr, col, src_states, out: Optional[torch.Tensor]
     return out
 
 
-def gru_cell(x, h, kernel, rkernel, bias, out: Optional[torch.Tensor] = None):
+def gru_cell(x, h, kernel, rkernel, bias, out: Optional[torch.Tensor] = None, tensor_cores: bool = True):
+    """One GRU step.  3xTF32 on tcgen05 when built for the shape (and out is not h), else fp32 FMA."""
     lib = _lib.load()
     n, units = h.shape
     if out is None:
         out = torch.empty_like(h)
+    ws, nbytes = None, 0
+    if tensor_cores and out.data_ptr() != h.data_ptr():
+        nbytes = lib.ign_gru_cell_ws_bytes(x.shape[1], units)
+        if nbytes:
+            ws = _workspace(nbytes, x.device)
     _lib.check(lib.ign_gru_cell(_f(x), _f(h), n, x.shape[1], units, _f(kernel), _f(rkernel), _f(bias),
-                                _f(out), _stream()), "gru_cell")
+                                _f(out), ws.data_ptr() if ws is not None else None, nbytes, _stream()),
+               "gru_cell")
     return out
 
 

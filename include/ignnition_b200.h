@@ -132,10 +132,14 @@ int ign_segment_reduce(int op, const int32_t* rowptr, const int32_t* col, const 
                        int F, int64_t num_dst, float* out, void* stream);
 
 /* One GRU step for every destination, x = aggregated messages, h = old state:
- * Recurrent_Cell.perform_unsorted_update (auxilary_classes.py:752-765).  out may alias h. */
+ * Recurrent_Cell.perform_unsorted_update (auxilary_classes.py:752-765).
+ * With a workspace of ign_gru_cell_ws_bytes(f_in, units) > 0 bytes (f_in == units in {32, 64}) the gate
+ * GEMMs run as 3xTF32 on tcgen05 and out must NOT alias h; without it (ws == NULL) the fp32 CUDA-core
+ * kernel runs and out may alias h. */
+size_t ign_gru_cell_ws_bytes(int f_in, int units);
 int ign_gru_cell(const float* x, const float* h, int64_t n, int f_in, int units,
                  const float* kernel, const float* recurrent_kernel, const float* bias,
-                 float* out, void* stream);
+                 float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* Fused gather + sum aggregation + GRU update (RouteNet stage 2, Q-size step 2, config 5):
  * generate_model.py:432,490 + Sum_aggr (auxilary_classes.py:254-262) + perform_unsorted_update

@@ -161,10 +161,11 @@ def test_gru_cell(fi, u, n):
     K, R, b = gru_weights(rng, fi, u)
     x = rng.randn(n, fi).astype(np.float32)
     h = rng.randn(n, u).astype(np.float32)
-    got = ops.gru_cell(dev(x), dev(h), dev(K), dev(R), dev(b)).cpu().numpy()
     want = orc.gru_cell(x.astype(np.float64), h.astype(np.float64), K.astype(np.float64), R.astype(np.float64),
                         b.astype(np.float64))
-    assert rel_err(got, want) < RTOL
+    for tc in (True, False):          # tcgen05 3xTF32 (32 / 64 wide, n >= 128) and the fp32 twin
+        got = ops.gru_cell(dev(x), dev(h), dev(K), dev(R), dev(b), tensor_cores=tc).cpu().numpy()
+        assert rel_err(got, want) < RTOL, tc
 
 
 def test_gru_unsupported_width_fails_loudly():
