@@ -30,9 +30,10 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (golden fixture holding model json + base topology, shape, qsize, default samples per GPU)
-    "routenet_geant2_b4096": ("routenet_geant2", "geant2", False, 4096),
-    "routenet_nsfnet_b4096": ("routenet_nsfnet", "nsfnet", False, 4096),
-    "qsize_nsfnet_b4096": ("qsize_nsfnet", "nsfnet", True, 4096),
+    "routenet_geant2_b4096": ("routenet_geant2", "geant2", False, 4096),      # BASELINE config 3 (default)
+    "routenet_nsfnet_b4096": ("routenet_nsfnet", "nsfnet", False, 4096),      # config 1 shape, batched
+    "qsize_nsfnet_b4096": ("qsize_nsfnet", "nsfnet", True, 4096),             # config 2
+    "routenet_synth50_b256": ("routenet_nsfnet", "synth50", False, 256),      # config 4 shape (use with --train)
 }
 DEFAULT_WORKLOAD = "routenet_geant2_b4096"
 
@@ -40,6 +41,13 @@ DEFAULT_WORKLOAD = "routenet_geant2_b4096"
 def load_case(name):
     fixture, shape, qsize, n = WORKLOADS[name]
     g = json.load(open(os.path.join(ROOT, "tests", "golden", fixture + ".json")))
+    if shape == "synth50":            # no committed fixture: same model json, topology from the seeded generator
+        from ignnition_b200 import ModelDescription, synthetic
+        from ignnition_b200.generator import sample_to_tensors
+        md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
+        t, _ = sample_to_tensors(synthetic.routenet_sample("synth50", 0, 0), [f.name for f in md.get_all_features()],
+                                 "delay", md.get_adjecency_info(), [], [], True)
+        g = dict(g, reference_tensors=[t])
     return g, shape, qsize, n
 
 
@@ -185,14 +193,26 @@ def run_ours(args):
     from oracle import ignnition_oracle as orc   # checker-side weights only (same seeded weights as the CPU leg)
     eng.set_weights(orc.Oracle(g["model_json"], dims).init_weights(1234))
     base = g["reference_tensors"][0]
+    out_entity0 = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
     batch = assemble_tiled(base, n_samples, eng.entities, eng.features, eng.adjacencies, eng.sequences,
-                           feature_fns(qsize), seed=rank)
+                           feature_fns(qsize), seed=rank,
+                           label_fn=(lambda r, n: r.normal(-1.0, 0.5, n)) if args.train else None,
+                           label_entity=out_entity0)
     pinned = batch.pack(pin=True)
     edges_per_iter = sum(batch.n_edges[a.name] for a in eng.adjacencies)
     out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
     n_pred = batch.num[out_entity]
 
+    trainer = None
+    if args.train:
+        from ignnition_b200.train import Trainer
+        trainer = Trainer(eng, world_size=world)
+
     def step_resident(graph):
+        if trainer is not None:        # model_fn train step: forward + loss + backward + all-reduce + Adam
+            eng.build_graph(graph, training=True)
+            graph.csr_t.clear()
+            return trainer.train_step(graph, global_n=n_pred * world)
         eng.build_graph(graph)
         return eng.forward(graph)
 
@@ -200,8 +220,7 @@ def run_ours(args):
 
     def step_e2e():
         graph = eng.upload(batch, pinned)
-        eng.build_graph(graph)
-        pred = eng.forward(graph)
+        pred = step_resident(graph)
         host_pred.copy_(pred, non_blocking=True)
         return graph
 
@@ -247,11 +266,11 @@ def run_ours(args):
     ms_e2e = float(t.item())
 
     # dominant kernel: per-kernel CUDA-event timing of one more pass (same stream, after the timed region)
-    kern = profile_kernels(eng, graph, torch, args.steps)
+    kern = profile_kernels(eng, graph, torch, args.steps, trainer, n_pred * world)
 
     # parity of the timed configuration: first 2 samples of this rank's batch vs the CPU oracle
     parity = None
-    if rank == 0:
+    if rank == 0 and not args.train:
         pred = eng.forward(graph).cpu().numpy().reshape(n_samples, -1)
         o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
         w64 = o64.init_weights(1234)
@@ -266,7 +285,7 @@ def run_ours(args):
         parity = {"max_rel_err_vs_fp64_oracle": worst, "samples_checked": 2, "tolerance": 1e-5}
 
     also = None
-    if not args.no_also:                 # every rank takes part: the big graph is partitioned across them
+    if not args.no_also and not args.train:   # every rank takes part: the big graph is partitioned across them
         del graph
         torch.cuda.empty_cache()
         try:
@@ -290,7 +309,8 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         cpu_val, cpu_n, cpu_dt = cpu_samples_per_s(args.workload, args.cpu_samples, 1)
         line = {
-            "metric": "routenet_samples_per_s", "value": n_samples * world * args.steps / (ms / 1e3),
+            "metric": "routenet_train_samples_per_s" if args.train else "routenet_samples_per_s",
+            "value": n_samples * world * args.steps / (ms / 1e3),
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -298,7 +318,8 @@ def run_ours(args):
                        "paths_per_gpu": batch.num.get("path"), "links_per_gpu": batch.num.get("link"),
                        "mp_edges_per_iteration_per_gpu": edges_per_iter,
                        "timing": "inputs+states per step exceed L2 (no flush needed)",
-                       "step": "device CSR build + T message-passing iterations + readout"},
+                       "step": ("device CSR build (+ transposed) + forward + MSE/l2 + backward + NCCL all-reduce + Adam"
+                                if args.train else "device CSR build + T message-passing iterations + readout")},
             "mp_edges_per_s": edges_per_iter * eng.T * world * args.steps / (ms / 1e3),
             "e2e": {"value": n_samples * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(pinned[0].numel()), "d2h_bytes_per_step": int(host_pred.numel() * 4),
@@ -325,7 +346,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def profile_kernels(eng, graph, torch, reps):
+def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
     """CUDA-event time of every launch class in one forward (events on the launching stream)."""
     from ignnition_b200 import ops
     records = {}
@@ -366,13 +387,20 @@ def profile_kernels(eng, graph, torch, reps):
     def b_gru_cell(x, h, *a, **kw):
         return 4 * (x.numel() + 2 * h.numel())
 
+    zero = lambda *a, **kw: 0
     for name, fn in (("gru_seq", b_gru_seq), ("agg_gru_cell", b_agg), ("segment_reduce", b_seg),
-                     ("dense", b_dense), ("csr_build", b_csr), ("gru_cell", b_gru_cell)):
+                     ("dense", b_dense), ("csr_build", b_csr), ("gru_cell", b_gru_cell),
+                     ("gru_seq_bwd", zero), ("gru_cell_bwd", zero), ("dense_bwd", zero)):
         wrap(name, fn)
     try:
         for _ in range(max(1, min(reps, 3))):
-            eng.build_graph(graph)
-            eng.forward(graph)
+            if trainer is not None:
+                eng.build_graph(graph, training=True)
+                graph.csr_t.clear()
+                trainer.train_step(graph, global_n=n_glob)
+            else:
+                eng.build_graph(graph)
+                eng.forward(graph)
         torch.cuda.synchronize()
     finally:
         for name, fn in orig.items():
@@ -514,6 +542,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--cpu-samples", type=int, default=48, help="samples of the bounded CPU-baseline leg")
     ap.add_argument("--no-also", action="store_true", help="skip the config-5 big-graph leg of the default run")
+    ap.add_argument("--train", action="store_true",
+                    help="time the train step (forward + loss + backward + gradient all-reduce + Adam) instead of inference")
     ap.add_argument("--mpnn-nodes", type=int, default=10_000_000)
     ap.add_argument("--mpnn-edges", type=int, default=200_000_000)
     args = ap.parse_args()
