@@ -288,7 +288,8 @@ bool ign_tensor_cores_enabled();
 bool ign_dense_tc_supported(int k, int n);
 size_t ign_dense_tc_ws(int k, int n);
 int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
-                        float* y, float* pre_act, void* ws, cudaStream_t st);
+                        float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w = nullptr,
+                        const float* head_b = nullptr, float* head_out = nullptr);
 
 extern "C" size_t ign_dense_ws_bytes(int k, int n) {
   return (k > 0 && n > 0 && ign_dense_tc_supported(k, n)) ? ign_dense_tc_ws(k, n) : 0;
@@ -314,6 +315,18 @@ extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const
   gemm_kernel<false, false, 0><<<grid, GEMM_THREADS, 0, st>>>(x, w, y, m, n, k, bias, act, pre_act, 0);
   IGN_CHECK_LAUNCH("dense");
   return IGN_OK;
+}
+
+extern "C" int ign_dense_head(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                              const float* head_w, const float* head_b, float* out, void* ws, size_t ws_bytes,
+                              void* stream) {
+  IGN_REQUIRE(m >= 0 && k > 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: dense_head: bad shape");
+  if (m == 0) return IGN_OK;
+  IGN_REQUIRE(x && w && head_w && out && ws, IGN_ERR_INVALID, "IGNNITION: dense_head: null pointer");
+  IGN_REQUIRE(ign_dense_tc_supported(k, n) && ws_bytes >= ign_dense_tc_ws(k, n) && m >= 128, IGN_ERR_UNSUPPORTED,
+              "IGNNITION: dense_head: built for the tensor-core shapes only (K %% 32 == 0, N %% 32 == 0, M >= 128)");
+  return ign_dense_tc_launch(x, m, k, w, bias, n, act, nullptr, nullptr, ws, ign_stream(stream), head_w,
+                             head_b, out);
 }
 
 extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, int n, int act,

@@ -21,7 +21,9 @@
 //     bias, apply the activation and write 64-byte row segments.
 // Shapes outside (K % 32 == 0, N % 16 == 0, 16 <= N <= 256) use the fp32 CUDA-core path (dense.cu).
 
-#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace ign_tc;
 
 namespace {
 
@@ -29,61 +31,6 @@ constexpr int TC_THREADS = 256;
 constexpr int TC_M = 128;
 constexpr int TC_KC = 32;                       // floats per K chunk = 128 bytes per row
 constexpr int A_IMG = TC_M * 128;               // bytes of one A image (hi or lo) of a chunk
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// 64-bit shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, 16-byte units
-  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-  return d;
-}
-
-// instruction descriptor, kind::tf32: D fp32, A/B tf32, both K-major, M = 128
-__host__ __device__ constexpr uint32_t umma_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 
 // activation in the epilogue: SELU / ELU use ex2.approx with a Taylor branch near zero instead of
 // expm1f (the epilogue is instruction-bound); everything else as act_fwd
@@ -97,11 +44,6 @@ __device__ __forceinline__ float act_epi(int act, float x) {
   if (act == IGN_ACT_LINEAR) return x;
   if (act == IGN_ACT_ELU) return x > 0.0f ? x : fast_expm1(x);
   return act_fwd(act, x);
-}
-
-// byte offset of float (row r, k) inside a [rows][32] K-major SWIZZLE_128B image
-__host__ __device__ __forceinline__ int sw128_off(int r, int k) {
-  return r * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4;
 }
 
 // W[K,N] -> per chunk c: [hi image: N rows x 128 B][lo image]  (the shared-memory layout of B)
@@ -122,7 +64,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
                                                                  const float* __restrict__ wimg,
                                                                  const float* __restrict__ bias, int N, int act,
                                                                  float* __restrict__ y, float* __restrict__ pre,
-                                                                 int tmem_cols) {
+                                                                 int tmem_cols, const float* __restrict__ head_w,
+                                                                 const float* __restrict__ head_b, float* __restrict__ head_out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve-up (1024-byte aligned images): stage s: A_hi | A_lo | B_hi | B_lo
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -132,6 +75,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
   __shared__ uint64_t bar_acc;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[256];
+  __shared__ __align__(16) float s_head[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -145,7 +89,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
                  "r"((uint32_t)tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  if (tid < N) s_bias[tid] = bias ? bias[tid] : 0.0f;
+  if (tid < N) {
+    s_bias[tid] = bias ? bias[tid] : 0.0f;
+    s_head[tid] = head_w ? head_w[tid] : 0.0f;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -216,6 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
       const int q = warp & 3, half = warp >> 2;
       const int64_t row = m0 + q * 32 + lane;
       const int ncol_half = N / 2;
+      float head_acc = 0.0f;
       for (int cb = 0; cb < ncol_half; cb += 32) {       // two 16-column TMEM loads in flight per wait
         const int col = half * ncol_half + cb;
         const bool second = cb + 16 < ncol_half;
@@ -238,11 +186,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
               v.w = __uint_as_float(hblk ? rb[i + 3] : ra[i + 3]) + bv.w;
               if (pre) st_f4(pre + row * N + c0 + i, v);
               v.x = act_epi(act, v.x); v.y = act_epi(act, v.y); v.z = act_epi(act, v.z); v.w = act_epi(act, v.w);
-              st_f4(y + row * N + c0 + i, v);
+              if (y) st_f4(y + row * N + c0 + i, v);
+              if (head_out) {
+                const float4 hw = *reinterpret_cast<const float4*>(s_head + c0 + i);
+                head_acc = fmaf(v.x, hw.x, head_acc); head_acc = fmaf(v.y, hw.y, head_acc);
+                head_acc = fmaf(v.z, hw.z, head_acc); head_acc = fmaf(v.w, hw.w, head_acc);
+              }
             }
           }
         }
       }
+      // fused single-output head: the two column halves of a row add their partial dot products
+      // (two commutative float adds onto a zeroed output: deterministic)
+      if (head_out && row < M) atomicAdd(head_out + row, head_acc + ((half == 0 && head_b) ? __ldg(head_b) : 0.0f));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                 // accumulator drained before the next tile's MMAs
@@ -262,7 +218,8 @@ bool ign_dense_tc_supported(int k, int n) { return k % TC_KC == 0 && k >= TC_KC 
 size_t ign_dense_tc_ws(int k, int n) { return (size_t)(k / TC_KC) * 2 * n * 128; }
 
 int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
-                        float* y, float* pre_act, void* ws, cudaStream_t st) {
+                        float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w,
+                        const float* head_b, float* head_out) {
   float* img = reinterpret_cast<float*>(ws);
   dense_tc_prep_kernel<<<(unsigned)ign_cdiv((int64_t)k * n, 256), 256, 0, st>>>(w, k, n, img);
   IGN_CHECK_LAUNCH("dense_tc_prep");
@@ -278,7 +235,9 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = ign_cdiv(m, TC_M);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  dense_tc_kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols);
+  if (head_out) IGN_CUDA(cudaMemsetAsync(head_out, 0, (size_t)m * sizeof(float), st));
+  dense_tc_kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols, head_w, head_b,
+                                                   head_out);
   IGN_CHECK_LAUNCH("dense_tc");
   return IGN_OK;
 }

@@ -19,11 +19,16 @@
 
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace ign_tc;
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int NSPLIT = 4;                 // warps per TMEM lane group: each owns 32 / NSPLIT units of a row
+constexpr int EPI_THREADS = 128 * NSPLIT;  // 16 epilogue warps
+constexpr int TC_THREADS = EPI_THREADS + 32;   // + one warp that only issues the tcgen05.mma stream
+constexpr int UPT = 32 / NSPLIT;          // units per thread
 constexpr int ROWS = 128;                 // destinations per tile = UMMA M
 constexpr int U = 32;                     // units = message width
 constexpr int IMG = ROWS * 128;           // bytes of one [128 x 32] fp32 operand image
@@ -37,79 +42,12 @@ __device__ __forceinline__ const float* pick_src(const SrcPtrs& s, int k) {
   return k == 0 ? s.p[0] : k == 1 ? s.p[1] : k == 2 ? s.p[2] : s.p[3];
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {     // K-major, SWIZZLE_128B, SBO 1024
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__host__ __device__ constexpr uint32_t umma_idesc(int n) {          // kind::tf32, fp32 accumulate, M = 128
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-
-
-// store 4 consecutive floats (16-byte chunk c4 of row r) as hi / lo into two swizzled images
-__device__ __forceinline__ void store_split(unsigned char* img_hi, unsigned char* img_lo, int r, int c4, float4 v) {
-  float4 hi, lo;
-  tf32_split(v.x, hi.x, lo.x);
-  tf32_split(v.y, hi.y, lo.y);
-  tf32_split(v.z, hi.z, lo.z);
-  tf32_split(v.w, hi.w, lo.w);
-  const int off = r * 128 + ((c4 ^ (r & 7)) << 4);
-  *reinterpret_cast<float4*>(img_hi + off) = hi;
-  *reinterpret_cast<float4*>(img_lo + off) = lo;
-}
-
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
-
 struct Slot {
   int d;        // destination of this thread's row (-1: none)
   int lo;       // first step
   int len;      // number of steps
   int entry;    // step-table entry of the next message to gather (one step of lookahead)
-  float h[16];  // running state, this thread's 16 units
+  float h[UPT]; // running state, this thread's units
 };
 
 template <bool FAST>
@@ -132,9 +70,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
   __shared__ int s_maxlen[2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
+  const bool mma_warp = warp == EPI_THREADS / 32;          // warp 16: MMA issuer, no rows
+  const int q = warp & 3, split = (warp >> 2) & (NSPLIT - 1);
   const int row = q * 32 + lane;                         // TMEM lane == row of the tile
-  const int u0 = half * 16;                              // this thread's units [u0, u0+16)
+  const int u0 = split * UPT;                            // this thread's units [u0, u0 + UPT)
 
   if (tid == 0) {
     mbar_init(&bar[0], 1);
@@ -159,7 +98,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     *reinterpret_cast<float*>(bh_lo + off) = lo;
   }
   for (int i = tid; i < 6 * U; i += TC_THREADS) s_bias[i] = bias[i];
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_async_smem();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -180,27 +119,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
 
   // gather this thread's 64 bytes of the message of step t (its entry was fetched one step earlier,
   // so the row load does not wait on an index load), then fetch the entry of step t + 1
-  auto load_x = [&](Slot& s, int t, float4 (&x)[4]) {
+  auto load_x = [&](Slot& s, int t, float4 (&x)[UPT / 4]) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < UPT / 4; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int entry = s.entry;
     s.entry = (t + 1 < s.len) ? __ldg(steps + s.lo + t + 1) : IGN_STEP_ZERO;
     if (t < s.len && entry >= 0) {
       const float* p = pick_src(srcs, entry >> IGN_STEP_SRC_SHIFT) + (int64_t)(entry & IGN_STEP_ROW_MASK) * U + u0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = ldg_f4(p + 4 * j);
+      for (int j = 0; j < UPT / 4; ++j) x[j] = ldg_f4(p + 4 * j);
     }
   };
-  auto store_x = [&](int slot, const float4 (&x)[4]) {
+  auto store_x = [&](int slot, const float4 (&x)[UPT / 4]) {
     unsigned char* b = slots + slot * SLOT_BYTES;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) store_split(b, b + IMG, row, half * 4 + j, x[j]);
+    for (int j = 0; j < UPT / 4; ++j) store_split(b, b + IMG, row, split * (UPT / 4) + j, x[j]);
   };
   auto store_h = [&](int slot, const Slot& s) {
     unsigned char* b = slots + slot * SLOT_BYTES + 2 * IMG;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      store_split(b, b + IMG, row, half * 4 + j, make_float4(s.h[4 * j], s.h[4 * j + 1], s.h[4 * j + 2], s.h[4 * j + 3]));
+    for (int j = 0; j < UPT / 4; ++j)
+      store_split(b, b + IMG, row, split * (UPT / 4) + j,
+                  make_float4(s.h[4 * j], s.h[4 * j + 1], s.h[4 * j + 2], s.h[4 * j + 3]));
   };
   auto issue_mma = [&](int slot) {           // one thread: 36 UMMAs of one step, then commit
     const uint32_t ax_hi = smem_u32(slots + slot * SLOT_BYTES), ax_lo = ax_hi + IMG;
@@ -235,7 +175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     for (int s = 0; s < 2; ++s) {
       const int64_t didx = (pr * 2 + s) * ROWS + row;
       nmeta[s] = make_int4(-1, 0, 0, IGN_STEP_ZERO);
-      if (pr < npairs && didx < num_dst) {
+      if (!mma_warp && pr < npairs && didx < num_dst) {
         if (meta) {
           nmeta[s] = __ldg(meta + didx);
         } else {
@@ -257,28 +197,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     for (int s = 0; s < 2; ++s) {
       sl[s].d = nmeta[s].x; sl[s].lo = nmeta[s].y; sl[s].len = nmeta[s].z; sl[s].entry = nmeta[s].w;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sl[s].h[j] = 0.f;
+      for (int j = 0; j < UPT; ++j) sl[s].h[j] = 0.f;
       if (sl[s].d >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < UPT / 4; ++j) {
           const float4 v = ldg_f4(h0 + (int64_t)sl[s].d * U + u0 + 4 * j);
           sl[s].h[4 * j] = v.x; sl[s].h[4 * j + 1] = v.y; sl[s].h[4 * j + 2] = v.z; sl[s].h[4 * j + 3] = v.w;
         }
       }
-      if (half == 0 && sl[s].len > 0) atomicMax(&s_maxlen[s], sl[s].len);
-      float4 x[4];
-      load_x(sl[s], 0, x);
-      store_x(s, x);
-      store_h(s, sl[s]);
+      if (split == 0 && sl[s].len > 0) atomicMax(&s_maxlen[s], sl[s].len);
+      if (!mma_warp) {
+        float4 x[UPT / 4];
+        load_x(sl[s], 0, x);
+        store_x(s, x);
+        store_h(s, sl[s]);
+      }
     }
     fetch_meta(pair + gridDim.x);                        // lands while this pair is being walked
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_async_smem();
     __syncthreads();
     const int maxlen0 = s_maxlen[0], maxlen1 = s_maxlen[1];
     const int maxlen = max(maxlen0, maxlen1);
-    if (tid == 0) {
-      if (maxlen0 > 0) issue_mma(0);
-      if (maxlen1 > 0) issue_mma(1);
+    if (mma_warp) {
+      // ---- MMA issuer warp: one elected lane feeds the tensor core; the epilogue warps never wait on it
+      if (lane == 0) {
+        if (maxlen0 > 0) issue_mma(0);
+        if (maxlen1 > 0) issue_mma(1);
+      }
+      for (int t = 0; t < maxlen; ++t) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int ml = s == 0 ? maxlen0 : maxlen1;
+          if (t + 1 >= ml) continue;
+          // operands of step t + 1 of slot s are in shared memory once all epilogue threads arrived
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(TC_THREADS) : "memory");
+          if (lane == 0) issue_mma(s);
+        }
+      }
+      continue;                                          // next pair (joins the set-up barriers)
     }
     if (maxlen0 > 0) uses[0] += 1;
     if (maxlen1 > 0) uses[1] += 1;
@@ -289,20 +245,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
         const int ml = s == 0 ? maxlen0 : maxlen1;
         if (t >= ml) continue;                           // uniform over the CTA
         Slot& S = sl[s];
-        float4 xn[4];
+        float4 xn[UPT / 4];
         load_x(S, t + 1, xn);                            // next message: in flight while we wait for the MMA
         mbar_wait(&bar[s], (uses[s] - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tbase = tmem_base + s * 128 + ((uint32_t)(q * 32) << 16) + u0;
-        uint32_t az[16], ar[16], axh[16], ahh[16];
-        tmem_ld16_nowait(tbase, az);
-        tmem_ld16_nowait(tbase + 32, ar);
-        tmem_ld16_nowait(tbase + 64, axh);
-        tmem_ld16_nowait(tbase + 96, ahh);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t az[UPT], ar[UPT], axh[UPT], ahh[UPT];
+        tmem_ld8_nowait(tbase, az);
+        tmem_ld8_nowait(tbase + 32, ar);
+        tmem_ld8_nowait(tbase + 64, axh);
+        tmem_ld8_nowait(tbase + 96, ahh);
+        tmem_ld_wait();
         if (t < S.len) {
 #pragma unroll
-          for (int j4 = 0; j4 < 16; j4 += 4) {
+          for (int j4 = 0; j4 < UPT; j4 += 4) {
             const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
             const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
             const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
@@ -323,18 +279,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
           if (h_seq) {
             float* p = h_seq + (int64_t)(S.lo + t) * U + u0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) st_f4(p + 4 * j, make_float4(S.h[4 * j], S.h[4 * j + 1], S.h[4 * j + 2], S.h[4 * j + 3]));
+            for (int j = 0; j < UPT / 4; ++j)
+              st_f4(p + 4 * j, make_float4(S.h[4 * j], S.h[4 * j + 1], S.h[4 * j + 2], S.h[4 * j + 3]));
           }
         }
         if (t + 1 < ml) {                                // operands of the next step
           store_h(s, S);
           store_x(s, xn);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          fence_async_smem();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (t + 1 < ml) {
-          if (tid == 0) issue_mma(s);
+        if (t + 1 < ml) {                                // hand the slot to the MMA warp, do not wait
+          asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "r"(TC_THREADS) : "memory");
           uses[s] += 1;
         }
       }
@@ -345,7 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
       if (sl[s].d >= 0) {
         float* p = out + (int64_t)sl[s].d * U + u0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < UPT / 4; ++j)
           st_f4(p + 4 * j, make_float4(sl[s].h[4 * j], sl[s].h[4 * j + 1], sl[s].h[4 * j + 2], sl[s].h[4 * j + 3]));
       }
     }

@@ -299,17 +299,34 @@ class Engine:
         return ops.ACTIVATIONS[name]
 
     def _run_ff(self, prefix: str, ff: FeedForward, x: torch.Tensor, saves: Optional[list] = None) -> torch.Tensor:
-        for l in ff.layers:
-            w = self.param("%s/%s/kernel" % (prefix, l.name))
-            b = self.param("%s/%s/bias" % (prefix, l.name)) if l.use_bias else None
-            pre = None
-            if saves is not None:
-                pre = torch.empty(x.shape[0], w.shape[1], dtype=torch.float32, device=self.device)
-            y = ops.dense(x, w, b, self._act(l.activation), pre_act=pre)
-            if saves is not None:
-                saves.append((prefix, l, x, pre))
-            x = y
+        layers = ff.layers
+        # inference: a Dense layer followed by a single-output linear layer runs as one kernel
+        # (the hidden activations never leave the SM) -- the readout head of RouteNet / Q-size
+        if (saves is None and len(layers) >= 2 and layers[-1].activation in (None, "None", "linear")
+                and self.param("%s/%s/kernel" % (prefix, layers[-1].name)).shape[1] == 1):
+            wl = self.param("%s/%s/kernel" % (prefix, layers[-2].name))
+            if ops.dense_head_supported(x.shape[0], wl.shape[0], wl.shape[1]):
+                for l in layers[:-2]:
+                    x = self._dense_layer(prefix, l, x, None)
+                l2, l3 = layers[-2], layers[-1]
+                return ops.dense_head(
+                    x, wl, self.param("%s/%s/bias" % (prefix, l2.name)) if l2.use_bias else None,
+                    self._act(l2.activation), self.param("%s/%s/kernel" % (prefix, l3.name)).reshape(-1),
+                    self.param("%s/%s/bias" % (prefix, l3.name)) if l3.use_bias else None)
+        for l in layers:
+            x = self._dense_layer(prefix, l, x, saves)
         return x
+
+    def _dense_layer(self, prefix: str, l, x: torch.Tensor, saves: Optional[list]) -> torch.Tensor:
+        w = self.param("%s/%s/kernel" % (prefix, l.name))
+        b = self.param("%s/%s/bias" % (prefix, l.name)) if l.use_bias else None
+        pre = None
+        if saves is not None:
+            pre = torch.empty(x.shape[0], w.shape[1], dtype=torch.float32, device=self.device)
+        y = ops.dense(x, w, b, self._act(l.activation), pre_act=pre)
+        if saves is not None:
+            saves.append((prefix, l, x, pre))
+        return y
 
     def _messages(self, p: _MPPlan, k: int, g: DeviceGraph, state: Dict[str, torch.Tensor]):
         """Per-edge messages of source k in INPUT edge order, or None for direct_assignation."""

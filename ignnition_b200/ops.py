@@ -206,6 +206,31 @@ def dense(x, w, bias, act: int, out=None, pre_act=None, tensor_cores: bool = Tru
     return out
 
 
+def tensor_cores_enabled() -> bool:
+    lib = _lib.load()
+    prev = lib.ign_set_tensor_cores(1)
+    lib.ign_set_tensor_cores(prev)
+    return bool(prev)
+
+
+def dense_head_supported(m: int, k: int, n: int) -> bool:
+    return m >= 128 and _lib.load().ign_dense_ws_bytes(k, n) > 0 and tensor_cores_enabled()
+
+
+def dense_head(x, w, bias, act: int, head_w, head_b, out=None):
+    """out[m, 1] = act(x w + b) . head_w + head_b on the tensor cores, hidden activations stay on chip."""
+    lib = _lib.load()
+    m, k = x.shape
+    n = w.shape[1]
+    if out is None:
+        out = torch.empty(m, 1, dtype=torch.float32, device=x.device)
+    nbytes = lib.ign_dense_ws_bytes(k, n)
+    ws = _workspace(nbytes, x.device)
+    _lib.check(lib.ign_dense_head(_f(x), m, k, _f(w), _f(bias), n, act, _f(head_w), _f(head_b),
+                                  _f(out), ws.data_ptr(), nbytes, _stream()), "dense_head")
+    return out
+
+
 def gather_concat(parts: List[torch.Tensor], idx: List[Optional[torch.Tensor]], rows: int, out=None):
     lib = _lib.load()
     widths = [p.shape[1] for p in parts]

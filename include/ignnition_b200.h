@@ -174,6 +174,14 @@ size_t ign_dense_ws_bytes(int k, int n);
 int ign_dense(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
               float* y, float* pre_act, void* ws, size_t ws_bytes, void* stream);
 
+/* Dense layer fused with a following single-output linear layer (the readout's 256 -> 1 head,
+ * examples/Routenet/model_description.json:119-141):  out[m] = act(x W + b) . head_w + head_b.
+ * The hidden activations never go to memory.  Tensor-core shapes only (ign_dense_ws_bytes(k, n) > 0,
+ * m >= 128); head_b points to one float on the device (nullable = 0). */
+int ign_dense_head(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                   const float* head_w, const float* head_b, float* out, void* ws,
+                   size_t ws_bytes, void* stream);
+
 /* Row-wise concatenation of up to 4 blocks, each optionally gathered by an index:
  * tf.concat([hs_source, hs_dest, edge_params], axis=1) after tf.gather (generate_model.py:432-465)
  * and tf.concat([agg, old_state], 1) of the FF update (:599).  idx[i] nullable = identity. */

@@ -312,6 +312,22 @@ def test_dense(m, k, n, act, tensor_cores):
     assert rel_err(got, orc.activation(act, z)) < RTOL
 
 
+def test_dense_head_fused():
+    """readout tail: out = selu(x W + b) . w3 + b3 in one kernel == two dense layers"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(11)
+    m, k, n = 3000, 256, 256
+    x = rng.randn(m, k).astype(np.float32)
+    w = (rng.randn(k, n) / np.sqrt(k)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+    w3 = (rng.randn(n) / np.sqrt(n)).astype(np.float32)
+    b3 = np.array([0.37], np.float32)
+    assert ops.dense_head_supported(m, k, n)
+    got = ops.dense_head(dev(x), dev(w), dev(b), ops.ACTIVATIONS["selu"], dev(w3), dev(b3)).cpu().numpy()
+    want = orc.activation("selu", x.astype(np.float64) @ w.astype(np.float64) + b) @ w3.astype(np.float64) + b3[0]
+    assert got.shape == (m, 1) and rel_err(got.reshape(-1), want) < RTOL
+
+
 def test_init_state_and_gather_concat():
     from ignnition_b200 import ops
     rng = np.random.RandomState(0)
