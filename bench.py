@@ -198,7 +198,7 @@ def run_ours(args):
                            feature_fns(qsize), seed=rank,
                            label_fn=(lambda r, n: r.normal(-1.0, 0.5, n)) if args.train else None,
                            label_entity=out_entity0)
-    pinned = batch.pack(pin=True)
+    pinned = eng.pack(batch)            # seq_* / sample_of_* stay on the host: the device sort does not need them
     edges_per_iter = sum(batch.n_edges[a.name] for a in eng.adjacencies)
     out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
     n_pred = batch.num[out_entity]
@@ -218,10 +218,35 @@ def run_ours(args):
 
     host_pred = torch.empty(n_pred, 1, dtype=torch.float32, pin_memory=True)
 
+    # end to end: a stream of batches.  Batch k+1 is copied host -> device on a copy stream while batch k
+    # is computed (two device staging buffers); every step still pays its own H2D and its own D2H.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty(pinned[0].numel(), dtype=torch.uint8, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"k": 0, "primed": False}
+
+    def issue_upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[slot])          # the compute that last read this buffer is done
+            g_ = eng.upload(batch, pinned, out=stage[slot])
+            ready[slot].record(copy_stream)
+        return g_
+
     def step_e2e():
-        graph = eng.upload(batch, pinned)
+        k = e2e_state["k"]
+        if not e2e_state["primed"]:
+            for s_ in range(2):
+                free[s_].record()
+            e2e_state["next"] = issue_upload(k & 1)
+            e2e_state["primed"] = True
+        graph = e2e_state["next"]
+        torch.cuda.current_stream().wait_event(ready[k & 1])
+        e2e_state["next"] = issue_upload((k + 1) & 1)   # overlaps with this step's compute
         pred = step_resident(graph)
+        free[k & 1].record()
         host_pred.copy_(pred, non_blocking=True)
+        e2e_state["k"] = k + 1
         return graph
 
     def barrier():

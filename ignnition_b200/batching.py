@@ -49,18 +49,21 @@ class Batch:
         self.n_edges: Dict[str, int] = {}
 
     # ---- packing: one contiguous buffer, 256-byte aligned slices
-    def pack(self, pin: bool = False):
+    def pack(self, pin: bool = False, skip=()):
+        """One contiguous host buffer (pinned when asked) + layout; arrays whose name starts with a
+        prefix in ``skip`` are left out (e.g. ``seq_`` when the device builds the CSR by sorting)."""
         import torch
         layout = {}
         off = 0
-        for k, a in self.arrays.items():
+        arrays = {k: a for k, a in self.arrays.items() if not any(k.startswith(p) for p in skip)}
+        for k, a in arrays.items():
             off = (off + 255) // 256 * 256
             layout[k] = (off, a.dtype, a.shape)
             off += a.nbytes
         total = max(off, 256)
         buf = torch.empty(total, dtype=torch.uint8, pin_memory=pin)
         view = buf.numpy()
-        for k, a in self.arrays.items():
+        for k, a in arrays.items():
             o = layout[k][0]
             view[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
         return buf, layout

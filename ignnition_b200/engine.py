@@ -242,13 +242,27 @@ class Engine:
     def assemble(self, samples: Sequence[dict], labels=None) -> Batch:
         return assemble(samples, self.entities, self.features, self.adjacencies, self.sequences, labels)
 
-    def upload(self, batch: Batch, pinned=None) -> DeviceGraph:
+    def upload_skip(self) -> tuple:
+        """Host arrays the device does not need: ``seq_*`` when the CSR is built by the stable sort
+        (seq is the rank in input order, generator_std_to_framework.py:153), ``sample_of_*`` when no
+        multi-source sequence needs the sample of a destination."""
+        skip = []
+        if self.csr_mode == ops.CSR_SORT:
+            skip.append("seq_")
+        if not self.sequences:
+            skip.append("sample_of_")
+        return tuple(skip)
+
+    def pack(self, batch: Batch, pin: bool = True, full: bool = False):
+        return batch.pack(pin=pin, skip=() if full else self.upload_skip())
+
+    def upload(self, batch: Batch, pinned=None, out: Optional[torch.Tensor] = None) -> DeviceGraph:
         """Host -> device copy of the packed batch (one cudaMemcpyAsync) + tensor views."""
         if pinned is None:
-            pinned = batch.pack(pin=True)
+            pinned = self.pack(batch, full=True)
         buf, layout = pinned
         g = DeviceGraph()
-        g.buf = torch.empty(buf.numel(), dtype=torch.uint8, device=self.device)
+        g.buf = out if out is not None else torch.empty(buf.numel(), dtype=torch.uint8, device=self.device)
         g.buf.copy_(buf, non_blocking=True)
         g.h2d_bytes = buf.numel()
         for k, (off, dtype, shape) in layout.items():
@@ -262,7 +276,10 @@ class Engine:
     def build_graph(self, g: DeviceGraph, training: bool = False, check: bool = False) -> DeviceGraph:
         """Device adjacency builder: CSR per adjacency, length order, step tables."""
         for a in self.adjacencies:
-            dst, src, seq = g.t["dst_" + a.name], g.t["src_" + a.name], g.t["seq_" + a.name]
+            dst, src, seq = g.t["dst_" + a.name], g.t["src_" + a.name], g.t.get("seq_" + a.name)
+            if seq is None and self.csr_mode != ops.CSR_SORT:
+                raise RuntimeError("IGNNITION: seq_%s was not uploaded but the rank-placement CSR build needs it"
+                                   % a.name)
             rowptr, col, perm, status = ops.csr_build(dst, src, seq, g.num[a.dst], self.csr_mode,
                                                       want_perm=training or check or a.name in self._needs_perm,
                                                       want_status=check)
