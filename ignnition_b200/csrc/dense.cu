@@ -317,6 +317,30 @@ extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const
   return IGN_OK;
 }
 
+// fused two-hidden-layer readout (mlp_head_tc.cu)
+bool ign_mlp_head_tc_supported(int k1, int n1, int n2);
+size_t ign_mlp_head_tc_ws(int k1, int n1, int n2);
+int ign_mlp_head_tc_launch(const float* x, int64_t m, int k1, const float* w1, const float* b1, int n1, int act1,
+                           const float* w2, const float* b2, int n2, int act2, const float* w3, const float* b3,
+                           float* out, void* ws, cudaStream_t st);
+
+extern "C" size_t ign_mlp_head_ws_bytes(int k1, int n1, int n2) {
+  return ign_mlp_head_tc_supported(k1, n1, n2) ? ign_mlp_head_tc_ws(k1, n1, n2) : 0;
+}
+
+extern "C" int ign_mlp_head(const float* x, int64_t m, int k1, const float* w1, const float* b1, int n1, int act1,
+                            const float* w2, const float* b2, int n2, int act2, const float* w3, const float* b3,
+                            float* out, void* ws, size_t ws_bytes, void* stream) {
+  IGN_REQUIRE(m >= 0 && k1 > 0 && n1 > 0 && n2 > 0, IGN_ERR_INVALID, "IGNNITION: mlp_head: bad shape");
+  if (m == 0) return IGN_OK;
+  IGN_REQUIRE(x && w1 && w2 && w3 && out && ws, IGN_ERR_INVALID, "IGNNITION: mlp_head: null pointer");
+  IGN_REQUIRE(ign_mlp_head_tc_supported(k1, n1, n2) && ws_bytes >= ign_mlp_head_tc_ws(k1, n1, n2) && m >= 128 &&
+                  ign_tensor_cores_enabled(),
+              IGN_ERR_UNSUPPORTED,
+              "IGNNITION: mlp_head: built for K1 %% 32 == 0, N1, N2 %% 32 == 0 (<= 256), M >= 128, tensor cores on");
+  return ign_mlp_head_tc_launch(x, m, k1, w1, b1, n1, act1, w2, b2, n2, act2, w3, b3, out, ws, ign_stream(stream));
+}
+
 extern "C" int ign_dense_head(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
                               const float* head_w, const float* head_b, float* out, void* ws, size_t ws_bytes,
                               void* stream) {

@@ -322,6 +322,13 @@ class Engine:
         if (saves is None and len(layers) >= 2 and layers[-1].activation in (None, "None", "linear")
                 and self.param("%s/%s/kernel" % (prefix, layers[-1].name)).shape[1] == 1):
             wl = self.param("%s/%s/kernel" % (prefix, layers[-2].name))
+            pb = lambda l: self.param("%s/%s/bias" % (prefix, l.name)) if l.use_bias else None
+            if len(layers) == 3:
+                w1 = self.param("%s/%s/kernel" % (prefix, layers[0].name))
+                if ops.mlp_head_supported(x.shape[0], w1.shape[0], w1.shape[1], wl.shape[1]):
+                    return ops.mlp_head(x, w1, pb(layers[0]), self._act(layers[0].activation), wl, pb(layers[1]),
+                                        self._act(layers[1].activation),
+                                        self.param("%s/%s/kernel" % (prefix, layers[2].name)).reshape(-1), pb(layers[2]))
             if ops.dense_head_supported(x.shape[0], wl.shape[0], wl.shape[1]):
                 for l in layers[:-2]:
                     x = self._dense_layer(prefix, l, x, None)

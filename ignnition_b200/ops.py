@@ -231,6 +231,24 @@ def dense_head(x, w, bias, act: int, head_w, head_b, out=None):
     return out
 
 
+def mlp_head_supported(m: int, k1: int, n1: int, n2: int) -> bool:
+    return m >= 128 and _lib.load().ign_mlp_head_ws_bytes(k1, n1, n2) > 0 and tensor_cores_enabled()
+
+
+def mlp_head(x, w1, b1, act1: int, w2, b2, act2: int, w3, b3, out=None):
+    """out[m, 1] = act2(act1(x w1 + b1) w2 + b2) . w3 + b3 in one tensor-core kernel."""
+    lib = _lib.load()
+    m, k1 = x.shape
+    n1, n2 = w1.shape[1], w2.shape[1]
+    if out is None:
+        out = torch.empty(m, 1, dtype=torch.float32, device=x.device)
+    nbytes = lib.ign_mlp_head_ws_bytes(k1, n1, n2)
+    ws = _workspace(nbytes, x.device)
+    _lib.check(lib.ign_mlp_head(_f(x), m, k1, _f(w1), _f(b1), n1, act1, _f(w2), _f(b2), n2, act2, _f(w3), _f(b3),
+                                _f(out), ws.data_ptr(), nbytes, _stream()), "mlp_head")
+    return out
+
+
 def gather_concat(parts: List[torch.Tensor], idx: List[Optional[torch.Tensor]], rows: int, out=None):
     lib = _lib.load()
     widths = [p.shape[1] for p in parts]

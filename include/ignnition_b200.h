@@ -182,6 +182,16 @@ int ign_dense_head(const float* x, int64_t m, int k, const float* w, const float
                    const float* head_w, const float* head_b, float* out, void* ws,
                    size_t ws_bytes, void* stream);
 
+/* The whole predict stack with two hidden layers and one linear output in ONE kernel:
+ *   out[m] = act2( act1(x W1 + b1) W2 + b2 ) . w3 + b3
+ * (RouteNet / Q-size readout 32 -> 256 -> 256 -> 1, generate_model.py:612-629).  Both hidden activations
+ * stay on chip (TMEM -> shared-memory operand image -> next GEMM).  Inference only; tensor-core shapes
+ * only (ign_mlp_head_ws_bytes > 0, m >= 128).  b1, b2, b3 nullable; b3 points to one device float. */
+size_t ign_mlp_head_ws_bytes(int k1, int n1, int n2);
+int ign_mlp_head(const float* x, int64_t m, int k1, const float* w1, const float* b1, int n1, int act1,
+                 const float* w2, const float* b2, int n2, int act2, const float* w3, const float* b3,
+                 float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* Row-wise concatenation of up to 4 blocks, each optionally gathered by an index:
  * tf.concat([hs_source, hs_dest, edge_params], axis=1) after tf.gather (generate_model.py:432-465)
  * and tf.concat([agg, old_state], 1) of the FF update (:599).  idx[i] nullable = identity. */

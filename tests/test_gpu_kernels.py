@@ -328,6 +328,24 @@ def test_dense_head_fused():
     assert got.shape == (m, 1) and rel_err(got.reshape(-1), want) < RTOL
 
 
+@pytest.mark.parametrize("m,k1,n1,n2", [(3000, 32, 256, 256), (128, 64, 96, 32), (70001, 32, 256, 256)])
+def test_mlp_head_fused(m, k1, n1, n2):
+    """whole readout stack in one kernel == three dense layers of the oracle"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(m % 97)
+    x = rng.randn(m, k1).astype(np.float32)
+    w1 = (rng.randn(k1, n1) / np.sqrt(k1)).astype(np.float32); b1 = rng.uniform(-0.1, 0.1, n1).astype(np.float32)
+    w2 = (rng.randn(n1, n2) / np.sqrt(n1)).astype(np.float32); b2 = rng.uniform(-0.1, 0.1, n2).astype(np.float32)
+    w3 = (rng.randn(n2) / np.sqrt(n2)).astype(np.float32); b3 = np.array([-0.21], np.float32)
+    assert ops.mlp_head_supported(m, k1, n1, n2)
+    got = ops.mlp_head(dev(x), dev(w1), dev(b1), ops.ACTIVATIONS["selu"], dev(w2), dev(b2), ops.ACTIVATIONS["selu"],
+                       dev(w3), dev(b3)).cpu().numpy()
+    h1 = orc.activation("selu", x.astype(np.float64) @ w1.astype(np.float64) + b1)
+    h2 = orc.activation("selu", h1 @ w2.astype(np.float64) + b2)
+    want = h2 @ w3.astype(np.float64) + b3[0]
+    assert got.shape == (m, 1) and rel_err(got.reshape(-1), want) < RTOL
+
+
 def test_init_state_and_gather_concat():
     from ignnition_b200 import ops
     rng = np.random.RandomState(0)
