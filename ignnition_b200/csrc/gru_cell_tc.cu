@@ -17,7 +17,8 @@ using namespace ign_tc;
 
 namespace {
 
-constexpr int TC_THREADS = 256;
+constexpr int NPART = 4;                      // warps per TMEM lane group
+constexpr int TC_THREADS = 128 * NPART;       // 16 warps: the gate epilogue is latency-bound with fewer
 constexpr int ROWS = 128;
 constexpr int A_IMG = ROWS * 128;
 
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_cell_tc_kernel(const float*
         const float* base = (c < NC) ? x : h;
         const int koff = (c < NC ? c : c - NC) * 32;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 1024 / TC_THREADS; ++j) {
           const int idx = tid + j * TC_THREADS;
           const int r = idx >> 3, c4 = idx & 7;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -130,40 +131,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_cell_tc_kernel(const float*
     const int64_t m0 = tile * ROWS;
     mbar_wait(&bar_acc[ab], (acc_uses[ab] - 1) & 1);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;
     const int64_t row = m0 + q * 32 + lane;
     const uint32_t tb = tmem_base + ab * DCOLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-    for (int ub = 0; ub < U / 2; ub += 16) {
-      const int u0 = half * (U / 2) + ub;
-      uint32_t az[16], ar[16], axh[16], ahh[16];
+    constexpr int UPT = U / NPART;                       // units per thread: 16 (U = 64) or 8 (U = 32)
+    const int u0 = part * UPT;
+    uint32_t az[UPT], ar[UPT], axh[UPT], ahh[UPT];
+    if constexpr (UPT == 16) {
       tmem_ld16_nowait(tb + u0, az);
       tmem_ld16_nowait(tb + U + u0, ar);
       tmem_ld16_nowait(tb + 2 * U + u0, axh);
       tmem_ld16_nowait(tb + 3 * U + u0, ahh);
-      tmem_ld_wait();
-      if (row < n) {
+    } else {
+      tmem_ld8_nowait(tb + u0, az);
+      tmem_ld8_nowait(tb + U + u0, ar);
+      tmem_ld8_nowait(tb + 2 * U + u0, axh);
+      tmem_ld8_nowait(tb + 3 * U + u0, ahh);
+    }
+    tmem_ld_wait();
+    if (row < n) {
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
-          const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
-          const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
-          const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + u0 + j4);
-          const float4 ho = ldg_f4(h + row * U + u0 + j4);
-          const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
-          const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
-          const float hold[4] = {ho.x, ho.y, ho.z, ho.w};
-          float hn[4];
+      for (int j4 = 0; j4 < UPT; j4 += 4) {
+        const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
+        const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
+        const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
+        const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + u0 + j4);
+        const float4 ho = ldg_f4(h + row * U + u0 + j4);
+        const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
+        const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
+        const float hold[4] = {ho.x, ho.y, ho.z, ho.w};
+        float hn[4];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = j4 + jj;
-            const float z = fast_sigmoid(__uint_as_float(az[j]) + bz[jj]);
-            const float r = fast_sigmoid(__uint_as_float(ar[j]) + br[jj]);
-            const float hh = fast_tanh(fmaf(r, __uint_as_float(ahh[j]) + bhh[jj], __uint_as_float(axh[j]) + bxh[jj]));
-            hn[jj] = fmaf(z, hold[jj] - hh, hh);
-          }
-          st_f4(out + row * U + u0 + j4, make_float4(hn[0], hn[1], hn[2], hn[3]));
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = j4 + jj;
+          const float z = fast_sigmoid(__uint_as_float(az[j]) + bz[jj]);
+          const float r = fast_sigmoid(__uint_as_float(ar[j]) + br[jj]);
+          const float hh = fast_tanh(fmaf(r, __uint_as_float(ahh[j]) + bhh[jj], __uint_as_float(axh[j]) + bxh[jj]));
+          hn[jj] = fmaf(z, hold[jj] - hh, hh);
         }
+        st_f4(out + row * U + u0 + j4, make_float4(hn[0], hn[1], hn[2], hn[3]));
       }
     }
     tc_fence_before();
