@@ -326,8 +326,13 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         top = max(kern.values(), key=lambda k: k["ms_total"])
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
+        # workload (profiles/r1_ncu_full_tc.md); only known for the kernels profiled there
+        ncu_traffic = {("ign_gru_seq", "routenet_geant2_b4096"): 821.9e6,
+                       ("ign_agg_gru_cell", "routenet_geant2_b4096"): 387.8e6}
         roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": top["gbs"] / hbm_peak, "traffic": None,
+                "frac": top["gbs"] / hbm_peak,
+                "traffic": ncu_traffic.get((top["name"], args.workload)) if n_samples == n_default else None,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "algorithmic_bytes_per_launch": top["bytes"], "avg_launch_ms": top["ms_avg"],
                 "share_of_step": top["ms_total"] / max(sum(k["ms_total"] for k in kern.values()), 1e-9)}
@@ -413,8 +418,20 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
         return 4 * (x.numel() + 2 * h.numel())
 
     zero = lambda *a, **kw: 0
+
+    def b_mlp_head(x, w1, b1, act1, w2, b2, act2, w3, b3, *a, **kw):
+        return 4 * (x.numel() + x.shape[0] + w1.numel() + w2.numel())      # x in, one float per row out
+
+    def b_dense_head(x, w, bias, act, head_w, head_b, *a, **kw):
+        return 4 * (x.numel() + x.shape[0] + w.numel())
+
+    def b_init(feats, sizes, n, hidden, *a, **kw):
+        return 4 * (n * hidden + sum(int(f.numel()) for f in feats))
+
     for name, fn in (("gru_seq", b_gru_seq), ("agg_gru_cell", b_agg), ("segment_reduce", b_seg),
                      ("dense", b_dense), ("csr_build", b_csr), ("gru_cell", b_gru_cell),
+                     ("mlp_head", b_mlp_head), ("dense_head", b_dense_head), ("init_state", b_init),
+                     ("length_order", zero), ("seq_meta", zero), ("steps_build", zero),
                      ("gru_seq_bwd", zero), ("gru_cell_bwd", zero), ("dense_bwd", zero)):
         wrap(name, fn)
     try:
