@@ -128,4 +128,4 @@ class TorchOracle:
         total = mse + reg
         total.backward()
         grads = {k: (v.grad.numpy().copy() if v.grad is not None else np.zeros(v.shape)) for k, v in w.items()}
-        return float(mse), float(reg), preds.detach().numpy(), grads
+        return float(mse.detach()), float(reg.detach()), preds.detach().numpy(), grads

@@ -214,3 +214,32 @@ def test_full_size_properties_geant2_batch():
     assert np.array_equal(pred, np.broadcast_to(pred[0], pred.shape))        # idempotent across replicas
     want = o64.forward(orc.normalize_inputs(g["model_json"], base), w).reshape(-1)
     assert rel_err(pred[0], want) < RTOL and rel_err(pred[-1], want) < RTOL
+
+
+def test_zero_fan_in_and_tiny_samples():
+    """a link no path traverses (empty segment in the sum aggregation), a 1-path sample, in one ragged batch"""
+    g = load_golden("routenet_nsfnet")
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    tiny = {"traffic": [100.0], "delay": [0.3], "jitter": [0.1], "link_capacity": [10000.0, 40000.0, 10000.0],
+            "entities": {"l0": "link", "l1": "link", "l2": "link", "p0": "path"},
+            "adj_links_paths": {"p0": ["l0"]}, "adj_paths_links": {"l0": ["p0"]}}          # l1, l2 unused
+    two = {"traffic": [100.0, 250.0], "delay": [0.3, 0.4], "jitter": [0.1, 0.1],
+           "link_capacity": [10000.0, 40000.0, 10000.0],
+           "entities": {"l0": "link", "l1": "link", "l2": "link", "p0": "path", "p1": "path"},
+           "adj_links_paths": {"p1": ["l2", "l0"], "p0": ["l0"]},
+           "adj_paths_links": {"l2": ["p1"], "l0": ["p1", "p0"]}}                           # l1 unused
+    samples = [tiny, synthetic.routenet_sample("nsfnet", 0, 0), two]
+    tens = [orc.normalize_inputs(g["model_json"], tensors_of(md, s)[0]) for s in samples]
+    graph = eng.prepare(tens, check=True)
+    for st in graph.status.values():
+        assert st.cpu().numpy()[0] == 0
+    pred, state = eng.forward(graph, return_states=True)
+    want_p, want_l = [], []
+    for t in tens:
+        p, s = o64.forward(t, w, return_states=True)
+        want_p.append(p.reshape(-1)); want_l.append(s["link"])
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate(want_p)) < RTOL
+    assert rel_err(state["link"].cpu().numpy(), np.concatenate(want_l)) < RTOL_STATE_TC
+    # single-sample call on the tiny graph (1 path, 3 links)
+    assert rel_err(eng(tens[0]).cpu().numpy().reshape(-1), want_p[0]) < RTOL

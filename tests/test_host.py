@@ -328,3 +328,23 @@ def test_learning_rate_schedules():
                                                    "decay_steps": 80000, "decay_rate": 0.6}})
     assert lr(40000) == pytest.approx(orc.exponential_decay(40000, 1e-3, 80000, 0.6))
     assert LearningRate({"type": "Adam", "learning_rate": 0.01})(5) == 0.01
+
+
+def test_cabi_rejects_oversized_and_bad_arguments_on_the_host():
+    """argument validation happens before any launch, so it is testable without a GPU"""
+    import ctypes as C
+    from ignnition_b200 import _lib
+    lib = _lib.load()
+    one = C.c_void_p(16)          # never dereferenced: the size checks come first
+    rc = lib.ign_csr_build(one, one, None, 1 << 31, 10, 0, one, one, None, None, one, 1 << 40, None)
+    assert rc == -2 and "int32" in _lib.last_error()                    # IGN_ERR_UNSUPPORTED: maximum size
+    rc = lib.ign_csr_build(one, one, None, 100, 10, 0, one, one, None, None, one, 16, None)
+    assert rc == -3 and "workspace" in _lib.last_error()                # IGN_ERR_WORKSPACE
+    rc = lib.ign_gru_seq(one, one, None, 9, one, 32, one, 10, 32, one, one, one, one, None, None, None)
+    assert rc == -1                                                      # too many sources
+    rc = lib.ign_gru_cell(one, one, 10, 48, 48, one, one, one, one, None, 0, None)
+    assert rc == -2 and "not built" in _lib.last_error()
+    assert lib.ign_csr_build_ws_bytes(200_000_000, 10_000_000) > 3_200_000_000   # 4 x E x 4 B of sort buffers
+    assert lib.ign_dense_ws_bytes(256, 256) == 8 * 2 * 256 * 128 and lib.ign_dense_ws_bytes(65, 20) == 0
+    with pytest.raises(RuntimeError, match="IGNNITION"):
+        _lib.check(-1, "x")
