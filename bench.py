@@ -432,6 +432,7 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
                      ("dense", b_dense), ("csr_build", b_csr), ("gru_cell", b_gru_cell),
                      ("mlp_head", b_mlp_head), ("dense_head", b_dense_head), ("init_state", b_init),
                      ("length_order", zero), ("seq_meta", zero), ("steps_build", zero),
+                     ("gru_seq_steps", zero), ("seq_step_plan", zero),
                      ("gru_seq_bwd", zero), ("gru_cell_bwd", zero), ("dense_bwd", zero)):
         wrap(name, fn)
     try:

@@ -47,6 +47,7 @@ class Batch:
         self.offsets: Dict[str, np.ndarray] = {}
         self.n_samples = 0
         self.n_edges: Dict[str, int] = {}
+        self.max_seq: Dict[str, int] = {}     # adjacency -> longest per-destination list (max(seq) + 1)
 
     # ---- packing: one contiguous buffer, 256-byte aligned slices
     def pack(self, pin: bool = False, skip=()):
@@ -143,6 +144,7 @@ def assemble(samples: Sequence[dict], entities: Sequence[str], features: Sequenc
         b.arrays["dst_" + a.name] = _as_i32(np.concatenate(dst))
         b.arrays["seq_" + a.name] = _as_i32(np.concatenate(seq))
         b.n_edges[a.name] = int(b.arrays["src_" + a.name].size)
+        b.max_seq[a.name] = int(b.arrays["seq_" + a.name].max()) + 1 if b.n_edges[a.name] else 0
         if a.uses_params:
             # declared tf.int64 then cast to float32 (generate_model.py:149, :454-456): truncation
             p = [np.trunc(np.asarray(s["params_" + a.name], dtype=np.float64)).astype(np.float32)
@@ -188,6 +190,7 @@ def assemble_tiled(base: dict, n_samples: int, entities: Sequence[str],
         b.arrays["dst_" + a.name] = _as_i32((dst[None, :] + (ar * nd)[:, None]).reshape(-1))
         b.arrays["seq_" + a.name] = _as_i32(np.tile(seq, n_samples))
         b.n_edges[a.name] = int(src.size) * n_samples
+        b.max_seq[a.name] = int(seq.max()) + 1 if seq.size else 0
     for q in sequences:
         ps, pc = position_table(base, q)
         b.arrays["pos_off_" + q.key] = _as_i32(np.arange(n_samples + 1, dtype=np.int64) * ps.size)

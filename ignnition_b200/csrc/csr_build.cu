@@ -385,6 +385,41 @@ __global__ void seq_meta_kernel(const int* __restrict__ steps_rowptr, const int*
   meta[i] = make_int4(d, lo, len, len > 0 ? steps[lo] : IGN_STEP_ZERO);
 }
 
+// ---- step-major plan of an ordered aggregation (destinations sorted by descending length) ----
+// cnt[l] = number of destinations with exactly l steps (l clamped to max_steps)
+__global__ void seq_len_hist_kernel(const int4* __restrict__ meta, int64_t n, int max_steps, int* __restrict__ cnt) {
+  __shared__ int h[1025];                              // max_steps <= 1024: per-CTA histogram first
+  for (int k = threadIdx.x; k <= max_steps; k += blockDim.x) h[k] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&h[min(meta[i].z, max_steps)], 1);
+  __syncthreads();
+  for (int k = threadIdx.x; k <= max_steps; k += blockDim.x)
+    if (h[k]) atomicAdd(&cnt[k], h[k]);
+}
+// nt[t] = #destinations with more than t steps (a prefix of the sorted order); off[t] = sum_{u<t} nt[u]
+__global__ void seq_plan_scan_kernel(const int* __restrict__ cnt, int max_steps, int* __restrict__ nt,
+                                     int* __restrict__ off) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int run = 0;
+  for (int t = max_steps - 1; t >= 0; --t) {        // suffix sums
+    run += cnt[t + 1];
+    nt[t] = run;
+  }
+  int o = 0;
+  for (int t = 0; t < max_steps; ++t) { off[t] = o; o += nt[t]; }
+  off[max_steps] = o;
+}
+// steps_T[off[t] + i] = step t of the i-th destination of the sorted order
+__global__ void seq_steps_transpose_kernel(const int4* __restrict__ meta, const int* __restrict__ steps, int64_t n,
+                                           int max_steps, const int* __restrict__ off, int* __restrict__ steps_T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 m = meta[i];
+  const int len = min(m.z, max_steps);
+  for (int t = 0; t < len; ++t) steps_T[off[t] + i] = steps[m.y + t];
+}
+
 inline unsigned grid1d(int64_t n, int threads = 256) { return (unsigned)ign_cdiv(n > 0 ? n : 1, threads); }
 
 }  // namespace
@@ -540,5 +575,29 @@ extern "C" int ign_seq_meta(const int32_t* steps_rowptr, const int32_t* steps, c
   seq_meta_kernel<<<grid1d(num_dst), 256, 0, ign_stream(stream)>>>(steps_rowptr, steps, order, num_dst,
                                                                     reinterpret_cast<int4*>(meta));
   IGN_CHECK_LAUNCH("seq_meta");
+  return IGN_OK;
+}
+
+extern "C" int ign_seq_step_plan(const int32_t* meta, const int32_t* steps, int64_t num_dst, int max_steps,
+                                 int32_t* nt, int32_t* off, int32_t* steps_T, void* stream) {
+  IGN_REQUIRE(num_dst >= 0 && max_steps >= 1 && max_steps <= 1024, IGN_ERR_INVALID,
+              "IGNNITION: seq_step_plan: bad argument (1 <= max_steps <= 1024)");
+  IGN_REQUIRE(meta && steps && nt && off && steps_T, IGN_ERR_INVALID, "IGNNITION: seq_step_plan: null pointer");
+  cudaStream_t st = ign_stream(stream);
+  // nt doubles as the histogram scratch: cnt lives in off[] until the scan overwrites both in order
+  IGN_CUDA(cudaMemsetAsync(off, 0, (size_t)(max_steps + 1) * sizeof(int), st));
+  if (num_dst > 0) {
+    seq_len_hist_kernel<<<grid1d(num_dst), 256, 0, st>>>(reinterpret_cast<const int4*>(meta), num_dst, max_steps, off);
+    IGN_CHECK_LAUNCH("seq_len_hist");
+  }
+  // scan reads cnt from a copy: move the histogram into steps_T's first max_steps+1 ints first
+  IGN_CUDA(cudaMemcpyAsync(steps_T, off, (size_t)(max_steps + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  seq_plan_scan_kernel<<<1, 32, 0, st>>>(steps_T, max_steps, nt, off);
+  IGN_CHECK_LAUNCH("seq_plan_scan");
+  if (num_dst > 0) {
+    seq_steps_transpose_kernel<<<grid1d(num_dst), 256, 0, st>>>(reinterpret_cast<const int4*>(meta), steps, num_dst,
+                                                                  max_steps, off, steps_T);
+    IGN_CHECK_LAUNCH("seq_steps_transpose");
+  }
   return IGN_OK;
 }

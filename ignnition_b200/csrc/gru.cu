@@ -369,6 +369,28 @@ extern "C" int ign_agg_gru_cell(const int32_t* rowptr, const int32_t* col, const
   return IGN_ERR_UNSUPPORTED;
 }
 
+// step-synchronous tensor-core variant of the ordered update (gru_step_tc.cu)
+int ign_gru_step_tc_launch(int t, const int* nt, const int* off, int64_t num_dst, int64_t rows_bound, const int* meta,
+                           const int* steps_T, int n_src, const float* const* srcs, const float* h0, float* hs,
+                           float* out, float* h_seq, const float* kernel, const float* rkernel, const float* bias,
+                           cudaStream_t st);
+
+extern "C" int ign_gru_seq_step(int t, const int32_t* nt, const int32_t* off, const int32_t* meta,
+                                const int32_t* steps_T, int n_src, const float* const* srcs, int f_in, const float* h0,
+                                float* hs, int64_t num_dst, int units, const float* kernel,
+                                const float* recurrent_kernel, const float* bias, float* out, float* h_seq,
+                                void* stream) {
+  IGN_REQUIRE(num_dst >= 0 && t >= 0, IGN_ERR_INVALID, "IGNNITION: gru_seq_step: bad argument");
+  IGN_REQUIRE(n_src >= 1 && n_src <= IGN_MAX_SOURCES && srcs, IGN_ERR_INVALID, "IGNNITION: gru_seq_step: bad sources");
+  IGN_REQUIRE(f_in == 32 && units == 32, IGN_ERR_UNSUPPORTED,
+              "IGNNITION: gru_seq_step: built for 32-wide messages and states (got %d, %d)", f_in, units);
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(nt && off && meta && steps_T && h0 && hs && out && kernel && recurrent_kernel && bias, IGN_ERR_INVALID,
+              "IGNNITION: gru_seq_step: null pointer");
+  return ign_gru_step_tc_launch(t, nt, off, num_dst, num_dst, meta, steps_T, n_src, srcs, h0, hs, out, h_seq, kernel,
+                                recurrent_kernel, bias, ign_stream(stream));
+}
+
 // tensor-core variant (gru_cell_tc.cu)
 bool ign_gru_cell_tc_supported(int f_in, int units);
 size_t ign_gru_cell_tc_ws(int units);

@@ -40,6 +40,8 @@ class DeviceGraph:
         self.steps: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.order: Dict[str, torch.Tensor] = {}
         self.meta: Dict[str, torch.Tensor] = {}
+        self.max_seq: Dict[str, int] = {}                 # host-known longest list per adjacency
+        self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
         self.status: Dict[str, torch.Tensor] = {}
         self.h2d_bytes = 0
 
@@ -60,13 +62,16 @@ class _MPPlan:
 
 class Engine:
     def __init__(self, model: ModelDescription, device: Optional[torch.device] = None, seed: int = 0,
-                 csr_mode: int = ops.CSR_SORT, sort_by_length: bool = True):
+                 csr_mode: int = ops.CSR_SORT, sort_by_length: bool = True, max_step_launches: int = 0):
         self.model = model
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.type != "cuda":
             raise RuntimeError("IGNNITION: ignnition_b200 runs on CUDA devices only (no CPU fallback)")
         self.csr_mode = csr_mode
         self.sort_by_length = sort_by_length
+        # ordered updates whose longest sequence is <= this run step-synchronously (one launch per step,
+        # ign_gru_seq_step); 0 = always the sequence walk (ign_gru_seq), which is faster in round 1
+        self.max_step_launches = max_step_launches
         self.dims = model.get_input_dimensions()
         self.entities = [e.name for e in model.get_entities()]
         self.hidden = {e.name: e.hidden_state_dimension for e in model.get_entities()}
@@ -271,6 +276,7 @@ class Engine:
             g.t[k] = g.buf[off:off + n * 4].view(tdt).view(*shape) if n else torch.empty(shape, dtype=tdt, device=self.device)
         g.num = dict(batch.num)
         g.n_samples = batch.n_samples
+        g.max_seq = dict(batch.max_seq)
         return g
 
     def build_graph(self, g: DeviceGraph, training: bool = False, check: bool = False) -> DeviceGraph:
@@ -305,6 +311,11 @@ class Engine:
                     g.order[p.key] = ops.length_order(g.steps[p.key][0])
                 if g.num[p.dst] > 0:
                     g.meta[p.key] = ops.seq_meta(g.steps[p.key][0], g.steps[p.key][1], g.order.get(p.key))
+                    # short sequences (RouteNet paths): one streaming launch per step instead of a walk
+                    max_steps = sum(g.max_seq.get(a.name, 1 << 30) for a in p.adjs)
+                    if (p.key in g.order and 1 <= max_steps <= self.max_step_launches and p.msg_dim == 32
+                            and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()):
+                        g.step_plan[p.key] = (ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
         return g
 
     def prepare(self, samples_or_batch, labels=None, training: bool = False, check: bool = False) -> DeviceGraph:
@@ -393,8 +404,12 @@ class Engine:
             h_seq = None
             if tape is not None:
                 h_seq = torch.empty(steps.numel(), h.shape[1], dtype=torch.float32, device=self.device)
-            ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq,
-                        meta=g.meta.get(p.key))
+            if p.key in g.step_plan and ops.tensor_cores_enabled():
+                plan, max_steps = g.step_plan[p.key]
+                ops.gru_seq_steps(plan, g.meta[p.key], srcs, h, K, R, B, max_steps, out=out, h_seq=h_seq)
+            else:
+                ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq,
+                            meta=g.meta.get(p.key))
             if tape is not None:
                 tape.append(("seq_gru", p, [state[a.src] for a in p.adjs], h, h_seq))
             return out

@@ -175,6 +175,37 @@ def seq_meta(steps_rowptr, steps, order) -> torch.Tensor:
     return meta
 
 
+def seq_step_plan(meta, steps, max_steps: int):
+    """(nt[max_steps], off[max_steps+1], steps_T) of ign_seq_step_plan."""
+    lib = _lib.load()
+    n = meta.shape[0]
+    dev = meta.device
+    nt = torch.empty(max_steps, dtype=torch.int32, device=dev)
+    off = torch.empty(max_steps + 1, dtype=torch.int32, device=dev)
+    steps_t = torch.empty(max(int(steps.numel()), max_steps + 1), dtype=torch.int32, device=dev)
+    _lib.check(lib.ign_seq_step_plan(_i(meta), _i(steps), n, max_steps, _i(nt), _i(off), _i(steps_t), _stream()),
+               "seq_step_plan")
+    return nt, off, steps_t
+
+
+def gru_seq_steps(plan, meta, srcs: List[torch.Tensor], h0, kernel, rkernel, bias, max_steps: int, out=None,
+                  h_seq=None, hs=None):
+    """Ordered update as max_steps step-synchronous launches (ign_gru_seq_step)."""
+    lib = _lib.load()
+    nt, off, steps_t = plan
+    n, units = h0.shape
+    if out is None:
+        out = torch.empty_like(h0)
+    if hs is None:
+        hs = torch.empty_like(h0)
+    sp = _ptr_array(srcs, torch.float32)
+    for t in range(max_steps):
+        _lib.check(lib.ign_gru_seq_step(t, _i(nt), _i(off), _i(meta), _i(steps_t), len(srcs), sp, srcs[0].shape[1],
+                                        _f(h0), _f(hs), n, units, _f(kernel), _f(rkernel), _f(bias), _f(out),
+                                        _f(h_seq), _stream()), "gru_seq_step")
+    return out
+
+
 def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rkernel, bias, out=None,
             h_seq=None, meta=None):
     lib = _lib.load()

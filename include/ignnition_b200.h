@@ -164,6 +164,23 @@ int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, const int32_t
                 float* h_seq, const int32_t* meta /* nullable: output of ign_seq_meta for this order */,
                 void* stream);
 
+/* Step-synchronous form of ign_gru_seq for short sequences (RouteNet paths: <= 6 links): launch t
+ * executes step t of every destination that has one.  Needs the destinations sorted by descending
+ * length (ign_length_order), their walk plan (ign_seq_meta) and the step-major plan of
+ * ign_seq_step_plan:  nt[t] = destinations with more than t steps (a prefix of the sorted order),
+ * off[t] = sum_{u<t} nt[u], steps_T[off[t] + i] = step t of the i-th sorted destination
+ * (steps_T must hold max(sum len, max_steps + 1) ints; max_steps >= the longest sequence).
+ * hs[num_dst, units] is the running state in sorted order between launches; the launch that runs a
+ * destination's last step writes out[d]; launch 0 also copies the state of destinations without any
+ * step.  Call for t = 0 .. max_steps-1.  Same results as ign_gru_seq.  32-wide, tcgen05 3xTF32. */
+int ign_seq_step_plan(const int32_t* meta, const int32_t* steps, int64_t num_dst, int max_steps,
+                      int32_t* nt, int32_t* off, int32_t* steps_T, void* stream);
+int ign_gru_seq_step(int t, const int32_t* nt, const int32_t* off, const int32_t* meta,
+                     const int32_t* steps_T, int n_src, const float* const* srcs, int f_in,
+                     const float* h0, float* hs, int64_t num_dst, int units, const float* kernel,
+                     const float* recurrent_kernel, const float* bias, float* out, float* h_seq,
+                     void* stream);
+
 /* Dense layer y = act(x W + b): Feed_forward_Layer (auxilary_classes.py:800-866), used by the
  * message MLP (generate_model.py:448-473), the FF update (:594-600) and the readout (:607-629).
  * bias nullable.  pre_act (nullable) receives x W + b (saved for the backward pass).

@@ -256,6 +256,50 @@ def test_gru_seq_vs_masked_rnn(fi, u, use_order):
     assert rel_err(got2, want2) < RTOL
 
 
+@pytest.mark.parametrize("max_len", [1, 6, 16])
+def test_gru_seq_step_synchronous(max_len):
+    """step-synchronous launches == the sequence walk == masked RNN of the oracle (incl. empty destinations,
+    zero messages and the saved per-step states)"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(max_len)
+    n_dst, n_src, u = 3000, 500, 32
+    lens = rng.randint(0, max_len + 1, n_dst)
+    lens[:5] = max_len
+    dst = np.repeat(np.arange(n_dst), lens)
+    seq = np.concatenate([np.arange(l) for l in lens])
+    src = rng.randint(0, n_src, len(dst))
+    states = (rng.randn(n_src, u) * 0.5).astype(np.float32)
+    h0 = rng.randn(n_dst, u).astype(np.float32)
+    K, R, b = gru_weights(rng, u, u)
+    r, c, _ = orc.csr_from_edges(src, dst, seq, n_dst)
+    c = c.copy()
+    zero_slots = rng.rand(len(c)) < 0.05
+    c[zero_slots] = -1                                  # IGN_STEP_ZERO entries: zero messages inside a sequence
+    rp, cc = dev(r, torch.int32), dev(c, torch.int32)
+    order = ops.length_order(rp)
+    meta = ops.seq_meta(rp, cc, order)
+    plan = ops.seq_step_plan(meta, cc, max_len)
+    nt = plan[0].cpu().numpy()
+    assert np.array_equal(nt, [(lens > t).sum() for t in range(max_len)])
+    h_seq = torch.zeros(len(dst), u, device="cuda")
+    got = ops.gru_seq_steps(plan, meta, [dev(states)], dev(h0), dev(K), dev(R), dev(b), max_len, h_seq=h_seq).cpu().numpy()
+    h_seq2 = torch.zeros(len(dst), u, device="cuda")
+    walk = ops.gru_seq(rp, cc, order, [dev(states)], dev(h0), dev(K), dev(R), dev(b), h_seq=h_seq2, meta=meta).cpu().numpy()
+    padded = np.zeros((n_dst, max_len, u), np.float64)
+    msgs = np.where(c[:, None] >= 0, states[np.maximum(c, 0)], 0.0)
+    d_sorted = np.repeat(np.arange(n_dst), lens)
+    padded[d_sorted, np.arange(len(c)) - r[d_sorted]] = msgs
+    K64, R64, b64 = K.astype(np.float64), R.astype(np.float64), b.astype(np.float64)
+    cell = lambda a, h: orc.gru_cell(a, h, K64, R64, b64)
+    nz = lens > 0
+    want = h0.astype(np.float64).copy()
+    want[nz] = orc.masked_rnn_last(cell, padded[nz], h0[nz].astype(np.float64), lens[nz])
+    assert rel_err(got, want) < RTOL and rel_err(walk, want) < RTOL
+    assert np.array_equal(got[~nz], h0[~nz])
+    assert np.array_equal(h_seq.cpu().numpy()[r[1:][nz] - 1], got[nz])
+    assert rel_err(h_seq.cpu().numpy(), h_seq2.cpu().numpy().astype(np.float64)) < RTOL
+
+
 def test_gru_seq_interleave_step_table(golden):
     """Q-size step 1: step table from ign_steps_build == reference interleave of the padded tensors."""
     from ignnition_b200 import ops

@@ -100,6 +100,23 @@ def test_forward_fp32_twin_kernels():
         ops.set_tensor_cores(prev)
 
 
+def test_step_synchronous_engine_path():
+    """Engine(max_step_launches=16): ordered updates as one launch per step give the same predictions"""
+    from ignnition_b200 import Engine
+    for case in ("routenet_nsfnet", "qsize_nsfnet"):
+        g = load_golden(case)
+        dims = g["reference_meta"]["dimensions"]
+        md, _, o64, w = make(g["model_json"], dims)
+        eng = Engine(md, device="cuda:0", max_step_launches=16)
+        eng.set_weights(w)
+        tens = [orc.normalize_inputs(g["model_json"], t) for t in g["reference_tensors"]]
+        graph = eng.prepare(tens)
+        assert graph.step_plan
+        pred = eng.forward(graph).cpu().numpy().reshape(-1)
+        want = np.concatenate([o64.forward(t, w).reshape(-1) for t in tens])
+        assert rel_err(pred, want) < RTOL
+
+
 def test_qsize_batch_interleave():
     g = load_golden("qsize_nsfnet")
     dims = g["reference_meta"]["dimensions"]
