@@ -55,6 +55,11 @@ SIGNATURES = {
                                _p, _p, _p, _p]),
     "ign_l2_reg": (_int, [_p, _i64, _f, _p, _p, _p]),
     "ign_adam_step": (_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
+    "ign_attention_ws_bytes": (_sz, [_i64, _i64, _int]),
+    "ign_attention_aggregate": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "ign_partner_index": (_int, [_p, _p, _p, _i64, _p, _p]),
+    "ign_mul": (_int, [_i64, _p, _p, _p, _p]),
+    "ign_conv_finish": (_int, [_p, _p, _p, _int, _i64, _int, _p, _p]),
     "ign_axpy": (_int, [_i64, _f, _p, _p, _p]),
 }
 

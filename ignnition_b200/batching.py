@@ -126,6 +126,7 @@ def assemble(samples: Sequence[dict], entities: Sequence[str], features: Sequenc
         b.offsets[e] = off
         b.num[e] = int(off[-1])
         b.arrays["sample_of_" + e] = np.repeat(np.arange(len(samples), dtype=np.int32), counts)
+        b.arrays["offsets_" + e] = _as_i32(off)
     for name, ent, size in features:
         parts = []
         for s in samples:
@@ -179,6 +180,7 @@ def assemble_tiled(base: dict, n_samples: int, entities: Sequence[str],
         b.offsets[e] = ar_off = np.arange(n_samples + 1, dtype=np.int64) * n
         b.num[e] = int(ar_off[-1])
         b.arrays["sample_of_" + e] = np.repeat(ar.astype(np.int32), n)
+        b.arrays["offsets_" + e] = _as_i32(ar_off)
     for name, ent, size in features:
         b.arrays["feat_" + name] = _as_f32(feature_fns[name](rng, b.num[ent] * size))
     for a in adjacencies:

@@ -1,0 +1,162 @@
+// Attention aggregation of the generated model (reference: Attention_aggr.calculate_input,
+// auxilary_classes.py:278-344), on the CSR by destination.
+//
+// What the reference computes, restated on the CSR (edge j of destination d sits at column
+// s = j - rowptr[d] of the padded [num_dst, max_len, 1] tensor):
+//   a_j       = leaky_relu([m_j . kernel1 | h_d . kernel2] . attn_kernel, 0.2)
+//             = leaky_relu(m_j . (kernel1 . ak_top) + h_d . (kernel2 . ak_bottom))      (associativity)
+//   aux[d, s] = a_j, zero where destination d has no message at column s
+//   coef      = softmax(aux, axis = 0): over the DESTINATIONS of one sample, per column s, zero pads
+//               included (SURVEY section 8f rank 3 "reproduce as-is")
+//   out[d]    = sum_j coef[d, s_j] * m_j
+// The two matrix-vector folds and the per-row scores are ign_dense calls on the host side; this file
+// does the column softmax and the weighted segment sum.  Column statistics: max by integer atomicMax
+// on an order-preserving encoding, sum by fp64 atomicAdd (order-independent after rounding to fp32).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int enc_f(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec_f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+struct AttnWs {
+  int* colmax;      // [n_cols] encoded float
+  int* cnt;         // [n_cols] destinations with a message at this column
+  double* colsum;   // [n_cols]
+  float* a;         // [E]
+};
+
+__device__ __forceinline__ int sample_of(const int* __restrict__ off, int n_samples, int d) {
+  int lo = 0, hi = n_samples;                 // off[lo] <= d < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= d) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void attn_init_kernel(int64_t n_cols, AttnWs w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cols) return;
+  w.colmax[i] = enc_f(-INFINITY);
+  w.cnt[i] = 0;
+  w.colsum[i] = 0.0;
+}
+
+__global__ void attn_score_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                  const float* __restrict__ src_score, const float* __restrict__ dst_score,
+                                  const int* __restrict__ off, int n_samples, int64_t num_dst, int max_len, AttnWs w) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= num_dst) return;
+  const int lo = rowptr[d], hi = rowptr[d + 1];
+  if (hi == lo) return;
+  const int64_t base = (int64_t)sample_of(off, n_samples, (int)d) * max_len;
+  const float q = dst_score[d];
+  for (int j = lo; j < hi; ++j) {
+    float a = src_score[col[j]] + q;
+    a = a > 0.f ? a : 0.2f * a;               // tf.keras.layers.LeakyReLU(alpha=0.2), auxilary_classes.py:319
+    w.a[j] = a;
+    atomicMax(&w.colmax[base + (j - lo)], enc_f(a));
+    atomicAdd(&w.cnt[base + (j - lo)], 1);
+  }
+}
+
+__device__ __forceinline__ float col_shift(const AttnWs& w, int64_t c, int n_in_sample) {
+  float m = dec_f(w.colmax[c]);
+  if (w.cnt[c] < n_in_sample) m = fmaxf(m, 0.f);       // zero pads take part in the softmax
+  return m;
+}
+
+__global__ void attn_sum_kernel(const int* __restrict__ rowptr, const int* __restrict__ off, int n_samples,
+                                int64_t num_dst, int max_len, AttnWs w) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= num_dst) return;
+  const int lo = rowptr[d], hi = rowptr[d + 1];
+  if (hi == lo) return;
+  const int s = sample_of(off, n_samples, (int)d);
+  const int n_in = off[s + 1] - off[s];
+  const int64_t base = (int64_t)s * max_len;
+  for (int j = lo; j < hi; ++j) {
+    const int64_t c = base + (j - lo);
+    atomicAdd(&w.colsum[c], (double)expf(w.a[j] - col_shift(w, c, n_in)));
+  }
+}
+
+// 8 lanes per destination, float4 columns strided by 8 lanes
+__global__ void attn_apply_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                  const float* __restrict__ rows, int F, const int* __restrict__ off, int n_samples,
+                                  int64_t num_dst, int max_len, AttnWs w, float* __restrict__ out) {
+  const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int gl = threadIdx.x & 7;
+  if (d >= num_dst) return;
+  const int lo = rowptr[d], hi = rowptr[d + 1];
+  const int s = sample_of(off, n_samples, (int)d);
+  const int n_in = off[s + 1] - off[s];
+  const int64_t base = (int64_t)s * max_len;
+  for (int f = gl * 4; f < F; f += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = lo; j < hi; ++j) {
+      const int64_t c = base + (j - lo);
+      const float m = col_shift(w, c, n_in);
+      const double den = w.colsum[c] + (double)(n_in - w.cnt[c]) * (double)expf(-m);
+      const float coef = (float)((double)expf(w.a[j] - m) / den);
+      const float4 v = *reinterpret_cast<const float4*>(rows + (int64_t)col[j] * F + f);
+      acc.x += coef * v.x; acc.y += coef * v.y; acc.z += coef * v.z; acc.w += coef * v.w;
+    }
+    *reinterpret_cast<float4*>(out + d * F + f) = acc;
+  }
+}
+
+AttnWs carve(void* ws, int64_t n_edges, int64_t n_cols) {
+  AttnWs w;
+  char* p = static_cast<char*>(ws);
+  w.colsum = reinterpret_cast<double*>(p); p += ign_align_up(n_cols * sizeof(double), 256);
+  w.colmax = reinterpret_cast<int*>(p);    p += ign_align_up(n_cols * sizeof(int), 256);
+  w.cnt = reinterpret_cast<int*>(p);       p += ign_align_up(n_cols * sizeof(int), 256);
+  w.a = reinterpret_cast<float*>(p);
+  (void)n_edges;
+  return w;
+}
+
+}  // namespace
+
+extern "C" size_t ign_attention_ws_bytes(int64_t n_edges, int64_t n_samples, int max_len) {
+  const int64_t n_cols = (n_samples > 0 ? n_samples : 0) * (int64_t)(max_len > 0 ? max_len : 0);
+  return ign_align_up(n_cols * sizeof(double), 256) + 2 * ign_align_up(n_cols * sizeof(int), 256) +
+         ign_align_up((n_edges > 0 ? n_edges : 0) * sizeof(float), 256) + 256;
+}
+
+extern "C" int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const float* rows, int F,
+                                       const float* src_score, const float* dst_score,
+                                       const int32_t* sample_offsets, int64_t n_samples, int64_t num_dst,
+                                       int64_t n_edges, int max_len, float* out, void* ws, size_t ws_bytes,
+                                       void* stream) {
+  IGN_REQUIRE(num_dst >= 0 && n_edges >= 0 && n_samples >= 0 && max_len >= 0, IGN_ERR_INVALID,
+              "IGNNITION: attention: negative size");
+  IGN_REQUIRE(F > 0 && F % 4 == 0, IGN_ERR_UNSUPPORTED, "IGNNITION: attention: message width must be a multiple of 4");
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr && out && sample_offsets && dst_score, IGN_ERR_INVALID, "IGNNITION: attention: null pointer");
+  IGN_REQUIRE(n_edges == 0 || (col && rows && src_score), IGN_ERR_INVALID, "IGNNITION: attention: null pointer");
+  IGN_REQUIRE(ws_bytes >= ign_attention_ws_bytes(n_edges, n_samples, max_len) && (ws || ws_bytes == 0),
+              IGN_ERR_INVALID, "IGNNITION: attention: workspace too small");
+  cudaStream_t st = ign_stream(stream);
+  const int64_t n_cols = n_samples * (int64_t)max_len;
+  AttnWs w = carve(ws, n_edges, n_cols);
+  if (n_cols > 0) {
+    attn_init_kernel<<<(unsigned)ign_cdiv(n_cols, 256), 256, 0, st>>>(n_cols, w);
+    IGN_CHECK_LAUNCH("attn_init");
+    attn_score_kernel<<<(unsigned)ign_cdiv(num_dst, 128), 128, 0, st>>>(rowptr, col, src_score, dst_score,
+                                                                        sample_offsets, (int)n_samples, num_dst, max_len, w);
+    IGN_CHECK_LAUNCH("attn_score");
+    attn_sum_kernel<<<(unsigned)ign_cdiv(num_dst, 128), 128, 0, st>>>(rowptr, sample_offsets, (int)n_samples, num_dst,
+                                                                      max_len, w);
+    IGN_CHECK_LAUNCH("attn_sum");
+  }
+  attn_apply_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(rowptr, col, rows, F, sample_offsets,
+                                                                          (int)n_samples, num_dst, max_len, w, out);
+  IGN_CHECK_LAUNCH("attn_apply");
+  return IGN_OK;
+}

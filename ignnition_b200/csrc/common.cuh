@@ -47,6 +47,7 @@ void ign_count_launch();
 static inline cudaStream_t ign_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ign_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t ign_align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 static inline size_t ign_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------

@@ -158,7 +158,7 @@ __global__ void gather_concat_kernel(ConcatParts p, int64_t rows, float* __restr
   for (int k = 0; k < p.n; ++k) {
     if (c < p.width[k]) {
       const int64_t r = p.idx[k] ? (int64_t)p.idx[k][row] : row;
-      v = p.ptr[k][r * p.width[k] + c];
+      if (r >= 0) v = p.ptr[k][r * p.width[k] + c];        // negative index: a zero (padded) row
       break;
     }
     c -= p.width[k];
@@ -171,7 +171,63 @@ __global__ void axpy_kernel(int64_t n, float a, const float* __restrict__ x, flo
   if (i < n) y[i] += a * x[i];
 }
 
+// Concat_aggr along the feature axis (generate_model.py:496-505, concat_axis = 2): position j of the
+// first source's CSR (destination d, column s = j - rowptr[d]) pairs with column s of another source's
+// padded block: that source's row index, or -1 where its block holds zeros.
+__global__ void partner_index_kernel(const int* __restrict__ rowptr0, const int* __restrict__ rowptr1,
+                                     const int* __restrict__ idx1, int64_t num_dst, int* __restrict__ out) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= num_dst) return;
+  const int lo0 = rowptr0[d], n0 = rowptr0[d + 1] - lo0;
+  const int lo1 = rowptr1[d], n1 = rowptr1[d + 1] - lo1;
+  for (int s = 0; s < n0; ++s) out[lo0 + s] = s < n1 ? idx1[lo1 + s] : -1;
+}
+
+__global__ void mul_kernel(int64_t n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i];
+}
+
+// Conv_aggr tail (auxilary_classes.py:388-401): act((neighbour_sum + self) / degree)
+__global__ void conv_finish_kernel(const float* __restrict__ nsum, const float* __restrict__ self,
+                                   const int* __restrict__ rowptr, int F, int64_t n, int act, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * F) return;
+  const int64_t d = i / F;
+  const float deg = (float)(rowptr[d + 1] - rowptr[d]);
+  out[i] = act_fwd(act, (nsum[i] + self[i]) / deg);         // degree 0 -> inf / nan, as in the reference
+}
+
 }  // namespace
+
+extern "C" int ign_partner_index(const int32_t* rowptr0, const int32_t* rowptr1, const int32_t* idx1, int64_t num_dst,
+                                 int32_t* out, void* stream) {
+  IGN_REQUIRE(num_dst >= 0, IGN_ERR_INVALID, "IGNNITION: partner_index: negative size");
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr0 && rowptr1, IGN_ERR_INVALID, "IGNNITION: partner_index: null pointer");
+  partner_index_kernel<<<(unsigned)ign_cdiv(num_dst, 128), 128, 0, ign_stream(stream)>>>(rowptr0, rowptr1, idx1, num_dst, out);
+  IGN_CHECK_LAUNCH("partner_index");
+  return IGN_OK;
+}
+
+extern "C" int ign_mul(int64_t n, const float* a, const float* b, float* out, void* stream) {
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: mul: negative size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(a && b && out, IGN_ERR_INVALID, "IGNNITION: mul: null pointer");
+  mul_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(n, a, b, out);
+  IGN_CHECK_LAUNCH("mul");
+  return IGN_OK;
+}
+
+extern "C" int ign_conv_finish(const float* nsum, const float* self, const int32_t* rowptr, int F, int64_t n, int act,
+                               float* out, void* stream) {
+  IGN_REQUIRE(n >= 0 && F > 0, IGN_ERR_INVALID, "IGNNITION: conv_finish: bad size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(nsum && self && rowptr && out, IGN_ERR_INVALID, "IGNNITION: conv_finish: null pointer");
+  conv_finish_kernel<<<(unsigned)ign_cdiv(n * F, 256), 256, 0, ign_stream(stream)>>>(nsum, self, rowptr, F, n, act, out);
+  IGN_CHECK_LAUNCH("conv_finish");
+  return IGN_OK;
+}
 
 extern "C" int ign_segment_reduce(int op, const int32_t* rowptr, const int32_t* col, const float* src_states,
                                   int F, int64_t num_dst, float* out, void* stream) {

@@ -41,6 +41,7 @@ class DeviceGraph:
         self.order: Dict[str, torch.Tensor] = {}
         self.meta: Dict[str, torch.Tensor] = {}
         self.max_seq: Dict[str, int] = {}                 # host-known longest list per adjacency
+        self.partner: Dict[str, list] = {}               # concat axis 2: per-source row index per CSR position
         self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
         self.status: Dict[str, torch.Tensor] = {}
         self.h2d_bytes = 0
@@ -58,6 +59,10 @@ class _MPPlan:
         self.op = ops.OP_SUM
         self.seq: Optional[SequenceSpec] = None
         self.msg_dim = 0
+        self.concat2 = False   # concat along the feature axis: rows gathered per CSR position of source 0
+        self.msg_rows = False  # ordered walk over message-MLP rows instead of source states
+        self.attn = False      # attention aggregation: column softmax over one sample's destinations
+        self.conv = False      # convolution aggregation: (sum . conv_kernel + self) / degree, activation
 
 
 class Engine:
@@ -79,6 +84,7 @@ class Engine:
         self.features = [(f.name, e.name, f.size) for e in model.get_entities() for f in e.features]
         self.adjacencies = [AdjacencySpec(a[0], a[1], a[2], a[3] == "True") for a in model.get_adjecency_info()]
         self._adj_by_name = {a.name: a for a in self.adjacencies}
+        self._msg_adjacencies = list(self.adjacencies)
         self._needs_perm = set()
         self.plans: List[List[_MPPlan]] = []
         self.sequences: List[SequenceSpec] = []
@@ -152,21 +158,65 @@ class Engine:
                                     "either (generate_model.py:458 vs :470)" % i)
                         d = self._add_ff("%s_to_%s_message_creation_%d" % (src.name, p.dst, k), op.model, din)
                     msg_dims.append(d)
-                if len(set(msg_dims)) != 1:
+                concat2 = mp.aggregation.type == "concat" and mp.aggregation.concat_axis == 2
+                if len(set(msg_dims)) != 1 and not concat2:
                     raise RuntimeError("IGNNITION: all sources of a message passing must send messages of "
                                        "the same dimension, got %s" % msg_dims)
                 p.msg_dim = msg_dims[0]
                 agg = mp.aggregation.type
-                if agg in ("sum", "mean", "max"):
+                has_msg_nn = any(op.type == "feed_forward_nn" for src in mp.source_entities
+                                 for op in src.message_formation)
+                if concat2:
+                    # padded blocks side by side along the FEATURE axis, lengths of the first source
+                    # (generate_model.py:496-505); one GRU walk over rows gathered per step
+                    if mp.update.type != "recurrent_nn":
+                        raise RuntimeError("IGNNITION: concat aggregation needs a recurrent update")
+                    p.msg_dim = sum(msg_dims)
+                    p.kind = "seq_gru"
+                    p.concat2 = True
+                    for a in p.adjs:
+                        self._needs_perm.add(a.name)
+                elif agg in ("sum", "mean", "max"):
                     p.op = {"sum": ops.OP_SUM, "mean": ops.OP_MEAN, "max": ops.OP_MAX}[agg]
                     p.kind = "agg_gru" if mp.update.type == "recurrent_nn" else "agg_ff"
-                elif agg in ("ordered", "interleave"):
+                elif agg in ("ordered", "interleave") or (agg == "concat" and mp.aggregation.concat_axis == 1):
+                    # concat along axis 1 = the sources' padded blocks one after the other
+                    # (generate_model.py:496-505): the multi-source ordered layout of the step table
                     if mp.update.type != "recurrent_nn":
                         raise RuntimeError("IGNNITION: %s aggregation needs a recurrent update" % agg)
                     p.kind = "seq_gru"
                     if len(p.adjs) > 1 or agg == "interleave":
+                        if has_msg_nn:
+                            raise RuntimeError("IGNNITION: message neural networks feeding a multi-source ordered "
+                                               "aggregation are not built yet (step table indexes source rows)")
                         p.seq = SequenceSpec(p.key, p.dst, p.adjs, agg == "interleave")
                         self.sequences.append(p.seq)
+                    p.msg_rows = has_msg_nn           # the walk reads message rows (edge order) through perm
+                elif agg == "attention":
+                    if len(p.adjs) != 1:
+                        raise RuntimeError("IGNNITION: attention over several sources is not built yet in the B200 "
+                                           "engine (the reference sums colliding padded columns, SURVEY quirk 7)")
+                    if p.msg_dim != fd:          # [m.kernel1 | h.kernel2] . attn_kernel[2 * fd, 1] must conform
+                        raise RuntimeError("IGNNITION: attention needs messages as wide as the destination state "
+                                           "(%d vs %d)" % (p.msg_dim, fd))
+                    self._add_param(p.dst + "_attention/kernel1", (p.msg_dim, p.msg_dim), "glorot")
+                    self._add_param(p.dst + "_attention/kernel2", (fd, p.msg_dim), "glorot")
+                    self._add_param(p.dst + "_attention/attn_kernel", (2 * fd, 1), "glorot")
+                    p.op = ops.OP_SUM
+                    p.attn = True
+                    p.kind = "agg_gru" if mp.update.type == "recurrent_nn" else "agg_ff"
+                elif agg == "convolution":
+                    if p.msg_dim != fd:
+                        raise RuntimeError(
+                            "IGNNITION: When doing the a convolution, both the dimension of the messages sent and the "
+                            "destination hidden states should match. In this case, however,the dimensions are %d and "
+                            "%d of the source and destination respectively." % (p.msg_dim, fd))
+                    if mp.aggregation.activation_function not in ops.ACTIVATIONS:
+                        raise RuntimeError("IGNNITION: activation %s is not supported" % mp.aggregation.activation_function)
+                    self._add_param(p.dst + "_convolution/conv_kernel", (fd, fd), "glorot")
+                    p.op = ops.OP_SUM
+                    p.conv = True
+                    p.kind = "agg_gru" if mp.update.type == "recurrent_nn" else "agg_ff"
                 else:
                     raise RuntimeError("IGNNITION: aggregation '%s' is not built yet in the B200 engine "
                                        "(SURVEY.md section 8f, next rows)" % agg)
@@ -195,6 +245,21 @@ class Engine:
                 self.readout.append((k, op))
                 if op.type == "predict":
                     break
+            elif op.type == "pooling":                   # auxilary_classes.py:1165-1185, per sample
+                if op.type_pooling not in ("sum", "mean", "max"):
+                    raise RuntimeError("IGNNITION: pooling '%s' is not supported" % op.type_pooling)
+                dims[op.output_name] = dims[op.input[0]]
+                self.readout.append((k, op))
+            elif op.type == "product":                   # auxilary_classes.py:1072-1094
+                if op.type_product != "element_wise":
+                    raise RuntimeError("IGNNITION: product '%s' is not built yet in the B200 engine (the reference's "
+                                       "dot_product is tf.tensordot(axes=0), an outer product)" % op.type_product)
+                dims[op.output_name] = dims[op.input[0]]
+                self.readout.append((k, op))
+            elif op.type == "extend_adjacencies":        # auxilary_classes.py:1236-1265
+                dims[op.output_name[0]] = dims[op.input[0]]
+                dims[op.output_name[1]] = dims[op.input[1]]
+                self.readout.append((k, op))
             else:
                 raise RuntimeError("IGNNITION: readout operation '%s' is not built yet in the B200 engine "
                                    "(SURVEY.md section 8f, next rows)" % op.type)
@@ -296,9 +361,24 @@ class Engine:
             for p in stage:
                 if p.kind != "seq_gru":
                     continue
-                if p.seq is None:
-                    rowptr, col, _ = g.csr[p.adjs[0].name]
-                    g.steps[p.key] = (rowptr, col)
+                if p.concat2:
+                    names = [a.name for a in p.adjs]
+                    if len(set(g.max_seq.get(n, 0) for n in names)) != 1:
+                        raise RuntimeError("IGNNITION: concat along axis 2 needs padded blocks of equal length, "
+                                           "got %s (tf.concat fails in the reference)"
+                                           % [g.max_seq.get(n, 0) for n in names])
+                    rowptr0, col0, perm0 = g.csr[names[0]]
+                    use_msgs = [any(op.type == "feed_forward_nn" for op in src.message_formation)
+                                for src in p.mp.source_entities]
+                    idx = [perm0 if use_msgs[0] else col0]
+                    for k in range(1, len(names)):
+                        rp, c, pm = g.csr[names[k]]
+                        idx.append(ops.partner_index(rowptr0, rp, pm if use_msgs[k] else c, int(col0.numel())))
+                    g.partner[p.key] = idx
+                    g.steps[p.key] = (rowptr0, torch.arange(col0.numel(), dtype=torch.int32, device=self.device))
+                elif p.seq is None:
+                    rowptr, col, perm = g.csr[p.adjs[0].name]
+                    g.steps[p.key] = (rowptr, perm if p.msg_rows else col)
                 else:
                     rps = [g.csr[a.name][0] for a in p.adjs]
                     cols = [g.csr[a.name][1] for a in p.adjs]
@@ -398,9 +478,11 @@ class Engine:
             srcs = []
             for k, a in enumerate(p.adjs):
                 srcs.append(msgs[k] if msgs[k] is not None else state[a.src])
-            if any(m is not None for m in msgs):
-                raise RuntimeError("IGNNITION: message neural networks feeding an ordered aggregation are "
-                                   "not built yet (step table indexes source rows)")
+            if p.concat2:
+                srcs = [ops.gather_concat(srcs, g.partner[p.key], int(g.partner[p.key][0].numel()))]
+            if (p.concat2 or p.msg_rows) and tape is not None:
+                raise RuntimeError("IGNNITION: training through concat / message-network ordered aggregations "
+                                   "is not built")
             h_seq = None
             if tape is not None:
                 h_seq = torch.empty(steps.numel(), h.shape[1], dtype=torch.float32, device=self.device)
@@ -416,7 +498,7 @@ class Engine:
 
         # aggregating kinds
         fused = (p.kind == "agg_gru" and p.op == ops.OP_SUM and len(p.adjs) == 1 and msgs[0] is None
-                 and self._fusable(p.msg_dim, h.shape[1]))
+                 and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1]))
         if fused:
             rowptr, col, _ = g.csr[p.adjs[0].name]
             agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
@@ -425,7 +507,19 @@ class Engine:
                 tape.append(("agg_gru", p, state[p.adjs[0].src], h, agg))
             return out
         agg = None
-        for k, a in enumerate(p.adjs):
+        if p.attn:      # Attention_aggr (auxilary_classes.py:278-344)
+            if tape is not None:
+                raise RuntimeError("IGNNITION: training through the attention aggregation is not built")
+            a = p.adjs[0]
+            rowptr, col, perm = g.csr[a.name]
+            rows, idx = (state[a.src], col) if msgs[0] is None else (msgs[0], perm)
+            F = p.msg_dim
+            ak = self.param(dst + "_attention/attn_kernel")
+            v1 = ops.dense(self.param(dst + "_attention/kernel1"), ak[:F], None, 0)
+            v2 = ops.dense(self.param(dst + "_attention/kernel2"), ak[F:], None, 0)
+            agg = ops.attention_aggregate(rowptr, idx, rows, ops.dense(rows, v1, None, 0), ops.dense(h, v2, None, 0),
+                                          g.t["offsets_" + dst], max(g.max_seq.get(a.name, 0), 1))
+        for k, a in enumerate(p.adjs if not p.attn else []):
             rowptr, col, perm = g.csr[a.name]
             if msgs[k] is None:
                 part = ops.segment_reduce(ops.OP_SUM if len(p.adjs) > 1 else p.op, rowptr, col, state[a.src])
@@ -437,6 +531,13 @@ class Engine:
                 ops.axpy(1.0, part, agg)
         if len(p.adjs) > 1 and p.op != ops.OP_SUM:
             raise RuntimeError("IGNNITION: mean/max over several sources is not built")
+        if p.conv:      # Conv_aggr (auxilary_classes.py:366-401); the kernel product commutes with the sum
+            if len(p.adjs) != 1:
+                raise RuntimeError("IGNNITION: convolution over several sources is not built")
+            nsum = ops.dense(agg, self.param(dst + "_convolution/conv_kernel"), None, 0)
+            agg = ops.conv_finish(nsum, h, g.csr[p.adjs[0].name][0], self._act(p.mp.aggregation.activation_function))
+            if tape is not None:
+                raise RuntimeError("IGNNITION: training through the convolution aggregation is not built")
         if p.kind == "agg_gru":
             ops.gru_cell(agg, h, K, R, B, out=out)
             if tape is not None:
@@ -474,10 +575,41 @@ class Engine:
                     state[p.dst] = self._mp_forward(p, g, state, tape)      # written back at once (:602)
         return state
 
-    def readout_forward(self, state: Dict[str, torch.Tensor], tape: Optional[list] = None) -> torch.Tensor:
+    def readout_forward(self, state: Dict[str, torch.Tensor], tape: Optional[list] = None,
+                        g: Optional[DeviceGraph] = None, return_states: bool = False):
         st = dict(state)
+        owner = {e: e for e in self.entities}            # which entity's rows a derived state is laid out by
         result = None
         for k, op in self.readout:
+            if op.type == "pooling":
+                if tape is not None:
+                    raise RuntimeError("IGNNITION: training through readout pooling is not built")
+                ent = owner.get(op.input[0])
+                if ent is None or g is None:
+                    raise RuntimeError("IGNNITION: pooling needs an entity-shaped input")
+                red = {"sum": ops.OP_SUM, "mean": ops.OP_MEAN, "max": ops.OP_MAX}[op.type_pooling]
+                st[op.output_name] = ops.segment_reduce(red, g.t["offsets_" + ent], None, st[op.input[0]])
+                owner[op.output_name] = None              # one row per sample
+                continue
+            if op.type == "product":
+                if tape is not None:
+                    raise RuntimeError("IGNNITION: training through readout products is not built")
+                a, b = st[op.input[0]], st[op.input[1]]
+                if a.shape != b.shape:
+                    raise RuntimeError("IGNNITION:  The product operation between %s and %s failed. Check that the "
+                                       "dimensions are compatible." % (op.input[0], op.input[1]))
+                st[op.output_name] = ops.mul(a, b)
+                owner[op.output_name] = owner.get(op.input[0])
+                continue
+            if op.type == "extend_adjacencies":
+                if tape is not None or g is None:
+                    raise RuntimeError("IGNNITION: training through extend_adjacencies is not built")
+                src_idx, dst_idx = g.t["src_" + op.adj_list], g.t["dst_" + op.adj_list]
+                n_e = src_idx.numel()
+                st[op.output_name[0]] = ops.gather_concat([st[op.input[0]]], [src_idx], n_e)
+                st[op.output_name[1]] = ops.gather_concat([st[op.input[1]]], [dst_idx], n_e)
+                owner[op.output_name[0]] = owner[op.output_name[1]] = None
+                continue
             if len(op.input) == 1:
                 x = st[op.input[0]]
             else:
@@ -490,13 +622,16 @@ class Engine:
                 result = y
                 break
             st[op.output_name] = y
+            owner[op.output_name] = owner.get(op.input[0])
+        if return_states:
+            return result, st
         return result
 
     def forward(self, g: DeviceGraph, training: bool = False, return_states: bool = False,
                 tape: Optional[list] = None):
         state = self.initial_states(g)
         state = self.message_passing(g, state, tape=tape)
-        pred = self.readout_forward(state, tape=tape)
+        pred = self.readout_forward(state, tape=tape, g=g)
         if return_states:
             return pred, state
         return pred

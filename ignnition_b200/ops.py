@@ -341,3 +341,44 @@ def adam_step(w, g, m, v, lr: float, beta1: float, beta2: float, eps: float, ste
 def axpy(a: float, x, y):
     lib = _lib.load()
     _lib.check(lib.ign_axpy(x.numel(), a, _f(x), _f(y), _stream()), "axpy")
+
+
+def mul(a, b, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty_like(a)
+    _lib.check(lib.ign_mul(a.numel(), _f(a), _f(b), _f(out), _stream()), "mul")
+    return out
+
+
+def conv_finish(nsum, self_state, rowptr, act: int, out=None):
+    lib = _lib.load()
+    n, F = nsum.shape
+    if out is None:
+        out = torch.empty_like(nsum)
+    _lib.check(lib.ign_conv_finish(_f(nsum), _f(self_state), _i(rowptr), F, n, act, _f(out), _stream()), "conv_finish")
+    return out
+
+
+def attention_aggregate(rowptr, col, rows, src_score, dst_score, sample_offsets, max_len: int, out=None):
+    lib = _lib.load()
+    num_dst = rowptr.numel() - 1
+    n_edges = col.numel()
+    n_samples = sample_offsets.numel() - 1
+    F = rows.shape[1]
+    if out is None:
+        out = torch.empty(num_dst, F, dtype=torch.float32, device=rows.device)
+    nbytes = lib.ign_attention_ws_bytes(n_edges, n_samples, max_len)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
+    _lib.check(lib.ign_attention_aggregate(_i(rowptr), _i(col), _f(rows), F, _f(src_score), _f(dst_score),
+                                           _i(sample_offsets), n_samples, num_dst, n_edges, max_len, _f(out),
+                                           ws.data_ptr(), nbytes, _stream()), "attention_aggregate")
+    return out
+
+
+def partner_index(rowptr0, rowptr1, idx1, n_edges0: int):
+    lib = _lib.load()
+    out = torch.empty(n_edges0, dtype=torch.int32, device=rowptr0.device)
+    _lib.check(lib.ign_partner_index(_i(rowptr0), _i(rowptr1), _i(idx1) if idx1.numel() else None,
+                                     rowptr0.numel() - 1, _i(out) if n_edges0 else None, _stream()), "partner_index")
+    return out

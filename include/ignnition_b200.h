@@ -255,6 +255,34 @@ int ign_l2_reg(const float* w, int64_t n, float lambda, float* dw, double* reg, 
 int ign_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, int64_t step, void* stream);
 
+/* Attention_aggr.calculate_input (auxilary_classes.py:278-344) on the CSR by destination:
+ * a_j = leaky_relu(src_score[col[j]] + dst_score[d], 0.2); softmax over the destinations of one sample
+ * per padded column s = j - rowptr[d] (zero pads included, as the reference's softmax over axis 0 does);
+ * out[d] = sum_j coef_j * rows[col[j]].  src_score = rows . (kernel1 . attn_kernel[:F]) and
+ * dst_score = h_dst . (kernel2 . attn_kernel[F:]) are ign_dense calls.  sample_offsets[n_samples+1] are
+ * the destination entity's per-sample row offsets; max_len >= the longest destination list. */
+size_t ign_attention_ws_bytes(int64_t n_edges, int64_t n_samples, int max_len);
+int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const float* rows, int F,
+                            const float* src_score, const float* dst_score, const int32_t* sample_offsets,
+                            int64_t n_samples, int64_t num_dst, int64_t n_edges, int max_len, float* out,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* Concat_aggr with concat_axis = 2 (generate_model.py:496-505): for CSR position j of the first source
+ * (destination d, padded column s = j - rowptr0[d]) the row of another source sitting at the same padded
+ * column: out[j] = idx1[rowptr1[d] + s], or -1 where that source's block is zero padding.  Feed the index
+ * lists to ign_gather_concat (a negative index gathers a zero row). */
+int ign_partner_index(const int32_t* rowptr0, const int32_t* rowptr1, const int32_t* idx1, int64_t num_dst,
+                      int32_t* out, void* stream);
+
+/* Product_operation 'element_wise' (auxilary_classes.py:1085-1086): out = a * b. */
+int ign_mul(int64_t n, const float* a, const float* b, float* out, void* stream);
+
+/* Tail of Conv_aggr.calculate_input (auxilary_classes.py:388-401):
+ * out[d] = act((nsum[d] + self[d]) / in-degree(d)), in-degree from the CSR rowptr (0 -> inf / nan as in TF).
+ * nsum = (sum of messages) . conv_kernel = ign_segment_reduce + ign_dense (the matrix product is linear). */
+int ign_conv_finish(const float* nsum, const float* self, const int32_t* rowptr, int F, int64_t n, int act,
+                    float* out, void* stream);
+
 /* y[i] += x[idx[i]] row-wise helper and elementwise utilities used by the backward pass */
 int ign_axpy(int64_t n, float a, const float* x, float* y, void* stream);
 

@@ -283,6 +283,13 @@ class Oracle:
                     din = int(l["units"])
                 if op["type"] == "neural_network":
                     self.hs[op["output_name"]] = din
+            elif op["type"] == "pooling":
+                self.hs[op["output_name"]] = int(self.hs[op["input"][0]])
+            elif op["type"] == "product" and op["type_product"] == "element_wise":
+                self.hs[op["output_name"]] = int(self.hs[op["input"][0]])
+            elif op["type"] == "extend_adjacencies":
+                self.hs[op["output_name_src"]] = int(self.hs[op["input"][0]])
+                self.hs[op["output_name_dst"]] = int(self.hs[op["input"][1]])
         return shapes
 
     def init_weights(self, seed=1234) -> Dict[str, np.ndarray]:

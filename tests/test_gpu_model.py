@@ -179,6 +179,7 @@ def _mpnn_sample(rng, n, max_deg, feat=3, params=False):
     ("sum", 32, "ff", False),       # feed-forward update (semantics of call; crashes in the reference)
     ("sum", 32, "gru", True),       # message MLP on [hs_source | hs_dest | edge_params]
     ("ordered", 32, "gru", False),
+    ("ordered", 32, "gru", True),   # the ordered walk reads message-MLP rows (edge order) through perm
 ])
 def test_generic_mpnn(agg, hidden, update, message_nn):
     rng = np.random.RandomState(len(agg) + hidden)
@@ -187,7 +188,7 @@ def test_generic_mpnn(agg, hidden, update, message_nn):
     if agg == "ordered":           # ordered needs >= 1 message per destination in the reference
         for s in samples:
             for v in s["entities"]:
-                s["adj"].setdefault(v, [v])
+                s["adj"].setdefault(v, [[v, [1.0, 2.0]]] if message_nn else [v])
     dims = sample_dimensions(samples[0])
     md, eng, o64, w = make(model_json, dims)
     tens = [tensors_of(md, s)[0] for s in samples]
@@ -200,9 +201,172 @@ def test_generic_mpnn(agg, hidden, update, message_nn):
     assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate(want)) < RTOL
 
 
+def test_convolution_aggregation():
+    """Conv_aggr = act((sum_j W.m_j + h_d) / deg_d) -> GRU (auxilary_classes.py:366-401)."""
+    rng = np.random.RandomState(5)
+    mj = _mpnn_json("convolution", 32)
+    mj["message_passing"]["stages"][0]["stage_mp"][0]["aggregation"]["activation_function"] = "relu"
+    samples = [_mpnn_sample(rng, n, 5) for n in (30, 200)]
+    for s in samples:                       # every destination has >= 1 neighbour (degree 0 divides by zero)
+        for v in s["entities"]:
+            s["adj"].setdefault(v, [v])
+    md, eng, o64, w = make(mj, sample_dimensions(samples[0]))
+    assert "node_convolution/conv_kernel" in w
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    want = [o64.forward(t, w, return_states=True) for t in tens]
+    assert rel_err(state["node"].cpu().numpy(), np.concatenate([s["node"] for _, s in want])) < RTOL
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
+
+
+@pytest.mark.parametrize("message_nn", [False, True])
+def test_attention_aggregation(message_nn):
+    """Attention_aggr as the reference computes it -- the softmax runs over the
+    DESTINATIONS of a sample per padded column, zero pads included (auxilary_classes.py:278-344)."""
+    rng = np.random.RandomState(8)
+    mj = _mpnn_json("attention", 32, "gru", message_nn)
+    samples = [_mpnn_sample(rng, n, 5, params=message_nn) for n in (25, 2, 150)]
+    md, eng, o64, w = make(mj, sample_dimensions(samples[0]))
+    assert w["node_attention/attn_kernel"].shape == (64, 1)
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    want = [o64.forward(t, w, return_states=True) for t in tens]
+    assert rel_err(state["node"].cpu().numpy(), np.concatenate([s["node"] for _, s in want])) < RTOL
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
+
+
+def _two_entity_json(agg):
+    """paths receive from links AND from nodes (two sources of one message passing), links from paths."""
+    nns = [{"nn_name": "rec", "nn_type": "recurrent_neural_network", "recurrent_type": "GRU"},
+           {"nn_name": "ro", "nn_type": "feed_forward", "nn_architecture": [
+               {"type_layer": "Dense", "units": 8, "activation": "selu"},
+               {"type_layer": "Dense", "units": 1, "activation": "None"}]}]
+    upd = {"type": "recurrent_neural_network", "nn_name": "rec"}
+    da = [{"type": "direct_assignation"}]
+    return {
+        "entities": [{"name": "link", "hidden_state_dimension": 16, "features": [{"name": "cap", "normalization": "None"}]},
+                     {"name": "node", "hidden_state_dimension": 16, "features": [{"name": "deg", "normalization": "None"}]},
+                     {"name": "path", "hidden_state_dimension": 16, "features": [{"name": "tr", "normalization": "None"}]}],
+        "message_passing": {"num_iterations": 2, "stages": [
+            {"stage_name": "s1", "stage_mp": [{
+                "destination_entity": "path",
+                "source_entities": [{"name": "link", "adj_vector": "lp", "message": da},
+                                    {"name": "node", "adj_vector": "np", "message": da}],
+                "aggregation": agg, "update": upd}]},
+            {"stage_name": "s2", "stage_mp": [{
+                "destination_entity": "link",
+                "source_entities": [{"name": "path", "adj_vector": "pl", "message": da}],
+                "aggregation": {"type": "sum"}, "update": upd}]}]},
+        "readout": [{"type": "predict", "input": ["path"], "label": "y", "nn_name": "ro"}],
+        "neural_networks": nns,
+        "learning_options": {"loss": "MeanSquaredError", "optimizer": {"type": "Adam"}},
+    }
+
+
+def _two_entity_sample(rng, n_link, n_node, n_path):
+    ent = {}
+    for i in range(n_link): ent["l%d" % i] = "link"
+    for i in range(n_node): ent["n%d" % i] = "node"
+    for i in range(n_path): ent["p%d" % i] = "path"
+    lp, npth, pl = {}, {}, {}
+    for p_ in range(n_path):
+        ls = rng.choice(n_link, rng.randint(1, min(5, n_link) + 1), replace=False)
+        ns = rng.choice(n_node, rng.randint(1, min(4, n_node) + 1), replace=False)
+        lp["p%d" % p_] = ["l%d" % l for l in ls]
+        npth["p%d" % p_] = ["n%d" % n for n in ns]
+        for l in ls:
+            pl.setdefault("l%d" % l, []).append("p%d" % p_)
+    return {"entities": ent, "lp": lp, "np": npth, "pl": pl,
+            "cap": rng.rand(n_link).tolist(), "deg": rng.rand(n_node).tolist(), "tr": rng.rand(n_path).tolist(),
+            "y": rng.rand(n_path).tolist()}
+
+
+@pytest.mark.parametrize("agg", [{"type": "concat", "concat_axis": 1}, {"type": "ordered"}])
+def test_two_source_concat_axis1_and_ordered(agg):
+    """Concat_aggr along axis 1 and the default multi-source combine (generate_model.py:496-505, :523-543):
+    the sources' right-padded blocks sit one after the other, the RNN mask keeps the first sum(len)
+    columns (zero columns mid-sequence are real GRU steps)."""
+    rng = np.random.RandomState(11)
+    mj = _two_entity_json(agg)
+    samples = [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 30)]
+    dims = sample_dimensions(samples[0])
+    md, eng, o64, w = make(mj, dims)
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    want = [o64.forward(t, w, return_states=True) for t in tens]
+    for e in ("path", "link"):
+        assert rel_err(state[e].cpu().numpy(), np.concatenate([s[e] for _, s in want])) < RTOL_STATE_TC
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
+
+
+def test_two_source_concat_axis2():
+    """Concat_aggr along the feature axis (generate_model.py:496-505): step t of a path reads
+    [link_t | node_t] (zeros where the node block is padding), the mask keeps the FIRST source's length."""
+    rng = np.random.RandomState(21)
+    mj = _two_entity_json({"type": "concat", "concat_axis": 2})
+    samples = [_two_entity_sample(rng, 8, 6, 12), _two_entity_sample(rng, 12, 7, 30)]
+    for s in samples:                         # the two padded blocks must be equally long (tf.concat)
+        s["lp"]["p0"] = ["l%d" % i for i in range(5)]
+        s["np"]["p0"] = ["n%d" % i for i in range(5)]
+        s["pl"] = {}
+        for p_, ls in s["lp"].items():
+            for l in ls:
+                s["pl"].setdefault(l, []).append(p_)
+    md, eng, o64, w = make(mj, sample_dimensions(samples[0]))
+    assert w["path_update/kernel"].shape == (32, 48)
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    want = [o64.forward(t, w, return_states=True) for t in tens]
+    for e in ("path", "link"):
+        assert rel_err(state[e].cpu().numpy(), np.concatenate([s[e] for _, s in want])) < RTOL_STATE_TC
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
+    bad = copy.deepcopy(samples[0])
+    bad["np"]["p0"] = ["n0"]
+    bad["np"] = {k: v[:2] for k, v in bad["np"].items()}
+    with pytest.raises(RuntimeError, match="equal length"):
+        eng.prepare([tensors_of(md, bad)[0]])
+
+
+@pytest.mark.parametrize("pool", ["sum", "mean", "max"])
+def test_readout_pooling_product_extend_chain(pool):
+    """extend_adjacencies -> element-wise product -> neural_network -> pooling -> predict
+    (auxilary_classes.py:1072-1094, :1165-1185, :1236-1265; generate_model.py:632-656), one graph-level
+    prediction per sample."""
+    rng = np.random.RandomState(3)
+    mj = _mpnn_json("sum", 32)
+    mj["neural_networks"].append({"nn_name": "edge_nn", "nn_type": "feed_forward", "nn_architecture": [
+        {"type_layer": "Dense", "units": 20, "activation": "tanh"}]})
+    mj["readout"] = [
+        {"type": "extend_adjacencies", "adj_list": "adj", "input": ["node", "node"],
+         "output_name_src": "e_src", "output_name_dst": "e_dst"},
+        {"type": "product", "type_product": "element_wise", "input": ["e_src", "e_dst"], "output_name": "e_prod"},
+        {"type": "neural_network", "input": ["node"], "nn_name": "edge_nn", "output_name": "node2"},
+        {"type": "pooling", "type_pooling": pool, "input": ["node2"], "output_name": "graph"},
+        {"type": "predict", "input": ["graph"], "label": "y", "nn_name": "ro"},
+    ]
+    samples = [_mpnn_sample(rng, n, 4) for n in (17, 1, 120)]
+    for s in samples:
+        s["y"] = [float(rng.randn())]
+    md, eng, o64, w = make(mj, sample_dimensions(samples[0]))
+    tens = [tensors_of(md, s)[0] for s in samples]
+    g = eng.prepare(tens)
+    pred = eng.forward(g)
+    assert tuple(pred.shape) == (len(samples), 1)
+    want = np.concatenate([o64.forward(t, w).reshape(-1) for t in tens])
+    assert rel_err(pred.cpu().numpy().reshape(-1), want) < RTOL
+    # the per-edge derived states (not consumed by predict here) against the oracle, first sample alone
+    _, st0 = o64.forward(tens[0], w, return_states=True)
+    g0 = eng.prepare([tens[0]])
+    h = eng.message_passing(g0, eng.initial_states(g0))
+    _, rd = eng.readout_forward(h, g=g0, return_states=True)
+    assert rel_err(rd["e_prod"].cpu().numpy(), st0["e_prod"]) < RTOL_STATE_TC
+
+
 def test_unsupported_keywords_fail_loudly():
     from ignnition_b200 import Engine
-    mj = _mpnn_json("attention")
+    mj = _mpnn_json("sum")
+    mj["readout"].insert(0, {"type": "product", "type_product": "dot_product", "input": ["node", "node"],
+                             "output_name": "outer"})
     with pytest.raises(RuntimeError, match="IGNNITION.*not built yet"):
         Engine(ModelDescription(mj, {"x": 3, "adj": 0}), device="cuda:0")
     with pytest.raises(RuntimeError, match="CUDA devices only"):
