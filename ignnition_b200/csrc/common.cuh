@@ -109,10 +109,12 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // 3xTF32 operand split: hi = round-to-nearest TF32 of v, lo = round-to-nearest TF32 of (v - hi).
 // |v - (hi + lo)| <= 2^-24 |v|, i.e. the pair carries v to fp32 precision; the tensor core reads
 // both exactly (their low 13 mantissa bits are zero).
+// round to nearest, ties away from zero, onto the 10-bit tf32 mantissa: what cvt.rna.tf32.f32 computes
+// for every finite input, in two integer instructions (ptxas expands the cvt into four, with an
+// inf / nan guard the split does not need: inf stays inf, and a nan reaches the product through
+// lo = v - hi)
 __device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void tf32_split(float v, float& hi, float& lo) {
   hi = tf32_rna(v);

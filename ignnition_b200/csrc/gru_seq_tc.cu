@@ -5,35 +5,48 @@
 // but the two gate GEMMs of every step run as 3xTF32 tcgen05.mma with the accumulator in TMEM:
 //
 //   D[128 rows, 128 cols] = [ z | r | xh | hh ] pre-activations of 128 destinations
-//     x chunk : D[:, 0:96]   = x_t  . K[:, z|r|h]          (N = 96)
-//     h chunk : D[:, 0:64]  += h    . R[:, z|r]            (N = 64)
-//               D[:, 96:128] = h    . R[:, h]              (N = 32)
-//   each product as  A_hi B_hi + A_lo B_hi + A_hi B_lo  (hi = top 19 bits, lo = remainder), so the
-//   result keeps fp32 accuracy (parity bar 1e-5).
+//     D  = x_t . [ Kz | Kr | Kh | 0  ]         (N = 128, 12 UMMAs)
+//     D += h   . [ Rz | Rr | 0  | Rh ]         (N = 128, 12 UMMAs; a UMMA of N <= 128 costs the same
+//                                               71 cycles whatever N is, profiles/r1_umma_tf32_rate.md)
+//   each product as  A_hi B_hi + A_lo B_hi + A_hi B_lo  (hi = rna_tf32(v), lo = rna_tf32(v - hi)), so
+//   the result keeps fp32 accuracy (parity bar 1e-5).
 //
-// One CTA (256 threads, persistent) owns TWO tiles of 128 destinations at a time: while the tensor
-// core computes step t of one tile, all 8 warps run the epilogue of the other (tcgen05.ld of the
-// gates, sigmoid / tanh, new state, re-split of h and of the next gathered message into the
-// swizzled shared-memory operand images).  K and R are split and laid out once per CTA.  The
-// running state h stays in registers in full fp32 (thread = one destination x 16 units).
+// One persistent CTA per SM (512 threads) runs TWO independent walkers of 8 warps each.  A walker
+// owns one tile of 128 destinations at a time: it waits for the tensor core (mbarrier armed by
+// tcgen05.commit), reads the gates from TMEM, applies sigmoid / tanh and the state update (h stays in
+// registers in full fp32; thread = one destination x 16 units), re-splits h and the next gathered
+// message into the swizzled operand images, meets on its own named barrier and lets one thread issue
+// the 24 UMMAs of the next step.  The walkers never synchronise with each other: while one sets up
+// its next tile or runs its epilogue, the tensor core works for the other.  K and R are split and
+// laid out once per CTA.
 
 #include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
 
 #include "tc_common.cuh"
 
 using namespace ign_tc;
 
-namespace {
+// -DIGN_WALK_PROFILE: per-phase clock64() sums of one warp per walker, printed after every launch
+// (profiles/r1_walk_phases.md).  Compiles to nothing otherwise.
+#ifdef IGN_WALK_PROFILE
+#define PROF(...) __VA_ARGS__
+#else
+#define PROF(...)
+#endif
 
-constexpr int NSPLIT = 4;                 // warps per TMEM lane group: each owns 32 / NSPLIT units of a row
-constexpr int EPI_THREADS = 128 * NSPLIT;  // 16 epilogue warps
-constexpr int TC_THREADS = EPI_THREADS + 32;   // + one warp that only issues the tcgen05.mma stream
-constexpr int UPT = 32 / NSPLIT;          // units per thread
-constexpr int ROWS = 128;                 // destinations per tile = UMMA M
-constexpr int U = 32;                     // units = message width
-constexpr int IMG = ROWS * 128;           // bytes of one [128 x 32] fp32 operand image
-constexpr int BIMG = 96 * 128;            // bytes of one [96 x 32] weight image
-constexpr int SLOT_BYTES = 4 * IMG;       // Ax_hi | Ax_lo | Ah_hi | Ah_lo
+namespace {
+PROF(__device__ unsigned long long prof_cyc[12]; __device__ unsigned long long prof_cyc2[2];)
+
+constexpr int WALKERS = 2;
+constexpr int WALKER_THREADS = 256;                       // 8 warps: 4 TMEM lane groups x 2 unit halves
+constexpr int TC_THREADS = WALKERS * WALKER_THREADS;
+constexpr int UPT = 16;                                   // units per thread
+constexpr int ROWS = 128;                                 // destinations per tile = UMMA M
+constexpr int U = 32;                                     // units = message width
+constexpr int IMG = ROWS * 128;                           // bytes of one [128 x 32] fp32 operand image
+constexpr int SLOT_BYTES = 4 * IMG;                       // Ax_hi | Ax_lo | Ah_hi | Ah_lo
 
 struct SrcPtrs {
   const float* p[IGN_MAX_SOURCES];
@@ -42,275 +55,293 @@ __device__ __forceinline__ const float* pick_src(const SrcPtrs& s, int k) {
   return k == 0 ? s.p[0] : k == 1 ? s.p[1] : k == 2 ? s.p[2] : s.p[3];
 }
 
-struct Slot {
-  int d;        // destination of this thread's row (-1: none)
-  int lo;       // first step
-  int len;      // number of steps
-  int entry;    // step-table entry of the next message to gather (one step of lookahead)
-  float h[UPT]; // running state, this thread's units
-};
-
 template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     const int* __restrict__ steps_rowptr, const int* __restrict__ steps, const int* __restrict__ order, SrcPtrs srcs,
     const float* __restrict__ h0, int64_t num_dst, const float* __restrict__ kernel, const float* __restrict__ rkernel,
     const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ h_seq,
-    const int4* __restrict__ meta) {
+    const int4* __restrict__ meta PROF(, int dbg)) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* bx_hi = smem;
-  unsigned char* bx_lo = bx_hi + BIMG;
-  unsigned char* bh_hi = bx_lo + BIMG;
-  unsigned char* bh_lo = bh_hi + BIMG;
-  unsigned char* slots = bh_lo + BIMG;                  // 4 * 12288 = 49152 = 48 * 1024: still 1024-aligned
-  __shared__ uint64_t bar[2];
+  unsigned char* bx_hi = smem;                          // [128 n][32 k] images of [Kz|Kr|Kh|0] and [Rz|Rr|0|Rh]
+  unsigned char* bx_lo = bx_hi + IMG;
+  unsigned char* bh_hi = bx_lo + IMG;
+  unsigned char* bh_lo = bh_hi + IMG;
+  unsigned char* slots = bh_lo + IMG;
+  __shared__ uint64_t bar_acc[WALKERS];                 // tensor core -> walker: gates are in TMEM
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[6 * U];
   __shared__ __align__(16) float s_gb[4 * U];
-  __shared__ int s_maxlen[2];
+  __shared__ int s_maxlen[WALKERS][2];                  // per tile parity: reset one tile ahead of its use
+  __shared__ int4 s_meta[WALKERS][ROWS];                // walk plan of the walker's current tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool mma_warp = warp == EPI_THREADS / 32;          // warp 16: MMA issuer, no rows
-  const int q = warp & 3, split = (warp >> 2) & (NSPLIT - 1);
-  const int row = q * 32 + lane;                         // TMEM lane == row of the tile
-  const int u0 = split * UPT;                            // this thread's units [u0, u0 + UPT)
 
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int g = 0; g < WALKERS; ++g) mbar_init(&bar_acc[g], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                 "r"(256u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  // weight images: Bx[n][k] = K[k][n], Bh[n][k] = R[k][n], n in [0,96), hi / lo, swizzled
-  for (int i = tid; i < U * 3 * U; i += TC_THREADS) {
-    const int k = i / (3 * U), n = i % (3 * U);
-    const int off = n * 128 + ((((k >> 2) ^ (n & 7)) & 7) << 4) + (k & 3) * 4;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256u);
+  // weight images, n = output column of D, k = input unit
+  for (int i = tid; i < 128 * U; i += TC_THREADS) {
+    const int n = i >> 5, k = i & 31;
+    const int off = sw128_off(n, k);
+    const float kx = n < 96 ? __ldg(kernel + k * 96 + n) : 0.f;
+    const float kh = n < 64 ? __ldg(rkernel + k * 96 + n) : n < 96 ? 0.f : __ldg(rkernel + k * 96 + n - 32);
     float hi, lo;
-    tf32_split(__ldg(kernel + i), hi, lo);
+    tf32_split(kx, hi, lo);
     *reinterpret_cast<float*>(bx_hi + off) = hi;
     *reinterpret_cast<float*>(bx_lo + off) = lo;
-    tf32_split(__ldg(rkernel + i), hi, lo);
+    tf32_split(kh, hi, lo);
     *reinterpret_cast<float*>(bh_hi + off) = hi;
     *reinterpret_cast<float*>(bh_lo + off) = lo;
   }
-  for (int i = tid; i < 6 * U; i += TC_THREADS) s_bias[i] = bias[i];
-  fence_async_smem();
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_s;
-
-  // merged gate biases in shared memory: [bz | br | bxh | bhh], read as broadcast float4
-  __syncthreads();
+  // merged gate biases [bz | br | bxh | bhh] (Keras bias[2, 3u]: input row, recurrent row)
   if (tid < U) {
-    const float b0z = s_bias[tid], b0r = s_bias[U + tid], b0h = s_bias[2 * U + tid];
-    const float b1z = s_bias[3 * U + tid], b1r = s_bias[4 * U + tid], b1h = s_bias[5 * U + tid];
-    s_gb[tid] = b0z + b1z; s_gb[U + tid] = b0r + b1r; s_gb[2 * U + tid] = b0h; s_gb[3 * U + tid] = b1h;
+    s_gb[tid] = bias[tid] + bias[3 * U + tid];
+    s_gb[U + tid] = bias[U + tid] + bias[4 * U + tid];
+    s_gb[2 * U + tid] = bias[2 * U + tid];
+    s_gb[3 * U + tid] = bias[5 * U + tid];
   }
+  fence_async_smem();
+  tc_fence_before();
   __syncthreads();
-
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
   const int64_t ntiles = (num_dst + ROWS - 1) / ROWS;
-  const int64_t npairs = (ntiles + 1) / 2;
-  uint32_t uses[2] = {0, 0};
 
-  // gather this thread's 64 bytes of the message of step t (its entry was fetched one step earlier,
-  // so the row load does not wait on an index load), then fetch the entry of step t + 1
-  auto load_x = [&](Slot& s, int t, float4 (&x)[UPT / 4]) {
-#pragma unroll
-    for (int j = 0; j < UPT / 4; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int entry = s.entry;
-    s.entry = (t + 1 < s.len) ? __ldg(steps + s.lo + t + 1) : IGN_STEP_ZERO;
-    if (t < s.len && entry >= 0) {
-      const float* p = pick_src(srcs, entry >> IGN_STEP_SRC_SHIFT) + (int64_t)(entry & IGN_STEP_ROW_MASK) * U + u0;
-#pragma unroll
-      for (int j = 0; j < UPT / 4; ++j) x[j] = ldg_f4(p + 4 * j);
-    }
-  };
-  auto store_x = [&](int slot, const float4 (&x)[UPT / 4]) {
-    unsigned char* b = slots + slot * SLOT_BYTES;
-#pragma unroll
-    for (int j = 0; j < UPT / 4; ++j) store_split(b, b + IMG, row, split * (UPT / 4) + j, x[j]);
-  };
-  auto store_h = [&](int slot, const Slot& s) {
-    unsigned char* b = slots + slot * SLOT_BYTES + 2 * IMG;
-#pragma unroll
-    for (int j = 0; j < UPT / 4; ++j)
-      store_split(b, b + IMG, row, split * (UPT / 4) + j,
-                  make_float4(s.h[4 * j], s.h[4 * j + 1], s.h[4 * j + 2], s.h[4 * j + 3]));
-  };
-  auto issue_mma = [&](int slot) {           // one thread: 36 UMMAs of one step, then commit
-    const uint32_t ax_hi = smem_u32(slots + slot * SLOT_BYTES), ax_lo = ax_hi + IMG;
-    const uint32_t ah_hi = ax_lo + IMG, ah_lo = ah_hi + IMG;
-    const uint32_t bxh_ = smem_u32(bx_hi), bxl_ = smem_u32(bx_lo), bhh_ = smem_u32(bh_hi), bhl_ = smem_u32(bh_lo);
-    const uint32_t d = tmem_base + slot * 128;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const uint32_t ko = kk * 32;
-      umma_tf32(d, umma_desc(ax_hi + ko), umma_desc(bxh_ + ko), umma_idesc(96), kk > 0 ? 1u : 0u);
-      umma_tf32(d, umma_desc(ax_lo + ko), umma_desc(bxh_ + ko), umma_idesc(96), 1u);
-      umma_tf32(d, umma_desc(ax_hi + ko), umma_desc(bxl_ + ko), umma_idesc(96), 1u);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const uint32_t ko = kk * 32;
-      umma_tf32(d, umma_desc(ah_hi + ko), umma_desc(bhh_ + ko), umma_idesc(64), 1u);
-      umma_tf32(d, umma_desc(ah_lo + ko), umma_desc(bhh_ + ko), umma_idesc(64), 1u);
-      umma_tf32(d, umma_desc(ah_hi + ko), umma_desc(bhl_ + ko), umma_idesc(64), 1u);
-      umma_tf32(d + 96, umma_desc(ah_hi + ko), umma_desc(bhh_ + 64 * 128 + ko), umma_idesc(32), kk > 0 ? 1u : 0u);
-      umma_tf32(d + 96, umma_desc(ah_lo + ko), umma_desc(bhh_ + 64 * 128 + ko), umma_idesc(32), 1u);
-      umma_tf32(d + 96, umma_desc(ah_hi + ko), umma_desc(bhl_ + 64 * 128 + ko), umma_idesc(32), 1u);
-    }
-    umma_commit(&bar[slot]);
-  };
+  {
+    // ================================ walkers ================================
+    const int g = warp >> 3;                               // walker of this thread
+    const int gw = warp & 7, gtid = tid & (WALKER_THREADS - 1);
+    // owner mapping (epilogue): thread = one destination (TMEM lane) x 16 units
+    const int q = gw & 3, split = gw >> 2;
+    const int row = q * 32 + lane;
+    const int u0 = split * UPT;
+    // loader mapping (global <-> shared): 8 lanes cover the 128 bytes of one row, a warp instruction
+    // touches 4 whole rows (4 L1 wavefronts instead of 32 with one row per lane)
+    const int lc = lane & 7;                               // 16-byte chunk of the row
+    const int lr0 = gw * 16 + (lane >> 3);                 // rows lr0 + 4 i, i = 0..3
+    unsigned char* slot = slots + g * SLOT_BYTES;
+    const uint32_t tbase = tmem_base + g * 128 + ((uint32_t)(q * 32) << 16) + u0;
+    const int64_t tile_stride = (int64_t)WALKERS * gridDim.x;
+    uint32_t acc_phase = 0;
 
-  // walk plan of this thread's rows in the NEXT pair of tiles (prefetched one pair ahead)
-  int4 nmeta[2];
-  auto fetch_meta = [&](int64_t pr) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int64_t didx = (pr * 2 + s) * ROWS + row;
-      nmeta[s] = make_int4(-1, 0, 0, IGN_STEP_ZERO);
-      if (!mma_warp && pr < npairs && didx < num_dst) {
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(WALKER_THREADS) : "memory"); };
+    // walk plan of this thread's row in a later tile (prefetched two tiles ahead)
+    auto fetch_meta = [&](int64_t tile) -> int4 {
+      const int64_t didx = tile * ROWS + row;
+      int4 m = make_int4(-1, 0, 0, IGN_STEP_ZERO);
+      if (tile < ntiles && didx < num_dst) {
         if (meta) {
-          nmeta[s] = __ldg(meta + didx);
+          m = __ldg(meta + didx);
         } else {
           const int d = order ? __ldg(order + didx) : (int)didx;
           const int lo = __ldg(steps_rowptr + d), len = __ldg(steps_rowptr + d + 1) - lo;
-          nmeta[s] = make_int4(d, lo, len, len > 0 ? __ldg(steps + lo) : IGN_STEP_ZERO);
+          m = make_int4(d, lo, len, len > 0 ? __ldg(steps + lo) : IGN_STEP_ZERO);
         }
       }
-    }
-  };
-  fetch_meta(blockIdx.x);
+      return m;
+    };
+    int l_d[4], l_lo[4], l_len[4], l_ent[4];               // loader rows: destination, first step, steps, next entry
+    int s_len, s_lo;                                       // owner row: steps, first step
+    float h[UPT];
+    // gather this thread's 16 bytes of the messages of step t of its 4 loader rows (the entries were
+    // fetched one step earlier, so the row loads do not wait on an index load), then fetch the entries
+    // of step t + 1
+    auto load_x = [&](int t, float4 (&x)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int entry = l_ent[i];
+        if (t < l_len[i] && entry >= 0)
+          x[i] = ldg_f4(pick_src(srcs, entry >> IGN_STEP_SRC_SHIFT) + (int64_t)(entry & IGN_STEP_ROW_MASK) * U + lc * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        l_ent[i] = (t + 1 < l_len[i]) ? __ldg(steps + l_lo[i] + t + 1) : IGN_STEP_ZERO;
+    };
+    auto store_x = [&](const float4 (&x)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) store_split(slot, slot + IMG, lr0 + 4 * i, lc, x[i]);
+    };
+    auto store_h = [&]() {
+#pragma unroll
+      for (int j = 0; j < UPT / 4; ++j)
+        store_split(slot + 2 * IMG, slot + 3 * IMG, row, split * (UPT / 4) + j,
+                    make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+    };
+    const uint32_t bxh_ = smem_u32(bx_hi), bxl_ = smem_u32(bx_lo), bhh_ = smem_u32(bh_hi), bhl_ = smem_u32(bh_lo);
+    auto publish = [&]() {                                 // operands written: visible to the async proxy, walker-wide
+      fence_async_smem();
+      tc_fence_before();
+      group_sync();
+    };
+    auto issue = [&]() {                                   // one thread: the 24 UMMAs of one step, then commit
+      if (gtid == 0) {
+        const uint32_t ax_hi = smem_u32(slot), ax_lo = ax_hi + IMG, ah_hi = ax_lo + IMG, ah_lo = ah_hi + IMG;
+        tc_fence_after();
+        umma_chunk_3x(tmem_base + g * 128, ax_hi, ax_lo, bxh_, bxl_, 128, false);
+        umma_chunk_3x(tmem_base + g * 128, ah_hi, ah_lo, bhh_, bhl_, 128, true);
+        umma_commit(&bar_acc[g]);
+      }
+      __syncwarp();
+    };
 
-  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-    Slot sl[2];
-    if (tid < 2) s_maxlen[tid] = 0;
-    __syncthreads();
-    // ---- tile set-up: meta, h0 -> registers + image, x_0 -> image
+    PROF(long long p_a = 0, p_b = 0, ca; long long p_load = 0, p_setup = 0, p_wait = 0, p_epi = 0, p_store = 0, p_pub = 0, p_out = 0, p_tiles = 0,
+         p_steps = 0, p_t0 = clock64(), c0, c1;)
+    int4 nmeta = fetch_meta((int64_t)blockIdx.x * WALKERS + g);
+    int4 nmeta2 = fetch_meta((int64_t)blockIdx.x * WALKERS + g + tile_stride);
+    if (split == 0) s_meta[g][row] = nmeta;
+    if (gtid == 0) s_maxlen[g][0] = s_maxlen[g][1] = 0;
+    group_sync();
+    int par = 0;
+    for (int64_t tile = (int64_t)blockIdx.x * WALKERS + g; tile < ntiles PROF(&& !(dbg == 1 && g == 1)); tile += tile_stride) {
+      // ---- tile set-up.  Loaders: plan of their rows from shared memory, h0 and x_0 -> operand images.
+      PROF(c0 = clock64(); ++p_tiles;)
+      {
+        float4 hv[4], x[4];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      sl[s].d = nmeta[s].x; sl[s].lo = nmeta[s].y; sl[s].len = nmeta[s].z; sl[s].entry = nmeta[s].w;
-#pragma unroll
-      for (int j = 0; j < UPT; ++j) sl[s].h[j] = 0.f;
-      if (sl[s].d >= 0) {
-#pragma unroll
-        for (int j = 0; j < UPT / 4; ++j) {
-          const float4 v = ldg_f4(h0 + (int64_t)sl[s].d * U + u0 + 4 * j);
-          sl[s].h[4 * j] = v.x; sl[s].h[4 * j + 1] = v.y; sl[s].h[4 * j + 2] = v.z; sl[s].h[4 * j + 3] = v.w;
+        for (int i = 0; i < 4; ++i) {
+          const int4 m = s_meta[g][lr0 + 4 * i];
+          l_d[i] = m.x; l_lo[i] = m.y; l_len[i] = m.z; l_ent[i] = m.w;
+          hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m.x >= 0 PROF(&& !(dbg & 16))) hv[i] = ldg_f4(h0 + (int64_t)m.x * U + lc * 4);
         }
+        PROF(if (dbg & 8) { for (int i = 0; i < 4; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f); } else)
+        load_x(0, x);
+        s_len = nmeta.z; s_lo = nmeta.y;                   // owner row
+        {
+          const int wmax = __reduce_max_sync(0xffffffffu, max(max(l_len[0], l_len[1]), max(l_len[2], l_len[3])));
+          if (lane == 0 && wmax > 0 PROF(&& !(dbg & 4))) atomicMax(&s_maxlen[g][par], wmax);
+        }
+        // the tile after this one: its plan landed during the previous walk; pull its state rows
+        // into L2 now, and fetch the plan after it
+        nmeta = nmeta2;
+        if (split == 0 && nmeta.x >= 0 PROF(&& !(dbg & 2))) asm volatile("prefetch.global.L2 [%0];" ::"l"(h0 + (int64_t)nmeta.x * U));
+        nmeta2 = fetch_meta(tile + 2 * tile_stride);
+        PROF(ca = clock64(); p_a += ca - c0;)
+        // h0 as hi + lo with lo = v - hi unrounded (the tensor core truncates it: 2^-21 |v| for this one
+        // step instead of 2^-22), so that the owners read hi + lo == h0 back exactly
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = lr0 + 4 * i, off = r * 128 + ((lc ^ (r & 7)) << 4);
+          float4 hi;
+          hi.x = tf32_rna(hv[i].x); hi.y = tf32_rna(hv[i].y); hi.z = tf32_rna(hv[i].z); hi.w = tf32_rna(hv[i].w);
+          *reinterpret_cast<float4*>(slot + 2 * IMG + off) = hi;
+          *reinterpret_cast<float4*>(slot + 3 * IMG + off) =
+              make_float4(hv[i].x - hi.x, hv[i].y - hi.y, hv[i].z - hi.z, hv[i].w - hi.w);
+        }
+        PROF(ca = clock64(); p_b += ca - c0;)
+        store_x(x);
       }
-      if (split == 0 && sl[s].len > 0) atomicMax(&s_maxlen[s], sl[s].len);
-      if (!mma_warp) {
-        float4 x[UPT / 4];
-        load_x(sl[s], 0, x);
-        store_x(s, x);
-        store_h(s, sl[s]);
+      PROF(c1 = clock64(); p_load += c1 - c0;)
+      publish();
+      const int maxlen = PROF((dbg & 4) ? 3 :) s_maxlen[g][par];
+      if (maxlen > 0) issue();
+      // owners: the running state in full fp32, read back from the state images (rows without a
+      // destination hold zeros)
+#pragma unroll
+      for (int j = 0; j < UPT / 4; ++j) {
+        const int off = row * 128 + (((split * (UPT / 4) + j) ^ (row & 7)) << 4);
+        const float4 hi = *reinterpret_cast<const float4*>(slot + 2 * IMG + off);
+        const float4 lo = *reinterpret_cast<const float4*>(slot + 3 * IMG + off);
+        h[4 * j] = hi.x + lo.x; h[4 * j + 1] = hi.y + lo.y; h[4 * j + 2] = hi.z + lo.z; h[4 * j + 3] = hi.w + lo.w;
       }
-    }
-    fetch_meta(pair + gridDim.x);                        // lands while this pair is being walked
-    fence_async_smem();
-    __syncthreads();
-    const int maxlen0 = s_maxlen[0], maxlen1 = s_maxlen[1];
-    const int maxlen = max(maxlen0, maxlen1);
-    if (mma_warp) {
-      // ---- MMA issuer warp: one elected lane feeds the tensor core; the epilogue warps never wait on it
-      if (lane == 0) {
-        if (maxlen0 > 0) issue_mma(0);
-        if (maxlen1 > 0) issue_mma(1);
-      }
+      PROF(c0 = clock64(); p_setup += c0 - c1;)
+
       for (int t = 0; t < maxlen; ++t) {
+        float4 xn[4];
+        PROF(c0 = clock64(); ++p_steps;)
+        load_x(t + 1, xn);                                 // next messages: in flight while we wait for the MMA
+        mbar_wait(&bar_acc[g], acc_phase);
+        PROF(c1 = clock64(); p_wait += c1 - c0;)
+        acc_phase ^= 1;
+        tc_fence_after();
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int ml = s == 0 ? maxlen0 : maxlen1;
-          if (t + 1 >= ml) continue;
-          // operands of step t + 1 of slot s are in shared memory once all epilogue threads arrived
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "r"(TC_THREADS) : "memory");
-          if (lane == 0) issue_mma(s);
-        }
-      }
-      continue;                                          // next pair (joins the set-up barriers)
-    }
-    if (maxlen0 > 0) uses[0] += 1;
-    if (maxlen1 > 0) uses[1] += 1;
-
-    for (int t = 0; t < maxlen; ++t) {
+        for (int half = 0; half < 2; ++half) {             // 8 units at a time keeps the live registers down
+          uint32_t az[8], ar[8], axh[8], ahh[8];
+          tmem_ld8_nowait(tbase + half * 8, az);
+          tmem_ld8_nowait(tbase + 32 + half * 8, ar);
+          tmem_ld8_nowait(tbase + 64 + half * 8, axh);
+          tmem_ld8_nowait(tbase + 96 + half * 8, ahh);
+          tmem_ld_wait();
+          if (t < s_len) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int ml = s == 0 ? maxlen0 : maxlen1;
-        if (t >= ml) continue;                           // uniform over the CTA
-        Slot& S = sl[s];
-        float4 xn[UPT / 4];
-        load_x(S, t + 1, xn);                            // next message: in flight while we wait for the MMA
-        mbar_wait(&bar[s], (uses[s] - 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tbase = tmem_base + s * 128 + ((uint32_t)(q * 32) << 16) + u0;
-        uint32_t az[UPT], ar[UPT], axh[UPT], ahh[UPT];
-        tmem_ld8_nowait(tbase, az);
-        tmem_ld8_nowait(tbase + 32, ar);
-        tmem_ld8_nowait(tbase + 64, axh);
-        tmem_ld8_nowait(tbase + 96, ahh);
-        tmem_ld_wait();
-        if (t < S.len) {
+            for (int j4 = 0; j4 < 8; j4 += 4) {
+              const int ub = u0 + half * 8 + j4;
+              const float4 vz = *reinterpret_cast<const float4*>(s_gb + ub);
+              const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + ub);
+              const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + ub);
+              const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + ub);
+              const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
+              const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
 #pragma unroll
-          for (int j4 = 0; j4 < UPT; j4 += 4) {
-            const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
-            const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
-            const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
-            const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + u0 + j4);
-            const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
-            const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 + jj;
-              const float pz = __uint_as_float(az[j]) + bz[jj], pr = __uint_as_float(ar[j]) + br[jj];
-              const float z = FAST ? fast_sigmoid(pz) : sigmoid_f(pz);
-              const float r = FAST ? fast_sigmoid(pr) : sigmoid_f(pr);
-              const float ph = fmaf(r, __uint_as_float(ahh[j]) + bhh[jj], __uint_as_float(axh[j]) + bxh[jj]);
-              const float hh = FAST ? fast_tanh(ph) : tanhf(ph);
-              S.h[j] = fmaf(z, S.h[j] - hh, hh);
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 + jj;
+                const float pz = __uint_as_float(az[j]) + bz[jj], pr = __uint_as_float(ar[j]) + br[jj];
+                float& hv = h[half * 8 + j];
+                if (FAST) {
+                  hv = fast_gru_gate(pz, pr, __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hv);
+                } else {
+                  const float z = sigmoid_f(pz), r = sigmoid_f(pr);
+                  const float hh = tanhf(fmaf(r, __uint_as_float(ahh[j]) + bhh[jj], __uint_as_float(axh[j]) + bxh[jj]));
+                  hv = fmaf(z, hv - hh, hh);
+                }
+              }
             }
           }
-          if (h_seq) {
-            float* p = h_seq + (int64_t)(S.lo + t) * U + u0;
+        }
+        if (h_seq && t < s_len) {
+          float* p = h_seq + (int64_t)(s_lo + t) * U + u0;
 #pragma unroll
-            for (int j = 0; j < UPT / 4; ++j)
-              st_f4(p + 4 * j, make_float4(S.h[4 * j], S.h[4 * j + 1], S.h[4 * j + 2], S.h[4 * j + 3]));
-          }
+          for (int j = 0; j < UPT / 4; ++j)
+            st_f4(p + 4 * j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
         }
-        if (t + 1 < ml) {                                // operands of the next step
-          store_h(s, S);
-          store_x(s, xn);
-          fence_async_smem();
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (t + 1 < ml) {                                // hand the slot to the MMA warp, do not wait
-          asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "r"(TC_THREADS) : "memory");
-          uses[s] += 1;
+        PROF(c0 = clock64(); p_epi += c0 - c1;)
+        if (t + 1 < maxlen) {                              // operands of the next step, then do not wait
+          store_h();
+          store_x(xn);
+          PROF(c1 = clock64(); p_store += c1 - c0;)
+          publish();
+          issue();
+          PROF(c0 = clock64(); p_pub += c0 - c1;)
         }
       }
-    }
-    // ---- results
+      // ---- results: owners park the final state in the (now idle) message image, loaders write whole
+      // rows; the same barrier publishes the plan of the next tile
+      PROF(c0 = clock64();)
+      {
+        unsigned char* stage = slot;
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (sl[s].d >= 0) {
-        float* p = out + (int64_t)sl[s].d * U + u0;
+        for (int j = 0; j < UPT / 4; ++j) {
+          const int c4 = split * (UPT / 4) + j;
+          *reinterpret_cast<float4*>(stage + row * 128 + ((c4 ^ (row & 7)) << 4)) =
+              make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+        }
+        if (split == 0) s_meta[g][row] = nmeta;
+        if (gtid == 0) s_maxlen[g][par ^ 1] = 0;          // the next tile's slot (last read one tile ago)
+        group_sync();
+        par ^= 1;
 #pragma unroll
-        for (int j = 0; j < UPT / 4; ++j)
-          st_f4(p + 4 * j, make_float4(sl[s].h[4 * j], sl[s].h[4 * j + 1], sl[s].h[4 * j + 2], sl[s].h[4 * j + 3]));
+        for (int i = 0; i < 4; ++i) {
+          const int r = lr0 + 4 * i;
+          if (l_d[i] >= 0)
+            st_f4(out + (int64_t)l_d[i] * U + lc * 4,
+                  *reinterpret_cast<const float4*>(stage + r * 128 + ((lc ^ (r & 7)) << 4)));
+        }
       }
+      PROF(c1 = clock64(); p_out += c1 - c0;)
     }
+    PROF(if (gtid == 32) {
+      const long long v[10] = {p_load, p_setup, p_wait, p_epi, p_store, p_pub, p_out, p_tiles, p_steps, clock64() - p_t0};
+      for (int i = 0; i < 10; ++i) atomicAdd(&prof_cyc[i], (unsigned long long)v[i]);
+      atomicAdd(&prof_cyc2[0], (unsigned long long)p_a); atomicAdd(&prof_cyc2[1], (unsigned long long)p_b);
+      atomicAdd(&prof_cyc[10], 1ull);
+    })
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
-  }
+  if (warp == 0) tmem_dealloc(tmem_base, 256u);
 }
 
 }  // namespace
@@ -321,7 +352,7 @@ int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* 
                           cudaStream_t st) {
   SrcPtrs sp;
   for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
-  const size_t smem = 1024 + 4 * (size_t)BIMG + 2 * (size_t)SLOT_BYTES;
+  const size_t smem = 1024 + 4 * (size_t)IMG + WALKERS * (size_t)SLOT_BYTES;
   static thread_local bool configured = false;
   static const bool fast = getenv("IGN_GRU_TC_EXACT_MATH") == nullptr;   // default: ex2.approx-based sigmoid / tanh
   if (!configured) {
@@ -331,16 +362,32 @@ int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* 
   }
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t npairs = (ign_cdiv(num_dst, ROWS) + 1) / 2;
-  const int grid = (int)(npairs < sms ? npairs : sms);
+  const int64_t nctas = ign_cdiv(ign_cdiv(num_dst, ROWS), WALKERS);
+  const int grid = (int)(nctas < sms ? nctas : sms);
   if (fast)
     gru_seq_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
                                                              rkernel, bias, out, h_seq,
-                                                             reinterpret_cast<const int4*>(meta));
+                                                             reinterpret_cast<const int4*>(meta) PROF(, getenv("IGN_DBG") ? atoi(getenv("IGN_DBG")) : 0));
   else
     gru_seq_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
                                                               rkernel, bias, out, h_seq,
-                                                              reinterpret_cast<const int4*>(meta));
+                                                              reinterpret_cast<const int4*>(meta) PROF(, getenv("IGN_DBG") ? atoi(getenv("IGN_DBG")) : 0));
   IGN_CHECK_LAUNCH("gru_seq_tc");
+  PROF({
+    unsigned long long h[12];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, prof_cyc, sizeof(h));
+    const double w = (double)h[10], nt = (double)h[7], ns = (double)h[8];
+    fprintf(stderr, "gru_seq_tc walkers %.0f tiles/walker %.1f steps/walker %.1f cycles/walker %.0f | per tile: load+split %.0f "
+                    "publish+issue %.0f results %.0f | per step: wait %.0f gates %.0f split+store %.0f publish+issue %.0f\n",
+            w, nt / w, ns / w, h[9] / w, h[0] / nt, h[1] / nt, h[6] / nt, h[2] / ns, h[3] / ns, h[4] / ns, h[5] / ns);
+    unsigned long long h2[2];
+    cudaMemcpyFromSymbol(h2, prof_cyc2, sizeof(h2));
+    fprintf(stderr, "   set-up cumulative per tile: loads issued %.0f | h0 images stored %.0f | x0 images stored %.0f\n", h2[0] / nt, h2[1] / nt, h[0] / nt);
+    memset(h2, 0, sizeof(h2));
+    cudaMemcpyToSymbol(prof_cyc2, h2, sizeof(h2));
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(prof_cyc, h, sizeof(h));
+  })
   return IGN_OK;
 }

@@ -55,9 +55,6 @@ __device__ __forceinline__ void store_split_exact(unsigned char* img_hi, unsigne
   *reinterpret_cast<float4*>(img_hi + off) = hi;
   *reinterpret_cast<float4*>(img_lo + off) = lo;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gru_step_tc_kernel(
     int t, const int* __restrict__ nt, const int* __restrict__ off, int64_t num_dst, const int4* __restrict__ meta,

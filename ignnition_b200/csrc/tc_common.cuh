@@ -67,6 +67,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one try_wait (may suspend for a hardware-chosen time); true once the phase with this parity completed
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (expect_tx armed first)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -117,7 +134,38 @@ __device__ __forceinline__ void store_split(unsigned char* img_hi, unsigned char
   *reinterpret_cast<float4*>(img_lo + off) = lo;
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.0f, fast_sigmoid(2.0f * x), -1.0f); }
+// 1 / (1 + 2^(-x log2 e)) on the SFU approximations (ex2 2 ulp, rcp 1 ulp): 4 instructions, saturates
+// cleanly (ex2 -> inf gives rcp -> 0)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(2.0f, r, -1.0f);
+}
+
+// One GRU element on 5 SFU operations instead of 6: the reciprocals of the update gate and of the
+// candidate's tanh share one rcp,  z = b / (a b),  tanh = 2 a / (a b) - 1  with a = 1 + e^-pz,
+// b = 1 + e^-2ph.  The exponents are clamped (NaN-propagating min) so that a b stays finite:
+// sigmoid(x) below 2^-40 and 1 - |tanh| below 2^-39 are returned as those bounds.
+__device__ __forceinline__ float fast_gru_gate(float pz, float pr, float pxh, float phh, float h) {
+  float tz, ez, er, r, th, eh, inv;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(tz) : "f"(pz * -1.4426950408889634f), "f"(40.0f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ez) : "f"(tz));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(er) : "f"(pr * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + er));
+  const float ph = fmaf(r, phh, pxh);
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(th) : "f"(ph * -2.8853900817779268f), "f"(40.0f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(th));
+  const float a = 1.0f + ez, b = 1.0f + eh;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(a * b));
+  const float z = b * inv, hh = fmaf(2.0f * a, inv, -1.0f);
+  return fmaf(z, h - hh, hh);
+}
 
 }  // namespace ign_tc

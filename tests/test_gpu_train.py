@@ -11,6 +11,12 @@ from oracle.torch_port import TorchOracle
 
 pytestmark = pytest.mark.gpu
 GRAD_RTOL = 2e-4      # fp32 backward through T=8 x BPTT vs an fp64 autograd reference (normwise)
+# selu' jumps from 1.0507 to 1.7581 at 0: ONE readout pre-activation (of ~1e5) that sits within the
+# forward tolerance of zero and lands on the other side flips that row's whole contribution to the
+# gradients of the layers below it (measured: 6.8e-4 on the 2nd readout layer from one flip with the
+# 3xTF32 forward at 2.7e-6; the fp32 twin kernels at 6e-7 do not flip it).  TF's own fp32 kernels are
+# exposed to the same jump, so the layers under a selu get this bound instead.
+GRAD_RTOL_SELU_KINK = 1.5e-3
 
 
 def rel_err(got, want):
@@ -52,7 +58,8 @@ def test_gradients_match_autograd(case):
     got = tr.grads.cpu().numpy()
     for name, (off, shape) in eng.param_table.items():
         gn = got[off:off + int(np.prod(shape))].reshape(shape)
-        assert rel_err(gn, grads[name]) < GRAD_RTOL, name
+        tol = GRAD_RTOL_SELU_KINK if name.startswith("readout_model") else GRAD_RTOL
+        assert rel_err(gn, grads[name]) < tol, name
 
 
 def test_adam_step_matches_keras_formula():
