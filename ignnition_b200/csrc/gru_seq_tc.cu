@@ -37,7 +37,7 @@ using namespace ign_tc;
 #endif
 
 namespace {
-PROF(__device__ unsigned long long prof_cyc[12]; __device__ unsigned long long prof_cyc2[2];)
+PROF(__device__ unsigned long long prof_cyc[12];)
 
 constexpr int WALKERS = 2;
 constexpr int WALKER_THREADS = 256;                       // 8 warps: 4 TMEM lane groups x 2 unit halves
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_gb[4 * U];
   __shared__ int s_maxlen[WALKERS][2];                  // per tile parity: reset one tile ahead of its use
-  __shared__ int4 s_meta[WALKERS][ROWS];                // walk plan of the walker's current tile
+  __shared__ __align__(16) int4 s_meta[WALKERS][3][ROWS];  // ring of walk plans: this tile, the next, the one after
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -127,22 +127,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
     uint32_t acc_phase = 0;
 
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(WALKER_THREADS) : "memory"); };
-    // walk plan of this thread's row in a later tile (prefetched two tiles ahead)
-    auto fetch_meta = [&](int64_t tile) -> int4 {
+    // walk plan of this thread's row in a later tile -> ring slot, asynchronously (no registers held
+    // across the walk); rows past the end get an empty plan
+    auto plan_to_smem = [&](int64_t tile, int ring) {
+      if (split != 0) return;
+      int4* dst = &s_meta[g][ring][row];
       const int64_t didx = tile * ROWS + row;
-      int4 m = make_int4(-1, 0, 0, IGN_STEP_ZERO);
       if (tile < ntiles && didx < num_dst) {
         if (meta) {
-          m = __ldg(meta + didx);
+          cp_async16(dst, meta + didx);
         } else {
           const int d = order ? __ldg(order + didx) : (int)didx;
           const int lo = __ldg(steps_rowptr + d), len = __ldg(steps_rowptr + d + 1) - lo;
-          m = make_int4(d, lo, len, len > 0 ? __ldg(steps + lo) : IGN_STEP_ZERO);
+          *dst = make_int4(d, lo, len, len > 0 ? __ldg(steps + lo) : IGN_STEP_ZERO);
         }
+      } else {
+        *dst = make_int4(-1, 0, 0, IGN_STEP_ZERO);
       }
-      return m;
+      cp_async_commit();
     };
-    int l_d[4], l_lo[4], l_len[4], l_ent[4];               // loader rows: destination, first step, steps, next entry
+    int l_lo[4], l_len[4], l_ent[4];               // loader rows: destination, first step, steps, next entry
     int s_len, s_lo;                                       // owner row: steps, first step
     float h[UPT];
     // gather this thread's 16 bytes of the messages of step t of its 4 loader rows (the entries were
@@ -187,57 +191,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
       __syncwarp();
     };
 
-    PROF(long long p_a = 0, p_b = 0, ca; long long p_load = 0, p_setup = 0, p_wait = 0, p_epi = 0, p_store = 0, p_pub = 0, p_out = 0, p_tiles = 0,
+    PROF(long long p_load = 0, p_setup = 0, p_wait = 0, p_epi = 0, p_store = 0, p_pub = 0, p_out = 0, p_tiles = 0,
          p_steps = 0, p_t0 = clock64(), c0, c1;)
-    int4 nmeta = fetch_meta((int64_t)blockIdx.x * WALKERS + g);
-    int4 nmeta2 = fetch_meta((int64_t)blockIdx.x * WALKERS + g + tile_stride);
-    if (split == 0) s_meta[g][row] = nmeta;
-    if (gtid == 0) s_maxlen[g][0] = s_maxlen[g][1] = 0;
-    group_sync();
-    int par = 0;
-    for (int64_t tile = (int64_t)blockIdx.x * WALKERS + g; tile < ntiles PROF(&& !(dbg == 1 && g == 1)); tile += tile_stride) {
-      // ---- tile set-up.  Loaders: plan of their rows from shared memory, h0 and x_0 -> operand images.
-      PROF(c0 = clock64(); ++p_tiles;)
-      {
-        float4 hv[4], x[4];
+    // Loads of the NEXT tile's rows (plan from shared memory): h0 chunks into registers, first messages
+    // into x, entries of step 1; its longest list into the other parity's slot.  Issued before the wait
+    // of the current tile's last step, so the set-up of the next tile never sits on a memory round trip.
+    auto next_loads = [&](int ring, int np, float4 (&hv)[4], float4 (&x)[4]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int4 m = s_meta[g][lr0 + 4 * i];
-          l_d[i] = m.x; l_lo[i] = m.y; l_len[i] = m.z; l_ent[i] = m.w;
-          hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m.x >= 0 PROF(&& !(dbg & 16))) hv[i] = ldg_f4(h0 + (int64_t)m.x * U + lc * 4);
-        }
-        PROF(if (dbg & 8) { for (int i = 0; i < 4; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f); } else)
-        load_x(0, x);
-        s_len = nmeta.z; s_lo = nmeta.y;                   // owner row
-        {
-          const int wmax = __reduce_max_sync(0xffffffffu, max(max(l_len[0], l_len[1]), max(l_len[2], l_len[3])));
-          if (lane == 0 && wmax > 0 PROF(&& !(dbg & 4))) atomicMax(&s_maxlen[g][par], wmax);
-        }
-        // the tile after this one: its plan landed during the previous walk; pull its state rows
-        // into L2 now, and fetch the plan after it
-        nmeta = nmeta2;
-        if (split == 0 && nmeta.x >= 0 PROF(&& !(dbg & 2))) asm volatile("prefetch.global.L2 [%0];" ::"l"(h0 + (int64_t)nmeta.x * U));
-        nmeta2 = fetch_meta(tile + 2 * tile_stride);
-        PROF(ca = clock64(); p_a += ca - c0;)
-        // h0 as hi + lo with lo = v - hi unrounded (the tensor core truncates it: 2^-21 |v| for this one
-        // step instead of 2^-22), so that the owners read hi + lo == h0 back exactly
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = lr0 + 4 * i, off = r * 128 + ((lc ^ (r & 7)) << 4);
-          float4 hi;
-          hi.x = tf32_rna(hv[i].x); hi.y = tf32_rna(hv[i].y); hi.z = tf32_rna(hv[i].z); hi.w = tf32_rna(hv[i].w);
-          *reinterpret_cast<float4*>(slot + 2 * IMG + off) = hi;
-          *reinterpret_cast<float4*>(slot + 3 * IMG + off) =
-              make_float4(hv[i].x - hi.x, hv[i].y - hi.y, hv[i].z - hi.z, hv[i].w - hi.w);
-        }
-        PROF(ca = clock64(); p_b += ca - c0;)
-        store_x(x);
+      for (int i = 0; i < 4; ++i) {
+        const int4 m = s_meta[g][ring][lr0 + 4 * i];
+        l_lo[i] = m.y; l_len[i] = m.z; l_ent[i] = m.w;
+        hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m.x >= 0) hv[i] = ldg_f4(h0 + (int64_t)m.x * U + lc * 4);
       }
+      load_x(0, x);
+      const int wmax = __reduce_max_sync(0xffffffffu, max(max(l_len[0], l_len[1]), max(l_len[2], l_len[3])));
+      if (lane == 0 && wmax > 0) atomicMax(&s_maxlen[g][np], wmax);
+    };
+    // h0 as hi + lo with lo = v - hi unrounded (the tensor core truncates it: 2^-21 |v| for this one step
+    // instead of 2^-22), so that the owners read hi + lo == h0 back exactly
+    auto store_h0 = [&](const float4 (&hv)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = lr0 + 4 * i, off = r * 128 + ((lc ^ (r & 7)) << 4);
+        float4 hi;
+        hi.x = tf32_rna(hv[i].x); hi.y = tf32_rna(hv[i].y); hi.z = tf32_rna(hv[i].z); hi.w = tf32_rna(hv[i].w);
+        *reinterpret_cast<float4*>(slot + 2 * IMG + off) = hi;
+        *reinterpret_cast<float4*>(slot + 3 * IMG + off) =
+            make_float4(hv[i].x - hi.x, hv[i].y - hi.y, hv[i].z - hi.z, hv[i].w - hi.w);
+      }
+    };
+
+    const int64_t tile0 = (int64_t)blockIdx.x * WALKERS + g;
+    int par = 0, ring = 0;                                 // parity / ring slot of the current tile
+    {
+      // prologue: plans of the first two tiles, the first tile's operands
+      plan_to_smem(tile0, 0);
+      plan_to_smem(tile0 + tile_stride, 1);
+      if (gtid == 0) s_maxlen[g][0] = s_maxlen[g][1] = 0;
+      cp_async_wait<0>();
+      group_sync();
+      float4 hv[4], x[4];
+      next_loads(0, 0, hv, x);
+      store_h0(hv);
+      store_x(x);
+    }
+    for (int64_t tile = tile0; tile < ntiles PROF(&& !(dbg == 1 && g == 1)); tile += tile_stride) {
+      // ---- the tile's operand images are in place (prologue / tail of the previous tile)
+      PROF(c0 = clock64(); ++p_tiles;)
+      const int ring1 = ring == 2 ? 0 : ring + 1, ring2 = ring1 == 2 ? 0 : ring1 + 1;
+      {
+        const int4 m = s_meta[g][ring][row];               // owner row
+        s_len = m.z; s_lo = m.y;
+      }
+      if (gtid == 0) s_maxlen[g][par ^ 1] = 0;             // last read one tile ago
+      cp_async_wait<0>();                                  // my part of the next tile's plan has landed
       PROF(c1 = clock64(); p_load += c1 - c0;)
       publish();
-      const int maxlen = PROF((dbg & 4) ? 3 :) s_maxlen[g][par];
+      const int maxlen = s_maxlen[g][par];
       if (maxlen > 0) issue();
+      // the plan after the next one (its slot was last read before the barrier above); the next tile's
+      // state rows into L2
+      plan_to_smem(tile + 2 * tile_stride, ring2);
+      if (split == 0) {
+        const int nd = s_meta[g][ring1][row].x;
+        if (nd >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(h0 + (int64_t)nd * U));
+      }
       // owners: the running state in full fp32, read back from the state images (rows without a
       // destination hold zeros)
 #pragma unroll
@@ -249,14 +268,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
       }
       PROF(c0 = clock64(); p_setup += c0 - c1;)
 
+      float4 xn[4];                                        // next messages; after the last step: x_0 of the next tile
+      if (maxlen == 0) {                                   // nothing to walk: the state images are idle already
+        float4 hv[4];
+        next_loads(ring1, par ^ 1, hv, xn);
+        group_sync();                                      // every owner has read its h0 back
+        store_h0(hv);
+      }
       for (int t = 0; t < maxlen; ++t) {
-        float4 xn[4];
+        const bool last = t + 1 == maxlen;
+        float4 hv[4];
         PROF(c0 = clock64(); ++p_steps;)
-        load_x(t + 1, xn);                                 // next messages: in flight while we wait for the MMA
+        if (!last) load_x(t + 1, xn);                      // in flight while we wait for the MMA
+        else next_loads(ring1, par ^ 1, hv, xn);
         mbar_wait(&bar_acc[g], acc_phase);
-        PROF(c1 = clock64(); p_wait += c1 - c0;)
         acc_phase ^= 1;
         tc_fence_after();
+        PROF(c1 = clock64(); p_wait += c1 - c0;)
+        if (last) {                                        // the last MMA is done: the state images are idle
+          if (maxlen == 1) group_sync();                   // ... once every owner has read its h0 back
+          store_h0(hv);
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {             // 8 units at a time keeps the live registers down
           uint32_t az[8], ar[8], axh[8], ahh[8];
@@ -279,13 +311,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = j4 + jj;
                 const float pz = __uint_as_float(az[j]) + bz[jj], pr = __uint_as_float(ar[j]) + br[jj];
-                float& hv = h[half * 8 + j];
+                float& hv_ = h[half * 8 + j];
                 if (FAST) {
-                  hv = fast_gru_gate(pz, pr, __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hv);
+                  hv_ = fast_gru_gate(pz, pr, __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hv_);
                 } else {
                   const float z = sigmoid_f(pz), r = sigmoid_f(pr);
                   const float hh = tanhf(fmaf(r, __uint_as_float(ahh[j]) + bhh[jj], __uint_as_float(axh[j]) + bxh[jj]));
-                  hv = fmaf(z, hv - hh, hh);
+                  hv_ = fmaf(z, hv_ - hh, hh);
                 }
               }
             }
@@ -298,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
             st_f4(p + 4 * j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
         }
         PROF(c0 = clock64(); p_epi += c0 - c1;)
-        if (t + 1 < maxlen) {                              // operands of the next step, then do not wait
+        if (!last) {                                       // operands of the next step, then do not wait
           store_h();
           store_x(xn);
           PROF(c1 = clock64(); p_store += c1 - c0;)
@@ -307,8 +339,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
           PROF(c0 = clock64(); p_pub += c0 - c1;)
         }
       }
-      // ---- results: owners park the final state in the (now idle) message image, loaders write whole
-      // rows; the same barrier publishes the plan of the next tile
+      // ---- results: owners park the final state in the (idle) message image, loaders write whole rows,
+      // then drop the next tile's first messages into the same image
       PROF(c0 = clock64();)
       {
         unsigned char* stage = slot;
@@ -318,24 +350,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_seq_tc_kernel(
           *reinterpret_cast<float4*>(stage + row * 128 + ((c4 ^ (row & 7)) << 4)) =
               make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
         }
-        if (split == 0) s_meta[g][row] = nmeta;
-        if (gtid == 0) s_maxlen[g][par ^ 1] = 0;          // the next tile's slot (last read one tile ago)
         group_sync();
-        par ^= 1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = lr0 + 4 * i;
-          if (l_d[i] >= 0)
-            st_f4(out + (int64_t)l_d[i] * U + lc * 4,
+          const int d = s_meta[g][ring][r].x;              // this tile's plan stays until the next tile's barrier
+          if (d >= 0)
+            st_f4(out + (int64_t)d * U + lc * 4,
                   *reinterpret_cast<const float4*>(stage + r * 128 + ((lc ^ (r & 7)) << 4)));
         }
+        store_x(xn);
+        par ^= 1;
+        ring = ring1;
       }
       PROF(c1 = clock64(); p_out += c1 - c0;)
     }
     PROF(if (gtid == 32) {
       const long long v[10] = {p_load, p_setup, p_wait, p_epi, p_store, p_pub, p_out, p_tiles, p_steps, clock64() - p_t0};
       for (int i = 0; i < 10; ++i) atomicAdd(&prof_cyc[i], (unsigned long long)v[i]);
-      atomicAdd(&prof_cyc2[0], (unsigned long long)p_a); atomicAdd(&prof_cyc2[1], (unsigned long long)p_b);
       atomicAdd(&prof_cyc[10], 1ull);
     })
   }
@@ -378,14 +410,9 @@ int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* 
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, prof_cyc, sizeof(h));
     const double w = (double)h[10], nt = (double)h[7], ns = (double)h[8];
-    fprintf(stderr, "gru_seq_tc walkers %.0f tiles/walker %.1f steps/walker %.1f cycles/walker %.0f | per tile: load+split %.0f "
-                    "publish+issue %.0f results %.0f | per step: wait %.0f gates %.0f split+store %.0f publish+issue %.0f\n",
+    fprintf(stderr, "gru_seq_tc walkers %.0f tiles/walker %.1f steps/walker %.1f cycles/walker %.0f | per tile: head %.0f "
+                    "publish+issue+readback %.0f results+x0 %.0f | per step: wait %.0f gates %.0f split+store %.0f publish+issue %.0f\n",
             w, nt / w, ns / w, h[9] / w, h[0] / nt, h[1] / nt, h[6] / nt, h[2] / ns, h[3] / ns, h[4] / ns, h[5] / ns);
-    unsigned long long h2[2];
-    cudaMemcpyFromSymbol(h2, prof_cyc2, sizeof(h2));
-    fprintf(stderr, "   set-up cumulative per tile: loads issued %.0f | h0 images stored %.0f | x0 images stored %.0f\n", h2[0] / nt, h2[1] / nt, h[0] / nt);
-    memset(h2, 0, sizeof(h2));
-    cudaMemcpyToSymbol(prof_cyc2, h2, sizeof(h2));
     memset(h, 0, sizeof(h));
     cudaMemcpyToSymbol(prof_cyc, h, sizeof(h));
   })

@@ -67,7 +67,8 @@ class _MPPlan:
 
 class Engine:
     def __init__(self, model: ModelDescription, device: Optional[torch.device] = None, seed: int = 0,
-                 csr_mode: int = ops.CSR_SORT, sort_by_length: bool = True, max_step_launches: int = 0):
+                 csr_mode: int = ops.CSR_SORT, sort_by_length: bool = True, max_step_launches: int = 0,
+                 fuse_sum_gru: Optional[bool] = None):
         self.model = model
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if self.device.type != "cuda":
@@ -77,6 +78,9 @@ class Engine:
         # ordered updates whose longest sequence is <= this run step-synchronously (one launch per step,
         # ign_gru_seq_step); 0 = always the sequence walk (ign_gru_seq), which is faster in round 1
         self.max_step_launches = max_step_launches
+        # sum aggregation + GRU: one fused fp32 kernel, or segment_reduce + tensor-core cell.  None picks by
+        # measurement (GEANT2 x 4096 links: 0.121 + 0.087 ms unfused on tensor cores vs 0.333 ms fused fp32)
+        self.fuse_sum_gru = fuse_sum_gru
         self.dims = model.get_input_dimensions()
         self.entities = [e.name for e in model.get_entities()]
         self.hidden = {e.name: e.hidden_state_dimension for e in model.get_entities()}
@@ -498,7 +502,8 @@ class Engine:
 
         # aggregating kinds
         fused = (p.kind == "agg_gru" and p.op == ops.OP_SUM and len(p.adjs) == 1 and msgs[0] is None
-                 and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1]))
+                 and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1])
+                 and (self.fuse_sum_gru if self.fuse_sum_gru is not None else not ops.tensor_cores_enabled()))
         if fused:
             rowptr, col, _ = g.csr[p.adjs[0].name]
             agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
