@@ -32,20 +32,6 @@ constexpr int TC_M = 128;
 constexpr int TC_KC = 32;                       // floats per K chunk = 128 bytes per row
 constexpr int A_IMG = TC_M * 128;               // bytes of one A image (hi or lo) of a chunk
 
-// activation in the epilogue: SELU / ELU use ex2.approx with a Taylor branch near zero instead of
-// expm1f (the epilogue is instruction-bound); everything else as act_fwd
-__device__ __forceinline__ float fast_expm1(float x) {       // x <= 0
-  const float p = x * (1.0f + x * (0.5f + x * (0.16666667f + x * (0.041666668f + x * 0.0083333338f))));
-  return x > -0.125f ? p : __expf(x) - 1.0f;
-}
-__device__ __forceinline__ float act_epi(int act, float x) {
-  if (act == IGN_ACT_SELU) return x > 0.0f ? IGN_SELU_SCALE * x : (IGN_SELU_SCALE * IGN_SELU_ALPHA) * fast_expm1(x);
-  if (act == IGN_ACT_RELU) return fmaxf(x, 0.0f);
-  if (act == IGN_ACT_LINEAR) return x;
-  if (act == IGN_ACT_ELU) return x > 0.0f ? x : fast_expm1(x);
-  return act_fwd(act, x);
-}
-
 // W[K,N] -> per chunk c: [hi image: N rows x 128 B][lo image]  (the shared-memory layout of B)
 __global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ img) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,13 +46,16 @@ __global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, 
   *reinterpret_cast<float*>(base + N * 128 + sw128_off(n, kk)) = lo;
 }
 
+// ACT >= 0: compile-time activation (see act_epi); -1: taken from the argument
+template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __restrict__ x, int64_t M, int K,
                                                                  const float* __restrict__ wimg,
-                                                                 const float* __restrict__ bias, int N, int act,
+                                                                 const float* __restrict__ bias, int N, int act_,
                                                                  float* __restrict__ y, float* __restrict__ pre,
                                                                  int tmem_cols, const float* __restrict__ head_w,
                                                                  const float* __restrict__ head_b, float* __restrict__ head_out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int act = ACT >= 0 ? ACT : act_;
   // carve-up (1024-byte aligned images): stage s: A_hi | A_lo | B_hi | B_lo
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_img = N * 128;
@@ -224,11 +213,6 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   dense_tc_prep_kernel<<<(unsigned)ign_cdiv((int64_t)k * n, 256), 256, 0, st>>>(w, k, n, img);
   IGN_CHECK_LAUNCH("dense_tc_prep");
   const size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * n * 128);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    IGN_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   int cols = 32;
   while (cols < n) cols <<= 1;
   int sms = IGN_NUM_SMS, dev = 0;
@@ -236,8 +220,21 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   const int64_t tiles = ign_cdiv(m, TC_M);
   const int grid = (int)(tiles < sms ? tiles : sms);
   if (head_out) IGN_CUDA(cudaMemsetAsync(head_out, 0, (size_t)m * sizeof(float), st));
-  dense_tc_kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols, head_w, head_b,
-                                                   head_out);
+  auto launch = [&](auto kernel) -> int {
+    IGN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols, head_w, head_b, head_out);
+    return IGN_OK;
+  };
+  int rc;
+  switch (act) {
+    case IGN_ACT_LINEAR: rc = launch(dense_tc_kernel<IGN_ACT_LINEAR>); break;
+    case IGN_ACT_RELU: rc = launch(dense_tc_kernel<IGN_ACT_RELU>); break;
+    case IGN_ACT_SELU: rc = launch(dense_tc_kernel<IGN_ACT_SELU>); break;
+    case IGN_ACT_SIGMOID: rc = launch(dense_tc_kernel<IGN_ACT_SIGMOID>); break;
+    case IGN_ACT_TANH: rc = launch(dense_tc_kernel<IGN_ACT_TANH>); break;
+    default: rc = launch(dense_tc_kernel<-1>); break;
+  }
+  if (rc != IGN_OK) return rc;
   IGN_CHECK_LAUNCH("dense_tc");
   return IGN_OK;
 }

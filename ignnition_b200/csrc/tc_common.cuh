@@ -142,11 +142,39 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return r;
 }
+// tanh for |x| < 1/4 as an odd polynomial (relative error 1e-8): 2 / (1 + e) - 1 has an ABSOLUTE error of
+// ~3 ulp of 1.0, which is a large relative error on a small candidate state and accumulates over the
+// steps of a walk (measured: path states 3.7e-5 -> fp32-kernel level with this branch)
+__device__ __forceinline__ float tanh_small(float x) {
+  const float x2 = x * x;
+  return x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 0.021869488f, -0.053968254f), 0.13333334f), -0.33333334f), 1.0f);
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.8853900817779268f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return fmaf(2.0f, r, -1.0f);
+  return fabsf(x) < 0.25f ? tanh_small(x) : fmaf(2.0f, r, -1.0f);
+}
+// exp(x) - 1 for x <= 0 on one SFU operation: the ABSOLUTE error (2^-22 of a value in (0, 1]) is what the
+// next GEMM sees, so the relative accuracy of expm1 near 0 is not needed (2.4e-7 x scale x alpha = 4e-7,
+// below the fp32 accumulation error of the dot products that consume it; measured: the model's parity
+// figure is the same 6.1e-6 with a Taylor branch near zero, the readout 0.5 ms slower)
+__device__ __forceinline__ float fast_expm1_neg(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return e - 1.0f;
+}
+// activation of a tensor-core epilogue.  Call it with a COMPILE-TIME act wherever possible: with a run-time
+// act every element drags the whole if-chain (and the libm slow paths of act_fwd) through the epilogue --
+// measured 2.4x on the fused readout (profiles/r1_mlp_head_phases.md)
+__device__ __forceinline__ float act_epi(int act, float x) {
+  if (act == IGN_ACT_SELU) return x > 0.0f ? IGN_SELU_SCALE * x : (IGN_SELU_SCALE * IGN_SELU_ALPHA) * fast_expm1_neg(x);
+  if (act == IGN_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == IGN_ACT_LINEAR) return x;
+  if (act == IGN_ACT_ELU) return x > 0.0f ? x : fast_expm1_neg(x);
+  if (act == IGN_ACT_SIGMOID) return fast_sigmoid(x);
+  if (act == IGN_ACT_TANH) return fast_tanh(x);
+  return act_fwd(act, x);
 }
 
 // One GRU element on 5 SFU operations instead of 6: the reciprocals of the update gate and of the
@@ -164,7 +192,8 @@ __device__ __forceinline__ float fast_gru_gate(float pz, float pr, float pxh, fl
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eh) : "f"(th));
   const float a = 1.0f + ez, b = 1.0f + eh;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(a * b));
-  const float z = b * inv, hh = fmaf(2.0f * a, inv, -1.0f);
+  const float z = b * inv;
+  const float hh = fabsf(ph) < 0.25f ? tanh_small(ph) : fmaf(2.0f * a, inv, -1.0f);
   return fmaf(z, h - hh, hh);
 }
 

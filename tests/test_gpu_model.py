@@ -17,9 +17,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5          # BASELINE.json north star: 1e-5 relative (fp32) on states and predictions
 # States that are re-aggregated over large fan-ins (links, Q-size nodes) amplify the fp32 rounding of
 # the path states ~10x: measured vs the fp64 oracle, the fp32 CUDA-core kernels reach 8.3e-6 on the
-# Q-size node states and the 3xTF32 tensor-core kernels 0.95-1.3e-5 ("Numerics").  The
-# tensor-core path is therefore held to 1e-5 on predictions and 2e-5 on intermediate states; the
-# fp32 twin path to 1e-5 on everything.
+# Q-size node states of the golden cases (6e-5 on link states of random GEANT2 samples: fp32 itself is
+# not 1e-5 away from fp64 there) and the 3xTF32 tensor-core kernels 1.0-1.9e-5 (1.1-1.2x the fp32
+# kernels on the same inputs; DESIGN.md, "Numerics").  The tensor-core path is therefore held to 1e-5
+# on predictions and 2e-5 on intermediate states; the fp32 twin path to 1e-5 on everything.
 RTOL_STATE_TC = 2e-5
 
 
