@@ -119,8 +119,10 @@ constexpr int RADIX = 256;
 // per-CTA digit histogram, written bin-major (hist[d * nblocks + b]) so one scan yields the
 // global base of every (digit, CTA) pair
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, int64_t n,
-                                                             int shift, int* __restrict__ hist, int nblocks) {
+                                                             int shift, int* __restrict__ hist, int nblocks,
+                                                             const int* __restrict__ unsorted) {
   __shared__ int h[RADIX];
+  if (unsorted && *unsorted == 0) return;              // input already in key order: nothing to sort
   h[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
@@ -140,8 +142,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* 
                                                                 const int* __restrict__ vals_in,
                                                                 uint32_t* __restrict__ keys_out,
                                                                 int* __restrict__ vals_out, int64_t n, int shift,
-                                                                const int* __restrict__ offsets, int nblocks) {
+                                                                const int* __restrict__ offsets, int nblocks,
+                                                                const int* __restrict__ unsorted) {
   __shared__ int cnt[RS_WARPS][RADIX];
+  if (unsorted && *unsorted == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&cnt[0][0])[i] = 0;
   __syncthreads();
@@ -214,8 +218,11 @@ size_t sort_ws_bytes(int64_t n, int64_t max_key_exclusive) {
 }
 
 // sorts (keys, iota) by key; the sorted keys/values end in *keys_sorted / *vals_sorted (inside ws)
+// unsorted (optional, device): 0 = the keys are already non-decreasing, the passes return at once and the
+// caller uses (keys, iota) instead of the buffers
 int radix_sort_pairs(const uint32_t* keys, int64_t n, int64_t max_key_exclusive, void* ws,
-                     const uint32_t** keys_sorted, const int** vals_sorted, cudaStream_t st) {
+                     const uint32_t** keys_sorted, const int** vals_sorted, cudaStream_t st,
+                     const int* unsorted = nullptr) {
   SortPlan p = sort_plan(n, max_key_exclusive);
   char* w = reinterpret_cast<char*>(ws);
   uint32_t* kbuf[2] = {reinterpret_cast<uint32_t*>(w), reinterpret_cast<uint32_t*>(w + p.keys_bytes)};
@@ -226,12 +233,12 @@ int radix_sort_pairs(const uint32_t* keys, int64_t n, int64_t max_key_exclusive,
   const int* vin = nullptr;   // iota on the first pass
   for (int pass = 0; pass < p.passes; ++pass) {
     const int shift = pass * 8;
-    rs_hist_kernel<<<p.nblocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, p.nblocks);
+    rs_hist_kernel<<<p.nblocks, RS_THREADS, 0, st>>>(kin, n, shift, hist, p.nblocks, unsorted);
     IGN_CHECK_LAUNCH("rs_hist");
     int rc = exclusive_scan(hist, hist, (int64_t)RADIX * p.nblocks, scan_ws, st);
     if (rc) return rc;
     rs_scatter_kernel<<<p.nblocks, RS_THREADS, 0, st>>>(kin, vin, kbuf[pass & 1], vbuf[pass & 1], n, shift, hist,
-                                                         p.nblocks);
+                                                         p.nblocks, unsorted);
     IGN_CHECK_LAUNCH("rs_scatter");
     kin = kbuf[pass & 1];
     vin = vbuf[pass & 1];
@@ -244,9 +251,20 @@ int radix_sort_pairs(const uint32_t* keys, int64_t n, int64_t max_key_exclusive,
 // ------------------------------------------------------------------------------------------
 // CSR assembly
 // ------------------------------------------------------------------------------------------
+// *unsorted = 1 if some key is smaller than its predecessor (flag cleared by the caller).  The generator
+// emits every adjacency destination by destination (generator_std_to_framework.py:140-160), so edge lists
+// usually arrive in destination order and the stable sort is the identity.
+__global__ void sorted_check_kernel(const uint32_t* __restrict__ keys, int64_t n, int* __restrict__ unsorted) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < n && keys[i] > keys[i + 1]) *unsorted = 1;
+}
+
 // rowptr[d] = number of sorted keys < d: position i owns every d in (keys[i-1], keys[i]]
-__global__ void rowptr_fill_kernel(const uint32_t* __restrict__ keys, int64_t n, int64_t num_dst,
+// (keys = keys_orig when the input was already sorted)
+__global__ void rowptr_fill_kernel(const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ keys_orig,
+                                   const int* __restrict__ unsorted, int64_t n, int64_t num_dst,
                                    int* __restrict__ rowptr) {
+  const uint32_t* __restrict__ keys = (unsorted && *unsorted == 0) ? keys_orig : keys_sorted;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   const int64_t lo = (i == 0) ? 0 : (int64_t)keys[i - 1] + 1;
@@ -256,10 +274,11 @@ __global__ void rowptr_fill_kernel(const uint32_t* __restrict__ keys, int64_t n,
 }
 
 __global__ void gather_col_kernel(const int* __restrict__ perm, const int* __restrict__ src, int64_t n,
-                                  int* __restrict__ col, int* __restrict__ perm_out) {
+                                  int* __restrict__ col, int* __restrict__ perm_out,
+                                  const int* __restrict__ unsorted) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int e = perm[i];
+  const int e = (unsorted && *unsorted == 0) ? (int)i : perm[i];
   col[i] = src[e];
   if (perm_out) perm_out[i] = e;
 }
@@ -464,11 +483,17 @@ extern "C" int ign_csr_build(const int32_t* dst, const int32_t* src, const int32
   if (mode == IGN_CSR_SORT) {
     const uint32_t* ks = nullptr;
     const int* vs = nullptr;
-    int rc = radix_sort_pairs(reinterpret_cast<const uint32_t*>(dst), n_edges, num_dst, w2, &ks, &vs, st);
+    // the 256 spare bytes at the end of the workspace hold the "unsorted" flag
+    int* unsorted = reinterpret_cast<int*>(w + ign_csr_build_ws_bytes(n_edges, num_dst) - 256);
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(dst);
+    IGN_CUDA(cudaMemsetAsync(unsorted, 0, sizeof(int), st));
+    sorted_check_kernel<<<grid1d(n_edges), 256, 0, st>>>(keys, n_edges, unsorted);
+    IGN_CHECK_LAUNCH("sorted_check");
+    int rc = radix_sort_pairs(keys, n_edges, num_dst, w2, &ks, &vs, st, unsorted);
     if (rc) return rc;
-    rowptr_fill_kernel<<<grid1d(n_edges + 1), 256, 0, st>>>(ks, n_edges, num_dst, rowptr);
+    rowptr_fill_kernel<<<grid1d(n_edges + 1), 256, 0, st>>>(ks, keys, unsorted, n_edges, num_dst, rowptr);
     IGN_CHECK_LAUNCH("rowptr_fill");
-    gather_col_kernel<<<grid1d(n_edges), 256, 0, st>>>(vs, src, n_edges, col, perm_buf);
+    gather_col_kernel<<<grid1d(n_edges), 256, 0, st>>>(vs, src, n_edges, col, perm_buf, unsorted);
     IGN_CHECK_LAUNCH("gather_col");
   } else {
     int* counts = reinterpret_cast<int*>(w2);

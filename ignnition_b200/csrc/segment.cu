@@ -118,21 +118,27 @@ __device__ __forceinline__ float init_state_value(const FeatList& f, int64_t row
   }
   return 0.0f;
 }
-// one thread per 4 consecutive columns (hidden % 4 == 0), 16-byte stores
+// one thread per row: the feature columns (a handful) then zeros, all as 16-byte stores; rows are
+// hidden * 4 bytes apart, so a warp writes 32 consecutive rows = one contiguous span (hidden % 4 == 0)
 __global__ void init_state_kernel(FeatList f, int64_t n, int hidden, int total_feat, float* __restrict__ state) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = hidden / 4;
-  if (i >= n * q) return;
-  const int64_t row = i / q;
-  const int c = (int)(i - row * q) * 4;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c < total_feat) {
-    v.x = init_state_value(f, row, c);
-    v.y = init_state_value(f, row, c + 1);
-    v.z = init_state_value(f, row, c + 2);
-    v.w = init_state_value(f, row, c + 3);
+  const int q = hidden / 4;                                    // float4 columns per row
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // lane l of a warp takes float4 column (l % q), (l % q) + 32 ... of row (warp rows) -- simple and
+  // coalesced: 32 lanes cover 32 consecutive float4 of the flat [n * q] array, the row index costs one
+  // 32-bit division per lane instead of a 64-bit one per float4
+  const int64_t total4 = n * q;
+  for (int64_t i = gid; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = (i >> 31) == 0 ? (int64_t)((uint32_t)i / (uint32_t)q) : i / q;
+    const int c = (int)(i - row * q) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < total_feat) {
+      v.x = init_state_value(f, row, c);
+      v.y = init_state_value(f, row, c + 1);
+      v.z = init_state_value(f, row, c + 2);
+      v.w = init_state_value(f, row, c + 3);
+    }
+    st_f4(state + row * hidden + c, v);
   }
-  st_f4(state + row * hidden + c, v);
 }
 __global__ void init_state_scalar_kernel(FeatList f, int64_t n, int hidden, float* __restrict__ state) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,8 +274,10 @@ extern "C" int ign_init_state(int n_feat, const float* const* feats, const int32
   IGN_REQUIRE(total <= hidden, IGN_ERR_INVALID,
               "IGNNITION: init_state: features (%d) wider than the hidden state (%d)", total, hidden);
   if (hidden % 4 == 0)
-    init_state_kernel<<<(unsigned)ign_cdiv(n * (hidden / 4), 256), 256, 0, ign_stream(stream)>>>(f, n, hidden, total,
-                                                                                                 state);
+  {
+    const int64_t blocks = ign_cdiv(n * (hidden / 4), 256 * 4);       // 4 float4 per thread
+    init_state_kernel<<<(unsigned)(blocks > 0 ? blocks : 1), 256, 0, ign_stream(stream)>>>(f, n, hidden, total, state);
+  }
   else
     init_state_scalar_kernel<<<(unsigned)ign_cdiv(n * hidden, 256), 256, 0, ign_stream(stream)>>>(f, n, hidden, state);
   IGN_CHECK_LAUNCH("init_state");
