@@ -8,17 +8,33 @@
 //                D[:, 3U:4U]  (+)= h . R[:, h]      (N = U)
 // K and R do not fit in shared memory next to the operand tiles at U = 64, so their split / swizzled
 // images are prepared once per call into a caller workspace (gru_cell_tc_prep) and streamed per
-// 32-float K chunk with cp.async; two shared-memory stages and two TMEM accumulators let the
-// loads + MMAs of tile i+1 run under the epilogue (gates, new state) of tile i.
+// 32-float K chunk by TMA bulk copies; two shared-memory stages and two TMEM accumulators, with the
+// work split by role (loaders / MMA issuer / TMA producer / gate epilogue) so that the loads + MMAs of
+// tile i+1 run under the epilogue of tile i.  History (10 M rows, U = 64): 5.31 ms in lock-step with
+// thread 0 issuing in line -> 3.57 ms; a third weight slot made it slower (4.11 ms: less L1 left for the
+// row-per-lane state loads / stores of the epilogue, which is what bounds it now).
+
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
 using namespace ign_tc;
 
-namespace {
+// -DIGN_CELL_PROFILE: per-phase clock64() sums of thread 0, printed after every launch.
+#ifdef IGN_CELL_PROFILE
+#include <stdio.h>
+#include <string.h>
+#define PROF(...) __VA_ARGS__
+#else
+#define PROF(...)
+#endif
 
-constexpr int NPART = 4;                      // warps per TMEM lane group
-constexpr int TC_THREADS = 128 * NPART;       // 16 warps: the gate epilogue is latency-bound with fewer
+namespace {
+PROF(__device__ unsigned long long cell_prof[8];)
+
+constexpr int GROUP = 256;                    // threads of the loader group and of the epilogue group
+constexpr int MMA_WARP = 16, TMA_WARP = 17;
+constexpr int CELL_THREADS = 2 * GROUP + 64;
 constexpr int ROWS = 128;
 constexpr int A_IMG = ROWS * 128;
 
@@ -40,27 +56,40 @@ __global__ void gru_cell_tc_prep_kernel(const float* __restrict__ kernel, const 
   *reinterpret_cast<float*>(base + 3 * U * 128 + sw128_off(n, kk)) = lo;
 }
 
+// Roles (warp-specialised, mbarriers only inside the tile loop):
+//   warps 0-7    loaders: operand chunk (128 rows x 32 floats of x or h) -> hi / lo images of the stage,
+//                arrive on full[stage]
+//   warps 8-15   epilogue: gates + new state of tile i from accumulator i & 1 while the loaders and the
+//                tensor core work on tile i + 1
+//   warp 16      MMA issuer (one lane): waits full[stage] + the weight chunk, issues, commits to
+//                stage[stage] and, after a tile's last chunk, to acc[ab]
+//   warp 17      TMA producer (one lane): the weight chunk of a stage as soon as the stage is free
 template <int U>
-__global__ void __launch_bounds__(TC_THREADS, 1) gru_cell_tc_kernel(const float* __restrict__ x,
-                                                                    const float* __restrict__ h, int64_t n,
-                                                                    const float* __restrict__ wimg,
-                                                                    const float* __restrict__ bias,
-                                                                    float* __restrict__ out) {
+__global__ void __launch_bounds__(CELL_THREADS, 1) gru_cell_tc_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ h, int64_t n,
+                                                                      const float* __restrict__ wimg,
+                                                                      const float* __restrict__ bias,
+                                                                      float* __restrict__ out) {
   constexpr int NC = U / 32;                 // K chunks per operand
   constexpr int B_IMG = 3 * U * 128;         // bytes of one weight image (hi or lo) of a chunk
   constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
   constexpr int DCOLS = 4 * U;               // accumulator columns
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_stage[2];
-  __shared__ uint64_t bar_acc[2];
+  __shared__ uint64_t bar_stage[2];          // the UMMAs that read the stage are done
+  __shared__ uint64_t bar_full[2];           // operand images of the stage are in place (256 arrivals)
+  __shared__ uint64_t bar_b[2];              // weight chunk landed (complete_tx)
+  __shared__ uint64_t bar_acc[2];            // accumulator complete
+  __shared__ uint64_t bar_drained[2];        // accumulator read by every epilogue thread (256 arrivals)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_gb[4 * U];          // merged gate biases [bz | br | bxh | bhh]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    mbar_init(&bar_stage[0], 1); mbar_init(&bar_stage[1], 1);
-    mbar_init(&bar_acc[0], 1); mbar_init(&bar_acc[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_stage[i], 1); mbar_init(&bar_full[i], GROUP); mbar_init(&bar_b[i], 1);
+      mbar_init(&bar_acc[i], 1); mbar_init(&bar_drained[i], GROUP);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 2 * DCOLS);
@@ -75,117 +104,147 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gru_cell_tc_kernel(const float*
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int64_t ntiles = (n + ROWS - 1) / ROWS;
-  uint32_t stage_uses[2] = {0, 0}, acc_uses[2] = {0, 0};
-  uint32_t chunk_ctr = 0;                                 // global chunk counter -> stage = ctr & 1
+  uint32_t stage_uses[2] = {0, 0}, acc_uses[2] = {0, 0}, ctr = 0;   // every role walks the same chunk sequence
 
-  // loads + MMAs of one tile into accumulator `ab`
-  auto produce = [&](int64_t tile, int ab) {
-    const int64_t m0 = tile * ROWS;
-    const uint32_t d = tmem_base + ab * DCOLS;
-#pragma unroll 1
-    for (int c = 0; c < 2 * NC; ++c) {
-      const int s = chunk_ctr & 1;
-      unsigned char* st = smem + s * STAGE;
-      if (stage_uses[s] > 0) mbar_wait(&bar_stage[s], (stage_uses[s] - 1) & 1);
-      {   // weight chunk image (hi + lo): straight copy
-        const char* src = reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG);
-        unsigned char* dst = st + 2 * A_IMG;
-        for (int i = tid * 16; i < 2 * B_IMG; i += TC_THREADS * 16) cp_async16(dst + i, src + i);
-        cp_async_commit();
-      }
-      {   // operand chunk: 128 rows x 32 floats of x (c < NC) or h
-        const float* base = (c < NC) ? x : h;
-        const int koff = (c < NC ? c : c - NC) * 32;
-#pragma unroll
-        for (int j = 0; j < 1024 / TC_THREADS; ++j) {
-          const int idx = tid + j * TC_THREADS;
-          const int r = idx >> 3, c4 = idx & 7;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m0 + r < n) v = ldg_f4(base + (m0 + r) * U + koff + c4 * 4);
-          store_split(st, st + A_IMG, r, c4, v);
+  if (warp == MMA_WARP) {
+    int ab = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ab ^= 1) {
+      const uint32_t d = tmem_base + ab * DCOLS;
+      for (int c = 0; c < 2 * NC; ++c, ++ctr) {
+        const int s = ctr & 1;
+        if (lane == 0) {
+          unsigned char* st = smem + s * STAGE;
+          if (c == 0 && acc_uses[ab] > 0) mbar_wait(&bar_drained[ab], (acc_uses[ab] - 1) & 1);
+          mbar_wait(&bar_full[s], stage_uses[s] & 1);
+          mbar_wait(&bar_b[s], stage_uses[s] & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+          if (c < NC) {
+            umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 3 * U, c > 0);
+          } else {
+            umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 2 * U, true);
+            umma_chunk_3x(d + 3 * U, a_hi, a_lo, b_hi + 2 * U * 128, b_lo + 2 * U * 128, U, c > NC);
+          }
+          umma_commit(&bar_stage[s]);
+          if (c == 2 * NC - 1) umma_commit(&bar_acc[ab]);
         }
+        __syncwarp();
+        stage_uses[s] += 1;
       }
-      cp_async_wait<0>();
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
-        if (c < NC) {
-          umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 3 * U, c > 0);
-        } else {
-          umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 2 * U, true);
-          umma_chunk_3x(d + 3 * U, a_hi, a_lo, b_hi + 2 * U * 128, b_lo + 2 * U * 128, U, c > NC);
-        }
-        umma_commit(&bar_stage[s]);
-        if (c == 2 * NC - 1) umma_commit(&bar_acc[ab]);
-      }
-      stage_uses[s] += 1;
-      chunk_ctr += 1;
+      acc_uses[ab] += 1;
     }
-    acc_uses[ab] += 1;
-  };
-
-  // gates + new state of one tile from accumulator `ab`
-  auto consume = [&](int64_t tile, int ab) {
-    const int64_t m0 = tile * ROWS;
-    mbar_wait(&bar_acc[ab], (acc_uses[ab] - 1) & 1);
-    tc_fence_after();
-    const int q = warp & 3, part = warp >> 2;
-    const int64_t row = m0 + q * 32 + lane;
-    const uint32_t tb = tmem_base + ab * DCOLS + ((uint32_t)(q * 32) << 16);
-    constexpr int UPT = U / NPART;                       // units per thread: 16 (U = 64) or 8 (U = 32)
-    const int u0 = part * UPT;
-    uint32_t az[UPT], ar[UPT], axh[UPT], ahh[UPT];
-    if constexpr (UPT == 16) {
-      tmem_ld16_nowait(tb + u0, az);
-      tmem_ld16_nowait(tb + U + u0, ar);
-      tmem_ld16_nowait(tb + 2 * U + u0, axh);
-      tmem_ld16_nowait(tb + 3 * U + u0, ahh);
-    } else {
-      tmem_ld8_nowait(tb + u0, az);
-      tmem_ld8_nowait(tb + U + u0, ar);
-      tmem_ld8_nowait(tb + 2 * U + u0, axh);
-      tmem_ld8_nowait(tb + 3 * U + u0, ahh);
-    }
-    tmem_ld_wait();
-    if (row < n) {
-#pragma unroll
-      for (int j4 = 0; j4 < UPT; j4 += 4) {
-        const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
-        const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
-        const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
-        const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + u0 + j4);
-        const float4 ho = ldg_f4(h + row * U + u0 + j4);
-        const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
-        const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
-        const float hold[4] = {ho.x, ho.y, ho.z, ho.w};
-        float hn[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = j4 + jj;
-          const float z = fast_sigmoid(__uint_as_float(az[j]) + bz[jj]);
-          const float r = fast_sigmoid(__uint_as_float(ar[j]) + br[jj]);
-          const float hh = fast_tanh(fmaf(r, __uint_as_float(ahh[j]) + bhh[jj], __uint_as_float(axh[j]) + bxh[jj]));
-          hn[jj] = fmaf(z, hold[jj] - hh, hh);
+  } else if (warp == TMA_WARP) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < 2 * NC; ++c, ++ctr) {
+        const int s = ctr & 1;
+        if (lane == 0) {
+          if (stage_uses[s] > 0) mbar_wait(&bar_stage[s], (stage_uses[s] - 1) & 1);
+          mbar_expect_tx(&bar_b[s], 2 * B_IMG);
+          bulk_g2s(smem + s * STAGE + 2 * A_IMG, reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG),
+                   2 * B_IMG, &bar_b[s]);
         }
-        st_f4(out + row * U + u0 + j4, make_float4(hn[0], hn[1], hn[2], hn[3]));
+        __syncwarp();
+        stage_uses[s] += 1;
       }
     }
-    tc_fence_before();
-  };
-
-  // software pipeline: MMAs of tile i+1 are in flight while the gates of tile i are computed
-  int64_t tile = blockIdx.x;
-  int ab = 0;
-  if (tile < ntiles) produce(tile, ab);
-  while (tile < ntiles) {
-    const int64_t next = tile + gridDim.x;
-    if (next < ntiles) produce(next, ab ^ 1);
-    consume(tile, ab);
-    __syncthreads();                 // accumulator `ab` fully read before it is produced again
-    tile = next;
-    ab ^= 1;
+  } else if (warp < GROUP / 32) {
+    // ---- loaders: every chunk is loaded into registers two chunks ahead of its use (32 KB per SM in
+    // flight; with one chunk in flight the kernel was bound by bytes in flight at 1.5 TB/s)
+    PROF(long long p_stage = 0, p_load = 0, c0, c1;)
+    constexpr int PER = 1024 / GROUP;                      // float4 per thread per chunk
+    float4 v[2][PER];                                      // chunk parity -> register set (2 NC is even)
+    auto load_chunk = [&](float4 (&dst)[PER], int64_t tile, int c) {
+      const int64_t m0 = tile * ROWS;
+      const float* base = (c < NC) ? x : h;
+      const int koff = (c < NC ? c : c - NC) * 32;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int idx = tid + j * GROUP;
+        const int r = idx >> 3, c4 = idx & 7;
+        dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tile < ntiles && m0 + r < n) dst[j] = ldg_f4(base + (m0 + r) * U + koff + c4 * 4);
+      }
+    };
+    load_chunk(v[0], blockIdx.x, 0);
+    load_chunk(v[1], blockIdx.x, 1);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+      for (int c = 0; c < 2 * NC; ++c, ++ctr) {
+        const int s = ctr & 1;
+        unsigned char* st = smem + s * STAGE;
+        PROF(c0 = clock64();)
+        if (stage_uses[s] > 0) mbar_wait(&bar_stage[s], (stage_uses[s] - 1) & 1);
+        PROF(c1 = clock64(); p_stage += c1 - c0;)
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int idx = tid + j * GROUP;
+          store_split(st, st + A_IMG, idx >> 3, idx & 7, v[c & 1][j]);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_full[s]);
+        if (c + 2 < 2 * NC) load_chunk(v[c & 1], tile, c + 2);        // two chunks ahead
+        else load_chunk(v[c & 1], tile + gridDim.x, c + 2 - 2 * NC);
+        PROF(c0 = clock64(); p_load += c0 - c1;)
+        stage_uses[s] += 1;
+      }
+    }
+    PROF(if (tid == 32) { atomicAdd(&cell_prof[0], (unsigned long long)p_stage); atomicAdd(&cell_prof[1], (unsigned long long)p_load); })
+  } else {
+    // ---- epilogue: gates + new state, thread = one row x U / 2 units, 16 at a time
+    PROF(long long p_acc = 0, p_gate = 0, c0, c1;)
+    const int ew = warp - GROUP / 32;
+    const int q = ew & 3, half = ew >> 2;
+    int ab = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ab ^= 1) {
+      const int64_t row = tile * ROWS + q * 32 + lane;
+      const uint32_t tb = tmem_base + ab * DCOLS + ((uint32_t)(q * 32) << 16);
+      float4 hold_all[U / 8];                              // old state of this thread's U / 2 units
+#pragma unroll
+      for (int j = 0; j < U / 8; ++j)
+        hold_all[j] = row < n ? ldg_f4(h + row * U + half * (U / 2) + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      PROF(c0 = clock64();)
+      mbar_wait(&bar_acc[ab], acc_uses[ab] & 1);
+      tc_fence_after();
+      PROF(c1 = clock64(); p_acc += c1 - c0;)
+#pragma unroll
+      for (int u0 = half * (U / 2); u0 < (half + 1) * (U / 2); u0 += 16) {
+        uint32_t az[16], ar[16], axh[16], ahh[16];
+        tmem_ld16_nowait(tb + u0, az);
+        tmem_ld16_nowait(tb + U + u0, ar);
+        tmem_ld16_nowait(tb + 2 * U + u0, axh);
+        tmem_ld16_nowait(tb + 3 * U + u0, ahh);
+        const float4* ho = hold_all + (u0 - half * (U / 2)) / 4;
+        tmem_ld_wait();
+        if (u0 + 16 >= (half + 1) * (U / 2)) {           // last read of this accumulator by this thread
+          tc_fence_before();
+          mbar_arrive(&bar_drained[ab]);
+        }
+        if (row < n) {
+#pragma unroll
+          for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
+            const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
+            const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
+            const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + u0 + j4);
+            const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
+            const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
+            const float hold[4] = {ho[j4 / 4].x, ho[j4 / 4].y, ho[j4 / 4].z, ho[j4 / 4].w};
+            float hn[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              hn[jj] = fast_gru_gate(__uint_as_float(az[j]) + bz[jj], __uint_as_float(ar[j]) + br[jj],
+                                     __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hold[jj]);
+            }
+            st_f4(out + row * U + u0 + j4, make_float4(hn[0], hn[1], hn[2], hn[3]));
+          }
+        }
+      }
+      acc_uses[ab] += 1;
+      PROF(c0 = clock64(); p_gate += c0 - c1;)
+    }
+    PROF(if (tid == GROUP + 32) { atomicAdd(&cell_prof[2], (unsigned long long)p_acc); atomicAdd(&cell_prof[3], (unsigned long long)p_gate); })
   }
   tc_fence_before();
   __syncthreads();
@@ -213,15 +272,25 @@ int ign_gru_cell_tc_launch(const float* x, const float* h, int64_t n, int units,
       IGN_CUDA(cudaFuncSetAttribute(gru_cell_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[1] = true;
     }
-    gru_cell_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(x, h, n, img, bias, out);
+    gru_cell_tc_kernel<64><<<grid, CELL_THREADS, smem, st>>>(x, h, n, img, bias, out);
   } else {
     const size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * 3 * 32 * 128);
     if (!configured[0]) {
       IGN_CUDA(cudaFuncSetAttribute(gru_cell_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured[0] = true;
     }
-    gru_cell_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(x, h, n, img, bias, out);
+    gru_cell_tc_kernel<32><<<grid, CELL_THREADS, smem, st>>>(x, h, n, img, bias, out);
   }
   IGN_CHECK_LAUNCH("gru_cell_tc");
+  PROF({
+    unsigned long long hp[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(hp, cell_prof, sizeof(hp));
+    const double nt = (double)tiles, nc = nt * 2 * (units / 32);
+    fprintf(stderr, "gru_cell_tc<%d> loader warp 1 per chunk: wait stage %.0f split+store %.0f | epilogue warp 1 per tile: "
+                    "wait acc %.0f gates %.0f\n", units, hp[0] / nc, hp[1] / nc, hp[2] / nt, hp[3] / nt);
+    memset(hp, 0, sizeof(hp));
+    cudaMemcpyToSymbol(cell_prof, hp, sizeof(hp));
+  })
   return IGN_OK;
 }
