@@ -327,9 +327,11 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         top = max(kern.values(), key=lambda k: k["ms_total"])
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
-        # workload (profiles/r1_ncu_full_tc.md); only known for the kernels profiled there
-        ncu_traffic = {("ign_gru_seq", "routenet_geant2_b4096"): 821.9e6,
-                       ("ign_agg_gru_cell", "routenet_geant2_b4096"): 387.8e6}
+        # workload (profiles/r1_final.md); only known for the kernels profiled there
+        ncu_traffic = {("ign_gru_seq", "routenet_geant2_b4096"): 819.5e6,     # profiles/r1_final.md
+                       ("ign_mlp_head", "routenet_geant2_b4096"): 301.5e6,
+                       ("ign_segment_reduce", "routenet_geant2_b4096"): 348.7e6,
+                       ("ign_gru_cell", "routenet_geant2_b4096"): 88.8e6}
         roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": top["gbs"] / hbm_peak,
                 "traffic": ncu_traffic.get((top["name"], args.workload)) if n_samples == n_default else None,
