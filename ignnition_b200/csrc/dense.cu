@@ -289,7 +289,7 @@ bool ign_dense_tc_supported(int k, int n);
 size_t ign_dense_tc_ws(int k, int n);
 int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
                         float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w = nullptr,
-                        const float* head_b = nullptr, float* head_out = nullptr);
+                        const float* head_b = nullptr, float* head_out = nullptr, bool w_transposed = false);
 
 extern "C" size_t ign_dense_ws_bytes(int k, int n) {
   return (k > 0 && n > 0 && ign_dense_tc_supported(k, n)) ? ign_dense_tc_ws(k, n) : 0;
@@ -353,8 +353,14 @@ extern "C" int ign_dense_head(const float* x, int64_t m, int k, const float* w, 
                              head_b, out);
 }
 
+// dX = dZ W^T is a Dense layer with the transposed kernel: K' = n, N' = k
+extern "C" size_t ign_dense_bwd_ws_bytes(int k, int n) {
+  return (k > 0 && n > 0 && ign_dense_tc_supported(n, k)) ? ign_dense_tc_ws(n, k) : 0;
+}
+
 extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, int n, int act,
-                             const float* pre_act, float* dy, float* dx, float* dw, float* db, void* stream) {
+                             const float* pre_act, float* dy, float* dx, float* dw, float* db, void* ws,
+                             size_t ws_bytes, void* stream) {
   IGN_REQUIRE(m >= 0 && k > 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: dense_bwd: bad shape");
   if (m == 0) return IGN_OK;
   IGN_REQUIRE(x && w && dy, IGN_ERR_INVALID, "IGNNITION: dense_bwd: null pointer");
@@ -364,7 +370,13 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
     act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db);
     IGN_CHECK_LAUNCH("act_bwd_bias");
   }
-  if (dx) {   // dX[m,k] = dZ[m,n] W^T : B = W stored [k,n] = [N',K'] with N'=k, K'=n
+  if (dx && ws && ign_tensor_cores_enabled() && ign_dense_tc_supported(n, k) && ws_bytes >= ign_dense_tc_ws(n, k) &&
+      m >= 128) {
+    // tensor cores (3xTF32): y[m, k] = dZ[m, n] . W^T[n, k]
+    int rc = ign_dense_tc_launch(dy, m, n, w, nullptr, k, IGN_ACT_LINEAR, dx, nullptr, ws, st, nullptr, nullptr,
+                                 nullptr, true);
+    if (rc != IGN_OK) return rc;
+  } else if (dx) {   // dX[m,k] = dZ[m,n] W^T : B = W stored [k,n] = [N',K'] with N'=k, K'=n
     dim3 grid((unsigned)ign_cdiv(m, BM), (unsigned)ign_cdiv(k, BN), 1);
     gemm_kernel<false, true, 1><<<grid, GEMM_THREADS, 0, st>>>(dy, w, dx, m, k, n, nullptr, 0, nullptr, 0);
     IGN_CHECK_LAUNCH("dense_bwd_dx");

@@ -33,11 +33,13 @@ constexpr int TC_KC = 32;                       // floats per K chunk = 128 byte
 constexpr int A_IMG = TC_M * 128;               // bytes of one A image (hi or lo) of a chunk
 
 // W[K,N] -> per chunk c: [hi image: N rows x 128 B][lo image]  (the shared-memory layout of B)
-__global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ img) {
+// transposed: the GEMM uses W^T, i.e. element (k, n) of the [K, N] operand is w[n * K + k] (w stored [N, K])
+__global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ img,
+                                     bool transposed) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K * N) return;
   const int k = i / N, n = i % N;
-  const float v = w[i];
+  const float v = transposed ? w[(size_t)n * K + k] : w[i];
   float hi, lo;
   tf32_split(v, hi, lo);
   const int c = k / TC_KC, kk = k % TC_KC;
@@ -208,9 +210,9 @@ size_t ign_dense_tc_ws(int k, int n) { return (size_t)(k / TC_KC) * 2 * n * 128;
 
 int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
                         float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w,
-                        const float* head_b, float* head_out) {
+                        const float* head_b, float* head_out, bool w_transposed) {
   float* img = reinterpret_cast<float*>(ws);
-  dense_tc_prep_kernel<<<(unsigned)ign_cdiv((int64_t)k * n, 256), 256, 0, st>>>(w, k, n, img);
+  dense_tc_prep_kernel<<<(unsigned)ign_cdiv((int64_t)k * n, 256), 256, 0, st>>>(w, k, n, img, w_transposed);
   IGN_CHECK_LAUNCH("dense_tc_prep");
   const size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * n * 128);
   int cols = 32;

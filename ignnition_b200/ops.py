@@ -303,7 +303,13 @@ def dense_bwd(x, w, act: int, pre_act, dy, dx, dw, db):
     lib = _lib.load()
     m, k = x.shape
     n = w.shape[1]
+    ws, nbytes = None, 0
+    if dx is not None and tensor_cores_enabled():
+        nbytes = lib.ign_dense_bwd_ws_bytes(k, n)
+        if nbytes:
+            ws = _workspace(nbytes, x.device)
     _lib.check(lib.ign_dense_bwd(_f(x), m, k, _f(w), n, act, _f(pre_act), _f(dy), _f(dx), _f(dw), _f(db),
+                                 ws.data_ptr() if ws is not None else None, nbytes if ws is not None else 0,
                                  _stream()), "dense_bwd")
 
 

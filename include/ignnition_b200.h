@@ -225,9 +225,13 @@ int ign_mse_loss(const float* pred, const float* label, int64_t n, float grad_sc
                  double* sse, void* stream);
 
 /* dx = (dy * act'(pre)) W^T ; dW += x^T (dy*act') ; db += colsum(dy*act').
- * dx nullable.  dy is overwritten with dy*act'(pre).  dW/db are ACCUMULATED (caller zeroes). */
+ * dx nullable.  dy is overwritten with dy*act'(pre).  dW/db are ACCUMULATED (caller zeroes).
+ * ws (nullable, ign_dense_bwd_ws_bytes(k, n) bytes, 0 = shape not built for tensor cores): with it dx
+ * runs as a 3xTF32 tcgen05 GEMM with the transposed kernel; dW stays an fp32 CUDA-core GEMM. */
+size_t ign_dense_bwd_ws_bytes(int k, int n);
 int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, int n, int act,
-                  const float* pre_act, float* dy, float* dx, float* dw, float* db, void* stream);
+                  const float* pre_act, float* dy, float* dx, float* dw, float* db, void* ws,
+                  size_t ws_bytes, void* stream);
 
 /* backward of ign_gru_cell: given d_out [n,units] computes dx [n,f_in], dh [n,units] (both nullable)
  * and ACCUMULATES d_kernel, d_recurrent_kernel, d_bias. */
