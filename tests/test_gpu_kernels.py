@@ -390,6 +390,83 @@ def test_mlp_head_fused(m, k1, n1, n2):
     assert got.shape == (m, 1) and rel_err(got.reshape(-1), want) < RTOL
 
 
+def test_attention_aggregate_vs_padded_softmax():
+    """ign_attention_aggregate against the reference formulation on the padded tensor: softmax over the
+    DESTINATIONS of one sample per padded column, zero pads included (auxilary_classes.py:318-338)."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(4)
+    F = 32
+    samples = [(7, 5), (1, 3), (40, 25)]                 # (destinations, sources) per sample; block-diagonal batch
+    dsts, srcs, doff, soff = [], [], [0], [0]
+    for nd, ns in samples:
+        for d in range(nd):
+            k = rng.randint(0, 5)                        # some destinations receive nothing
+            dsts += [doff[-1] + d] * k
+            srcs += list(soff[-1] + rng.randint(0, ns, k))
+        doff.append(doff[-1] + nd); soff.append(soff[-1] + ns)
+    dst = np.asarray(dsts, np.int32); src = np.asarray(srcs, np.int32)
+    n_dst, n_src = doff[-1], soff[-1]
+    rows = rng.randn(n_src, F).astype(np.float32)
+    s_src = rng.randn(n_src).astype(np.float32); s_dst = rng.randn(n_dst).astype(np.float32)
+    rowptr, col, _, _ = ops.csr_build(dev(dst), dev(src), None, n_dst)
+    deg = np.bincount(dst, minlength=n_dst)
+    got = ops.attention_aggregate(rowptr, col, dev(rows), dev(s_src), dev(s_dst), dev(np.asarray(doff, np.int32)),
+                                  int(deg.max())).cpu().numpy()
+    want = np.zeros((n_dst, F))
+    for k in range(len(samples)):
+        d0, d1 = doff[k], doff[k + 1]
+        L = max(int(deg[d0:d1].max()), 1)
+        aux = np.zeros((d1 - d0, L)); msg = np.zeros((d1 - d0, L, F)); pos = np.zeros(d1 - d0, int)
+        for e in range(len(dst)):
+            if d0 <= dst[e] < d1:
+                a = float(s_src[src[e]]) + float(s_dst[dst[e]])
+                aux[dst[e] - d0, pos[dst[e] - d0]] = a if a > 0 else 0.2 * a
+                msg[dst[e] - d0, pos[dst[e] - d0]] = rows[src[e]]
+                pos[dst[e] - d0] += 1
+        ex = np.exp(aux - aux.max(axis=0, keepdims=True))
+        coef = ex / ex.sum(axis=0, keepdims=True)        # softmax over axis 0
+        valid = np.arange(L)[None, :] < deg[d0:d1, None]
+        want[d0:d1] = ((coef * valid)[:, :, None] * msg).sum(axis=1)
+    assert rel_err(got, want) < RTOL
+
+
+def test_partner_index_conv_finish_mul():
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(6)
+    rp0 = np.asarray([0, 2, 2, 5, 6], np.int32); rp1 = np.asarray([0, 1, 4, 6, 6], np.int32)
+    idx1 = np.asarray([10, 11, 12, 13, 14, 15], np.int32)
+    got = ops.partner_index(dev(rp0), dev(rp1), dev(idx1), 6).cpu().numpy()
+    assert np.array_equal(got, [10, -1, 14, 15, -1, -1])     # bit-exact index work
+    n, F = 50, 12
+    nsum = rng.randn(n, F).astype(np.float32); me = rng.randn(n, F).astype(np.float32)
+    deg = rng.randint(1, 6, n); rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    got = ops.conv_finish(dev(nsum), dev(me), dev(rowptr), ops.ACTIVATIONS["relu"]).cpu().numpy()
+    assert rel_err(got, np.maximum((nsum.astype(np.float64) + me) / deg[:, None], 0)) < RTOL
+    a = rng.randn(33, 7).astype(np.float32); b = rng.randn(33, 7).astype(np.float32)
+    assert np.array_equal(ops.mul(dev(a), dev(b)).cpu().numpy(), a * b)
+    # a negative index gathers a zero row (padding of the concat-axis-2 layout)
+    out = ops.gather_concat([dev(a)], [dev(np.asarray([0, -1, 32], np.int32))], 3).cpu().numpy()
+    assert np.array_equal(out, np.stack([a[0], np.zeros(7, np.float32), a[32]]))
+
+
+def test_csr_build_presorted_and_unsorted_agree():
+    """the sorted-input fast path (no radix passes) and the sort give the same CSR, bit for bit"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(9)
+    n_dst, E = 5000, 60000
+    dst_sorted = np.sort(rng.randint(0, n_dst, E)).astype(np.int32)
+    src = rng.randint(0, 777, E).astype(np.int32)
+    rp, col, perm, _ = ops.csr_build(dev(dst_sorted), dev(src), None, n_dst, want_perm=True)
+    want_rp, want_col, want_perm = orc.stable_sort_csr(src, dst_sorted, n_dst)
+    assert np.array_equal(rp.cpu().numpy(), want_rp) and np.array_equal(col.cpu().numpy(), want_col)
+    assert np.array_equal(perm.cpu().numpy(), np.arange(E))
+    shuffle = rng.permutation(E)
+    rp2, col2, perm2, _ = ops.csr_build(dev(dst_sorted[shuffle]), dev(src[shuffle]), None, n_dst, want_perm=True)
+    w_rp, w_col, w_perm = orc.stable_sort_csr(src[shuffle], dst_sorted[shuffle], n_dst)
+    assert np.array_equal(rp2.cpu().numpy(), w_rp) and np.array_equal(col2.cpu().numpy(), w_col)
+    assert np.array_equal(perm2.cpu().numpy(), w_perm)
+
+
 def test_init_state_and_gather_concat():
     from ignnition_b200 import ops
     rng = np.random.RandomState(0)
