@@ -221,6 +221,8 @@ def run_ours(args):
     # end to end: a stream of batches.  Batch k+1 is copied host -> device on a copy stream while batch k
     # is computed (two device staging buffers); every step still pays its own H2D and its own D2H.
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)          # predictions go back while the next batch computes
+    pred_done = torch.cuda.Event()
     stage = [torch.empty(pinned[0].numel(), dtype=torch.uint8, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
@@ -245,7 +247,12 @@ def run_ours(args):
         e2e_state["next"] = issue_upload((k + 1) & 1)   # overlaps with this step's compute
         pred = step_resident(graph)
         free[k & 1].record()
-        host_pred.copy_(pred, non_blocking=True)
+        pred_done.record()
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(pred_done)
+            if torch.is_tensor(pred) and pred.numel() == host_pred.numel():
+                host_pred.copy_(pred, non_blocking=True)
+                pred.record_stream(d2h_stream)
         e2e_state["k"] = k + 1
         return graph
 
