@@ -59,6 +59,15 @@ SIGNATURES = {
     "ign_attention_ws_bytes": (_sz, [_i64, _i64, _int]),
     "ign_attention_aggregate": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "ign_partner_index": (_int, [_p, _p, _p, _i64, _p, _p]),
+    "ign_ingest_create": (_p, [_int, _p, _int, _p, _p, _int, _p, _p, _p, _p, C.c_char_p]),
+    "ign_ingest_destroy": (None, [_p]),
+    "ign_ingest_reset": (None, [_p]),
+    "ign_ingest_parse": (_i64, [_p, C.c_char_p, _sz, _i64]),
+    "ign_ingest_n_samples": (_i64, [_p]),
+    "ign_ingest_offsets": (_p, [_p, _int]),
+    "ign_ingest_feature": (_i64, [_p, _int, _p]),
+    "ign_ingest_adjacency": (_i64, [_p, _int, _p, _p, _p, _p, _p]),
+    "ign_ingest_labels": (_i64, [_p, _p]),
     "ign_mul": (_int, [_i64, _p, _p, _p, _p]),
     "ign_conv_finish": (_int, [_p, _p, _p, _int, _i64, _int, _p, _p]),
     "ign_axpy": (_int, [_i64, _f, _p, _p, _p]),

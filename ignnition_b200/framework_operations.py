@@ -107,6 +107,32 @@ def samples_of(model: ModelDescription, directory: str, training: bool, shuffle:
             return
 
 
+def native_batches(model: ModelDescription, engine, directory: str, training: bool,
+                   namespace: Optional[dict] = None, workers: int = 8) -> Iterator:
+    """One normalised :class:`Batch` per ``*.tar.gz`` of ``directory`` through the C++ ingest
+    (``ingest.NativeIngest``): the same arrays as ``samples_of`` + ``Engine.assemble`` without the per-edge
+    Python loops.  The user's normalisation functions are applied to the whole batch array at once, so
+    they must be elementwise (every one in ``examples/`` is)."""
+    from .ingest import NativeIngest
+    fns = {}
+    for f in model.get_all_features():
+        if str(f.normalization) != "None":
+            fn = _resolve(f.normalization, namespace)
+            if fn is None:
+                raise RuntimeError("IGNNITION: The normalization function %s is not defined in the main file."
+                                   % f.normalization)
+            fns[f.name] = (lambda v, fn=fn, name=f.name: fn(v, name))
+    out_name, out_norm, _ = model.get_output_info()
+    label_fn = None
+    if training and str(out_norm) != "None":
+        fn = _resolve(out_norm, namespace)
+        if fn is None:
+            raise RuntimeError("IGNNITION: The normalization function %s is not defined in the main file." % out_norm)
+        label_fn = lambda v, fn=fn: fn(v, out_name)
+    return NativeIngest.batches_parallel(engine, directory, workers, out_name if training else None,
+                                         feature_fns=fns, label_fn=label_fn)
+
+
 def eval_metrics(labels: np.ndarray, preds: np.ndarray) -> Dict[str, float]:
     """label/prediction mean, MAE, MRE, R^2 (generate_model.py:770-787, 201-216)."""
     y, p = labels.astype(np.float64).reshape(-1), preds.astype(np.float64).reshape(-1)
@@ -138,10 +164,26 @@ def load_checkpoint(engine, path: str) -> int:
 
 
 def evaluate(model: ModelDescription, engine, directory: str, n_samples: int, shuffle: bool = False,
-             namespace: Optional[dict] = None) -> Dict[str, float]:
+             namespace: Optional[dict] = None, native_ingest: Optional[bool] = None) -> Dict[str, float]:
+    """``native_ingest`` (default: the IGNNITION_NATIVE_INGEST environment variable, off): read the dataset
+    through the C++ ingest, one batch per file, instead of the per-sample Python generator."""
     out_name, _, out_denorm = model.get_output_info()
     ys, ps = [], []
-    it = samples_of(model, directory, True, shuffle, namespace)
+    if native_ingest is None:
+        native_ingest = os.environ.get("IGNNITION_NATIVE_INGEST", "0") not in ("", "0")
+    if native_ingest:
+        from .ingest import NativeIngest
+        native_ingest = NativeIngest.supported(engine) and not shuffle
+    if native_ingest:
+        n_seen = 0
+        for batch in native_batches(model, engine, directory, True, namespace):
+            graph = engine.build_graph(engine.upload(batch))
+            ps.append(engine.forward(graph).cpu().numpy().reshape(-1))
+            ys.append(batch.arrays["labels"].reshape(-1))
+            n_seen += batch.n_samples
+            if n_samples and n_seen >= n_samples:
+                break
+    it = samples_of(model, directory, True, shuffle, namespace) if not native_ingest else iter(())
     while True:
         chunk = list(itertools.islice(it, min(64, n_samples - len(ys)) if n_samples else 64))
         if not chunk:

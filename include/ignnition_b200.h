@@ -290,6 +290,36 @@ int ign_conv_finish(const float* nsum, const float* self, const int32_t* rowptr,
 /* y[i] += x[idx[i]] row-wise helper and elementwise utilities used by the backward pass */
 int ign_axpy(int64_t n, float a, const float* x, float* y, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Native dataset ingest (host only): the text of a data.json -> the block-diagonal batch arrays.
+ * Replaces the per-edge Python loops of generator (generator_std_to_framework.py:32-50, :102-107,
+ * :134-190) and the per-sample concatenation; results are identical array for array.
+ *
+ * The model side is given as flat tables: entity type names; features (name, index of the entity
+ * type they belong to); adjacencies (name, source / destination entity type index, 1 if the model
+ * reads edge parameters); the label name (nullable: inference).  ign_ingest_parse appends every sample
+ * of `json` (one sample object, or an array of them, at most max_samples if >= 0) to the batch under
+ * construction and returns how many it appended (< 0: error, message in ign_last_error).  Source and
+ * destination indices already carry the per-sample offsets; seq is the position inside the
+ * destination's list; edge parameters are truncated towards zero like the reference's int64 cast.
+ * The result pointers stay valid until the next parse / reset / destroy.  A handle is single-threaded;
+ * different handles may parse different files concurrently (the call holds no global state).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ign_ingest ign_ingest_t;
+ign_ingest_t* ign_ingest_create(int n_entities, const char* const* entity_names, int n_features,
+                                const char* const* feature_names, const int32_t* feature_entity, int n_adj,
+                                const char* const* adj_names, const int32_t* adj_src, const int32_t* adj_dst,
+                                const int32_t* adj_params, const char* label_name);
+void ign_ingest_destroy(ign_ingest_t* g);
+void ign_ingest_reset(ign_ingest_t* g);
+int64_t ign_ingest_parse(ign_ingest_t* g, const char* json, size_t len, int64_t max_samples);
+int64_t ign_ingest_n_samples(const ign_ingest_t* g);
+const int64_t* ign_ingest_offsets(const ign_ingest_t* g, int entity);          /* [n_samples + 1] */
+int64_t ign_ingest_feature(const ign_ingest_t* g, int feature, const float** data);
+int64_t ign_ingest_adjacency(const ign_ingest_t* g, int adj, const int32_t** src, const int32_t** dst,
+                             const int32_t** seq, const float** params, int32_t* params_width);
+int64_t ign_ingest_labels(const ign_ingest_t* g, const float** data);
+
 #ifdef __cplusplus
 }
 #endif

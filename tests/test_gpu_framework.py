@@ -66,3 +66,7 @@ execute_gpu: True
     assert len(preds) == 6 and preds[0].shape == (182,) and np.all(preds[0] > 0)
     m = ignnition.evaluate(model, engine, str(tmp_path / "eval"), 6, namespace=ns)
     assert set(m) >= {"label/mean", "prediction/mean", "mae", "mre", "r-squared", "loss"}
+    # the same evaluation with the dataset read through the C++ ingest (one batch per file)
+    m2 = ignnition.evaluate(model, engine, str(tmp_path / "eval"), 6, namespace=ns, native_ingest=True)
+    for k in m:
+        assert abs(m2[k] - m[k]) <= 1e-5 * max(abs(m[k]), 1e-12), k

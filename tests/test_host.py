@@ -357,3 +357,120 @@ def test_cabi_rejects_oversized_and_bad_arguments_on_the_host():
     assert lib.ign_partner_index(None, None, None, 5, None, None) == -1 and lib.ign_partner_index(None, None, None, 0, None, None) == 0
     with pytest.raises(RuntimeError, match="IGNNITION"):
         _lib.check(-1, "x")
+
+
+class _SpecEngine:
+    """what NativeIngest reads from an Engine (no GPU needed to build it)"""
+
+    def __init__(self, md):
+        from ignnition_b200.batching import AdjacencySpec
+        self.entities = [e.name for e in md.get_entities()]
+        self.features = [(f.name, e.name, f.size) for e in md.get_entities() for f in e.features]
+        self.adjacencies, self.sequences = [], []
+        seen = set()
+        for _, mps in md.get_mp_instances():
+            for mp in mps:
+                for src in mp.source_entities:
+                    if src.adj_vector not in seen:
+                        seen.add(src.adj_vector)
+                        uses = any(i == "edge_params" for op in src.message_formation for i in getattr(op, "input", []) or [])
+                        self.adjacencies.append(AdjacencySpec(src.adj_vector, src.name, mp.destination_entity, uses))
+
+
+@pytest.mark.parametrize("case", ["routenet_nsfnet", "routenet_geant2"])
+def test_native_ingest_equals_python_generator(case):
+    """the C++ ingest of data.json text gives, array for array, what the Python mirror of
+    the reference generator + block-diagonal assembly gives (integer arrays bit-exact, floats bit-exact)."""
+    import json
+    from ignnition_b200 import synthetic
+    from ignnition_b200.batching import assemble
+    from ignnition_b200.generator import sample_dimensions, sample_to_tensors
+    from ignnition_b200.ingest import NativeIngest
+    from ignnition_b200.model_description import ModelDescription
+    g = load_golden(case)
+    topo = "geant2" if "geant2" in case else "nsfnet"
+    samples = [synthetic.routenet_sample(topo, s, s) for s in range(5)] + list((g.get("samples") or [])[:1])
+    md = ModelDescription(g["model_json"], sample_dimensions(samples[0]))
+    eng = _SpecEngine(md)
+    out_name = md.get_output_info()[0]
+    feats = [f[0] for f in eng.features]
+    adj = md.get_adjecency_info()
+    pairs = [sample_to_tensors(s, feats, out_name, adj, [], [], True) for s in samples]
+    want = assemble([p[0] for p in pairs], eng.entities, eng.features, eng.adjacencies, (), [p[1] for p in pairs])
+    ing = NativeIngest(eng, label_name=out_name)
+    text = json.dumps(samples)
+    assert ing.parse(text) == len(samples)
+    got = ing.batch()
+    assert got.n_samples == want.n_samples and got.num == want.num and got.n_edges == want.n_edges
+    assert got.max_seq == want.max_seq
+    assert set(got.arrays) == set(want.arrays)
+    for k in want.arrays:
+        assert got.arrays[k].dtype == want.arrays[k].dtype, k
+        assert np.array_equal(got.arrays[k], want.arrays[k]), k
+    for e in eng.entities:
+        assert np.array_equal(got.offsets[e], want.offsets[e])
+    # one object at a time appends to the same batch; reset starts over
+    ing.reset()
+    for s in samples:
+        assert ing.parse(json.dumps(s, indent=1)) == 1          # whitespace-tolerant
+    again = ing.batch()
+    for k in want.arrays:
+        assert np.array_equal(again.arrays[k], want.arrays[k]), k
+
+
+def test_native_ingest_edge_params_and_errors():
+    import json
+    from ignnition_b200.batching import AdjacencySpec
+    from ignnition_b200.ingest import NativeIngest
+
+    class E:
+        entities = ["node"]
+        features = [("x", "node", 2)]
+        adjacencies = [AdjacencySpec("adj", "node", "node", True)]
+        sequences = []
+
+    s = {"entities": {"b": "node", "a\u00e9": "node", "c": "node"}, "x": [[1, 2.5], [3e-1, -4], [0.1, 7]],
+         "adj": {"c": [["b", [1.9, -2.9]], ["a\u00e9", [3, 4]]], "b": []}, "y": 3.25}
+    ing = NativeIngest(E(), label_name="y")
+    assert ing.parse(json.dumps(s)) == 1 and ing.parse(json.dumps([s, s])) == 2
+    b = ing.batch()
+    assert b.n_samples == 3 and b.num["node"] == 9
+    assert np.array_equal(b.arrays["src_adj"], [0, 1, 3, 4, 6, 7]) and np.array_equal(b.arrays["dst_adj"], [2, 2, 5, 5, 8, 8])
+    assert np.array_equal(b.arrays["seq_adj"], [0, 1] * 3)
+    assert np.array_equal(b.arrays["params_adj"][:2], [[1.0, -2.0], [3.0, 4.0]])       # truncation, quirk 11
+    assert np.array_equal(b.arrays["feat_x"][:6], np.asarray([1, 2.5, 3e-1, -4, 0.1, 7], np.float32))
+    assert np.array_equal(b.arrays["labels"], [3.25] * 3)
+    bad = dict(s); bad["adj"] = {"zzz": ["b"]}
+    ing.reset()
+    with pytest.raises(RuntimeError, match="not in the entities"):
+        ing.parse(json.dumps(bad))
+    ing.reset()
+    with pytest.raises(RuntimeError, match="was not found although being expected"):
+        ing.parse(json.dumps({"entities": {"a": "node"}, "x": [[1, 2]]}))
+    with pytest.raises(RuntimeError, match="malformed"):
+        ing.parse('{"entities": {"a": "node"}, "x": [[1, 2]], "adj": {"a": ["a",]')
+
+
+def test_native_ingest_reads_dataset_files_in_parallel(tmp_path):
+    import json
+    from ignnition_b200 import synthetic
+    from ignnition_b200.batching import assemble
+    from ignnition_b200.generator import read_dataset, sample_dimensions, sample_to_tensors
+    from ignnition_b200.ingest import NativeIngest
+    from ignnition_b200.model_description import ModelDescription
+    g = load_golden("routenet_nsfnet")
+    samples = [synthetic.routenet_sample("nsfnet", k % 3, k) for k in range(10)]
+    synthetic.write_dataset(str(tmp_path), samples, per_file=4)            # 3 files: 4 + 4 + 2 samples
+    md = ModelDescription(g["model_json"], sample_dimensions(samples[0]))
+    eng = _SpecEngine(md)
+    out_name = md.get_output_info()[0]
+    feats = [f[0] for f in eng.features]
+    scale = {"traffic": lambda v: v * 0.5}
+    batches = list(NativeIngest.batches_parallel(eng, str(tmp_path), workers=3, label_name=out_name, feature_fns=scale))
+    assert [b.n_samples for b in batches] == [4, 4, 2]
+    for k, b in enumerate(batches):
+        pairs = [sample_to_tensors(s, feats, out_name, md.get_adjecency_info(), [], [], True) for s in samples[4 * k:4 * k + 4]]
+        want = assemble([p[0] for p in pairs], eng.entities, eng.features, eng.adjacencies, (), [p[1] for p in pairs])
+        for key in want.arrays:
+            ref = want.arrays[key] * np.float32(0.5) if key == "feat_traffic" else want.arrays[key]
+            assert np.array_equal(b.arrays[key], ref), key
