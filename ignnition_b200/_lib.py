@@ -60,6 +60,8 @@ SIGNATURES = {
     "ign_attention_aggregate": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "ign_partner_index": (_int, [_p, _p, _p, _i64, _p, _p]),
     "ign_ingest_create": (_p, [_int, _p, _int, _p, _p, _int, _p, _p, _p, _p, C.c_char_p]),
+    "ign_ingest_add_sequence": (_int, [_p, _int, _p, _int, C.c_char_p]),
+    "ign_ingest_sequence": (_i64, [_p, _int, _p, _p, _p]),
     "ign_ingest_destroy": (None, [_p]),
     "ign_ingest_reset": (None, [_p]),
     "ign_ingest_parse": (_i64, [_p, C.c_char_p, _sz, _i64]),

@@ -187,6 +187,17 @@ struct Feat {
   int entity;
   std::vector<float> v;
 };
+// a multi-source ordered / interleave message passing: which (source, column) of the reference's
+// concatenated padded tensor sits at sequence position p (batching.position_table)
+struct Seq {
+  std::vector<int> adjs;
+  bool interleave;
+  std::string pattern_key;           // sample key of the interleave pattern (list of entity type names)
+  std::vector<int32_t> off{0}, src, col;
+  std::vector<int> pattern;          // this sample's pattern as entity type indices
+  bool have_pattern = false;
+};
+constexpr int32_t BIG_COL = 1 << 30;   // "no such column" (batching.BIG_COL)
 
 }  // namespace
 
@@ -194,6 +205,7 @@ struct ign_ingest {
   std::vector<std::string> entity_names;
   std::vector<Feat> feats;
   std::vector<Adj> adjs;
+  std::vector<Seq> seqs;
   std::string label;
   bool has_label = false;
   std::vector<float> labels;
@@ -208,6 +220,7 @@ struct ign_ingest {
     for (auto& f : feats) f.v.clear();
     for (auto& a : adjs) { a.s.clear(); a.d.clear(); a.q.clear(); a.p.clear(); a.p_width = 0; }
     labels.clear();
+    for (auto& q : seqs) { q.off.assign(1, 0); q.src.clear(); q.col.clear(); }
     for (auto& o : offsets) o.assign(1, 0);
     n_samples = 0;
   }
@@ -332,6 +345,7 @@ struct ign_ingest {
     for (size_t i = 0; i < nf; ++i) f0[i] = feats[i].v.size();
     for (size_t i = 0; i < na; ++i) { a0[i] = adjs[i].s.size(); ap0[i] = adjs[i].p.size(); }
     const size_t l0 = labels.size();
+    for (auto& q : seqs) q.have_pattern = false;
     std::vector<char> f_seen(nf, 0), a_done(na, 0);
     std::vector<const char*> a_at(na, nullptr);
     bool have_entities = false, have_label = false;
@@ -376,6 +390,28 @@ struct ign_ingest {
             }
             used = true;
           }
+        for (size_t i = 0; i < seqs.size() && !used; ++i)
+          if (seqs[i].interleave && k == seqs[i].pattern_key) {
+            const char* at = sc.p;
+            for (size_t j = i; j < seqs.size(); ++j) {        // several message passings may share one definition
+              if (!seqs[j].interleave || seqs[j].pattern_key != k) continue;
+              Scan ps{at, sc.end};
+              seqs[j].pattern.clear();
+              ps.expect('[');
+              if (!ps.accept(']')) {
+                do {
+                  std::string_view ent = ps.str(arena);
+                  const int t = entity_index(ent);
+                  if (t < 0) throw Err{"IGNNITION: the interleave definition \"" + seqs[j].pattern_key + "\" names the unknown entity \"" + std::string(ent) + "\""};
+                  seqs[j].pattern.push_back(t);
+                } while (ps.accept(','));
+                ps.expect(']');
+              }
+              seqs[j].have_pattern = true;
+              sc.p = ps.p;
+            }
+            used = true;
+          }
         if (!used) sc.skip();
       } while (sc.accept(','));
       sc.expect('}');
@@ -391,6 +427,72 @@ struct ign_ingest {
       if (!a_at[i]) throw Err{"IGNNITION: A list for the adjecency vector named \"" + adjs[i].name + "\" was not found although being expected."};
       Scan s{a_at[i], sc.end};
       parse_adjacency(adjs[i], s);
+    }
+    // ---- position tables of the multi-source sequences (batching.position_table; interleave:
+    // generator_std_to_framework.py:193-219 + auxilary_classes.py:421-440)
+    for (auto& q : seqs) {
+      std::vector<int32_t> maxlen(q.adjs.size(), 0);
+      int64_t total = 0;
+      for (size_t k = 0; k < q.adjs.size(); ++k) {
+        const Adj& a = adjs[(size_t)q.adjs[k]];
+        int32_t m = 0;
+        for (size_t j = a0[(size_t)q.adjs[k]]; j < a.q.size(); ++j) m = a.q[j] + 1 > m ? a.q[j] + 1 : m;
+        maxlen[k] = m;
+        total += m;
+      }
+      const size_t base = q.src.size();
+      q.src.resize(base + (size_t)total, 0);
+      q.col.resize(base + (size_t)total, q.interleave ? BIG_COL : 0);
+      if (!q.interleave) {
+        size_t p = base;
+        for (size_t k = 0; k < q.adjs.size(); ++k)
+          for (int32_t c = 0; c < maxlen[k]; ++c, ++p) { q.src[p] = (int32_t)k; q.col[p] = c; }
+      } else {
+        if (!q.have_pattern) throw Err{"IGNNITION: the interleave definition \"" + q.pattern_key + "\" was not found although being expected."};
+        // ids of the pattern's entities in order of first appearance; n_total = sum of their longest lists
+        std::vector<int> ids;                     // entity type of id i
+        std::vector<int> numeric;
+        for (int t : q.pattern) {
+          size_t i = 0;
+          while (i < ids.size() && ids[i] != t) ++i;
+          if (i == ids.size()) ids.push_back(t);
+          numeric.push_back((int)i);
+        }
+        std::vector<int32_t> ent_max(ids.size(), -1);
+        for (size_t i = 0; i < ids.size(); ++i)
+          for (size_t k = 0; k < q.adjs.size(); ++k)
+            if (adjs[(size_t)q.adjs[k]].src == ids[i]) ent_max[i] = maxlen[k];
+        int64_t n_total = 0;
+        for (size_t i = 0; i < ids.size(); ++i) {
+          if (ent_max[i] < 0) throw Err{"IGNNITION: the interleave definition \"" + q.pattern_key + "\" names \"" + entity_names[(size_t)ids[i]] + "\", which sends no message here"};
+          n_total += ent_max[i];
+        }
+        // positions of entity i in the pattern tiled to n_total entries, then concatenated in source order
+        std::vector<std::vector<int32_t>> where(ids.size());
+        if (!numeric.empty())
+          for (int64_t p = 0; p < n_total; ++p) where[(size_t)numeric[(size_t)(p % (int64_t)numeric.size())]].push_back((int32_t)p);
+        size_t j = 0;
+        bool ok = true;
+        for (size_t k = 0; k < q.adjs.size() && ok; ++k) {
+          size_t i = 0;
+          while (i < ids.size() && ids[i] != adjs[(size_t)q.adjs[k]].src) ++i;
+          if (i == ids.size()) throw Err{"IGNNITION: the interleave definition \"" + q.pattern_key + "\" does not name \"" + entity_names[(size_t)adjs[(size_t)q.adjs[k]].src] + "\""};
+          // column c of source k's block (k-th block of the concatenation) moves to position where[i][c']
+          for (int32_t w : where[i]) {
+            if ((int64_t)j >= total) { ok = false; break; }
+            // j-th entry of the concatenated padded tensor: (source, column)
+            size_t kk = 0; int64_t jj = (int64_t)j;
+            while (kk < maxlen.size() && jj >= maxlen[kk]) { jj -= maxlen[kk]; ++kk; }
+            if (w >= total) { ok = false; break; }
+            q.src[base + (size_t)w] = (int32_t)kk;
+            q.col[base + (size_t)w] = (int32_t)jj;
+            ++j;
+          }
+        }
+        if (!ok || (int64_t)j != total)
+          throw Err{"IGNNITION: interleave indices (" + std::to_string(n_total) + ") do not match the padded length (" + std::to_string(total) + ")"};
+      }
+      q.off.push_back(q.off.back() + (int32_t)total);
     }
     for (size_t t = 0; t < entity_names.size(); ++t) {
       const int64_t total = offsets[t].back() + count[t];
@@ -434,6 +536,36 @@ extern "C" ign_ingest_t* ign_ingest_create(int n_entities, const char* const* en
   if (label_name) { g->label = label_name; g->has_label = true; }
   g->offsets.assign((size_t)n_entities, std::vector<int64_t>(1, 0));
   return g;
+}
+
+extern "C" int ign_ingest_add_sequence(ign_ingest_t* g, int n_adj, const int32_t* adj_indices, int interleave,
+                                       const char* pattern_key) {
+  if (!g || n_adj <= 0 || !adj_indices || (interleave && !pattern_key)) {
+    ign_set_error("IGNNITION: ingest_add_sequence: bad argument");
+    return IGN_ERR_INVALID;
+  }
+  Seq q;
+  for (int i = 0; i < n_adj; ++i) {
+    if (adj_indices[i] < 0 || adj_indices[i] >= (int)g->adjs.size()) {
+      ign_set_error("IGNNITION: ingest_add_sequence: unknown adjacency %d", adj_indices[i]);
+      return IGN_ERR_INVALID;
+    }
+    q.adjs.push_back(adj_indices[i]);
+  }
+  q.interleave = interleave != 0;
+  if (pattern_key) q.pattern_key = pattern_key;
+  g->seqs.push_back(std::move(q));
+  return (int)g->seqs.size() - 1;
+}
+
+extern "C" int64_t ign_ingest_sequence(const ign_ingest_t* g, int seq, const int32_t** pos_off, const int32_t** pos_src,
+                                       const int32_t** pos_col) {
+  if (!g || seq < 0 || seq >= (int)g->seqs.size()) return IGN_ERR_INVALID;
+  const Seq& q = g->seqs[(size_t)seq];
+  if (pos_off) *pos_off = q.off.data();
+  if (pos_src) *pos_src = q.src.data();
+  if (pos_col) *pos_col = q.col.data();
+  return (int64_t)q.src.size();
 }
 
 extern "C" void ign_ingest_destroy(ign_ingest_t* g) { delete g; }

@@ -5,8 +5,9 @@ Same result, array for array, as ``generator.sample_to_tensors`` on every sample
 ``code/utils/generator_std_to_framework.py:53-230``), without the per-edge Python loops: SURVEY.md
 section 8f rank 1.  The on-disk format is unchanged (``*.tar.gz`` holding ``data.json``).
 
-Models with an ``interleave`` aggregation keep the Python path (their position tables are built per
-sample from the pattern lists); ``NativeIngest.supported(engine)`` says which one applies.
+Multi-source ordered / concat / interleave message passings get their per-sample position tables
+(``batching.position_table``) from the same pass; an interleave needs the name of the sample key that
+holds its pattern (``interleave_names``: ``ModelDescription.get_interleave_tensors()``).
 """
 
 from __future__ import annotations
@@ -36,11 +37,11 @@ def _ints(values: Sequence[int]):
 class NativeIngest:
     """Parses dataset text into the batch arrays of one :class:`Engine`."""
 
-    def __init__(self, engine, label_name: Optional[str] = None):
-        if not self.supported(engine):
-            raise RuntimeError("IGNNITION: the native ingest does not build interleave position tables; "
-                               "use generator.sample_to_tensors + Engine.assemble for this model")
+    def __init__(self, engine, label_name: Optional[str] = None, interleave_names: Optional[Sequence] = None):
         self.lib = _lib.load()
+        if interleave_names is None and getattr(engine, "model", None) is not None:
+            interleave_names = engine.model.get_interleave_tensors()
+        pattern_of = {dst: name for name, dst in (interleave_names or [])}      # destination entity -> sample key
         self.entities = list(engine.entities)
         self.features = list(engine.features)            # (name, entity, size)
         self.adjacencies = list(engine.adjacencies)
@@ -56,10 +57,20 @@ class NativeIngest:
                                                  label_name.encode("utf-8") if label_name else None)
         if not self.handle:
             raise RuntimeError(_lib.last_error() or "IGNNITION: ingest_create failed")
+        self.sequences = list(engine.sequences)
+        a_index = {a.name: i for i, a in enumerate(self.adjacencies)}
+        for q in self.sequences:
+            if q.interleave and q.dst not in pattern_of:
+                raise RuntimeError("IGNNITION: no interleave definition was given for destination " + q.dst)
+            rc = self.lib.ign_ingest_add_sequence(self.handle, len(q.adjs), _ints([a_index[a.name] for a in q.adjs]),
+                                                  1 if q.interleave else 0,
+                                                  pattern_of[q.dst].encode("utf-8") if q.interleave else None)
+            if rc < 0:
+                raise RuntimeError(_lib.last_error() or "IGNNITION: ingest_add_sequence failed")
 
     @staticmethod
     def supported(engine) -> bool:
-        return not any(q.interleave for q in engine.sequences)
+        return True
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -117,6 +128,12 @@ class NativeIngest:
             b.max_seq[a.name] = int(seq.max()) + 1 if n else 0
             if a.uses_params:
                 b.arrays["params_" + a.name] = self._array(pp, n * w.value, C.c_float, np.float32).reshape(n, -1)
+        for i, q in enumerate(self.sequences):
+            po, ps, pc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            n = lib.ign_ingest_sequence(h, i, C.byref(po), C.byref(ps), C.byref(pc))
+            b.arrays["pos_off_" + q.key] = self._array(po, b.n_samples + 1, C.c_int32, np.int32)
+            b.arrays["pos_src_" + q.key] = self._array(ps, n, C.c_int32, np.int32)
+            b.arrays["pos_col_" + q.key] = self._array(pc, n, C.c_int32, np.int32)
         if self.label_name:
             ptr = C.c_void_p()
             n = lib.ign_ingest_labels(h, C.byref(ptr))
@@ -128,14 +145,15 @@ class NativeIngest:
 
     # ------------------------------------------------------------------ files
     @staticmethod
-    def batches_parallel(engine, directory: str, workers: int = 8, label_name: Optional[str] = None, **kw):
+    def batches_parallel(engine, directory: str, workers: int = 8, label_name: Optional[str] = None,
+                         interleave_names: Optional[Sequence] = None, **kw):
         """One batch per ``*.tar.gz`` of a directory, files parsed concurrently by ``workers`` threads (each
         with its own handle; zlib and the parser both run without the GIL).  Yields in file order."""
         from concurrent.futures import ThreadPoolExecutor
         paths = sorted(glob.glob(str(directory) + "/*.tar.gz"))
 
         def one(path):
-            ing = NativeIngest(engine, label_name)
+            ing = NativeIngest(engine, label_name, kw.pop("interleave_names", None) if False else interleave_names)
             with tarfile.open(path, "r:gz") as tar:
                 ing.parse(tar.extractfile("data.json").read())
             return ing.batch(**kw)

@@ -310,6 +310,15 @@ ign_ingest_t* ign_ingest_create(int n_entities, const char* const* entity_names,
                                 const char* const* feature_names, const int32_t* feature_entity, int n_adj,
                                 const char* const* adj_names, const int32_t* adj_src, const int32_t* adj_dst,
                                 const int32_t* adj_params, const char* label_name);
+/* A multi-source ordered / concat / interleave message passing (generate_model.py:496-543): registers the
+ * adjacencies that feed it, in source order; interleave = 1 reads the pattern (a list of entity type names)
+ * from the sample key pattern_key (generator_std_to_framework.py:193-219).  Returns the sequence id.
+ * ign_ingest_sequence gives, per sample (pos_off[n_samples + 1]), which (source, column) of the reference's
+ * concatenated padded tensor sits at sequence position p: the input of ign_steps_build. */
+int ign_ingest_add_sequence(ign_ingest_t* g, int n_adj, const int32_t* adj_indices, int interleave,
+                            const char* pattern_key);
+int64_t ign_ingest_sequence(const ign_ingest_t* g, int seq, const int32_t** pos_off, const int32_t** pos_src,
+                            const int32_t** pos_col);
 void ign_ingest_destroy(ign_ingest_t* g);
 void ign_ingest_reset(ign_ingest_t* g);
 int64_t ign_ingest_parse(ign_ingest_t* g, const char* json, size_t len, int64_t max_samples);

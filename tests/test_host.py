@@ -366,15 +366,22 @@ class _SpecEngine:
         from ignnition_b200.batching import AdjacencySpec
         self.entities = [e.name for e in md.get_entities()]
         self.features = [(f.name, e.name, f.size) for e in md.get_entities() for f in e.features]
+        from ignnition_b200.batching import SequenceSpec
+        self.model = md
         self.adjacencies, self.sequences = [], []
-        seen = set()
-        for _, mps in md.get_mp_instances():
-            for mp in mps:
+        by_name = {}
+        for si, (_, mps) in enumerate(md.get_mp_instances()):
+            for mi, mp in enumerate(mps):
                 for src in mp.source_entities:
-                    if src.adj_vector not in seen:
-                        seen.add(src.adj_vector)
+                    if src.adj_vector not in by_name:
                         uses = any(i == "edge_params" for op in src.message_formation for i in getattr(op, "input", []) or [])
-                        self.adjacencies.append(AdjacencySpec(src.adj_vector, src.name, mp.destination_entity, uses))
+                        by_name[src.adj_vector] = AdjacencySpec(src.adj_vector, src.name, mp.destination_entity, uses)
+                        self.adjacencies.append(by_name[src.adj_vector])
+                agg = mp.aggregation.type
+                if agg == "interleave" or (agg in ("ordered", "concat") and len(mp.source_entities) > 1):
+                    self.sequences.append(SequenceSpec("s%d_m%d" % (si, mi), mp.destination_entity,
+                                                       [by_name[s.adj_vector] for s in mp.source_entities],
+                                                       agg == "interleave"))
 
 
 @pytest.mark.parametrize("case", ["routenet_nsfnet", "routenet_geant2"])
@@ -474,3 +481,36 @@ def test_native_ingest_reads_dataset_files_in_parallel(tmp_path):
         for key in want.arrays:
             ref = want.arrays[key] * np.float32(0.5) if key == "feat_traffic" else want.arrays[key]
             assert np.array_equal(b.arrays[key], ref), key
+
+
+@pytest.mark.parametrize("interleave", [True, False])
+def test_native_ingest_position_tables_of_multi_source_sequences(interleave):
+    """Q-size (links + nodes -> paths, interleave) and the same model with an `ordered` two-source
+    aggregation: the per-sample position tables of batching.position_table, bit for bit."""
+    import copy
+    import json
+    from ignnition_b200 import synthetic
+    from ignnition_b200.batching import assemble
+    from ignnition_b200.generator import sample_dimensions, sample_to_tensors
+    from ignnition_b200.ingest import NativeIngest
+    from ignnition_b200.model_description import ModelDescription
+    g = load_golden("qsize_nsfnet")
+    mj = copy.deepcopy(g["model_json"])
+    if not interleave:
+        mj["message_passing"]["stages"][0]["stage_mp"][0]["aggregation"] = {"type": "ordered"}
+    samples = [synthetic.routenet_sample("nsfnet", s, s, qsize=True) for s in range(4)] + list((g.get("samples") or [])[:1])
+    md = ModelDescription(mj, sample_dimensions(samples[0]))
+    eng = _SpecEngine(md)
+    assert len(eng.sequences) == 1 and eng.sequences[0].interleave == interleave
+    out_name = md.get_output_info()[0]
+    feats = [f[0] for f in eng.features]
+    pairs = [sample_to_tensors(s, feats, out_name, md.get_adjecency_info(), md.get_interleave_tensors(), [], True)
+             for s in samples]
+    want = assemble([p[0] for p in pairs], eng.entities, eng.features, eng.adjacencies, eng.sequences, [p[1] for p in pairs])
+    ing = NativeIngest(eng, label_name=out_name)
+    assert ing.parse(json.dumps(samples)) == len(samples)
+    got = ing.batch()
+    assert set(got.arrays) == set(want.arrays)
+    for k in want.arrays:
+        assert got.arrays[k].dtype == want.arrays[k].dtype, k
+        assert np.array_equal(got.arrays[k], want.arrays[k]), k
