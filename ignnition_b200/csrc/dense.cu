@@ -354,6 +354,10 @@ extern "C" int ign_dense_head(const float* x, int64_t m, int k, const float* w, 
 }
 
 // dX = dZ W^T is a Dense layer with the transposed kernel: K' = n, N' = k
+// tensor-core weight gradient (dw_tc.cu)
+bool ign_dw_tc_supported(int k, int n);
+int ign_dw_tc_launch(const float* x, const float* dz, int64_t m, int k, int n, float* dw, cudaStream_t st);
+
 extern "C" size_t ign_dense_bwd_ws_bytes(int k, int n) {
   return (k > 0 && n > 0 && ign_dense_tc_supported(n, k)) ? ign_dense_tc_ws(n, k) : 0;
 }
@@ -381,7 +385,11 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
     gemm_kernel<false, true, 1><<<grid, GEMM_THREADS, 0, st>>>(dy, w, dx, m, k, n, nullptr, 0, nullptr, 0);
     IGN_CHECK_LAUNCH("dense_bwd_dx");
   }
-  if (dw) {   // dW[k,n] += X^T[k,m] dZ[m,n] : A = X stored [m,k] = [K',M'] with M'=k, K'=m
+  if (dw && ign_tensor_cores_enabled() && ign_dw_tc_supported(k, n) && m >= 4096) {
+    // tensor cores (3xTF32, MN-major operands, accumulators resident in TMEM): csrc/dw_tc.cu
+    int rc = ign_dw_tc_launch(x, dy, m, k, n, dw, st);
+    if (rc != IGN_OK) return rc;
+  } else if (dw) {   // dW[k,n] += X^T[k,m] dZ[m,n] : A = X stored [m,k] = [K',M'] with M'=k, K'=m
     int64_t splits = ign_cdiv(m, 4096);
     if (splits > 1024) splits = 1024;
     const int64_t per = ign_cdiv(ign_cdiv(m, splits), BK) * BK;

@@ -478,3 +478,43 @@ def test_init_state_and_gather_concat():
     p = rng.randn(250, 2).astype(np.float32)
     out = ops.gather_concat([dev(st), dev(p)], [dev(idx), None], 250).cpu().numpy()
     assert np.array_equal(out[:, :32], st[idx]) and np.array_equal(out[:, 32:], p)
+
+
+@pytest.mark.parametrize("m,k,n,act", [(5003, 32, 256, "selu"), (9001, 256, 256, "selu"), (4500, 64, 128, "tanh"),
+                                       (4096, 128, 64, "relu"), (6000, 256, 32, None), (777, 32, 256, "selu"),
+                                       (5000, 256, 1, None)])
+def test_dense_bwd(m, k, n, act):
+    """tf.gradients through Dense (generate_model.py:791): dX = dZ W^T, dW += X^T dZ, db += colsum(dZ),
+    dZ = dY * act'(pre).  m >= 4096 with 32-multiples runs dW on tcgen05 (MN-major operands, dw_tc.cu),
+    the rest on the fp32 kernels; both against fp64."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(m + k + n)
+    x = rng.randn(m, k).astype(np.float32)
+    w = (rng.randn(k, n) / np.sqrt(k)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, n).astype(np.float32)
+    dy = rng.randn(m, n).astype(np.float32)
+    pre = x.astype(np.float64) @ w.astype(np.float64) + b
+    a = ops.ACTIVATIONS[act]
+    if act == "selu":
+        s, al = 1.0507009873554805, 1.6732632423543772
+        d = np.where(pre > 0, s, s * al * np.exp(pre))
+    elif act == "tanh":
+        d = 1 - np.tanh(pre) ** 2
+    elif act == "relu":
+        d = (pre > 0).astype(np.float64)
+    else:
+        d = np.ones_like(pre)
+    dz = dy.astype(np.float64) * d
+    want_dx = dz @ w.astype(np.float64).T
+    want_dw = x.astype(np.float64).T @ dz
+    want_db = dz.sum(0)
+    dx = torch.empty(m, k, dtype=torch.float32, device="cuda")
+    dw = torch.zeros(k, n, dtype=torch.float32, device="cuda")
+    db = torch.zeros(n, dtype=torch.float32, device="cuda")
+    ops.dense_bwd(dev(x), dev(w), a, dev(pre.astype(np.float32)), dev(dy), dx, dw, db)
+    assert rel_err(dx.cpu().numpy(), want_dx) < RTOL
+    assert rel_err(dw.cpu().numpy(), want_dw) < RTOL
+    assert rel_err(db.cpu().numpy(), want_db) < RTOL
+    # gradients accumulate: a second call doubles dW and db
+    ops.dense_bwd(dev(x), dev(w), a, dev(pre.astype(np.float32)), dev(dy), dx, dw, db)
+    assert rel_err(dw.cpu().numpy(), 2 * want_dw) < RTOL
