@@ -456,3 +456,40 @@ extern "C" int ign_gru_seq_bwd(const int32_t* steps_rowptr, const int32_t* steps
   IGN_CHECK_LAUNCH("gru_seq_bwd");
   return IGN_OK;
 }
+
+// step-synchronous tensor-core variant (gru_step_bwd_tc.cu)
+size_t ign_gru_step_bwd_tc_ws(int64_t num_dst);
+int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int64_t num_dst, const int* meta,
+                               const int* steps_T, int n_src, const float* const* srcs, const float* h0,
+                               const float* h_seq, const float* kernel, const float* rkernel, const float* bias,
+                               const float* d_out, float* d_steps, float* dh0, float* dK, float* dR, float* dB,
+                               void* ws, cudaStream_t st);
+
+extern "C" size_t ign_gru_seq_bwd_steps_ws_bytes(int64_t num_dst) {
+  return num_dst >= 0 ? ign_gru_step_bwd_tc_ws(num_dst) : 0;
+}
+
+extern "C" int ign_gru_seq_bwd_steps(int max_steps, const int32_t* nt, const int32_t* off, const int32_t* meta,
+                                     const int32_t* steps_T, int n_src, const float* const* srcs, int f_in,
+                                     const float* h0, const float* h_seq, int64_t num_dst, int units,
+                                     const float* kernel, const float* recurrent_kernel, const float* bias,
+                                     const float* d_out, float* d_steps, float* dh0, float* d_kernel,
+                                     float* d_recurrent_kernel, float* d_bias, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  IGN_REQUIRE(num_dst >= 0 && max_steps >= 1 && max_steps <= 1024, IGN_ERR_INVALID,
+              "IGNNITION: gru_seq_bwd_steps: bad argument (1 <= max_steps <= 1024)");
+  IGN_REQUIRE(n_src >= 1 && n_src <= IGN_MAX_SOURCES && srcs, IGN_ERR_INVALID,
+              "IGNNITION: gru_seq_bwd_steps: bad sources");
+  IGN_REQUIRE(f_in == 32 && units == 32, IGN_ERR_UNSUPPORTED,
+              "IGNNITION: gru_seq_bwd_steps: built for 32-wide messages and states (got %d, %d)", f_in, units);
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(nt && off && meta && steps_T && h0 && h_seq && kernel && recurrent_kernel && bias && d_out && d_steps &&
+                  dh0 && d_kernel && d_recurrent_kernel && d_bias,
+              IGN_ERR_INVALID, "IGNNITION: gru_seq_bwd_steps: null pointer");
+  IGN_REQUIRE(ws && ws_bytes >= ign_gru_step_bwd_tc_ws(num_dst), IGN_ERR_WORKSPACE,
+              "IGNNITION: gru_seq_bwd_steps: workspace too small (%zu < %zu)", ws_bytes,
+              ign_gru_step_bwd_tc_ws(num_dst));
+  return ign_gru_step_bwd_tc_launch(max_steps, nt, off, num_dst, meta, steps_T, n_src, srcs, h0, h_seq, kernel,
+                                    recurrent_kernel, bias, d_out, d_steps, dh0, d_kernel, d_recurrent_kernel, d_bias,
+                                    ws, ign_stream(stream));
+}

@@ -1,0 +1,527 @@
+// Backward pass of the ordered / interleave aggregation on the tcgen05 tensor cores (sm_100a), 32-wide:
+// tf.gradients through keras.layers.RNN(GRUCell) over every destination's message sequence
+// (reference code/utils/generate_model.py:791 through auxilary_classes.py:767-796), organised like the
+// step-synchronous forward (gru_step_tc.cu): BPTT step t of ALL destinations that have a step t is one
+// streaming launch, t = max_len-1 .. 0.  Destinations are sorted by descending length, so the rows alive
+// at step t are the prefix [0, nt[t]) of the sorted order; the running dL/dh lives in a sorted-order
+// buffer dhs[num_dst, 32] between launches.
+//
+// Per 128-row tile (3xTF32 everywhere, fp32 accumulation in TMEM):
+//   GEMM1  P[128, 128] = [x_t | h_{t-1}] . [K ; R]       gate pre-activations z | r | xh | hh (as the forward)
+//   gates  -> gate gradients G = [d_az | d_ar | d_axh | d_ahh] and the direct term dh z, in registers;
+//          G goes to global memory (the weight-gradient kernel below reads it) and, split into hi / lo, into
+//          the A images of GEMM2 -- which are the x / h operand images of GEMM1, dead by then
+//   GEMM2  [dx | dh][128, 64] = G[128, 128] . W2[128, 64] with W2 = [K^T ; R^T] arranged to G's columns; the
+//          128 G columns are walked as 4 chunks of (8 units x 4 gates), each chunk issued as soon as the
+//          epilogue warps that own those units have stored it
+//   out    dx -> d_steps row, dh_{t-1} = dh z + dh part -> dhs (or dh0[d] at t = 0)
+// Roles: 8 producer warps (gather x_t rows by the step-major table, h_{t-1} rows from h_seq / h0: 8 lanes per
+// 128-byte row; next tile's rows are in registers while the current tile computes), 1 MMA-issuer warp,
+// 8 epilogue warps; mbarriers only.
+//
+// The weight gradients dK = sum x^T GX, dR = sum h^T GH, db = colsum(G) are a tall-skinny product over all
+// row-steps: gru_dw_tc_kernel runs it with MN-major operands and TMEM-resident accumulators (see dw_tc.cu
+// for the layout), gathering [x_t | h_{t-1}] again and reading G.
+
+#include "tc_common.cuh"
+
+using namespace ign_tc;
+
+namespace {
+
+constexpr int ROWS = 128;
+constexpr int U = 32;
+constexpr int IMG = ROWS * 128;           // bytes of one [128 x 32] fp32 image
+constexpr int W2IMG = 64 * 128;           // bytes of one [64 x 32] image
+constexpr int PROD_WARPS = 8;
+constexpr int EPI_WARPS = 8;
+constexpr int MMA_WARP = PROD_WARPS;
+constexpr int EPI_WARP0 = MMA_WARP + 1;
+constexpr int BW_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);    // 17 warps
+
+struct SrcPtrs {
+  const float* p[IGN_MAX_SOURCES];
+};
+__device__ __forceinline__ const float* pick_src(const SrcPtrs& s, int k) {
+  return k == 0 ? s.p[0] : k == 1 ? s.p[1] : k == 2 ? s.p[2] : s.p[3];
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
+    int t, const int* __restrict__ nt, const int* __restrict__ off, const int4* __restrict__ meta,
+    const int* __restrict__ steps_T, SrcPtrs srcs, const float* __restrict__ h0, const float* __restrict__ h_seq,
+    const float* __restrict__ d_out, float* __restrict__ dhs, float* __restrict__ dh0, float* __restrict__ d_steps,
+    float* __restrict__ g_out, const float* __restrict__ kernel, const float* __restrict__ rkernel,
+    const float* __restrict__ bias) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // forward gate weights, 128 rows each: Bx = [K_z | K_r | K_h | 0], Bh = [R_z | R_r | 0 | R_h]
+  unsigned char* bx_hi = smem;
+  unsigned char* bx_lo = bx_hi + IMG;
+  unsigned char* bh_hi = bx_lo + IMG;
+  unsigned char* bh_lo = bh_hi + IMG;
+  // W2 chunk q (units 8q .. 8q+7, column k = gate * 8 + jj): [hi 64 rows | lo 64 rows], rows 0-31 -> dx, 32-63 -> dh
+  unsigned char* w2 = bh_lo + IMG;
+  // operand stage: X_hi | X_lo | H_hi | H_lo; after GEMM1 (X_hi, X_lo) is G slot 0 and (H_hi, H_lo) G slot 1
+  unsigned char* stage = w2 + 8 * W2IMG;
+  __shared__ uint64_t bar_full, bar_acc1, bar_acc2, bar_d2free, bar_gfull[2], bar_gdone[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_gb[4 * U];                // merged gate biases [bz | br | bxh | bhh]
+  __shared__ int4 s_meta[2][ROWS];                           // per tile parity: (d, lo, len, alive)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bar_full, PROD_WARPS);
+    mbar_init(&bar_acc1, 1);
+    mbar_init(&bar_acc2, 1);
+    mbar_init(&bar_d2free, EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_gfull[s], EPI_WARPS / 2);
+      mbar_init(&bar_gdone[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, 256);
+  for (int i = tid; i < 4 * IMG / 16; i += BW_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int i = tid; i < U * 3 * U; i += BW_THREADS) {
+    const int k = i / (3 * U), n = i % (3 * U);
+    float hi, lo;
+    tf32_split(__ldg(kernel + i), hi, lo);                   // K column n -> Bx row n (n < 96)
+    *reinterpret_cast<float*>(bx_hi + sw128_off(n, k)) = hi;
+    *reinterpret_cast<float*>(bx_lo + sw128_off(n, k)) = lo;
+    tf32_split(__ldg(rkernel + i), hi, lo);                  // R column n -> Bh row n (z, r) or n + 32 (h)
+    const int nh = n < 2 * U ? n : n + U;
+    *reinterpret_cast<float*>(bh_hi + sw128_off(nh, k)) = hi;
+    *reinterpret_cast<float*>(bh_lo + sw128_off(nh, k)) = lo;
+  }
+  for (int i = tid; i < 4 * 64 * 32; i += BW_THREADS) {
+    const int q = i >> 11, n = (i >> 5) & 63, k = i & 31;
+    const int gate = k >> 3, u = 8 * q + (k & 7);
+    float v = 0.0f;
+    if (n < U) {                                             // dx_n = sum GX[c] K[n][c]
+      if (gate < 3) v = __ldg(kernel + n * 3 * U + gate * U + u);
+    } else {                                                 // dh_m = sum GH[c] R[m][c]
+      const int mrow = n - U;
+      if (gate < 2) v = __ldg(rkernel + mrow * 3 * U + gate * U + u);
+      else if (gate == 3) v = __ldg(rkernel + mrow * 3 * U + 2 * U + u);
+    }
+    float hi, lo;
+    tf32_split(v, hi, lo);
+    *reinterpret_cast<float*>(w2 + q * 2 * W2IMG + sw128_off(n, k)) = hi;
+    *reinterpret_cast<float*>(w2 + q * 2 * W2IMG + W2IMG + sw128_off(n, k)) = lo;
+  }
+  if (tid < U) {
+    s_gb[tid] = bias[tid] + bias[3 * U + tid];
+    s_gb[U + tid] = bias[U + tid] + bias[4 * U + tid];
+    s_gb[2 * U + tid] = bias[2 * U + tid];
+    s_gb[3 * U + tid] = bias[5 * U + tid];
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int64_t n_alive = (int64_t)__ldg(nt + t);
+  const int* entries = steps_T + __ldg(off + t);
+  const int64_t ntiles = (n_alive + ROWS - 1) / ROWS;
+  const int G = gridDim.x;
+  const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + G - 1) / G : 0;
+
+  if (warp < MMA_WARP) {
+    // ================================ producers ================================
+    const int ptid = tid;                                    // 0..255
+    const int c4 = ptid & 7;
+    for (int64_t j = 0; j < my_tiles; ++j) {
+      const int64_t tile = blockIdx.x + j * G;
+      int4 m[4];
+      int ent[4];
+      bool inb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                          // rows (ptid >> 3) + 32 k
+        const int64_t i = tile * ROWS + (ptid >> 3) + 32 * k;
+        inb[k] = i < n_alive;
+        m[k] = __ldg(meta + (inb[k] ? i : n_alive - 1));
+        ent[k] = __ldg(entries + (inb[k] ? i : 0));
+      }
+      float4 xv[4], hv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = inb[k] ? ent[k] : IGN_STEP_ZERO;
+        const float* hp = (t == 0) ? h0 + (int64_t)m[k].x * U : h_seq + (int64_t)(m[k].y + t - 1) * U;
+        const float* xp = e >= 0 ? pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U : srcs.p[0];
+        hv[k] = ldg_f4(hp + c4 * 4);
+        xv[k] = ldg_f4(xp + c4 * 4);
+        if (e < 0) xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!inb[k]) { hv[k] = make_float4(0.f, 0.f, 0.f, 0.f); m[k] = make_int4(-1, 0, 0, 0); }
+        m[k].w = inb[k] ? 1 : 0;
+      }
+      if (j > 0) mbar_wait(&bar_acc2, (uint32_t)(j - 1) & 1);     // GEMM2 of the previous tile has read its G images
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = (ptid >> 3) + 32 * k;
+        store_split(stage, stage + IMG, r, c4, xv[k]);
+        store_split(stage + 2 * IMG, stage + 3 * IMG, r, c4, hv[k]);
+        if (c4 == 0) s_meta[j & 1][r] = m[k];
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full);
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================ MMA issuer ================================
+    const uint32_t ax_hi = smem_u32(stage), ax_lo = ax_hi + IMG, ah_hi = ax_lo + IMG, ah_lo = ah_hi + IMG;
+    const uint32_t d1 = tmem_base, d2 = tmem_base + 128;
+    for (int64_t j = 0; j < my_tiles; ++j) {
+      mbar_wait(&bar_full, (uint32_t)j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        umma_chunk_3x(d1, ax_hi, ax_lo, smem_u32(bx_hi), smem_u32(bx_lo), 128, false);    // z | r | xh | 0
+        umma_chunk_3x(d1, ah_hi, ah_lo, smem_u32(bh_hi), smem_u32(bh_lo), 128, true);     // z | r | 0  | hh
+        umma_commit(&bar_acc1);
+      }
+      __syncwarp();
+      if (j > 0) mbar_wait(&bar_d2free, (uint32_t)(j - 1) & 1);   // the epilogue has read the previous [dx | dh]
+#pragma unroll 1
+      for (int n = 0; n < 4; ++n) {                          // chunk order 0, 2, 1, 3: the two halves alternate
+        const int slot = n & 1, c = n >> 1, q = slot * 2 + c;
+        mbar_wait(&bar_gfull[slot], (uint32_t)c);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t g_hi = slot ? ah_hi : ax_hi, g_lo = g_hi + IMG;
+          const uint32_t w_hi = smem_u32(w2 + q * 2 * W2IMG);
+          umma_chunk_3x(d2, g_hi, g_lo, w_hi, w_hi + W2IMG, 64, n > 0);
+          umma_commit(&bar_gdone[slot]);
+          if (n == 3) umma_commit(&bar_acc2);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int e = warp - EPI_WARP0;                          // 0..7
+    const int q = warp & 3;                                  // TMEM lane group this warp may access
+    const int half = e >> 2;                                 // units [16 half, 16 half + 16): G slot `half`
+    const int row = q * 32 + lane;
+    unsigned char* g_hi = stage + half * 2 * IMG;
+    unsigned char* g_lo = g_hi + IMG;
+    for (int64_t j = 0; j < my_tiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1;
+      const int64_t tile = blockIdx.x + j * G;
+      const int64_t i = tile * ROWS + row;
+      mbar_wait(&bar_full, ph);                              // s_meta of this tile is visible
+      const int4 mr = s_meta[j & 1][row];
+      const bool alive = mr.w != 0;
+      const float* dsrc = alive ? ((mr.z == t + 1) ? d_out + (int64_t)mr.x * U : dhs + i * U) : d_out;
+      const float* hsrc = alive ? ((t == 0) ? h0 + (int64_t)mr.x * U : h_seq + (int64_t)(mr.y + t - 1) * U) : h0;
+      float direct[16];
+      mbar_wait(&bar_acc1, ph);                              // gate pre-activations are in TMEM, x / h images free
+      tc_fence_after();
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int u0 = half * 16 + 8 * c;
+        uint32_t az[8], ar[8], axh[8], ahh[8];
+        tmem_ld8_nowait(tb + u0, az);
+        tmem_ld8_nowait(tb + 32 + u0, ar);
+        tmem_ld8_nowait(tb + 64 + u0, axh);
+        tmem_ld8_nowait(tb + 96 + u0, ahh);
+        const float4 d0 = ldg_f4(dsrc + u0), d1v = ldg_f4(dsrc + u0 + 4);
+        const float4 h0v = ldg_f4(hsrc + u0), h1v = ldg_f4(hsrc + u0 + 4);
+        const float dh[8] = {d0.x, d0.y, d0.z, d0.w, d1v.x, d1v.y, d1v.z, d1v.w};
+        const float hold[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+        tmem_ld_wait();
+        float gz[8], gr[8], gx[8], gh[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float z = fast_sigmoid(__uint_as_float(az[u]) + s_gb[u0 + u]);
+          const float r = fast_sigmoid(__uint_as_float(ar[u]) + s_gb[U + u0 + u]);
+          const float phh = __uint_as_float(ahh[u]) + s_gb[3 * U + u0 + u];
+          const float hh = fast_tanh(fmaf(r, phh, __uint_as_float(axh[u]) + s_gb[2 * U + u0 + u]));
+          const float dv = alive ? dh[u] : 0.0f;
+          const float t1 = dv * (1.0f - z);
+          gx[u] = t1 * (1.0f - hh * hh);
+          gh[u] = gx[u] * r;
+          gr[u] = gx[u] * phh * r * (1.0f - r);
+          gz[u] = dv * (hold[u] - hh) * z * (1.0f - z);
+          direct[8 * c + u] = dv * z;
+        }
+        if (alive) {                                         // G row for the weight-gradient kernel
+          float* gp = g_out + i * (4 * U) + u0;
+          st_f4(gp, make_float4(gz[0], gz[1], gz[2], gz[3]));
+          st_f4(gp + 4, make_float4(gz[4], gz[5], gz[6], gz[7]));
+          st_f4(gp + U, make_float4(gr[0], gr[1], gr[2], gr[3]));
+          st_f4(gp + U + 4, make_float4(gr[4], gr[5], gr[6], gr[7]));
+          st_f4(gp + 2 * U, make_float4(gx[0], gx[1], gx[2], gx[3]));
+          st_f4(gp + 2 * U + 4, make_float4(gx[4], gx[5], gx[6], gx[7]));
+          st_f4(gp + 3 * U, make_float4(gh[0], gh[1], gh[2], gh[3]));
+          st_f4(gp + 3 * U + 4, make_float4(gh[4], gh[5], gh[6], gh[7]));
+        }
+        // second chunk of this slot: the MMAs of the first one must have read it
+        if (c == 1) mbar_wait(&bar_gdone[half], 0);
+        store_split(g_hi, g_lo, row, 0, make_float4(gz[0], gz[1], gz[2], gz[3]));
+        store_split(g_hi, g_lo, row, 1, make_float4(gz[4], gz[5], gz[6], gz[7]));
+        store_split(g_hi, g_lo, row, 2, make_float4(gr[0], gr[1], gr[2], gr[3]));
+        store_split(g_hi, g_lo, row, 3, make_float4(gr[4], gr[5], gr[6], gr[7]));
+        store_split(g_hi, g_lo, row, 4, make_float4(gx[0], gx[1], gx[2], gx[3]));
+        store_split(g_hi, g_lo, row, 5, make_float4(gx[4], gx[5], gx[6], gx[7]));
+        store_split(g_hi, g_lo, row, 6, make_float4(gh[0], gh[1], gh[2], gh[3]));
+        store_split(g_hi, g_lo, row, 7, make_float4(gh[4], gh[5], gh[6], gh[7]));
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_gfull[half]);
+      }
+      mbar_wait(&bar_acc2, ph);                              // [dx | dh] of the tile is in TMEM
+      tc_fence_after();
+      uint32_t vx[16], vh[16];
+      tmem_ld16_nowait(tb + 128 + half * 16, vx);
+      tmem_ld16_nowait(tb + 128 + U + half * 16, vh);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_d2free);
+      if (alive) {
+        float* xp = d_steps + (int64_t)(mr.y + t) * U + half * 16;
+        float* hp = ((t == 0) ? dh0 + (int64_t)mr.x * U : dhs + i * U) + half * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+          st_f4(xp + k, make_float4(__uint_as_float(vx[k]), __uint_as_float(vx[k + 1]), __uint_as_float(vx[k + 2]),
+                                    __uint_as_float(vx[k + 3])));
+          st_f4(hp + k, make_float4(direct[k] + __uint_as_float(vh[k]), direct[k + 1] + __uint_as_float(vh[k + 1]),
+                                    direct[k + 2] + __uint_as_float(vh[k + 2]), direct[k + 3] + __uint_as_float(vh[k + 3])));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
+}
+
+// destinations without any step: the state passes through, so does its gradient
+__global__ void gru_bwd_passthrough_kernel(const int* __restrict__ nt, int64_t num_dst, const int4* __restrict__ meta,
+                                           const float* __restrict__ d_out, float* __restrict__ dh0) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)__ldg(nt) + (idx >> 3);
+  if (i >= num_dst) return;
+  const int d = __ldg(meta + i).x;
+  const int c4 = (int)(idx & 7);
+  st_f4(dh0 + (int64_t)d * U + c4 * 4, ldg_f4(d_out + (int64_t)d * U + c4 * 4));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradients of one step: D[128 lanes = x_hi | h_hi | x_lo | h_lo features][128 = G columns] accumulated
+// over the CTA's rows in TMEM (MN-major SWIZZLE_128B_BASE32B operands, see dw_tc.cu)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int R16 = 16;                    // rows per stage = 2 K-steps
+constexpr int DIMG = R16 * 128;            // bytes of one [16 x 32] image
+constexpr int DW_BLOCKS = 12;              // x_hi h_hi x_lo h_lo | G_hi[4] | G_lo[4]
+constexpr int DW_STAGE = DW_BLOCKS * DIMG;
+constexpr int DW_STAGES = 6;
+constexpr int DW_PROD_WARPS = 16;
+constexpr int DW_PROD_THREADS = 32 * DW_PROD_WARPS;
+constexpr int DW_THREADS = DW_PROD_THREADS + 32;
+
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                    // SWIZZLE_128B_BASE32B
+  return d;
+}
+__device__ __forceinline__ void store_split_mn(unsigned char* img_hi, unsigned char* img_lo, int r, int c4, float4 v) {
+  float4 hi, lo;
+  tf32_split(v.x, hi.x, lo.x);
+  tf32_split(v.y, hi.y, lo.y);
+  tf32_split(v.z, hi.z, lo.z);
+  tf32_split(v.w, hi.w, lo.w);
+  const int o = r * 128 + ((((c4 >> 1) ^ (r & 3)) << 5) | ((c4 & 1) << 4));
+  *reinterpret_cast<float4*>(img_hi + o) = hi;
+  *reinterpret_cast<float4*>(img_lo + o) = lo;
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
+    int t, const int* __restrict__ nt, const int* __restrict__ off, const int4* __restrict__ meta,
+    const int* __restrict__ steps_T, SrcPtrs srcs, const float* __restrict__ h0, const float* __restrict__ h_seq,
+    const float* __restrict__ g_in, float* __restrict__ dK, float* __restrict__ dR, float* __restrict__ dB) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full[DW_STAGES], bar_free[DW_STAGES], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(&bar_full[s], DW_PROD_WARPS);
+      mbar_init(&bar_free[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == DW_PROD_WARPS) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int64_t n_alive = (int64_t)__ldg(nt + t);
+  const int* entries = steps_T + __ldg(off + t);
+  const int64_t nchunks = (n_alive + R16 - 1) / R16;
+  const int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c0 = (int64_t)blockIdx.x * per;
+  const int64_t c1 = c0 + per < nchunks ? c0 + per : nchunks;
+  const int64_t n_my = c1 > c0 ? c1 - c0 : 0;
+
+  if (warp < DW_PROD_WARPS) {
+    // threads 0..255: one float4 of [x | h] (row tid / 16, chunk tid % 16) and one of G (row 8 + tid / 32);
+    // threads 256..511: one float4 of G (row (tid - 256) / 32).  Every thread's G chunk is column tid % 32.
+    const bool has_a = tid < 256;
+    const int ra = tid >> 4, wa = tid & 15;
+    const int rg = has_a ? 8 + (tid >> 5) : (tid - 256) >> 5, wg = tid & 31;
+    float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    // row pointer of the [x | h] float4 this thread loads for a chunk (nullptr = zeros)
+    auto a_ptr = [&](int64_t chunk) -> const float* {
+      const int64_t i = chunk * R16 + ra;
+      if (!has_a || i >= n_alive) return nullptr;
+      if (wa < 8) {
+        const int e = __ldg(entries + i);
+        return e >= 0 ? pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U + wa * 4 : nullptr;
+      }
+      const int4 m = __ldg(meta + i);
+      return ((t == 0) ? h0 + (int64_t)m.x * U : h_seq + (int64_t)(m.y + t - 1) * U) + (wa - 8) * 4;
+    };
+    auto load = [&](int64_t chunk, const float* ap, float4& va, float4& vg) {
+      va = ap ? ldg_f4(ap) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t i = chunk * R16 + rg;
+      vg = i < n_alive ? ld_stream_f4(g_in + i * 128 + wg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 ca, cg, na = make_float4(0.f, 0.f, 0.f, 0.f), ng = na;
+    const float* p_next = nullptr;
+    if (n_my > 0) {
+      load(c0, a_ptr(c0), ca, cg);
+      if (n_my > 1) p_next = a_ptr(c0 + 1);
+    }
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int s = (int)(i % DW_STAGES);
+      if (i + 1 < n_my) load(c0 + i + 1, p_next, na, ng);
+      if (i + 2 < n_my) p_next = a_ptr(c0 + i + 2);
+      if (i >= DW_STAGES) mbar_wait(&bar_free[s], (uint32_t)((i / DW_STAGES) - 1) & 1);
+      unsigned char* st = smem + (size_t)s * DW_STAGE;
+      if (has_a) {                                           // blocks: x_hi 0, h_hi 1, x_lo 2, h_lo 3
+        unsigned char* hi = st + (wa >> 3) * DIMG;
+        store_split_mn(hi, hi + 2 * DIMG, ra, wa & 7, ca);
+      }
+      {
+        unsigned char* hi = st + (4 + (wg >> 3)) * DIMG;
+        store_split_mn(hi, hi + 4 * DIMG, rg, wg & 7, cg);
+        colsum.x += cg.x; colsum.y += cg.y; colsum.z += cg.z; colsum.w += cg.w;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[s]);
+      ca = na; cg = ng;
+    }
+    if (n_my > 0) {
+      // bias gradients: G column c -> db[0][c] for z, r, xh (c < 96); db[1][c] for z, r and db[1][c - 32] for hh
+      const float cs[4] = {colsum.x, colsum.y, colsum.z, colsum.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = wg * 4 + k;
+        if (c < 3 * U) atomicAdd(dB + c, cs[k]);
+        if (c < 2 * U) atomicAdd(dB + 3 * U + c, cs[k]);
+        if (c >= 3 * U) atomicAdd(dB + 3 * U + c - U, cs[k]);
+      }
+      mbar_wait(&bar_done, 0);
+      tc_fence_after();
+      const int lg = warp & 3, gate = warp >> 2;             // lanes: x_hi | h_hi | x_lo | h_lo; columns: one gate
+      const bool is_h = lg & 1;
+      // x rows take z, r, xh (gates 0-2); h rows take z, r (0, 1) and hh (3) -> recurrent column block 2
+      const bool used = is_h ? gate != 2 : gate != 3;
+      if (used) {
+        float* base = (is_h ? dR : dK) + lane * 3 * U + (gate == 3 ? 2 : gate) * U;
+#pragma unroll 1
+        for (int cb = 0; cb < U; cb += 8) {
+          uint32_t v[8];
+          tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + gate * U + cb, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) atomicAdd(base + cb + k, __uint_as_float(v[k]));
+        }
+      }
+    }
+  } else {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int s = (int)(i % DW_STAGES);
+      mbar_wait(&bar_full[s], (uint32_t)(i / DW_STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * DW_STAGE);
+        const uint32_t b_hi = st + 4 * DIMG, b_lo = b_hi + 4 * DIMG;
+#pragma unroll
+        for (int ks = 0; ks < R16 / 8; ++ks) {
+          const uint32_t ko = ks * 1024;
+          umma_tf32(tmem_base, umma_desc_mn(st + ko, DIMG), umma_desc_mn(b_hi + ko, DIMG), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, umma_desc_mn(st + ko, DIMG), umma_desc_mn(b_lo + ko, DIMG), idesc, 1u);
+        }
+        umma_commit(&bar_free[s]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && n_my > 0) umma_commit(&bar_done);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == DW_PROD_WARPS) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+size_t ign_gru_step_bwd_tc_ws(int64_t num_dst) {
+  return ign_align((size_t)(num_dst > 0 ? num_dst : 1) * 4 * U * sizeof(float)) +      // G rows of one step
+         ign_align((size_t)(num_dst > 0 ? num_dst : 1) * U * sizeof(float));           // running dL/dh
+}
+
+int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int64_t num_dst, const int* meta,
+                               const int* steps_T, int n_src, const float* const* srcs, const float* h0,
+                               const float* h_seq, const float* kernel, const float* rkernel, const float* bias,
+                               const float* d_out, float* d_steps, float* dh0, float* dK, float* dR, float* dB,
+                               void* ws, cudaStream_t st) {
+  SrcPtrs sp;
+  for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
+  float* g_rows = reinterpret_cast<float*>(ws);
+  float* dhs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ign_align((size_t)num_dst * 4 * U * sizeof(float)));
+  const size_t smem_a = 1024 + 4 * (size_t)IMG + 8 * (size_t)W2IMG + 4 * (size_t)IMG;
+  const size_t smem_w = 1024 + (size_t)DW_STAGES * DW_STAGE;
+  static thread_local bool configured = false;
+  if (!configured) {
+    IGN_CUDA(cudaFuncSetAttribute(gru_step_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    IGN_CUDA(cudaFuncSetAttribute(gru_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+    configured = true;
+  }
+  int sms = IGN_NUM_SMS, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ign_cdiv(num_dst, ROWS);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  const int4* meta4 = reinterpret_cast<const int4*>(meta);
+  gru_bwd_passthrough_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(nt, num_dst, meta4, d_out, dh0);
+  IGN_CHECK_LAUNCH("gru_bwd_passthrough");
+  // enough 16-row chunks per CTA that the atomic flush of the accumulators stays small
+  int64_t grid_w = ign_cdiv(ign_cdiv(num_dst, R16), 32);
+  if (grid_w > sms) grid_w = sms;
+  if (grid_w < 1) grid_w = 1;
+  for (int t = max_steps - 1; t >= 0; --t) {
+    gru_step_bwd_tc_kernel<<<grid, BW_THREADS, smem_a, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, d_out, dhs, dh0,
+                                                              d_steps, g_rows, kernel, rkernel, bias);
+    IGN_CHECK_LAUNCH("gru_step_bwd_tc");
+    gru_dw_tc_kernel<<<(unsigned)grid_w, DW_THREADS, smem_w, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, g_rows, dK,
+                                                                    dR, dB);
+    IGN_CHECK_LAUNCH("gru_dw_tc");
+  }
+  return IGN_OK;
+}

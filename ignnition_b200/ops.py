@@ -332,6 +332,21 @@ def gru_seq_bwd(steps_rowptr, steps, order, srcs, h0, h_seq, kernel, rkernel, bi
                "gru_seq_bwd")
 
 
+def gru_seq_bwd_steps(plan, meta, max_steps: int, srcs, h0, h_seq, kernel, rkernel, bias, d_out, d_steps, dh0,
+                      dk, drk, db):
+    """BPTT of an ordered update as step-synchronous tensor-core launches (ign_gru_seq_bwd_steps)."""
+    lib = _lib.load()
+    nt, off, steps_t = plan
+    n, units = h0.shape
+    sp = _ptr_array(srcs, torch.float32)
+    nbytes = lib.ign_gru_seq_bwd_steps_ws_bytes(n)
+    ws = _workspace(nbytes, h0.device)
+    _lib.check(lib.ign_gru_seq_bwd_steps(max_steps, _i(nt), _i(off), _i(meta), _i(steps_t), len(srcs), sp,
+                                         srcs[0].shape[1], _f(h0), _f(h_seq), n, units, _f(kernel), _f(rkernel),
+                                         _f(bias), _f(d_out), _f(d_steps), _f(dh0), _f(dk), _f(drk), _f(db),
+                                         ws.data_ptr(), ws.numel(), _stream()), "gru_seq_bwd_steps")
+
+
 def l2_reg(w, lam: float, dw, reg):
     lib = _lib.load()
     _lib.check(lib.ign_l2_reg(_f(w), w.numel(), lam, _f(dw), _ptr(reg, torch.float64, "reg"), _stream()),

@@ -251,6 +251,21 @@ int ign_gru_seq_bwd(const int32_t* steps_rowptr, const int32_t* steps, const int
                     float* d_steps, float* dh0, float* d_kernel, float* d_recurrent_kernel,
                     float* d_bias, void* stream);
 
+/* Step-synchronous form of ign_gru_seq_bwd on the tcgen05 tensor cores (3xTF32; 32-wide messages and
+ * states): BPTT step t of every destination that has one is a pair of launches (gate recomputation +
+ * [dx | dh] GEMM; weight-gradient GEMM with TMEM-resident accumulators), t = max_steps-1 .. 0.  Needs the
+ * plan of ign_seq_step_plan over destinations sorted by descending length (nt, off, steps_T, meta; see
+ * ign_gru_seq_step) and h_seq of the forward call.  Same outputs as ign_gru_seq_bwd; weight gradients are
+ * ACCUMULATED.  ws: ign_gru_seq_bwd_steps_ws_bytes(num_dst) bytes. */
+size_t ign_gru_seq_bwd_steps_ws_bytes(int64_t num_dst);
+int ign_gru_seq_bwd_steps(int max_steps, const int32_t* nt, const int32_t* off, const int32_t* meta,
+                          const int32_t* steps_T, int n_src, const float* const* srcs, int f_in,
+                          const float* h0, const float* h_seq, int64_t num_dst, int units,
+                          const float* kernel, const float* recurrent_kernel, const float* bias,
+                          const float* d_out, float* d_steps, float* dh0, float* d_kernel,
+                          float* d_recurrent_kernel, float* d_bias, void* ws, size_t ws_bytes,
+                          void* stream);
+
 /* l2 regulariser: reg[0] += lambda * sum(w^2) (fp64), dw += 2 lambda w (auxilary_classes.py:834). */
 int ign_l2_reg(const float* w, int64_t n, float lambda, float* dw, double* reg, void* stream);
 

@@ -518,3 +518,77 @@ def test_dense_bwd(m, k, n, act):
     # gradients accumulate: a second call doubles dW and db
     ops.dense_bwd(dev(x), dev(w), a, dev(pre.astype(np.float32)), dev(dy), dx, dw, db)
     assert rel_err(dw.cpu().numpy(), 2 * want_dw) < RTOL
+
+
+@pytest.mark.parametrize("max_len,n_dst", [(1, 700), (6, 3000), (16, 1000)])
+def test_gru_seq_bwd_step_synchronous(max_len, n_dst):
+    """BPTT as step-synchronous tcgen05 launches (ign_gru_seq_bwd_steps) == torch.autograd in fp64 through the
+    oracle's GRU recurrence, and == the fp32 tile-walk kernel (ign_gru_seq_bwd): message gradients per step,
+    initial-state gradients (incl. destinations without steps), kernel / recurrent kernel / bias gradients;
+    two sources and zero-message entries in the step table."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(max_len + n_dst)
+    n_src, u = 400, 32
+    lens = rng.randint(0, max_len + 1, n_dst)
+    lens[:5] = max_len
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n_steps = int(rowptr[-1])
+    which = rng.randint(0, 2, n_steps)
+    rows = rng.randint(0, n_src, n_steps)
+    steps = ((which << ops.STEP_SRC_SHIFT) | rows).astype(np.int32)
+    steps[rng.rand(n_steps) < 0.05] = -1
+    s0 = (rng.randn(n_src, u) * 0.5).astype(np.float32)
+    s1 = (rng.randn(n_src, u) * 0.5).astype(np.float32)
+    h0 = (rng.randn(n_dst, u) * 0.7).astype(np.float32)
+    d_out = rng.randn(n_dst, u).astype(np.float32)
+    K, R, b = gru_weights(rng, u, u)
+
+    # fp64 autograd through h <- GRU(x_t, h) (Keras GRUCell v2, reset_after=True)
+    tK, tR, tb = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (K, R, b)]
+    th0 = torch.tensor(h0, dtype=torch.float64, requires_grad=True)
+    src_all = torch.tensor(np.concatenate([s0, s1, np.zeros((1, u), np.float32)]), dtype=torch.float64)
+    idx = np.where(steps >= 0, (steps >> ops.STEP_SRC_SHIFT) * n_src + (steps & ((1 << ops.STEP_SRC_SHIFT) - 1)), 2 * n_src)
+    x_all = src_all[torch.from_numpy(idx)].clone().requires_grad_(True)
+    h = th0
+    lens_t = torch.from_numpy(lens)
+    rp_t = torch.from_numpy(rowptr[:-1].astype(np.int64))
+    for t in range(max_len):
+        act = lens_t > t
+        pos = (rp_t + t)[act]
+        x = x_all[pos]
+        hp = h[act]
+        mx = x @ tK + tb[0]
+        mh = hp @ tR + tb[1]
+        z = torch.sigmoid(mx[:, :u] + mh[:, :u])
+        r = torch.sigmoid(mx[:, u:2 * u] + mh[:, u:2 * u])
+        hh = torch.tanh(mx[:, 2 * u:] + r * mh[:, 2 * u:])
+        hn = z * hp + (1 - z) * hh
+        h = h.clone()
+        h[act] = hn
+    (h * torch.tensor(d_out, dtype=torch.float64)).sum().backward()
+
+    rp, st = dev(rowptr), dev(steps)
+    order = ops.length_order(rp)
+    meta = ops.seq_meta(rp, st, order)
+    plan = ops.seq_step_plan(meta, st, max_len)
+    srcs = [dev(s0), dev(s1)]
+    h_seq = torch.zeros(max(n_steps, 1), u, device="cuda")
+    ops.gru_seq(rp, st, order, srcs, dev(h0), dev(K), dev(R), dev(b), h_seq=h_seq, meta=meta)
+
+    def run(tc):
+        d_steps = torch.zeros(max(n_steps, 1), u, device="cuda")
+        dh0 = torch.zeros(n_dst, u, device="cuda")
+        dk, dr, db = torch.zeros(u, 3 * u, device="cuda"), torch.zeros(u, 3 * u, device="cuda"), torch.zeros(2, 3 * u, device="cuda")
+        if tc:
+            ops.gru_seq_bwd_steps(plan, meta, max_len, srcs, dev(h0), h_seq, dev(K), dev(R), dev(b), dev(d_out),
+                                  d_steps, dh0, dk, dr, db)
+        else:
+            ops.gru_seq_bwd(rp, st, order, srcs, dev(h0), h_seq, dev(K), dev(R), dev(b), dev(d_out), d_steps, dh0,
+                            dk, dr, db)
+        return [a.cpu().numpy() for a in (d_steps[:n_steps], dh0, dk, dr, db)]
+
+    want = [x_all.grad.numpy(), th0.grad.numpy(), tK.grad.numpy(), tR.grad.numpy(), tb.grad.numpy()]
+    for tc in (False, True):
+        got = run(tc)
+        for name, g, w in zip(("d_steps", "dh0", "dK", "dR", "db"), got, want):
+            assert rel_err(g, w) < 2e-5, (tc, name, rel_err(g, w))
