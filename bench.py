@@ -442,7 +442,7 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
                      ("mlp_head", b_mlp_head), ("dense_head", b_dense_head), ("init_state", b_init),
                      ("length_order", zero), ("seq_meta", zero), ("steps_build", zero),
                      ("gru_seq_steps", zero), ("seq_step_plan", zero),
-                     ("gru_seq_bwd", zero), ("gru_cell_bwd", zero), ("dense_bwd", zero)):
+                     ("gru_seq_bwd", zero), ("gru_seq_bwd_steps", zero), ("gru_cell_bwd", zero), ("dense_bwd", zero)):
         wrap(name, fn)
     try:
         for _ in range(max(1, min(reps, 3))):

@@ -15,7 +15,7 @@
 //          128 G columns are walked as 4 chunks of (8 units x 4 gates), each chunk issued as soon as the
 //          epilogue warps that own those units have stored it
 //   out    dx -> d_steps row, dh_{t-1} = dh z + dh part -> dhs (or dh0[d] at t = 0)
-// Roles: 8 producer warps (gather x_t rows by the step-major table, h_{t-1} rows from h_seq / h0: 8 lanes per
+// Roles: 4 producer warps (gather x_t rows by the step-major table, h_{t-1} rows from h_seq / h0: 8 lanes per
 // 128-byte row; next tile's rows are in registers while the current tile computes), 1 MMA-issuer warp,
 // 8 epilogue warps; mbarriers only.
 //
@@ -33,11 +33,12 @@ constexpr int ROWS = 128;
 constexpr int U = 32;
 constexpr int IMG = ROWS * 128;           // bytes of one [128 x 32] fp32 image
 constexpr int W2IMG = 64 * 128;           // bytes of one [64 x 32] image
-constexpr int PROD_WARPS = 8;
+constexpr int PROD_WARPS = 4;
 constexpr int EPI_WARPS = 8;
-constexpr int MMA_WARP = PROD_WARPS;
-constexpr int EPI_WARP0 = MMA_WARP + 1;
-constexpr int BW_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);    // 17 warps
+constexpr int EPI_WARP0 = PROD_WARPS;                       // warps 4..11: TMEM lane groups 0..3 twice
+constexpr int MMA1_WARP = EPI_WARP0 + EPI_WARPS;
+constexpr int MMA2_WARP = MMA1_WARP + 1;
+constexpr int BW_THREADS = 32 * (MMA2_WARP + 1);            // 14 warps
 
 struct SrcPtrs {
   const float* p[IGN_MAX_SOURCES];
@@ -61,27 +62,28 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
   unsigned char* bh_lo = bh_hi + IMG;
   // W2 chunk q (units 8q .. 8q+7, column k = gate * 8 + jj): [hi 64 rows | lo 64 rows], rows 0-31 -> dx, 32-63 -> dh
   unsigned char* w2 = bh_lo + IMG;
-  // operand stage: X_hi | X_lo | H_hi | H_lo; after GEMM1 (X_hi, X_lo) is G slot 0 and (H_hi, H_lo) G slot 1
-  unsigned char* stage = w2 + 8 * W2IMG;
-  __shared__ uint64_t bar_full, bar_acc1, bar_acc2, bar_d2free, bar_gfull[2], bar_gdone[2];
+  unsigned char* stage = w2 + 8 * W2IMG;                     // X_hi | X_lo | H_hi | H_lo of the tile in GEMM1
+  unsigned char* gslot = stage + 4 * IMG;                    // G_hi | G_lo of the chunk in GEMM2
+  __shared__ uint64_t bar_full, bar_acc1[2], bar_a1free[2], bar_gfull, bar_gdone[2], bar_acc2, bar_d2free;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_gb[4 * U];                // merged gate biases [bz | br | bxh | bhh]
-  __shared__ int4 s_meta[2][ROWS];                           // per tile parity: (d, lo, len, alive)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(&bar_full, PROD_WARPS);
-    mbar_init(&bar_acc1, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_acc1[s], 1);
+      mbar_init(&bar_a1free[s], EPI_WARPS);
+    }
+    mbar_init(&bar_gfull, EPI_WARPS / 2);
+    mbar_init(&bar_gdone[0], 1);
+    mbar_init(&bar_gdone[1], 1);
     mbar_init(&bar_acc2, 1);
     mbar_init(&bar_d2free, EPI_WARPS);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_gfull[s], EPI_WARPS / 2);
-      mbar_init(&bar_gdone[s], 1);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, 256);
+  if (warp == MMA1_WARP) tmem_alloc(&tmem_base_s, 512);
   for (int i = tid; i < 4 * IMG / 16; i += BW_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   for (int i = tid; i < U * 3 * U; i += BW_THREADS) {
@@ -129,70 +131,76 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
   const int G = gridDim.x;
   const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + G - 1) / G : 0;
 
-  if (warp < MMA_WARP) {
+  if (warp < PROD_WARPS) {
     // ================================ producers ================================
-    const int ptid = tid;                                    // 0..255
+    const int ptid = tid;                                    // 0..127
     const int c4 = ptid & 7;
     for (int64_t j = 0; j < my_tiles; ++j) {
       const int64_t tile = blockIdx.x + j * G;
-      int4 m[4];
-      int ent[4];
-      bool inb[4];
+      int4 m[8];
+      int ent[8];
+      bool inb[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {                          // rows (ptid >> 3) + 32 k
-        const int64_t i = tile * ROWS + (ptid >> 3) + 32 * k;
+      for (int k = 0; k < 8; ++k) {                          // rows (ptid >> 3) + 16 k
+        const int64_t i = tile * ROWS + (ptid >> 3) + 16 * k;
         inb[k] = i < n_alive;
         m[k] = __ldg(meta + (inb[k] ? i : n_alive - 1));
         ent[k] = __ldg(entries + (inb[k] ? i : 0));
       }
-      float4 xv[4], hv[4];
+      float4 xv[8], hv[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         const int e = inb[k] ? ent[k] : IGN_STEP_ZERO;
         const float* hp = (t == 0) ? h0 + (int64_t)m[k].x * U : h_seq + (int64_t)(m[k].y + t - 1) * U;
         const float* xp = e >= 0 ? pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U : srcs.p[0];
         hv[k] = ldg_f4(hp + c4 * 4);
         xv[k] = ldg_f4(xp + c4 * 4);
         if (e < 0) xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!inb[k]) { hv[k] = make_float4(0.f, 0.f, 0.f, 0.f); m[k] = make_int4(-1, 0, 0, 0); }
-        m[k].w = inb[k] ? 1 : 0;
+        if (!inb[k]) hv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (j > 0) mbar_wait(&bar_acc2, (uint32_t)(j - 1) & 1);     // GEMM2 of the previous tile has read its G images
+      // GEMM1 of the previous tile has read the stage
+      if (j > 0) mbar_wait(&bar_acc1[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = (ptid >> 3) + 32 * k;
+      for (int k = 0; k < 8; ++k) {
+        const int r = (ptid >> 3) + 16 * k;
         store_split(stage, stage + IMG, r, c4, xv[k]);
         store_split(stage + 2 * IMG, stage + 3 * IMG, r, c4, hv[k]);
-        if (c4 == 0) s_meta[j & 1][r] = m[k];
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full);
     }
-  } else if (warp == MMA_WARP) {
-    // ================================ MMA issuer ================================
+  } else if (warp == MMA1_WARP) {
+    // ================================ issuer of GEMM1 ================================
     const uint32_t ax_hi = smem_u32(stage), ax_lo = ax_hi + IMG, ah_hi = ax_lo + IMG, ah_lo = ah_hi + IMG;
-    const uint32_t d1 = tmem_base, d2 = tmem_base + 128;
     for (int64_t j = 0; j < my_tiles; ++j) {
+      const int buf = (int)(j & 1);
       mbar_wait(&bar_full, (uint32_t)j & 1);
+      if (j >= 2) mbar_wait(&bar_a1free[buf], (uint32_t)((j >> 1) - 1) & 1);   // epilogue of tile j - 2 has read it
       tc_fence_after();
       if (lane == 0) {
+        const uint32_t d1 = tmem_base + buf * 128;
         umma_chunk_3x(d1, ax_hi, ax_lo, smem_u32(bx_hi), smem_u32(bx_lo), 128, false);    // z | r | xh | 0
         umma_chunk_3x(d1, ah_hi, ah_lo, smem_u32(bh_hi), smem_u32(bh_lo), 128, true);     // z | r | 0  | hh
-        umma_commit(&bar_acc1);
+        umma_commit(&bar_acc1[buf]);
       }
       __syncwarp();
-      if (j > 0) mbar_wait(&bar_d2free, (uint32_t)(j - 1) & 1);   // the epilogue has read the previous [dx | dh]
+    }
+  } else if (warp == MMA2_WARP) {
+    // ================================ issuer of GEMM2 ================================
+    const uint32_t g_hi = smem_u32(gslot), g_lo = g_hi + IMG;
+    const uint32_t d2 = tmem_base + 256;
+    for (int64_t j = 0; j < my_tiles; ++j) {
 #pragma unroll 1
-      for (int n = 0; n < 4; ++n) {                          // chunk order 0, 2, 1, 3: the two halves alternate
-        const int slot = n & 1, c = n >> 1, q = slot * 2 + c;
-        mbar_wait(&bar_gfull[slot], (uint32_t)c);
+      for (int n = 0; n < 4; ++n) {                          // fills alternate between the two halves of the units
+        const int q = (n & 1) * 2 + (n >> 1);
+        mbar_wait(&bar_gfull, (uint32_t)n & 1);
+        if (n == 0 && j > 0) mbar_wait(&bar_d2free, (uint32_t)(j - 1) & 1);   // previous [dx | dh] has been read
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t g_hi = slot ? ah_hi : ax_hi, g_lo = g_hi + IMG;
           const uint32_t w_hi = smem_u32(w2 + q * 2 * W2IMG);
           umma_chunk_3x(d2, g_hi, g_lo, w_hi, w_hi + W2IMG, 64, n > 0);
-          umma_commit(&bar_gdone[slot]);
+          umma_commit(&bar_gdone[n & 1]);                   // one barrier per half: see the epilogue's wait
           if (n == 3) umma_commit(&bar_acc2);
         }
         __syncwarp();
@@ -202,36 +210,62 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     // ================================ epilogue ================================
     const int e = warp - EPI_WARP0;                          // 0..7
     const int q = warp & 3;                                  // TMEM lane group this warp may access
-    const int half = e >> 2;                                 // units [16 half, 16 half + 16): G slot `half`
+    const int half = e >> 2;                                 // units [16 half, 16 half + 16)
     const int row = q * 32 + lane;
-    unsigned char* g_hi = stage + half * 2 * IMG;
-    unsigned char* g_lo = g_hi + IMG;
+    unsigned char* g_hi = gslot;
+    unsigned char* g_lo = gslot + IMG;
+    // (dL/dh, h_{t-1}) of this thread's 16 units, prefetched one tile ahead
+    float4 pre_d[4], pre_h[4];
+    int4 mr_next = make_int4(-1, 0, 0, 0);
+    auto fetch_meta = [&](int64_t j) {
+      const int64_t i = (blockIdx.x + j * G) * ROWS + row;
+      mr_next = (j < my_tiles && i < n_alive) ? __ldg(meta + i) : make_int4(-1, 0, 0, 0);
+    };
+    auto fetch_rows = [&](int64_t j) {
+      if (mr_next.x < 0) return;
+      const int64_t i = (blockIdx.x + j * G) * ROWS + row;
+      const float* dsrc = ((mr_next.z == t + 1) ? d_out + (int64_t)mr_next.x * U : dhs + i * U) + half * 16;
+      const float* hsrc = ((t == 0) ? h0 + (int64_t)mr_next.x * U : h_seq + (int64_t)(mr_next.y + t - 1) * U) + half * 16;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        pre_d[k] = ldg_f4(dsrc + 4 * k);
+        pre_h[k] = ldg_f4(hsrc + 4 * k);
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pre_d[k] = pre_h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fetch_meta(0);
+    fetch_rows(0);
     for (int64_t j = 0; j < my_tiles; ++j) {
-      const uint32_t ph = (uint32_t)j & 1;
-      const int64_t tile = blockIdx.x + j * G;
-      const int64_t i = tile * ROWS + row;
-      mbar_wait(&bar_full, ph);                              // s_meta of this tile is visible
-      const int4 mr = s_meta[j & 1][row];
-      const bool alive = mr.w != 0;
-      const float* dsrc = alive ? ((mr.z == t + 1) ? d_out + (int64_t)mr.x * U : dhs + i * U) : d_out;
-      const float* hsrc = alive ? ((t == 0) ? h0 + (int64_t)mr.x * U : h_seq + (int64_t)(mr.y + t - 1) * U) : h0;
+      const int buf = (int)(j & 1);
+      const int64_t i = (blockIdx.x + j * G) * ROWS + row;
+      const int4 mr = mr_next;
+      const bool alive = mr.x >= 0;
+      float dh[16], hold[16];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dh[4 * k] = pre_d[k].x; dh[4 * k + 1] = pre_d[k].y; dh[4 * k + 2] = pre_d[k].z; dh[4 * k + 3] = pre_d[k].w;
+        hold[4 * k] = pre_h[k].x; hold[4 * k + 1] = pre_h[k].y; hold[4 * k + 2] = pre_h[k].z; hold[4 * k + 3] = pre_h[k].w;
+      }
+      fetch_meta(j + 1);
       float direct[16];
-      mbar_wait(&bar_acc1, ph);                              // gate pre-activations are in TMEM, x / h images free
+      mbar_wait(&bar_acc1[buf], (uint32_t)(j >> 1) & 1);     // gate pre-activations of the tile are in TMEM
       tc_fence_after();
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int u0 = half * 16 + 8 * c;
         uint32_t az[8], ar[8], axh[8], ahh[8];
-        tmem_ld8_nowait(tb + u0, az);
-        tmem_ld8_nowait(tb + 32 + u0, ar);
-        tmem_ld8_nowait(tb + 64 + u0, axh);
-        tmem_ld8_nowait(tb + 96 + u0, ahh);
-        const float4 d0 = ldg_f4(dsrc + u0), d1v = ldg_f4(dsrc + u0 + 4);
-        const float4 h0v = ldg_f4(hsrc + u0), h1v = ldg_f4(hsrc + u0 + 4);
-        const float dh[8] = {d0.x, d0.y, d0.z, d0.w, d1v.x, d1v.y, d1v.z, d1v.w};
-        const float hold[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+        tmem_ld8_nowait(tb + buf * 128 + u0, az);
+        tmem_ld8_nowait(tb + buf * 128 + 32 + u0, ar);
+        tmem_ld8_nowait(tb + buf * 128 + 64 + u0, axh);
+        tmem_ld8_nowait(tb + buf * 128 + 96 + u0, ahh);
         tmem_ld_wait();
+        if (c == 1) {                                        // acc1[buf] is free for the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_a1free[buf]);
+        }
         float gz[8], gr[8], gx[8], gh[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -239,12 +273,12 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
           const float r = fast_sigmoid(__uint_as_float(ar[u]) + s_gb[U + u0 + u]);
           const float phh = __uint_as_float(ahh[u]) + s_gb[3 * U + u0 + u];
           const float hh = fast_tanh(fmaf(r, phh, __uint_as_float(axh[u]) + s_gb[2 * U + u0 + u]));
-          const float dv = alive ? dh[u] : 0.0f;
+          const float dv = alive ? dh[8 * c + u] : 0.0f;
           const float t1 = dv * (1.0f - z);
           gx[u] = t1 * (1.0f - hh * hh);
           gh[u] = gx[u] * r;
           gr[u] = gx[u] * phh * r * (1.0f - r);
-          gz[u] = dv * (hold[u] - hh) * z * (1.0f - z);
+          gz[u] = dv * (hold[8 * c + u] - hh) * z * (1.0f - z);
           direct[8 * c + u] = dv * z;
         }
         if (alive) {                                         // G row for the weight-gradient kernel
@@ -258,8 +292,13 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
           st_f4(gp + 3 * U, make_float4(gh[0], gh[1], gh[2], gh[3]));
           st_f4(gp + 3 * U + 4, make_float4(gh[4], gh[5], gh[6], gh[7]));
         }
-        // second chunk of this slot: the MMAs of the first one must have read it
-        if (c == 1) mbar_wait(&bar_gdone[half], 0);
+        // fill n = 2 c + half of this tile goes into the slot once the MMAs of the previous fill -- by the OTHER
+        // half -- have read it.  Completions are counted per half (bar_gdone[h]: index 2 j + c), so a waiter is
+        // never more than one phase away from the phase it names (a single barrier would alias phases F - 1 and
+        // F - 3 through the parity bit).
+        if (half == 1) mbar_wait(&bar_gdone[0], (uint32_t)c);                   // fill (j, c) of half 0
+        else if (c == 1) mbar_wait(&bar_gdone[1], 0);                            // fill (j, 0) of half 1
+        else if (j > 0) mbar_wait(&bar_gdone[1], 1);                             // fill (j - 1, 1) of half 1
         store_split(g_hi, g_lo, row, 0, make_float4(gz[0], gz[1], gz[2], gz[3]));
         store_split(g_hi, g_lo, row, 1, make_float4(gz[4], gz[5], gz[6], gz[7]));
         store_split(g_hi, g_lo, row, 2, make_float4(gr[0], gr[1], gr[2], gr[3]));
@@ -269,15 +308,15 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
         store_split(g_hi, g_lo, row, 6, make_float4(gh[0], gh[1], gh[2], gh[3]));
         store_split(g_hi, g_lo, row, 7, make_float4(gh[4], gh[5], gh[6], gh[7]));
         fence_async_smem();
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_gfull[half]);
+        if (lane == 0) mbar_arrive(&bar_gfull);
       }
-      mbar_wait(&bar_acc2, ph);                              // [dx | dh] of the tile is in TMEM
+      fetch_rows(j + 1);                                     // lands while GEMM2 finishes
+      mbar_wait(&bar_acc2, (uint32_t)j & 1);                 // [dx | dh] of the tile is in TMEM
       tc_fence_after();
       uint32_t vx[16], vh[16];
-      tmem_ld16_nowait(tb + 128 + half * 16, vx);
-      tmem_ld16_nowait(tb + 128 + U + half * 16, vh);
+      tmem_ld16_nowait(tb + 256 + half * 16, vx);
+      tmem_ld16_nowait(tb + 256 + U + half * 16, vh);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem_base, 256);
+  if (warp == MMA1_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 // destinations without any step: the state passes through, so does its gradient
@@ -315,11 +354,11 @@ __global__ void gru_bwd_passthrough_kernel(const int* __restrict__ nt, int64_t n
 // weight gradients of one step: D[128 lanes = x_hi | h_hi | x_lo | h_lo features][128 = G columns] accumulated
 // over the CTA's rows in TMEM (MN-major SWIZZLE_128B_BASE32B operands, see dw_tc.cu)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int R16 = 16;                    // rows per stage = 2 K-steps
-constexpr int DIMG = R16 * 128;            // bytes of one [16 x 32] image
+constexpr int RW = 64;                     // rows per stage = 8 K-steps
+constexpr int DIMG = RW * 128;             // bytes of one [64 x 32] image
 constexpr int DW_BLOCKS = 12;              // x_hi h_hi x_lo h_lo | G_hi[4] | G_lo[4]
 constexpr int DW_STAGE = DW_BLOCKS * DIMG;
-constexpr int DW_STAGES = 6;
+constexpr int DW_STAGES = 2;
 constexpr int DW_PROD_WARPS = 16;
 constexpr int DW_PROD_THREADS = 32 * DW_PROD_WARPS;
 constexpr int DW_THREADS = DW_PROD_THREADS + 32;
@@ -369,23 +408,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
 
   const int64_t n_alive = (int64_t)__ldg(nt + t);
   const int* entries = steps_T + __ldg(off + t);
-  const int64_t nchunks = (n_alive + R16 - 1) / R16;
+  const int64_t nchunks = (n_alive + RW - 1) / RW;
   const int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
   const int64_t c0 = (int64_t)blockIdx.x * per;
   const int64_t c1 = c0 + per < nchunks ? c0 + per : nchunks;
   const int64_t n_my = c1 > c0 ? c1 - c0 : 0;
 
   if (warp < DW_PROD_WARPS) {
-    // threads 0..255: one float4 of [x | h] (row tid / 16, chunk tid % 16) and one of G (row 8 + tid / 32);
-    // threads 256..511: one float4 of G (row (tid - 256) / 32).  Every thread's G chunk is column tid % 32.
-    const bool has_a = tid < 256;
+    // per 64-row chunk a thread loads two float4 of [x | h] (rows tid / 16 + 32 p, chunk tid % 16) and four of G
+    // (rows tid / 32 + 16 p, chunk tid % 32): its G column chunk never changes, so the bias sums stay in registers
     const int ra = tid >> 4, wa = tid & 15;
-    const int rg = has_a ? 8 + (tid >> 5) : (tid - 256) >> 5, wg = tid & 31;
+    const int rg = tid >> 5, wg = tid & 31;
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    // row pointer of the [x | h] float4 this thread loads for a chunk (nullptr = zeros)
-    auto a_ptr = [&](int64_t chunk) -> const float* {
-      const int64_t i = chunk * R16 + ra;
-      if (!has_a || i >= n_alive) return nullptr;
+    auto a_ptr = [&](int64_t chunk, int p) -> const float* {
+      const int64_t i = chunk * RW + ra + 32 * p;
+      if (i >= n_alive) return nullptr;
       if (wa < 8) {
         const int e = __ldg(entries + i);
         return e >= 0 ? pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U + wa * 4 : nullptr;
@@ -393,36 +430,50 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
       const int4 m = __ldg(meta + i);
       return ((t == 0) ? h0 + (int64_t)m.x * U : h_seq + (int64_t)(m.y + t - 1) * U) + (wa - 8) * 4;
     };
-    auto load = [&](int64_t chunk, const float* ap, float4& va, float4& vg) {
-      va = ap ? ldg_f4(ap) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int64_t i = chunk * R16 + rg;
-      vg = i < n_alive ? ld_stream_f4(g_in + i * 128 + wg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load = [&](int64_t chunk, const float* const (&ap)[2], float4 (&va)[2], float4 (&vg)[4]) {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) va[p] = ap[p] ? ldg_f4(ap[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int64_t i = chunk * RW + rg + 16 * p;
+        vg[p] = i < n_alive ? ld_stream_f4(g_in + i * 128 + wg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
-    float4 ca, cg, na = make_float4(0.f, 0.f, 0.f, 0.f), ng = na;
-    const float* p_next = nullptr;
+    float4 ca[2], cg[4], na[2], ng[4];
+    const float* p_next[2] = {nullptr, nullptr};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) na[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) ng[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n_my > 0) {
-      load(c0, a_ptr(c0), ca, cg);
-      if (n_my > 1) p_next = a_ptr(c0 + 1);
+      const float* p0[2] = {a_ptr(c0, 0), a_ptr(c0, 1)};
+      load(c0, p0, ca, cg);
+      if (n_my > 1) { p_next[0] = a_ptr(c0 + 1, 0); p_next[1] = a_ptr(c0 + 1, 1); }
     }
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % DW_STAGES);
       if (i + 1 < n_my) load(c0 + i + 1, p_next, na, ng);
-      if (i + 2 < n_my) p_next = a_ptr(c0 + i + 2);
+      if (i + 2 < n_my) { p_next[0] = a_ptr(c0 + i + 2, 0); p_next[1] = a_ptr(c0 + i + 2, 1); }
       if (i >= DW_STAGES) mbar_wait(&bar_free[s], (uint32_t)((i / DW_STAGES) - 1) & 1);
       unsigned char* st = smem + (size_t)s * DW_STAGE;
-      if (has_a) {                                           // blocks: x_hi 0, h_hi 1, x_lo 2, h_lo 3
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {                          // blocks: x_hi 0, h_hi 1, x_lo 2, h_lo 3
         unsigned char* hi = st + (wa >> 3) * DIMG;
-        store_split_mn(hi, hi + 2 * DIMG, ra, wa & 7, ca);
+        store_split_mn(hi, hi + 2 * DIMG, ra + 32 * p, wa & 7, ca[p]);
       }
-      {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
         unsigned char* hi = st + (4 + (wg >> 3)) * DIMG;
-        store_split_mn(hi, hi + 4 * DIMG, rg, wg & 7, cg);
-        colsum.x += cg.x; colsum.y += cg.y; colsum.z += cg.z; colsum.w += cg.w;
+        store_split_mn(hi, hi + 4 * DIMG, rg + 16 * p, wg & 7, cg[p]);
+        colsum.x += cg[p].x; colsum.y += cg[p].y; colsum.z += cg[p].z; colsum.w += cg[p].w;
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[s]);
-      ca = na; cg = ng;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) ca[p] = na[p];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) cg[p] = ng[p];
     }
     if (n_my > 0) {
       // bias gradients: G column c -> db[0][c] for z, r, xh (c < 96); db[1][c] for z, r and db[1][c - 32] for hh
@@ -463,7 +514,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
         const uint32_t st = smem_u32(smem + (size_t)s * DW_STAGE);
         const uint32_t b_hi = st + 4 * DIMG, b_lo = b_hi + 4 * DIMG;
 #pragma unroll
-        for (int ks = 0; ks < R16 / 8; ++ks) {
+        for (int ks = 0; ks < RW / 8; ++ks) {
           const uint32_t ko = ks * 1024;
           umma_tf32(tmem_base, umma_desc_mn(st + ko, DIMG), umma_desc_mn(b_hi + ko, DIMG), idesc, (i > 0 || ks > 0) ? 1u : 0u);
           umma_tf32(tmem_base, umma_desc_mn(st + ko, DIMG), umma_desc_mn(b_lo + ko, DIMG), idesc, 1u);
@@ -496,7 +547,7 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
   for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
   float* g_rows = reinterpret_cast<float*>(ws);
   float* dhs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ign_align((size_t)num_dst * 4 * U * sizeof(float)));
-  const size_t smem_a = 1024 + 4 * (size_t)IMG + 8 * (size_t)W2IMG + 4 * (size_t)IMG;
+  const size_t smem_a = 1024 + 4 * (size_t)IMG + 8 * (size_t)W2IMG + 4 * (size_t)IMG + 2 * (size_t)IMG;
   const size_t smem_w = 1024 + (size_t)DW_STAGES * DW_STAGE;
   static thread_local bool configured = false;
   if (!configured) {
@@ -511,8 +562,8 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
   const int4* meta4 = reinterpret_cast<const int4*>(meta);
   gru_bwd_passthrough_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(nt, num_dst, meta4, d_out, dh0);
   IGN_CHECK_LAUNCH("gru_bwd_passthrough");
-  // enough 16-row chunks per CTA that the atomic flush of the accumulators stays small
-  int64_t grid_w = ign_cdiv(ign_cdiv(num_dst, R16), 32);
+  // enough 64-row chunks per CTA that the atomic flush of the accumulators stays small
+  int64_t grid_w = ign_cdiv(ign_cdiv(num_dst, RW), 8);
   if (grid_w > sms) grid_w = sms;
   if (grid_w < 1) grid_w = 1;
   for (int t = max_steps - 1; t >= 0; --t) {

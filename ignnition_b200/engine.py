@@ -43,6 +43,7 @@ class DeviceGraph:
         self.max_seq: Dict[str, int] = {}                 # host-known longest list per adjacency
         self.partner: Dict[str, list] = {}               # concat axis 2: per-source row index per CSR position
         self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
+        self.step_plan_bwd: Dict[str, tuple] = {}        # the same plan for the step-synchronous backward pass
         self.status: Dict[str, torch.Tensor] = {}
         self.h2d_bytes = 0
 
@@ -78,6 +79,9 @@ class Engine:
         # ordered updates whose longest sequence is <= this run step-synchronously (one launch per step,
         # ign_gru_seq_step); 0 = always the sequence walk (ign_gru_seq), which is faster in round 1
         self.max_step_launches = max_step_launches
+        # backward of ordered updates: sequences up to this long run as step-synchronous tensor-core launches
+        # (two per step); longer ones walk tiles on the fp32 CUDA cores (ign_gru_seq_bwd)
+        self.max_bwd_step_launches = 64
         # sum aggregation + GRU: one fused fp32 kernel, or segment_reduce + tensor-core cell.  None picks by
         # measurement (GEANT2 x 4096 links: 0.121 + 0.087 ms unfused on tensor cores vs 0.333 ms fused fp32)
         self.fuse_sum_gru = fuse_sum_gru
@@ -400,6 +404,11 @@ class Engine:
                     if (p.key in g.order and 1 <= max_steps <= self.max_step_launches and p.msg_dim == 32
                             and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()):
                         g.step_plan[p.key] = (ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
+                    # training: BPTT runs step-synchronously on the tensor cores (ign_gru_seq_bwd_steps)
+                    if (training and p.key in g.order and 1 <= max_steps <= self.max_bwd_step_launches
+                            and p.msg_dim == 32 and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()):
+                        g.step_plan_bwd[p.key] = g.step_plan.get(p.key) or (
+                            ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
         return g
 
     def prepare(self, samples_or_batch, labels=None, training: bool = False, check: bool = False) -> DeviceGraph:

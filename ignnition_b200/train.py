@@ -134,11 +134,19 @@ class Trainer:
                 rowptr_s, steps = graph.steps[p.key]
                 d_steps = torch.empty(steps.numel(), p.msg_dim, dtype=torch.float32, device=dev)
                 dh0 = torch.empty_like(h_old)
-                ops.gru_seq_bwd(rowptr_s, steps, graph.order.get(p.key), src_states, h_old, h_seq,
-                                e.param(p.dst + "_update/kernel"), e.param(p.dst + "_update/recurrent_kernel"),
-                                e.param(p.dst + "_update/bias"), g_new, d_steps, dh0,
-                                self.g(p.dst + "_update/kernel"), self.g(p.dst + "_update/recurrent_kernel"),
-                                self.g(p.dst + "_update/bias"))
+                if p.key in graph.step_plan_bwd:
+                    plan, max_steps = graph.step_plan_bwd[p.key]
+                    ops.gru_seq_bwd_steps(plan, graph.meta[p.key], max_steps, src_states, h_old, h_seq,
+                                          e.param(p.dst + "_update/kernel"), e.param(p.dst + "_update/recurrent_kernel"),
+                                          e.param(p.dst + "_update/bias"), g_new, d_steps, dh0,
+                                          self.g(p.dst + "_update/kernel"), self.g(p.dst + "_update/recurrent_kernel"),
+                                          self.g(p.dst + "_update/bias"))
+                else:
+                    ops.gru_seq_bwd(rowptr_s, steps, graph.order.get(p.key), src_states, h_old, h_seq,
+                                    e.param(p.dst + "_update/kernel"), e.param(p.dst + "_update/recurrent_kernel"),
+                                    e.param(p.dst + "_update/bias"), g_new, d_steps, dh0,
+                                    self.g(p.dst + "_update/kernel"), self.g(p.dst + "_update/recurrent_kernel"),
+                                    self.g(p.dst + "_update/bias"))
                 gstate[p.dst] = dh0
                 for k, a in enumerate(p.adjs):
                     rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]

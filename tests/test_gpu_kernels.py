@@ -520,7 +520,7 @@ def test_dense_bwd(m, k, n, act):
     assert rel_err(dw.cpu().numpy(), 2 * want_dw) < RTOL
 
 
-@pytest.mark.parametrize("max_len,n_dst", [(1, 700), (6, 3000), (16, 1000)])
+@pytest.mark.parametrize("max_len,n_dst", [(1, 700), (6, 3000), (16, 1000), (3, 90000)])
 def test_gru_seq_bwd_step_synchronous(max_len, n_dst):
     """BPTT as step-synchronous tcgen05 launches (ign_gru_seq_bwd_steps) == torch.autograd in fp64 through the
     oracle's GRU recurrence, and == the fp32 tile-walk kernel (ign_gru_seq_bwd): message gradients per step,
