@@ -38,7 +38,10 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_WARP0 = PROD_WARPS;                       // warps 4..11: TMEM lane groups 0..3 twice
 constexpr int MMA1_WARP = EPI_WARP0 + EPI_WARPS;
 constexpr int MMA2_WARP = MMA1_WARP + 1;
-constexpr int BW_THREADS = 32 * (MMA2_WARP + 1);            // 14 warps
+constexpr int PF_WARP0 = MMA2_WARP + 1;                       // two warps that run ahead and pull rows into L2
+constexpr int PF_WARPS = 2;
+constexpr int PF_AHEAD = 3;                                 // tiles
+constexpr int BW_THREADS = 32 * (PF_WARP0 + PF_WARPS);      // 16 warps
 
 struct SrcPtrs {
   const float* p[IGN_MAX_SOURCES];
@@ -46,13 +49,53 @@ struct SrcPtrs {
 __device__ __forceinline__ const float* pick_src(const SrcPtrs& s, int k) {
   return k == 0 ? s.p[0] : k == 1 ? s.p[1] : k == 2 ? s.p[2] : s.p[3];
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// D[128, n] (+)= A B^T with A[128 lanes, 8 columns] in TENSOR MEMORY (tf32 bit patterns, one K element per column)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// TMA bulk store shared -> global (linear bytes) and its bookkeeping
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+#ifdef IGN_BWD_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_DECL unsigned long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64();
+#define PROF(k) { const long long n_ = clock64(); pt_[k] += (unsigned long long)(n_ - pc_); pc_ = n_; }
+#define PROF_FLUSH(base, n) if (lane == 0) { for (int k_ = 0; k_ < n; ++k_) atomicAdd(&g_prof[base + k_], pt_[k_]); }
+#else
+#define PROF_DECL
+#define PROF(k)
+#define PROF_FLUSH(base, n)
+#endif
 
 __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     int t, const int* __restrict__ nt, const int* __restrict__ off, const int4* __restrict__ meta,
     const int* __restrict__ steps_T, SrcPtrs srcs, const float* __restrict__ h0, const float* __restrict__ h_seq,
     const float* __restrict__ d_out, float* __restrict__ dhs, float* __restrict__ dh0, float* __restrict__ d_steps,
-    float* __restrict__ g_out, const float* __restrict__ kernel, const float* __restrict__ rkernel,
-    const float* __restrict__ bias) {
+    float* __restrict__ g_out, int64_t g_rows_bound, const float* __restrict__ kernel,
+    const float* __restrict__ rkernel, const float* __restrict__ bias, int dbg) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // forward gate weights, 128 rows each: Bx = [K_z | K_r | K_h | 0], Bh = [R_z | R_r | 0 | R_h]
@@ -63,20 +106,23 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
   // W2 chunk q (units 8q .. 8q+7, column k = gate * 8 + jj): [hi 64 rows | lo 64 rows], rows 0-31 -> dx, 32-63 -> dh
   unsigned char* w2 = bh_lo + IMG;
   unsigned char* stage = w2 + 8 * W2IMG;                     // X_hi | X_lo | H_hi | H_lo of the tile in GEMM1
-  unsigned char* gslot = stage + 4 * IMG;                    // G_hi | G_lo of the chunk in GEMM2
-  __shared__ uint64_t bar_full, bar_acc1[2], bar_a1free[2], bar_gfull, bar_gdone[2], bar_acc2, bar_d2free;
+  unsigned char* gstage = stage + 4 * IMG;                   // per epilogue warp: [32 rows][128 B] of G on its way out
+  __shared__ uint64_t bar_full, bar_acc1[2], bar_a1free[2], bar_gfull[2], bar_gdone[2], bar_acc2, bar_d2free;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_gb[4 * U];                // merged gate biases [bz | br | bxh | bhh]
+  __shared__ volatile int s_progress;                        // tiles whose GEMM1 has been issued (throttles the prefetch)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
+    s_progress = 0;
     mbar_init(&bar_full, PROD_WARPS);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_acc1[s], 1);
       mbar_init(&bar_a1free[s], EPI_WARPS);
     }
-    mbar_init(&bar_gfull, EPI_WARPS / 2);
+    mbar_init(&bar_gfull[0], EPI_WARPS / 2);
+    mbar_init(&bar_gfull[1], EPI_WARPS / 2);
     mbar_init(&bar_gdone[0], 1);
     mbar_init(&bar_gdone[1], 1);
     mbar_init(&bar_acc2, 1);
@@ -135,6 +181,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     // ================================ producers ================================
     const int ptid = tid;                                    // 0..127
     const int c4 = ptid & 7;
+    PROF_DECL
     for (int64_t j = 0; j < my_tiles; ++j) {
       const int64_t tile = blockIdx.x + j * G;
       int4 m[8];
@@ -159,7 +206,12 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
         if (!inb[k]) hv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // GEMM1 of the previous tile has read the stage
+#ifdef IGN_BWD_PROFILE
+      if (__float_as_uint(xv[0].x + hv[0].x + xv[7].x + hv[7].x) == 0x7fc12345u) __nanosleep(1);   // loads landed
+#endif
+      PROF(0)
       if (j > 0) mbar_wait(&bar_acc1[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1);
+      PROF(1)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int r = (ptid >> 3) + 16 * k;
@@ -169,7 +221,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full);
+      PROF(2)
     }
+    if (warp == 0) { PROF_FLUSH(0, 3) }
   } else if (warp == MMA1_WARP) {
     // ================================ issuer of GEMM1 ================================
     const uint32_t ax_hi = smem_u32(stage), ax_lo = ax_hi + IMG, ah_hi = ax_lo + IMG, ah_lo = ah_hi + IMG;
@@ -183,24 +237,53 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
         umma_chunk_3x(d1, ax_hi, ax_lo, smem_u32(bx_hi), smem_u32(bx_lo), 128, false);    // z | r | xh | 0
         umma_chunk_3x(d1, ah_hi, ah_lo, smem_u32(bh_hi), smem_u32(bh_lo), 128, true);     // z | r | 0  | hh
         umma_commit(&bar_acc1[buf]);
+        s_progress = (int)(j + 1);
       }
       __syncwarp();
     }
+  } else if (warp >= PF_WARP0) {
+    // ================================ L2 prefetch ================================
+    // The gathers are two dependent loads deep (meta / step entry -> row); with one tile of rows in flight per SM
+    // the kernel ran at the latency of that chain (1.6 TB/s).  These warps resolve the chain PF_AHEAD tiles early
+    // and leave the rows in L2, holding no registers across the wait.
+    const int pl = tid - PF_WARP0 * 32;                      // 0..63: rows pl, pl + 64
+    for (int64_t j = 0; j < my_tiles; ++j) {
+      if (dbg & 8) break;
+      while (j - s_progress > PF_AHEAD) __nanosleep(200);
+      const int64_t tile = blockIdx.x + j * G;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int64_t i = tile * ROWS + pl + 64 * k;
+        if (i >= n_alive) continue;
+        const int4 m = __ldg(meta + i);
+        const int e = __ldg(entries + i);
+        if (e >= 0) prefetch_l2(pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U);
+        prefetch_l2((t == 0) ? h0 + (int64_t)m.x * U : h_seq + (int64_t)(m.y + t - 1) * U);
+        prefetch_l2((m.z == t + 1) ? d_out + (int64_t)m.x * U : dhs + i * U);
+      }
+    }
   } else if (warp == MMA2_WARP) {
     // ================================ issuer of GEMM2 ================================
-    const uint32_t g_hi = smem_u32(gslot), g_lo = g_hi + IMG;
+    // A = G chunk in tensor memory (slot of the half that wrote it: hi 32 columns | lo 32 columns), B = W2 chunk images
     const uint32_t d2 = tmem_base + 256;
+    constexpr uint32_t idesc = umma_idesc(64);
     for (int64_t j = 0; j < my_tiles; ++j) {
 #pragma unroll 1
-      for (int n = 0; n < 4; ++n) {                          // fills alternate between the two halves of the units
-        const int q = (n & 1) * 2 + (n >> 1);
-        mbar_wait(&bar_gfull, (uint32_t)n & 1);
+      for (int n = 0; n < 4; ++n) {                          // fills (half, c) in the order (0,0) (1,0) (0,1) (1,1)
+        const int hf = n & 1, c = n >> 1, q = hf * 2 + c;
+        mbar_wait(&bar_gfull[hf], (uint32_t)c);
         if (n == 0 && j > 0) mbar_wait(&bar_d2free, (uint32_t)(j - 1) & 1);   // previous [dx | dh] has been read
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t w_hi = smem_u32(w2 + q * 2 * W2IMG);
-          umma_chunk_3x(d2, g_hi, g_lo, w_hi, w_hi + W2IMG, 64, n > 0);
-          umma_commit(&bar_gdone[n & 1]);                   // one barrier per half: see the epilogue's wait
+          const uint32_t a_hi = tmem_base + 320 + hf * 64, a_lo = a_hi + 32;
+          const uint32_t w_hi = smem_u32(w2 + q * 2 * W2IMG), w_lo = w_hi + W2IMG;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_tf32_ts(d2, a_hi + 8 * kk, umma_desc(w_hi + 32 * kk), idesc, (n > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32_ts(d2, a_lo + 8 * kk, umma_desc(w_hi + 32 * kk), idesc, 1u);
+            umma_tf32_ts(d2, a_hi + 8 * kk, umma_desc(w_lo + 32 * kk), idesc, 1u);
+          }
+          umma_commit(&bar_gdone[hf]);
           if (n == 3) umma_commit(&bar_acc2);
         }
         __syncwarp();
@@ -212,8 +295,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     const int q = warp & 3;                                  // TMEM lane group this warp may access
     const int half = e >> 2;                                 // units [16 half, 16 half + 16)
     const int row = q * 32 + lane;
-    unsigned char* g_hi = gslot;
-    unsigned char* g_lo = gslot + IMG;
+    unsigned char* my_stage = gstage + e * 4096;
+    const int64_t warp_row0 = q * 32;                        // first tile row of this warp
+    PROF_DECL
     // (dL/dh, h_{t-1}) of this thread's 16 units, prefetched one tile ahead
     float4 pre_d[4], pre_h[4];
     int4 mr_next = make_int4(-1, 0, 0, 0);
@@ -222,7 +306,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
       mr_next = (j < my_tiles && i < n_alive) ? __ldg(meta + i) : make_int4(-1, 0, 0, 0);
     };
     auto fetch_rows = [&](int64_t j) {
-      if (mr_next.x < 0) return;
+      if (mr_next.x < 0 || (dbg & 2)) return;
       const int64_t i = (blockIdx.x + j * G) * ROWS + row;
       const float* dsrc = ((mr_next.z == t + 1) ? d_out + (int64_t)mr_next.x * U : dhs + i * U) + half * 16;
       const float* hsrc = ((t == 0) ? h0 + (int64_t)mr_next.x * U : h_seq + (int64_t)(mr_next.y + t - 1) * U) + half * 16;
@@ -249,8 +333,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
       }
       fetch_meta(j + 1);
       float direct[16];
+      PROF(0)
       mbar_wait(&bar_acc1[buf], (uint32_t)(j >> 1) & 1);     // gate pre-activations of the tile are in TMEM
       tc_fence_after();
+      PROF(1)
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -281,39 +367,63 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
           gz[u] = dv * (hold[8 * c + u] - hh) * z * (1.0f - z);
           direct[8 * c + u] = dv * z;
         }
-        if (alive) {                                         // G row for the weight-gradient kernel
-          float* gp = g_out + i * (4 * U) + u0;
-          st_f4(gp, make_float4(gz[0], gz[1], gz[2], gz[3]));
-          st_f4(gp + 4, make_float4(gz[4], gz[5], gz[6], gz[7]));
-          st_f4(gp + U, make_float4(gr[0], gr[1], gr[2], gr[3]));
-          st_f4(gp + U + 4, make_float4(gr[4], gr[5], gr[6], gr[7]));
-          st_f4(gp + 2 * U, make_float4(gx[0], gx[1], gx[2], gx[3]));
-          st_f4(gp + 2 * U + 4, make_float4(gx[4], gx[5], gx[6], gx[7]));
-          st_f4(gp + 3 * U, make_float4(gh[0], gh[1], gh[2], gh[3]));
-          st_f4(gp + 3 * U + 4, make_float4(gh[4], gh[5], gh[6], gh[7]));
+        // G chunk (k = gate * 8 + unit) -> tensor memory as the A operand of GEMM2 (hi | lo), slot of this half; the
+        // slot's previous chunk (c == 0 of this tile) must have been consumed
+        PROF(2)
+        if (c == 1) mbar_wait(&bar_gdone[half], 0);
+        PROF(3)
+        {
+          const float* gsrc[4] = {gz, gr, gx, gh};
+          uint32_t hi[16], lo[16];
+          const uint32_t ta = tb + 320 + half * 64;
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {                   // gates (0, 1) then (2, 3)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float v = gsrc[2 * hb + (k >> 3)][k & 7];
+              const float vh_ = tf32_rna(v);
+              hi[k] = __float_as_uint(vh_);
+              lo[k] = __float_as_uint(tf32_rna(v - vh_));
+            }
+            tmem_st16(ta + 16 * hb, hi);
+            tmem_st16(ta + 32 + 16 * hb, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_gfull[half]);
         }
-        // fill n = 2 c + half of this tile goes into the slot once the MMAs of the previous fill -- by the OTHER
-        // half -- have read it.  Completions are counted per half (bar_gdone[h]: index 2 j + c), so a waiter is
-        // never more than one phase away from the phase it names (a single barrier would alias phases F - 1 and
-        // F - 3 through the parity bit).
-        if (half == 1) mbar_wait(&bar_gdone[0], (uint32_t)c);                   // fill (j, c) of half 0
-        else if (c == 1) mbar_wait(&bar_gdone[1], 0);                            // fill (j, 0) of half 1
-        else if (j > 0) mbar_wait(&bar_gdone[1], 1);                             // fill (j - 1, 1) of half 1
-        store_split(g_hi, g_lo, row, 0, make_float4(gz[0], gz[1], gz[2], gz[3]));
-        store_split(g_hi, g_lo, row, 1, make_float4(gz[4], gz[5], gz[6], gz[7]));
-        store_split(g_hi, g_lo, row, 2, make_float4(gr[0], gr[1], gr[2], gr[3]));
-        store_split(g_hi, g_lo, row, 3, make_float4(gr[4], gr[5], gr[6], gr[7]));
-        store_split(g_hi, g_lo, row, 4, make_float4(gx[0], gx[1], gx[2], gx[3]));
-        store_split(g_hi, g_lo, row, 5, make_float4(gx[4], gx[5], gx[6], gx[7]));
-        store_split(g_hi, g_lo, row, 6, make_float4(gh[0], gh[1], gh[2], gh[3]));
-        store_split(g_hi, g_lo, row, 7, make_float4(gh[4], gh[5], gh[6], gh[7]));
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_gfull);
+        PROF(4)
+        // the same chunk to global memory for the weight-gradient kernel: chunk-major G[q][row][32] with the
+        // 16-byte pieces of a row XOR-ed by (row & 7), staged per warp and written as one 4 KB TMA bulk store
+        if (!(dbg & 1)) {
+          if (lane == 0) bulk_wait_read();                   // the previous bulk store has read the staging rows
+          __syncwarp();
+          unsigned char* srow = my_stage + lane * 128;
+          const int sw = lane & 7;
+          *reinterpret_cast<float4*>(srow + ((0 ^ sw) << 4)) = make_float4(gz[0], gz[1], gz[2], gz[3]);
+          *reinterpret_cast<float4*>(srow + ((1 ^ sw) << 4)) = make_float4(gz[4], gz[5], gz[6], gz[7]);
+          *reinterpret_cast<float4*>(srow + ((2 ^ sw) << 4)) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+          *reinterpret_cast<float4*>(srow + ((3 ^ sw) << 4)) = make_float4(gr[4], gr[5], gr[6], gr[7]);
+          *reinterpret_cast<float4*>(srow + ((4 ^ sw) << 4)) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+          *reinterpret_cast<float4*>(srow + ((5 ^ sw) << 4)) = make_float4(gx[4], gx[5], gx[6], gx[7]);
+          *reinterpret_cast<float4*>(srow + ((6 ^ sw) << 4)) = make_float4(gh[0], gh[1], gh[2], gh[3]);
+          *reinterpret_cast<float4*>(srow + ((7 ^ sw) << 4)) = make_float4(gh[4], gh[5], gh[6], gh[7]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int qc = half * 2 + c;
+            const int64_t r0 = (blockIdx.x + j * G) * ROWS + warp_row0;
+            bulk_s2g(g_out + ((int64_t)qc * g_rows_bound + r0) * U, my_stage, 4096);
+          }
+        }
+        PROF(5)
       }
       fetch_rows(j + 1);                                     // lands while GEMM2 finishes
+      PROF(0)
       mbar_wait(&bar_acc2, (uint32_t)j & 1);                 // [dx | dh] of the tile is in TMEM
       tc_fence_after();
+      PROF(6)
       uint32_t vx[16], vh[16];
       tmem_ld16_nowait(tb + 256 + half * 16, vx);
       tmem_ld16_nowait(tb + 256 + U + half * 16, vh);
@@ -321,7 +431,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_d2free);
-      if (alive) {
+      if (alive && !(dbg & 4)) {
         float* xp = d_steps + (int64_t)(mr.y + t) * U + half * 16;
         float* hp = ((t == 0) ? dh0 + (int64_t)mr.x * U : dhs + i * U) + half * 16;
 #pragma unroll
@@ -332,8 +442,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
                                     direct[k + 2] + __uint_as_float(vh[k + 2]), direct[k + 3] + __uint_as_float(vh[k + 3])));
         }
       }
+      PROF(7)
     }
+    if (warp == EPI_WARP0) { PROF_FLUSH(3, 8) }
   }
+  if (warp >= EPI_WARP0 && warp < MMA1_WARP && lane == 0) bulk_wait_all();   // G rows are in global memory
   tc_fence_before();
   __syncthreads();
   if (warp == MMA1_WARP) tmem_dealloc(tmem_base, 512);
@@ -386,7 +499,8 @@ __device__ __forceinline__ void store_split_mn(unsigned char* img_hi, unsigned c
 __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
     int t, const int* __restrict__ nt, const int* __restrict__ off, const int4* __restrict__ meta,
     const int* __restrict__ steps_T, SrcPtrs srcs, const float* __restrict__ h0, const float* __restrict__ h_seq,
-    const float* __restrict__ g_in, float* __restrict__ dK, float* __restrict__ dR, float* __restrict__ dB) {
+    const float* __restrict__ g_in, int64_t g_rows_bound, float* __restrict__ dK, float* __restrict__ dR,
+    float* __restrict__ dB) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_full[DW_STAGES], bar_free[DW_STAGES], bar_done;
@@ -436,7 +550,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int64_t i = chunk * RW + rg + 16 * p;
-        vg[p] = i < n_alive ? ld_stream_f4(g_in + i * 128 + wg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // chunk-major G[q][row][32], 16-byte pieces XOR-ed by (row & 7) (as the backward kernel stores it)
+        vg[p] = i < n_alive ? ld_stream_f4(g_in + ((int64_t)(wg >> 3) * g_rows_bound + i) * U + (((wg & 7) ^ (int)(i & 7)) << 2))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     float4 ca[2], cg[4], na[2], ng[4];
@@ -453,7 +569,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % DW_STAGES);
       if (i + 1 < n_my) load(c0 + i + 1, p_next, na, ng);
-      if (i + 2 < n_my) { p_next[0] = a_ptr(c0 + i + 2, 0); p_next[1] = a_ptr(c0 + i + 2, 1); }
+      if (i + 2 < n_my) {
+        p_next[0] = a_ptr(c0 + i + 2, 0);
+        p_next[1] = a_ptr(c0 + i + 2, 1);
+        if ((wa & 7) == 0) {                                 // the gather is resolved one chunk early: start it now
+          if (p_next[0]) prefetch_l2(p_next[0]);
+          if (p_next[1]) prefetch_l2(p_next[1]);
+        }
+        const int64_t gi = (c0 + i + 2) * RW + rg;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if ((wg & 7) == 0 && gi + 16 * p < n_alive)
+            prefetch_l2(g_in + ((int64_t)(wg >> 3) * g_rows_bound + gi + 16 * p) * U);
+      }
       if (i >= DW_STAGES) mbar_wait(&bar_free[s], (uint32_t)((i / DW_STAGES) - 1) & 1);
       unsigned char* st = smem + (size_t)s * DW_STAGE;
 #pragma unroll
@@ -476,31 +604,34 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
       for (int p = 0; p < 4; ++p) cg[p] = ng[p];
     }
     if (n_my > 0) {
-      // bias gradients: G column c -> db[0][c] for z, r, xh (c < 96); db[1][c] for z, r and db[1][c - 32] for hh
+      // G column c' = q * 32 + gate * 8 + jj holds gate `gate` of unit 8 q + jj (gates: z, r, xh, hh)
+      // bias gradients: db[0] takes z, r, xh; db[1] takes z, r and hh (third block)
       const float cs[4] = {colsum.x, colsum.y, colsum.z, colsum.w};
+      {
+        const int gate = (wg & 7) >> 1;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = wg * 4 + k;
-        if (c < 3 * U) atomicAdd(dB + c, cs[k]);
-        if (c < 2 * U) atomicAdd(dB + 3 * U + c, cs[k]);
-        if (c >= 3 * U) atomicAdd(dB + 3 * U + c - U, cs[k]);
+        for (int k = 0; k < 4; ++k) {
+          const int unit = 8 * (wg >> 3) + (wg & 1) * 4 + k;
+          if (gate < 3) atomicAdd(dB + gate * U + unit, cs[k]);
+          if (gate < 2) atomicAdd(dB + 3 * U + gate * U + unit, cs[k]);
+          if (gate == 3) atomicAdd(dB + 3 * U + 2 * U + unit, cs[k]);
+        }
       }
       mbar_wait(&bar_done, 0);
       tc_fence_after();
-      const int lg = warp & 3, gate = warp >> 2;             // lanes: x_hi | h_hi | x_lo | h_lo; columns: one gate
+      const int lg = warp & 3, qc = warp >> 2;               // lanes: x_hi | h_hi | x_lo | h_lo; columns: chunk q
       const bool is_h = lg & 1;
-      // x rows take z, r, xh (gates 0-2); h rows take z, r (0, 1) and hh (3) -> recurrent column block 2
-      const bool used = is_h ? gate != 2 : gate != 3;
-      if (used) {
-        float* base = (is_h ? dR : dK) + lane * 3 * U + (gate == 3 ? 2 : gate) * U;
+      float* wrow = (is_h ? dR : dK) + lane * 3 * U + 8 * qc;
 #pragma unroll 1
-        for (int cb = 0; cb < U; cb += 8) {
-          uint32_t v[8];
-          tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + gate * U + cb, v);
-          tmem_ld_wait();
+      for (int gate = 0; gate < 4; ++gate) {
+        // x rows take z, r, xh (gates 0-2); h rows take z, r (0, 1) and hh (3) -> recurrent column block 2
+        if (is_h ? gate == 2 : gate == 3) continue;
+        uint32_t v[8];
+        tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + qc * U + gate * 8, v);
+        tmem_ld_wait();
+        float* base = wrow + (gate == 3 ? 2 : gate) * U;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) atomicAdd(base + cb + k, __uint_as_float(v[k]));
-        }
+        for (int k = 0; k < 8; ++k) atomicAdd(base + k, __uint_as_float(v[k]));
       }
     }
   } else {
@@ -533,8 +664,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
 
 }  // namespace
 
+#ifdef IGN_BWD_PROFILE
+extern "C" void ign_debug_bwd_prof(unsigned long long* out, int reset) {
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); return; }
+  cudaMemcpyFromSymbol(out, g_prof, 16 * sizeof(unsigned long long));
+}
+#endif
+static int g_dbg = 0;
+extern "C" void ign_debug_bwd(int v) { g_dbg = v; }
+
+static inline int64_t g_bound(int64_t num_dst) { return ign_cdiv(num_dst > 0 ? num_dst : 1, ROWS) * ROWS; }
+
 size_t ign_gru_step_bwd_tc_ws(int64_t num_dst) {
-  return ign_align((size_t)(num_dst > 0 ? num_dst : 1) * 4 * U * sizeof(float)) +      // G rows of one step
+  return ign_align((size_t)g_bound(num_dst) * 4 * U * sizeof(float)) +                 // G rows of one step (whole tiles)
          ign_align((size_t)(num_dst > 0 ? num_dst : 1) * U * sizeof(float));           // running dL/dh
 }
 
@@ -546,8 +688,8 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
   SrcPtrs sp;
   for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
   float* g_rows = reinterpret_cast<float*>(ws);
-  float* dhs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ign_align((size_t)num_dst * 4 * U * sizeof(float)));
-  const size_t smem_a = 1024 + 4 * (size_t)IMG + 8 * (size_t)W2IMG + 4 * (size_t)IMG + 2 * (size_t)IMG;
+  float* dhs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ign_align((size_t)g_bound(num_dst) * 4 * U * sizeof(float)));
+  const size_t smem_a = 1024 + 4 * (size_t)IMG + 8 * (size_t)W2IMG + 4 * (size_t)IMG + EPI_WARPS * 4096;
   const size_t smem_w = 1024 + (size_t)DW_STAGES * DW_STAGE;
   static thread_local bool configured = false;
   if (!configured) {
@@ -568,10 +710,11 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
   if (grid_w < 1) grid_w = 1;
   for (int t = max_steps - 1; t >= 0; --t) {
     gru_step_bwd_tc_kernel<<<grid, BW_THREADS, smem_a, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, d_out, dhs, dh0,
-                                                              d_steps, g_rows, kernel, rkernel, bias);
+                                                              d_steps, g_rows, g_bound(num_dst), kernel, rkernel, bias, g_dbg);
     IGN_CHECK_LAUNCH("gru_step_bwd_tc");
-    gru_dw_tc_kernel<<<(unsigned)grid_w, DW_THREADS, smem_w, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, g_rows, dK,
-                                                                    dR, dB);
+    if (g_dbg & 16) continue;
+    gru_dw_tc_kernel<<<(unsigned)grid_w, DW_THREADS, smem_w, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, g_rows,
+                                                                    g_bound(num_dst), dK, dR, dB);
     IGN_CHECK_LAUNCH("gru_dw_tc");
   }
   return IGN_OK;

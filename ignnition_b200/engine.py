@@ -485,6 +485,10 @@ class Engine:
         B = self.param(dst + "_update/bias") if K is not None else None
         out = torch.empty_like(h)
         msgs = [self._messages(p, k, g, state) for k in range(len(p.adjs))]
+        if tape is not None and any(m is not None for m in msgs):
+            raise RuntimeError("IGNNITION: training through message neural networks is not built")
+        if tape is not None and p.kind == "agg_ff":
+            raise RuntimeError("IGNNITION: training through a feed-forward update is not built")
 
         if p.kind == "seq_gru":
             rowptr_s, steps = g.steps[p.key]
