@@ -207,6 +207,47 @@ __global__ void __launch_bounds__(256) dense_small_n_kernel(const float* __restr
   }
 }
 
+// backward of a single-output layer (the readout head, K -> 1):  dx[m, k] = dz[m] w[k],  dw[k] += sum_m x[m, k] dz[m].
+// Two HBM streams (x in, dx out); a warp owns whole rows, a lane the same float4 columns of every row, so the
+// weight-gradient partial sums stay in registers until the CTA adds them once.
+template <int KV>
+__global__ void __launch_bounds__(256) dense_bwd_head_kernel(const float* __restrict__ x, int64_t M,
+                                                             const float* __restrict__ w, const float* __restrict__ dz,
+                                                             float* __restrict__ dx, float* __restrict__ dw) {
+  constexpr int K = KV * 128;
+  __shared__ float4 red[8][KV * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wv[KV], acc[KV];
+#pragma unroll
+  for (int v = 0; v < KV; ++v) {
+    wv[v] = ldg_f4(w + (v * 32 + lane) * 4);
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < M; r += nwarps) {
+    const float g = __ldg(dz + r);
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+      if (dw) {
+        const float4 xv = ld_stream_f4(x + r * K + (v * 32 + lane) * 4);
+        acc[v].x = fmaf(xv.x, g, acc[v].x); acc[v].y = fmaf(xv.y, g, acc[v].y);
+        acc[v].z = fmaf(xv.z, g, acc[v].z); acc[v].w = fmaf(xv.w, g, acc[v].w);
+      }
+      if (dx) st_f4(dx + r * K + (v * 32 + lane) * 4, make_float4(g * wv[v].x, g * wv[v].y, g * wv[v].z, g * wv[v].w));
+    }
+  }
+  if (!dw) return;
+#pragma unroll
+  for (int v = 0; v < KV; ++v) red[warp][v * 32 + lane] = acc[v];
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += 256) {
+    float s = 0.0f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) s += reinterpret_cast<const float*>(&red[wq][0])[i];
+    atomicAdd(dw + i, s);
+  }
+}
+
 // dz = dy * act'(pre), in place; db += column sums of dz (per-CTA partial, then atomics)
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ dy, const float* __restrict__ pre,
                                                            int64_t M, int N, int act, float* __restrict__ db) {
@@ -224,6 +265,41 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ d
       s += g;
     }
     if (db) atomicAdd(db + n, s);
+  }
+}
+
+// the same for few columns (N <= 8, the readout head): one thread per row, one atomic per column and CTA
+__global__ void __launch_bounds__(256) act_bwd_bias_small_kernel(float* __restrict__ dy, const float* __restrict__ pre,
+                                                                 int64_t M, int N, int act, float* __restrict__ db) {
+  __shared__ float red[8][8];
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    s[n] = 0.0f;
+    if (n < N && r < M) {
+      float g = dy[r * N + n];
+      if (act != IGN_ACT_LINEAR) {
+        g *= act_bwd(act, pre[r * N + n]);
+        dy[r * N + n] = g;
+      }
+      s[n] = g;
+    }
+  }
+  if (!db) return;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[n] += __shfl_xor_sync(0xffffffffu, s[n], o);
+    if (lane == 0) red[warp][n] = s[n];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += red[wq][threadIdx.x];
+    atomicAdd(db + threadIdx.x, t);
   }
 }
 
@@ -371,8 +447,21 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
   IGN_REQUIRE(act == IGN_ACT_LINEAR || pre_act, IGN_ERR_INVALID, "IGNNITION: dense_bwd: pre-activation needed");
   cudaStream_t st = ign_stream(stream);
   if (act != IGN_ACT_LINEAR || db) {
-    act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db);
+    if (n <= 8) act_bwd_bias_small_kernel<<<(unsigned)ign_cdiv(m, 256), 256, 0, st>>>(dy, pre_act, m, n, act, db);
+    else act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db);
     IGN_CHECK_LAUNCH("act_bwd_bias");
+  }
+  if (n == 1 && (k == 128 || k == 256 || k == 512) && m >= 1024) {
+    // single-output head: both gradients in one streaming pass
+    int sms = IGN_NUM_SMS, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = ign_cdiv(m, 8 * 16);
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    if (k == 128) dense_bwd_head_kernel<1><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw);
+    else if (k == 256) dense_bwd_head_kernel<2><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw);
+    else dense_bwd_head_kernel<4><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw);
+    IGN_CHECK_LAUNCH("dense_bwd_head");
+    return IGN_OK;
   }
   if (dx && ws && ign_tensor_cores_enabled() && ign_dense_tc_supported(n, k) && ws_bytes >= ign_dense_tc_ws(n, k) &&
       m >= 128) {

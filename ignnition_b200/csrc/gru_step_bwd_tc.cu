@@ -46,6 +46,18 @@ constexpr int BW_THREADS = 32 * (PF_WARP0 + PF_WARPS);      // 16 warps
 struct SrcPtrs {
   const float* p[IGN_MAX_SOURCES];
 };
+// h operand: lo = v - hi kept exactly (the tensor core truncates it to TF32 on read), so that the epilogue can
+// rebuild the old state bit for bit as hi + lo from the operand images
+__device__ __forceinline__ void store_split_exact(unsigned char* img_hi, unsigned char* img_lo, int r, int c4, float4 v) {
+  float4 hi, lo;
+  hi.x = tf32_rna(v.x); lo.x = v.x - hi.x;
+  hi.y = tf32_rna(v.y); lo.y = v.y - hi.y;
+  hi.z = tf32_rna(v.z); lo.z = v.z - hi.z;
+  hi.w = tf32_rna(v.w); lo.w = v.w - hi.w;
+  const int off = r * 128 + ((c4 ^ (r & 7)) << 4);
+  *reinterpret_cast<float4*>(img_hi + off) = hi;
+  *reinterpret_cast<float4*>(img_lo + off) = lo;
+}
 __device__ __forceinline__ const float* pick_src(const SrcPtrs& s, int k) {
   return k == 0 ? s.p[0] : k == 1 ? s.p[1] : k == 2 ? s.p[2] : s.p[3];
 }
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
   unsigned char* w2 = bh_lo + IMG;
   unsigned char* stage = w2 + 8 * W2IMG;                     // X_hi | X_lo | H_hi | H_lo of the tile in GEMM1
   unsigned char* gstage = stage + 4 * IMG;                   // per epilogue warp: [32 rows][128 B] of G on its way out
-  __shared__ uint64_t bar_full, bar_acc1[2], bar_a1free[2], bar_gfull[2], bar_gdone[2], bar_acc2, bar_d2free;
+  __shared__ uint64_t bar_full, bar_acc1[2], bar_a1free[2], bar_gfull[2], bar_gdone[2], bar_acc2, bar_d2free, bar_hfree;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_gb[4 * U];                // merged gate biases [bz | br | bxh | bhh]
   __shared__ volatile int s_progress;                        // tiles whose GEMM1 has been issued (throttles the prefetch)
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     mbar_init(&bar_gdone[1], 1);
     mbar_init(&bar_acc2, 1);
     mbar_init(&bar_d2free, EPI_WARPS);
+    mbar_init(&bar_hfree, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA1_WARP) tmem_alloc(&tmem_base_s, 512);
@@ -182,17 +195,30 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     const int ptid = tid;                                    // 0..127
     const int c4 = ptid & 7;
     PROF_DECL
+    // (meta, step entry) of this thread's 8 rows, fetched one tile ahead so that the row loads of a tile can be
+    // issued at once (the gathers are two dependent loads deep)
+    int4 m_nx[8];
+    int ent_nx[8];
+    auto fetch_index = [&](int64_t j) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {                          // rows (ptid >> 3) + 16 k
+        const int64_t i = (blockIdx.x + j * G) * ROWS + (ptid >> 3) + 16 * k;
+        const bool ok = j < my_tiles && i < n_alive;
+        m_nx[k] = ok ? __ldg(meta + i) : make_int4(-1, 0, 0, 0);
+        ent_nx[k] = ok ? __ldg(entries + i) : IGN_STEP_ZERO;
+      }
+    };
+    fetch_index(0);
     for (int64_t j = 0; j < my_tiles; ++j) {
-      const int64_t tile = blockIdx.x + j * G;
       int4 m[8];
       int ent[8];
       bool inb[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {                          // rows (ptid >> 3) + 16 k
-        const int64_t i = tile * ROWS + (ptid >> 3) + 16 * k;
-        inb[k] = i < n_alive;
-        m[k] = __ldg(meta + (inb[k] ? i : n_alive - 1));
-        ent[k] = __ldg(entries + (inb[k] ? i : 0));
+      for (int k = 0; k < 8; ++k) {
+        m[k] = m_nx[k];
+        ent[k] = ent_nx[k];
+        inb[k] = m[k].x >= 0;
+        if (!inb[k]) m[k] = make_int4(0, 0, 1, 0);           // any readable row; masked below
       }
       float4 xv[8], hv[8];
 #pragma unroll
@@ -205,18 +231,22 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
         if (e < 0) xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!inb[k]) hv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      fetch_index(j + 1);
       // GEMM1 of the previous tile has read the stage
 #ifdef IGN_BWD_PROFILE
       if (__float_as_uint(xv[0].x + hv[0].x + xv[7].x + hv[7].x) == 0x7fc12345u) __nanosleep(1);   // loads landed
 #endif
       PROF(0)
-      if (j > 0) mbar_wait(&bar_acc1[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1);
+      if (j > 0) {
+        mbar_wait(&bar_acc1[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1);
+        mbar_wait(&bar_hfree, (uint32_t)(j - 1) & 1);        // ... and the epilogue has taken h_{t-1} from the h images
+      }
       PROF(1)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int r = (ptid >> 3) + 16 * k;
         store_split(stage, stage + IMG, r, c4, xv[k]);
-        store_split(stage + 2 * IMG, stage + 3 * IMG, r, c4, hv[k]);
+        store_split_exact(stage + 2 * IMG, stage + 3 * IMG, r, c4, hv[k]);
       }
       fence_async_smem();
       __syncwarp();
@@ -299,7 +329,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
     const int64_t warp_row0 = q * 32;                        // first tile row of this warp
     PROF_DECL
     // (dL/dh, h_{t-1}) of this thread's 16 units, prefetched one tile ahead
-    float4 pre_d[4], pre_h[4];
+    float4 pre_d[4];
     int4 mr_next = make_int4(-1, 0, 0, 0);
     auto fetch_meta = [&](int64_t j) {
       const int64_t i = (blockIdx.x + j * G) * ROWS + row;
@@ -309,15 +339,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
       if (mr_next.x < 0 || (dbg & 2)) return;
       const int64_t i = (blockIdx.x + j * G) * ROWS + row;
       const float* dsrc = ((mr_next.z == t + 1) ? d_out + (int64_t)mr_next.x * U : dhs + i * U) + half * 16;
-      const float* hsrc = ((t == 0) ? h0 + (int64_t)mr_next.x * U : h_seq + (int64_t)(mr_next.y + t - 1) * U) + half * 16;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        pre_d[k] = ldg_f4(dsrc + 4 * k);
-        pre_h[k] = ldg_f4(hsrc + 4 * k);
-      }
+      for (int k = 0; k < 4; ++k) pre_d[k] = ldg_f4(dsrc + 4 * k);
     };
 #pragma unroll
-    for (int k = 0; k < 4; ++k) pre_d[k] = pre_h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) pre_d[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     fetch_meta(0);
     fetch_rows(0);
     for (int64_t j = 0; j < my_tiles; ++j) {
@@ -329,13 +355,23 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         dh[4 * k] = pre_d[k].x; dh[4 * k + 1] = pre_d[k].y; dh[4 * k + 2] = pre_d[k].z; dh[4 * k + 3] = pre_d[k].w;
-        hold[4 * k] = pre_h[k].x; hold[4 * k + 1] = pre_h[k].y; hold[4 * k + 2] = pre_h[k].z; hold[4 * k + 3] = pre_h[k].w;
       }
       fetch_meta(j + 1);
       float direct[16];
       PROF(0)
       mbar_wait(&bar_acc1[buf], (uint32_t)(j >> 1) & 1);     // gate pre-activations of the tile are in TMEM
       tc_fence_after();
+      // h_{t-1} of this thread's 16 units = hi + lo of the h operand images (GEMM1 has read them; the producers wait
+      // for bar_hfree before the next tile overwrites them)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int o = row * 128 + (((half * 4 + k) ^ (row & 7)) << 4);
+        const float4 a = *reinterpret_cast<const float4*>(stage + 2 * IMG + o);
+        const float4 b = *reinterpret_cast<const float4*>(stage + 3 * IMG + o);
+        hold[4 * k] = a.x + b.x; hold[4 * k + 1] = a.y + b.y; hold[4 * k + 2] = a.z + b.z; hold[4 * k + 3] = a.w + b.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_hfree);
       PROF(1)
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -431,16 +467,36 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_d2free);
-      if (alive && !(dbg & 4)) {
-        float* xp = d_steps + (int64_t)(mr.y + t) * U + half * 16;
-        float* hp = ((t == 0) ? dh0 + (int64_t)mr.x * U : dhs + i * U) + half * 16;
+      if (!(dbg & 4)) {
+        // [dx | dh] leave through the staging rows of this lane group's two warps (half 0's buffer: dx rows, half 1's:
+        // dh rows; 16-byte pieces XOR-ed by row & 7), then each warp writes one of the two with 8 lanes per 128-byte row
+        unsigned char* buf_x = gstage + (e & 3) * 4096;
+        unsigned char* buf_h = buf_x + 4 * 4096;
+        if (lane == 0) bulk_wait_read();                     // the bulk store of the last G chunk has read the rows
+        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");            // ... in both warps of the pair
 #pragma unroll
-        for (int k = 0; k < 16; k += 4) {
-          st_f4(xp + k, make_float4(__uint_as_float(vx[k]), __uint_as_float(vx[k + 1]), __uint_as_float(vx[k + 2]),
-                                    __uint_as_float(vx[k + 3])));
-          st_f4(hp + k, make_float4(direct[k] + __uint_as_float(vh[k]), direct[k + 1] + __uint_as_float(vh[k + 1]),
-                                    direct[k + 2] + __uint_as_float(vh[k + 2]), direct[k + 3] + __uint_as_float(vh[k + 3])));
+        for (int k = 0; k < 4; ++k) {
+          const int o = lane * 128 + (((half * 4 + k) ^ (lane & 7)) << 4);
+          *reinterpret_cast<float4*>(buf_x + o) = make_float4(__uint_as_float(vx[4 * k]), __uint_as_float(vx[4 * k + 1]),
+                                                               __uint_as_float(vx[4 * k + 2]), __uint_as_float(vx[4 * k + 3]));
+          *reinterpret_cast<float4*>(buf_h + o) =
+              make_float4(direct[4 * k] + __uint_as_float(vh[4 * k]), direct[4 * k + 1] + __uint_as_float(vh[4 * k + 1]),
+                          direct[4 * k + 2] + __uint_as_float(vh[4 * k + 2]), direct[4 * k + 3] + __uint_as_float(vh[4 * k + 3]));
         }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const int64_t dst_row = (half == 0) ? (int64_t)(mr.y + t) : ((t == 0) ? (int64_t)mr.x : i);
+        float* dst_base = (half == 0) ? d_steps : ((t == 0) ? dh0 : dhs);
+        const unsigned char* buf = half == 0 ? buf_x : buf_h;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rr = (lane >> 3) + 4 * k, ch = lane & 7;
+          const long long drow = __shfl_sync(0xffffffffu, (long long)dst_row, rr);
+          const int al = __shfl_sync(0xffffffffu, alive ? 1 : 0, rr);
+          const float4 v = *reinterpret_cast<const float4*>(buf + rr * 128 + ((ch ^ (rr & 7)) << 4));
+          if (al) st_f4(dst_base + drow * U + ch * 4, v);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");            // rows are free for the next tile's G chunks
       }
       PROF(7)
     }
