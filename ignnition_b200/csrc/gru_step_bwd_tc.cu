@@ -530,7 +530,7 @@ constexpr int DW_STAGE = DW_BLOCKS * DIMG;
 constexpr int DW_STAGES = 2;
 constexpr int DW_PROD_WARPS = 16;
 constexpr int DW_PROD_THREADS = 32 * DW_PROD_WARPS;
-constexpr int DW_THREADS = DW_PROD_THREADS + 32;
+constexpr int DW_THREADS = DW_PROD_THREADS;                 // warp 0 also issues the MMAs: 16 warps keep 128 registers
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
     int t, const int* __restrict__ nt, const int* __restrict__ off, const int4* __restrict__ meta,
     const int* __restrict__ steps_T, SrcPtrs srcs, const float* __restrict__ h0, const float* __restrict__ h_seq,
     const float* __restrict__ g_in, int64_t g_rows_bound, float* __restrict__ dK, float* __restrict__ dR,
-    float* __restrict__ dB) {
+    float* __restrict__ dB, int dbg) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar_full[DW_STAGES], bar_free[DW_STAGES], bar_done;
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == DW_PROD_WARPS) tmem_alloc(&tmem_base_s, 128);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
   const int64_t c1 = c0 + per < nchunks ? c0 + per : nchunks;
   const int64_t n_my = c1 > c0 ? c1 - c0 : 0;
 
-  if (warp < DW_PROD_WARPS) {
+  {
     // per 64-row chunk a thread loads two float4 of [x | h] (rows tid / 16 + 32 p, chunk tid % 16) and four of G
     // (rows tid / 32 + 16 p, chunk tid % 32): its G column chunk never changes, so the bias sums stay in registers
     const int ra = tid >> 4, wa = tid & 15;
@@ -611,28 +611,35 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 ca[2], cg[4], na[2], ng[4];
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
+    // rows of chunks i + 1 and i + 2 are in registers while chunk i is split and stored (the loads see ~3 us)
+    float4 ca[2], cg[4], na[2], ng[4], fa[2], fg[4];
     const float* p_next[2] = {nullptr, nullptr};
 #pragma unroll
-    for (int p = 0; p < 2; ++p) na[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < 2; ++p) na[p] = fa[p] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) ng[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < 4; ++p) ng[p] = fg[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n_my > 0) {
       const float* p0[2] = {a_ptr(c0, 0), a_ptr(c0, 1)};
       load(c0, p0, ca, cg);
-      if (n_my > 1) { p_next[0] = a_ptr(c0 + 1, 0); p_next[1] = a_ptr(c0 + 1, 1); }
+      if (n_my > 1) {
+        const float* p1[2] = {a_ptr(c0 + 1, 0), a_ptr(c0 + 1, 1)};
+        load(c0 + 1, p1, na, ng);
+      }
+      if (n_my > 2) { p_next[0] = a_ptr(c0 + 2, 0); p_next[1] = a_ptr(c0 + 2, 1); }
     }
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % DW_STAGES);
-      if (i + 1 < n_my) load(c0 + i + 1, p_next, na, ng);
-      if (i + 2 < n_my) {
-        p_next[0] = a_ptr(c0 + i + 2, 0);
-        p_next[1] = a_ptr(c0 + i + 2, 1);
+      if (i + 2 < n_my) load(c0 + i + 2, p_next, fa, fg);
+      if (i + 3 < n_my) {
+        p_next[0] = a_ptr(c0 + i + 3, 0);
+        p_next[1] = a_ptr(c0 + i + 3, 1);
         if ((wa & 7) == 0) {                                 // the gather is resolved one chunk early: start it now
           if (p_next[0]) prefetch_l2(p_next[0]);
           if (p_next[1]) prefetch_l2(p_next[1]);
         }
-        const int64_t gi = (c0 + i + 2) * RW + rg;
+        const int64_t gi = (c0 + i + 3) * RW + rg;
 #pragma unroll
         for (int p = 0; p < 4; ++p)
           if ((wg & 7) == 0 && gi + 16 * p < n_alive)
@@ -651,13 +658,30 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
         store_split_mn(hi, hi + 4 * DIMG, rg + 16 * p, wg & 7, cg[p]);
         colsum.x += cg[p].x; colsum.y += cg[p].y; colsum.z += cg[p].z; colsum.w += cg[p].w;
       }
-      fence_async_smem();
+      if (!(dbg & 32)) fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[s]);
+      if (warp == 0) {                                       // issue the stage once every warp has stored its part
+        mbar_wait(&bar_full[s], (uint32_t)(i / DW_STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(st);
+          const uint32_t b_hi = sa + 4 * DIMG, b_lo = b_hi + 4 * DIMG;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) ca[p] = na[p];
+          for (int ks = 0; ks < RW / 8; ++ks) {
+            const uint32_t ko = ks * 1024;
+            umma_tf32(tmem_base, umma_desc_mn(sa + ko, DIMG), umma_desc_mn(b_hi + ko, DIMG), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, umma_desc_mn(sa + ko, DIMG), umma_desc_mn(b_lo + ko, DIMG), idesc, 1u);
+          }
+          umma_commit(&bar_free[s]);
+          if (i + 1 == n_my) umma_commit(&bar_done);
+        }
+        __syncwarp();
+      }
 #pragma unroll
-      for (int p = 0; p < 4; ++p) cg[p] = ng[p];
+      for (int p = 0; p < 2; ++p) { ca[p] = na[p]; na[p] = fa[p]; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { cg[p] = ng[p]; ng[p] = fg[p]; }
     }
     if (n_my > 0) {
       // G column c' = q * 32 + gate * 8 + jj holds gate `gate` of unit 8 q + jj (gates: z, r, xh, hh)
@@ -690,32 +714,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
         for (int k = 0; k < 8; ++k) atomicAdd(base + k, __uint_as_float(v[k]));
       }
     }
-  } else {
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
-    for (int64_t i = 0; i < n_my; ++i) {
-      const int s = (int)(i % DW_STAGES);
-      mbar_wait(&bar_full[s], (uint32_t)(i / DW_STAGES) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = smem_u32(smem + (size_t)s * DW_STAGE);
-        const uint32_t b_hi = st + 4 * DIMG, b_lo = b_hi + 4 * DIMG;
-#pragma unroll
-        for (int ks = 0; ks < RW / 8; ++ks) {
-          const uint32_t ko = ks * 1024;
-          umma_tf32(tmem_base, umma_desc_mn(st + ko, DIMG), umma_desc_mn(b_hi + ko, DIMG), idesc, (i > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, umma_desc_mn(st + ko, DIMG), umma_desc_mn(b_lo + ko, DIMG), idesc, 1u);
-        }
-        umma_commit(&bar_free[s]);
-      }
-      __syncwarp();
-    }
-    if (lane == 0 && n_my > 0) umma_commit(&bar_done);
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == DW_PROD_WARPS) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace
@@ -770,7 +772,7 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
     IGN_CHECK_LAUNCH("gru_step_bwd_tc");
     if (g_dbg & 16) continue;
     gru_dw_tc_kernel<<<(unsigned)grid_w, DW_THREADS, smem_w, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, g_rows,
-                                                                    g_bound(num_dst), dK, dR, dB);
+                                                                    g_bound(num_dst), dK, dR, dB, g_dbg);
     IGN_CHECK_LAUNCH("gru_dw_tc");
   }
   return IGN_OK;
