@@ -74,6 +74,7 @@ SIGNATURES = {
     "ign_ingest_adjacency": (_i64, [_p, _int, _p, _p, _p, _p, _p]),
     "ign_ingest_labels": (_i64, [_p, _p]),
     "ign_mul": (_int, [_i64, _p, _p, _p, _p]),
+    "ign_slice_cols": (_int, [_p, _i64, _int, _int, _int, _p, _p]),
     "ign_conv_finish": (_int, [_p, _p, _p, _int, _i64, _int, _p, _p]),
     "ign_axpy": (_int, [_i64, _f, _p, _p, _p]),
 }

@@ -148,9 +148,11 @@ def assemble(samples: Sequence[dict], entities: Sequence[str], features: Sequenc
         b.max_seq[a.name] = int(b.arrays["seq_" + a.name].max()) + 1 if b.n_edges[a.name] else 0
         if a.uses_params:
             # declared tf.int64 then cast to float32 (generate_model.py:149, :454-456): truncation
+            # (a sample without any edge of this adjacency carries no parameter rows, nor the key)
             p = [np.trunc(np.asarray(s["params_" + a.name], dtype=np.float64)).astype(np.float32)
-                 .reshape(len(s["src_" + a.name]), -1) for s in samples]
-            b.arrays["params_" + a.name] = np.ascontiguousarray(np.concatenate(p, axis=0))
+                 .reshape(len(s["src_" + a.name]), -1) for s in samples if len(s["src_" + a.name])]
+            b.arrays["params_" + a.name] = (np.ascontiguousarray(np.concatenate(p, axis=0)) if p
+                                            else np.zeros((0, 1), dtype=np.float32))
     for q in sequences:
         tabs = [position_table(s, q) for s in samples]
         off = np.zeros(len(samples) + 1, dtype=np.int64)

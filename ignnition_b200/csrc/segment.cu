@@ -304,6 +304,25 @@ extern "C" int ign_gather_concat(int n_parts, const float* const* parts, const i
   return IGN_OK;
 }
 
+// out[r, c] = x[r, col0 + c]: the column block of one concatenated input (backward of the concat in ign_gather_concat)
+__global__ void slice_cols_kernel(const float* __restrict__ x, int64_t rows, int ld, int col0, int w, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * w) return;
+  const int64_t r = i / w;
+  const int c = (int)(i % w);
+  out[i] = x[r * ld + col0 + c];
+}
+
+extern "C" int ign_slice_cols(const float* x, int64_t rows, int ld, int col0, int width, float* out, void* stream) {
+  IGN_REQUIRE(rows >= 0 && ld > 0 && col0 >= 0 && width > 0 && col0 + width <= ld, IGN_ERR_INVALID,
+              "IGNNITION: slice_cols: bad shape");
+  if (rows == 0) return IGN_OK;
+  IGN_REQUIRE(x && out, IGN_ERR_INVALID, "IGNNITION: slice_cols: null pointer");
+  slice_cols_kernel<<<(unsigned)ign_cdiv(rows * width, 256), 256, 0, ign_stream(stream)>>>(x, rows, ld, col0, width, out);
+  IGN_CHECK_LAUNCH("slice_cols");
+  return IGN_OK;
+}
+
 extern "C" int ign_axpy(int64_t n, float a, const float* x, float* y, void* stream) {
   IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: axpy: negative size");
   if (n == 0) return IGN_OK;

@@ -456,11 +456,13 @@ class Engine:
             saves.append((prefix, l, x, pre))
         return y
 
-    def _messages(self, p: _MPPlan, k: int, g: DeviceGraph, state: Dict[str, torch.Tensor]):
+    def _messages(self, p: _MPPlan, k: int, g: DeviceGraph, state: Dict[str, torch.Tensor],
+                  tape: Optional[list] = None):
         """Per-edge messages of source k in INPUT edge order, or None for direct_assignation."""
         src = p.mp.source_entities[k]
         a = p.adjs[k]
         msgs = None
+        last = None
         for j, op in enumerate(src.message_formation):
             if op.type != "feed_forward_nn":
                 continue
@@ -473,7 +475,11 @@ class Engine:
                 else:
                     parts.append(g.t["params_" + a.name]); idx.append(None)
             x = ops.gather_concat(parts, idx, g.t["src_" + a.name].numel())
-            msgs = self._run_ff("%s_to_%s_message_creation_%d" % (src.name, p.dst, j), op.model, x)
+            saves = [] if tape is not None else None
+            msgs = self._run_ff("%s_to_%s_message_creation_%d" % (src.name, p.dst, j), op.model, x, saves)
+            last = (list(op.input), [int(t.shape[1]) for t in parts], saves)
+        if tape is not None and last is not None:       # only the last network's output is the message (:470-475)
+            tape.append(("msg_ff", p, k) + last)
         return msgs
 
     def _mp_forward(self, p: _MPPlan, g: DeviceGraph, state: Dict[str, torch.Tensor], tape: Optional[list]):
@@ -484,11 +490,11 @@ class Engine:
         R = self.param(dst + "_update/recurrent_kernel") if K is not None else None
         B = self.param(dst + "_update/bias") if K is not None else None
         out = torch.empty_like(h)
-        msgs = [self._messages(p, k, g, state) for k in range(len(p.adjs))]
-        if tape is not None and any(m is not None for m in msgs):
-            raise RuntimeError("IGNNITION: training through message neural networks is not built")
-        if tape is not None and p.kind == "agg_ff":
-            raise RuntimeError("IGNNITION: training through a feed-forward update is not built")
+        msgs = [self._messages(p, k, g, state, tape) for k in range(len(p.adjs))]
+        has_msg = [m is not None for m in msgs]
+        if tape is not None and any(has_msg) and p.kind == "seq_gru":
+            raise RuntimeError("IGNNITION: training through message neural networks that feed an ordered "
+                               "aggregation is not built")
 
         if p.kind == "seq_gru":
             rowptr_s, steps = g.steps[p.key]
@@ -522,7 +528,7 @@ class Engine:
             agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
             ops.agg_gru_cell(rowptr, col, state[p.adjs[0].src], h, K, R, B, out=out, agg_out=agg)
             if tape is not None:
-                tape.append(("agg_gru", p, state[p.adjs[0].src], h, agg))
+                tape.append(("agg_gru", p, has_msg, h, agg))
             return out
         agg = None
         if p.attn:      # Attention_aggr (auxilary_classes.py:278-344)
@@ -559,15 +565,16 @@ class Engine:
         if p.kind == "agg_gru":
             ops.gru_cell(agg, h, K, R, B, out=out)
             if tape is not None:
-                tape.append(("agg_gru_unfused", p, [state[a.src] for a in p.adjs], h, agg))
+                tape.append(("agg_gru_unfused", p, has_msg, h, agg))
             return out
         x = ops.gather_concat([agg, h], [None, None], n_dst)          # FF update, generate_model.py:599
         ff = p.mp.update.model
         layers = FeedForward(list(ff.layers))
-        return self._run_ff_last_units(dst + "_ff_update", layers, x)
-
-    def _run_ff_last_units(self, prefix, ff, x):
-        return self._run_ff(prefix, ff, x)
+        saves = [] if tape is not None else None
+        y = self._run_ff(dst + "_ff_update", layers, x, saves)
+        if tape is not None:
+            tape.append(("agg_ff", p, has_msg, int(agg.shape[1]), saves))
+        return y
 
     @staticmethod
     def _fusable(f_in: int, units: int) -> bool:

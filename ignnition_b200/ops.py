@@ -364,6 +364,15 @@ def axpy(a: float, x, y):
     _lib.check(lib.ign_axpy(x.numel(), a, _f(x), _f(y), _stream()), "axpy")
 
 
+def slice_cols(x, col0: int, width: int, out=None):
+    lib = _lib.load()
+    rows, ld = x.shape
+    if out is None:
+        out = torch.empty(rows, width, dtype=torch.float32, device=x.device)
+    _lib.check(lib.ign_slice_cols(_f(x), rows, ld, col0, width, _f(out), _stream()), "slice_cols")
+    return out
+
+
 def mul(a, b, out=None):
     lib = _lib.load()
     if out is None:

@@ -95,9 +95,11 @@ class Trainer:
                     for a in p.adjs:
                         if a.name in graph.csr_t:
                             continue
-                        rp, col_t, _, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name], None,
-                                                        graph.num[a.src], ops.CSR_SORT)
-                        graph.csr_t[a.name] = (rp, col_t)
+                        # perm (edge position per slot) only where per-edge rows are reduced: message networks
+                        rp, col_t, perm_t, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name], None,
+                                                             graph.num[a.src], ops.CSR_SORT,
+                                                             want_perm=a.name in e._needs_perm)
+                        graph.csr_t[a.name] = (rp, col_t, perm_t)
 
     # ------------------------------------------------------------------ backward
     def backward(self, graph, tape: list, d_pred: torch.Tensor):
@@ -111,9 +113,57 @@ class Trainer:
             else:
                 ops.axpy(1.0, contrib, gstate[ent])
 
+        pending: Dict[tuple, torch.Tensor] = {}          # (mp key, source) -> dL/d(per-edge message), input edge order
+
+        def dense_chain_bwd(saves, dy):
+            for prefix, layer, x, pre in reversed(saves):
+                w = e.param("%s/%s/kernel" % (prefix, layer.name))
+                dw = self.g("%s/%s/kernel" % (prefix, layer.name))
+                db = self.g("%s/%s/bias" % (prefix, layer.name)) if layer.use_bias else None
+                dx = torch.empty_like(x)
+                ops.dense_bwd(x, w, e._act(layer.activation), pre, dy, dx, dw, db)
+                dy = dx
+            return dy
+
+        def route_aggregate_grad(p, has_msg, d_agg):
+            """dL/d(sum of messages per destination) -> source states, or -> per-edge messages of a message network"""
+            for k, a in enumerate(p.adjs):
+                if has_msg[k]:       # every edge's message received d_agg of its destination
+                    pending[(p.key, k)] = ops.gather_concat([d_agg], [graph.t["dst_" + a.name]],
+                                                            int(graph.t["dst_" + a.name].numel()))
+                else:
+                    rp_t, col_t, _ = graph.csr_t[a.name]
+                    add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, col_t, d_agg))
+
         for entry in reversed(tape):
             kind = entry[0]
-            if kind == "readout":
+            if kind == "msg_ff":
+                _, p, k, inputs, widths, saves = entry
+                dy = pending.pop((p.key, k), None)
+                if dy is None:
+                    continue
+                a = p.adjs[k]
+                dx = dense_chain_bwd(saves, dy)                   # [E, sum(widths)], input edge order
+                off = 0
+                for name, w_ in zip(inputs, widths):
+                    if name == "hs_source":                       # rows gathered by src index: reduce per source row
+                        rp_t, _, perm_t = graph.csr_t[a.name]
+                        add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, ops.slice_cols(dx, off, w_)))
+                    elif name == "hs_dest":                       # rows gathered by dst index: reduce per destination
+                        rowptr, _, perm = graph.csr[a.name]
+                        add_grad(p.dst, ops.segment_reduce(ops.OP_SUM, rowptr, perm, ops.slice_cols(dx, off, w_)))
+                    off += w_                                     # edge_params are inputs, not variables
+            elif kind == "agg_ff":
+                _, p, has_msg, msg_dim, saves = entry
+                if p.op != ops.OP_SUM:
+                    raise RuntimeError("IGNNITION: training through mean/max aggregation is not built")
+                g_new = gstate[p.dst]
+                if g_new is None:
+                    continue
+                dx = dense_chain_bwd(saves, g_new)                # [n, msg_dim + hidden]: concat([agg, h], 1)
+                gstate[p.dst] = ops.slice_cols(dx, msg_dim, dx.shape[1] - msg_dim)
+                route_aggregate_grad(p, has_msg, ops.slice_cols(dx, 0, msg_dim))
+            elif kind == "readout":
                 _, op, saves = entry
                 dy = d_pred
                 for prefix, layer, x, pre in reversed(saves):
@@ -152,7 +202,7 @@ class Trainer:
                     rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]
                     add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_steps))
             elif kind in ("agg_gru", "agg_gru_unfused"):
-                _, p, src_state, h_old, agg = entry
+                _, p, has_msg, h_old, agg = entry
                 if p.op != ops.OP_SUM:
                     raise RuntimeError("IGNNITION: training through mean/max aggregation is not built")
                 g_new = gstate[p.dst]
@@ -165,9 +215,7 @@ class Trainer:
                                  g_new, d_agg, dh, self.g(p.dst + "_update/kernel"),
                                  self.g(p.dst + "_update/recurrent_kernel"), self.g(p.dst + "_update/bias"))
                 gstate[p.dst] = dh
-                for a in p.adjs:
-                    rp_t, col_t = graph.csr_t[a.name]
-                    add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, col_t, d_agg))
+                route_aggregate_grad(p, has_msg, d_agg)
             else:
                 raise RuntimeError("IGNNITION: training through '%s' is not built" % kind)
 

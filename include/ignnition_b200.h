@@ -293,6 +293,11 @@ int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const flo
 int ign_partner_index(const int32_t* rowptr0, const int32_t* rowptr1, const int32_t* idx1, int64_t num_dst,
                       int32_t* out, void* stream);
 
+/* out[rows, width] = x[:, col0 : col0 + width] of a row-major [rows, ld] matrix: the gradient of one input of
+ * the concat at generate_model.py:465 / :599 (backward of ign_gather_concat; the caller reduces gathered
+ * parts per row with ign_segment_reduce). */
+int ign_slice_cols(const float* x, int64_t rows, int ld, int col0, int width, float* out, void* stream);
+
 /* Product_operation 'element_wise' (auxilary_classes.py:1085-1086): out = a * b. */
 int ign_mul(int64_t n, const float* a, const float* b, float* out, void* stream);
 

@@ -380,6 +380,9 @@ class Oracle:
                         parts.append(dst_messages)
                     elif i == "edge_params":
                         # declared tf.int64 then cast (generate_model.py:149, :454-456): truncation
+                        if len(src_idx) == 0:            # a sample without edges carries no parameter rows
+                            parts.append(np.zeros((0, int(self.dims.get(src["adj_vector"], 0))), dtype=dt))
+                            continue
                         p = np.asarray(inp["params_" + src["adj_vector"]])
                         parts.append(np.trunc(p).astype(dt).reshape(len(src_idx), -1))
                     else:

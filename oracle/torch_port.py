@@ -3,8 +3,9 @@
 The same op-for-op restatement of ``ComnetModel.call`` as ``oracle/ignnition_oracle.py`` (dense
 right-padded message tensor, masked RNN, Keras GRU / Dense / SELU formulas), written on torch CPU
 tensors so that ``torch.autograd`` gives the reference for ``tf.gradients(total_loss, variables)``
-(``code/utils/generate_model.py:791``).  Covers what the BASELINE configs train: direct_assignation
-messages, sum / ordered / interleave aggregation, GRU update, Dense readout.  Cross-checked against
+(``code/utils/generate_model.py:791``).  Covers what the BASELINE configs train (direct_assignation
+messages, sum / ordered / interleave aggregation, GRU update, Dense readout) plus message neural networks on
+``hs_source | hs_dest | edge_params`` (:440-475) and the feed-forward update (:594-600).  Cross-checked against
 the NumPy oracle in ``tests/test_host.py``.  float parity vs TensorFlow itself is unpinned (see the
 NumPy oracle's header).
 """
@@ -43,6 +44,17 @@ def gru_cell(x, h, K, R, b):
     return z * h + (1 - z) * hh
 
 
+def dense_stack(x, layers, prefix, w):
+    """Keras functional Model of Dense layers (auxilary_classes.py:918-975) on torch tensors."""
+    for l in layers:
+        x = x @ w[prefix + "/" + l["name"] + "/kernel"]
+        if (prefix + "/" + l["name"] + "/bias") in w:
+            x = x + w[prefix + "/" + l["name"] + "/bias"]
+        a = l.get("activation")
+        x = _act(None if a == "None" else a, x)
+    return x
+
+
 class TorchOracle:
     def __init__(self, model_json: dict, dims: Dict[str, int], dtype=torch.float64):
         self.np_oracle = Oracle(model_json, dims, dtype=np.float64)
@@ -78,13 +90,32 @@ class TorchOracle:
         agg = mp["aggregation"]["type"]
         blocks, lens_all, idx_all = [], [], []
         for src in mp["source_entities"]:
-            if any(op["type"] != "direct_assignation" for op in src["message"]):
-                raise ValueError("torch oracle: message neural networks are not restated here")
             src_idx = torch.as_tensor(np.asarray(inp["src_" + src["adj_vector"]], dtype=np.int64))
             dst_idx = torch.as_tensor(np.asarray(inp["dst_" + src["adj_vector"]], dtype=np.int64))
             seq = torch.as_tensor(np.asarray(inp["seq_" + src["name"] + "_" + dst], dtype=np.int64))
             msgs = state[src["name"]][src_idx]                                   # tf.gather
-            max_len = int(seq.max()) + 1
+            src_messages, dst_messages = msgs, state[dst][dst_idx]
+            for k, op in enumerate(src["message"]):                              # generate_model.py:440-475
+                if op["type"] != "neural_network":
+                    continue
+                parts = []
+                for i in op["input"]:
+                    if i == "hs_source":
+                        parts.append(src_messages)
+                    elif i == "hs_dest":
+                        parts.append(dst_messages)
+                    elif i == "edge_params":                                     # int64 then cast: truncation (:149)
+                        if len(src_idx) == 0:                                    # no edges: no parameter rows
+                            parts.append(torch.zeros(0, int(self.np_oracle.dims.get(src["adj_vector"], 0)), dtype=dt))
+                            continue
+                        pr = np.trunc(np.asarray(inp["params_" + src["adj_vector"]], dtype=np.float64))
+                        parts.append(torch.tensor(pr.reshape(len(src_idx), -1), dtype=dt))
+                    else:
+                        raise ValueError("torch oracle: named message inputs are broken in the reference")
+                msgs = dense_stack(torch.cat(parts, dim=1),
+                                   self.np_oracle.layer_names(op["nn_name"], "message_creation_%d" % k),
+                                   "%s_to_%s_message_creation_%d" % (src["name"], dst, k), w)
+            max_len = int(seq.max()) + 1 if len(seq) else 0
             s = torch.zeros(num_dst, max_len, msgs.shape[1], dtype=dt).index_put((dst_idx, seq), msgs)  # scatter_nd
             blocks.append(s)
             lens_all.append(torch.bincount(dst_idx, minlength=num_dst))
@@ -92,8 +123,13 @@ class TorchOracle:
                 idx_all.append(np.asarray(inp["indices_" + src["name"] + "_to_" + dst], dtype=np.int64))
         src_input = torch.cat(blocks, dim=1)
         final_len = sum(lens_all)
-        K, R, b = w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"], w[dst + "_update/bias"]
         h = state[dst]
+        if mp["update"]["type"] != "recurrent_neural_network":                  # feed-forward update (:594-600)
+            if agg != "sum":
+                raise ValueError("torch oracle: feed-forward update is restated for the sum aggregation")
+            ls = self.np_oracle.layer_names(mp["update"]["nn_name"], "update")
+            return dense_stack(torch.cat([src_input.sum(dim=1), h], dim=1), ls, dst + "_ff_update", w)
+        K, R, b = w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"], w[dst + "_update/bias"]
         if agg == "sum":
             return gru_cell(src_input.sum(dim=1), h, K, R, b)
         if agg == "interleave":

@@ -86,3 +86,55 @@ def test_training_unsupported_shapes_fail_loudly():
     b = torch.zeros(2, 192, device="cuda")
     with pytest.raises(RuntimeError, match="IGNNITION.*backward pass is built for"):
         ops.gru_cell_bwd(z, z, w, w, b, z, z.clone(), z.clone(), w.clone(), w.clone(), b.clone())
+
+
+@pytest.mark.parametrize("update,message_nn", [("gru", True), ("ff", False), ("ff", True)])
+def test_gradients_message_network_and_ff_update(update, message_nn):
+    """tf.gradients through the message neural network on [hs_source | hs_dest | edge_params]
+    (generate_model.py:440-475) and through the feed-forward update (:594-600; semantics of call) vs fp64 autograd
+    on the differentiable oracle: every variable's gradient, batch of three samples incl. a one-node graph."""
+    from test_gpu_model import _mpnn_json, _mpnn_sample, make, tensors_of
+    from ignnition_b200.generator import sample_dimensions
+    from ignnition_b200.train import Trainer
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(7 + len(update) + int(message_nn))
+    model_json = _mpnn_json("sum", 32, update, message_nn)
+    samples = [_mpnn_sample(rng, n, 6, params=message_nn) for n in (40, 1, 300)]
+    dims = sample_dimensions(samples[0])
+    md, eng, o64, w = make(model_json, dims)
+    both = [tensors_of(md, s) for s in samples]
+    tens, labels = [b[0] for b in both], [np.asarray(b[1], np.float32) for b in both]
+    tr = Trainer(eng)
+    graph = eng.prepare(tens, labels=labels, training=True)
+    pred, n_local = tr.loss_and_grads(graph)
+    for name, lam in eng._reg.items():
+        ops.l2_reg(eng.param(name), lam, tr.g(name), tr.scalars[1:2])
+    mse, reg, p_ref, grads = TorchOracle(model_json, dims).loss_and_grads(tens, labels, w)
+    assert rel_err(pred.cpu().numpy().reshape(-1), p_ref) < 1e-5
+    sc = tr.scalars.cpu().numpy()
+    assert abs(sc[0] / n_local - mse) <= 1e-5 * abs(mse)
+    got = tr.grads.cpu().numpy()
+    assert any(n.startswith("node_to_node_message_creation") for n in eng.param_table) == message_nn
+    for name, (off, shape) in eng.param_table.items():
+        gn = got[off:off + int(np.prod(shape))].reshape(shape)
+        assert rel_err(gn, grads[name]) < GRAD_RTOL_SELU_KINK, name
+
+
+def test_training_unbuilt_paths_fail_loudly():
+    """paths whose backward pass does not exist raise instead of dropping gradients"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample, make, tensors_of
+    from ignnition_b200.generator import sample_dimensions
+    from ignnition_b200.train import Trainer
+    rng = np.random.RandomState(3)
+    for agg, msg in (("mean", False), ("ordered", True)):
+        model_json = _mpnn_json(agg, 32, "gru", msg)
+        samples = [_mpnn_sample(rng, 30, 4, params=msg)]
+        for s in samples:
+            for v in s["entities"]:
+                s["adj"].setdefault(v, [[v, [1.0, 2.0]]] if msg else [v])
+        dims = sample_dimensions(samples[0])
+        md, eng, o64, w = make(model_json, dims)
+        t, y = tensors_of(md, samples[0])[:2]
+        graph = eng.prepare([t], labels=[np.asarray(y, np.float32)], training=True)
+        with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
+            Trainer(eng).loss_and_grads(graph)
