@@ -590,16 +590,25 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
     const int ra = tid >> 4, wa = tid & 15;
     const int rg = tid >> 5, wg = tid & 31;
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto a_ptr = [&](int64_t chunk, int p) -> const float* {
+    // the gather is two loads deep (step entry / meta -> row): the raw indices of a chunk are fetched one iteration
+    // before its row pointers are formed, so no iteration waits on a load it has just issued
+    struct RawIdx { int a, b; };                             // x part: (entry, -); h part: (destination, first step)
+    auto fetch_raw = [&](int64_t chunk, int p) -> RawIdx {
       const int64_t i = chunk * RW + ra + 32 * p;
-      if (i >= n_alive) return nullptr;
-      if (wa < 8) {
-        const int e = __ldg(entries + i);
-        return e >= 0 ? pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U + wa * 4 : nullptr;
+      RawIdx r{IGN_STEP_ZERO, -1};
+      if (chunk < c1 && i < n_alive) {
+        if (wa < 8) r.a = __ldg(entries + i);
+        else { const int4 m = __ldg(meta + i); r.a = m.x; r.b = m.y; }
       }
-      const int4 m = __ldg(meta + i);
-      return ((t == 0) ? h0 + (int64_t)m.x * U : h_seq + (int64_t)(m.y + t - 1) * U) + (wa - 8) * 4;
+      return r;
     };
+    auto make_ptr = [&](const RawIdx& r) -> const float* {
+      if (wa < 8)
+        return r.a >= 0 ? pick_src(srcs, r.a >> IGN_STEP_SRC_SHIFT) + (int64_t)(r.a & IGN_STEP_ROW_MASK) * U + wa * 4 : nullptr;
+      if (r.b < 0) return nullptr;
+      return ((t == 0) ? h0 + (int64_t)r.a * U : h_seq + (int64_t)(r.b + t - 1) * U) + (wa - 8) * 4;
+    };
+    auto a_ptr = [&](int64_t chunk, int p) -> const float* { return make_ptr(fetch_raw(chunk, p)); };
     auto load = [&](int64_t chunk, const float* const (&ap)[2], float4 (&va)[2], float4 (&vg)[4]) {
 #pragma unroll
       for (int p = 0; p < 2; ++p) va[p] = ap[p] ? ldg_f4(ap[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -629,12 +638,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
       }
       if (n_my > 2) { p_next[0] = a_ptr(c0 + 2, 0); p_next[1] = a_ptr(c0 + 2, 1); }
     }
+    RawIdx raw_next[2] = {fetch_raw(c0 + 3, 0), fetch_raw(c0 + 3, 1)};
     for (int64_t i = 0; i < n_my; ++i) {
       const int s = (int)(i % DW_STAGES);
       if (i + 2 < n_my) load(c0 + i + 2, p_next, fa, fg);
       if (i + 3 < n_my) {
-        p_next[0] = a_ptr(c0 + i + 3, 0);
-        p_next[1] = a_ptr(c0 + i + 3, 1);
+        p_next[0] = make_ptr(raw_next[0]);
+        p_next[1] = make_ptr(raw_next[1]);
+        raw_next[0] = fetch_raw(c0 + i + 4, 0);
+        raw_next[1] = fetch_raw(c0 + i + 4, 1);
         if ((wa & 7) == 0) {                                 // the gather is resolved one chunk early: start it now
           if (p_next[0]) prefetch_l2(p_next[0]);
           if (p_next[1]) prefetch_l2(p_next[1]);
