@@ -428,6 +428,24 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
 
     zero = lambda *a, **kw: 0
 
+    def b_seq_bwd_steps(plan, meta, max_steps, srcs, h0, h_seq, *a, **kw):
+        # per step: x, h, dL/dh gathered, dx and dL/dh written (5 rows), G (4 rows) written and read once, [x | h]
+        # read again by the weight-gradient kernel
+        E, F = h_seq.shape[0], h0.shape[1]
+        return E * (5 * 4 * F + 2 * 16 * F + 8 * F)
+
+    def b_seq_bwd(steps_rowptr, steps, order, srcs, h0, h_seq, *a, **kw):
+        E, F = steps.numel(), h0.shape[1]
+        return E * 5 * 4 * F
+
+    def b_dense_bwd(x, w, act, pre_act, dy, dx, dw, db):
+        m, k = x.shape
+        n = w.shape[1]                       # dZ in place (r + w, pre-activation read), dX written, X and dZ read for dW
+        return 4 * m * ((3 * n if pre_act is not None else 0) + n + (k if dx is not None else 0) + k + n)
+
+    def b_gru_cell_bwd(x, h, *a, **kw):
+        return 4 * (2 * x.numel() + 3 * h.numel())
+
     def b_mlp_head(x, w1, b1, act1, w2, b2, act2, w3, b3, *a, **kw):
         return 4 * (x.numel() + x.shape[0] + w1.numel() + w2.numel())      # x in, one float per row out
 
@@ -442,7 +460,8 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
                      ("mlp_head", b_mlp_head), ("dense_head", b_dense_head), ("init_state", b_init),
                      ("length_order", zero), ("seq_meta", zero), ("steps_build", zero),
                      ("gru_seq_steps", zero), ("seq_step_plan", zero),
-                     ("gru_seq_bwd", zero), ("gru_seq_bwd_steps", zero), ("gru_cell_bwd", zero), ("dense_bwd", zero)):
+                     ("gru_seq_bwd", b_seq_bwd), ("gru_seq_bwd_steps", b_seq_bwd_steps),
+                     ("gru_cell_bwd", b_gru_cell_bwd), ("dense_bwd", b_dense_bwd)):
         wrap(name, fn)
     try:
         for _ in range(max(1, min(reps, 3))):
