@@ -201,6 +201,179 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined variant for large M (the train step's readout layers and their dX): the same math, warp-specialised
+// so that nothing waits on a CTA-wide barrier inside the tile loop:
+//   warps 0-3   A producers: x chunk [128 rows x 32] -> hi / lo images of the stage (next job's rows already in
+//               registers), arrive on full[stage]
+//   warp  4     TMA producer: the prepared weight chunk (hi + lo, 2 N 128 bytes) as one cp.async.bulk per job
+//   warp  5     MMA issuer: 12 tcgen05.mma per job, commit -> stage_free[stage]; last chunk of a tile -> acc_full[buf]
+//   warps 8-15  epilogue of the PREVIOUS tile (two TMEM accumulators): tcgen05.ld -> bias -> (pre) -> activation ->
+//               32-column chunks through a per-warp staging block so that 8 lanes write each 128-byte row segment
+// N % 64 == 0, N <= 256.
+constexpr int P_PROD_WARPS = 4, P_TMA_WARP = 4, P_MMA_WARP = 5, P_EPI_WARP0 = 8, P_EPI_WARPS = 8;
+constexpr int P_THREADS = 32 * (P_EPI_WARP0 + P_EPI_WARPS);
+constexpr int P_STAGING = P_EPI_WARPS * 4096;
+
+template <int ACT>
+__global__ void __launch_bounds__(P_THREADS, 1) dense_pipe_tc_kernel(const float* __restrict__ x, int64_t M, int K,
+                                                                     const float* __restrict__ wimg,
+                                                                     const float* __restrict__ bias, int N, int act_,
+                                                                     float* __restrict__ y, float* __restrict__ pre,
+                                                                     int nst, int tmem_cols) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int act = ACT >= 0 ? ACT : act_;
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_img = N * 128;
+  const int stage_bytes = 2 * A_IMG + 2 * b_img;
+  unsigned char* staging = smem + (size_t)nst * stage_bytes;
+  __shared__ uint64_t bar_full[4], bar_b[4], bar_free[4], bar_acc_full[2], bar_acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&bar_full[s], P_PROD_WARPS);
+      mbar_init(&bar_b[s], 1);
+      mbar_init(&bar_free[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_acc_full[b], 1);
+      mbar_init(&bar_acc_free[b], P_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == P_MMA_WARP) tmem_alloc(&tmem_base_s, (uint32_t)tmem_cols);
+  if (tid < N) s_bias[tid] = bias ? bias[tid] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int acc_stride = tmem_cols / 2;
+  const int nchunks = K / TC_KC;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t njobs = my_tiles * nchunks;
+
+  if (warp < P_PROD_WARPS) {
+    // ================================ A producers ================================
+    const int r0 = tid >> 3, c4 = tid & 7;                   // rows r0 + 16 k
+    float4 cur[8], nxt[8];
+    auto load = [&](int64_t job, float4 (&v)[8]) {
+      const int64_t m0 = (blockIdx.x + (job / nchunks) * gridDim.x) * TC_M;
+      const int c = (int)(job % nchunks);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int64_t r = m0 + r0 + 16 * k;
+        v[k] = r < M ? ld_stream_f4(x + r * K + c * TC_KC + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (njobs > 0) load(0, cur);
+    for (int64_t job = 0; job < njobs; ++job) {
+      const int s = (int)(job % nst);
+      if (job + 1 < njobs) load(job + 1, nxt);
+      if (job >= nst) mbar_wait(&bar_free[s], (uint32_t)((job / nst) - 1) & 1);
+      unsigned char* st = smem + (size_t)s * stage_bytes;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) store_split(st, st + A_IMG, r0 + 16 * k, c4, cur[k]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[s]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+    }
+  } else if (warp == P_TMA_WARP) {
+    // ================================ weight chunks ================================
+    if (lane == 0) {
+      const uint32_t bytes = 2u * (uint32_t)b_img;
+      for (int64_t job = 0; job < njobs; ++job) {
+        const int s = (int)(job % nst);
+        if (job >= nst) mbar_wait(&bar_free[s], (uint32_t)((job / nst) - 1) & 1);
+        mbar_expect_tx(&bar_b[s], bytes);
+        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * A_IMG,
+                 reinterpret_cast<const char*>(wimg) + (size_t)(job % nchunks) * bytes, bytes, &bar_b[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == P_MMA_WARP) {
+    // ================================ MMA issuer ================================
+    for (int64_t job = 0; job < njobs; ++job) {
+      const int s = (int)(job % nst);
+      const int64_t tl = job / nchunks;                      // index of the tile among this CTA's tiles
+      const int c = (int)(job % nchunks), buf = (int)(tl & 1);
+      const uint32_t ph = (uint32_t)(job / nst) & 1;
+      mbar_wait(&bar_full[s], ph);
+      mbar_wait(&bar_b[s], ph);
+      if (c == 0 && tl >= 2) mbar_wait(&bar_acc_free[buf], (uint32_t)((tl >> 1) - 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), b_hi = a_hi + 2 * A_IMG;
+        umma_chunk_3x(tmem_base + buf * acc_stride, a_hi, a_hi + A_IMG, b_hi, b_hi + b_img, N, c > 0);
+        umma_commit(&bar_free[s]);
+        if (c == nchunks - 1) umma_commit(&bar_acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= P_EPI_WARP0) {
+    // ================================ epilogue ================================
+    const int e = warp - P_EPI_WARP0, q = warp & 3, half = e >> 2;
+    unsigned char* my_stage = staging + e * 4096;
+    const int ncol_half = N / 2;
+    // one 32-column chunk of this warp's 32 rows -> global, 8 lanes per 128-byte row segment
+    auto emit = [&](const float (&v)[32], float* __restrict__ dst, int64_t m0, int col0) {
+      __syncwarp();
+      unsigned char* srow = my_stage + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(srow + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int rr = (lane >> 3) + 4 * k, ch = lane & 7;
+        const int64_t grow = m0 + q * 32 + rr;
+        const float4 val = *reinterpret_cast<const float4*>(my_stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        if (grow < M) st_f4(dst + grow * N + col0 + ch * 4, val);
+      }
+    };
+    for (int64_t tl = 0; tl < my_tiles; ++tl) {
+      const int buf = (int)(tl & 1);
+      const int64_t m0 = (blockIdx.x + tl * gridDim.x) * TC_M;
+      mbar_wait(&bar_acc_full[buf], (uint32_t)(tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tb = tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16);
+      for (int cb = 0; cb < ncol_half; cb += 32) {
+        const int col0 = half * ncol_half + cb;
+        uint32_t ra[16], rb[16];
+        tmem_ld16_nowait(tb + col0, ra);
+        tmem_ld16_nowait(tb + col0 + 16, rb);
+        tmem_ld_wait();
+        if (cb + 32 >= ncol_half) {                          // the accumulator has been read: free for the tile after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_free[buf]);
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = __uint_as_float(ra[i]) + s_bias[col0 + i];
+          v[16 + i] = __uint_as_float(rb[i]) + s_bias[col0 + 16 + i];
+        }
+        if (pre) emit(v, pre, m0, col0);
+        if (y) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_epi(act, v[i]);
+          emit(v, y, m0, col0);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == P_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
 }  // namespace
 
 // true when the tensor-core path is built for this shape
@@ -222,6 +395,33 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   const int64_t tiles = ign_cdiv(m, TC_M);
   const int grid = (int)(tiles < sms ? tiles : sms);
   if (head_out) IGN_CUDA(cudaMemsetAsync(head_out, 0, (size_t)m * sizeof(float), st));
+  if (!head_out && n % 64 == 0 && m >= 4096) {
+    // large M: the warp-specialised pipeline (two accumulators, weight chunks by TMA, staged coalesced stores)
+    const size_t stage_bytes = 2 * (size_t)A_IMG + 2 * (size_t)n * 128;
+    int nst = (int)((227 * 1024 - 1024 - 2048 - (size_t)P_STAGING) / stage_bytes);
+    if (nst > 4) nst = 4;
+    if (nst >= 2) {
+      const size_t psmem = 1024 + (size_t)nst * stage_bytes + P_STAGING;
+      int pcols = 64;
+      while (pcols < 2 * n) pcols <<= 1;
+      auto plaunch = [&](auto kernel) -> int {
+        IGN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        kernel<<<grid, P_THREADS, psmem, st>>>(x, m, k, img, bias, n, act, y, pre_act, nst, pcols);
+        return IGN_OK;
+      };
+      int prc;
+      switch (act) {
+        case IGN_ACT_LINEAR: prc = plaunch(dense_pipe_tc_kernel<IGN_ACT_LINEAR>); break;
+        case IGN_ACT_RELU: prc = plaunch(dense_pipe_tc_kernel<IGN_ACT_RELU>); break;
+        case IGN_ACT_SELU: prc = plaunch(dense_pipe_tc_kernel<IGN_ACT_SELU>); break;
+        case IGN_ACT_TANH: prc = plaunch(dense_pipe_tc_kernel<IGN_ACT_TANH>); break;
+        default: prc = plaunch(dense_pipe_tc_kernel<-1>); break;
+      }
+      if (prc != IGN_OK) return prc;
+      IGN_CHECK_LAUNCH("dense_pipe_tc");
+      return IGN_OK;
+    }
+  }
   auto launch = [&](auto kernel) -> int {
     IGN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols, head_w, head_b, head_out);

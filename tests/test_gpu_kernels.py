@@ -339,7 +339,10 @@ def test_gru_seq_interleave_step_table(golden):
 @pytest.mark.parametrize("tensor_cores", [True, False])
 @pytest.mark.parametrize("m,k,n,act", [(1, 32, 256, "selu"), (1000, 32, 256, "selu"), (777, 256, 256, "relu"),
                                        (5000, 256, 1, None), (130, 65, 20, "tanh"), (300, 7, 3, "sigmoid"),
-                                       (128, 32, 32, None), (40000, 64, 96, "selu"), (2049, 256, 128, "tanh")])
+                                       (128, 32, 32, None), (40000, 64, 96, "selu"), (2049, 256, 128, "tanh"),
+                                       # M >= 4096 and N % 64 == 0: the warp-specialised pipeline (dense_pipe_tc_kernel)
+                                       (5003, 256, 256, "selu"), (4097, 32, 64, "tanh"), (9000, 96, 192, "relu"),
+                                       (4500, 64, 128, None), (20000, 32, 256, "selu")])
 def test_dense(m, k, n, act, tensor_cores):
     """tensor_cores=True: 3xTF32 on tcgen05 where the shape is built (K % 32 == 0, N % 32 == 0, M >= 128),
     else the fp32 CUDA-core kernel; both must meet the fp32 parity bar."""

@@ -63,6 +63,8 @@ if prof is not None:
     import ctypes as C
     buf = (C.c_ulonglong * 16)()
     prof(buf, 1)
+    if dbg is not None:
+        dbg(int(os.environ.get("IGN_PROF_FLAGS", "0")))      # phase profile under an ablation
     step()
     torch.cuda.synchronize()
     prof(buf, 0)
