@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const float* __res
           tmem_ld_wait();
           const int mt = col / C::N, n0 = col % C::N;
           float* dst = dw + (int64_t)(mt * 128 + f) * C::N + n0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          red_add_v4(dst, __uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          red_add_v4(dst + 4, __uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
         }
       }
     }

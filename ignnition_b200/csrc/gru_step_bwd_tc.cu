@@ -579,7 +579,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
   const int64_t n_alive = (int64_t)__ldg(nt + t);
   const int* entries = steps_T + __ldg(off + t);
   const int64_t nchunks = (n_alive + RW - 1) / RW;
-  const int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  // at least 32 chunks (2048 rows) per CTA: a short step must not pay 148 accumulator flushes (12 k reductions each)
+  int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
+  if (per < 32) per = 32;
   const int64_t c0 = (int64_t)blockIdx.x * per;
   const int64_t c1 = c0 + per < nchunks ? c0 + per : nchunks;
   const int64_t n_my = c1 > c0 ? c1 - c0 : 0;
@@ -722,8 +724,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
         tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + qc * U + gate * 8, v);
         tmem_ld_wait();
         float* base = wrow + (gate == 3 ? 2 : gate) * U;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(base + k, __uint_as_float(v[k]));
+        red_add_v4(base, __uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+        red_add_v4(base + 4, __uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
       }
     }
   }

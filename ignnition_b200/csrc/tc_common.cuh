@@ -118,6 +118,11 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// four adjacent floats added to global memory with one reduction (16-byte aligned address)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // byte offset of float (row r, k) inside a [rows][32] K-major SWIZZLE_128B image
 __host__ __device__ __forceinline__ int sw128_off(int r, int k) {
   return r * 128 + ((((k >> 2) ^ (r & 7)) & 7) << 4) + (k & 3) * 4;
