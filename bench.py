@@ -189,7 +189,8 @@ def run_ours(args):
     n_samples = args.batch or n_default
     dims = g["reference_meta"]["dimensions"]
     md = ModelDescription(g["model_json"], dims)
-    eng = Engine(md, device=dev, seed=0, fuse_sum_gru=(True if os.environ.get('IGN_FUSE_SUM_GRU') else None))
+    eng = Engine(md, device=dev, seed=0, fuse_sum_gru=(True if os.environ.get('IGN_FUSE_SUM_GRU') else None),
+                 csr_mode=int(os.environ.get('IGN_CSR_MODE', '1')))
     from oracle import ignnition_oracle as orc   # checker-side weights only (same seeded weights as the CPU leg)
     eng.set_weights(orc.Oracle(g["model_json"], dims).init_weights(1234))
     base = g["reference_tensors"][0]

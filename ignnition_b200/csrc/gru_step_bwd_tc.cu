@@ -226,6 +226,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gru_step_bwd_tc_kernel(
         const int e = inb[k] ? ent[k] : IGN_STEP_ZERO;
         const float* hp = (t == 0) ? h0 + (int64_t)m[k].x * U : h_seq + (int64_t)(m[k].y + t - 1) * U;
         const float* xp = e >= 0 ? pick_src(srcs, e >> IGN_STEP_SRC_SHIFT) + (int64_t)(e & IGN_STEP_ROW_MASK) * U : srcs.p[0];
+        if (dbg & 32) {                                      // timing experiment only: every row from the same 128 KB
+          hp = h0 + (int64_t)(((ptid >> 3) + 16 * k) * U);
+          xp = srcs.p[0] + (int64_t)(((ptid >> 3) + 16 * k) * U);
+        }
         hv[k] = ldg_f4(hp + c4 * 4);
         xv[k] = ldg_f4(xp + c4 * 4);
         if (e < 0) xv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
