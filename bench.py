@@ -199,7 +199,7 @@ def run_ours(args):
                            feature_fns(qsize), seed=rank,
                            label_fn=(lambda r, n: r.normal(-1.0, 0.5, n)) if args.train else None,
                            label_entity=out_entity0)
-    pinned = eng.pack(batch)            # seq_* / sample_of_* stay on the host: the device sort does not need them
+    pinned = eng.pack(batch)            # sample_of_* and the seq_* of destination-ordered lists stay on the host
     edges_per_iter = sum(batch.n_edges[a.name] for a in eng.adjacencies)
     out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
     n_pred = batch.num[out_entity]

@@ -48,6 +48,7 @@ class Batch:
         self.n_samples = 0
         self.n_edges: Dict[str, int] = {}
         self.max_seq: Dict[str, int] = {}     # adjacency -> longest per-destination list (max(seq) + 1)
+        self.dst_sorted: Dict[str, bool] = {}  # adjacency -> the edge list arrives in destination order
 
     # ---- packing: one contiguous buffer, 256-byte aligned slices
     def pack(self, pin: bool = False, skip=()):
@@ -146,6 +147,9 @@ def assemble(samples: Sequence[dict], entities: Sequence[str], features: Sequenc
         b.arrays["seq_" + a.name] = _as_i32(np.concatenate(seq))
         b.n_edges[a.name] = int(b.arrays["src_" + a.name].size)
         b.max_seq[a.name] = int(b.arrays["seq_" + a.name].max()) + 1 if b.n_edges[a.name] else 0
+        # per-sample lists in destination order stay in order after the block-diagonal shift
+        b.dst_sorted[a.name] = all(bool(np.all(np.diff(np.asarray(s["dst_" + a.name], dtype=np.int64)) >= 0))
+                                   for s in samples)
         if a.uses_params:
             # declared tf.int64 then cast to float32 (generate_model.py:149, :454-456): truncation
             # (a sample without any edge of this adjacency carries no parameter rows, nor the key)
@@ -195,6 +199,7 @@ def assemble_tiled(base: dict, n_samples: int, entities: Sequence[str],
         b.arrays["seq_" + a.name] = _as_i32(np.tile(seq, n_samples))
         b.n_edges[a.name] = int(src.size) * n_samples
         b.max_seq[a.name] = int(seq.max()) + 1 if seq.size else 0
+        b.dst_sorted[a.name] = bool(np.all(np.diff(dst) >= 0))
     for q in sequences:
         ps, pc = position_table(base, q)
         b.arrays["pos_off_" + q.key] = _as_i32(np.arange(n_samples + 1, dtype=np.int64) * ps.size)

@@ -335,7 +335,12 @@ class Engine:
         return tuple(skip)
 
     def pack(self, batch: Batch, pin: bool = True, full: bool = False):
-        return batch.pack(pin=pin, skip=() if full else self.upload_skip())
+        skip = () if full else self.upload_skip()
+        if not full and self.csr_mode == ops.CSR_RANK:
+            # an edge list that arrives in destination order needs no seq on the device: the stable-sort builder
+            # takes its pre-sorted fast path (and still verifies the order on the device)
+            skip = skip + tuple("seq_" + n for n, srt in batch.dst_sorted.items() if srt)
+        return batch.pack(pin=pin, skip=skip)
 
     def upload(self, batch: Batch, pinned=None, out: Optional[torch.Tensor] = None) -> DeviceGraph:
         """Host -> device copy of the packed batch (one cudaMemcpyAsync) + tensor views."""
@@ -359,10 +364,9 @@ class Engine:
         """Device adjacency builder: CSR per adjacency, length order, step tables."""
         for a in self.adjacencies:
             dst, src, seq = g.t["dst_" + a.name], g.t["src_" + a.name], g.t.get("seq_" + a.name)
-            if seq is None and self.csr_mode != ops.CSR_SORT:
-                raise RuntimeError("IGNNITION: seq_%s was not uploaded but the rank-placement CSR build needs it"
-                                   % a.name)
-            rowptr, col, perm, status = ops.csr_build(dst, src, seq, g.num[a.dst], self.csr_mode,
+            # no seq on the device (the host saw the list in destination order): stable sort, pre-sorted fast path
+            mode = self.csr_mode if seq is not None else ops.CSR_SORT
+            rowptr, col, perm, status = ops.csr_build(dst, src, seq, g.num[a.dst], mode,
                                                       want_perm=training or check or a.name in self._needs_perm,
                                                       want_status=check)
             g.csr[a.name] = (rowptr, col, perm)
