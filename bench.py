@@ -375,6 +375,19 @@ def run_ours(args):
             "parity": parity,
             "also": also,
         }
+        if top["name"] == "ign_gru_seq" and not args.train and args.workload.startswith("routenet"):
+            # the ordered update is a chain of small GEMMs: the tensor-pipe view of the same launch.  FLOPs issued =
+            # 3 (3xTF32 products) x 2 E 3U (F + U); the tf32 dense rate is half of the measured bf16 rate
+            e_steps = edges_per_iter // 2                    # path-link incidences = steps of one ordered update
+            fl = 3.0 * 2.0 * e_steps * 96 * 64
+            tf32_peak = float(peaks.get("bf16_tflops", 1615.9)) / 2.0
+            ach = fl / (top["ms_avg"] * 1e-3) / 1e12
+            line["roofline_tensor"] = {
+                "bound": "tensor", "kernel": "ign_gru_seq", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": ach / tf32_peak, "flops_issued_per_launch": fl,
+                "note": "tf32 operations issued (3 per fp32 product); peak = MEASURED_PEAKS bf16_tflops / 2; ncu "
+                        "sm__pipe_tensor_cycles_active 32.5 % (profiles/r1_final.md); the kernel is bound by the "
+                        "per-tile dependency chain (profiles/r1_walk_phases.md)"}
         if also and "segment_reduce" in also[0]:
             sr = also[0]["segment_reduce"]
             line["roofline_gather_segment"] = {
