@@ -745,9 +745,13 @@ extern "C" void ign_debug_bwd_prof(unsigned long long* out, int reset) {
   if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); return; }
   cudaMemcpyFromSymbol(out, g_prof, 16 * sizeof(unsigned long long));
 }
-#endif
+// timing experiments (tools/ordered_bwd_bench.py <flags>): switch parts of the kernels off -- RESULTS ARE WRONG with a
+// non-zero value, so the switch only exists in the profiling build (tools/build_profile_lib.sh)
 static int g_dbg = 0;
 extern "C" void ign_debug_bwd(int v) { g_dbg = v; }
+#else
+static const int g_dbg = 0;
+#endif
 
 static inline int64_t g_bound(int64_t num_dst) { return ign_cdiv(num_dst > 0 ? num_dst : 1, ROWS) * ROWS; }
 

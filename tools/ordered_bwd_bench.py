@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """Times the backward pass of one ordered update (RouteNet stage 1 shape: 2.26 M paths, 303 k links, ~6.1 M
 incidences, 32-wide): fp32 tile walk (ign_gru_seq_bwd) vs step-synchronous tcgen05 launches
-(ign_gru_seq_bwd_steps), CUDA events."""
+(ign_gru_seq_bwd_steps), CUDA events.
+
+With the profiling build (tools/build_profile_lib.sh, copied over ignnition_b200/libignnition_b200.so on the GPU box):
+  * extra arguments are ablation flags of the step kernel (results invalid, timing only): 1 no G stores, 2 no dL/dh
+    loads in the epilogue, 4 no output rows, 8 no L2-prefetch warps, 16 skip the weight-gradient kernel, 32 all producer
+    rows from one 128 KB region;
+  * the per-phase cycle counts of one warp per role are printed (IGN_PROF_FLAGS=<flags> profiles under an ablation)."""
 import os
 import sys
 
