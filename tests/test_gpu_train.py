@@ -138,3 +138,61 @@ def test_training_unbuilt_paths_fail_loudly():
         graph = eng.prepare([t], labels=[np.asarray(y, np.float32)], training=True)
         with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
             Trainer(eng).loss_and_grads(graph)
+
+
+def test_full_size_gradients_tensor_core_vs_fp32_backward():
+    """BASELINE config 3 / 4 scale (GEANT2-shaped x 1024: 565 k paths, 1.5 M steps per ordered update, many tiles per
+    CTA): size-independent properties of the train step --
+      * the tcgen05 step-synchronous backward (ign_gru_seq_bwd_steps + dw_tc) and the fp32 CUDA-core backward
+        (ign_gru_seq_bwd, tensor cores off for the Dense gradients) give the same gradients;
+      * a batch of N identical samples has N x the gradient of the MSE term of one sample (linearity over samples:
+        the loss is a mean over all predictions, so the gradient of N replicas equals the gradient of one)."""
+    from ignnition_b200 import ops
+    from ignnition_b200.batching import assemble_tiled
+    from ignnition_b200.train import Trainer
+    from test_gpu_model import make
+    g = load_golden("routenet_geant2")
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    base = g["reference_tensors"][0]
+    P, L = base["num_path"], base["num_link"]
+    tr_ = orc.normalization_routenet(np.asarray(base["traffic"], np.float32), "traffic")
+    cap = orc.normalization_routenet(np.asarray(base["link_capacity"], np.float32), "link_capacity")
+    lab = np.log(np.abs(np.random.RandomState(5).randn(P)).astype(np.float32) + 0.5)
+    fns = {"traffic": lambda r, c: np.tile(tr_, c // P), "link_capacity": lambda r, c: np.tile(cap, c // L)}
+
+    def grads(n, tensor_core_bwd):
+        batch = assemble_tiled(base, n, eng.entities, eng.features, eng.adjacencies, eng.sequences, fns)
+        batch.arrays["labels"] = np.tile(lab, n)
+        eng.max_bwd_step_launches = 64 if tensor_core_bwd else 0
+        prev = ops.set_tensor_cores(True)
+        try:
+            graph = eng.prepare(batch, training=True)
+            assert (len(graph.step_plan_bwd) > 0) == tensor_core_bwd
+            tr = Trainer(eng)
+            if not tensor_core_bwd:
+                # forward on the same (tensor-core) kernels, backward entirely on the fp32 kernels
+                tape = []
+                tr.build_transposed(graph)
+                tr.grads.zero_(); tr.scalars.zero_()
+                pred = eng.forward(graph, training=True, tape=tape)
+                d_pred = torch.empty_like(pred)
+                ops.mse_loss(pred, graph.t["labels"], 1.0 / float(pred.numel()), d_pred, tr.scalars[0:1])
+                ops.set_tensor_cores(False)
+                tr.backward(graph, tape, d_pred)
+            else:
+                tr.loss_and_grads(graph)
+            return tr.grads.cpu().numpy().astype(np.float64)
+        finally:
+            ops.set_tensor_cores(prev)
+            eng.max_bwd_step_launches = 64
+
+    g_tc = grads(1024, True)
+    g_fp = grads(1024, False)
+    g_one = grads(1, False)
+    for name, (off, shape) in eng.param_table.items():
+        n_el = int(np.prod(shape))
+        a, b, c = g_tc[off:off + n_el], g_fp[off:off + n_el], g_one[off:off + n_el]
+        tol = GRAD_RTOL_SELU_KINK if name.startswith("readout_model") else GRAD_RTOL
+        assert rel_err(a, b) < tol, ("tc vs fp32", name, rel_err(a, b))
+        assert rel_err(b, c) < tol, ("replicas vs one sample", name, rel_err(b, c))
