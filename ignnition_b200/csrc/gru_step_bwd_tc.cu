@@ -527,14 +527,14 @@ __global__ void gru_bwd_passthrough_kernel(const int* __restrict__ nt, int64_t n
 // weight gradients of one step: D[128 lanes = x_hi | h_hi | x_lo | h_lo features][128 = G columns] accumulated
 // over the CTA's rows in TMEM (MN-major SWIZZLE_128B_BASE32B operands, see dw_tc.cu)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int RW = 64;                     // rows per stage = 8 K-steps
-constexpr int DIMG = RW * 128;             // bytes of one [64 x 32] image
+constexpr int RW = 32;                     // rows per stage = 4 K-steps
+constexpr int DIMG = RW * 128;             // bytes of one [32 x 32] image
 constexpr int DW_BLOCKS = 12;              // x_hi h_hi x_lo h_lo | G_hi[4] | G_lo[4]
 constexpr int DW_STAGE = DW_BLOCKS * DIMG;
 constexpr int DW_STAGES = 2;
-constexpr int DW_PROD_WARPS = 16;
+constexpr int DW_PROD_WARPS = 8;           // two CTAs per SM: one splits and stores while the other one's loads land
 constexpr int DW_PROD_THREADS = 32 * DW_PROD_WARPS;
-constexpr int DW_THREADS = DW_PROD_THREADS;                 // warp 0 also issues the MMAs: 16 warps keep 128 registers
+constexpr int DW_THREADS = DW_PROD_THREADS;                 // warp 0 also issues the MMAs; 2 x 8 warps keep 128 registers
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -556,7 +556,7 @@ __device__ __forceinline__ void store_split_mn(unsigned char* img_hi, unsigned c
   *reinterpret_cast<float4*>(img_lo + o) = lo;
 }
 
-__global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
+__global__ void __launch_bounds__(DW_THREADS, 2) gru_dw_tc_kernel(
     int t, const int* __restrict__ nt, const int* __restrict__ off, const int4* __restrict__ meta,
     const int* __restrict__ steps_T, SrcPtrs srcs, const float* __restrict__ h0, const float* __restrict__ h_seq,
     const float* __restrict__ g_in, int64_t g_rows_bound, float* __restrict__ dK, float* __restrict__ dR,
@@ -583,16 +583,17 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
   const int64_t n_alive = (int64_t)__ldg(nt + t);
   const int* entries = steps_T + __ldg(off + t);
   const int64_t nchunks = (n_alive + RW - 1) / RW;
-  // at least 32 chunks (2048 rows) per CTA: a short step must not pay 148 accumulator flushes (12 k reductions each)
+  // at least 64 chunks (2048 rows) per CTA: a short step must not pay a flush of the accumulators (12 k reductions)
+  // in every CTA
   int64_t per = (nchunks + gridDim.x - 1) / gridDim.x;
-  if (per < 32) per = 32;
+  if (per < 64) per = 64;
   const int64_t c0 = (int64_t)blockIdx.x * per;
   const int64_t c1 = c0 + per < nchunks ? c0 + per : nchunks;
   const int64_t n_my = c1 > c0 ? c1 - c0 : 0;
 
   {
-    // per 64-row chunk a thread loads two float4 of [x | h] (rows tid / 16 + 32 p, chunk tid % 16) and four of G
-    // (rows tid / 32 + 16 p, chunk tid % 32): its G column chunk never changes, so the bias sums stay in registers
+    // per 32-row chunk a thread loads two float4 of [x | h] (rows tid / 16 + 16 p, chunk tid % 16) and four of G
+    // (rows tid / 32 + 8 p, chunk tid % 32): its G column chunk never changes, so the bias sums stay in registers
     const int ra = tid >> 4, wa = tid & 15;
     const int rg = tid >> 5, wg = tid & 31;
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
     // before its row pointers are formed, so no iteration waits on a load it has just issued
     struct RawIdx { int a, b; };                             // x part: (entry, -); h part: (destination, first step)
     auto fetch_raw = [&](int64_t chunk, int p) -> RawIdx {
-      const int64_t i = chunk * RW + ra + 32 * p;
+      const int64_t i = chunk * RW + ra + 16 * p;
       RawIdx r{IGN_STEP_ZERO, -1};
       if (chunk < c1 && i < n_alive) {
         if (wa < 8) r.a = __ldg(entries + i);
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
       for (int p = 0; p < 2; ++p) va[p] = ap[p] ? ldg_f4(ap[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const int64_t i = chunk * RW + rg + 16 * p;
+        const int64_t i = chunk * RW + rg + 8 * p;
         // chunk-major G[q][row][32], 16-byte pieces XOR-ed by (row & 7) (as the backward kernel stores it)
         vg[p] = i < n_alive ? ld_stream_f4(g_in + ((int64_t)(wg >> 3) * g_rows_bound + i) * U + (((wg & 7) ^ (int)(i & 7)) << 2))
                             : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -660,20 +661,20 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
         const int64_t gi = (c0 + i + 3) * RW + rg;
 #pragma unroll
         for (int p = 0; p < 4; ++p)
-          if ((wg & 7) == 0 && gi + 16 * p < n_alive)
-            prefetch_l2(g_in + ((int64_t)(wg >> 3) * g_rows_bound + gi + 16 * p) * U);
+          if ((wg & 7) == 0 && gi + 8 * p < n_alive)
+            prefetch_l2(g_in + ((int64_t)(wg >> 3) * g_rows_bound + gi + 8 * p) * U);
       }
       if (i >= DW_STAGES) mbar_wait(&bar_free[s], (uint32_t)((i / DW_STAGES) - 1) & 1);
       unsigned char* st = smem + (size_t)s * DW_STAGE;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {                          // blocks: x_hi 0, h_hi 1, x_lo 2, h_lo 3
         unsigned char* hi = st + (wa >> 3) * DIMG;
-        store_split_mn(hi, hi + 2 * DIMG, ra + 32 * p, wa & 7, ca[p]);
+        store_split_mn(hi, hi + 2 * DIMG, ra + 16 * p, wa & 7, ca[p]);
       }
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         unsigned char* hi = st + (4 + (wg >> 3)) * DIMG;
-        store_split_mn(hi, hi + 4 * DIMG, rg + 16 * p, wg & 7, cg[p]);
+        store_split_mn(hi, hi + 4 * DIMG, rg + 8 * p, wg & 7, cg[p]);
         colsum.x += cg[p].x; colsum.y += cg[p].y; colsum.z += cg[p].z; colsum.w += cg[p].w;
       }
       if (!(dbg & 32)) fence_async_smem();
@@ -717,11 +718,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1) gru_dw_tc_kernel(
       }
       mbar_wait(&bar_done, 0);
       tc_fence_after();
-      const int lg = warp & 3, qc = warp >> 2;               // lanes: x_hi | h_hi | x_lo | h_lo; columns: chunk q
+      const int lg = warp & 3;                               // lanes: x_hi | h_hi | x_lo | h_lo
       const bool is_h = lg & 1;
-      float* wrow = (is_h ? dR : dK) + lane * 3 * U + 8 * qc;
+#pragma unroll 1
+      for (int qc = warp >> 2; qc < 4; qc += DW_PROD_WARPS / 4)   // columns: chunk q
 #pragma unroll 1
       for (int gate = 0; gate < 4; ++gate) {
+        float* wrow = (is_h ? dR : dK) + lane * 3 * U + 8 * qc;
         // x rows take z, r, xh (gates 0-2); h rows take z, r (0, 1) and hh (3) -> recurrent column block 2
         if (is_h ? gate == 2 : gate == 3) continue;
         uint32_t v[8];
@@ -785,8 +788,8 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
   gru_bwd_passthrough_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(nt, num_dst, meta4, d_out, dh0);
   IGN_CHECK_LAUNCH("gru_bwd_passthrough");
   // enough 64-row chunks per CTA that the atomic flush of the accumulators stays small
-  int64_t grid_w = ign_cdiv(ign_cdiv(num_dst, RW), 8);
-  if (grid_w > sms) grid_w = sms;
+  int64_t grid_w = ign_cdiv(ign_cdiv(num_dst, RW), 16);
+  if (grid_w > 2 * sms) grid_w = 2 * sms;                    // two CTAs per SM
   if (grid_w < 1) grid_w = 1;
   for (int t = max_steps - 1; t >= 0; --t) {
     gru_step_bwd_tc_kernel<<<grid, BW_THREADS, smem_a, st>>>(t, nt, off, meta4, steps_T, sp, h0, h_seq, d_out, dhs, dh0,
