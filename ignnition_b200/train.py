@@ -210,10 +210,27 @@ class Trainer:
                     continue
                 d_agg = torch.empty_like(agg)
                 dh = torch.empty_like(h_old)
-                ops.gru_cell_bwd(agg, h_old, e.param(p.dst + "_update/kernel"),
-                                 e.param(p.dst + "_update/recurrent_kernel"), e.param(p.dst + "_update/bias"),
-                                 g_new, d_agg, dh, self.g(p.dst + "_update/kernel"),
-                                 self.g(p.dst + "_update/recurrent_kernel"), self.g(p.dst + "_update/bias"))
+                n_dst = h_old.shape[0]
+                if (ops.tensor_cores_enabled() and agg.shape[1] == 32 and h_old.shape[1] == 32 and n_dst >= 4096
+                        and e.max_bwd_step_launches >= 1):
+                    # one GRU step = a sequence of length 1 whose message is the aggregate: the tensor-core BPTT kernels
+                    # with the identity plan (destination i, step i), built once per batch and entity
+                    key = "cell/" + p.dst
+                    if key not in graph.step_plan_bwd:
+                        rp = torch.arange(n_dst + 1, dtype=torch.int32, device=dev)
+                        st = torch.arange(n_dst, dtype=torch.int32, device=dev)
+                        meta = ops.seq_meta(rp, st, None)
+                        graph.step_plan_bwd[key] = (ops.seq_step_plan(meta, st, 1), meta)
+                    plan, meta = graph.step_plan_bwd[key]
+                    ops.gru_seq_bwd_steps(plan, meta, 1, [agg], h_old, agg, e.param(p.dst + "_update/kernel"),
+                                          e.param(p.dst + "_update/recurrent_kernel"), e.param(p.dst + "_update/bias"),
+                                          g_new, d_agg, dh, self.g(p.dst + "_update/kernel"),
+                                          self.g(p.dst + "_update/recurrent_kernel"), self.g(p.dst + "_update/bias"))
+                else:
+                    ops.gru_cell_bwd(agg, h_old, e.param(p.dst + "_update/kernel"),
+                                     e.param(p.dst + "_update/recurrent_kernel"), e.param(p.dst + "_update/bias"),
+                                     g_new, d_agg, dh, self.g(p.dst + "_update/kernel"),
+                                     self.g(p.dst + "_update/recurrent_kernel"), self.g(p.dst + "_update/bias"))
                 gstate[p.dst] = dh
                 route_aggregate_grad(p, has_msg, d_agg)
             else:
