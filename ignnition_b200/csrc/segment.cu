@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_reduce_kernel(const int* 
       r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
     }
     if (OP == IGN_OP_MAX && len == 0) r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (OP == IGN_OP_SUM_ADD) {
+      const float4 o = *reinterpret_cast<const float4*>(out + gid * F + (gl + v * G) * 4);
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
     st_f4(out + gid * F + (gl + v * G) * 4, r);
   }
 }
@@ -95,6 +99,9 @@ int launch_segment(int op, const int* rowptr, const int* col, const float* src, 
       break;
     case IGN_OP_MEAN:
       segment_reduce_kernel<G, V, IGN_OP_MEAN><<<grid, SEG_THREADS, 0, st>>>(rowptr, col, src, F, num_dst, out);
+      break;
+    case IGN_OP_SUM_ADD:
+      segment_reduce_kernel<G, V, IGN_OP_SUM_ADD><<<grid, SEG_THREADS, 0, st>>>(rowptr, col, src, F, num_dst, out);
       break;
     default:
       segment_reduce_kernel<G, V, IGN_OP_MAX><<<grid, SEG_THREADS, 0, st>>>(rowptr, col, src, F, num_dst, out);
@@ -237,7 +244,7 @@ extern "C" int ign_conv_finish(const float* nsum, const float* self, const int32
 
 extern "C" int ign_segment_reduce(int op, const int32_t* rowptr, const int32_t* col, const float* src_states,
                                   int F, int64_t num_dst, float* out, void* stream) {
-  IGN_REQUIRE(op == IGN_OP_SUM || op == IGN_OP_MEAN || op == IGN_OP_MAX, IGN_ERR_INVALID,
+  IGN_REQUIRE(op == IGN_OP_SUM || op == IGN_OP_MEAN || op == IGN_OP_MAX || op == IGN_OP_SUM_ADD, IGN_ERR_INVALID,
               "IGNNITION: segment_reduce: unknown aggregation %d", op);
   IGN_REQUIRE(num_dst >= 0, IGN_ERR_INVALID, "IGNNITION: segment_reduce: negative size");
   IGN_REQUIRE(F > 0 && F % 4 == 0 && F <= 256, IGN_ERR_UNSUPPORTED,

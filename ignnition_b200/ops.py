@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-OP_SUM, OP_MEAN, OP_MAX = 0, 1, 2
+OP_SUM, OP_MEAN, OP_MAX, OP_SUM_ADD = 0, 1, 2, 3
 CSR_SORT, CSR_RANK = 0, 1
 STEP_SRC_SHIFT = 28
 ACTIVATIONS = {None: 0, "None": 0, "linear": 0, "relu": 1, "selu": 2, "sigmoid": 3, "tanh": 4,

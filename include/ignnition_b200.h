@@ -38,6 +38,7 @@ extern "C" {
 #define IGN_OP_SUM 0
 #define IGN_OP_MEAN 1
 #define IGN_OP_MAX 2
+#define IGN_OP_SUM_ADD 3 /* out += segment sum: partial sums over buckets of edges (partitioned graphs), gradient accumulation */
 
 /* activations (tf.keras.activations names, auxilary_classes.py:839-865) */
 #define IGN_ACT_LINEAR 0
