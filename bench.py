@@ -552,98 +552,44 @@ def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="unifo
     g.n_samples = 1
     g.t = {"feat_x": torch.randn(own, hidden, device=dev, generator=gen)}
     # adjacency build: no seq in a raw edge list -> stable radix sort by destination (timed separately)
-    pipelined = world > 1 and os.environ.get("IGN_MPNN_EXCHANGE", "ring") == "ring"
-    parts = None
-    if pipelined:
-        # one CSR per source-owner rank: the edges whose sources live on rank b can be reduced as soon as rank b's
-        # states have arrived, while the other ranks' states are still on the wire (the split of the synthetic edge
-        # list is set-up, not timed)
-        owner = torch.div(src, own, rounding_mode="floor")
-        parts = []
-        for b in range(world):
-            sel = owner == b
-            parts.append((dst[sel].contiguous(), (src[sel] - b * own).contiguous()))
-        del owner, sel
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if pipelined:
-        buckets = []
-        for d_b, s_b in parts:
-            rp_b, col_b, _, _ = ops.csr_build(d_b, s_b, None, own, ops.CSR_SORT)
-            buckets.append((rp_b, col_b))
-    else:
-        rowptr, col, _, _ = ops.csr_build(dst, src, None, own, ops.CSR_SORT)
+    rowptr, col, _, _ = ops.csr_build(dst, src, None, own, ops.CSR_SORT)
     e1.record()
     torch.cuda.synchronize()
     csr_ms = e0.elapsed_time(e1)
-    del src, dst, parts
+    del src, dst
     h = eng.initial_states(g)["node"]                     # owned states
-    full = torch.empty(world, own, hidden, device=dev) if world > 1 else None
+    full = torch.empty(n_nodes, hidden, device=dev) if world > 1 else None
     K = eng.param("node_update/kernel"); R = eng.param("node_update/recurrent_kernel"); B = eng.param("node_update/bias")
     agg = torch.empty(own, hidden, device=dev)
     h2 = torch.empty_like(h)
-    compute = torch.cuda.current_stream()
-    comm = torch.cuda.Stream() if pipelined else None
-    ev_ready = torch.cuda.Event()
-    ev_chunk = [torch.cuda.Event(enable_timing=True) for _ in range(world)]
-    ev_comm0 = torch.cuda.Event(enable_timing=True)
 
     def gather_states():
         if world > 1:
-            dist.all_gather_into_tensor(full.view(world * own, hidden), h)   # NCCL over NVLink: every rank's owned states
-            return full.view(world * own, hidden)
+            dist.all_gather_into_tensor(full, h)          # NCCL over NVLink: every rank's owned states
+            return full
         return h
 
-    def iteration_ring(h, h2):
-        """One message-passing iteration with the exchange hidden behind the reduction: W - 1 shifted send / receive pairs
-        (step s: my states go to rank r - s, rank r + s's states arrive) on a communication stream; the compute stream
-        reduces the local-source bucket at once and every other bucket when its chunk has landed."""
-        ev_ready.record(compute)
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev_ready)                     # my new states are final; last iteration's buckets are done
-            ev_comm0.record(comm)
-            for s_ in range(1, world):
-                to, frm = (rank - s_) % world, (rank + s_) % world
-                reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, h, to), dist.P2POp(dist.irecv, full[frm], frm)])
-                for r_ in reqs:
-                    r_.wait()
-                ev_chunk[s_].record(comm)
-        ops.segment_reduce(ops.OP_SUM, buckets[rank][0], buckets[rank][1], h, out=agg)
-        for s_ in range(1, world):
-            frm = (rank + s_) % world
-            compute.wait_event(ev_chunk[s_])
-            ops.segment_reduce(ops.OP_SUM_ADD, buckets[frm][0], buckets[frm][1], full[frm], out=agg)
-        ops.gru_cell(agg, h, K, R, B, out=h2)
-
     for _ in range(max(warmup, 3)):
-        if pipelined:
-            iteration_ring(h, h2)
-        else:
-            ops.segment_reduce(ops.OP_SUM, rowptr, col, gather_states(), out=agg)
-            ops.gru_cell(agg, h, K, R, B, out=h2)
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, gather_states(), out=agg)
+        ops.gru_cell(agg, h, K, R, B, out=h2)
         h, h2 = h2, h
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    comm_ms = []
     t0.record()
     for k in range(steps):
         ev[4 * k].record()
-        if pipelined:
-            iteration_ring(h, h2)
-            ev[4 * k + 3].record()
-            torch.cuda.synchronize()                      # (per-iteration read-out of the exchange time; the next
-            comm_ms.append(ev_comm0.elapsed_time(ev_chunk[world - 1]))   # iteration cannot start earlier anyway)
-        else:
-            srcs = gather_states()
-            ev[4 * k + 1].record()
-            ops.segment_reduce(ops.OP_SUM, rowptr, col, srcs, out=agg)
-            ev[4 * k + 2].record()
-            ops.gru_cell(agg, h, K, R, B, out=h2)
-            ev[4 * k + 3].record()
+        srcs = gather_states()
+        ev[4 * k + 1].record()
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, srcs, out=agg)
+        ev[4 * k + 2].record()
+        ops.gru_cell(agg, h, K, R, B, out=h2)
+        ev[4 * k + 3].record()
         h, h2 = h2, h
     t1.record()
     torch.cuda.synchronize()
@@ -651,27 +597,21 @@ def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="unifo
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    ag_ms = float(np.mean([ev[4 * k].elapsed_time(ev[4 * k + 1]) for k in range(steps)]))
+    seg_avg = float(np.mean([ev[4 * k + 1].elapsed_time(ev[4 * k + 2]) for k in range(steps)]))
+    cell_avg = float(np.mean([ev[4 * k + 2].elapsed_time(ev[4 * k + 3]) for k in range(steps)]))
     seg_bytes = e_own * (4 + 4 * hidden) + own * (4 * hidden + 4)
-    if pipelined:
-        it_ms = float(np.mean([ev[4 * k].elapsed_time(ev[4 * k + 3]) for k in range(steps)]))
-        ag_ms = float(np.mean(comm_ms))
-        seg_avg = cell_avg = None
-    else:
-        ag_ms = float(np.mean([ev[4 * k].elapsed_time(ev[4 * k + 1]) for k in range(steps)]))
-        seg_avg = float(np.mean([ev[4 * k + 1].elapsed_time(ev[4 * k + 2]) for k in range(steps)]))
-        cell_avg = float(np.mean([ev[4 * k + 2].elapsed_time(ev[4 * k + 3]) for k in range(steps)]))
     out = {"workload": "mpnn_%s_n%d_e%d_h%d" % (variant, n_nodes, e_own * world, hidden), "n_gpus": world,
            "partition": "destination-node range, %d nodes / %d edges per GPU" % (own, e_own),
            "mp_edges_per_s_per_iteration": e_own * world * steps / (total_ms / 1e3),
            "ms_per_iteration": total_ms / steps, "iterations_timed": steps,
-           "csr_build_ms": csr_ms, "csr_build_edges_per_s": e_own / (csr_ms / 1e3)}
-    if not pipelined:
-        out["segment_reduce"] = {"avg_launch_ms": seg_avg, "algorithmic_bytes_per_launch": seg_bytes,
-                                 "achieved_gbs": seg_bytes / (seg_avg / 1e3) / 1e9}
-        out["gru_cell"] = {"avg_launch_ms": cell_avg,
-                           "tflops_fp32": 2.0 * own * 3 * hidden * 2 * hidden / (cell_avg / 1e3) / 1e12}
-    # the states after the timed iterations, summed over all ranks: the two exchange schemes (IGN_MPNN_EXCHANGE=ring |
-    # allgather) must agree up to the order of the fp32 partial sums
+           "csr_build_ms": csr_ms, "csr_build_edges_per_s": e_own / (csr_ms / 1e3),
+           "segment_reduce": {"avg_launch_ms": seg_avg, "algorithmic_bytes_per_launch": seg_bytes,
+                              "achieved_gbs": seg_bytes / (seg_avg / 1e3) / 1e9},
+           "gru_cell": {"avg_launch_ms": cell_avg,
+                        "tflops_fp32": 2.0 * own * 3 * hidden * 2 * hidden / (cell_avg / 1e3) / 1e12}}
+    # the states after the timed iterations, summed over all ranks (the same for every partitioning of the same graph up
+    # to the order of the fp32 partial sums)
     chk = torch.tensor([float(h.double().abs().sum().item())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(chk)
@@ -679,10 +619,7 @@ def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="unifo
     if world > 1:
         recv = (world - 1) * own * hidden * 4
         out["all_gather"] = {"avg_ms": ag_ms, "bytes_received_per_gpu": recv,
-                             "achieved_gbs_per_gpu": recv / (ag_ms / 1e3) / 1e9, "nvlink_peer_peak_gbs": 770.0,
-                             "how": ("ring of %d shifted send / receive pairs on a communication stream, overlapped with the "
-                                     "reduction of the edge buckets whose sources have arrived (iteration %.3f ms)"
-                                     % (world - 1, it_ms)) if pipelined else "one all_gather_into_tensor, not overlapped"}
+                             "achieved_gbs_per_gpu": recv / (ag_ms / 1e3) / 1e9, "nvlink_peer_peak_gbs": 770.0}
     return out
 
 

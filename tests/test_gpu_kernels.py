@@ -132,6 +132,25 @@ def test_segment_reduce(F, op):
         assert np.array_equal(got, seqsum)
 
 
+def test_segment_reduce_add_accumulates():
+    """IGN_OP_SUM_ADD: out += segment sum (partial sums over edge buckets); two halves of an edge list == the whole"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(11)
+    n_dst, n_src, F = 3000, 800, 64
+    src, dst, seq = random_edges(rng, n_dst, n_src, 9)
+    states = rng.randn(n_src, F).astype(np.float32)
+    half = rng.rand(len(dst)) < 0.5
+    outs = []
+    for sel in (half, ~half):
+        r, c, _ = orc.stable_sort_csr(src[sel], dst[sel], n_dst)
+        outs.append((dev(r, torch.int32), dev(c, torch.int32)))
+    out = ops.segment_reduce(ops.OP_SUM, outs[0][0], outs[0][1], dev(states))
+    ops.segment_reduce(ops.OP_SUM_ADD, outs[1][0], outs[1][1], dev(states), out=out)
+    want = np.zeros((n_dst, F), np.float64)
+    np.add.at(want, dst, states[src].astype(np.float64))
+    assert rel_err(out.cpu().numpy(), want) < RTOL
+
+
 def test_segment_reduce_identity_col_and_errors():
     from ignnition_b200 import ops
     rng = np.random.RandomState(9)
