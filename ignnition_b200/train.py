@@ -113,6 +113,14 @@ class Trainer:
             else:
                 ops.axpy(1.0, contrib, gstate[ent])
 
+        def reduce_into(ent: str, rowptr, idx, rows):
+            """gstate[ent] (+)= per-row sums of `rows` over the segments of (rowptr, idx): the accumulation happens in
+            the reduction kernel (IGN_OP_SUM_ADD), no temporary and no second pass"""
+            if gstate[ent] is None:
+                gstate[ent] = ops.segment_reduce(ops.OP_SUM, rowptr, idx, rows)
+            else:
+                ops.segment_reduce(ops.OP_SUM_ADD, rowptr, idx, rows, out=gstate[ent])
+
         pending: Dict[tuple, torch.Tensor] = {}          # (mp key, source) -> dL/d(per-edge message), input edge order
 
         def dense_chain_bwd(saves, dy):
@@ -133,7 +141,7 @@ class Trainer:
                                                             int(graph.t["dst_" + a.name].numel()))
                 else:
                     rp_t, col_t, _ = graph.csr_t[a.name]
-                    add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, col_t, d_agg))
+                    reduce_into(a.src, rp_t, col_t, d_agg)
 
         for entry in reversed(tape):
             kind = entry[0]
@@ -148,10 +156,10 @@ class Trainer:
                 for name, w_ in zip(inputs, widths):
                     if name == "hs_source":                       # rows gathered by src index: reduce per source row
                         rp_t, _, perm_t = graph.csr_t[a.name]
-                        add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, ops.slice_cols(dx, off, w_)))
+                        reduce_into(a.src, rp_t, perm_t, ops.slice_cols(dx, off, w_))
                     elif name == "hs_dest":                       # rows gathered by dst index: reduce per destination
                         rowptr, _, perm = graph.csr[a.name]
-                        add_grad(p.dst, ops.segment_reduce(ops.OP_SUM, rowptr, perm, ops.slice_cols(dx, off, w_)))
+                        reduce_into(p.dst, rowptr, perm, ops.slice_cols(dx, off, w_))
                     off += w_                                     # edge_params are inputs, not variables
             elif kind == "agg_ff":
                 _, p, has_msg, msg_dim, saves = entry
@@ -200,7 +208,7 @@ class Trainer:
                 gstate[p.dst] = dh0
                 for k, a in enumerate(p.adjs):
                     rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]
-                    add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_steps))
+                    reduce_into(a.src, rp_t, perm_t, d_steps)
             elif kind in ("agg_gru", "agg_gru_unfused"):
                 _, p, has_msg, h_old, agg = entry
                 if p.op != ops.OP_SUM:
