@@ -248,6 +248,45 @@ __global__ void __launch_bounds__(256) dense_bwd_head_kernel(const float* __rest
   }
 }
 
+// single output, K a multiple of 128 (the readout head on 256 features): a warp streams whole rows as float4, two rows in
+// flight per iteration, the weights stay in registers
+template <int KV>
+__global__ void __launch_bounds__(256) dense_head_fwd_kernel(const float* __restrict__ x, int64_t M,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             int act, float* __restrict__ y, float* __restrict__ pre) {
+  constexpr int K = KV * 128;
+  const int lane = threadIdx.x & 31;
+  float4 wv[KV];
+#pragma unroll
+  for (int v = 0; v < KV; ++v) wv[v] = ldg_f4(w + (v * 32 + lane) * 4);
+  const float b = bias ? __ldg(bias) : 0.0f;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t r = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 2; r < M; r += nwarps * 2) {
+    float acc[2] = {0.f, 0.f};
+    float4 xv[2][KV];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int v = 0; v < KV; ++v)
+        xv[i][v] = (r + i < M) ? ld_stream_f4(x + (r + i) * K + (v * 32 + lane) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int v = 0; v < KV; ++v) {
+        acc[i] = fmaf(xv[i][v].x, wv[v].x, acc[i]); acc[i] = fmaf(xv[i][v].y, wv[v].y, acc[i]);
+        acc[i] = fmaf(xv[i][v].z, wv[v].z, acc[i]); acc[i] = fmaf(xv[i][v].w, wv[v].w, acc[i]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane < 2 && r + lane < M) {
+      const float v = (lane == 0 ? acc[0] : acc[1]) + b;
+      if (pre) pre[r + lane] = v;
+      y[r + lane] = act_fwd(act, v);
+    }
+  }
+}
+
 // dz = dy * act'(pre), in place; db += column sums of dz (per-CTA partial, then atomics)
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ dy, const float* __restrict__ pre,
                                                            int64_t M, int N, int act, float* __restrict__ db) {
@@ -383,6 +422,17 @@ extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const
       m >= 128)
     return ign_dense_tc_launch(x, m, k, w, bias, n, act, y, pre_act, ws, st);
   if (n <= 8) {
+    if (n == 1 && (k == 128 || k == 256 || k == 512) && m >= 1024) {
+      int sms = IGN_NUM_SMS, dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int64_t grid = ign_cdiv(m, 16 * 8);
+      if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+      if (k == 128) dense_head_fwd_kernel<1><<<(unsigned)grid, 256, 0, st>>>(x, m, w, bias, act, y, pre_act);
+      else if (k == 256) dense_head_fwd_kernel<2><<<(unsigned)grid, 256, 0, st>>>(x, m, w, bias, act, y, pre_act);
+      else dense_head_fwd_kernel<4><<<(unsigned)grid, 256, 0, st>>>(x, m, w, bias, act, y, pre_act);
+      IGN_CHECK_LAUNCH("dense_head_fwd");
+      return IGN_OK;
+    }
     dense_small_n_kernel<8><<<(unsigned)ign_cdiv(m * 32, 256), 256, 0, st>>>(x, m, k, w, bias, n, act, y, pre_act);
     IGN_CHECK_LAUNCH("dense_small_n");
     return IGN_OK;
