@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
 //   warp  5     MMA issuer: 12 tcgen05.mma per job, commit -> stage_free[stage]; last chunk of a tile -> acc_full[buf]
 //   warps 8-15  epilogue of the PREVIOUS tile (two TMEM accumulators): tcgen05.ld -> bias -> (pre) -> activation ->
 //               32-column chunks through a per-warp staging block so that 8 lanes write each 128-byte row segment
-// N % 64 == 0, N <= 256.
+// N % 64 == 0 or N == 32, N <= 256.
 constexpr int P_PROD_WARPS = 4, P_TMA_WARP = 4, P_MMA_WARP = 5, P_EPI_WARP0 = 8, P_EPI_WARPS = 8;
 constexpr int P_THREADS = 32 * (P_EPI_WARP0 + P_EPI_WARPS);
 constexpr int P_STAGING = P_EPI_WARPS * 4096;
@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) dense_pipe_tc_kernel(const float
     // ================================ epilogue ================================
     const int e = warp - P_EPI_WARP0, q = warp & 3, half = e >> 2;
     unsigned char* my_stage = staging + e * 4096;
-    const int ncol_half = N / 2;
+    // N = 32: the four warps of half 0 take the whole row, the others only hand the accumulator back
+    const bool solo = N == 32;
+    const int ncol_half = solo ? 32 : N / 2;
     // one 32-column chunk of this warp's 32 rows -> global, 8 lanes per 128-byte row segment
     auto emit = [&](const float (&v)[32], float* __restrict__ dst, int64_t m0, int col0) {
       __syncwarp();
@@ -342,9 +344,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) dense_pipe_tc_kernel(const float
       const int64_t m0 = (blockIdx.x + tl * gridDim.x) * TC_M;
       mbar_wait(&bar_acc_full[buf], (uint32_t)(tl >> 1) & 1);
       tc_fence_after();
+      if (solo && half == 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_free[buf]);
+        continue;
+      }
       const uint32_t tb = tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16);
       for (int cb = 0; cb < ncol_half; cb += 32) {
-        const int col0 = half * ncol_half + cb;
+        const int col0 = (solo ? 0 : half * ncol_half) + cb;
         uint32_t ra[16], rb[16];
         tmem_ld16_nowait(tb + col0, ra);
         tmem_ld16_nowait(tb + col0 + 16, rb);
@@ -395,7 +402,7 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   const int64_t tiles = ign_cdiv(m, TC_M);
   const int grid = (int)(tiles < sms ? tiles : sms);
   if (head_out) IGN_CUDA(cudaMemsetAsync(head_out, 0, (size_t)m * sizeof(float), st));
-  if (!head_out && n % 64 == 0 && m >= 4096) {
+  if (!head_out && (n % 64 == 0 || n == 32) && m >= 4096) {
     // large M: the warp-specialised pipeline (two accumulators, weight chunks by TMA, staged coalesced stores)
     const size_t stage_bytes = 2 * (size_t)A_IMG + 2 * (size_t)n * 128;
     int nst = (int)((227 * 1024 - 1024 - 2048 - (size_t)P_STAGING) / stage_bytes);

@@ -361,7 +361,7 @@ def test_gru_seq_interleave_step_table(golden):
                                        (128, 32, 32, None), (40000, 64, 96, "selu"), (2049, 256, 128, "tanh"),
                                        # M >= 4096 and N % 64 == 0: the warp-specialised pipeline (dense_pipe_tc_kernel)
                                        (5003, 256, 256, "selu"), (4097, 32, 64, "tanh"), (9000, 96, 192, "relu"),
-                                       (4500, 64, 128, None), (20000, 32, 256, "selu")])
+                                       (4500, 64, 128, None), (20000, 32, 256, "selu"), (7001, 256, 32, None), (4100, 64, 32, "selu")])
 def test_dense(m, k, n, act, tensor_cores):
     """tensor_cores=True: 3xTF32 on tcgen05 where the shape is built (K % 32 == 0, N % 32 == 0, M >= 128),
     else the fp32 CUDA-core kernel; both must meet the fp32 parity bar."""
