@@ -196,3 +196,65 @@ def test_full_size_gradients_tensor_core_vs_fp32_backward():
         tol = GRAD_RTOL_SELU_KINK if name.startswith("readout_model") else GRAD_RTOL
         assert rel_err(a, b) < tol, ("tc vs fp32", name, rel_err(a, b))
         assert rel_err(b, c) < tol, ("replicas vs one sample", name, rel_err(b, c))
+
+
+def test_full_size_qsize_properties_inference_and_training():
+    """BASELINE config 2 at scale (Q-size NSFNET x 2048: links + paths + nodes, interleave aggregation with zero-message
+    entries, three GRU cells): size-independent properties --
+      * every replica of a tiled batch with identical features gives identical predictions, the first one == the oracle;
+      * the gradients of the tensor-core backward (step-synchronous BPTT over the interleaved step table) == those of
+        the fp32 CUDA-core backward, and N replicas give the gradient of one sample."""
+    from ignnition_b200 import ops
+    from ignnition_b200.batching import assemble_tiled
+    from ignnition_b200.train import Trainer
+    from test_gpu_model import make
+    g = load_golden("qsize_nsfnet")
+    dims = g["reference_meta"]["dimensions"]
+    md, eng, o64, w = make(g["model_json"], dims)
+    base = orc.normalize_inputs(g["model_json"], g["reference_tensors"][0])
+    counts = {e: int(base["num_" + e]) for e in eng.entities}
+    ent_of = {name: ent for name, ent, _ in eng.features}
+    fns = {name: (lambda r, c, name=name: np.tile(np.asarray(base[name], np.float32).reshape(-1),
+                                                   c // (counts[ent_of[name]] * 1))) for name, _, _ in eng.features}
+    out_name, out_norm, _ = md.get_output_info()
+    lab = np.asarray(orc.EXAMPLE_NORMALIZATIONS[out_norm](np.asarray(g["reference_labels"][0], np.float32), out_name),
+                     np.float32).reshape(-1)
+    n = 2048
+    batch = assemble_tiled(base, n, eng.entities, eng.features, eng.adjacencies, eng.sequences, fns)
+    pred = eng.forward(eng.prepare(batch)).cpu().numpy().reshape(n, -1)
+    assert np.array_equal(pred, np.broadcast_to(pred[0], pred.shape))
+    want = o64.forward(base, w).reshape(-1)
+    assert rel_err(pred[0], want) < 1e-5 and rel_err(pred[-1], want) < 1e-5
+
+    def grads(n_rep, tensor_core_bwd):
+        b = assemble_tiled(base, n_rep, eng.entities, eng.features, eng.adjacencies, eng.sequences, fns)
+        b.arrays["labels"] = np.tile(lab, n_rep)
+        eng.max_bwd_step_launches = 64 if tensor_core_bwd else 0
+        prev = ops.set_tensor_cores(True)
+        try:
+            graph = eng.prepare(b, training=True)
+            tr = Trainer(eng)
+            if tensor_core_bwd:
+                assert len(graph.step_plan_bwd) > 0
+                tr.loss_and_grads(graph)
+            else:
+                tape = []
+                tr.build_transposed(graph)
+                tr.grads.zero_(); tr.scalars.zero_()
+                p = eng.forward(graph, training=True, tape=tape)
+                d_pred = torch.empty_like(p)
+                ops.mse_loss(p, graph.t["labels"], 1.0 / float(p.numel()), d_pred, tr.scalars[0:1])
+                ops.set_tensor_cores(False)
+                tr.backward(graph, tape, d_pred)
+            return tr.grads.cpu().numpy().astype(np.float64)
+        finally:
+            ops.set_tensor_cores(prev)
+            eng.max_bwd_step_launches = 64
+
+    g_tc, g_fp, g_one = grads(512, True), grads(512, False), grads(1, False)
+    for name, (off, shape) in eng.param_table.items():
+        n_el = int(np.prod(shape))
+        a, b_, c = g_tc[off:off + n_el], g_fp[off:off + n_el], g_one[off:off + n_el]
+        tol = GRAD_RTOL_SELU_KINK if name.startswith("readout_model") else GRAD_RTOL
+        assert rel_err(a, b_) < tol, ("tc vs fp32", name, rel_err(a, b_))
+        assert rel_err(b_, c) < tol, ("replicas vs one sample", name, rel_err(b_, c))
