@@ -97,6 +97,20 @@ __device__ __forceinline__ float act_bwd(int act, float pre) {
   }
 }
 
+// the same derivative from the activation's OUTPUT y = act(pre) (IGN_ACT_FROM_OUTPUT)
+__device__ __forceinline__ float act_bwd_from_output(int act, float y) {
+  switch (act) {
+    case IGN_ACT_RELU: return y > 0.0f ? 1.0f : 0.0f;
+    case IGN_ACT_SELU: return y > 0.0f ? IGN_SELU_SCALE : y + IGN_SELU_SCALE * IGN_SELU_ALPHA;
+    case IGN_ACT_SIGMOID: return y * (1.0f - y);
+    case IGN_ACT_TANH: return 1.0f - y * y;
+    case IGN_ACT_ELU: return y > 0.0f ? 1.0f : y + 1.0f;
+    case IGN_ACT_SOFTPLUS: return 1.0f - expf(-y);
+    case IGN_ACT_LEAKY_RELU: return y > 0.0f ? 1.0f : 0.2f;
+    default: return 1.0f;
+  }
+}
+
 // cp.async 16-byte global->shared copy (LDGSTS), used to prefetch gathered rows
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);

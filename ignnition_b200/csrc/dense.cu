@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(256) dense_head_fwd_kernel(const float* __rest
 
 // dz = dy * act'(pre), in place; db += column sums of dz (per-CTA partial, then atomics)
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ dy, const float* __restrict__ pre,
-                                                           int64_t M, int N, int act, float* __restrict__ db) {
+                                                           int64_t M, int N, int act, float* __restrict__ db,
+                                                           bool from_out) {
   // each CTA covers 64 rows; thread t handles columns t, t+256, ...
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const int64_t r1 = min(M, r0 + 64);
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ d
     for (int64_t r = r0; r < r1; ++r) {
       float g = dy[r * N + n];
       if (act != IGN_ACT_LINEAR) {
-        g *= act_bwd(act, pre[r * N + n]);
+        g *= from_out ? act_bwd_from_output(act, pre[r * N + n]) : act_bwd(act, pre[r * N + n]);
         dy[r * N + n] = g;
       }
       s += g;
@@ -309,7 +310,8 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ d
 
 // the same for few columns (N <= 8, the readout head): one thread per row, one atomic per column and CTA
 __global__ void __launch_bounds__(256) act_bwd_bias_small_kernel(float* __restrict__ dy, const float* __restrict__ pre,
-                                                                 int64_t M, int N, int act, float* __restrict__ db) {
+                                                                 int64_t M, int N, int act, float* __restrict__ db,
+                                                                 bool from_out) {
   __shared__ float red[8][8];
   const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(256) act_bwd_bias_small_kernel(float* __restri
     if (n < N && r < M) {
       float g = dy[r * N + n];
       if (act != IGN_ACT_LINEAR) {
-        g *= act_bwd(act, pre[r * N + n]);
+        g *= from_out ? act_bwd_from_output(act, pre[r * N + n]) : act_bwd(act, pre[r * N + n]);
         dy[r * N + n] = g;
       }
       s[n] = g;
@@ -492,13 +494,15 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
                              const float* pre_act, float* dy, float* dx, float* dw, float* db, void* ws,
                              size_t ws_bytes, void* stream) {
   IGN_REQUIRE(m >= 0 && k > 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: dense_bwd: bad shape");
+  const bool from_out = (act & IGN_ACT_FROM_OUTPUT) != 0;    // pre_act holds act(x W + b)
+  act &= ~IGN_ACT_FROM_OUTPUT;
   if (m == 0) return IGN_OK;
   IGN_REQUIRE(x && w && dy, IGN_ERR_INVALID, "IGNNITION: dense_bwd: null pointer");
   IGN_REQUIRE(act == IGN_ACT_LINEAR || pre_act, IGN_ERR_INVALID, "IGNNITION: dense_bwd: pre-activation needed");
   cudaStream_t st = ign_stream(stream);
   if (act != IGN_ACT_LINEAR || db) {
-    if (n <= 8) act_bwd_bias_small_kernel<<<(unsigned)ign_cdiv(m, 256), 256, 0, st>>>(dy, pre_act, m, n, act, db);
-    else act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db);
+    if (n <= 8) act_bwd_bias_small_kernel<<<(unsigned)ign_cdiv(m, 256), 256, 0, st>>>(dy, pre_act, m, n, act, db, from_out);
+    else act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db, from_out);
     IGN_CHECK_LAUNCH("act_bwd_bias");
   }
   if (n == 1 && (k == 128 || k == 256 || k == 512) && m >= 1024) {

@@ -455,12 +455,11 @@ class Engine:
     def _dense_layer(self, prefix: str, l, x: torch.Tensor, saves: Optional[list]) -> torch.Tensor:
         w = self.param("%s/%s/kernel" % (prefix, l.name))
         b = self.param("%s/%s/bias" % (prefix, l.name)) if l.use_bias else None
-        pre = None
+        y = ops.dense(x, w, b, self._act(l.activation))
         if saves is not None:
-            pre = torch.empty(x.shape[0], w.shape[1], dtype=torch.float32, device=self.device)
-        y = ops.dense(x, w, b, self._act(l.activation), pre_act=pre)
-        if saves is not None:
-            saves.append((prefix, l, x, pre))
+            # the backward pass takes act' from the layer's OUTPUT (every supported activation allows it), so the
+            # pre-activation is never written: one [M, N] tensor per layer instead of two
+            saves.append((prefix, l, x, y))
         return y
 
     def _messages(self, p: _MPPlan, k: int, g: DeviceGraph, state: Dict[str, torch.Tensor],

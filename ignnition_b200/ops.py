@@ -19,6 +19,7 @@ CSR_SORT, CSR_RANK = 0, 1
 STEP_SRC_SHIFT = 28
 ACTIVATIONS = {None: 0, "None": 0, "linear": 0, "relu": 1, "selu": 2, "sigmoid": 3, "tanh": 4,
                "elu": 5, "softplus": 6, "leaky_relu": 7}
+ACT_FROM_OUTPUT = 0x100      # dense_bwd: the `pre_act` argument holds the layer's output (IGN_ACT_FROM_OUTPUT)
 
 
 def set_tensor_cores(enable: bool) -> bool:

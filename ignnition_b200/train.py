@@ -129,7 +129,7 @@ class Trainer:
                 dw = self.g("%s/%s/kernel" % (prefix, layer.name))
                 db = self.g("%s/%s/bias" % (prefix, layer.name)) if layer.use_bias else None
                 dx = torch.empty_like(x)
-                ops.dense_bwd(x, w, e._act(layer.activation), pre, dy, dx, dw, db)
+                ops.dense_bwd(x, w, e._act(layer.activation) | ops.ACT_FROM_OUTPUT, pre, dy, dx, dw, db)   # pre = the layer's output
                 dy = dx
             return dy
 
@@ -179,7 +179,7 @@ class Trainer:
                     dw = self.g("%s/%s/kernel" % (prefix, layer.name))
                     db = self.g("%s/%s/bias" % (prefix, layer.name)) if layer.use_bias else None
                     dx = torch.empty_like(x)
-                    ops.dense_bwd(x, w, e._act(layer.activation), pre, dy, dx, dw, db)
+                    ops.dense_bwd(x, w, e._act(layer.activation) | ops.ACT_FROM_OUTPUT, pre, dy, dx, dw, db)   # pre = the layer's output
                     dy = dx
                 if len(op.input) != 1:
                     raise RuntimeError("IGNNITION: training with a multi-input readout is not built")

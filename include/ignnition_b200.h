@@ -49,6 +49,10 @@ extern "C" {
 #define IGN_ACT_ELU 5
 #define IGN_ACT_SOFTPLUS 6
 #define IGN_ACT_LEAKY_RELU 7
+/* ign_dense_bwd only: OR-ed into `act` when the `pre_act` argument holds the layer's OUTPUT act(x W + b) instead of the
+ * pre-activation.  Every activation above has a derivative that is a function of its output (selu: y > 0 ? scale :
+ * y + scale alpha), so the train step saves one tensor per layer instead of two. */
+#define IGN_ACT_FROM_OUTPUT 0x100
 
 /* step-table entries of ign_gru_seq: (source id << 28) | row, or IGN_STEP_ZERO for a zero message */
 #define IGN_STEP_SRC_SHIFT 28

@@ -537,9 +537,12 @@ def test_dense_bwd(m, k, n, act):
     assert rel_err(dx.cpu().numpy(), want_dx) < RTOL
     assert rel_err(dw.cpu().numpy(), want_dw) < RTOL
     assert rel_err(db.cpu().numpy(), want_db) < RTOL
-    # gradients accumulate: a second call doubles dW and db
-    ops.dense_bwd(dev(x), dev(w), a, dev(pre.astype(np.float32)), dev(dy), dx, dw, db)
-    assert rel_err(dw.cpu().numpy(), 2 * want_dw) < RTOL
+    # gradients accumulate: a second call doubles dW and db; this one takes act' from the layer's OUTPUT
+    # (IGN_ACT_FROM_OUTPUT), which is what the train step saves
+    y = orc.activation(act, pre).astype(np.float32)
+    ops.dense_bwd(dev(x), dev(w), a | ops.ACT_FROM_OUTPUT, dev(y), dev(dy), dx, dw, db)
+    assert rel_err(dx.cpu().numpy(), want_dx) < 2 * RTOL
+    assert rel_err(dw.cpu().numpy(), 2 * want_dw) < 2 * RTOL
 
 
 @pytest.mark.parametrize("max_len,n_dst", [(1, 700), (6, 3000), (16, 1000), (3, 90000)])
