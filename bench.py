@@ -475,7 +475,8 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
                      ("length_order", zero), ("seq_meta", zero), ("steps_build", zero),
                      ("gru_seq_steps", zero), ("seq_step_plan", zero),
                      ("gru_seq_bwd", b_seq_bwd), ("gru_seq_bwd_steps", b_seq_bwd_steps),
-                     ("gru_cell_bwd", b_gru_cell_bwd), ("dense_bwd", b_dense_bwd)):
+                     ("gru_cell_bwd", b_gru_cell_bwd), ("dense_bwd", b_dense_bwd),
+                     ("dense_head_bwd_chain", lambda x, *a, **kw: 8 * x.numel())):
         wrap(name, fn)
     try:
         for _ in range(max(1, min(reps, 3))):

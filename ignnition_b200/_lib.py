@@ -57,6 +57,7 @@ SIGNATURES = {
     "ign_gru_seq_bwd_steps_ws_bytes": (_sz, [_i64]),
     "ign_gru_seq_bwd_steps": (_int, [_int, _p, _p, _p, _p, _int, _p, _int, _p, _p, _i64, _int, _p, _p, _p, _p,
                                      _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "ign_dense_head_bwd_chain": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p, _p, _p]),
     "ign_l2_reg": (_int, [_p, _i64, _f, _p, _p, _p]),
     "ign_adam_step": (_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
     "ign_attention_ws_bytes": (_sz, [_i64, _i64, _int]),

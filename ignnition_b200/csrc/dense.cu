@@ -213,38 +213,64 @@ __global__ void __launch_bounds__(256) dense_small_n_kernel(const float* __restr
 template <int KV>
 __global__ void __launch_bounds__(256) dense_bwd_head_kernel(const float* __restrict__ x, int64_t M,
                                                              const float* __restrict__ w, const float* __restrict__ dz,
-                                                             float* __restrict__ dx, float* __restrict__ dw) {
+                                                             float* __restrict__ dx, float* __restrict__ dw,
+                                                             int prev_act, float* __restrict__ db_prev) {
+  // prev_act >= 0: x is the OUTPUT of the previous layer with that activation; dx is then written as that layer's dZ =
+  // (dz w) * act'(x) (act' from the output, which this kernel reads anyway) and its bias gradient is summed here, so the
+  // previous layer needs no activation pass of its own
   constexpr int K = KV * 128;
   __shared__ float4 red[8][KV * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 wv[KV], acc[KV];
+  float4 wv[KV], acc[KV], bacc[KV];
 #pragma unroll
   for (int v = 0; v < KV; ++v) {
     wv[v] = ldg_f4(w + (v * 32 + lane) * 4);
-    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[v] = bacc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int64_t nwarps = (int64_t)gridDim.x * 8;
   for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < M; r += nwarps) {
     const float g = __ldg(dz + r);
 #pragma unroll
     for (int v = 0; v < KV; ++v) {
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dw || prev_act >= 0) xv = ld_stream_f4(x + r * K + (v * 32 + lane) * 4);
       if (dw) {
-        const float4 xv = ld_stream_f4(x + r * K + (v * 32 + lane) * 4);
         acc[v].x = fmaf(xv.x, g, acc[v].x); acc[v].y = fmaf(xv.y, g, acc[v].y);
         acc[v].z = fmaf(xv.z, g, acc[v].z); acc[v].w = fmaf(xv.w, g, acc[v].w);
       }
-      if (dx) st_f4(dx + r * K + (v * 32 + lane) * 4, make_float4(g * wv[v].x, g * wv[v].y, g * wv[v].z, g * wv[v].w));
+      if (dx) {
+        float4 d = make_float4(g * wv[v].x, g * wv[v].y, g * wv[v].z, g * wv[v].w);
+        if (prev_act >= 0) {
+          d.x *= act_bwd_from_output(prev_act, xv.x); d.y *= act_bwd_from_output(prev_act, xv.y);
+          d.z *= act_bwd_from_output(prev_act, xv.z); d.w *= act_bwd_from_output(prev_act, xv.w);
+          bacc[v].x += d.x; bacc[v].y += d.y; bacc[v].z += d.z; bacc[v].w += d.w;
+        }
+        st_f4(dx + r * K + (v * 32 + lane) * 4, d);
+      }
     }
   }
-  if (!dw) return;
+  if (dw) {
 #pragma unroll
-  for (int v = 0; v < KV; ++v) red[warp][v * 32 + lane] = acc[v];
-  __syncthreads();
-  for (int i = threadIdx.x; i < K; i += 256) {
-    float s = 0.0f;
+    for (int v = 0; v < KV; ++v) red[warp][v * 32 + lane] = acc[v];
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += 256) {
+      float s = 0.0f;
 #pragma unroll
-    for (int wq = 0; wq < 8; ++wq) s += reinterpret_cast<const float*>(&red[wq][0])[i];
-    atomicAdd(dw + i, s);
+      for (int wq = 0; wq < 8; ++wq) s += reinterpret_cast<const float*>(&red[wq][0])[i];
+      atomicAdd(dw + i, s);
+    }
+  }
+  if (db_prev && prev_act >= 0) {
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < KV; ++v) red[warp][v * 32 + lane] = bacc[v];
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += 256) {
+      float s = 0.0f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) s += reinterpret_cast<const float*>(&red[wq][0])[i];
+      atomicAdd(db_prev + i, s);
+    }
   }
 }
 
@@ -505,15 +531,16 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
     else act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db, from_out);
     IGN_CHECK_LAUNCH("act_bwd_bias");
   }
+  if (!dx && !dw) return IGN_OK;                             // only the activation / bias step was asked for
   if (n == 1 && (k == 128 || k == 256 || k == 512) && m >= 1024) {
     // single-output head: both gradients in one streaming pass
     int sms = IGN_NUM_SMS, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int64_t grid = ign_cdiv(m, 8 * 16);
     if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
-    if (k == 128) dense_bwd_head_kernel<1><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw);
-    else if (k == 256) dense_bwd_head_kernel<2><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw);
-    else dense_bwd_head_kernel<4><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw);
+    if (k == 128) dense_bwd_head_kernel<1><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw, -1, nullptr);
+    else if (k == 256) dense_bwd_head_kernel<2><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw, -1, nullptr);
+    else dense_bwd_head_kernel<4><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dy, dx, dw, -1, nullptr);
     IGN_CHECK_LAUNCH("dense_bwd_head");
     return IGN_OK;
   }
@@ -541,6 +568,27 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
     gemm_kernel<true, false, 2><<<grid, GEMM_THREADS, 0, st>>>(x, dy, dw, k, n, m, nullptr, 0, nullptr, per);
     IGN_CHECK_LAUNCH("dense_bwd_dw");
   }
+  return IGN_OK;
+}
+
+extern "C" int ign_dense_head_bwd_chain(const float* x, int64_t m, int k, const float* w, const float* dz, int prev_act,
+                                        float* dz_prev, float* dw, float* db_prev, void* stream) {
+  IGN_REQUIRE(m >= 0 && (k == 128 || k == 256 || k == 512), IGN_ERR_UNSUPPORTED,
+              "IGNNITION: dense_head_bwd_chain: built for 128, 256 or 512 inputs (got %d)", k);
+  IGN_REQUIRE(prev_act >= IGN_ACT_LINEAR && prev_act <= IGN_ACT_LEAKY_RELU, IGN_ERR_INVALID,
+              "IGNNITION: dense_head_bwd_chain: unknown activation %d", prev_act);
+  if (m == 0) return IGN_OK;
+  IGN_REQUIRE(x && w && dz && dz_prev && dw, IGN_ERR_INVALID, "IGNNITION: dense_head_bwd_chain: null pointer");
+  cudaStream_t st = ign_stream(stream);
+  int sms = IGN_NUM_SMS, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t grid = ign_cdiv(m, 8 * 16);
+  if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+  if (grid < 1) grid = 1;
+  if (k == 128) dense_bwd_head_kernel<1><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dz, dz_prev, dw, prev_act, db_prev);
+  else if (k == 256) dense_bwd_head_kernel<2><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dz, dz_prev, dw, prev_act, db_prev);
+  else dense_bwd_head_kernel<4><<<(unsigned)grid, 256, 0, st>>>(x, m, w, dz, dz_prev, dw, prev_act, db_prev);
+  IGN_CHECK_LAUNCH("dense_head_bwd_chain");
   return IGN_OK;
 }
 

@@ -314,6 +314,18 @@ def dense_bwd(x, w, act: int, pre_act, dy, dx, dw, db):
                                  _stream()), "dense_bwd")
 
 
+def dense_head_bwd_chain_supported(m: int, k: int, n: int) -> bool:
+    return n == 1 and k in (128, 256, 512) and m >= 1024
+
+
+def dense_head_bwd_chain(x, w, dz, prev_act: int, dz_prev, dw, db_prev):
+    """Backward of a linear k -> 1 head fused with act' of the layer below (ign_dense_head_bwd_chain)."""
+    lib = _lib.load()
+    m, k = x.shape
+    _lib.check(lib.ign_dense_head_bwd_chain(_f(x), m, k, _f(w), _f(dz), prev_act, _f(dz_prev), _f(dw), _f(db_prev),
+                                            _stream()), "dense_head_bwd_chain")
+
+
 def gru_cell_bwd(x, h, kernel, rkernel, bias, d_out, dx, dh, dk, drk, db):
     lib = _lib.load()
     n, units = h.shape

@@ -124,12 +124,28 @@ class Trainer:
         pending: Dict[tuple, torch.Tensor] = {}          # (mp key, source) -> dL/d(per-edge message), input edge order
 
         def dense_chain_bwd(saves, dy):
-            for prefix, layer, x, pre in reversed(saves):
+            dz_ready = False          # dy already holds dZ of the layer (act' and bias gradient applied by the layer above)
+            for j in range(len(saves) - 1, -1, -1):
+                prefix, layer, x, out = saves[j]               # out = the layer's output (act' is taken from it)
                 w = e.param("%s/%s/kernel" % (prefix, layer.name))
                 dw = self.g("%s/%s/kernel" % (prefix, layer.name))
                 db = self.g("%s/%s/bias" % (prefix, layer.name)) if layer.use_bias else None
                 dx = torch.empty_like(x)
-                ops.dense_bwd(x, w, e._act(layer.activation) | ops.ACT_FROM_OUTPUT, pre, dy, dx, dw, db)   # pre = the layer's output
+                act = ops.ACTIVATIONS["linear"] if dz_ready else e._act(layer.activation)
+                below = saves[j - 1] if j > 0 else None
+                if (below is not None and below[3] is x and act == 0
+                        and ops.dense_head_bwd_chain_supported(x.shape[0], x.shape[1], w.shape[1])):
+                    # linear single-output head: its dX is written as dZ of the layer below in the same streaming pass
+                    if db is not None and not dz_ready:
+                        ops.dense_bwd(x, w, 0, None, dy, None, None, db)         # bias gradient of the head itself
+                    bl = below[1]
+                    db_below = self.g("%s/%s/bias" % (below[0], bl.name)) if bl.use_bias else None
+                    ops.dense_head_bwd_chain(x, w.reshape(-1), dy.reshape(-1), e._act(bl.activation), dx, dw.reshape(-1),
+                                             db_below)
+                    dz_ready = True
+                else:
+                    ops.dense_bwd(x, w, act | ops.ACT_FROM_OUTPUT, out, dy, dx, dw, None if dz_ready else db)
+                    dz_ready = False
                 dy = dx
             return dy
 
@@ -173,14 +189,7 @@ class Trainer:
                 route_aggregate_grad(p, has_msg, ops.slice_cols(dx, 0, msg_dim))
             elif kind == "readout":
                 _, op, saves = entry
-                dy = d_pred
-                for prefix, layer, x, pre in reversed(saves):
-                    w = e.param("%s/%s/kernel" % (prefix, layer.name))
-                    dw = self.g("%s/%s/kernel" % (prefix, layer.name))
-                    db = self.g("%s/%s/bias" % (prefix, layer.name)) if layer.use_bias else None
-                    dx = torch.empty_like(x)
-                    ops.dense_bwd(x, w, e._act(layer.activation) | ops.ACT_FROM_OUTPUT, pre, dy, dx, dw, db)   # pre = the layer's output
-                    dy = dx
+                dy = dense_chain_bwd(saves, d_pred)
                 if len(op.input) != 1:
                     raise RuntimeError("IGNNITION: training with a multi-input readout is not built")
                 add_grad(op.input[0], dy)

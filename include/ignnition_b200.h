@@ -271,6 +271,13 @@ int ign_gru_seq_bwd_steps(int max_steps, const int32_t* nt, const int32_t* off, 
                           float* d_recurrent_kernel, float* d_bias, void* ws, size_t ws_bytes,
                           void* stream);
 
+/* Backward of a linear single-output layer (the readout head, k -> 1) chained with the activation of the layer below it:
+ * x [m, k] is that layer's OUTPUT (activation prev_act), dz [m] the gradient w.r.t. the head's output.
+ *   dw[k] += sum_m x[m, k] dz[m];   dz_prev[m, k] = dz[m] w[k] act'(x[m, k]);   db_prev[k] += colsum(dz_prev) (nullable)
+ * One streaming pass; the layer below then calls ign_dense_bwd with IGN_ACT_LINEAR and d_bias = NULL.  k in {128, 256, 512}. */
+int ign_dense_head_bwd_chain(const float* x, int64_t m, int k, const float* w, const float* dz, int prev_act,
+                             float* dz_prev, float* dw, float* db_prev, void* stream);
+
 /* l2 regulariser: reg[0] += lambda * sum(w^2) (fp64), dw += 2 lambda w (auxilary_classes.py:834). */
 int ign_l2_reg(const float* w, int64_t n, float lambda, float* dw, double* reg, void* stream);
 
