@@ -617,3 +617,35 @@ def test_gru_seq_bwd_step_synchronous(max_len, n_dst):
         got = run(tc)
         for name, g, w in zip(("d_steps", "dh0", "dK", "dR", "db"), got, want):
             assert rel_err(g, w) < 2e-5, (tc, name, rel_err(g, w))
+
+
+@pytest.mark.parametrize("m,k,act", [(5000, 256, "selu"), (1500, 128, "tanh"), (3000, 512, "relu"), (2048, 256, None)])
+def test_dense_head_bwd_chain(m, k, act):
+    """backward of a linear k -> 1 head chained with the layer below (ign_dense_head_bwd_chain): dw += x^T dz,
+    dz_prev = (dz w^T) * act'(x) with act' taken from x = the lower layer's output, db_prev += colsum(dz_prev); vs fp64"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(m + k)
+    pre = rng.randn(m, k)
+    x = orc.activation(act, pre).astype(np.float32)             # output of the layer below
+    w = (rng.randn(k) / np.sqrt(k)).astype(np.float32)
+    dz = rng.randn(m).astype(np.float32)
+    x64 = x.astype(np.float64)
+    if act == "selu":
+        s_, al = 1.0507009873554805, 1.6732632423543772
+        d = np.where(x64 > 0, s_, x64 + s_ * al)
+    elif act == "tanh":
+        d = 1 - x64 ** 2
+    elif act == "relu":
+        d = (x64 > 0).astype(np.float64)
+    else:
+        d = np.ones_like(x64)
+    want_prev = dz.astype(np.float64)[:, None] * w.astype(np.float64)[None, :] * d
+    want_dw = x64.T @ dz.astype(np.float64)
+    dz_prev = torch.empty(m, k, device="cuda")
+    dw = torch.zeros(k, device="cuda")
+    db = torch.zeros(k, device="cuda")
+    assert ops.dense_head_bwd_chain_supported(m, k, 1)
+    ops.dense_head_bwd_chain(dev(x), dev(w), dev(dz), ops.ACTIVATIONS[act], dz_prev, dw, db)
+    assert rel_err(dz_prev.cpu().numpy(), want_prev) < RTOL
+    assert rel_err(dw.cpu().numpy(), want_dw) < RTOL
+    assert rel_err(db.cpu().numpy(), want_prev.sum(0)) < RTOL
