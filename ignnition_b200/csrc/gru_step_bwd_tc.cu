@@ -40,7 +40,7 @@ constexpr int MMA1_WARP = EPI_WARP0 + EPI_WARPS;
 constexpr int MMA2_WARP = MMA1_WARP + 1;
 constexpr int PF_WARP0 = MMA2_WARP + 1;                       // two warps that run ahead and pull rows into L2
 constexpr int PF_WARPS = 2;
-constexpr int PF_AHEAD = 3;                                 // tiles
+constexpr int PF_AHEAD = 1;                                 // tiles
 constexpr int BW_THREADS = 32 * (PF_WARP0 + PF_WARPS);      // 16 warps
 
 struct SrcPtrs {
