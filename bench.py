@@ -523,104 +523,133 @@ def mpnn_model_json(hidden=64, iterations=8):
     }
 
 
-def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="uniform", rank=0, world=1):
-    """Message-passing iterations of the generic MPNN on ONE large synthetic graph (strong scaling).
+def mpnn_shard(n_nodes, n_edges, hidden, variant, rank, world, torch, dev, seed=0):
+    """This rank's contiguous shard of ONE global synthetic graph (the same graph for every world size):
+    the edge list and the node features are generated in fixed chunks, each seeded by its global chunk
+    index, so rank r of W produces exactly the pieces [r/W, (r+1)/W) of the list a single rank produces."""
+    e_chunk, n_chunk = 1_000_000, 50_000
+    while n_edges % (e_chunk * world) and e_chunk > 1:
+        e_chunk //= 2
+    while n_nodes % (n_chunk * world) and n_chunk > 1:
+        n_chunk //= 2
+    gen = torch.Generator(device=dev)
+    srcs, dsts = [], []
+    for c in range(rank * (n_edges // world) // e_chunk, (rank + 1) * (n_edges // world) // e_chunk):
+        gen.manual_seed(seed * 1_000_003 + 2 * c)
+        src = torch.randint(0, n_nodes, (e_chunk,), device=dev, dtype=torch.int32, generator=gen)
+        if variant == "skew":                # power-law-like in-degrees: dst = floor(N u^3)
+            u = torch.rand(e_chunk, device=dev, generator=gen)
+            dst = (u * u * u * n_nodes).to(torch.int32).clamp_(0, n_nodes - 1)
+        else:
+            dst = torch.randint(0, n_nodes, (e_chunk,), device=dev, dtype=torch.int32, generator=gen)
+        if variant == "local":               # SURVEY 8d variant C: 90 % of the sources live in the destination's
+            blk = n_nodes // 8               # eighth of the node range (the owner's rows at 8 GPUs)
+            loc = torch.rand(e_chunk, device=dev, generator=gen) < 0.9
+            near = (dst // blk) * blk + torch.randint(0, blk, (e_chunk,), device=dev, dtype=torch.int32, generator=gen)
+            src = torch.where(loc, near.clamp_(0, n_nodes - 1), src)
+        srcs.append(src)
+        dsts.append(dst)
+    feats = []
+    for c in range(rank * (n_nodes // world) // n_chunk, (rank + 1) * (n_nodes // world) // n_chunk):
+        gen.manual_seed(seed * 1_000_003 + 2 * c + 1)
+        feats.append(torch.randn(n_chunk, hidden, device=dev, generator=gen))
+    return torch.cat(srcs), torch.cat(dsts), torch.cat(feats)
 
-    The graph is partitioned by destination-node range: rank r owns the rows
-    [r N/W, (r+1) N/W) of the CSR (all their in-edges) and the authoritative state of those nodes.
-    Every iteration all-gathers the owned states over NCCL / NVLink into the full source-state
-    buffer, then runs gather + segment-sum and the GRU update on the owned rows.  world == 1: no
-    collective.  Returns edges/s per iteration (whole graph, max over ranks) and the roofline of the
-    gather + segment-sum kernel."""
+
+def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="uniform", rank=0, world=1,
+             exchange="peer"):
+    """Message-passing iterations of the generic MPNN on ONE large synthetic graph (strong scaling) through
+    the product path ``ignnition_b200.parallel.PartitionedEngine``: rank r owns a contiguous range of
+    destination rows; one fused kernel per iteration gathers, sums, applies the GRU and stores the new rows
+    into every rank's peer-mapped state array (exchange 'peer'), or hands them to ncclAllGather ('nccl') or
+    sends only the rows a peer reads ('boundary').  Returns edges/s per iteration of the WHOLE graph (max
+    over ranks) with the HBM roofline of the kernel and the NVLink floor of the exchange."""
     import torch.distributed as dist
     from ignnition_b200 import Engine, ModelDescription, ops
-    from ignnition_b200.engine import DeviceGraph
+    from ignnition_b200.parallel import PartitionedEngine
+    n_nodes = n_nodes // (8 * 128) * (8 * 128)
+    n_edges = n_edges // 8 * 8
     md = ModelDescription(mpnn_model_json(hidden), {"x": hidden, "adj": 0})
     eng = Engine(md, device=dev, seed=0)
-    own = n_nodes // world
-    n_nodes = own * world
-    e_own = n_edges // world
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1000 + rank)
-    src = torch.randint(0, n_nodes, (e_own,), device=dev, dtype=torch.int32, generator=gen)
-    if variant == "uniform":
-        dst = torch.randint(0, own, (e_own,), device=dev, dtype=torch.int32, generator=gen)   # local row ids
-    else:                                   # skewed in-degrees (power-law-like): dst = floor(own * u^3)
-        u = torch.rand(e_own, device=dev, generator=gen)
-        dst = (u * u * u * own).to(torch.int32).clamp_(0, own - 1)
-    g = DeviceGraph()
-    g.num = {"node": own}
-    g.n_samples = 1
-    g.t = {"feat_x": torch.randn(own, hidden, device=dev, generator=gen)}
-    # adjacency build: no seq in a raw edge list -> stable radix sort by destination (timed separately)
+    src, dst, x = mpnn_shard(n_nodes, n_edges, hidden, variant, rank, world, torch, dev)
+    pe = PartitionedEngine(eng, exchange=exchange if world > 1 else "peer")
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    rowptr, col, _, _ = ops.csr_build(dst, src, None, own, ops.CSR_SORT)
+    pe.build({"node": n_nodes}, {"adj": (src, dst)}, {"x": x})
     e1.record()
     torch.cuda.synchronize()
-    csr_ms = e0.elapsed_time(e1)
-    del src, dst
-    h = eng.initial_states(g)["node"]                     # owned states
-    full = torch.empty(n_nodes, hidden, device=dev) if world > 1 else None
-    K = eng.param("node_update/kernel"); R = eng.param("node_update/recurrent_kernel"); B = eng.param("node_update/bias")
-    agg = torch.empty(own, hidden, device=dev)
-    h2 = torch.empty_like(h)
-
-    def gather_states():
-        if world > 1:
-            dist.all_gather_into_tensor(full, h)          # NCCL over NVLink: every rank's owned states
-            return full
-        return h
-
+    build_ms = e0.elapsed_time(e1)
+    del src, dst, x
+    own = pe.own("node")[1] - pe.own("node")[0]
+    e_own = pe.n_edges["adj"]
     for _ in range(max(warmup, 3)):
-        ops.segment_reduce(ops.OP_SUM, rowptr, col, gather_states(), out=agg)
-        ops.gru_cell(agg, h, K, R, B, out=h2)
-        h, h2 = h2, h
+        pe.message_passing(iterations=1)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * steps)]
+    pe.exchanged_bytes = 0
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for k in range(steps):
-        ev[4 * k].record()
-        srcs = gather_states()
-        ev[4 * k + 1].record()
-        ops.segment_reduce(ops.OP_SUM, rowptr, col, srcs, out=agg)
-        ev[4 * k + 2].record()
-        ops.gru_cell(agg, h, K, R, B, out=h2)
-        ev[4 * k + 3].record()
-        h, h2 = h2, h
+    pe.message_passing(iterations=steps)
     t1.record()
     torch.cuda.synchronize()
     t = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    ag_ms = float(np.mean([ev[4 * k].elapsed_time(ev[4 * k + 1]) for k in range(steps)]))
-    seg_avg = float(np.mean([ev[4 * k + 1].elapsed_time(ev[4 * k + 2]) for k in range(steps)]))
-    cell_avg = float(np.mean([ev[4 * k + 2].elapsed_time(ev[4 * k + 3]) for k in range(steps)]))
+    recv = pe.exchanged_bytes / steps
+    chk = pe.checksum()["node"]
+    # the fused kernel alone on this rank's rows (no exchange): its HBM roofline
+    rowptr, col = pe.csr["adj"]
+    lo, hi = pe.own("node")
+    K, R, B = (eng.param("node_update/kernel"), eng.param("node_update/recurrent_kernel"), eng.param("node_update/bias"))
+    scratch = torch.empty(hi, hidden, device=dev)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(steps, 3)
+    for _ in range(2):
+        ops.agg_gru_cell_tc(ops.OP_SUM, rowptr, col, pe.full_state("node"), pe.state("node"), K, R, B, [scratch], out_row0=lo)
+    k0.record()
+    for _ in range(reps):
+        ops.agg_gru_cell_tc(ops.OP_SUM, rowptr, col, pe.full_state("node"), pe.state("node"), K, R, B, [scratch], out_row0=lo)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / reps
+    # the round-1 pair on the same rows, for the ablation: gather + segment sum, then the GRU cell
+    agg = torch.empty(own, hidden, device=dev)
+    p0, p1, p2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ops.segment_reduce(ops.OP_SUM, rowptr, col, pe.full_state("node"), out=agg)
+    ops.gru_cell(agg, pe.state("node"), K, R, B, out=scratch[lo:hi])
+    p0.record()
+    for _ in range(reps):
+        ops.segment_reduce(ops.OP_SUM, rowptr, col, pe.full_state("node"), out=agg)
+    p1.record()
+    for _ in range(reps):
+        ops.gru_cell(agg, pe.state("node"), K, R, B, out=scratch[lo:hi])
+    p2.record()
+    torch.cuda.synchronize()
+    seg_ms, cell_ms = p0.elapsed_time(p1) / reps, p1.elapsed_time(p2) / reps
+    del scratch, agg
+    kern_bytes = e_own * (4 + 4 * hidden) + own * (8 * hidden + 4)
     seg_bytes = e_own * (4 + 4 * hidden) + own * (4 * hidden + 4)
-    out = {"workload": "mpnn_%s_n%d_e%d_h%d" % (variant, n_nodes, e_own * world, hidden), "n_gpus": world,
-           "partition": "destination-node range, %d nodes / %d edges per GPU" % (own, e_own),
-           "mp_edges_per_s_per_iteration": e_own * world * steps / (total_ms / 1e3),
+    out = {"workload": "mpnn_%s_n%d_e%d_h%d" % (variant, n_nodes, n_edges, hidden), "n_gpus": world,
+           "path": "ignnition_b200.parallel.PartitionedEngine", "exchange": pe.exchange if world > 1 else "none",
+           "partition": "destination-node range, %d nodes / %d in-edges on rank 0" % (own, e_own),
+           "mp_edges_per_s_per_iteration": n_edges * steps / (total_ms / 1e3),
            "ms_per_iteration": total_ms / steps, "iterations_timed": steps,
-           "csr_build_ms": csr_ms, "csr_build_edges_per_s": e_own / (csr_ms / 1e3),
-           "segment_reduce": {"avg_launch_ms": seg_avg, "algorithmic_bytes_per_launch": seg_bytes,
-                              "achieved_gbs": seg_bytes / (seg_avg / 1e3) / 1e9},
-           "gru_cell": {"avg_launch_ms": cell_avg,
-                        "tflops_fp32": 2.0 * own * 3 * hidden * 2 * hidden / (cell_avg / 1e3) / 1e12}}
-    # the states after the timed iterations, summed over all ranks (the same for every partitioning of the same graph up
-    # to the order of the fp32 partial sums)
-    chk = torch.tensor([float(h.double().abs().sum().item())], device=dev, dtype=torch.float64)
+           "build_ms": build_ms, "build_edges_per_s": n_edges / (build_ms / 1e3),
+           "fused_update": {"kernel": "ign_agg_gru_cell_tc (gather + sum + GRU + TMA stores)", "avg_launch_ms": kern_ms,
+                            "algorithmic_bytes_per_launch": kern_bytes,
+                            "achieved_gbs": kern_bytes / (kern_ms / 1e3) / 1e9},
+           "unfused_pair": {"segment_reduce_ms": seg_ms, "gru_cell_ms": cell_ms,
+                            "segment_reduce_gbs": seg_bytes / (seg_ms / 1e3) / 1e9},
+           "state_checksum": chk}
     if world > 1:
-        dist.all_reduce(chk)
-    out["state_abs_sum"] = float(chk.item())
-    if world > 1:
-        recv = (world - 1) * own * hidden * 4
-        out["all_gather"] = {"avg_ms": ag_ms, "bytes_received_per_gpu": recv,
-                             "achieved_gbs_per_gpu": recv / (ag_ms / 1e3) / 1e9, "nvlink_peer_peak_gbs": 770.0}
+        floor_ms = recv / 770e9 * 1e3
+        out["exchange_detail"] = {"bytes_received_per_gpu_per_iteration": recv, "nvlink_peer_peak_gbs": 770.0,
+                                  "nvlink_floor_ms": floor_ms,
+                                  "floor_over_achieved": max(floor_ms, kern_ms) / (total_ms / steps)}
+    pe.close()
     return out
 
 

@@ -78,6 +78,20 @@ SIGNATURES = {
     "ign_slice_cols": (_int, [_p, _i64, _int, _int, _int, _p, _p]),
     "ign_conv_finish": (_int, [_p, _p, _p, _int, _i64, _int, _p, _p]),
     "ign_axpy": (_int, [_i64, _f, _p, _p, _p]),
+    "ign_agg_gru_cell_tc_ws_bytes": (_sz, [_int, _int]),
+    "ign_agg_gru_cell_tc": (_int, [_int, _p, _p, _p, _int, _p, _i64, _int, _p, _p, _p, _int, _p, _i64, _p, _p, _sz, _p]),
+    "ign_peer_alloc": (_int, [_sz, C.POINTER(_p)]),
+    "ign_peer_free": (_int, [_p]),
+    "ign_peer_export": (_int, [_p, _p]),
+    "ign_peer_open": (_int, [_p, C.POINTER(_p)]),
+    "ign_peer_close": (_int, [_p]),
+    "ign_edge_owner": (_int, [_p, _i64, _p, _int, _p, _p]),
+    "ign_gather_int": (_int, [_p, _p, _i64, _int, _p, _p]),
+    "ign_mark_rows": (_int, [_p, _i64, _p, _p]),
+    "ign_flag_compact_ws_bytes": (_sz, [_i64]),
+    "ign_flag_compact": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _p]),
+    "ign_rows_put": (_int, [_p, _p, _i64, _int, _p, _p]),
+    "ign_index_range_check": (_int, [_p, _i64, _i64, _p, _p]),
 }
 
 _lib = None

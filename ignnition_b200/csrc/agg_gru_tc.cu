@@ -1,0 +1,460 @@
+// Fused gather + segmented aggregation + GRU update + state exchange on sm_100a (one kernel per
+// message passing of a sum / mean / max aggregation with a recurrent update):
+//
+//   agg[d]  = op_{slots of d} src_states[col[slot]]            generate_model.py:432,479-490 + Sum_aggr
+//   h'[d]   = GRUCell(agg[d], h[d])                            auxilary_classes.py:254-262, 752-765
+//   outs[k][out_row0 + d] = h'[d]  for k < n_out               generate_model.py:602 (state write-back)
+//
+// The aggregated messages never leave the SM: gather warps reduce the rows of a 128-destination tile in
+// registers (one sub-warp of U/4 lanes per destination, single accumulator in slot order = the
+// sequential fp32 sum of ign_segment_reduce, bit for bit) and drop them, split hi / lo, straight into
+// the swizzled A-operand images of the gate GEMMs (3xTF32 tcgen05.mma, accumulator [z | r | xh | hh]
+// in TMEM, same math as gru_cell_tc.cu).  The new states leave through a swizzled staging tile and
+// TMA TENSOR stores (cp.async.bulk.tensor.2d, one per output buffer): with n_out > 1 the outputs are
+// the caller's own state buffer and every peer GPU's mapped copy (cudaIpc over NVLink), i.e. the
+// all-gather of a destination-partitioned graph happens tile by tile from the epilogue of the kernel
+// that computes the states, while the gather warps are already reducing the next tile.
+//
+// Roles of the 512-thread persistent CTA (one per SM), mbarriers between them:
+//   warps 0-7    gather: rowptr slice -> edge-balanced row ranges per sub-warp -> software-pipelined
+//                flat walk over the tile's slots (8 row loads in flight behind the 8 being summed,
+//                column indices two batches ahead) -> x operand images
+//   warps 8-11   epilogue: TMEM -> gates -> staging tile -> TMA stores (thread = one destination)
+//   warp  12     MMA issuer (one lane)
+//   warp  13     TMA producer of the prepared weight chunks (gru_cell_tc prep layout)
+//   warps 14-15  h loaders: the old state rows -> h operand images
+// HBM-bound by the gather: algorithmic bytes E (4 + 4F) + n (8U + 4)  (DESIGN.md section 4).
+
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+using namespace ign_tc;
+
+// prepared weight images of gru_cell_tc.cu (same layout: chunk-major, [3U rows][32] hi then lo)
+size_t ign_gru_cell_tc_ws(int units);
+int ign_gru_cell_tc_prep(const float* kernel, const float* rkernel, int units, void* ws, cudaStream_t st);
+
+namespace {
+
+constexpr int GATHER_WARPS = 8;
+constexpr int GATHER_THREADS = GATHER_WARPS * 32;
+constexpr int EPI_WARP0 = 8, EPI_THREADS = 128;
+constexpr int MMA_WARP = 12, TMA_WARP = 13, HLOAD_WARP0 = 14, HLOAD_THREADS = 64;
+constexpr int AGG_THREADS = 512;
+constexpr int ROWS = 128;
+constexpr int A_IMG = ROWS * 128;                       // one [128 x 32] fp32 image
+constexpr int DEPTH = 8;                                // row loads per batch and lane
+constexpr int BAR_GATHER = 1, BAR_EPI = 2, BAR_HLOAD = 3;   // named barriers (0 = __syncthreads)
+
+struct OutMaps {
+  CUtensorMap m[IGN_MAX_PEERS];
+};
+
+__device__ __forceinline__ void named_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int OP>
+__device__ __forceinline__ void acc_row(float4& a, const float4& v) {
+  if (OP == IGN_OP_MAX) {
+    a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w);
+  } else {
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+}
+
+template <int U, int OP>
+__global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
+    const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ src,
+    const float* __restrict__ h, int64_t n, const float* __restrict__ wimg, const float* __restrict__ bias,
+    const __grid_constant__ OutMaps maps, int n_out, int out_row0, float* __restrict__ agg_out) {
+  constexpr int NC = U / 32;                 // K chunks per operand
+  constexpr int B_IMG = 3 * U * 128;         // one weight image (hi or lo) of a chunk
+  constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
+  constexpr int DCOLS = 4 * U;               // accumulator columns
+  constexpr int G = U / 4;                   // gather lanes per destination
+  constexpr int NG = GATHER_THREADS / G;     // destinations reduced at the same time
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* out_stage = smem + 2 * STAGE;           // NC boxes of [128 x 32] fp32, SWIZZLE_128B
+  __shared__ uint64_t bar_stage[2];          // the UMMAs that read the stage are done
+  __shared__ uint64_t bar_full[2];           // operand images of the stage are in place
+  __shared__ uint64_t bar_b[2];              // weight chunk landed (complete_tx)
+  __shared__ uint64_t bar_acc[2];            // accumulator complete
+  __shared__ uint64_t bar_drained[2];        // accumulator read by every epilogue thread
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_gb[4 * U];            // merged gate biases [bz | br | bxh | bhh]
+  __shared__ int s_rp[ROWS + 2];                         // rowptr slice of the tile being gathered
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_stage[i], 1); mbar_init(&bar_full[i], 1); mbar_init(&bar_b[i], 1);
+      mbar_init(&bar_acc[i], 1); mbar_init(&bar_drained[i], EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 2 * DCOLS);
+  if (tid < U) {
+    s_gb[tid] = bias[tid] + bias[3 * U + tid];
+    s_gb[U + tid] = bias[U + tid] + bias[4 * U + tid];
+    s_gb[2 * U + tid] = bias[2 * U + tid];
+    s_gb[3 * U + tid] = bias[5 * U + tid];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t ntiles = (n + ROWS - 1) / ROWS;
+  // every role walks the same chunk sequence: chunk ctr of the CTA uses stage ctr & 1 for the (ctr >> 1)-th time
+  uint32_t ctr = 0;
+
+  if (warp == MMA_WARP) {
+    int ab = 0;
+    uint32_t acc_uses[2] = {0, 0};
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ab ^= 1) {
+      const uint32_t d = tmem_base + ab * DCOLS;
+      for (int c = 0; c < 2 * NC; ++c, ++ctr) {
+        const int s = ctr & 1;
+        const uint32_t use = ctr >> 1;
+        if (lane == 0) {
+          unsigned char* st = smem + s * STAGE;
+          if (c == 0 && acc_uses[ab] > 0) mbar_wait(&bar_drained[ab], (acc_uses[ab] - 1) & 1);
+          mbar_wait(&bar_full[s], use & 1);
+          mbar_wait(&bar_b[s], use & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+          if (c < NC) {
+            umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 3 * U, c > 0);
+          } else {
+            umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 2 * U, true);
+            umma_chunk_3x(d + 3 * U, a_hi, a_lo, b_hi + 2 * U * 128, b_lo + 2 * U * 128, U, c > NC);
+          }
+          umma_commit(&bar_stage[s]);
+          if (c == 2 * NC - 1) umma_commit(&bar_acc[ab]);
+        }
+        __syncwarp();
+      }
+      acc_uses[ab] += 1;
+    }
+  } else if (warp == TMA_WARP) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int c = 0; c < 2 * NC; ++c, ++ctr) {
+        const int s = ctr & 1;
+        const uint32_t use = ctr >> 1;
+        if (lane == 0) {
+          if (use > 0) mbar_wait(&bar_stage[s], (use - 1) & 1);
+          mbar_expect_tx(&bar_b[s], 2 * B_IMG);
+          bulk_g2s(smem + s * STAGE + 2 * A_IMG, reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG),
+                   2 * B_IMG, &bar_b[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= HLOAD_WARP0) {
+    // ---- h loaders: chunk c (32 columns of the old state rows) -> hi / lo images of its stage
+    const int ht = tid - HLOAD_WARP0 * 32;
+    constexpr int PER = 1024 / HLOAD_THREADS;              // float4 per thread per chunk
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t m0 = tile * ROWS;
+      ctr += NC;                                           // the x chunks of the tile
+      for (int c = 0; c < NC; ++c, ++ctr) {
+        const int s = ctr & 1;
+        const uint32_t use = ctr >> 1;
+        float4 v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int idx = ht + j * HLOAD_THREADS;
+          const int r = idx >> 3, c4 = idx & 7;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m0 + r < n) v[j] = ldg_f4(h + (m0 + r) * U + c * 32 + c4 * 4);
+        }
+        unsigned char* st = smem + s * STAGE;
+        if (use > 0) mbar_wait(&bar_stage[s], (use - 1) & 1);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+          const int idx = ht + j * HLOAD_THREADS;
+          store_split(st, st + A_IMG, idx >> 3, idx & 7, v[j]);
+        }
+        fence_async_smem();
+        named_sync(BAR_HLOAD, HLOAD_THREADS);
+        if (ht == 0) mbar_arrive(&bar_full[s]);
+      }
+    }
+  } else if (warp < GATHER_WARPS) {
+    // ---- gather: one sub-warp of G lanes per destination, rows handed out in edge-balanced ranges
+    const int gl = lane & (G - 1);                         // lane inside the sub-warp
+    const int grp = tid / G;                               // sub-warp of the CTA, 0..NG-1
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int chunk = gl >> 3, c4 = gl & 7;                // which x chunk / 16-byte column of it this lane feeds
+    const float init = (OP == IGN_OP_MAX) ? -INFINITY : 0.0f;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t m0 = tile * ROWS;
+      // the x stages of this tile are free once the UMMAs of their previous use are done (long ago)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const uint32_t cc = ctr + c, use = cc >> 1;
+        if (use > 0) mbar_wait(&bar_stage[cc & 1], (use - 1) & 1);
+      }
+      for (int i = tid; i <= ROWS; i += GATHER_THREADS) {
+        const int64_t r = m0 + i;
+        s_rp[i] = __ldg(rowptr + (r < n ? r : n));
+      }
+      named_sync(BAR_GATHER, GATHER_THREADS);
+      const int e0 = s_rp[0], e1 = s_rp[ROWS];
+      // rows [b0, b1) of the tile: first row whose slots start at or after the sub-warp's share of the edges
+      auto bound = [&](int g) -> int {
+        if (g <= 0) return 0;
+        if (g >= NG) return ROWS;
+        const int target = e0 + (int)(((int64_t)(e1 - e0) * g) / NG);
+        int lo = 0, hi = ROWS;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_rp[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int b0 = bound(grp), b1 = bound(grp + 1);
+      const int eb0 = s_rp[b0], eb1 = s_rp[b1];
+      unsigned char* img_hi = smem + ((ctr + chunk) & 1) * STAGE;
+      unsigned char* img_lo = img_hi + A_IMG;
+
+      int row = b0;
+      int row_end = s_rp[b0 + (b0 < ROWS ? 1 : 0)];
+      float4 acc = make_float4(init, init, init, init);
+      auto flush = [&]() {                                 // destination `row` is complete
+        float4 r = acc;
+        const int len = row_end - s_rp[row];
+        if (OP == IGN_OP_MEAN) {
+          const float inv = 1.0f / (float)max(len, 1);
+          r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+        }
+        if (OP == IGN_OP_MAX && len == 0) r = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_split(img_hi, img_lo, row, c4, r);
+        if (agg_out && m0 + row < n) st_f4(agg_out + (m0 + row) * U + gl * 4, r);
+        ++row;
+        row_end = s_rp[min(row + 1, ROWS)];
+        acc = make_float4(init, init, init, init);
+      };
+      // column indices of batch b: lanes 0..7 of the sub-warp hold slots eb0 + 8 b + lane
+      auto load_idx = [&](int b) -> int {
+        const int e = eb0 + DEPTH * b + gl;
+        return (gl < DEPTH && e < eb1) ? __ldg(col + e) : -1;
+      };
+      auto issue = [&](int b, int idx, float4 (&v)[DEPTH]) {
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+          const int c = __shfl_sync(gmask, idx, u, G);
+          if (eb0 + DEPTH * b + u < eb1 && c >= 0) v[u] = ldg_f4(src + (int64_t)c * U + gl * 4);
+          else v[u] = make_float4(init, init, init, init);
+        }
+      };
+      auto consume = [&](int b, const float4 (&v)[DEPTH]) {
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+          const int e = eb0 + DEPTH * b + u;
+          if (e < eb1) {
+            while (e >= row_end) flush();
+            acc_row<OP>(acc, v[u]);
+          }
+        }
+      };
+      const int nb = (eb1 - eb0 + DEPTH - 1) / DEPTH;
+      if (nb > 0) {
+        float4 va[DEPTH], vb[DEPTH];
+        int idx_a = load_idx(0), idx_b = load_idx(1);
+        issue(0, idx_a, va);
+        for (int b = 0; b < nb; b += 2) {
+          idx_a = load_idx(b + 2);
+          if (b + 1 < nb) issue(b + 1, idx_b, vb);
+          consume(b, va);
+          if (b + 1 < nb) {
+            idx_b = load_idx(b + 3);
+            if (b + 2 < nb) issue(b + 2, idx_a, va);
+            consume(b + 1, vb);
+          }
+        }
+      }
+      while (row < b1) flush();                            // the last destination, and ones without slots
+      fence_async_smem();
+      named_sync(BAR_GATHER, GATHER_THREADS);              // every image row written; s_rp may be reused
+      if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) mbar_arrive(&bar_full[(ctr + c) & 1]);
+      }
+      ctr += 2 * NC;
+    }
+  } else {
+    // ---- epilogue: gates + new state; thread = one destination of the tile, 8 units at a time
+    const int q = warp - EPI_WARP0;                        // == warp % 4: the TMEM lane group of this warp
+    const int et = tid - EPI_WARP0 * 32;
+    const int r = q * 32 + lane;                           // row of the tile
+    uint32_t acc_uses[2] = {0, 0};
+    int ab = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ab ^= 1) {
+      const int64_t row = tile * ROWS + r;
+      const uint32_t tb = tmem_base + ab * DCOLS + ((uint32_t)(q * 32) << 16);
+      mbar_wait(&bar_acc[ab], acc_uses[ab] & 1);
+      tc_fence_after();
+      if (et == 0) bulk_wait_read();                       // the stores of the previous tile have read the staging tile
+      named_sync(BAR_EPI, EPI_THREADS);
+#pragma unroll 1
+      for (int u0 = 0; u0 < U; u0 += 8) {
+        float4 ho[2];
+        ho[0] = ho[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < n) {
+          ho[0] = ldg_f4(h + row * U + u0);
+          ho[1] = ldg_f4(h + row * U + u0 + 4);
+        }
+        uint32_t az[8], ar[8], axh[8], ahh[8];
+        tmem_ld8_nowait(tb + u0, az);
+        tmem_ld8_nowait(tb + U + u0, ar);
+        tmem_ld8_nowait(tb + 2 * U + u0, axh);
+        tmem_ld8_nowait(tb + 3 * U + u0, ahh);
+        tmem_ld_wait();
+        if (u0 + 8 >= U) {                                 // last read of this accumulator by this thread
+          tc_fence_before();
+          mbar_arrive(&bar_drained[ab]);
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4 += 4) {
+          const float4 vz = *reinterpret_cast<const float4*>(s_gb + u0 + j4);
+          const float4 vr = *reinterpret_cast<const float4*>(s_gb + U + u0 + j4);
+          const float4 vx = *reinterpret_cast<const float4*>(s_gb + 2 * U + u0 + j4);
+          const float4 vh = *reinterpret_cast<const float4*>(s_gb + 3 * U + u0 + j4);
+          const float bz[4] = {vz.x, vz.y, vz.z, vz.w}, br[4] = {vr.x, vr.y, vr.z, vr.w};
+          const float bxh[4] = {vx.x, vx.y, vx.z, vx.w}, bhh[4] = {vh.x, vh.y, vh.z, vh.w};
+          const float hold[4] = {ho[j4 / 4].x, ho[j4 / 4].y, ho[j4 / 4].z, ho[j4 / 4].w};
+          float hn[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 + jj;
+            hn[jj] = fast_gru_gate(__uint_as_float(az[j]) + bz[jj], __uint_as_float(ar[j]) + br[jj],
+                                   __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hold[jj]);
+          }
+          const int cc = u0 + j4;                          // column -> box cc / 32, 16-byte chunk (cc % 32) / 4
+          *reinterpret_cast<float4*>(out_stage + (cc >> 5) * A_IMG + r * 128 + ((((cc & 31) >> 2) ^ (r & 7)) << 4)) =
+              make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
+      }
+      acc_uses[ab] += 1;
+      fence_async_smem();
+      named_sync(BAR_EPI, EPI_THREADS);
+      if (et == 0) {
+        const int r0 = out_row0 + (int)(tile * ROWS);
+        for (int k = 0; k < n_out; ++k) {
+#pragma unroll
+          for (int bx = 0; bx < NC; ++bx) tma_store_2d(&maps.m[k], out_stage + bx * A_IMG, bx * 32, r0);
+        }
+        bulk_commit();
+      }
+    }
+    if (et == 0) bulk_wait_all();                          // every state row has left the SM
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * DCOLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+template <int U, int OP>
+int launch(const int* rowptr, const int* col, const float* src, const float* h, int64_t n, const float* wimg,
+           const float* bias, const OutMaps& maps, int n_out, int out_row0, float* agg_out, int grid,
+           cudaStream_t st) {
+  constexpr size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * 3 * U * 128) + (size_t)(U / 32) * A_IMG;
+  IGN_CUDA(cudaFuncSetAttribute(agg_gru_tc_kernel<U, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  agg_gru_tc_kernel<U, OP><<<grid, AGG_THREADS, smem, st>>>(rowptr, col, src, h, n, wimg, bias, maps, n_out, out_row0,
+                                                            agg_out);
+  IGN_CHECK_LAUNCH("agg_gru_tc");
+  return IGN_OK;
+}
+
+}  // namespace
+
+extern "C" size_t ign_agg_gru_cell_tc_ws_bytes(int f_in, int units) {
+  return (f_in == units && (units == 32 || units == 64)) ? ign_gru_cell_tc_ws(units) : 0;
+}
+
+extern "C" int ign_agg_gru_cell_tc(int op, const int32_t* rowptr, const int32_t* col, const float* src_states,
+                                   int f_in, const float* h_dst, int64_t num_dst, int units, const float* kernel,
+                                   const float* recurrent_kernel, const float* bias, int n_out, float* const* outs,
+                                   int64_t out_row0, float* agg_out, void* ws, size_t ws_bytes, void* stream) {
+  IGN_REQUIRE(op == IGN_OP_SUM || op == IGN_OP_MEAN || op == IGN_OP_MAX, IGN_ERR_INVALID,
+              "IGNNITION: agg_gru_cell_tc: unknown aggregation %d", op);
+  IGN_REQUIRE(num_dst >= 0 && out_row0 >= 0, IGN_ERR_INVALID, "IGNNITION: agg_gru_cell_tc: negative size");
+  IGN_REQUIRE(ign_agg_gru_cell_tc_ws_bytes(f_in, units) > 0, IGN_ERR_UNSUPPORTED,
+              "IGNNITION: agg_gru_cell_tc: built for message width == units in {32, 64} (got %d, %d)", f_in, units);
+  IGN_REQUIRE(n_out >= 1 && n_out <= IGN_MAX_PEERS && outs, IGN_ERR_INVALID,
+              "IGNNITION: agg_gru_cell_tc: between 1 and %d output buffers", IGN_MAX_PEERS);
+  IGN_REQUIRE(out_row0 + num_dst < ((int64_t)1 << 31), IGN_ERR_UNSUPPORTED, "IGNNITION: agg_gru_cell_tc: int32 rows only");
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr && col && src_states && h_dst && kernel && recurrent_kernel && bias, IGN_ERR_INVALID,
+              "IGNNITION: agg_gru_cell_tc: null pointer");
+  IGN_REQUIRE(ws && ws_bytes >= ign_gru_cell_tc_ws(units), IGN_ERR_WORKSPACE,
+              "IGNNITION: agg_gru_cell_tc: workspace too small (%zu < %zu)", ws_bytes, ign_gru_cell_tc_ws(units));
+  EncodeTiledFn enc = encode_tiled();
+  IGN_REQUIRE(enc, IGN_ERR_UNSUPPORTED, "IGNNITION: agg_gru_cell_tc: cuTensorMapEncodeTiled is not available");
+  OutMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int k = 0; k < n_out; ++k) {
+    IGN_REQUIRE(outs[k] && ((uintptr_t)outs[k] & 15) == 0, IGN_ERR_INVALID,
+                "IGNNITION: agg_gru_cell_tc: output buffer %d is null or not 16-byte aligned", k);
+    // rows past out_row0 + num_dst are clipped by the TMA unit: the last tile cannot touch the next owner's rows
+    const cuuint64_t dims[2] = {(cuuint64_t)units, (cuuint64_t)(out_row0 + num_dst)};
+    const cuuint64_t strides[1] = {(cuuint64_t)units * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, outs[k], dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IGN_REQUIRE(r == CUDA_SUCCESS, IGN_ERR_INVALID, "IGNNITION: agg_gru_cell_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+  cudaStream_t st = ign_stream(stream);
+  int rc = ign_gru_cell_tc_prep(kernel, recurrent_kernel, units, ws, st);
+  if (rc) return rc;
+  int sms = IGN_NUM_SMS, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = ign_cdiv(num_dst, ROWS);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  const float* wimg = reinterpret_cast<const float*>(ws);
+#define IGN_AGG_LAUNCH(UU)                                                                                        \
+  switch (op) {                                                                                                   \
+    case IGN_OP_SUM:                                                                                              \
+      return launch<UU, IGN_OP_SUM>(rowptr, col, src_states, h_dst, num_dst, wimg, bias, maps, n_out,             \
+                                    (int)out_row0, agg_out, grid, st);                                            \
+    case IGN_OP_MEAN:                                                                                             \
+      return launch<UU, IGN_OP_MEAN>(rowptr, col, src_states, h_dst, num_dst, wimg, bias, maps, n_out,            \
+                                     (int)out_row0, agg_out, grid, st);                                           \
+    default:                                                                                                      \
+      return launch<UU, IGN_OP_MAX>(rowptr, col, src_states, h_dst, num_dst, wimg, bias, maps, n_out,             \
+                                    (int)out_row0, agg_out, grid, st);                                            \
+  }
+  if (units == 64) { IGN_AGG_LAUNCH(64) }
+  IGN_AGG_LAUNCH(32)
+#undef IGN_AGG_LAUNCH
+}

@@ -443,9 +443,61 @@ inline unsigned grid1d(int64_t n, int threads = 256) { return (unsigned)ign_cdiv
 
 }  // namespace
 
+__global__ void range_check_kernel(const int* __restrict__ idx, int64_t n, int64_t bound, int* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int b = (i < n && (idx[i] < 0 || idx[i] >= bound)) ? 1 : 0;
+  b = __reduce_add_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(bad, b);
+}
+
+// out[pos[i]] = i for every flagged i; *count = number of flags
+__global__ void compact_kernel(const int* __restrict__ flags, const int* __restrict__ pos, int64_t n, int add,
+                               int* __restrict__ out, int* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[i]) out[pos[i]] = (int)i + add;
+  if (i == n - 1) *count = pos[i] + (flags[i] ? 1 : 0);
+}
+
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
+// *bad += number of idx[i] outside [0, bound): the source rows of a user-supplied adjacency (the gathers
+// trust them), checked on request like the status pass of ign_csr_build
+extern "C" int ign_index_range_check(const int32_t* idx, int64_t n, int64_t bound, int32_t* bad, void* stream) {
+  IGN_REQUIRE(n >= 0 && bad, IGN_ERR_INVALID, "IGNNITION: index_range_check: bad argument");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(idx, IGN_ERR_INVALID, "IGNNITION: index_range_check: null pointer");
+  range_check_kernel<<<grid1d(n), 256, 0, ign_stream(stream)>>>(idx, n, bound, bad);
+  IGN_CHECK_LAUNCH("range_check");
+  return IGN_OK;
+}
+
+extern "C" size_t ign_flag_compact_ws_bytes(int64_t n) {
+  if (n < 0) return 0;
+  return ign_align((size_t)(n > 0 ? n : 1) * 4) + scan_ws_bytes(n) + 256;
+}
+
+extern "C" int ign_flag_compact(const int32_t* flags, int64_t n, int add, int32_t* out, int32_t* count, void* ws,
+                                size_t ws_bytes, void* stream) {
+  IGN_REQUIRE(n >= 0 && count, IGN_ERR_INVALID, "IGNNITION: flag_compact: bad argument");
+  cudaStream_t st = ign_stream(stream);
+  if (n == 0) {
+    IGN_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+    return IGN_OK;
+  }
+  IGN_REQUIRE(flags && out, IGN_ERR_INVALID, "IGNNITION: flag_compact: null pointer");
+  IGN_REQUIRE(ws && ws_bytes >= ign_flag_compact_ws_bytes(n), IGN_ERR_WORKSPACE,
+              "IGNNITION: flag_compact: workspace too small");
+  int* pos = reinterpret_cast<int*>(ws);
+  void* scan_ws = reinterpret_cast<char*>(ws) + ign_align((size_t)n * 4);
+  int rc = exclusive_scan(flags, pos, n, scan_ws, st);
+  if (rc) return rc;
+  compact_kernel<<<grid1d(n), 256, 0, st>>>(flags, pos, n, add, out, count);
+  IGN_CHECK_LAUNCH("compact");
+  return IGN_OK;
+}
+
 extern "C" size_t ign_csr_build_ws_bytes(int64_t n_edges, int64_t num_dst) {
   if (n_edges < 0 || num_dst < 0) return 0;
   size_t sort = sort_ws_bytes(n_edges, num_dst > 0 ? num_dst : 1);
@@ -504,6 +556,9 @@ extern "C" int ign_csr_build(const int32_t* dst, const int32_t* src, const int32
     int rc = exclusive_scan(counts, rowptr, num_dst + 1, scan_ws, st);
     if (rc) return rc;
     IGN_CUDA(cudaMemsetAsync(perm_buf, 0xff, (size_t)n_edges * 4, st));   // -1 = unfilled slot
+    // a slot no edge claims (gaps / duplicates in seq) is a zero row for every consumer, as in the reference's
+    // scatter_nd (generate_model.py:490), never an uninitialised index
+    IGN_CUDA(cudaMemsetAsync(col, 0xff, (size_t)n_edges * 4, st));
     rank_place_kernel<<<grid1d(n_edges), 256, 0, st>>>(dst, src, seq, n_edges, num_dst, rowptr, col, perm_buf);
     IGN_CHECK_LAUNCH("rank_place");
   }

@@ -256,11 +256,19 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) gru_cell_tc_kernel(const floa
 bool ign_gru_cell_tc_supported(int f_in, int units) { return f_in == units && (units == 32 || units == 64); }
 size_t ign_gru_cell_tc_ws(int units) { return (size_t)2 * (units / 32) * 2 * 3 * units * 128; }
 
+// split / swizzled weight images of one cell into the caller's workspace (also used by agg_gru_tc.cu)
+int ign_gru_cell_tc_prep(const float* kernel, const float* rkernel, int units, void* ws, cudaStream_t st) {
+  gru_cell_tc_prep_kernel<<<(unsigned)ign_cdiv(2 * units * 3 * units, 256), 256, 0, st>>>(
+      kernel, rkernel, units, reinterpret_cast<float*>(ws));
+  IGN_CHECK_LAUNCH("gru_cell_tc_prep");
+  return IGN_OK;
+}
+
 int ign_gru_cell_tc_launch(const float* x, const float* h, int64_t n, int units, const float* kernel,
                            const float* rkernel, const float* bias, float* out, void* ws, cudaStream_t st) {
   float* img = reinterpret_cast<float*>(ws);
-  gru_cell_tc_prep_kernel<<<(unsigned)ign_cdiv(2 * units * 3 * units, 256), 256, 0, st>>>(kernel, rkernel, units, img);
-  IGN_CHECK_LAUNCH("gru_cell_tc_prep");
+  int prc = ign_gru_cell_tc_prep(kernel, rkernel, units, ws, st);
+  if (prc) return prc;
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = ign_cdiv(n, ROWS);

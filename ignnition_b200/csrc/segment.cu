@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_reduce_kernel(const int* 
         const bool ok = (j + u < cnt);
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (ok && colok[v]) val[u][v] = ldg_f4(src + (int64_t)c[u] * F + (gl + v * G) * 4);
+          if (ok && colok[v])     // a negative column is a zero row (slot no edge claimed, csr_build.cu)
+            val[u][v] = c[u] >= 0 ? ldg_f4(src + (int64_t)c[u] * F + (gl + v * G) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < SEG_UNROLL; ++u) {

@@ -15,6 +15,7 @@ sm_100a kernel behind the C-ABI (``ops.py`` -> ``libignnition_b200.so``).  There
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -88,6 +89,9 @@ class Engine:
         # sum aggregation + GRU: one fused fp32 kernel, or segment_reduce + tensor-core cell.  None picks by
         # measurement (GEANT2 x 4096 links: 0.121 + 0.087 ms unfused on tensor cores vs 0.333 ms fused fp32)
         self.fuse_sum_gru = fuse_sum_gru
+        # aggregation + GRU update as ONE tensor-core kernel (ign_agg_gru_cell_tc: gather, sum / mean / max, gate GEMMs,
+        # TMA stores); False = ign_segment_reduce + ign_gru_cell (the round-1 pair, kept for ablation)
+        self.fused_tc = os.environ.get("IGN_NO_FUSED_TC") is None
         self.dims = model.get_input_dimensions()
         self.entities = [e.name for e in model.get_entities()]
         self.hidden = {e.name: e.hidden_state_dimension for e in model.get_entities()}
@@ -529,6 +533,16 @@ class Engine:
         fused = (p.kind == "agg_gru" and p.op == ops.OP_SUM and len(p.adjs) == 1 and msgs[0] is None
                  and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1])
                  and (self.fuse_sum_gru if self.fuse_sum_gru is not None else not ops.tensor_cores_enabled()))
+        fused_tc = (p.kind == "agg_gru" and len(p.adjs) == 1 and msgs[0] is None and not p.conv and not p.attn
+                    and not fused and self.fused_tc and n_dst > 0
+                    and ops.agg_gru_cell_tc_supported(p.msg_dim, h.shape[1]))
+        if fused_tc:
+            rowptr, col, _ = g.csr[p.adjs[0].name]
+            agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
+            ops.agg_gru_cell_tc(p.op, rowptr, col, state[p.adjs[0].src], h, K, R, B, [out], agg_out=agg)
+            if tape is not None:
+                tape.append(("agg_gru_unfused", p, has_msg, h, agg))
+            return out
         if fused:
             rowptr, col, _ = g.csr[p.adjs[0].name]
             agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None

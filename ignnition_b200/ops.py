@@ -17,6 +17,7 @@ from . import _lib
 OP_SUM, OP_MEAN, OP_MAX, OP_SUM_ADD = 0, 1, 2, 3
 CSR_SORT, CSR_RANK = 0, 1
 STEP_SRC_SHIFT = 28
+MAX_PEERS = 8               # IGN_MAX_PEERS: state arrays one fused update can write
 ACTIVATIONS = {None: 0, "None": 0, "linear": 0, "relu": 1, "selu": 2, "sigmoid": 3, "tanh": 4,
                "elu": 5, "softplus": 6, "leaky_relu": 7}
 ACT_FROM_OUTPUT = 0x100      # dense_bwd: the `pre_act` argument holds the layer's output (IGN_ACT_FROM_OUTPUT)
@@ -166,6 +167,30 @@ def agg_gru_cell(rowptr, col, src_states, h_dst, kernel, rkernel, bias, out=None
                                     units, _f(kernel), _f(rkernel), _f(bias), _f(out), _f(agg_out),
                                     _stream()), "agg_gru_cell")
     return out
+
+
+def agg_gru_cell_tc_supported(f_in: int, units: int) -> bool:
+    return _lib.load().ign_agg_gru_cell_tc_ws_bytes(f_in, units) > 0 and tensor_cores_enabled()
+
+
+def agg_gru_cell_tc(op: int, rowptr, col, src_states, h_dst, kernel, rkernel, bias, outs, out_row0: int = 0,
+                    agg_out=None):
+    """Fused gather + aggregation + GRU update (ign_agg_gru_cell_tc).  ``outs``: the state arrays that receive
+    rows [out_row0, out_row0 + num_dst): torch tensors or raw device pointers (peer-mapped buffers)."""
+    lib = _lib.load()
+    n, units = h_dst.shape
+    f_in = src_states.shape[1]
+    nbytes = lib.ign_agg_gru_cell_tc_ws_bytes(f_in, units)
+    if not nbytes:
+        raise RuntimeError("IGNNITION: agg_gru_cell_tc is built for message width == units in {32, 64}, got %d, %d"
+                           % (f_in, units))
+    ws = _workspace(nbytes, h_dst.device)
+    arr = (C.c_void_p * max(len(outs), 1))()
+    for k, o in enumerate(outs):
+        arr[k] = _f(o, "output state array") if torch.is_tensor(o) else int(o)
+    _lib.check(lib.ign_agg_gru_cell_tc(op, _i(rowptr), _i(col), _f(src_states), f_in, _f(h_dst), n, units,
+                                       _f(kernel), _f(rkernel), _f(bias), len(outs), arr, out_row0, _f(agg_out),
+                                       ws.data_ptr(), ws.numel(), _stream()), "agg_gru_cell_tc")
 
 
 def seq_meta(steps_rowptr, steps, order) -> torch.Tensor:
@@ -425,3 +450,52 @@ def partner_index(rowptr0, rowptr1, idx1, n_edges0: int):
     _lib.check(lib.ign_partner_index(_i(rowptr0), _i(rowptr1), _i(idx1) if idx1.numel() else None,
                                      rowptr0.numel() - 1, _i(out) if n_edges0 else None, _stream()), "partner_index")
     return out
+
+
+# ------------------------------------------------------------------------------- partitioned graphs
+def edge_owner(dst, bounds: Sequence[int]) -> torch.Tensor:
+    """Owner rank of every edge's destination; ``bounds`` = world + 1 ascending row bounds (host)."""
+    lib = _lib.load()
+    world = len(bounds) - 1
+    owner = torch.empty_like(dst)
+    b = (C.c_int32 * (world + 1))(*[int(v) for v in bounds])
+    _lib.check(lib.ign_edge_owner(_i(dst), dst.numel(), b, world, _i(owner), _stream()), "edge_owner")
+    return owner
+
+
+def gather_int(values, perm=None, add: int = 0, out=None) -> torch.Tensor:
+    lib = _lib.load()
+    n = perm.numel() if perm is not None else values.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=values.device)
+    _lib.check(lib.ign_gather_int(_i(values), _i(perm), n, add, _i(out), _stream()), "gather_int")
+    return out
+
+
+def mark_rows(col, flags):
+    lib = _lib.load()
+    _lib.check(lib.ign_mark_rows(_i(col), col.numel(), _i(flags), _stream()), "mark_rows")
+
+
+def flag_compact(flags, add: int = 0):
+    """(rows[n] int32 with the flagged positions + add first, count[1] device int32)."""
+    lib = _lib.load()
+    n = flags.numel()
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=flags.device)
+    count = torch.empty(1, dtype=torch.int32, device=flags.device)
+    ws = _workspace(lib.ign_flag_compact_ws_bytes(n), flags.device)
+    _lib.check(lib.ign_flag_compact(_i(flags), n, add, _i(out), _i(count), ws.data_ptr(), ws.numel(), _stream()),
+               "flag_compact")
+    return out, count
+
+
+def rows_put(src, rows, dst):
+    """dst[rows] = src[rows]; ``dst``: a tensor or the raw device pointer of a peer-mapped array."""
+    lib = _lib.load()
+    d = _f(dst) if torch.is_tensor(dst) else int(dst)
+    _lib.check(lib.ign_rows_put(_f(src), _i(rows), rows.numel(), src.shape[1], d, _stream()), "rows_put")
+
+
+def index_range_check(idx, bound: int, bad):
+    lib = _lib.load()
+    _lib.check(lib.ign_index_range_check(_i(idx), idx.numel(), bound, _i(bad), _stream()), "index_range_check")

@@ -59,6 +59,8 @@ extern "C" {
 #define IGN_STEP_ROW_MASK 0x0FFFFFFF
 #define IGN_STEP_ZERO (-1)
 #define IGN_MAX_SOURCES 4
+/* state buffers one fused update can write (the caller's own + every peer GPU of a partitioned graph) */
+#define IGN_MAX_PEERS 8
 
 int ign_version(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
@@ -360,6 +362,62 @@ int64_t ign_ingest_feature(const ign_ingest_t* g, int feature, const float** dat
 int64_t ign_ingest_adjacency(const ign_ingest_t* g, int adj, const int32_t** src, const int32_t** dst,
                              const int32_t** seq, const float** params, int32_t* params_width);
 int64_t ign_ingest_labels(const ign_ingest_t* g, const float** data);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused message passing of an aggregating update on the tensor cores, with the state exchange of a
+ * destination-partitioned graph in its epilogue (north_star: "gather ...
+ * aggregation ... update", one kernel).  Replaces, for one message passing whose sources send their
+ * states (direct_assignation) into a sum / mean / max aggregation with a GRU update:
+ *   tf.gather + tf.scatter_nd + reduce_sum   generate_model.py:432, 479-490, auxilary_classes.py:254-262
+ *   GRUCell step                              auxilary_classes.py:752-765
+ *   state write-back                          generate_model.py:602
+ * rowptr[num_dst + 1] / col[E] index rows of src_states [*, f_in] (col < 0 = zero row); h_dst
+ * [num_dst, units] are the old states of the destinations.  The new states are written to rows
+ * [out_row0, out_row0 + num_dst) of EVERY buffer outs[k] (host array of n_out device pointers, each
+ * the base of a [>= out_row0 + num_dst, units] array): the caller's own state array and, on a
+ * partitioned graph, the peer-mapped copies of it on the other GPUs (ign_peer_open), so the
+ * per-iteration all-gather happens tile by tile from the kernel that computes the states (TMA
+ * tensor stores over NVLink).  No buffer may alias src_states / h_dst rows that are still read.
+ * agg_out (nullable): the aggregated messages [num_dst, f_in] (saved for the backward pass).
+ * Built for f_in == units in {32, 64} (ws_bytes == 0 otherwise: use ign_segment_reduce + ign_gru_cell).
+ */
+size_t ign_agg_gru_cell_tc_ws_bytes(int f_in, int units);
+int ign_agg_gru_cell_tc(int op, const int32_t* rowptr, const int32_t* col, const float* src_states, int f_in,
+                        const float* h_dst, int64_t num_dst, int units, const float* kernel,
+                        const float* recurrent_kernel, const float* bias, int n_out,
+                        float* const* outs /*host array of device ptrs*/, int64_t out_row0, float* agg_out,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Destination-partitioned graphs: peer-mapped state buffers and the builder's routing helpers.
+ * The reference is single-process; these have no counterpart there.
+ * ign_peer_* are the ONLY calls of the library that allocate: a CUDA IPC handle covers one whole
+ * cudaMalloc allocation, so an exchanged buffer cannot come out of the caller's memory pool.
+ *   alloc / free     : cudaMalloc / cudaFree on the current device
+ *   export           : 64-byte handle (host memory) to send to the other processes of the node
+ *   open / close     : map / unmap a peer's buffer into this process (peer access enabled lazily)
+ * ------------------------------------------------------------------------------------------- */
+#define IGN_PEER_HANDLE_BYTES 64
+int ign_peer_alloc(size_t bytes, void** ptr);
+int ign_peer_free(void* ptr);
+int ign_peer_export(void* ptr, void* handle64 /*host*/);
+int ign_peer_open(const void* handle64 /*host*/, void** ptr);
+int ign_peer_close(void* ptr);
+/* owner[i] = rank whose row range [bounds[r], bounds[r+1]) holds dst[i]; bounds: HOST array of world + 1 ints */
+int ign_edge_owner(const int32_t* dst, int64_t n_edges, const int32_t* bounds /*host*/, int world, int32_t* owner,
+                   void* stream);
+/* out[i] = in[perm[i]] + add (perm nullable = identity): edge arrays in routed order, global -> local row ids */
+int ign_gather_int(const int32_t* in, const int32_t* perm, int64_t n, int add, int32_t* out, void* stream);
+/* flags[col[e]] = 1: the source rows an adjacency reads (boundary-only exchange) */
+int ign_mark_rows(const int32_t* col, int64_t n, int32_t* flags, void* stream);
+/* out[0 .. *count) = add + i for every i with flags[i] != 0, ascending; count: device int */
+size_t ign_flag_compact_ws_bytes(int64_t n);
+int ign_flag_compact(const int32_t* flags, int64_t n, int add, int32_t* out, int32_t* count, void* ws,
+                     size_t ws_bytes, void* stream);
+/* dst[rows[i], :] = src[rows[i], :] for a [*, width] fp32 array; dst may be a peer-mapped buffer */
+int ign_rows_put(const float* src, const int32_t* rows, int64_t n_rows, int width, float* dst, void* stream);
+/* *bad (device int, caller-zeroed) += number of idx[i] outside [0, bound) */
+int ign_index_range_check(const int32_t* idx, int64_t n, int64_t bound, int32_t* bad, void* stream);
 
 #ifdef __cplusplus
 }

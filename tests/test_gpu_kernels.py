@@ -649,3 +649,78 @@ def test_dense_head_bwd_chain(m, k, act):
     assert rel_err(dz_prev.cpu().numpy(), want_prev) < RTOL
     assert rel_err(dw.cpu().numpy(), want_dw) < RTOL
     assert rel_err(db.cpu().numpy(), want_prev.sum(0)) < RTOL
+
+
+# ------------------------------------------------------------------ fused gather + aggregation + GRU + TMA stores
+def _skewed_edges(rng, n_dst, n_src, max_len, hub=0):
+    src, dst, seq = random_edges(rng, n_dst, n_src, max_len)
+    if hub and n_dst > 3:          # one destination with a long list (edge-balanced row ranges must cope)
+        extra = rng.randint(0, n_src, hub)
+        d = 3
+        base = int((dst == d).sum())
+        src = np.concatenate([src, extra])
+        dst = np.concatenate([dst, np.full(hub, d)])
+        seq = np.concatenate([seq, base + np.arange(hub)])
+    return src, dst, seq
+
+
+@pytest.mark.parametrize("u", [32, 64])
+@pytest.mark.parametrize("op", [0, 1, 2])
+@pytest.mark.parametrize("n_dst,max_len,hub", [(1, 3, 0), (127, 5, 0), (128, 0, 0), (129, 9, 0), (1000, 40, 700),
+                                              (20000, 12, 0)])
+def test_agg_gru_cell_tc(u, op, n_dst, max_len, hub):
+    """ign_agg_gru_cell_tc == ign_segment_reduce + ign_gru_cell (same sum order, same gate GEMMs: bit for bit)
+    and == the fp64 oracle to 1e-5; two output arrays written at a row offset, rows past the range untouched."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(u + op + n_dst)
+    n_src = max(3, n_dst // 2)
+    src, dst, seq = _skewed_edges(rng, n_dst, n_src, max_len, hub)
+    states = (rng.randn(n_src, u) * 0.3).astype(np.float32)
+    h = rng.randn(n_dst, u).astype(np.float32)
+    K, R, b = gru_weights(rng, u, u)
+    r, c, _ = orc.csr_from_edges(src, dst, seq, n_dst)
+    rp, cl, st, hd = dev(r, torch.int32), dev(c, torch.int32), dev(states), dev(h)
+    row0, pad = 77, 200
+    outs = [torch.full((row0 + n_dst + pad, u), 7.5, device="cuda") for _ in range(2)]
+    agg_out = torch.empty(n_dst, u, device="cuda")
+    ops.agg_gru_cell_tc(op, rp, cl, st, hd, dev(K), dev(R), dev(b), outs, out_row0=row0, agg_out=agg_out)
+    agg_ref = ops.segment_reduce(op, rp, cl, st)
+    assert torch.equal(agg_out, agg_ref)
+    got = outs[0][row0:row0 + n_dst].cpu().numpy()
+    assert torch.equal(outs[0], outs[1])
+    assert float(outs[0][:row0].min()) == 7.5 and float(outs[0][row0 + n_dst:].max()) == 7.5
+    want = orc.gru_cell(agg_ref.cpu().numpy().astype(np.float64), h.astype(np.float64), K.astype(np.float64),
+                        R.astype(np.float64), b.astype(np.float64))
+    assert rel_err(got, want) < RTOL
+    if n_dst >= 128:   # the unfused tensor-core pair computes the same products in the same order
+        pair = ops.gru_cell(agg_ref, hd, dev(K), dev(R), dev(b)).cpu().numpy()
+        assert np.array_equal(got, pair)
+
+
+def test_agg_gru_cell_tc_errors():
+    from ignnition_b200 import ops
+    z = torch.zeros(4, 48, device="cuda")
+    rp = torch.zeros(5, dtype=torch.int32, device="cuda")
+    cl = torch.zeros(1, dtype=torch.int32, device="cuda")
+    w = torch.zeros(48, 144, device="cuda")
+    with pytest.raises(RuntimeError, match="IGNNITION"):
+        ops.agg_gru_cell_tc(0, rp, cl, z, z, w, w, torch.zeros(2, 144, device="cuda"), [torch.empty_like(z)])
+
+
+def test_csr_rank_gaps_are_zero_rows():
+    """a seq with gaps / duplicates leaves slots no edge claims; they must read as zero rows, not as
+    uninitialised indices, and the status word must report them."""
+    from ignnition_b200 import ops
+    dst = np.array([0, 0, 0, 1, 1], np.int32)
+    src = np.array([2, 1, 0, 3, 3], np.int32)
+    seq = np.array([0, 0, 2, 0, 1], np.int32)          # duplicate 0, gap at 1 in destination 0
+    rowptr, col, perm, status = ops.csr_build(dev(dst), dev(src), dev(seq), 2, ops.CSR_RANK, want_perm=True,
+                                              want_status=True)
+    c = col.cpu().numpy()
+    assert c[1] == -1 and status.cpu().numpy()[0] > 0
+    states = np.arange(4 * 4, dtype=np.float32).reshape(4, 4)
+    got = ops.segment_reduce(0, rowptr, col, dev(states)).cpu().numpy()
+    assert np.array_equal(got[0], states[c[0]] + states[0]) and np.array_equal(got[1], 2 * states[3])
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.index_range_check(dev(np.array([0, 5, -1, 3], np.int32)), 4, bad)
+    assert int(bad.item()) == 2
