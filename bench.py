@@ -426,6 +426,10 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
         E, n, F, U = col.numel(), h_dst.shape[0], src_states.shape[1], h_dst.shape[1]
         return E * (4 + 4 * F) + n * (8 * U + 4)
 
+    def b_agg_tc(op, rowptr, col, src_states, h_dst, *a, **kw):
+        E, n, F, U = col.numel(), h_dst.shape[0], src_states.shape[1], h_dst.shape[1]
+        return E * (4 + 4 * F) + n * (8 * U + 4)             # col + gathered row per slot; old state in, new state out, rowptr
+
     def b_seg(op, rowptr, col, src_states, *a, **kw):
         n, F = rowptr.numel() - 1, src_states.shape[1]
         E = col.numel() if col is not None else src_states.shape[0]
@@ -469,7 +473,7 @@ def profile_kernels(eng, graph, torch, reps, trainer=None, n_glob=None):
     def b_init(feats, sizes, n, hidden, *a, **kw):
         return 4 * (n * hidden + sum(int(f.numel()) for f in feats))
 
-    for name, fn in (("gru_seq", b_gru_seq), ("agg_gru_cell", b_agg), ("segment_reduce", b_seg),
+    for name, fn in (("gru_seq", b_gru_seq), ("agg_gru_cell", b_agg), ("agg_gru_cell_tc", b_agg_tc), ("segment_reduce", b_seg),
                      ("dense", b_dense), ("csr_build", b_csr), ("gru_cell", b_gru_cell),
                      ("mlp_head", b_mlp_head), ("dense_head", b_dense_head), ("init_state", b_init),
                      ("length_order", zero), ("seq_meta", zero), ("steps_build", zero),

@@ -16,9 +16,9 @@
 // that computes the states, while the gather warps are already reducing the next tile.
 //
 // Roles of the 512-thread persistent CTA (one per SM), mbarriers between them:
-//   warps 0-7    gather: rowptr slice -> edge-balanced row ranges per sub-warp -> software-pipelined
-//                flat walk over the tile's slots (8 row loads in flight behind the 8 being summed,
-//                column indices two batches ahead) -> x operand images
+//   warps 0-7    gather: rowptr slice -> edge-balanced row ranges per sub-warp -> flat walk over the tile's
+//                slots through a cp.async ring in shared memory (16 rows in flight per sub-warp behind the 4
+//                being summed, column indices one chunk ahead) -> x operand images
 //   warps 8-11   epilogue: TMEM -> gates -> staging tile -> TMA stores (thread = one destination)
 //   warp  12     MMA issuer (one lane)
 //   warp  13     TMA producer of the prepared weight chunks (gru_cell_tc prep layout)
@@ -45,7 +45,8 @@ constexpr int MMA_WARP = 12, TMA_WARP = 13, HLOAD_WARP0 = 14, HLOAD_THREADS = 64
 constexpr int AGG_THREADS = 512;
 constexpr int ROWS = 128;
 constexpr int A_IMG = ROWS * 128;                       // one [128 x 32] fp32 image
-constexpr int DEPTH = 8;                                // row loads per batch and lane
+constexpr int BATCH = 4;                                // gathered rows per cp.async group
+constexpr int NB = 5;                                   // batches in a sub-warp's ring: NB - 1 in flight
 constexpr int BAR_GATHER = 1, BAR_EPI = 2, BAR_HLOAD = 3;   // named barriers (0 = __syncthreads)
 
 struct OutMaps {
@@ -80,16 +81,19 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     const __grid_constant__ OutMaps maps, int n_out, int out_row0, float* __restrict__ agg_out) {
   constexpr int NC = U / 32;                 // K chunks per operand
   constexpr int B_IMG = 3 * U * 128;         // one weight image (hi or lo) of a chunk
-  constexpr int STAGE = 2 * A_IMG + 2 * B_IMG;
+  constexpr int STAGE_A = 2 * A_IMG;         // operand stage: hi + lo image of one 32-column chunk
   constexpr int DCOLS = 4 * U;               // accumulator columns
   constexpr int G = U / 4;                   // gather lanes per destination
   constexpr int NG = GATHER_THREADS / G;     // destinations reduced at the same time
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* out_stage = smem + 2 * STAGE;           // NC boxes of [128 x 32] fp32, SWIZZLE_128B
+  unsigned char* b_buf = smem + 2 * STAGE_A;             // ONE weight chunk (hi + lo): the tile time is the gather's
+  unsigned char* out_stage = b_buf + 2 * B_IMG;          // NC boxes of [128 x 32] fp32, SWIZZLE_128B
+  unsigned char* ring = out_stage + NC * A_IMG;          // gathered rows in flight: NG rings of NB x BATCH rows
+  constexpr int RING_GROUP = NB * BATCH * U * 4;
   __shared__ uint64_t bar_stage[2];          // the UMMAs that read the stage are done
   __shared__ uint64_t bar_full[2];           // operand images of the stage are in place
-  __shared__ uint64_t bar_b[2];              // weight chunk landed (complete_tx)
+  __shared__ uint64_t bar_b;                 // weight chunk landed (complete_tx)
   __shared__ uint64_t bar_acc[2];            // accumulator complete
   __shared__ uint64_t bar_drained[2];        // accumulator read by every epilogue thread
   __shared__ uint32_t tmem_base_s;
@@ -99,9 +103,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_stage[i], 1); mbar_init(&bar_full[i], 1); mbar_init(&bar_b[i], 1);
+      mbar_init(&bar_stage[i], 1); mbar_init(&bar_full[i], 1);
       mbar_init(&bar_acc[i], 1); mbar_init(&bar_drained[i], EPI_THREADS);
     }
+    mbar_init(&bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 2 * DCOLS);
@@ -128,12 +133,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
         const int s = ctr & 1;
         const uint32_t use = ctr >> 1;
         if (lane == 0) {
-          unsigned char* st = smem + s * STAGE;
+          unsigned char* st = smem + s * STAGE_A;
           if (c == 0 && acc_uses[ab] > 0) mbar_wait(&bar_drained[ab], (acc_uses[ab] - 1) & 1);
           mbar_wait(&bar_full[s], use & 1);
-          mbar_wait(&bar_b[s], use & 1);
+          mbar_wait(&bar_b, ctr & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+          const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = smem_u32(b_buf), b_lo = b_hi + B_IMG;
           if (c < NC) {
             umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 3 * U, c > 0);
           } else {
@@ -150,13 +155,11 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   } else if (warp == TMA_WARP) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int c = 0; c < 2 * NC; ++c, ++ctr) {
-        const int s = ctr & 1;
-        const uint32_t use = ctr >> 1;
         if (lane == 0) {
-          if (use > 0) mbar_wait(&bar_stage[s], (use - 1) & 1);
-          mbar_expect_tx(&bar_b[s], 2 * B_IMG);
-          bulk_g2s(smem + s * STAGE + 2 * A_IMG, reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG),
-                   2 * B_IMG, &bar_b[s]);
+          // the weight buffer is free when the UMMAs of the previous chunk are done: its stage's commit
+          if (ctr > 0) mbar_wait(&bar_stage[(ctr - 1) & 1], ((ctr - 1) >> 1) & 1);
+          mbar_expect_tx(&bar_b, 2 * B_IMG);
+          bulk_g2s(b_buf, reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG), 2 * B_IMG, &bar_b);
         }
         __syncwarp();
       }
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m0 + r < n) v[j] = ldg_f4(h + (m0 + r) * U + c * 32 + c4 * 4);
         }
-        unsigned char* st = smem + s * STAGE;
+        unsigned char* st = smem + s * STAGE_A;
         if (use > 0) mbar_wait(&bar_stage[s], (use - 1) & 1);
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
@@ -192,12 +195,17 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
       }
     }
   } else if (warp < GATHER_WARPS) {
-    // ---- gather: one sub-warp of G lanes per destination, rows handed out in edge-balanced ranges
+    // ---- gather: one sub-warp of G lanes per destination range, rows handed out in edge-balanced ranges.
+    // Rows in flight live in shared memory, not in registers: every lane copies its 16 bytes of a gathered row
+    // with cp.async into the sub-warp's private ring (NB batches of BATCH rows) and reads back only what it
+    // copied itself, so the ring needs no barrier; NB - 1 batches (16 rows) are in flight behind the one being
+    // summed, 16 sub-warps (U = 64) x 16 rows x 256 B = 64 KB per SM, which is what the HBM latency asks for.
     const int gl = lane & (G - 1);                         // lane inside the sub-warp
     const int grp = tid / G;                               // sub-warp of the CTA, 0..NG-1
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int chunk = gl >> 3, c4 = gl & 7;                // which x chunk / 16-byte column of it this lane feeds
     const float init = (OP == IGN_OP_MAX) ? -INFINITY : 0.0f;
+    unsigned char* my_ring = ring + grp * RING_GROUP + gl * 16;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t m0 = tile * ROWS;
       // the x stages of this tile are free once the UMMAs of their previous use are done (long ago)
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
       };
       const int b0 = bound(grp), b1 = bound(grp + 1);
       const int eb0 = s_rp[b0], eb1 = s_rp[b1];
-      unsigned char* img_hi = smem + ((ctr + chunk) & 1) * STAGE;
+      unsigned char* img_hi = smem + ((ctr + chunk) & 1) * STAGE_A;
       unsigned char* img_lo = img_hi + A_IMG;
 
       int row = b0;
@@ -246,42 +254,56 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
         row_end = s_rp[min(row + 1, ROWS)];
         acc = make_float4(init, init, init, init);
       };
-      // column indices of batch b: lanes 0..7 of the sub-warp hold slots eb0 + 8 b + lane
-      auto load_idx = [&](int b) -> int {
-        const int e = eb0 + DEPTH * b + gl;
-        return (gl < DEPTH && e < eb1) ? __ldg(col + e) : -1;
+      // column indices arrive G at a time (one coalesced load per sub-warp), one chunk ahead of their use
+      auto load_idx = [&](int k) -> int {
+        const int e = eb0 + G * k + gl;
+        return e < eb1 ? __ldg(col + e) : -1;
       };
-      auto issue = [&](int b, int idx, float4 (&v)[DEPTH]) {
+      // batch b of the range -> ring slot b % NB: this lane's 16 bytes of each of its BATCH rows
+      auto issue = [&](int b, int slot, int idx, int j) {
 #pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-          const int c = __shfl_sync(gmask, idx, u, G);
-          if (eb0 + DEPTH * b + u < eb1 && c >= 0) v[u] = ldg_f4(src + (int64_t)c * U + gl * 4);
-          else v[u] = make_float4(init, init, init, init);
+        for (int u = 0; u < BATCH; ++u) {
+          const int c = __shfl_sync(gmask, idx, j * BATCH + u, G);
+          unsigned char* dst = my_ring + (slot * BATCH + u) * (U * 4);
+          if (eb0 + BATCH * b + u < eb1) {
+            if (c >= 0) cp_async16(dst, src + (int64_t)c * U + gl * 4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(init, init, init, init);   // a slot no edge claimed
+          }
         }
+        cp_async_commit();
       };
-      auto consume = [&](int b, const float4 (&v)[DEPTH]) {
+      auto consume = [&](int b, int slot) {
 #pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-          const int e = eb0 + DEPTH * b + u;
+        for (int u = 0; u < BATCH; ++u) {
+          const int e = eb0 + BATCH * b + u;
           if (e < eb1) {
             while (e >= row_end) flush();
-            acc_row<OP>(acc, v[u]);
+            acc_row<OP>(acc, *reinterpret_cast<const float4*>(my_ring + (slot * BATCH + u) * (U * 4)));
           }
         }
       };
-      const int nb = (eb1 - eb0 + DEPTH - 1) / DEPTH;
+      const int nb = (eb1 - eb0 + BATCH - 1) / BATCH;
       if (nb > 0) {
-        float4 va[DEPTH], vb[DEPTH];
-        int idx_a = load_idx(0), idx_b = load_idx(1);
-        issue(0, idx_a, va);
-        for (int b = 0; b < nb; b += 2) {
-          idx_a = load_idx(b + 2);
-          if (b + 1 < nb) issue(b + 1, idx_b, vb);
-          consume(b, va);
-          if (b + 1 < nb) {
-            idx_b = load_idx(b + 3);
-            if (b + 2 < nb) issue(b + 2, idx_a, va);
-            consume(b + 1, vb);
+        constexpr int CPB = G / BATCH;                     // batches per index chunk
+        int idx_cur, idx_next = load_idx(0);
+        int islot = 0, cslot = 0;
+        // the issue pointer runs NB - 1 batches ahead of the consume pointer; empty groups are committed past the
+        // end so that "at most NB - 1 groups pending" always means "the batch being consumed has landed"
+        for (int k = 0; k * CPB < nb + NB - 1; ++k) {
+          idx_cur = idx_next;
+          idx_next = load_idx(k + 1);
+#pragma unroll
+          for (int j = 0; j < CPB; ++j) {
+            const int b = k * CPB + j;                     // batch to issue; b - (NB - 1) is consumed
+            if (b < nb + NB - 1) {
+              issue(b, islot, idx_cur, j);
+              islot = islot + 1 == NB ? 0 : islot + 1;
+              if (b >= NB - 1) {
+                cp_async_wait<NB - 1>();
+                consume(b - (NB - 1), cslot);
+                cslot = cslot + 1 == NB ? 0 : cslot + 1;
+              }
+            }
           }
         }
       }
@@ -386,7 +408,8 @@ template <int U, int OP>
 int launch(const int* rowptr, const int* col, const float* src, const float* h, int64_t n, const float* wimg,
            const float* bias, const OutMaps& maps, int n_out, int out_row0, float* agg_out, int grid,
            cudaStream_t st) {
-  constexpr size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * 3 * U * 128) + (size_t)(U / 32) * A_IMG;
+  constexpr size_t smem = 1024 + 2 * (size_t)(2 * A_IMG) + 2 * (size_t)(3 * U * 128) + (size_t)(U / 32) * A_IMG +
+                          (size_t)(GATHER_THREADS / (U / 4)) * NB * BATCH * U * 4;
   IGN_CUDA(cudaFuncSetAttribute(agg_gru_tc_kernel<U, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   agg_gru_tc_kernel<U, OP><<<grid, AGG_THREADS, smem, st>>>(rowptr, col, src, h, n, wimg, bias, maps, n_out, out_row0,
                                                             agg_out);
@@ -413,7 +436,7 @@ extern "C" int ign_agg_gru_cell_tc(int op, const int32_t* rowptr, const int32_t*
               "IGNNITION: agg_gru_cell_tc: between 1 and %d output buffers", IGN_MAX_PEERS);
   IGN_REQUIRE(out_row0 + num_dst < ((int64_t)1 << 31), IGN_ERR_UNSUPPORTED, "IGNNITION: agg_gru_cell_tc: int32 rows only");
   if (num_dst == 0) return IGN_OK;
-  IGN_REQUIRE(rowptr && col && src_states && h_dst && kernel && recurrent_kernel && bias, IGN_ERR_INVALID,
+  IGN_REQUIRE(rowptr && src_states && h_dst && kernel && recurrent_kernel && bias, IGN_ERR_INVALID,   // col: null iff no slot
               "IGNNITION: agg_gru_cell_tc: null pointer");
   IGN_REQUIRE(ws && ws_bytes >= ign_gru_cell_tc_ws(units), IGN_ERR_WORKSPACE,
               "IGNNITION: agg_gru_cell_tc: workspace too small (%zu < %zu)", ws_bytes, ign_gru_cell_tc_ws(units));

@@ -87,15 +87,17 @@ def normalize(model: ModelDescription, x: dict, y=None, namespace: Optional[dict
 
 
 def samples_of(model: ModelDescription, directory: str, training: bool, shuffle: bool = False,
-               namespace: Optional[dict] = None, repeat: bool = False) -> Iterator:
-    """The reference's input_fn as a Python iterator of normalised tensor dicts (+ labels)."""
+               namespace: Optional[dict] = None, repeat: bool = False, seed: Optional[int] = None) -> Iterator:
+    """The reference's input_fn as a Python iterator of normalised tensor dicts (+ labels).  ``seed``: the file
+    shuffle of pass k uses seed + k, so that all ranks of a data-parallel run read the same stream."""
     feats = [f.name for f in model.get_all_features()]
     out_name, _, _ = model.get_output_info()
     adj, inter = model.get_adjecency_info(), model.get_interleave_tensors()
     extra = [a for a in model.get_additional_input_names() if a not in feats]
+    epoch = 0
     while True:
         n = 0
-        for sample in read_dataset(directory, shuffle):
+        for sample in read_dataset(directory, shuffle, None if seed is None else seed + epoch):
             n += 1
             if training:
                 x, y = sample_to_tensors(sample, feats, out_name, adj, inter, extra, True)
@@ -105,6 +107,7 @@ def samples_of(model: ModelDescription, directory: str, training: bool, shuffle:
                                 namespace=namespace)
         if not repeat or n == 0:
             return
+        epoch += 1
 
 
 def native_batches(model: ModelDescription, engine, directory: str, training: bool,
@@ -144,23 +147,53 @@ def eval_metrics(labels: np.ndarray, preds: np.ndarray) -> Dict[str, float]:
 def save_checkpoint(engine, trainer, model_dir: str, keep_max: int) -> str:
     os.makedirs(model_dir, exist_ok=True)
     path = os.path.join(model_dir, "model.ckpt-%d.npz" % trainer.step)
-    np.savez(path, __step__=np.int64(trainer.step), **engine.get_weights())
-    old = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.npz")), key=os.path.getmtime)
+    np.savez(path, __step__=np.int64(trainer.step), __adam_m__=trainer.m.cpu().numpy(),
+             __adam_v__=trainer.v.cpu().numpy(), **engine.get_weights())
+    old = sorted(glob.glob(os.path.join(model_dir, "model.ckpt-*.npz")), key=_ckpt_step)
     for p in old[:-keep_max] if keep_max > 0 else []:
         os.remove(p)
     return path
 
 
-def load_checkpoint(engine, path: str) -> int:
-    """Warm start: every stored kernel / recurrent_kernel / bias variable (framework_operations.py:126-129)."""
+def _ckpt_step(path: str) -> int:
+    name = os.path.basename(path)
+    try:
+        return int(name[len("model.ckpt-"):].split(".")[0])
+    except ValueError:
+        return -1
+
+
+def load_checkpoint(engine, path: str, trainer=None) -> int:
+    """Warm start: every stored kernel / recurrent_kernel / bias variable (framework_operations.py:126-129).
+    With ``trainer`` the Adam moments and the step are restored too (a resume, not only a warm start).
+    Reads this engine's ``.npz`` checkpoints and TensorFlow checkpoints of the reference (``model.ckpt-N.index``
+    + ``.data-*``: ``tf_checkpoint.read``), whose variables map 1:1 by name and layout."""
+    from . import tf_checkpoint
     if os.path.isdir(path):
-        files = sorted(glob.glob(os.path.join(path, "model.ckpt-*.npz")), key=os.path.getmtime)
-        if not files:
-            raise RuntimeError("IGNNITION: no checkpoint found in " + path)
-        path = files[-1]
+        files = sorted(glob.glob(os.path.join(path, "model.ckpt-*.npz")), key=_ckpt_step)
+        if files:
+            path = files[-1]
+        else:
+            prefix = tf_checkpoint.latest(path)
+            if prefix is None:
+                raise RuntimeError("IGNNITION: no checkpoint found in " + path)
+            path = prefix
+    if tf_checkpoint.is_tf_checkpoint(path):
+        weights, step = tf_checkpoint.read_for_engine(path, engine)
+        engine.set_weights(weights)
+        if trainer is not None:
+            trainer.step = step
+        return step
     data = np.load(path)
-    engine.set_weights({k: data[k] for k in data.files if k != "__step__"})
-    return int(data["__step__"]) if "__step__" in data.files else 0
+    engine.set_weights({k: data[k] for k in data.files if not k.startswith("__")})
+    step = int(data["__step__"]) if "__step__" in data.files else 0
+    if trainer is not None:
+        trainer.step = step
+        if "__adam_m__" in data.files:
+            import torch
+            trainer.m.copy_(torch.from_numpy(data["__adam_m__"]))
+            trainer.v.copy_(torch.from_numpy(data["__adam_v__"]))
+    return step
 
 
 def evaluate(model: ModelDescription, engine, directory: str, n_samples: int, shuffle: bool = False,
@@ -224,15 +257,17 @@ def train_and_evaluate(model: ModelDescription, namespace: Optional[dict] = None
         torch.distributed.init_process_group("nccl", device_id=engine.device)
     trainer = Trainer(engine, world_size=world)
     if cfg.has_option("PATHS", "warm_start_path") and cfg["PATHS"]["warm_start_path"].strip():
-        load_checkpoint(engine, cfg["PATHS"]["warm_start_path"])
+        load_checkpoint(engine, cfg["PATHS"]["warm_start_path"],
+                        trainer if opt.get("resume", "False") == "True" else None)
     model_dir = os.path.join(cfg["PATHS"]["model_dir"], "experiment_" + str(datetime.datetime.now()).replace(" ", "_"))
     batch = int(opt["batch_size"])
     steps = int(opt["train_steps"]) if max_steps is None else max_steps
     keep = int(opt.get("keep_checkpoint_max", 20))
     ckpt_secs, eval_secs = float(opt.get("save_checkpoints_secs", 300)), float(opt.get("throttle_secs", 300))
+    # every rank reads the SAME stream (file shuffle seeded identically on all ranks) and keeps its slice of each
+    # global batch; the global prediction count is checked across ranks below
     it = samples_of(model, cfg["PATHS"]["train_dataset"], True, opt.get("shuffle_train_samples", "True") == "True",
-                    namespace, repeat=True)
-    # every rank reads the same stream and keeps its slice of each global batch
+                    namespace, repeat=True, seed=int(opt.get("shuffle_seed", 0)) if world > 1 else None)
     t_ckpt = t_eval = time.time()
     history = []
     for step in range(steps):
@@ -241,6 +276,13 @@ def train_and_evaluate(model: ModelDescription, namespace: Optional[dict] = None
             break
         mine = chunk[rank::world] if world > 1 else chunk
         n_glob = sum(c[1].size for c in chunk)
+        if world > 1 and step % 100 == 0:         # the 1/N of the loss must be the same number on every rank
+            chk = torch.tensor([n_glob, -n_glob], dtype=torch.int64, device=engine.device)
+            torch.distributed.all_reduce(chk, op=torch.distributed.ReduceOp.MAX)
+            if int(chk[0]) != n_glob or int(-chk[1]) != n_glob:
+                raise RuntimeError("IGNNITION: the ranks of the data-parallel run read different sample streams "
+                                   "(global batch of %d predictions here, %d..%d across ranks)"
+                                   % (n_glob, int(-chk[1]), int(chk[0])))
         graph = engine.prepare([c[0] for c in mine], labels=[c[1] for c in mine], training=True)
         trainer.train_step(graph, global_n=n_glob)
         if step % 10 == 0:                        # LoggingTensorHook every 10 iterations (:820-824)
@@ -284,9 +326,20 @@ def predict(model: ModelDescription, namespace: Optional[dict] = None, engine=No
     if fn is None:
         _log("A denormalization function for output %s was not defined. The output will be normalized." % out_name)
     result = []
-    for x in samples_of(model, cfg["PATHS"]["predict_dataset"], False, False, namespace):
-        p = engine(x).cpu().numpy().reshape(-1)
-        result.append(np.asarray(fn(p, out_name)) if fn is not None else p)
+    it = samples_of(model, cfg["PATHS"]["predict_dataset"], False, False, namespace)
+    out_entity = [o for o in model.get_readout_operations() if o.type == "predict"][0].input[0]
+    chunk_size = int(cfg["TRAINING_OPTIONS"].get("predict_batch", 256)) if cfg.has_section("TRAINING_OPTIONS") else 256
+    while True:                                   # block-diagonal batches: one forward per chunk, split per sample
+        chunk = list(itertools.islice(it, chunk_size))
+        if not chunk:
+            break
+        p = engine.forward(engine.prepare(chunk)).cpu().numpy().reshape(-1)
+        off = 0
+        for x in chunk:
+            n = int(x["num_" + out_entity])
+            q = p[off:off + n]
+            off += n
+            result.append(np.asarray(fn(q, out_name)) if fn is not None else q)
     return result
 
 

@@ -21,7 +21,7 @@ import json
 import math
 import random
 import tarfile
-from typing import Dict, Iterable, Iterator, List, Sequence, Tuple
+from typing import Optional, Dict, Iterable, Iterator, List, Sequence, Tuple
 
 import numpy as np
 
@@ -144,11 +144,14 @@ def sample_to_tensors(sample: dict, feature_names: Iterable[str], output_name, a
     return (data, output) if training else data
 
 
-def read_dataset(directory: str, shuffle: bool = False) -> Iterator[dict]:
-    """Yield raw samples from every ``*.tar.gz`` (each holding ``data.json``) of a directory."""
-    files = glob.glob(str(directory) + '/*.tar.gz')
+def read_dataset(directory: str, shuffle: bool = False, seed: Optional[int] = None) -> Iterator[dict]:
+    """Yield raw samples from every ``*.tar.gz`` (each holding ``data.json``) of a directory.
+
+    The file list is sorted before it is shuffled, and ``seed`` makes the shuffle reproducible: every rank of a
+    data-parallel run must walk the files in the SAME order (it keeps a slice of each global batch)."""
+    files = sorted(glob.glob(str(directory) + '/*.tar.gz'))
     if shuffle:
-        random.shuffle(files)
+        (random.Random(seed) if seed is not None else random).shuffle(files)
     for path in files:
         with tarfile.open(path, 'r:gz') as tar:
             try:
