@@ -91,7 +91,11 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   unsigned char* out_stage = b_buf + 2 * B_IMG;          // NC boxes of [128 x 32] fp32, SWIZZLE_128B
   unsigned char* ring = out_stage + NC * A_IMG;          // gathered rows in flight: NG rings of NB x BATCH rows
   constexpr int RING_GROUP = NB * BATCH * U * 4;
-  __shared__ uint64_t bar_stage[2];          // the UMMAs that read the stage are done
+  // bar_mma[c]: the UMMAs of chunk c of a tile are done (phase = tile count of the CTA).  One barrier per chunk of
+  // the tile, not per stage: a stage is used twice per tile at U = 64 (x chunk, then h chunk) and its two users wait
+  // for each other's use only -- with one barrier per stage the gather warps would test a parity two phases back
+  // and pass while the x chunk they overwrite is still being read.
+  __shared__ uint64_t bar_mma[4];
   __shared__ uint64_t bar_full[2];           // operand images of the stage are in place
   __shared__ uint64_t bar_b;                 // weight chunk landed (complete_tx)
   __shared__ uint64_t bar_acc[2];            // accumulator complete
@@ -103,9 +107,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_stage[i], 1); mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_full[i], 1);
       mbar_init(&bar_acc[i], 1); mbar_init(&bar_drained[i], EPI_THREADS);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_mma[i], 1);
     mbar_init(&bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -121,8 +126,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int64_t ntiles = (n + ROWS - 1) / ROWS;
-  // every role walks the same chunk sequence: chunk ctr of the CTA uses stage ctr & 1 for the (ctr >> 1)-th time
+  // every role walks the same chunk sequence: chunk ctr of the CTA (= chunk ctr % 2NC of its tile ctr / 2NC) uses
+  // stage ctr & 1 for the (ctr >> 1)-th time
   uint32_t ctr = 0;
+  uint32_t lt = 0;                           // tiles this CTA has finished (phase of the per-chunk barriers)
 
   if (warp == MMA_WARP) {
     int ab = 0;
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
             umma_chunk_3x(d, a_hi, a_lo, b_hi, b_lo, 2 * U, true);
             umma_chunk_3x(d + 3 * U, a_hi, a_lo, b_hi + 2 * U * 128, b_lo + 2 * U * 128, U, c > NC);
           }
-          umma_commit(&bar_stage[s]);
+          umma_commit(&bar_mma[c]);
           if (c == 2 * NC - 1) umma_commit(&bar_acc[ab]);
         }
         __syncwarp();
@@ -153,11 +160,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
       acc_uses[ab] += 1;
     }
   } else if (warp == TMA_WARP) {
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       for (int c = 0; c < 2 * NC; ++c, ++ctr) {
         if (lane == 0) {
-          // the weight buffer is free when the UMMAs of the previous chunk are done: its stage's commit
-          if (ctr > 0) mbar_wait(&bar_stage[(ctr - 1) & 1], ((ctr - 1) >> 1) & 1);
+          // the weight buffer is free when the UMMAs of the previous chunk are done
+          if (c > 0) mbar_wait(&bar_mma[c - 1], lt & 1);
+          else if (lt > 0) mbar_wait(&bar_mma[2 * NC - 1], (lt - 1) & 1);
           mbar_expect_tx(&bar_b, 2 * B_IMG);
           bulk_g2s(b_buf, reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG), 2 * B_IMG, &bar_b);
         }
@@ -168,12 +176,11 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     // ---- h loaders: chunk c (32 columns of the old state rows) -> hi / lo images of its stage
     const int ht = tid - HLOAD_WARP0 * 32;
     constexpr int PER = 1024 / HLOAD_THREADS;              // float4 per thread per chunk
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int64_t m0 = tile * ROWS;
       ctr += NC;                                           // the x chunks of the tile
       for (int c = 0; c < NC; ++c, ++ctr) {
         const int s = ctr & 1;
-        const uint32_t use = ctr >> 1;
         float4 v[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
@@ -183,7 +190,9 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
           if (m0 + r < n) v[j] = ldg_f4(h + (m0 + r) * U + c * 32 + c4 * 4);
         }
         unsigned char* st = smem + s * STAGE_A;
-        if (use > 0) mbar_wait(&bar_stage[s], (use - 1) & 1);
+        // previous user of this stage: x chunk c of this tile (U = 64), or the h chunk of the previous tile (U = 32)
+        if (NC == 2) mbar_wait(&bar_mma[c], lt & 1);
+        else if (lt > 0) mbar_wait(&bar_mma[1], (lt - 1) & 1);
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
           const int idx = ht + j * HLOAD_THREADS;
@@ -206,13 +215,13 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     const int chunk = gl >> 3, c4 = gl & 7;                // which x chunk / 16-byte column of it this lane feeds
     const float init = (OP == IGN_OP_MAX) ? -INFINITY : 0.0f;
     unsigned char* my_ring = ring + grp * RING_GROUP + gl * 16;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int64_t m0 = tile * ROWS;
-      // the x stages of this tile are free once the UMMAs of their previous use are done (long ago)
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const uint32_t cc = ctr + c, use = cc >> 1;
-        if (use > 0) mbar_wait(&bar_stage[cc & 1], (use - 1) & 1);
+      // the x stages of this tile are free once the UMMAs of their previous use are done (long ago): the h chunks of
+      // the previous tile at U = 64 (same stages), the x chunk of the previous tile at U = 32
+      if (lt > 0) {
+        if (NC == 2) { mbar_wait(&bar_mma[2], (lt - 1) & 1); mbar_wait(&bar_mma[3], (lt - 1) & 1); }
+        else mbar_wait(&bar_mma[0], (lt - 1) & 1);
       }
       for (int i = tid; i <= ROWS; i += GATHER_THREADS) {
         const int64_t r = m0 + i;

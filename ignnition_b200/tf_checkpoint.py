@@ -265,7 +265,8 @@ def write(prefix: str, tensors: Dict[str, np.ndarray], block_entries: int = 4):
     data = bytearray()
     items: List[Tuple[bytes, bytes]] = [(b"", b"\x08\x01\x1a\x02\x08\x01")]     # num_shards = 1, version.producer = 1
     for name in sorted(tensors):
-        a = np.ascontiguousarray(tensors[name])
+        a = np.asarray(tensors[name])
+        a = a if a.ndim == 0 or a.flags.c_contiguous else np.ascontiguousarray(a)
         if a.dtype not in DTYPE_IDS:
             raise RuntimeError("IGNNITION: dtype %s cannot be written to a checkpoint" % a.dtype)
         raw = a.astype(a.dtype.newbyteorder("<")).tobytes()

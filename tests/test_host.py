@@ -514,3 +514,82 @@ def test_native_ingest_position_tables_of_multi_source_sequences(interleave):
     for k in want.arrays:
         assert got.arrays[k].dtype == want.arrays[k].dtype, k
         assert np.array_equal(got.arrays[k], want.arrays[k]), k
+
+
+# ------------------------------------------------------------------ round 2: host logic of the new pieces
+def test_tf_checkpoint_bundle_round_trip(tmp_path):
+    """The TensorFlow tensor-bundle reader against bundles written in the same format (several data blocks,
+    prefix 'model.ckpt-N'); optimizer slots are skipped, names match by suffix + shape."""
+    from ignnition_b200 import tf_checkpoint as tfc
+    rng = np.random.RandomState(0)
+    tensors = {"comnet_model/path_update/kernel": rng.randn(32, 96).astype(np.float32),
+               "comnet_model/path_update/recurrent_kernel": rng.randn(32, 96).astype(np.float32),
+               "comnet_model/path_update/bias": rng.randn(2, 96).astype(np.float32),
+               "comnet_model/path_update/kernel/Adam": rng.randn(32, 96).astype(np.float32),
+               "comnet_model/path_update/kernel/Adam_1": rng.randn(32, 96).astype(np.float32),
+               "global_step": np.asarray(1234, np.int64),
+               "scalar_f64": np.asarray(2.5, np.float64)}
+    prefix = str(tmp_path / "model.ckpt-1234")
+    tfc.write(prefix, tensors, block_entries=3)
+    assert tfc.is_tf_checkpoint(prefix) and tfc.latest(str(tmp_path)) == prefix
+    got = tfc.read(prefix)
+    assert set(got) == set(tensors)
+    for k, v in tensors.items():
+        assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v)
+
+    class FakeEngine:
+        param_table = {"path_update/kernel": (0, (32, 96)), "path_update/recurrent_kernel": (0, (32, 96)),
+                       "path_update/bias": (0, (2, 96))}
+    w, step = tfc.read_for_engine(prefix, FakeEngine)
+    assert step == 1234 and np.array_equal(w["path_update/kernel"], tensors["comnet_model/path_update/kernel"])
+    FakeEngine.param_table = dict(FakeEngine.param_table, **{"link_update/kernel": (0, (32, 96))})
+    with pytest.raises(RuntimeError, match="IGNNITION: the checkpoint"):
+        tfc.read_for_engine(prefix, FakeEngine)
+    with pytest.raises(RuntimeError, match="bad magic"):
+        bad = tmp_path / "x.index"
+        bad.write_bytes(b"\0" * 64)
+        tfc.read_index(str(bad))
+
+
+def test_tf_checkpoint_snappy_and_prefix_compression():
+    """leveldb block decoding with shared key prefixes, and the snappy decoder (literal + the three copy forms)"""
+    from ignnition_b200 import tf_checkpoint as tfc
+    body = b""
+    for shared, key, val in ((0, b"layer/bias", b"A"), (6, b"kernel", b"BC"), (0, b"z", b"")):
+        body += bytes([shared, len(key), len(val)]) + key + val
+    block = body + (0).to_bytes(4, "little") + (1).to_bytes(4, "little")
+    assert list(tfc._block_entries(block)) == [(b"layer/bias", b"A"), (b"layer/kernel", b"BC"), (b"z", b"")]
+    # "abcdabcdabcdabcd" + "x": literal 'abcd', copy(off 4, len 12) as 2-byte-offset form, literal 'x'
+    comp = bytes([17]) + bytes([3 << 2]) + b"abcd" + bytes([((12 - 1) << 2) | 2, 4, 0]) + bytes([0]) + b"x"
+    assert tfc._snappy(comp) == b"abcd" * 4 + b"x"
+    comp1 = bytes([8]) + bytes([3 << 2]) + b"abcd" + bytes([((4 - 4) << 2) | 1, 4])      # 1-byte-offset form
+    assert tfc._snappy(comp1) == b"abcdabcd"
+
+
+def test_read_dataset_shuffle_is_reproducible_across_ranks(tmp_path):
+    """every rank of a data-parallel run must read the same sample stream."""
+    import io
+    import tarfile
+    from ignnition_b200.generator import read_dataset
+    for k in range(6):
+        data = json.dumps([{"id": 10 * k + j} for j in range(3)]).encode()
+        with tarfile.open(tmp_path / ("s%d.tar.gz" % k), "w:gz") as tar:
+            info = tarfile.TarInfo("data.json")
+            info.size = len(data)
+            tar.addfile(info, io.BytesIO(data))
+    a = [s["id"] for s in read_dataset(str(tmp_path), True, seed=5)]
+    b = [s["id"] for s in read_dataset(str(tmp_path), True, seed=5)]
+    c = [s["id"] for s in read_dataset(str(tmp_path), True, seed=6)]
+    plain = [s["id"] for s in read_dataset(str(tmp_path), False)]
+    assert a == b and sorted(a) == sorted(plain) == plain and a != c
+
+
+def test_partition_bounds_and_split_counts():
+    from ignnition_b200.parallel import node_bounds, split_counts
+    for n in (0, 1, 7, 1000, 10_000_000):
+        for world in (1, 2, 3, 8):
+            b = node_bounds(n, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n
+            sizes = [b[r + 1] - b[r] for r in range(world)]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+    assert split_counts([0, 3, 3, 10]) == [3, 0, 7]
