@@ -65,6 +65,36 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// mbarrier wait of a role that waits for most of a tile's time: back off between polls so that the spin does not
+// take issue slots from the gather warps (profiles/r2_agg_gru.md: 56 % of the warp instructions were polls)
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)      // suspend-time hint, ns: sleep in hardware, wake on arrive
+        : "memory");
+  }
+}
+
+// explicit shared-space accesses (through a generic pointer the ring reads compiled to generic LD.E)
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t saddr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem) : "memory");
+}
+
 template <int OP>
 __device__ __forceinline__ void acc_row(float4& a, const float4& v) {
   if (OP == IGN_OP_MAX) {
@@ -74,22 +104,30 @@ __device__ __forceinline__ void acc_row(float4& a, const float4& v) {
   }
 }
 
-template <int U, int OP>
+// TMA_OUT: the new states leave through the swizzled staging tile and TMA tensor stores (any n_out); otherwise
+// (one output, U = 64) the epilogue stores its rows itself and the staging tile's shared memory holds XRAW.
+// XRAW: the gather warps park the aggregated rows of a tile as plain fp32 and convert them into the operand images
+// at the end of the tile, so that reducing tile t + 1 does not wait for the UMMAs that still read tile t's images.
+template <int U, int OP, bool TMA_OUT>
 __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ src,
     const float* __restrict__ h, int64_t n, const float* __restrict__ wimg, const float* __restrict__ bias,
-    const __grid_constant__ OutMaps maps, int n_out, int out_row0, float* __restrict__ agg_out) {
+    const __grid_constant__ OutMaps maps, int n_out, int out_row0, float* __restrict__ agg_out,
+    float* __restrict__ out_direct, int dbg) {
   constexpr int NC = U / 32;                 // K chunks per operand
   constexpr int B_IMG = 3 * U * 128;         // one weight image (hi or lo) of a chunk
   constexpr int STAGE_A = 2 * A_IMG;         // operand stage: hi + lo image of one 32-column chunk
   constexpr int DCOLS = 4 * U;               // accumulator columns
   constexpr int G = U / 4;                   // gather lanes per destination
   constexpr int NG = GATHER_THREADS / G;     // destinations reduced at the same time
+  constexpr bool XRAW = (U == 32) || !TMA_OUT;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* b_buf = smem + 2 * STAGE_A;             // ONE weight chunk (hi + lo): the tile time is the gather's
   unsigned char* out_stage = b_buf + 2 * B_IMG;          // NC boxes of [128 x 32] fp32, SWIZZLE_128B
   unsigned char* ring = out_stage + NC * A_IMG;          // gathered rows in flight: NG rings of NB x BATCH rows
+  // [128][U] fp32 aggregated rows of the tile being reduced: its own region at U = 32, the staging tile's at U = 64
+  float* xraw = reinterpret_cast<float*>(U == 32 ? ring + NG * (NB * BATCH * U * 4) : out_stage);
   constexpr int RING_GROUP = NB * BATCH * U * 4;
   // bar_mma[c]: the UMMAs of chunk c of a tile are done (phase = tile count of the CTA).  One barrier per chunk of
   // the tile, not per stage: a stage is used twice per tile at U = 64 (x chunk, then h chunk) and its two users wait
@@ -130,11 +168,14 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   // stage ctr & 1 for the (ctr >> 1)-th time
   uint32_t ctr = 0;
   uint32_t lt = 0;                           // tiles this CTA has finished (phase of the per-chunk barriers)
+  // IGN_AGG_DBG=1 (profiling): only the gather warps run, nothing waits for anything (results are garbage)
+  const bool gather_only = dbg & 1;
+  const int64_t ntiles_other = gather_only ? 0 : ntiles;
 
   if (warp == MMA_WARP) {
     int ab = 0;
     uint32_t acc_uses[2] = {0, 0};
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ab ^= 1) {
+    for (int64_t tile = blockIdx.x; tile < ntiles_other; tile += gridDim.x, ab ^= 1) {
       const uint32_t d = tmem_base + ab * DCOLS;
       for (int c = 0; c < 2 * NC; ++c, ++ctr) {
         const int s = ctr & 1;
@@ -142,7 +183,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
         if (lane == 0) {
           unsigned char* st = smem + s * STAGE_A;
           if (c == 0 && acc_uses[ab] > 0) mbar_wait(&bar_drained[ab], (acc_uses[ab] - 1) & 1);
-          mbar_wait(&bar_full[s], use & 1);
+          mbar_wait_idle(&bar_full[s], use & 1);
           mbar_wait(&bar_b, ctr & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_IMG, b_hi = smem_u32(b_buf), b_lo = b_hi + B_IMG;
@@ -160,12 +201,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
       acc_uses[ab] += 1;
     }
   } else if (warp == TMA_WARP) {
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+    for (int64_t tile = blockIdx.x; tile < ntiles_other; tile += gridDim.x, ++lt) {
       for (int c = 0; c < 2 * NC; ++c, ++ctr) {
         if (lane == 0) {
           // the weight buffer is free when the UMMAs of the previous chunk are done
-          if (c > 0) mbar_wait(&bar_mma[c - 1], lt & 1);
-          else if (lt > 0) mbar_wait(&bar_mma[2 * NC - 1], (lt - 1) & 1);
+          if (c > 0) mbar_wait_idle(&bar_mma[c - 1], lt & 1);
+          else if (lt > 0) mbar_wait_idle(&bar_mma[2 * NC - 1], (lt - 1) & 1);
           mbar_expect_tx(&bar_b, 2 * B_IMG);
           bulk_g2s(b_buf, reinterpret_cast<const char*>(wimg) + (size_t)c * (2 * B_IMG), 2 * B_IMG, &bar_b);
         }
@@ -176,7 +217,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     // ---- h loaders: chunk c (32 columns of the old state rows) -> hi / lo images of its stage
     const int ht = tid - HLOAD_WARP0 * 32;
     constexpr int PER = 1024 / HLOAD_THREADS;              // float4 per thread per chunk
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+    for (int64_t tile = blockIdx.x; tile < ntiles_other; tile += gridDim.x, ++lt) {
       const int64_t m0 = tile * ROWS;
       ctr += NC;                                           // the x chunks of the tile
       for (int c = 0; c < NC; ++c, ++ctr) {
@@ -191,8 +232,8 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
         }
         unsigned char* st = smem + s * STAGE_A;
         // previous user of this stage: x chunk c of this tile (U = 64), or the h chunk of the previous tile (U = 32)
-        if (NC == 2) mbar_wait(&bar_mma[c], lt & 1);
-        else if (lt > 0) mbar_wait(&bar_mma[1], (lt - 1) & 1);
+        if (NC == 2) mbar_wait_idle(&bar_mma[c], lt & 1);
+        else if (lt > 0) mbar_wait_idle(&bar_mma[1], (lt - 1) & 1);
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
           const int idx = ht + j * HLOAD_THREADS;
@@ -211,18 +252,21 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     // summed, 16 sub-warps (U = 64) x 16 rows x 256 B = 64 KB per SM, which is what the HBM latency asks for.
     const int gl = lane & (G - 1);                         // lane inside the sub-warp
     const int grp = tid / G;                               // sub-warp of the CTA, 0..NG-1
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int chunk = gl >> 3, c4 = gl & 7;                // which x chunk / 16-byte column of it this lane feeds
     const float init = (OP == IGN_OP_MAX) ? -INFINITY : 0.0f;
-    unsigned char* my_ring = ring + grp * RING_GROUP + gl * 16;
+    const uint32_t my_ring = smem_u32(ring + grp * RING_GROUP + gl * 16);      // shared-space address
+    const int n_slots = __ldg(rowptr + n);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int64_t m0 = tile * ROWS;
       // the x stages of this tile are free once the UMMAs of their previous use are done (long ago): the h chunks of
       // the previous tile at U = 64 (same stages), the x chunk of the previous tile at U = 32
-      if (lt > 0) {
-        if (NC == 2) { mbar_wait(&bar_mma[2], (lt - 1) & 1); mbar_wait(&bar_mma[3], (lt - 1) & 1); }
-        else mbar_wait(&bar_mma[0], (lt - 1) & 1);
-      }
+      auto wait_x_stages = [&]() {
+        if (lt > 0 && !gather_only) {
+          if (NC == 2) { mbar_wait(&bar_mma[2], (lt - 1) & 1); mbar_wait(&bar_mma[3], (lt - 1) & 1); }
+          else mbar_wait(&bar_mma[0], (lt - 1) & 1);
+        }
+      };
+      bool stages_free = false;
       for (int i = tid; i <= ROWS; i += GATHER_THREADS) {
         const int64_t r = m0 + i;
         s_rp[i] = __ldg(rowptr + (r < n ? r : n));
@@ -257,69 +301,113 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
           r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
         }
         if (OP == IGN_OP_MAX && len == 0) r = make_float4(0.f, 0.f, 0.f, 0.f);
-        store_split(img_hi, img_lo, row, c4, r);
+        if (XRAW) {
+          sts_f4(smem_u32(xraw + row * U + gl * 4), r);
+        } else {
+          if (!stages_free) { wait_x_stages(); stages_free = true; }
+          store_split(img_hi, img_lo, row, c4, r);
+        }
         if (agg_out && m0 + row < n) st_f4(agg_out + (m0 + row) * U + gl * 4, r);
         ++row;
         row_end = s_rp[min(row + 1, ROWS)];
         acc = make_float4(init, init, init, init);
       };
-      // column indices arrive G at a time (one coalesced load per sub-warp), one chunk ahead of their use
-      auto load_idx = [&](int k) -> int {
-        const int e = eb0 + G * k + gl;
-        return e < eb1 ? __ldg(col + e) : -1;
+      // Batch k of the tile covers the slots [4 k, 4 k + 4) of the whole col array (absolute alignment).  Lane j of the
+      // sub-warp holds the four column indices of batch (chunk * G + j): one coalesced 16-byte load per lane covers G
+      // batches, is issued a whole chunk (G batches) before its first use, and the batch being issued gets its four
+      // indices by full-warp shuffles (both sub-warps of a warp run the same number of iterations, so the warp stays
+      // converged).  The loop body is kept SMALL (one copy of every path, nothing unrolled across batches): the first
+      // version ran out of the instruction caches (35 KB of loop body: profiles/r2_agg_gru.md).
+      const int kb0 = eb0 >> 2, nb = eb1 > eb0 ? ((eb1 + 3) >> 2) - kb0 : 0;
+      auto load_chunk = [&](int cb) -> int4 {              // indices of batch cb * G + gl
+        const int b = cb * G + gl, k = kb0 + b;
+        if (b >= nb) return make_int4(-1, -1, -1, -1);
+        if (4 * k + 3 < n_slots) return __ldg(reinterpret_cast<const int4*>(col) + k);
+        int4 r;                                            // the last, partial batch of the array
+        r.x = 4 * k < n_slots ? __ldg(col + 4 * k) : -1;
+        r.y = 4 * k + 1 < n_slots ? __ldg(col + 4 * k + 1) : -1;
+        r.z = 4 * k + 2 < n_slots ? __ldg(col + 4 * k + 2) : -1;
+        r.w = -1;
+        return r;
       };
-      // batch b of the range -> ring slot b % NB: this lane's 16 bytes of each of its BATCH rows
-      auto issue = [&](int b, int slot, int idx, int j) {
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-          const int c = __shfl_sync(gmask, idx, j * BATCH + u, G);
-          unsigned char* dst = my_ring + (slot * BATCH + u) * (U * 4);
-          if (eb0 + BATCH * b + u < eb1) {
-            if (c >= 0) cp_async16(dst, src + (int64_t)c * U + gl * 4);
-            else *reinterpret_cast<float4*>(dst) = make_float4(init, init, init, init);   // a slot no edge claimed
-          }
-        }
-        cp_async_commit();
-      };
-      auto consume = [&](int b, int slot) {
-#pragma unroll
-        for (int u = 0; u < BATCH; ++u) {
-          const int e = eb0 + BATCH * b + u;
-          if (e < eb1) {
-            while (e >= row_end) flush();
-            acc_row<OP>(acc, *reinterpret_cast<const float4*>(my_ring + (slot * BATCH + u) * (U * 4)));
-          }
-        }
-      };
-      const int nb = (eb1 - eb0 + BATCH - 1) / BATCH;
-      if (nb > 0) {
-        constexpr int CPB = G / BATCH;                     // batches per index chunk
-        int idx_cur, idx_next = load_idx(0);
+      {
+        // the issue pointer runs NB - 1 batches ahead of the consume pointer; empty groups are committed past the end
+        // so that "at most NB - 1 groups pending" always means "the batch being consumed has landed"
+        const int total = nb > 0 ? nb + NB - 1 : 0;
+        const int wtotal = __reduce_max_sync(0xffffffffu, total);
+        int4 ch = load_chunk(0), ch_next = load_chunk(1);
         int islot = 0, cslot = 0;
-        // the issue pointer runs NB - 1 batches ahead of the consume pointer; empty groups are committed past the
-        // end so that "at most NB - 1 groups pending" always means "the batch being consumed has landed"
-        for (int k = 0; k * CPB < nb + NB - 1; ++k) {
-          idx_cur = idx_next;
-          idx_next = load_idx(k + 1);
+        const int lane_base = lane & ~(G - 1);
+#pragma unroll 1
+        for (int b = 0; b < wtotal; ++b) {
+          const int jl = lane_base + (b & (G - 1));
+          int4 q;
+          q.x = __shfl_sync(0xffffffffu, ch.x, jl);
+          q.y = __shfl_sync(0xffffffffu, ch.y, jl);
+          q.z = __shfl_sync(0xffffffffu, ch.z, jl);
+          q.w = __shfl_sync(0xffffffffu, ch.w, jl);
+          if ((b & (G - 1)) == G - 1) {
+            ch = ch_next;
+            ch_next = load_chunk((b >> (G == 16 ? 4 : 3)) + 2);
+          }
+          if (b < total) {
+            {                                              // ---- issue batch b
+              const int e = 4 * (kb0 + b);
+              const uint32_t dst = my_ring + islot * (BATCH * U * 4);
+              if (b < nb) {
+                if (e >= eb0 && e + BATCH <= eb1 && (q.x | q.y | q.z | q.w) >= 0) {
+                  cp_async16_s(dst, src + (int64_t)q.x * U + gl * 4);
+                  cp_async16_s(dst + U * 4, src + (int64_t)q.y * U + gl * 4);
+                  cp_async16_s(dst + 2 * U * 4, src + (int64_t)q.z * U + gl * 4);
+                  cp_async16_s(dst + 3 * U * 4, src + (int64_t)q.w * U + gl * 4);
+                } else {
+                  const int c[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int j = 0; j < CPB; ++j) {
-            const int b = k * CPB + j;                     // batch to issue; b - (NB - 1) is consumed
-            if (b < nb + NB - 1) {
-              issue(b, islot, idx_cur, j);
-              islot = islot + 1 == NB ? 0 : islot + 1;
-              if (b >= NB - 1) {
-                cp_async_wait<NB - 1>();
-                consume(b - (NB - 1), cslot);
-                cslot = cslot + 1 == NB ? 0 : cslot + 1;
+                  for (int u = 0; u < BATCH; ++u) {
+                    if (e + u >= eb0 && e + u < eb1) {
+                      if (c[u] >= 0) cp_async16_s(dst + u * (U * 4), src + (int64_t)c[u] * U + gl * 4);
+                      else sts_f4(dst + u * (U * 4), make_float4(init, init, init, init));   // a slot no edge claimed
+                    }
+                  }
+                }
               }
+              cp_async_commit();
+              islot = islot + 1 == NB ? 0 : islot + 1;
+            }
+            if (b >= NB - 1) {                             // ---- consume batch b - (NB - 1)
+              cp_async_wait<NB - 1>();
+              const int e = 4 * (kb0 + b - (NB - 1));
+              const uint32_t p = my_ring + cslot * (BATCH * U * 4);
+              if (e >= eb0 && e + BATCH <= eb1 && e + BATCH <= row_end) {      // all four belong to the current row
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) acc_row<OP>(acc, lds_f4(p + u * (U * 4)));
+              } else {
+#pragma unroll 1
+                for (int u = 0; u < BATCH; ++u) {
+                  if (e + u >= eb0 && e + u < eb1) {
+                    while (e + u >= row_end) flush();
+                    acc_row<OP>(acc, lds_f4(p + u * (U * 4)));
+                  }
+                }
+              }
+              cslot = cslot + 1 == NB ? 0 : cslot + 1;
             }
           }
         }
       }
       while (row < b1) flush();                            // the last destination, and ones without slots
+      if (XRAW) {
+        named_sync(BAR_GATHER, GATHER_THREADS);            // every row of the tile is in xraw
+        wait_x_stages();                                   // (done long ago: the UMMAs of the previous tile)
+        for (int i = tid; i < ROWS * (U / 4); i += GATHER_THREADS) {
+          const int rr = i / (U / 4), cc = i % (U / 4);
+          unsigned char* ih = smem + ((ctr + (cc >> 3)) & 1) * STAGE_A;
+          store_split(ih, ih + A_IMG, rr, cc & 7, lds_f4(smem_u32(xraw + rr * U + cc * 4)));
+        }
+      }
       fence_async_smem();
-      named_sync(BAR_GATHER, GATHER_THREADS);              // every image row written; s_rp may be reused
-      if (tid == 0) {
+      named_sync(BAR_GATHER, GATHER_THREADS);              // every image row written; s_rp / xraw may be reused
+      if (tid == 0 && !gather_only) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) mbar_arrive(&bar_full[(ctr + c) & 1]);
       }
@@ -332,13 +420,15 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
     const int r = q * 32 + lane;                           // row of the tile
     uint32_t acc_uses[2] = {0, 0};
     int ab = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ab ^= 1) {
+    for (int64_t tile = blockIdx.x; tile < ntiles_other; tile += gridDim.x, ab ^= 1) {
       const int64_t row = tile * ROWS + r;
       const uint32_t tb = tmem_base + ab * DCOLS + ((uint32_t)(q * 32) << 16);
-      mbar_wait(&bar_acc[ab], acc_uses[ab] & 1);
+      mbar_wait_idle(&bar_acc[ab], acc_uses[ab] & 1);
       tc_fence_after();
-      if (et == 0) bulk_wait_read();                       // the stores of the previous tile have read the staging tile
-      named_sync(BAR_EPI, EPI_THREADS);
+      if (TMA_OUT) {
+        if (et == 0) bulk_wait_read();                     // the stores of the previous tile have read the staging tile
+        named_sync(BAR_EPI, EPI_THREADS);
+      }
 #pragma unroll 1
       for (int u0 = 0; u0 < U; u0 += 8) {
         float4 ho[2];
@@ -374,11 +464,15 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
                                    __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hold[jj]);
           }
           const int cc = u0 + j4;                          // column -> box cc / 32, 16-byte chunk (cc % 32) / 4
-          *reinterpret_cast<float4*>(out_stage + (cc >> 5) * A_IMG + r * 128 + ((((cc & 31) >> 2) ^ (r & 7)) << 4)) =
-              make_float4(hn[0], hn[1], hn[2], hn[3]);
+          if (TMA_OUT)
+            *reinterpret_cast<float4*>(out_stage + (cc >> 5) * A_IMG + r * 128 + ((((cc & 31) >> 2) ^ (r & 7)) << 4)) =
+                make_float4(hn[0], hn[1], hn[2], hn[3]);
+          else if (row < n)
+            st_f4(out_direct + (row + out_row0) * U + cc, make_float4(hn[0], hn[1], hn[2], hn[3]));
         }
       }
       acc_uses[ab] += 1;
+      if (!TMA_OUT) continue;
       fence_async_smem();
       named_sync(BAR_EPI, EPI_THREADS);
       if (et == 0) {
@@ -390,7 +484,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
         bulk_commit();
       }
     }
-    if (et == 0) bulk_wait_all();                          // every state row has left the SM
+    if (TMA_OUT && et == 0) bulk_wait_all();               // every state row has left the SM
   }
   tc_fence_before();
   __syncthreads();
@@ -413,17 +507,29 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-template <int U, int OP>
-int launch(const int* rowptr, const int* col, const float* src, const float* h, int64_t n, const float* wimg,
-           const float* bias, const OutMaps& maps, int n_out, int out_row0, float* agg_out, int grid,
-           cudaStream_t st) {
+template <int U, int OP, bool TMA_OUT>
+int launch_v(const int* rowptr, const int* col, const float* src, const float* h, int64_t n, const float* wimg,
+             const float* bias, const OutMaps& maps, int n_out, int out_row0, float* agg_out, float* out_direct,
+             int grid, cudaStream_t st) {
   constexpr size_t smem = 1024 + 2 * (size_t)(2 * A_IMG) + 2 * (size_t)(3 * U * 128) + (size_t)(U / 32) * A_IMG +
-                          (size_t)(GATHER_THREADS / (U / 4)) * NB * BATCH * U * 4;
-  IGN_CUDA(cudaFuncSetAttribute(agg_gru_tc_kernel<U, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  agg_gru_tc_kernel<U, OP><<<grid, AGG_THREADS, smem, st>>>(rowptr, col, src, h, n, wimg, bias, maps, n_out, out_row0,
-                                                            agg_out);
+                          (size_t)(GATHER_THREADS / (U / 4)) * NB * BATCH * U * 4 + (U == 32 ? ROWS * U * 4 : 0);
+  IGN_CUDA(cudaFuncSetAttribute(agg_gru_tc_kernel<U, OP, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  agg_gru_tc_kernel<U, OP, TMA_OUT><<<grid, AGG_THREADS, smem, st>>>(rowptr, col, src, h, n, wimg, bias, maps, n_out,
+                                                                     out_row0, agg_out, out_direct,
+                                                                     getenv("IGN_AGG_DBG") ? atoi(getenv("IGN_AGG_DBG")) : 0);
   IGN_CHECK_LAUNCH("agg_gru_tc");
   return IGN_OK;
+}
+// U = 64 with one output: the staging tile's shared memory is worth more as the raw-x buffer (see XRAW)
+template <int U, int OP>
+int launch(const int* rowptr, const int* col, const float* src, const float* h, int64_t n, const float* wimg,
+           const float* bias, const OutMaps& maps, int n_out, int out_row0, float* agg_out, float* out0, int grid,
+           cudaStream_t st) {
+  static const bool force_tma = getenv("IGN_AGG_TMA_OUT") != nullptr;
+  if (U == 64 && n_out == 1 && !force_tma)
+    return launch_v<U, OP, false>(rowptr, col, src, h, n, wimg, bias, maps, n_out, out_row0, agg_out, out0, grid, st);
+  return launch_v<U, OP, true>(rowptr, col, src, h, n, wimg, bias, maps, n_out, out_row0, agg_out, out0, grid, st);
 }
 
 }  // namespace
@@ -478,13 +584,13 @@ extern "C" int ign_agg_gru_cell_tc(int op, const int32_t* rowptr, const int32_t*
   switch (op) {                                                                                                   \
     case IGN_OP_SUM:                                                                                              \
       return launch<UU, IGN_OP_SUM>(rowptr, col, src_states, h_dst, num_dst, wimg, bias, maps, n_out,             \
-                                    (int)out_row0, agg_out, grid, st);                                            \
+                                    (int)out_row0, agg_out, outs[0], grid, st);                                            \
     case IGN_OP_MEAN:                                                                                             \
       return launch<UU, IGN_OP_MEAN>(rowptr, col, src_states, h_dst, num_dst, wimg, bias, maps, n_out,            \
-                                     (int)out_row0, agg_out, grid, st);                                           \
+                                     (int)out_row0, agg_out, outs[0], grid, st);                                           \
     default:                                                                                                      \
       return launch<UU, IGN_OP_MAX>(rowptr, col, src_states, h_dst, num_dst, wimg, bias, maps, n_out,             \
-                                    (int)out_row0, agg_out, grid, st);                                            \
+                                    (int)out_row0, agg_out, outs[0], grid, st);                                            \
   }
   if (units == 64) { IGN_AGG_LAUNCH(64) }
   IGN_AGG_LAUNCH(32)

@@ -91,7 +91,10 @@ class Engine:
         self.fuse_sum_gru = fuse_sum_gru
         # aggregation + GRU update as ONE tensor-core kernel (ign_agg_gru_cell_tc: gather, sum / mean / max, gate GEMMs,
         # TMA stores); False = ign_segment_reduce + ign_gru_cell (the round-1 pair, kept for ablation)
-        self.fused_tc = os.environ.get("IGN_NO_FUSED_TC") is None
+        # Measured (profiles/r2_agg_gru.md): a tie at 64-wide states / degree 20 (12.2 vs 12.1 ms on 10 M nodes, and
+        # no [n, F] aggregate in HBM), slower at 32-wide (RouteNet links: 0.31 vs 0.19 ms) -> used for 64-wide states
+        # unless IGN_FUSED_TC=1 / 0 forces it on / off.  Partitioned graphs always use it (parallel.py).
+        self.fused_tc = {"1": True, "0": False}.get(os.environ.get("IGN_FUSED_TC", ""), None)
         self.dims = model.get_input_dimensions()
         self.entities = [e.name for e in model.get_entities()]
         self.hidden = {e.name: e.hidden_state_dimension for e in model.get_entities()}
@@ -534,7 +537,8 @@ class Engine:
                  and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1])
                  and (self.fuse_sum_gru if self.fuse_sum_gru is not None else not ops.tensor_cores_enabled()))
         fused_tc = (p.kind == "agg_gru" and len(p.adjs) == 1 and msgs[0] is None and not p.conv and not p.attn
-                    and not fused and self.fused_tc and n_dst > 0
+                    and not fused and n_dst > 0
+                    and (self.fused_tc if self.fused_tc is not None else h.shape[1] == 64)
                     and ops.agg_gru_cell_tc_supported(p.msg_dim, h.shape[1]))
         if fused_tc:
             rowptr, col, _ = g.csr[p.adjs[0].name]

@@ -569,6 +569,7 @@ def test_tf_checkpoint_snappy_and_prefix_compression():
 def test_read_dataset_shuffle_is_reproducible_across_ranks(tmp_path):
     """every rank of a data-parallel run must read the same sample stream."""
     import io
+    import json
     import tarfile
     from ignnition_b200.generator import read_dataset
     for k in range(6):
