@@ -561,7 +561,7 @@ def mpnn_shard(n_nodes, n_edges, hidden, variant, rank, world, torch, dev, seed=
 
 
 def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="uniform", rank=0, world=1,
-             exchange="peer"):
+             exchange="copy"):
     """Message-passing iterations of the generic MPNN on ONE large synthetic graph (strong scaling) through
     the product path ``ignnition_b200.parallel.PartitionedEngine``: rank r owns a contiguous range of
     destination rows; one fused kernel per iteration gathers, sums, applies the GRU and stores the new rows
@@ -576,7 +576,7 @@ def run_mpnn(n_nodes, n_edges, hidden, steps, warmup, torch, dev, variant="unifo
     md = ModelDescription(mpnn_model_json(hidden), {"x": hidden, "adj": 0})
     eng = Engine(md, device=dev, seed=0)
     src, dst, x = mpnn_shard(n_nodes, n_edges, hidden, variant, rank, world, torch, dev)
-    pe = PartitionedEngine(eng, exchange=exchange if world > 1 else "peer")
+    pe = PartitionedEngine(eng, exchange=exchange if world > 1 else "copy")
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

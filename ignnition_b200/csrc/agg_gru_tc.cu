@@ -51,7 +51,13 @@ constexpr int BAR_GATHER = 1, BAR_EPI = 2, BAR_HLOAD = 3;   // named barriers (0
 
 struct OutMaps {
   CUtensorMap m[IGN_MAX_PEERS];
+  float* p[IGN_MAX_PEERS];                  // the same arrays as plain pointers (1-D bulk stores)
 };
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
 
 __device__ __forceinline__ void named_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   uint32_t lt = 0;                           // tiles this CTA has finished (phase of the per-chunk barriers)
   // IGN_AGG_DBG=1 (profiling): only the gather warps run, nothing waits for anything (results are garbage)
   const bool gather_only = dbg & 1;
+  const bool bulk1d = !(dbg & 2);            // IGN_AGG_DBG=2: tensor stores (cp.async.bulk.tensor) instead of 1-D bulk stores
   const int64_t ntiles_other = gather_only ? 0 : ntiles;
 
   if (warp == MMA_WARP) {
@@ -464,9 +471,12 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
                                    __uint_as_float(axh[j]) + bxh[jj], __uint_as_float(ahh[j]) + bhh[jj], hold[jj]);
           }
           const int cc = u0 + j4;                          // column -> box cc / 32, 16-byte chunk (cc % 32) / 4
-          if (TMA_OUT)
-            *reinterpret_cast<float4*>(out_stage + (cc >> 5) * A_IMG + r * 128 + ((((cc & 31) >> 2) ^ (r & 7)) << 4)) =
-                make_float4(hn[0], hn[1], hn[2], hn[3]);
+          if (TMA_OUT) {
+            // tensor stores: two swizzled [128 x 32] boxes; bulk stores: the tile as it lies in global memory
+            const int so = bulk1d ? r * (U * 4) + cc * 4
+                                  : (cc >> 5) * A_IMG + r * 128 + ((((cc & 31) >> 2) ^ (r & 7)) << 4);
+            *reinterpret_cast<float4*>(out_stage + so) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          }
           else if (row < n)
             st_f4(out_direct + (row + out_row0) * U + cc, make_float4(hn[0], hn[1], hn[2], hn[3]));
         }
@@ -477,9 +487,15 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
       named_sync(BAR_EPI, EPI_THREADS);
       if (et == 0) {
         const int r0 = out_row0 + (int)(tile * ROWS);
-        for (int k = 0; k < n_out; ++k) {
+        if (bulk1d) {       // one contiguous store per output array: the tile's rows are adjacent in global memory
+          const int64_t left = n - tile * ROWS;
+          const uint32_t bytes = (uint32_t)(left < ROWS ? left : ROWS) * (U * 4);
+          for (int k = 0; k < n_out; ++k) bulk_s2g(maps.p[k] + (int64_t)r0 * U, out_stage, bytes);
+        } else {
+          for (int k = 0; k < n_out; ++k) {
 #pragma unroll
-          for (int bx = 0; bx < NC; ++bx) tma_store_2d(&maps.m[k], out_stage + bx * A_IMG, bx * 32, r0);
+            for (int bx = 0; bx < NC; ++bx) tma_store_2d(&maps.m[k], out_stage + bx * A_IMG, bx * 32, r0);
+          }
         }
         bulk_commit();
       }
@@ -567,6 +583,7 @@ extern "C" int ign_agg_gru_cell_tc(int op, const int32_t* rowptr, const int32_t*
     const cuuint64_t strides[1] = {(cuuint64_t)units * 4};
     const cuuint32_t box[2] = {32, (cuuint32_t)ROWS};
     const cuuint32_t estr[2] = {1, 1};
+    maps.p[k] = outs[k];
     const CUresult r = enc(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, outs[k], dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

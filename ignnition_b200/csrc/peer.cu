@@ -137,3 +137,10 @@ extern "C" int ign_rows_put(const float* src, const int32_t* rows, int64_t n_row
   IGN_CHECK_LAUNCH("rows_put");
   return IGN_OK;
 }
+
+extern "C" int ign_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return IGN_OK;
+  IGN_REQUIRE(dst && src, IGN_ERR_INVALID, "IGNNITION: peer_copy: null pointer");
+  IGN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ign_stream(stream)));
+  return IGN_OK;
+}

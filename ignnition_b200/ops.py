@@ -496,6 +496,13 @@ def rows_put(src, rows, dst):
     _lib.check(lib.ign_rows_put(_f(src), _i(rows), rows.numel(), src.shape[1], d, _stream()), "rows_put")
 
 
+def peer_copy(dst_ptr: int, src_ptr: int, nbytes: int):
+    """``nbytes`` from ``src_ptr`` to ``dst_ptr`` (raw device addresses; dst usually a peer-mapped buffer) by the copy
+    engine, on the current stream."""
+    lib = _lib.load()
+    _lib.check(lib.ign_peer_copy(int(dst_ptr), int(src_ptr), int(nbytes), _stream()), "peer_copy")
+
+
 def index_range_check(idx, bound: int, bad):
     lib = _lib.load()
     _lib.check(lib.ign_index_range_check(_i(idx), idx.numel(), bound, _i(bad), _stream()), "index_range_check")

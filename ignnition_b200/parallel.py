@@ -13,14 +13,24 @@ Two ways the generated model shards:
   state of those nodes -- and runs the message-passing loop of ``ComnetModel.call``
   (``generate_model.py:405-602``) on them.  Source states are needed from every rank, so every rank
   holds a full copy of each entity's state array; after an update the owners' new rows have to reach
-  all copies.  Three exchanges are built:
+  all copies.  Four exchanges are built:
 
+  ``copy``      (default) the update kernel runs over the owned rows in a few row chunks, each chunk
+                writes this rank's own array, and as soon as a chunk is done the COPY ENGINE pushes it
+                into every peer's mapped array (``ign_peer_copy`` = cudaMemcpyAsync on a side stream,
+                peers visited in rotated order so that no receiver has two senders at once) while the
+                SMs are already gathering the next chunk.  Measured (tools/p2p_rate.cu,
+                profiles/r2_p2p_rate.md): a copy-engine push runs at 735-764 GB/s next to a kernel that
+                saturates HBM and does not slow it; stores issued by the busy SMs themselves (TMA or
+                st.global alike) crawl at 30-70 GB/s.
   ``peer``      the update kernel itself (``ign_agg_gru_cell_tc``) stores every finished 128-row tile
                 into the state array of EVERY rank: the arrays are cudaMalloc'ed by the library and
                 mapped into all processes through CUDA IPC (``PeerBuffer``), the stores are TMA tensor
                 stores over NVLink issued from the epilogue while the gather warps reduce the next
                 tile.  No separate collective runs; one tiny NCCL all-reduce per message passing is
-                the barrier that orders "all tiles landed" before the next gather.
+                the barrier that orders "all tiles landed" before the next gather.  Kept as the measured
+                counter-example: the stores starve behind the SM's own gather traffic (12.8 ms per
+                iteration at 2 GPUs against 8.3 ms of ``nccl``).
   ``boundary``  like ``peer``, but only the rows a peer's edges actually read are sent
                 (``ign_rows_put`` per peer from lists built once): what a graph with locality needs.
   ``nccl``      the baseline: the kernel writes the owner's rows locally, then
@@ -191,9 +201,9 @@ class PartitionedEngine:
     sum / mean / max aggregation with a GRU update -- BASELINE config 5 and every model of that
     family; anything else raises.  ``engine`` supplies the model, the weights and the kernels."""
 
-    EXCHANGES = ("peer", "boundary", "nccl")
+    EXCHANGES = ("copy", "peer", "boundary", "nccl")
 
-    def __init__(self, engine, group=None, exchange: str = "peer"):
+    def __init__(self, engine, group=None, exchange: str = "copy", chunks: Optional[int] = None):
         from . import ops
         if exchange not in self.EXCHANGES:
             raise RuntimeError("IGNNITION: unknown exchange '%s' (one of %s)" % (exchange, ", ".join(self.EXCHANGES)))
@@ -220,6 +230,9 @@ class PartitionedEngine:
         self.n_edges: Dict[str, int] = {}
         self.exchanged_bytes = 0          # bytes this rank received over NVLink in message_passing()
         self._flag = None
+        # 'copy' exchange: row chunks per update (each a kernel launch followed by world - 1 copy-engine pushes)
+        self.chunks = int(chunks if chunks is not None else os.environ.get("IGN_EXCHANGE_CHUNKS", "8"))
+        self._copy_stream = None
 
     # ------------------------------------------------------------------ build
     def own(self, entity: str) -> Tuple[int, int]:
@@ -342,6 +355,10 @@ class PartitionedEngine:
         K, R, B = eng.param(dst + "_update/kernel"), eng.param(dst + "_update/recurrent_kernel"), eng.param(dst + "_update/bias")
         bufs = self.full[dst][nxt]
         fused = ops.agg_gru_cell_tc_supported(p.msg_dim, eng.hidden[dst])
+        if self.exchange == "copy" and self.world > 1:
+            self._mp_copy(p, rowptr, col, src_states, h, K, R, B, bufs, lo, hi, fused)
+            self.cur[dst] = nxt
+            return
         if self.exchange == "peer" and not fused and self.world > 1:
             raise RuntimeError("IGNNITION: the peer exchange needs the fused update kernel (message width == units "
                                "in {32, 64}); use exchange='nccl' for %d -> %d" % (p.msg_dim, eng.hidden[dst]))
@@ -369,6 +386,44 @@ class PartitionedEngine:
                 self.exchanged_bytes += (self.num_global[dst] - (hi - lo)) * width * 4
                 self._barrier()
         self.cur[dst] = nxt
+
+    def _mp_copy(self, p, rowptr, col, src_states, h, K, R, B, bufs, lo, hi, fused):
+        """One update with the 'copy' exchange: kernel launches over row chunks on the compute stream; after each,
+        the copy stream pushes the chunk's rows into every peer's array.  The next gather may start when every
+        rank's pushes have landed: the compute stream waits for the copy stream, then the NCCL barrier."""
+        import torch
+        from . import ops
+        width = self.engine.hidden[p.dst]
+        n = hi - lo
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.engine.device)
+        cs = self._copy_stream
+        # chunk bounds on 128-row tiles of the update kernel
+        tiles = -(-n // 128)
+        k = max(1, min(self.chunks, tiles))
+        cuts = sorted({min(n, ((tiles * c) // k) * 128) for c in range(k + 1)} | {n})
+        row_bytes = width * 4
+        for a, b in zip(cuts, cuts[1:]):
+            if b <= a:
+                continue
+            if fused:
+                ops.agg_gru_cell_tc(p.op, rowptr[a:b + 1], col, src_states, h[a:b], K, R, B, [bufs.ptr], out_row0=lo + a)
+            else:
+                agg = ops.segment_reduce(p.op, rowptr[a:b + 1], col, src_states)
+                ops.gru_cell(agg, h[a:b], K, R, B, out=bufs.tensor[lo + a:lo + b])
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(cs):
+                cs.wait_event(done)
+                off = (lo + a) * row_bytes
+                for j in range(1, self.world):
+                    r = (self.rank + j) % self.world
+                    ops.peer_copy(bufs.ptrs[r] + off, bufs.ptr + off, (b - a) * row_bytes)
+        pushed = torch.cuda.Event()
+        pushed.record(cs)
+        torch.cuda.current_stream().wait_event(pushed)
+        self.exchanged_bytes += (self.num_global[p.dst] - n) * row_bytes
+        self._barrier()
 
     def message_passing(self, iterations: Optional[int] = None):
         T = self.engine.T if iterations is None else iterations

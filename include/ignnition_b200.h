@@ -416,6 +416,11 @@ int ign_flag_compact(const int32_t* flags, int64_t n, int add, int32_t* out, int
                      size_t ws_bytes, void* stream);
 /* dst[rows[i], :] = src[rows[i], :] for a [*, width] fp32 array; dst may be a peer-mapped buffer */
 int ign_rows_put(const float* src, const int32_t* rows, int64_t n_rows, int width, float* dst, void* stream);
+/* dst[0 .. bytes) = src[0 .. bytes) by the COPY ENGINE (cudaMemcpyAsync), dst usually a peer-mapped buffer: the
+ * exchange of finished row chunks while the update kernel works on the next chunk.  Stores issued by SMs whose
+ * memory pipes are busy with a gather reach a peer at 30-70 GB/s, the copy engine at 750 GB/s and without slowing
+ * the gather (profiles/r2_p2p_rate.md). */
+int ign_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 /* *bad (device int, caller-zeroed) += number of idx[i] outside [0, bound) */
 int ign_index_range_check(const int32_t* idx, int64_t n, int64_t bound, int32_t* bad, void* stream);
 

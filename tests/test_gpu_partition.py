@@ -3,7 +3,8 @@
 * one rank: PartitionedEngine == Engine.forward == the CPU oracle on the same graph;
 * the routing helpers (owner ranks, stable split, flag compaction, row puts) against numpy;
 * two ranks (needs 2 GPUs; spawned here with torch.multiprocessing over NCCL, 127.0.0.1): every exchange
-  ('peer' = TMA stores from the update kernel into the peer-mapped arrays, 'boundary', 'nccl') gives the
+  ('copy' = copy-engine pushes of finished row chunks, 'peer' = TMA stores from the update kernel into the
+  peer-mapped arrays, 'boundary', 'nccl') gives the
   1-rank states BIT FOR BIT, from contiguous shards of the same global edge list."""
 
 import os
@@ -140,7 +141,7 @@ def _rank_main(rank, world, port, exchange, hidden, n, e, T, p_local, out_dir):
         from ignnition_b200 import Engine, ModelDescription
         md = ModelDescription(mpnn_json(hidden, T), {"x": hidden, "adj": 0})
         eng = Engine(md, device=torch.device("cuda", rank), seed=3)
-        pe = PartitionedEngine(eng, exchange=exchange)
+        pe = PartitionedEngine(eng, exchange=exchange, chunks=3)          # 'copy': three row chunks per update
         from ignnition_b200.parallel import node_bounds
         b = node_bounds(n, world)
         pe.build({"node": n}, {"adj": (torch.from_numpy(src[lo_e:hi_e]).cuda(), torch.from_numpy(dst[lo_e:hi_e]).cuda())},
@@ -154,7 +155,7 @@ def _rank_main(rank, world, port, exchange, hidden, n, e, T, p_local, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("exchange,p_local", [("peer", 0.0), ("nccl", 0.0), ("boundary", 0.9)])
+@pytest.mark.parametrize("exchange,p_local", [("copy", 0.0), ("peer", 0.0), ("nccl", 0.0), ("boundary", 0.9)])
 def test_partitioned_two_ranks_bitwise(exchange, p_local, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

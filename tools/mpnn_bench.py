@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--variant", default="uniform")
-    ap.add_argument("--exchange", default="peer")
+    ap.add_argument("--exchange", default="copy")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
