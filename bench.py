@@ -170,42 +170,36 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from ignnition_b200 import Engine, ModelDescription, _lib
+def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0, want_e2e=True, want_kernels=True,
+                 parity_samples=0, total_scale=None):
+    """One workload through the Engine on this rank's GPU: resident-input steps, end-to-end steps from pinned host
+    memory, per-kernel CUDA-event times, parity against the fp64 oracle.  Times are max over ranks.
+    ``total_scale``: samples the whole job processes per step (default: n_samples x world)."""
+    torch, dist, dev, rank, world, lib = (ctx[k] for k in ("torch", "dist", "dev", "rank", "world", "lib"))
+    from ignnition_b200 import Engine, ModelDescription
     from ignnition_b200.batching import assemble_tiled
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-
-    g, shape, qsize, n_default = load_case(args.workload)
-    n_samples = args.batch or n_default
+    g, shape, qsize, _ = load_case(workload)
     dims = g["reference_meta"]["dimensions"]
     md = ModelDescription(g["model_json"], dims)
-    eng = Engine(md, device=dev, seed=0, fuse_sum_gru=(True if os.environ.get('IGN_FUSE_SUM_GRU') else None),
+    eng = Engine(md, device=dev, seed=seed_weights,            # weights: the package's own seeded initialiser
+                 fuse_sum_gru=(True if os.environ.get('IGN_FUSE_SUM_GRU') else None),
                  csr_mode=int(os.environ.get('IGN_CSR_MODE', '1')))
-    from oracle import ignnition_oracle as orc   # checker-side weights only (same seeded weights as the CPU leg)
-    eng.set_weights(orc.Oracle(g["model_json"], dims).init_weights(1234))
     base = g["reference_tensors"][0]
-    out_entity0 = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
+    out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
     batch = assemble_tiled(base, n_samples, eng.entities, eng.features, eng.adjacencies, eng.sequences,
                            feature_fns(qsize), seed=rank,
-                           label_fn=(lambda r, n: r.normal(-1.0, 0.5, n)) if args.train else None,
-                           label_entity=out_entity0)
+                           label_fn=(lambda r, n: r.normal(-1.0, 0.5, n)) if train else None,
+                           label_entity=out_entity)
     pinned = eng.pack(batch)            # sample_of_* and the seq_* of destination-ordered lists stay on the host
     edges_per_iter = sum(batch.n_edges[a.name] for a in eng.adjacencies)
-    out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
     n_pred = batch.num[out_entity]
+    n_pred_glob = torch.tensor([n_pred], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_pred_glob)
+    n_pred_glob = int(n_pred_glob.item())
 
     trainer = None
-    if args.train:
+    if train:
         from ignnition_b200.train import Trainer
         trainer = Trainer(eng, world_size=world)
 
@@ -213,16 +207,17 @@ def run_ours(args):
         if trainer is not None:        # model_fn train step: forward + loss + backward + all-reduce + Adam
             eng.build_graph(graph, training=True)
             graph.csr_t.clear()
-            return trainer.train_step(graph, global_n=n_pred * world)
+            return trainer.train_step(graph, global_n=n_pred_glob)
         eng.build_graph(graph)
         return eng.forward(graph)
 
     host_pred = torch.empty(n_pred, 1, dtype=torch.float32, pin_memory=True)
+    host_loss = torch.empty(4, dtype=torch.float64, pin_memory=True)
 
     # end to end: a stream of batches.  Batch k+1 is copied host -> device on a copy stream while batch k
     # is computed (two device staging buffers); every step still pays its own H2D and its own D2H.
     copy_stream = torch.cuda.Stream(device=dev)
-    d2h_stream = torch.cuda.Stream(device=dev)          # predictions go back while the next batch computes
+    d2h_stream = torch.cuda.Stream(device=dev)          # results go back while the next batch computes
     pred_done = torch.cuda.Event()
     stage = [torch.empty(pinned[0].numel(), dtype=torch.uint8, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -251,7 +246,9 @@ def run_ours(args):
         pred_done.record()
         with torch.cuda.stream(d2h_stream):
             d2h_stream.wait_event(pred_done)
-            if torch.is_tensor(pred) and pred.numel() == host_pred.numel():
+            if trainer is not None:                     # the step's result is the loss (sse, reg, count)
+                host_loss.copy_(trainer.scalars, non_blocking=True)
+            elif torch.is_tensor(pred) and pred.numel() == host_pred.numel():
                 host_pred.copy_(pred, non_blocking=True)
                 pred.record_stream(d2h_stream)
         e2e_state["k"] = k + 1
@@ -262,137 +259,253 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     graph = eng.upload(batch, pinned)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_resident(graph)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(ctx["local"]) if (rank == 0 and ctx.get("clocks")) else None
+    if sampler:
         sampler.start()
     l0 = lib.ign_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_resident(graph)
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
     launches = lib.ign_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
 
-    # end to end from host buffers
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    ev1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    ms_e2e = None
+    if want_e2e:
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            step_e2e()
+        d2h_stream.synchronize()                    # the last step's result is on the host before the clock stops
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
 
-    # dominant kernel: per-kernel CUDA-event timing of one more pass (same stream, after the timed region)
-    kern = profile_kernels(eng, graph, torch, args.steps, trainer, n_pred * world)
+    # per-kernel CUDA-event timing of more passes (same stream, after the timed region)
+    kern = profile_kernels(eng, graph, torch, steps, trainer, n_pred_glob) if want_kernels else {}
 
-    # parity of the timed configuration: first 2 samples of this rank's batch vs the CPU oracle
+    # parity of the timed configuration: the first samples of this rank's batch vs the fp64 CPU oracle, predictions
+    # AND every entity's final state (north_star: 1e-5 on node and link states and predictions)
     parity = None
-    if rank == 0 and not args.train:
-        pred = eng.forward(graph).cpu().numpy().reshape(n_samples, -1)
+    if rank == 0 and not train and parity_samples:
+        from oracle import ignnition_oracle as orc          # checker only
+        pred_t, states_t = eng.forward(graph, return_states=True)
+        pred = pred_t.cpu().numpy().reshape(n_samples, -1)
+        states = {e: states_t[e].cpu().numpy() for e in eng.entities}
         o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
-        w64 = o64.init_weights(1234)
-        worst = 0.0
-        for k in range(2):
+        w32 = eng.get_weights()
+        worst_p, worst_s = 0.0, {e: 0.0 for e in eng.entities}
+        k_chk = min(parity_samples, n_samples)
+        for k in range(k_chk):
             t = dict(base)
             for name, ent, size in eng.features:
                 n_e = int(base["num_" + ent])
                 t[name] = batch.arrays["feat_" + name][k * n_e * size:(k + 1) * n_e * size]
-            want = o64.forward(t, {a: b.astype(np.float32) for a, b in w64.items()}).reshape(-1)
-            worst = max(worst, float(np.abs(pred[k] - want).max() / np.abs(want).max()))
-        parity = {"max_rel_err_vs_fp64_oracle": worst, "samples_checked": 2, "tolerance": 1e-5}
+            want, want_s = o64.forward(t, w32, return_states=True)
+            want = want.reshape(-1)
+            worst_p = max(worst_p, float(np.abs(pred[k] - want).max() / np.abs(want).max()))
+            for e in eng.entities:
+                n_e = int(base["num_" + e])
+                got = states[e][k * n_e:(k + 1) * n_e]
+                worst_s[e] = max(worst_s[e], float(np.abs(got - want_s[e]).max() / np.abs(want_s[e]).max()))
+        parity = {"max_rel_err_vs_fp64_oracle": worst_p, "state_max_rel_err_vs_fp64_oracle": worst_s,
+                  "samples_checked": k_chk, "tolerance": 1e-5,
+                  "norm": "max |a - b| / max |b| per sample and tensor",
+                  "within_tolerance": bool(worst_p < 1e-5 and all(v < 1e-5 for v in worst_s.values()))}
 
-    also = None
-    if not args.no_also and not args.train:   # every rank takes part: the big graph is partitioned across them
-        del graph
-        torch.cuda.empty_cache()
-        try:
-            also = [run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "uniform", rank, world)]
-        except Exception as exc:   # e.g. not enough free memory on a shared box: report, do not hide
-            also = [{"workload": "mpnn_uniform", "error": str(exc)[:200]}]
+    total = total_scale if total_scale is not None else n_samples * world
+    out = {"workload": workload, "mode": "train" if train else "inference", "n_gpus": world,
+           "samples_per_gpu": n_samples, "samples_per_step": total, "steps": steps,
+           "value": total * steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / steps,
+           "mp_edges_per_s": edges_per_iter * eng.T * world * steps / (ms / 1e3),
+           "gpu_launches": int(launches), "launches_per_step": launches / steps,
+           "iterations": eng.T, "paths_per_gpu": batch.num.get("path"), "links_per_gpu": batch.num.get("link"),
+           "mp_edges_per_iteration_per_gpu": edges_per_iter,
+           "h2d_bytes_per_step": int(pinned[0].numel()),
+           "d2h_bytes_per_step": int(host_loss.numel() * 8 if train else host_pred.numel() * 4),
+           "kern": kern, "clocks": clocks, "parity": parity}
+    if ms_e2e is not None:
+        out["e2e"] = {"value": total * steps / (ms_e2e / 1e3), "unit": "samples/s",
+                      "h2d_bytes_per_step": out["h2d_bytes_per_step"], "d2h_bytes_per_step": out["d2h_bytes_per_step"],
+                      "ms_per_step": ms_e2e / steps}
+    del graph, stage, eng, trainer
+    torch.cuda.empty_cache()
+    return out
+
+
+def load_json(path, default):
+    try:
+        return json.load(open(os.path.join(ROOT, path)))
+    except Exception:
+        return default
+
+
+def roofline_of(case, hbm_peak, peak_src, default_size):
+    """roofline object of the case's dominant kernel: algorithmic bytes / CUDA-event time vs the measured HBM peak"""
+    kern = case["kern"]
+    if not kern:
+        return None
+    top = max(kern.values(), key=lambda k: k["ms_total"])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full captures of this workload at its
+    # default size: profiles/ncu_traffic.json names the report every number comes from
+    traffic = load_json("profiles/ncu_traffic.json", {}).get(case["workload"] + ("/train" if case["mode"] == "train" else ""), {})
+    t = traffic.get(top["name"]) if default_size else None
+    return {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": top["gbs"] / hbm_peak, "traffic": (t or {}).get("bytes_per_launch"),
+            "traffic_source": (t or {}).get("source"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": top["bytes"], "avg_launch_ms": top["ms_avg"],
+            "share_of_step": top["ms_total"] / max(sum(k["ms_total"] for k in kern.values()), 1e-9)}
+
+
+def compact(case, hbm_peak, peak_src, scaling="weak", default_size=True, note=None):
+    """an `also` entry: the same fields as the main line, without the per-kernel list"""
+    out = {k: case[k] for k in ("workload", "mode", "n_gpus", "samples_per_gpu", "samples_per_step", "steps", "value",
+                                "unit", "ms_per_step", "gpu_launches", "launches_per_step")}
+    out["metric"] = "routenet_train_samples_per_s" if case["mode"] == "train" else "routenet_samples_per_s"
+    out["scaling"] = scaling
+    if "e2e" in case:
+        out["e2e"] = case["e2e"]
+    out["roofline"] = roofline_of(case, hbm_peak, peak_src, default_size)
+    top3 = sorted(case["kern"].values(), key=lambda k: -k["ms_total"])[:4]
+    out["top_kernels"] = [{"name": k["name"], "launches_per_step": k["launches_per_step"],
+                           "ms_total": round(k["ms_total"], 4), "gbs": round(k["gbs"], 1)} for k in top3]
+    if case.get("parity"):
+        out["parity"] = case["parity"]
+    if note:
+        out["note"] = note
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ignnition_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    ctx = {"torch": torch, "dist": dist, "dev": dev, "rank": rank, "world": world, "lib": lib, "local": local,
+           "clocks": True}
+    n_default = WORKLOADS[args.workload][3]
+    n_samples = args.batch or n_default
+    main = measure_case(ctx, args.workload, n_samples, args.train, args.steps, args.warmup, parity_samples=16)
+    ctx["clocks"] = False
+
+    peaks = load_json("MEASURED_PEAKS.json", {})
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+
+    also = []
+    if not args.no_also and not args.train:
+        def leg(fn, name):
+            try:
+                also.append(fn())
+            except Exception as exc:   # e.g. not enough free memory on a shared box: report, do not hide
+                also.append({"workload": name, "error": str(exc)[:300]})
+        # config 5: one big graph, destination-partitioned over the ranks (every rank takes part)
+        leg(lambda: run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "uniform", rank, world),
+            "mpnn_uniform")
+        if world > 1:      # SURVEY 8d variant C: 90 % of the edges stay inside the owner's rows, boundary rows only
+            leg(lambda: run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "local", rank, world,
+                                 "boundary"), "mpnn_local")
+        # config 4: RouteNet synth50 training, gradient all-reduce inside the step (weak scaling: 256 samples per GPU)
+        leg(lambda: compact(measure_case(ctx, "routenet_synth50_b256", 256, True, 10, 3), hbm_peak, peak_src),
+            "routenet_synth50_b256/train")
+        # config 3 training at the headline size (the BPTT kernels): 4096 samples per GPU
+        leg(lambda: compact(measure_case(ctx, "routenet_geant2_b4096", 4096, True, 6, 3), hbm_peak, peak_src),
+            "routenet_geant2_b4096/train")
+        # config 3 as BASELINE words it: batch 4096 data-parallel OVER the GPUs (strong scaling)
+        if world > 1:
+            leg(lambda: compact(measure_case(ctx, "routenet_geant2_b4096", 4096 // world, False, args.steps, 3,
+                                             total_scale=(4096 // world) * world),
+                                hbm_peak, peak_src, scaling="strong", default_size=False,
+                                note="4096 samples split over the GPUs, no collective"),
+                "routenet_geant2_b4096/strong")
+        # config 2: Q-size RouteNet (links + paths + nodes, interleave aggregation)
+        leg(lambda: compact(measure_case(ctx, "qsize_nsfnet_b4096", 4096, False, 10, 3, parity_samples=16), hbm_peak,
+                            peak_src), "qsize_nsfnet_b4096")
+        # config 1: RouteNet on the NSFNET sample at the reference's own batch sizes (train_options.ini: 3 / 32)
+        for bsz in (3, 32):
+            for tr in (False, True):
+                leg(lambda: compact(measure_case(ctx, "routenet_nsfnet_b4096", bsz, tr, 30, 5, parity_samples=0 if tr else 3),
+                                    hbm_peak, peak_src, default_size=False,
+                                    note="launch-bound size: %d samples per step" % bsz),
+                    "routenet_nsfnet_b%d/%s" % (bsz, "train" if tr else "inference"))
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        roof = roofline_of(main, hbm_peak, peak_src, n_samples == n_default)
+        kern = main["kern"]
         top = max(kern.values(), key=lambda k: k["ms_total"])
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this
-        # workload (profiles/r1_final.md); only known for the kernels profiled there
-        ncu_traffic = {("ign_gru_seq", "routenet_geant2_b4096"): 819.5e6,     # profiles/r1_final.md
-                       ("ign_mlp_head", "routenet_geant2_b4096"): 301.5e6,
-                       ("ign_segment_reduce", "routenet_geant2_b4096"): 348.7e6,
-                       ("ign_gru_cell", "routenet_geant2_b4096"): 88.8e6}
-        roof = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": top["gbs"] / hbm_peak,
-                "traffic": ncu_traffic.get((top["name"], args.workload)) if n_samples == n_default else None,
-                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "algorithmic_bytes_per_launch": top["bytes"], "avg_launch_ms": top["ms_avg"],
-                "share_of_step": top["ms_total"] / max(sum(k["ms_total"] for k in kern.values()), 1e-9)}
         cores = os.cpu_count() or 1
         cpu_val, cpu_n, cpu_dt = cpu_samples_per_s(args.workload, args.cpu_samples, 1)
         line = {
             "metric": "routenet_train_samples_per_s" if args.train else "routenet_samples_per_s",
-            "value": n_samples * world * args.steps / (ms / 1e3),
+            "value": main["value"],
             "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "samples_per_gpu": n_samples, "iterations": eng.T,
-                       "paths_per_gpu": batch.num.get("path"), "links_per_gpu": batch.num.get("link"),
-                       "mp_edges_per_iteration_per_gpu": edges_per_iter,
+            "config": {"workload": args.workload, "samples_per_gpu": n_samples, "iterations": main["iterations"],
+                       "paths_per_gpu": main["paths_per_gpu"], "links_per_gpu": main["links_per_gpu"],
+                       "mp_edges_per_iteration_per_gpu": main["mp_edges_per_iteration_per_gpu"],
                        "timing": "inputs+states per step exceed L2 (no flush needed)",
                        "step": ("device CSR build (+ transposed) + forward + MSE/l2 + backward + NCCL all-reduce + Adam"
                                 if args.train else "device CSR build + T message-passing iterations + readout")},
-            "mp_edges_per_s": edges_per_iter * eng.T * world * args.steps / (ms / 1e3),
-            "e2e": {"value": n_samples * world * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
-                    "h2d_bytes_per_step": int(pinned[0].numel()), "d2h_bytes_per_step": int(host_pred.numel() * 4),
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+            "mp_edges_per_s": main["mp_edges_per_s"],
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
             "roofline": roof,
             "kernels": sorted(kern.values(), key=lambda k: -k["ms_total"]),
             "cpu_baseline": {"value": cpu_val, "unit": "samples/s", "cores": 1, "kind": "port",
                              "host_cores": cores,
                              "sample": "%d samples of %s through oracle/ignnition_oracle.py (NumPy fp32, "
                                        "per-sample loop), %.1f s" % (cpu_n, args.workload, cpu_dt)},
-            "clocks": clocks,
-            "parity": parity,
-            "also": also,
+            "clocks": main["clocks"],
+            "parity": main["parity"],
+            "also": also or None,
         }
         if top["name"] == "ign_gru_seq" and not args.train and args.workload.startswith("routenet"):
             # the ordered update is a chain of small GEMMs: the tensor-pipe view of the same launch.  FLOPs issued =
-            # 3 (3xTF32 products) x 2 E 3U (F + U); the tf32 dense rate is half of the measured bf16 rate
-            e_steps = edges_per_iter // 2                    # path-link incidences = steps of one ordered update
+            # 3 (3xTF32 products) x 2 E 3U (F + U); peak = the tcgen05 kind::tf32 rate MEASURED on this chip
+            # (profiles/measured_tf32_peak.json, tools/umma_rate.cu), not a fraction of the bf16 number
+            e_steps = main["mp_edges_per_iteration_per_gpu"] // 2    # path-link incidences = steps of one ordered update
             fl = 3.0 * 2.0 * e_steps * 96 * 64
-            tf32_peak = float(peaks.get("bf16_tflops", 1615.9)) / 2.0
+            tf32 = load_json("profiles/measured_tf32_peak.json", {})
+            tf32_peak = float(tf32.get("tf32_tflops", float(peaks.get("bf16_tflops", 1615.9)) / 2.0))
             ach = fl / (top["ms_avg"] * 1e-3) / 1e12
             line["roofline_tensor"] = {
                 "bound": "tensor", "kernel": "ign_gru_seq", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": ach / tf32_peak, "flops_issued_per_launch": fl,
-                "note": "tf32 operations issued (3 per fp32 product); peak = MEASURED_PEAKS bf16_tflops / 2; ncu "
-                        "sm__pipe_tensor_cycles_active 32.5 % (profiles/r1_final.md); the kernel is bound by the "
-                        "per-tile dependency chain (profiles/r1_walk_phases.md)"}
-        if also and "segment_reduce" in also[0]:
-            sr = also[0]["segment_reduce"]
+                "peak_source": "profiles/measured_tf32_peak.json" if tf32 else "MEASURED_PEAKS bf16_tflops / 2",
+                "note": "tf32 operations issued (3 per fp32 product); the kernel is bound by the per-tile dependency "
+                        "chain (profiles/r1_walk_phases.md)"}
+        mp = also[0] if also else None
+        if mp and "unfused_pair" in mp:
             line["roofline_gather_segment"] = {
-                "bound": "hbm", "kernel": "ign_segment_reduce (config 5: 10M nodes / 200M edges, F=64)",
-                "achieved": sr["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": sr["achieved_gbs"] / hbm_peak,
+                "bound": "hbm", "kernel": "ign_agg_gru_cell_tc (config 5: gather + segment sum + GRU, F = U = 64)",
+                "achieved": mp["fused_update"]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": mp["fused_update"]["achieved_gbs"] / hbm_peak,
+                "segment_reduce_alone": {"achieved": mp["unfused_pair"]["segment_reduce_gbs"],
+                                         "frac": mp["unfused_pair"]["segment_reduce_gbs"] / hbm_peak},
                 "traffic": None}
         print(json.dumps(line))
     if world > 1:
