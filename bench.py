@@ -308,8 +308,10 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
         pred = pred_t.cpu().numpy().reshape(n_samples, -1)
         states = {e: states_t[e].cpu().numpy() for e in eng.entities}
         o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
+        o32 = orc.Oracle(g["model_json"], dims, dtype=np.float32)
         w32 = eng.get_weights()
         worst_p, worst_s = 0.0, {e: 0.0 for e in eng.entities}
+        floor_p, floor_s = 0.0, {e: 0.0 for e in eng.entities}     # the NumPy fp32 oracle against the fp64 one
         k_chk = min(parity_samples, n_samples)
         for k in range(k_chk):
             t = dict(base)
@@ -318,15 +320,22 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
                 t[name] = batch.arrays["feat_" + name][k * n_e * size:(k + 1) * n_e * size]
             want, want_s = o64.forward(t, w32, return_states=True)
             want = want.reshape(-1)
+            f32p, f32s = o32.forward(t, w32, return_states=True)
             worst_p = max(worst_p, float(np.abs(pred[k] - want).max() / np.abs(want).max()))
+            floor_p = max(floor_p, float(np.abs(f32p.reshape(-1) - want).max() / np.abs(want).max()))
             for e in eng.entities:
                 n_e = int(base["num_" + e])
                 got = states[e][k * n_e:(k + 1) * n_e]
                 worst_s[e] = max(worst_s[e], float(np.abs(got - want_s[e]).max() / np.abs(want_s[e]).max()))
+                floor_s[e] = max(floor_s[e], float(np.abs(f32s[e] - want_s[e]).max() / np.abs(want_s[e]).max()))
         parity = {"max_rel_err_vs_fp64_oracle": worst_p, "state_max_rel_err_vs_fp64_oracle": worst_s,
                   "samples_checked": k_chk, "tolerance": 1e-5,
                   "norm": "max |a - b| / max |b| per sample and tensor",
-                  "within_tolerance": bool(worst_p < 1e-5 and all(v < 1e-5 for v in worst_s.values()))}
+                  "within_tolerance": bool(worst_p < 1e-5 and all(v < 1e-5 for v in worst_s.values())),
+                  # what fp32 arithmetic itself costs on these inputs and weights: the reference's own program in
+                  # NumPy fp32 against the same program in fp64 (profiles/r2_parity.md)
+                  "fp32_oracle_vs_fp64_oracle": {"predictions": floor_p, "states": floor_s},
+                  "weights": "Keras default initialisers (glorot kernels, orthogonal recurrent kernels), seed 0"}
 
     total = total_scale if total_scale is not None else n_samples * world
     out = {"workload": workload, "mode": "train" if train else "inference", "n_gpus": world,
