@@ -231,8 +231,15 @@ class PartitionedEngine:
         self.exchanged_bytes = 0          # bytes this rank received over NVLink in message_passing()
         self._flag = None
         # 'copy' exchange: row chunks per update (each a kernel launch followed by world - 1 copy-engine pushes)
-        self.chunks = int(chunks if chunks is not None else os.environ.get("IGN_EXCHANGE_CHUNKS", "8"))
-        self._copy_stream = None
+        self.chunks = int(chunks if chunks is not None else os.environ.get("IGN_EXCHANGE_CHUNKS", "4"))
+        # one copy stream: pushes to two peers at once collide at the receivers (6.1 vs 4.1 ms at 8 GPUs)
+        self.copy_streams = int(os.environ.get("IGN_EXCHANGE_STREAMS", "1"))
+        # chunk sizes form a geometric series with ratio (push time per row) / (kernel time per row), estimated per
+        # update in _mp_copy: where NVLink is the longer leg (8 GPUs: ratio 2) a small first chunk starts the copy engine
+        # early and chunk c + 1 is ready just before the push of chunk c ends; where the kernel is (2 GPUs: ratio 0.3)
+        # the LAST chunk is the small one and little of the exchange is left after the last kernel.  0 = estimate.
+        self.growth = float(os.environ.get("IGN_EXCHANGE_GROWTH", "0"))
+        self._copy_streams: list = []
 
     # ------------------------------------------------------------------ build
     def own(self, entity: str) -> Tuple[int, int]:
@@ -395,34 +402,81 @@ class PartitionedEngine:
         from . import ops
         width = self.engine.hidden[p.dst]
         n = hi - lo
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=self.engine.device)
-        cs = self._copy_stream
+        while len(self._copy_streams) < max(1, self.copy_streams):
+            self._copy_streams.append(torch.cuda.Stream(device=self.engine.device))
+        streams = self._copy_streams[:max(1, self.copy_streams)]
+        row_bytes = width * 4
         # chunk bounds on 128-row tiles of the update kernel
         tiles = -(-n // 128)
         k = max(1, min(self.chunks, tiles))
-        cuts = sorted({min(n, ((tiles * c) // k) * 128) for c in range(k + 1)} | {n})
-        row_bytes = width * 4
+        growth = self.growth
+        if growth <= 0.0:
+            # measured rates (profiles/r2_p2p_rate.md, r2_agg_gru.md): copy engine 745 GB/s out per GPU, fused update
+            # 4.7 TB/s of algorithmic bytes
+            f_in = src_states.shape[1]
+            e_rows = float(col.numel()) / max(n, 1)
+            t_push = (self.world - 1) * row_bytes / 745e9
+            t_kern = (e_rows * (4 + 4 * f_in) + 2 * row_bytes + 4) / 4.7e12
+            growth = min(3.0, max(0.25, t_push / t_kern))
+        weights = [growth ** c for c in range(k)]
+        acc, marks = 0.0, [0]
+        for wgt in weights:
+            acc += wgt
+            marks.append(int(round(tiles * acc / sum(weights))))
+        marks[-1] = tiles
+        cuts = sorted({min(n, m * 128) for m in marks} | {n})
+        trace = getattr(self, "trace", None)             # profiling: [(label, start event, end event)] of one update
+        def mark(stream=None):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream) if stream is not None else ev.record()
+            return ev
         for a, b in zip(cuts, cuts[1:]):
             if b <= a:
                 continue
+            k0 = mark() if trace is not None else None
             if fused:
                 ops.agg_gru_cell_tc(p.op, rowptr[a:b + 1], col, src_states, h[a:b], K, R, B, [bufs.ptr], out_row0=lo + a)
             else:
                 agg = ops.segment_reduce(p.op, rowptr[a:b + 1], col, src_states)
                 ops.gru_cell(agg, h[a:b], K, R, B, out=bufs.tensor[lo + a:lo + b])
-            done = torch.cuda.Event()
-            done.record()
-            with torch.cuda.stream(cs):
+            done = mark() if trace is not None else torch.cuda.Event()
+            if trace is None:
+                done.record()
+            else:
+                trace.append(("kernel rows %d-%d" % (a, b), k0, done))
+            off = (lo + a) * row_bytes
+            for cs in streams:
                 cs.wait_event(done)
-                off = (lo + a) * row_bytes
-                for j in range(1, self.world):
-                    r = (self.rank + j) % self.world
+            c0 = mark(streams[0]) if trace is not None else None
+            for j in range(1, self.world):
+                r = (self.rank + j) % self.world
+                with torch.cuda.stream(streams[(j - 1) % len(streams)]):
                     ops.peer_copy(bufs.ptrs[r] + off, bufs.ptr + off, (b - a) * row_bytes)
-        pushed = torch.cuda.Event()
-        pushed.record(cs)
-        torch.cuda.current_stream().wait_event(pushed)
+            if trace is not None:
+                trace.append(("push rows %d-%d" % (a, b), c0, mark(streams[0])))
+        for cs in streams:
+            pushed = torch.cuda.Event()
+            pushed.record(cs)
+            torch.cuda.current_stream().wait_event(pushed)
         self.exchanged_bytes += (self.num_global[p.dst] - n) * row_bytes
+        b0 = mark() if trace is not None else None
+        self._barrier()
+        if trace is not None:
+            trace.append(("barrier", b0, mark()))
+
+    def exchange_only(self, entity: str):
+        """Profiling aid: push this rank's rows of the current array to every peer (the values are already there) and
+        run the barrier -- the exchange of one update without its kernel."""
+        import torch
+        from . import ops
+        if self.world == 1:
+            return
+        lo, hi = self.own(entity)
+        bufs = self.full[entity][self.cur[entity]]
+        row_bytes = self.engine.hidden[entity] * 4
+        for j in range(1, self.world):
+            r = (self.rank + j) % self.world
+            ops.peer_copy(bufs.ptrs[r] + lo * row_bytes, bufs.ptr + lo * row_bytes, (hi - lo) * row_bytes)
         self._barrier()
 
     def message_passing(self, iterations: Optional[int] = None):
