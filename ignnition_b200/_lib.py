@@ -39,6 +39,8 @@ SIGNATURES = {
     "ign_gru_cell": (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_agg_gru_cell": (_int, [_p, _p, _p, _int, _p, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "ign_gru_seq": (_int, [_p, _p, _p, _int, _p, _int, _p, _i64, _int, _p, _p, _p, _p, _p, _p, _p]),
+    "ign_gru_seq_proj_ws_bytes": (_sz, [_int, _p, _int, _int]),
+    "ign_gru_seq_proj": (_int, [_p, _p, _p, _int, _p, _p, _int, _p, _i64, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_seq_step_plan": (_int, [_p, _p, _i64, _int, _p, _p, _p, _p]),
     "ign_gru_seq_step": (_int, [_int, _p, _p, _p, _p, _int, _p, _int, _p, _p, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "ign_seq_meta": (_int, [_p, _p, _p, _i64, _p, _p]),

@@ -8,6 +8,7 @@ the status.  No torch op computes anything on this path and nothing falls back t
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -232,6 +233,16 @@ def gru_seq_steps(plan, meta, srcs: List[torch.Tensor], h0, kernel, rkernel, bia
     return out
 
 
+def gru_seq_proj_pays(n_steps: int, srcs, units: int, meta) -> bool:
+    """The hoisted-projection walk (ign_gru_seq_proj) is built for 32-wide states with a walk plan, and pays when the
+    source rows are walked over at least twice on average (the projected table is 3 x the source rows)."""
+    if meta is None or units != 32 or srcs[0].shape[1] != 32 or not tensor_cores_enabled():
+        return False
+    if os.environ.get("IGN_GRU_SEQ_PROJ", "1") == "0":
+        return False
+    return sum(int(s.shape[0]) for s in srcs) * 2 <= n_steps
+
+
 def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rkernel, bias, out=None,
             h_seq=None, meta=None):
     lib = _lib.load()
@@ -239,6 +250,14 @@ def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rk
     if out is None:
         out = torch.empty_like(h0)
     sp = _ptr_array(srcs, torch.float32)
+    if gru_seq_proj_pays(int(steps.numel()), srcs, units, meta):
+        rows = (C.c_int64 * len(srcs))(*[int(s.shape[0]) for s in srcs])
+        nbytes = lib.ign_gru_seq_proj_ws_bytes(len(srcs), rows, srcs[0].shape[1], units)
+        ws = _workspace(nbytes, h0.device)
+        _lib.check(lib.ign_gru_seq_proj(_i(steps_rowptr), _i(steps), _i(meta), len(srcs), sp, rows, srcs[0].shape[1],
+                                        _f(h0), n, units, _f(kernel), _f(rkernel), _f(bias), _f(out), _f(h_seq),
+                                        ws.data_ptr(), ws.numel(), _stream()), "gru_seq_proj")
+        return out
     _lib.check(lib.ign_gru_seq(_i(steps_rowptr), _i(steps), _i(order), len(srcs), sp, srcs[0].shape[1],
                                _f(h0), n, units, _f(kernel), _f(rkernel), _f(bias), _f(out), _f(h_seq),
                                _i(meta), _stream()), "gru_seq")

@@ -171,6 +171,19 @@ int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, const int32_t
                 float* h_seq, const int32_t* meta /* nullable: output of ign_seq_meta for this order */,
                 void* stream);
 
+/* The same update with the input projection hoisted out of the walk (csrc/gru_seq_proj_tc.cu): x K + b is computed
+ * once per SOURCE row into a 96-wide table (workspace), the walk gathers table rows and runs only the recurrent
+ * GEMM per step on tcgen05 with the state operand in tensor memory.  Pays when a source row is walked over more
+ * than once (RouteNet: 303 k link rows, 6.1 M steps).  f_in == units == 32; meta = the plan of ign_seq_meta
+ * (required); src_rows: HOST array, rows of every source array.  Results equal ign_gru_seq to fp32 rounding. */
+size_t ign_gru_seq_proj_ws_bytes(int n_src, const int64_t* src_rows /*host*/, int f_in, int units);
+int ign_gru_seq_proj(const int32_t* steps_rowptr, const int32_t* steps, const int32_t* meta, int n_src,
+                     const float* const* srcs /*host array of device ptrs*/, const int64_t* src_rows /*host*/,
+                     int f_in, const float* h0, int64_t num_dst, int units, const float* kernel,
+                     const float* recurrent_kernel, const float* bias, float* out, float* h_seq, void* ws,
+                     size_t ws_bytes, void* stream);
+
+
 /* Step-synchronous form of ign_gru_seq for short sequences (RouteNet paths: <= 6 links): launch t
  * executes step t of every destination that has one.  Needs the destinations sorted by descending
  * length (ign_length_order), their walk plan (ign_seq_meta) and the step-major plan of

@@ -275,6 +275,63 @@ def test_gru_seq_vs_masked_rnn(fi, u, use_order):
     assert rel_err(got2, want2) < RTOL
 
 
+@pytest.mark.parametrize("n_dst,max_len,n_srcs", [(1, 3, 1), (127, 1, 1), (129, 0, 1), (3000, 9, 1), (70000, 5, 2),
+                                                  (1000, 33, 3)])
+def test_gru_seq_proj(n_dst, max_len, n_srcs, monkeypatch):
+    """ign_gru_seq_proj (input projection hoisted, h operand in tensor memory, three walkers per SM) == the masked
+    RNN of the oracle (fp64) to 1e-5 and == ign_gru_seq to fp32 rounding: several source arrays, zero messages,
+    empty destinations, ragged last tile, many tiles per walker, saved per-step states."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(n_dst + max_len)
+    u = 32
+    rows = [max(2, n_dst // 40 + 3 * k) for k in range(n_srcs)]
+    lens = rng.randint(0, max_len + 1, n_dst)
+    if n_dst > 5 and max_len > 0:
+        lens[:5] = max_len
+    n_steps = int(lens.sum())
+    ent_src = rng.randint(0, n_srcs, n_steps)
+    ent_row = np.array([rng.randint(0, rows[k]) for k in ent_src], dtype=np.int64) if n_steps else np.zeros(0, np.int64)
+    steps = ((ent_src.astype(np.int64) << 28) | ent_row).astype(np.int32)
+    zero = rng.rand(n_steps) < 0.05
+    steps[zero] = -1
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    states = [(rng.randn(r, u) * 0.5).astype(np.float32) for r in rows]
+    h0 = rng.randn(n_dst, u).astype(np.float32)
+    K, R, b = gru_weights(rng, u, u)
+    rp, st = dev(rowptr, torch.int32), dev(steps if n_steps else np.full(1, -1, np.int32), torch.int32)
+    order = ops.length_order(rp)
+    meta = ops.seq_meta(rp, st, order)
+    srcs = [dev(x) for x in states]
+    monkeypatch.setattr(ops, "gru_seq_proj_pays", lambda *a, **k: True)
+    hs_p = torch.zeros(max(n_steps, 1), u, device="cuda")
+    got = ops.gru_seq(rp, st, order, srcs, dev(h0), dev(K), dev(R), dev(b), h_seq=hs_p, meta=meta).cpu().numpy()
+    monkeypatch.setattr(ops, "gru_seq_proj_pays", lambda *a, **k: False)
+    hs_o = torch.zeros(max(n_steps, 1), u, device="cuda")
+    old = ops.gru_seq(rp, st, order, srcs, dev(h0), dev(K), dev(R), dev(b), h_seq=hs_o, meta=meta).cpu().numpy()
+    # oracle: the dense right-padded tensor + mask
+    L = max(int(lens.max()) if n_dst else 0, 1)
+    padded = np.zeros((n_dst, L, u), np.float64)
+    d_of = np.repeat(np.arange(n_dst), lens)
+    t_of = np.arange(n_steps) - rowptr[d_of]
+    msgs = np.zeros((n_steps, u))
+    for k in range(n_srcs):
+        m = (ent_src == k) & ~zero
+        msgs[m] = states[k][ent_row[m]]
+    padded[d_of, t_of] = msgs
+    K64, R64, b64 = K.astype(np.float64), R.astype(np.float64), b.astype(np.float64)
+    cell = lambda a, h: orc.gru_cell(a, h, K64, R64, b64)
+    nz = lens > 0
+    want = h0.astype(np.float64).copy()
+    if nz.any():
+        want[nz] = orc.masked_rnn_last(cell, padded[nz], h0[nz].astype(np.float64), lens[nz])
+    assert rel_err(got, want) < RTOL
+    assert rel_err(got, old.astype(np.float64)) < RTOL
+    assert np.array_equal(got[~nz], h0[~nz])
+    if n_steps:
+        assert np.array_equal(hs_p.cpu().numpy()[rowptr[1:][nz] - 1], got[nz])
+        assert rel_err(hs_p.cpu().numpy(), hs_o.cpu().numpy().astype(np.float64)) < RTOL
+
+
 @pytest.mark.parametrize("max_len", [1, 6, 16])
 def test_gru_seq_step_synchronous(max_len):
     """step-synchronous launches == the sequence walk == masked RNN of the oracle (incl. empty destinations,

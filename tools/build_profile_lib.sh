@@ -8,10 +8,11 @@ cd "$(dirname "$0")/../ignnition_b200/csrc"
 make -s
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC --expt-relaxed-constexpr -I../../include"
 nvcc $FLAGS -DIGN_WALK_PROFILE -c gru_seq_tc.cu -o /tmp/ign_gru_seq_tc_prof.o
+nvcc $FLAGS -DIGN_PROJ_PROFILE -c gru_seq_proj_tc.cu -o /tmp/ign_gru_seq_proj_tc_prof.o
 nvcc $FLAGS -DIGN_MLP_PROFILE -c mlp_head_tc.cu -o /tmp/ign_mlp_head_tc_prof.o
 nvcc $FLAGS -DIGN_CELL_PROFILE -c gru_cell_tc.cu -o /tmp/ign_gru_cell_tc_prof.o
 nvcc $FLAGS -DIGN_BWD_PROFILE -c gru_step_bwd_tc.cu -o /tmp/ign_gru_step_bwd_tc_prof.o
-OBJS=$(ls *.o | grep -v -e '^gru_seq_tc.o$' -e '^mlp_head_tc.o$' -e '^gru_cell_tc.o$' -e '^gru_step_bwd_tc.o$')
+OBJS=$(ls *.o | grep -v -e '^gru_seq_tc.o$' -e '^gru_seq_proj_tc.o$' -e '^mlp_head_tc.o$' -e '^gru_cell_tc.o$' -e '^gru_step_bwd_tc.o$')
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../../tools/libignnition_b200_prof.so $OBJS \
-  /tmp/ign_gru_seq_tc_prof.o /tmp/ign_mlp_head_tc_prof.o /tmp/ign_gru_cell_tc_prof.o /tmp/ign_gru_step_bwd_tc_prof.o -lcudart
+  /tmp/ign_gru_seq_tc_prof.o /tmp/ign_gru_seq_proj_tc_prof.o /tmp/ign_mlp_head_tc_prof.o /tmp/ign_gru_cell_tc_prof.o /tmp/ign_gru_step_bwd_tc_prof.o -lcudart
 echo built tools/libignnition_b200_prof.so

@@ -42,8 +42,15 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
+alg = int(r[-1]) * (4 + 4 * u) + n_dst * (8 * u + 8)
+out3 = torch.empty_like(h0)
+t_proj = timed(lambda: ops.gru_seq(rp, cc, order, [states], h0, K, R, b, out=out3, meta=meta))   # hoisted projection
+os.environ["IGN_GRU_SEQ_PROJ"] = "0"
 t_walk = timed(lambda: ops.gru_seq(rp, cc, order, [states], h0, K, R, b, out=out1, meta=meta))
 t_step = timed(lambda: ops.gru_seq_steps(plan, meta, [states], h0, K, R, b, max_len, out=out2, hs=hs))
+torch.cuda.synchronize()
 alg = int(r[-1]) * (4 + 4 * u) + n_dst * (8 * u + 8)
+print("hoisted projection + TMEM state operand, 3 walkers: %.3f ms (%.0f GB/s algorithmic), max |diff| vs walk %.2e"
+      % (t_proj, alg / t_proj / 1e6, float((out3 - out1).abs().max())))
 print("steps %d | walk %.3f ms (%.0f GB/s algorithmic) | step-synchronous %.3f ms (%.0f GB/s) | max |diff| %.2e"
       % (int(r[-1]), t_walk, alg / t_walk / 1e6, t_step, alg / t_step / 1e6, float((out1 - out2).abs().max())))
