@@ -50,6 +50,8 @@ SIGNATURES = {
     "ign_mlp_head_ws_bytes": (_sz, [_int, _int, _int]),
     "ign_mlp_head": (_int, [_p, _i64, _int, _p, _p, _int, _int, _p, _p, _int, _int, _p, _p, _p, _p, _sz, _p]),
     "ign_gather_concat": (_int, [_int, _p, _p, _p, _i64, _p, _p]),
+    "ign_gather_dense_ws_bytes": (_sz, [_int, _p, _int]),
+    "ign_gather_dense": (_int, [_int, _p, _p, _p, _i64, _p, _p, _int, _int, _p, _p, _sz, _p]),
     "ign_mse_loss": (_int, [_p, _p, _i64, _f, _p, _p, _p]),
     "ign_dense_bwd_ws_bytes": (_sz, [_int, _int]),
     "ign_dense_bwd": (_int, [_p, _i64, _int, _p, _int, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -32,6 +32,33 @@ constexpr int TC_M = 128;
 constexpr int TC_KC = 32;                       // floats per K chunk = 128 bytes per row
 constexpr int A_IMG = TC_M * 128;               // bytes of one A image (hi or lo) of a chunk
 
+// Fused gather + concat of the A operand (the message network's input, generate_model.py:432-475): row r of the
+// [M, K] operand is  concat_k src[k][idx[k] ? idx[k][r] : r, :]  and is never written to memory -- the A loaders fetch
+// each 32-float chunk straight from the source state array its columns belong to.  Every width is a multiple of 32 (a
+// chunk lies inside one source); n == 0: plain x.  A negative index gives a zero row (as ign_gather_concat).
+struct GatherA {
+  const float* src[IGN_MAX_SOURCES];
+  const int* idx[IGN_MAX_SOURCES];
+  int width[IGN_MAX_SOURCES];
+  int col0[IGN_MAX_SOURCES];
+  int n;
+};
+// address of the 16-byte piece c4 of chunk c of operand row r, or nullptr for a zero row
+__device__ __forceinline__ const float* a_piece(const GatherA& ga, const float* x, int K, int64_t r, int c, int c4) {
+  if (ga.n == 0) return x + r * K + c * TC_KC + c4 * 4;
+  const int col = c * TC_KC;
+  int k = 0;
+#pragma unroll
+  for (int j = 1; j < IGN_MAX_SOURCES; ++j) k += (j < ga.n && col >= ga.col0[j]) ? 1 : 0;
+  const float* base = k == 0 ? ga.src[0] : k == 1 ? ga.src[1] : k == 2 ? ga.src[2] : ga.src[3];
+  const int* ix = k == 0 ? ga.idx[0] : k == 1 ? ga.idx[1] : k == 2 ? ga.idx[2] : ga.idx[3];
+  const int w = k == 0 ? ga.width[0] : k == 1 ? ga.width[1] : k == 2 ? ga.width[2] : ga.width[3];
+  const int c0 = k == 0 ? ga.col0[0] : k == 1 ? ga.col0[1] : k == 2 ? ga.col0[2] : ga.col0[3];
+  const int64_t row = ix ? (int64_t)__ldg(ix + r) : r;
+  if (row < 0) return nullptr;
+  return base + row * w + (col - c0) + c4 * 4;
+}
+
 // W[K,N] -> per chunk c: [hi image: N rows x 128 B][lo image]  (the shared-memory layout of B)
 // transposed: the GEMM uses W^T, i.e. element (k, n) of the [K, N] operand is w[n * K + k] (w stored [N, K])
 __global__ void dense_tc_prep_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ img,
@@ -55,7 +82,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
                                                                  const float* __restrict__ bias, int N, int act_,
                                                                  float* __restrict__ y, float* __restrict__ pre,
                                                                  int tmem_cols, const float* __restrict__ head_w,
-                                                                 const float* __restrict__ head_b, float* __restrict__ head_out) {
+                                                                 const float* __restrict__ head_b, float* __restrict__ head_out,
+                                                                 const GatherA ga) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int act = ACT >= 0 ? ACT : act_;
   // carve-up (1024-byte aligned images): stage s: A_hi | A_lo | B_hi | B_lo
@@ -115,7 +143,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const float* __
           const int idx = tid + j * TC_THREADS;        // 0..1023 : (row, 16-byte column)
           const int r = idx >> 3, c4 = idx & 7;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m0 + r < M) v = ldg_f4(x + (m0 + r) * K + c * TC_KC + c4 * 4);
+          if (m0 + r < M) {
+            const float* pz = a_piece(ga, x, K, m0 + r, c, c4);
+            if (pz) v = ldg_f4(pz);
+          }
           float4 hi, lo;
           tf32_split(v.x, hi.x, lo.x);
           tf32_split(v.y, hi.y, lo.y);
@@ -221,7 +252,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) dense_pipe_tc_kernel(const float
                                                                      const float* __restrict__ wimg,
                                                                      const float* __restrict__ bias, int N, int act_,
                                                                      float* __restrict__ y, float* __restrict__ pre,
-                                                                     int nst, int tmem_cols) {
+                                                                     int nst, int tmem_cols, const GatherA ga) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int act = ACT >= 0 ? ACT : act_;
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -267,7 +298,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) dense_pipe_tc_kernel(const float
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int64_t r = m0 + r0 + 16 * k;
-        v[k] = r < M ? ld_stream_f4(x + r * K + c * TC_KC + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < M) {
+          const float* pz = a_piece(ga, x, K, r, c, c4);
+          // gathered state rows are read again by other edges: keep them cacheable; a plain x is streamed
+          if (pz) v[k] = ga.n ? ldg_f4(pz) : ld_stream_f4(pz);
+        }
       }
     };
     if (njobs > 0) load(0, cur);
@@ -388,9 +424,12 @@ bool ign_dense_tc_supported(int k, int n) { return k % TC_KC == 0 && k >= TC_KC 
 
 size_t ign_dense_tc_ws(int k, int n) { return (size_t)(k / TC_KC) * 2 * n * 128; }
 
-int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
-                        float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w,
-                        const float* head_b, float* head_out, bool w_transposed) {
+static int dense_tc_launch_g(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                             float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w,
+                             const float* head_b, float* head_out, bool w_transposed, const GatherA* gather) {
+  GatherA ga;
+  memset(&ga, 0, sizeof(ga));
+  if (gather) ga = *gather;
   float* img = reinterpret_cast<float*>(ws);
   dense_tc_prep_kernel<<<(unsigned)ign_cdiv((int64_t)k * n, 256), 256, 0, st>>>(w, k, n, img, w_transposed);
   IGN_CHECK_LAUNCH("dense_tc_prep");
@@ -413,7 +452,7 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
       while (pcols < 2 * n) pcols <<= 1;
       auto plaunch = [&](auto kernel) -> int {
         IGN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        kernel<<<grid, P_THREADS, psmem, st>>>(x, m, k, img, bias, n, act, y, pre_act, nst, pcols);
+        kernel<<<grid, P_THREADS, psmem, st>>>(x, m, k, img, bias, n, act, y, pre_act, nst, pcols, ga);
         return IGN_OK;
       };
       int prc;
@@ -431,7 +470,7 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   }
   auto launch = [&](auto kernel) -> int {
     IGN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols, head_w, head_b, head_out);
+    kernel<<<grid, TC_THREADS, smem, st>>>(x, m, k, img, bias, n, act, y, pre_act, cols, head_w, head_b, head_out, ga);
     return IGN_OK;
   };
   int rc;
@@ -446,4 +485,53 @@ int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const 
   if (rc != IGN_OK) return rc;
   IGN_CHECK_LAUNCH("dense_tc");
   return IGN_OK;
+}
+
+int ign_dense_tc_launch(const float* x, int64_t m, int k, const float* w, const float* bias, int n, int act,
+                        float* y, float* pre_act, void* ws, cudaStream_t st, const float* head_w,
+                        const float* head_b, float* head_out, bool w_transposed) {
+  return dense_tc_launch_g(x, m, k, w, bias, n, act, y, pre_act, ws, st, head_w, head_b, head_out, w_transposed, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// First Dense layer of a message network with its input gathered on the fly (see GatherA above).
+extern "C" size_t ign_gather_dense_ws_bytes(int n_src, const int32_t* widths, int n) {
+  if (n_src < 1 || n_src > IGN_MAX_SOURCES || !widths) return 0;
+  int k = 0;
+  for (int j = 0; j < n_src; ++j) {
+    if (widths[j] <= 0 || widths[j] % TC_KC) return 0;
+    k += widths[j];
+  }
+  return (k <= 256 && ign_dense_tc_supported(k, n)) ? ign_dense_tc_ws(k, n) : 0;
+}
+
+bool ign_tensor_cores_enabled();
+
+extern "C" int ign_gather_dense(int n_src, const float* const* srcs, const int32_t* const* idx, const int32_t* widths,
+                                int64_t rows, const float* w, const float* bias, int n, int act, float* y, void* ws,
+                                size_t ws_bytes, void* stream) {
+  IGN_REQUIRE(rows >= 0 && n > 0, IGN_ERR_INVALID, "IGNNITION: gather_dense: bad shape");
+  IGN_REQUIRE(act >= IGN_ACT_LINEAR && act <= IGN_ACT_LEAKY_RELU, IGN_ERR_INVALID,
+              "IGNNITION: gather_dense: unknown activation %d", act);
+  const size_t need = ign_gather_dense_ws_bytes(n_src, widths, n);
+  IGN_REQUIRE(need > 0 && rows >= TC_M && ign_tensor_cores_enabled(), IGN_ERR_UNSUPPORTED,
+              "IGNNITION: gather_dense: built for 1..%d sources of widths that are multiples of 32 (sum <= 256), "
+              "32 <= units <= 256, at least 128 rows, tensor cores on", IGN_MAX_SOURCES);
+  IGN_REQUIRE(srcs && idx && w && y, IGN_ERR_INVALID, "IGNNITION: gather_dense: null pointer");
+  IGN_REQUIRE(ws && ws_bytes >= need, IGN_ERR_WORKSPACE, "IGNNITION: gather_dense: workspace too small (%zu < %zu)",
+              ws_bytes, need);
+  GatherA ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.n = n_src;
+  int k = 0;
+  for (int j = 0; j < n_src; ++j) {
+    IGN_REQUIRE(srcs[j], IGN_ERR_INVALID, "IGNNITION: gather_dense: null source %d", j);
+    ga.src[j] = srcs[j];
+    ga.idx[j] = idx[j];
+    ga.width[j] = widths[j];
+    ga.col0[j] = k;
+    k += widths[j];
+  }
+  return dense_tc_launch_g(nullptr, rows, k, w, bias, n, act, y, nullptr, ws, ign_stream(stream), nullptr, nullptr,
+                           nullptr, false, &ga);
 }

@@ -487,9 +487,24 @@ class Engine:
                     parts.append(state[p.dst]); idx.append(g.t["dst_" + a.name])
                 else:
                     parts.append(g.t["params_" + a.name]); idx.append(None)
-            x = ops.gather_concat(parts, idx, g.t["src_" + a.name].numel())
+            n_edges = g.t["src_" + a.name].numel()
+            prefix = "%s_to_%s_message_creation_%d" % (src.name, p.dst, j)
+            first = op.model.layers[0]
+            w0 = self.param("%s/%s/kernel" % (prefix, first.name))
+            if tape is None and ops.gather_dense_supported([int(t.shape[1]) for t in parts], int(w0.shape[1]), n_edges):
+                # inference: the gather and the concat run inside the first layer's GEMM (ign_gather_dense), the
+                # [E, sum F] input is never written; the remaining layers follow on its output
+                y0 = ops.gather_dense(parts, idx, n_edges, w0,
+                                      self.param("%s/%s/bias" % (prefix, first.name)) if first.use_bias else None,
+                                      self._act(first.activation))
+                msgs = y0
+                for l in op.model.layers[1:]:
+                    msgs = self._dense_layer(prefix, l, msgs, None)
+                last = (list(op.input), [int(t.shape[1]) for t in parts], None)
+                continue
+            x = ops.gather_concat(parts, idx, n_edges)
             saves = [] if tape is not None else None
-            msgs = self._run_ff("%s_to_%s_message_creation_%d" % (src.name, p.dst, j), op.model, x, saves)
+            msgs = self._run_ff(prefix, op.model, x, saves)
             last = (list(op.input), [int(t.shape[1]) for t in parts], saves)
         if tape is not None and last is not None:       # only the last network's output is the message (:470-475)
             tape.append(("msg_ff", p, k) + last)

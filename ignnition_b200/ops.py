@@ -337,6 +337,31 @@ def gather_concat(parts: List[torch.Tensor], idx: List[Optional[torch.Tensor]], 
     return out
 
 
+def gather_dense_supported(widths: Sequence[int], units: int, rows: int) -> bool:
+    lib = _lib.load()
+    wd = (C.c_int32 * len(widths))(*[int(v) for v in widths])
+    return (rows >= 128 and len(widths) <= 4 and tensor_cores_enabled()
+            and os.environ.get("IGN_GATHER_DENSE", "1") != "0"
+            and lib.ign_gather_dense_ws_bytes(len(widths), wd, int(units)) > 0)
+
+
+def gather_dense(parts: List[torch.Tensor], idx: List[Optional[torch.Tensor]], rows: int, w, bias, act: int, out=None):
+    """act(concat_k parts[k][idx[k]] w + b) with the gather and the concat fused into the GEMM's operand loaders
+    (ign_gather_dense): the concatenated input is never materialised."""
+    lib = _lib.load()
+    widths = [int(p.shape[1]) for p in parts]
+    n = int(w.shape[1])
+    if out is None:
+        out = torch.empty(rows, n, dtype=torch.float32, device=parts[0].device)
+    wd = (C.c_int32 * len(widths))(*widths)
+    nbytes = lib.ign_gather_dense_ws_bytes(len(widths), wd, n)
+    ws = _workspace(nbytes, parts[0].device)
+    _lib.check(lib.ign_gather_dense(len(parts), _ptr_array(parts, torch.float32), _ptr_array(idx, torch.int32), wd, rows,
+                                    _f(w), _f(bias), n, act, _f(out), ws.data_ptr(), ws.numel(), _stream()),
+               "gather_dense")
+    return out
+
+
 # ------------------------------------------------------------------------------- train step
 def mse_loss(pred, label, grad_scale: float, d_pred, sse):
     lib = _lib.load()

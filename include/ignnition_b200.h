@@ -235,6 +235,19 @@ int ign_mlp_head(const float* x, int64_t m, int k1, const float* w1, const float
 int ign_gather_concat(int n_parts, const float* const* parts, const int32_t* const* idx,
                       const int32_t* widths /*host*/, int64_t rows, float* out, void* stream);
 
+/* First Dense layer of a message network with the gather and the concat FUSED into the A-operand loaders of the
+ * tcgen05 GEMM (generate_model.py:432-475): y[r, :] = act(concat_k srcs[k][idx[k] ? idx[k][r] : r, :] W + b); the
+ * [rows, sum widths] input is never written (at 200 M edges and three 64-wide parts that is a 154 GB tensor).  Built
+ * for widths that are multiples of 32 with sum <= 256, 32 <= n <= 256 (n % 32 == 0), rows >= 128; anything else
+ * returns IGN_ERR_UNSUPPORTED and the caller runs ign_gather_concat + ign_dense.  idx entries may be NULL
+ * (identity) and negative indices give zero rows. */
+size_t ign_gather_dense_ws_bytes(int n_src, const int32_t* widths /*host*/, int n);
+int ign_gather_dense(int n_src, const float* const* srcs /*host array of device ptrs*/,
+                     const int32_t* const* idx /*host array of device ptrs, entries nullable*/,
+                     const int32_t* widths /*host*/, int64_t rows, const float* w, const float* bias, int n, int act,
+                     float* y, void* ws, size_t ws_bytes, void* stream);
+
+
 /* ---------------------------------------------------------------------------------------------
  * Train step (model_fn, generate_model.py:697-830): backward twins + loss + Adam.
  */

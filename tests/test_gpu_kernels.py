@@ -781,3 +781,45 @@ def test_csr_rank_gaps_are_zero_rows():
     bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     ops.index_range_check(dev(np.array([0, 5, -1, 3], np.int32)), 4, bad)
     assert int(bad.item()) == 2
+
+
+@pytest.mark.parametrize("rows,widths,units,act", [(128, [32], 32, "linear"), (1000, [32, 64], 64, "selu"),
+                                                   (5000, [64, 64, 32], 128, "tanh"), (9000, [32, 32], 32, "relu"),
+                                                   (4500, [64, 32, 32, 128], 256, "sigmoid")])
+def test_gather_dense(rows, widths, units, act):
+    """ign_gather_dense (gather + concat inside the A-operand loaders of the tcgen05 GEMM, small-M and pipelined
+    kernels) == ign_gather_concat + ign_dense bit for bit (same GEMM on the same operand values) and == numpy fp64 to
+    1e-5; identity index, negative indices (zero rows), ragged last tile."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(rows + units)
+    parts, idx, parts_np, idx_np = [], [], [], []
+    for k, wd in enumerate(widths):
+        if k == 1:                      # a per-edge array read in place (identity index)
+            a = rng.randn(rows, wd).astype(np.float32)
+            ix = None
+        else:
+            n_src = max(3, rows // 7 + k)
+            a = rng.randn(n_src, wd).astype(np.float32)
+            ix = rng.randint(0, n_src, rows).astype(np.int32)
+            ix[rng.rand(rows) < 0.03] = -1
+        parts_np.append(a); idx_np.append(ix)
+        parts.append(dev(a)); idx.append(None if ix is None else dev(ix, torch.int32))
+    K = sum(widths)
+    W = (rng.randn(K, units) / np.sqrt(K)).astype(np.float32)
+    b = rng.randn(units).astype(np.float32) * 0.1
+    a_id = ops.ACTIVATIONS[act]
+    assert ops.gather_dense_supported(widths, units, rows)
+    got = ops.gather_dense(parts, idx, rows, dev(W), dev(b), a_id).cpu().numpy()
+    x = ops.gather_concat(parts, idx, rows)
+    two = ops.dense(x, dev(W), dev(b), a_id).cpu().numpy()
+    assert np.array_equal(got, two)
+    x64 = np.concatenate([(a[np.maximum(ix, 0)] * (ix >= 0)[:, None]) if ix is not None else a
+                          for a, ix in zip(parts_np, idx_np)], axis=1).astype(np.float64)
+    assert np.array_equal(x.cpu().numpy(), x64.astype(np.float32))
+    want = orc.ACT[act](x64 @ W.astype(np.float64) + b.astype(np.float64)) if hasattr(orc, "ACT") else None
+    if want is None:
+        z = x64 @ W.astype(np.float64) + b.astype(np.float64)
+        want = {"linear": z, "relu": np.maximum(z, 0), "tanh": np.tanh(z), "sigmoid": 1 / (1 + np.exp(-z)),
+                "selu": 1.0507009873554805 * np.where(z > 0, z, 1.6732632423543772 * (np.exp(z) - 1))}[act]
+    assert rel_err(got, want) < RTOL
+    assert not ops.gather_dense_supported([24, 32], units, rows) and not ops.gather_dense_supported(widths, units, 100)

@@ -136,7 +136,14 @@ def _mpnn_json(agg="sum", hidden=64, update="gru", message_nn=False):
            {"nn_name": "ro", "nn_type": "feed_forward", "nn_architecture": [
                {"type_layer": "Dense", "units": 16, "activation": "relu"},
                {"type_layer": "Dense", "units": 1, "activation": "None"}]}]
-    if message_nn:
+    if message_nn == "fused":
+        # state-only inputs of widths that are multiples of 32 and a 64-unit first layer: the shape ign_gather_dense
+        # is built for (gather + concat inside the GEMM's operand loaders)
+        msg = [{"type": "neural_network", "nn_name": "msg", "input": ["hs_source", "hs_dest"]}]
+        nns.append({"nn_name": "msg", "nn_type": "feed_forward", "nn_architecture": [
+            {"type_layer": "Dense", "units": 64, "activation": "selu"},
+            {"type_layer": "Dense", "units": hidden, "activation": "None"}]})
+    elif message_nn:
         msg = [{"type": "neural_network", "nn_name": "msg", "input": ["hs_source", "hs_dest", "edge_params"]}]
         nns.append({"nn_name": "msg", "nn_type": "feed_forward", "nn_architecture": [
             {"type_layer": "Dense", "units": 24, "activation": "tanh", "kernel_regularizer": 0.01},
@@ -181,19 +188,29 @@ def _mpnn_sample(rng, n, max_deg, feat=3, params=False):
     ("sum", 32, "gru", True),       # message MLP on [hs_source | hs_dest | edge_params]
     ("ordered", 32, "gru", False),
     ("ordered", 32, "gru", True),   # the ordered walk reads message-MLP rows (edge order) through perm
+    ("sum", 32, "gru", "fused"),    # message MLP on [hs_source | hs_dest] through ign_gather_dense (no [E, 64] input tensor)
+    ("sum", 64, "gru", "fused"),
+    ("ordered", 32, "gru", "fused"),
 ])
-def test_generic_mpnn(agg, hidden, update, message_nn):
+def test_generic_mpnn(agg, hidden, update, message_nn, monkeypatch):
     rng = np.random.RandomState(len(agg) + hidden)
     model_json = _mpnn_json(agg, hidden, update, message_nn)
-    samples = [_mpnn_sample(rng, n, 6, params=message_nn) for n in (40, 1, 300)]
+    samples = [_mpnn_sample(rng, n, 6, params=message_nn is True) for n in (40, 1, 300)]
+    if message_nn == "fused":      # the fused path must be the one that runs
+        from ignnition_b200 import ops
+        calls = []
+        real = ops.gather_dense
+        monkeypatch.setattr(ops, "gather_dense", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
     if agg == "ordered":           # ordered needs >= 1 message per destination in the reference
         for s in samples:
             for v in s["entities"]:
-                s["adj"].setdefault(v, [[v, [1.0, 2.0]]] if message_nn else [v])
+                s["adj"].setdefault(v, [[v, [1.0, 2.0]]] if message_nn is True else [v])
     dims = sample_dimensions(samples[0])
     md, eng, o64, w = make(model_json, dims)
     tens = [tensors_of(md, s)[0] for s in samples]
     pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    if message_nn == "fused":
+        assert len(calls) == 3      # one fused first layer per message-passing iteration
     want, wstate = [], []
     for t in tens:
         p, s = o64.forward(t, w, return_states=True)
