@@ -171,7 +171,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ our arm
 def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0, want_e2e=True, want_kernels=True,
-                 parity_samples=0, total_scale=None):
+                 parity_samples=0, total_scale=None, graphed=False):
     """One workload through the Engine on this rank's GPU: resident-input steps, end-to-end steps from pinned host
     memory, per-kernel CUDA-event times, parity against the fp64 oracle.  Times are max over ranks.
     ``total_scale``: samples the whole job processes per step (default: n_samples x world)."""
@@ -204,6 +204,8 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
         trainer = Trainer(eng, world_size=world)
 
     def step_resident(graph):
+        if graphed:                    # one captured CUDA graph: adjacency build + forward (Engine.forward_graphed)
+            return eng.forward_graphed(batch, pinned, copy=False)
         if trainer is not None:        # model_fn train step: forward + loss + backward + all-reduce + Adam
             eng.build_graph(graph, training=True)
             graph.csr_t.clear()
@@ -231,7 +233,13 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
             ready[slot].record(copy_stream)
         return g_
 
+    def step_e2e_graphed():
+        pred = eng.forward_graphed(batch, pinned, copy=True)       # H2D into the graph's staging buffer + one replay
+        host_pred.copy_(pred, non_blocking=True)
+
     def step_e2e():
+        if graphed:
+            return step_e2e_graphed()
         k = e2e_state["k"]
         if not e2e_state["primed"]:
             for s_ in range(2):
@@ -297,7 +305,9 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
         ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
 
     # per-kernel CUDA-event timing of more passes (same stream, after the timed region)
-    kern = profile_kernels(eng, graph, torch, steps, trainer, n_pred_glob) if want_kernels else {}
+    kern = profile_kernels(eng, graph, torch, steps, trainer, n_pred_glob) if (want_kernels and not graphed) else {}
+    if graphed:                         # launches were counted at capture time: kernels inside the graph x replays
+        launches = eng.graphed_kernels(batch, pinned) * steps
 
     # parity of the timed configuration: the first samples of this rank's batch vs the fp64 CPU oracle, predictions
     # AND every entity's final state (north_star: 1e-5 on node and link states and predictions)
@@ -336,9 +346,12 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
                   # NumPy fp32 against the same program in fp64 (profiles/r2_parity.md)
                   "fp32_oracle_vs_fp64_oracle": {"predictions": floor_p, "states": floor_s},
                   "weights": "Keras default initialisers (glorot kernels, orthogonal recurrent kernels), seed 0"}
+        if graphed:
+            parity["graph_replay_equals_eager_forward"] = bool(torch.equal(eng.forward_graphed(batch, pinned), pred_t))
 
     total = total_scale if total_scale is not None else n_samples * world
-    out = {"workload": workload, "mode": "train" if train else "inference", "n_gpus": world,
+    out = {"workload": workload, "mode": ("inference, one CUDA graph per step" if graphed else
+                                          "train" if train else "inference"), "n_gpus": world,
            "samples_per_gpu": n_samples, "samples_per_step": total, "steps": steps,
            "value": total * steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / steps,
            "mp_edges_per_s": edges_per_iter * eng.T * world * steps / (ms / 1e3),
@@ -386,6 +399,7 @@ def compact(case, hbm_peak, peak_src, scaling="weak", default_size=True, note=No
     out = {k: case[k] for k in ("workload", "mode", "n_gpus", "samples_per_gpu", "samples_per_step", "steps", "value",
                                 "unit", "ms_per_step", "gpu_launches", "launches_per_step")}
     out["metric"] = "routenet_train_samples_per_s" if case["mode"] == "train" else "routenet_samples_per_s"
+    out["top_kernels"] = []
     out["scaling"] = scaling
     if "e2e" in case:
         out["e2e"] = case["e2e"]
@@ -460,6 +474,11 @@ def run_ours(args):
                                     hbm_peak, peak_src, default_size=False,
                                     note="launch-bound size: %d samples per step" % bsz),
                     "routenet_nsfnet_b%d/%s" % (bsz, "train" if tr else "inference"))
+            leg(lambda: compact(measure_case(ctx, "routenet_nsfnet_b4096", bsz, False, 100, 5, parity_samples=3,
+                                             graphed=True), hbm_peak, peak_src, default_size=False,
+                                note="%d samples per step; adjacency build + T = 8 iterations + readout replayed as one "
+                                     "captured CUDA graph (Engine.forward_graphed)" % bsz),
+                "routenet_nsfnet_b%d/graphed" % bsz)
 
     if rank == 0:
         roof = roofline_of(main, hbm_peak, peak_src, n_samples == n_default)

@@ -56,6 +56,10 @@ SIGNATURES = {
     "ign_dense_bwd_ws_bytes": (_sz, [_int, _int]),
     "ign_dense_bwd": (_int, [_p, _i64, _int, _p, _int, _int, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_gru_cell_bwd": (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ign_gru_gates_bwd": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
+    "ign_scale_rows_inv_degree": (_int, [_p, _p, _i64, _int, _p]),
+    "ign_segment_broadcast": (_int, [_p, _p, _i64, _int, _p, _p]),
+    "ign_segment_max_bwd": (_int, [_p, _p, _p, _p, _p, _p, _i64, _int, _p, _p]),
     "ign_gru_seq_bwd": (_int, [_p, _p, _p, _int, _p, _int, _p, _p, _i64, _int, _p, _p, _p, _p, _p, _p,
                                _p, _p, _p, _p]),
     "ign_gru_seq_bwd_steps_ws_bytes": (_sz, [_i64]),

@@ -387,6 +387,33 @@ int bwd_grid(KernelT k, size_t smem, int64_t ntiles, int* grid) {
   return IGN_OK;
 }
 
+// ---- generic GRU-cell backward (any f_in, units): the element-wise middle of a composition of Dense primitives.
+//   zx = x K + b_in, zh = h R + b_rec                  (ign_dense, linear)
+//   this kernel: zx <- GX = [d_az | d_ar | d_axh],  zh <- GH = [d_az | d_ar | d_ahh],  dh_direct = dL/dh' * z
+//   dx = GX K^T, dK += x^T GX, db_in += colsum GX;  dh = dh_direct + GH R^T, dR += h^T GH, db_rec += colsum GH
+//                                                      (ign_dense_bwd, linear)
+// Same formulas as bwd_tile_step above (Keras GRUCell v2, reset_after).
+__global__ void gru_gates_bwd_kernel(float* __restrict__ zx, float* __restrict__ zh, const float* __restrict__ h,
+                                     const float* __restrict__ d_out, int64_t n, int U, float* __restrict__ dh_direct) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * U) return;
+  const int64_t r = i / U;
+  const int u = (int)(i - r * U);
+  float* px = zx + r * 3 * U + u;
+  float* ph = zh + r * 3 * U + u;
+  const float z = sigmoid_f(px[0] + ph[0]);
+  const float rr = sigmoid_f(px[U] + ph[U]);
+  const float ahh = ph[2 * U];
+  const float hh = tanhf(fmaf(rr, ahh, px[2 * U]));
+  const float dh = d_out[i];
+  const float g_xh = dh * (1.0f - z) * (1.0f - hh * hh);
+  const float g_az = dh * (h[i] - hh) * z * (1.0f - z);
+  const float g_ar = g_xh * ahh * rr * (1.0f - rr);
+  px[0] = g_az; px[U] = g_ar; px[2 * U] = g_xh;
+  ph[0] = g_az; ph[U] = g_ar; ph[2 * U] = g_xh * rr;
+  dh_direct[i] = dh * z;
+}
+
 int check_bwd_shape(const char* who, int f_in, int units) {
   IGN_REQUIRE(f_in == units && (units == 16 || units == 32), IGN_ERR_UNSUPPORTED,
               "IGNNITION: %s: the backward pass is built for message width == units in {16, 32} "
@@ -420,6 +447,17 @@ extern "C" int ign_gru_cell_bwd(const float* x, const float* h, int64_t n, int f
                                                                       dx, dh, d_kernel, d_recurrent_kernel, d_bias);
   }
   IGN_CHECK_LAUNCH("gru_cell_bwd");
+  return IGN_OK;
+}
+
+extern "C" int ign_gru_gates_bwd(float* zx, float* zh, const float* h, const float* d_out, int64_t n, int units,
+                                 float* dh_direct, void* stream) {
+  IGN_REQUIRE(n >= 0 && units > 0, IGN_ERR_INVALID, "IGNNITION: gru_gates_bwd: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(zx && zh && h && d_out && dh_direct, IGN_ERR_INVALID, "IGNNITION: gru_gates_bwd: null pointer");
+  gru_gates_bwd_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh, h, d_out, n, units,
+                                                                                          dh_direct);
+  IGN_CHECK_LAUNCH("gru_gates_bwd");
   return IGN_OK;
 }
 

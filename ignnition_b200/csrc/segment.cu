@@ -339,3 +339,98 @@ extern "C" int ign_axpy(int64_t n, float a, const float* x, float* y, void* stre
   IGN_CHECK_LAUNCH("axpy");
   return IGN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the mean / max aggregations (north_star extensions; TensorFlow semantics of reduce_mean / of
+// unsorted_segment_max: the gradient of a maximum is split evenly among the slots that attain it).
+namespace {
+
+// d[r, :] *= 1 / max(deg(r), 1): turns dL/d(mean) into dL/d(sum)
+__global__ void scale_rows_inv_degree_kernel(float* __restrict__ d, const int* __restrict__ rowptr, int64_t n, int width) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * (width / 4)) return;
+  const int64_t r = i / (width / 4);
+  const int deg = rowptr[r + 1] - rowptr[r];
+  if (deg <= 1) return;
+  const float inv = 1.0f / (float)deg;
+  float4 v = reinterpret_cast<float4*>(d)[i];
+  v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+  reinterpret_cast<float4*>(d)[i] = v;
+}
+
+// d_msg[pos(slot), :] = (rows[idx[slot], f] == agg[d, f]) ? d_agg[d, f] / #ties : 0 for every slot of destination d;
+// pos(slot) = perm[slot] (input edge position) or the slot itself.  G = width / 4 lanes per destination.
+__global__ void segment_max_bwd_kernel(const int* __restrict__ rowptr, const int* __restrict__ idx,
+                                       const int* __restrict__ perm, const float* __restrict__ rows,
+                                       const float* __restrict__ agg, const float* __restrict__ d_agg, int64_t n,
+                                       int width, float* __restrict__ d_msg) {
+  const int q = width / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * q) return;
+  const int64_t d = i / q;
+  const int c = (int)(i - d * q) * 4;
+  const int lo = rowptr[d], hi = rowptr[d + 1];
+  if (hi <= lo) return;
+  const float4 m = *reinterpret_cast<const float4*>(agg + d * width + c);
+  const float4 g = *reinterpret_cast<const float4*>(d_agg + d * width + c);
+  float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = lo; s < hi; ++s) {
+    const int r = idx[s];
+    const float4 v = r >= 0 ? *reinterpret_cast<const float4*>(rows + (int64_t)r * width + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cnt.x += v.x == m.x; cnt.y += v.y == m.y; cnt.z += v.z == m.z; cnt.w += v.w == m.w;
+  }
+  const float4 w = make_float4(g.x / fmaxf(cnt.x, 1.f), g.y / fmaxf(cnt.y, 1.f), g.z / fmaxf(cnt.z, 1.f), g.w / fmaxf(cnt.w, 1.f));
+  for (int s = lo; s < hi; ++s) {
+    const int r = idx[s];
+    const float4 v = r >= 0 ? *reinterpret_cast<const float4*>(rows + (int64_t)r * width + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t pos = perm ? perm[s] : s;
+    *reinterpret_cast<float4*>(d_msg + pos * width + c) =
+        make_float4(v.x == m.x ? w.x : 0.f, v.y == m.y ? w.y : 0.f, v.z == m.z ? w.z : 0.f, v.w == m.w ? w.w : 0.f);
+  }
+}
+
+// out[r, :] = rows[s, :] for every row r of segment s (rowptr[s] <= r < rowptr[s + 1]): backward of a per-sample sum
+__global__ void segment_broadcast_kernel(const int* __restrict__ rowptr, const float* __restrict__ rows, int64_t n_seg,
+                                         int width, float* __restrict__ out) {
+  const int q = width / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seg * q) return;
+  const int64_t s = i / q;
+  const int c = (int)(i - s * q) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(rows + s * width + c);
+  for (int64_t r = rowptr[s]; r < rowptr[s + 1]; ++r) *reinterpret_cast<float4*>(out + r * width + c) = v;
+}
+
+}  // namespace
+
+extern "C" int ign_segment_broadcast(const int32_t* rowptr, const float* rows, int64_t n_seg, int width, float* out,
+                                     void* stream) {
+  IGN_REQUIRE(n_seg >= 0 && width > 0 && width % 4 == 0, IGN_ERR_INVALID, "IGNNITION: segment_broadcast: bad shape");
+  if (n_seg == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr && rows && out, IGN_ERR_INVALID, "IGNNITION: segment_broadcast: null pointer");
+  segment_broadcast_kernel<<<(unsigned)ign_cdiv(n_seg * (width / 4), 256), 256, 0, ign_stream(stream)>>>(rowptr, rows, n_seg,
+                                                                                                      width, out);
+  IGN_CHECK_LAUNCH("segment_broadcast");
+  return IGN_OK;
+}
+
+extern "C" int ign_scale_rows_inv_degree(float* d, const int32_t* rowptr, int64_t n, int width, void* stream) {
+  IGN_REQUIRE(n >= 0 && width > 0 && width % 4 == 0, IGN_ERR_INVALID, "IGNNITION: scale_rows_inv_degree: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(d && rowptr, IGN_ERR_INVALID, "IGNNITION: scale_rows_inv_degree: null pointer");
+  scale_rows_inv_degree_kernel<<<(unsigned)ign_cdiv(n * (width / 4), 256), 256, 0, ign_stream(stream)>>>(d, rowptr, n, width);
+  IGN_CHECK_LAUNCH("scale_rows_inv_degree");
+  return IGN_OK;
+}
+
+extern "C" int ign_segment_max_bwd(const int32_t* rowptr, const int32_t* idx, const int32_t* perm, const float* rows,
+                                   const float* agg, const float* d_agg, int64_t num_dst, int width, float* d_msg,
+                                   void* stream) {
+  IGN_REQUIRE(num_dst >= 0 && width > 0 && width % 4 == 0, IGN_ERR_INVALID, "IGNNITION: segment_max_bwd: bad shape");
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr && idx && rows && agg && d_agg && d_msg, IGN_ERR_INVALID, "IGNNITION: segment_max_bwd: null pointer");
+  segment_max_bwd_kernel<<<(unsigned)ign_cdiv(num_dst * (width / 4), 256), 256, 0, ign_stream(stream)>>>(
+      rowptr, idx, perm, rows, agg, d_agg, num_dst, width, d_msg);
+  IGN_CHECK_LAUNCH("segment_max_bwd");
+  return IGN_OK;
+}

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .batching import AdjacencySpec, Batch, SequenceSpec, assemble
 from .model_description import FeedForward, MessagePassing, ModelDescription
 
@@ -196,6 +196,9 @@ class Engine:
                         self._needs_perm.add(a.name)
                 elif agg in ("sum", "mean", "max"):
                     p.op = {"sum": ops.OP_SUM, "mean": ops.OP_MEAN, "max": ops.OP_MAX}[agg]
+                    if p.op == ops.OP_MAX:      # the backward of a max writes per-edge gradients in input edge order
+                        for a_ in p.adjs:
+                            self._needs_perm.add(a_.name)
                     p.kind = "agg_gru" if mp.update.type == "recurrent_nn" else "agg_ff"
                 elif agg in ("ordered", "interleave") or (agg == "concat" and mp.aggregation.concat_axis == 1):
                     # concat along axis 1 = the sources' padded blocks one after the other
@@ -277,6 +280,7 @@ class Engine:
             elif op.type == "extend_adjacencies":        # auxilary_classes.py:1236-1265
                 dims[op.output_name[0]] = dims[op.input[0]]
                 dims[op.output_name[1]] = dims[op.input[1]]
+                self._needs_perm.add(op.adj_list)        # its backward reduces per-edge rows in input edge order
                 self.readout.append((k, op))
             else:
                 raise RuntimeError("IGNNITION: readout operation '%s' is not built yet in the B200 engine "
@@ -348,6 +352,59 @@ class Engine:
             # takes its pre-sorted fast path (and still verifies the order on the device)
             skip = skip + tuple("seq_" + n for n, srt in batch.dst_sorted.items() if srt)
         return batch.pack(pin=pin, skip=skip)
+
+    # ------------------------------------------------------------------ small batches: captured CUDA graphs
+    def forward_graphed(self, batch: Batch, pinned=None, copy: bool = True) -> torch.Tensor:
+        """Inference of ``batch`` through a captured CUDA graph: adjacency build + T iterations + readout are ONE
+        graph launch instead of ~50 kernel launches issued from Python, which is what bounds the reference's own batch
+        sizes (train_options.ini: batch_size 3 ... 32; framework_operations.py:200-236).  One graph per batch SHAPE
+        (array layout of the packed batch, row counts, sequence lengths); a batch of a known shape costs one
+        host -> device copy into the graph's static staging buffer and one replay.  The returned predictions live in
+        the graph's static output buffer: read them before the next call with the same shape.
+        ``copy=False`` replays on whatever the staging buffer holds (bench: device-resident inputs)."""
+        if pinned is None:
+            pinned = self.pack(batch)
+        buf, layout = pinned
+        sig = (batch.n_samples, tuple(sorted(batch.num.items())), tuple(sorted(batch.max_seq.items())),
+               tuple(sorted(batch.dst_sorted.items())),
+               tuple((k, off, str(np.dtype(dt)), tuple(shape)) for k, (off, dt, shape) in layout.items()))
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        entry = self._graphs.get(sig)
+        if entry is None:
+            stage = torch.empty(buf.numel(), dtype=torch.uint8, device=self.device)
+            dg = self.upload(batch, pinned, out=stage)
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # eager pass first: one-time kernel attributes, workspace sizes
+                self.build_graph(dg)
+                self.forward(dg)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.load().ign_launch_count()
+            with torch.cuda.graph(graph):
+                self.build_graph(dg)
+                pred = self.forward(dg)
+            entry = (graph, stage, dg, pred, int(_lib.load().ign_launch_count() - l0))
+            self._graphs[sig] = entry
+            copy = True
+        graph, stage, dg, pred, _ = entry
+        if copy:
+            stage.copy_(buf, non_blocking=True)
+        graph.replay()
+        return pred
+
+    def graphed_kernels(self, batch: Batch, pinned=None) -> int:
+        """Kernels inside the captured graph of this batch shape (0 if none was captured yet)."""
+        if pinned is None:
+            pinned = self.pack(batch)
+        buf, layout = pinned
+        for sig, entry in getattr(self, "_graphs", {}).items():
+            if sig[0] == batch.n_samples and sig[1] == tuple(sorted(batch.num.items())):
+                return entry[4]
+        return 0
 
     def upload(self, batch: Batch, pinned=None, out: Optional[torch.Tensor] = None) -> DeviceGraph:
         """Host -> device copy of the packed batch (one cudaMemcpyAsync) + tensor views."""
@@ -560,16 +617,17 @@ class Engine:
             agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
             ops.agg_gru_cell_tc(p.op, rowptr, col, state[p.adjs[0].src], h, K, R, B, [out], agg_out=agg)
             if tape is not None:
-                tape.append(("agg_gru_unfused", p, has_msg, h, agg))
+                tape.append(("agg_gru_unfused", p, has_msg, h, agg, (state[p.adjs[0].src], col)))
             return out
         if fused:
             rowptr, col, _ = g.csr[p.adjs[0].name]
             agg = torch.empty(n_dst, p.msg_dim, dtype=torch.float32, device=self.device) if tape is not None else None
             ops.agg_gru_cell(rowptr, col, state[p.adjs[0].src], h, K, R, B, out=out, agg_out=agg)
             if tape is not None:
-                tape.append(("agg_gru", p, has_msg, h, agg))
+                tape.append(("agg_gru", p, has_msg, h, agg, None))
             return out
         agg = None
+        max_src = None       # (rows, index per CSR slot) the aggregation read: what the backward of a max compares
         if p.attn:      # Attention_aggr (auxilary_classes.py:278-344)
             if tape is not None:
                 raise RuntimeError("IGNNITION: training through the attention aggregation is not built")
@@ -586,8 +644,10 @@ class Engine:
             rowptr, col, perm = g.csr[a.name]
             if msgs[k] is None:
                 part = ops.segment_reduce(ops.OP_SUM if len(p.adjs) > 1 else p.op, rowptr, col, state[a.src])
+                max_src = (state[a.src], col)
             else:
                 part = ops.segment_reduce(ops.OP_SUM if len(p.adjs) > 1 else p.op, rowptr, perm, msgs[k])
+                max_src = (msgs[k], perm)
             if agg is None:
                 agg = part
             else:
@@ -597,14 +657,14 @@ class Engine:
         if p.conv:      # Conv_aggr (auxilary_classes.py:366-401); the kernel product commutes with the sum
             if len(p.adjs) != 1:
                 raise RuntimeError("IGNNITION: convolution over several sources is not built")
+            agg_sum = agg
             nsum = ops.dense(agg, self.param(dst + "_convolution/conv_kernel"), None, 0)
             agg = ops.conv_finish(nsum, h, g.csr[p.adjs[0].name][0], self._act(p.mp.aggregation.activation_function))
-            if tape is not None:
-                raise RuntimeError("IGNNITION: training through the convolution aggregation is not built")
+            max_src = ("conv", agg_sum)          # the backward needs the plain neighbour sum (train.py)
         if p.kind == "agg_gru":
             ops.gru_cell(agg, h, K, R, B, out=out)
             if tape is not None:
-                tape.append(("agg_gru_unfused", p, has_msg, h, agg))
+                tape.append(("agg_gru_unfused", p, has_msg, h, agg, max_src))
             return out
         x = ops.gather_concat([agg, h], [None, None], n_dst)          # FF update, generate_model.py:599
         ff = p.mp.update.model
@@ -612,7 +672,7 @@ class Engine:
         saves = [] if tape is not None else None
         y = self._run_ff(dst + "_ff_update", layers, x, saves)
         if tape is not None:
-            tape.append(("agg_ff", p, has_msg, int(agg.shape[1]), saves))
+            tape.append(("agg_ff", p, has_msg, int(agg.shape[1]), saves, agg, max_src))
         return y
 
     @staticmethod
@@ -646,33 +706,35 @@ class Engine:
         result = None
         for k, op in self.readout:
             if op.type == "pooling":
-                if tape is not None:
-                    raise RuntimeError("IGNNITION: training through readout pooling is not built")
                 ent = owner.get(op.input[0])
                 if ent is None or g is None:
                     raise RuntimeError("IGNNITION: pooling needs an entity-shaped input")
                 red = {"sum": ops.OP_SUM, "mean": ops.OP_MEAN, "max": ops.OP_MAX}[op.type_pooling]
                 st[op.output_name] = ops.segment_reduce(red, g.t["offsets_" + ent], None, st[op.input[0]])
                 owner[op.output_name] = None              # one row per sample
+                if tape is not None:
+                    tape.append(("pool", op, red, g.t["offsets_" + ent], st[op.input[0]], st[op.output_name]))
                 continue
             if op.type == "product":
-                if tape is not None:
-                    raise RuntimeError("IGNNITION: training through readout products is not built")
                 a, b = st[op.input[0]], st[op.input[1]]
                 if a.shape != b.shape:
                     raise RuntimeError("IGNNITION:  The product operation between %s and %s failed. Check that the "
                                        "dimensions are compatible." % (op.input[0], op.input[1]))
                 st[op.output_name] = ops.mul(a, b)
                 owner[op.output_name] = owner.get(op.input[0])
+                if tape is not None:
+                    tape.append(("product", op, a, b))
                 continue
             if op.type == "extend_adjacencies":
-                if tape is not None or g is None:
-                    raise RuntimeError("IGNNITION: training through extend_adjacencies is not built")
+                if g is None:
+                    raise RuntimeError("IGNNITION: extend_adjacencies needs the graph tensors")
                 src_idx, dst_idx = g.t["src_" + op.adj_list], g.t["dst_" + op.adj_list]
                 n_e = src_idx.numel()
                 st[op.output_name[0]] = ops.gather_concat([st[op.input[0]]], [src_idx], n_e)
                 st[op.output_name[1]] = ops.gather_concat([st[op.input[1]]], [dst_idx], n_e)
                 owner[op.output_name[0]] = owner[op.output_name[1]] = None
+                if tape is not None:
+                    tape.append(("extend", op))
                 continue
             if len(op.input) == 1:
                 x = st[op.input[0]]
@@ -681,7 +743,7 @@ class Engine:
             saves = [] if tape is not None else None
             y = self._run_ff("readout_model_%d" % k, op.architecture, x, saves)
             if tape is not None:
-                tape.append(("readout", op, saves))
+                tape.append(("readout", op, saves, [int(st[i].shape[1]) for i in op.input]))
             if op.type == "predict":
                 result = y
                 break

@@ -333,7 +333,9 @@ def predict(model: ModelDescription, namespace: Optional[dict] = None, engine=No
         chunk = list(itertools.islice(it, chunk_size))
         if not chunk:
             break
-        p = engine.forward(engine.prepare(chunk)).cpu().numpy().reshape(-1)
+        # chunks of one shape (the usual case: every sample of a dataset has the topology's sizes) replay one captured
+        # CUDA graph: a host -> device copy and one launch per chunk instead of ~50 launches
+        p = engine.forward_graphed(engine.assemble(chunk)).cpu().numpy().reshape(-1)
         off = 0
         for x in chunk:
             n = int(x["num_" + out_entity])

@@ -398,6 +398,19 @@ def dense_head_bwd_chain(x, w, dz, prev_act: int, dz_prev, dw, db_prev):
 def gru_cell_bwd(x, h, kernel, rkernel, bias, d_out, dx, dh, dk, drk, db):
     lib = _lib.load()
     n, units = h.shape
+    f_in = x.shape[1]
+    if not (f_in == units and units in (16, 32)):
+        # generic shapes (config 5's 64-wide model, f_in != units): recompute the two gate GEMMs, one element-wise
+        # kernel for the gate gradients, and the Dense backward for dx / dh and the weight gradients
+        zx = dense(x, kernel, bias[0], 0)
+        zh = dense(h, rkernel, bias[1], 0)
+        direct = torch.empty_like(h)
+        _lib.check(lib.ign_gru_gates_bwd(_f(zx), _f(zh), _f(h), _f(d_out), n, units, _f(direct), _stream()),
+                   "gru_gates_bwd")
+        dense_bwd(x, kernel, 0, None, zx, dx, dk, db[0])
+        dense_bwd(h, rkernel, 0, None, zh, dh, drk, db[1])
+        axpy(1.0, direct, dh)
+        return
     _lib.check(lib.ign_gru_cell_bwd(_f(x), _f(h), n, x.shape[1], units, _f(kernel), _f(rkernel), _f(bias),
                                     _f(d_out), _f(dx), _f(dh), _f(dk), _f(drk), _f(db), _stream()),
                "gru_cell_bwd")
@@ -538,6 +551,31 @@ def rows_put(src, rows, dst):
     lib = _lib.load()
     d = _f(dst) if torch.is_tensor(dst) else int(dst)
     _lib.check(lib.ign_rows_put(_f(src), _i(rows), rows.numel(), src.shape[1], d, _stream()), "rows_put")
+
+
+def scale_rows_inv_degree(d, rowptr):
+    """d[r, :] /= max(in-degree of r, 1), in place: dL/d(mean) -> dL/d(sum)."""
+    lib = _lib.load()
+    _lib.check(lib.ign_scale_rows_inv_degree(_f(d), _i(rowptr), d.shape[0], d.shape[1], _stream()), "scale_rows_inv_degree")
+    return d
+
+
+def segment_broadcast(rowptr, rows, n_out: int):
+    """out[r] = rows[s] for every row r of segment s: backward of a per-sample sum."""
+    lib = _lib.load()
+    out = torch.zeros(n_out, rows.shape[1], dtype=torch.float32, device=rows.device)
+    _lib.check(lib.ign_segment_broadcast(_i(rowptr), _f(rows), rows.shape[0], rows.shape[1], _f(out), _stream()),
+               "segment_broadcast")
+    return out
+
+
+def segment_max_bwd(rowptr, idx, perm, rows, agg, d_agg, n_edges: int):
+    """Per-edge message gradients of a max aggregation (ties share evenly), [n_edges, width], at row perm[slot]."""
+    lib = _lib.load()
+    d_msg = torch.zeros(n_edges, agg.shape[1], dtype=torch.float32, device=agg.device)
+    _lib.check(lib.ign_segment_max_bwd(_i(rowptr), _i(idx), _i(perm), _f(rows), _f(agg), _f(d_agg), agg.shape[0],
+                                       agg.shape[1], _f(d_msg), _stream()), "segment_max_bwd")
+    return d_msg
 
 
 def peer_copy(dst_ptr: int, src_ptr: int, nbytes: int):

@@ -101,14 +101,23 @@ class Trainer:
                                                              want_perm=a.name in e._needs_perm)
                         graph.csr_t[a.name] = (rp, col_t, perm_t)
 
+        for _, op in e.readout:
+            if op.type == "extend_adjacencies" and op.adj_list not in graph.csr_t:
+                a = [x for x in e.adjacencies if x.name == op.adj_list][0]
+                rp, col_t, perm_t, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name], None,
+                                                     graph.num[a.src], ops.CSR_SORT, want_perm=True)
+                graph.csr_t[a.name] = (rp, col_t, perm_t)
+
     # ------------------------------------------------------------------ backward
     def backward(self, graph, tape: list, d_pred: torch.Tensor):
         e = self.e
         dev = e.device
+        # dL/d(state) per entity, and per derived readout name (outputs of pooling / product / extend_adjacencies /
+        # neural_network operations) while the readout is walked backwards
         gstate: Dict[str, Optional[torch.Tensor]] = {n: None for n in e.entities}
 
         def add_grad(ent: str, contrib: torch.Tensor):
-            if gstate[ent] is None:
+            if gstate.get(ent) is None:
                 gstate[ent] = contrib
             else:
                 ops.axpy(1.0, contrib, gstate[ent])
@@ -116,7 +125,7 @@ class Trainer:
         def reduce_into(ent: str, rowptr, idx, rows):
             """gstate[ent] (+)= per-row sums of `rows` over the segments of (rowptr, idx): the accumulation happens in
             the reduction kernel (IGN_OP_SUM_ADD), no temporary and no second pass"""
-            if gstate[ent] is None:
+            if gstate.get(ent) is None:
                 gstate[ent] = ops.segment_reduce(ops.OP_SUM, rowptr, idx, rows)
             else:
                 ops.segment_reduce(ops.OP_SUM_ADD, rowptr, idx, rows, out=gstate[ent])
@@ -149,8 +158,35 @@ class Trainer:
                 dy = dx
             return dy
 
-        def route_aggregate_grad(p, has_msg, d_agg):
-            """dL/d(sum of messages per destination) -> source states, or -> per-edge messages of a message network"""
+        def route_aggregate_grad(p, has_msg, d_agg, agg=None, max_src=None):
+            """dL/d(aggregated messages per destination) -> source states, or -> per-edge messages of a message
+            network.  mean: dL/d(sum) = dL/d(mean) / degree; max: the slots that attain the maximum share the gradient
+            (TensorFlow's unsorted_segment_max), written per edge and reduced per source row."""
+            if p.conv:
+                # Conv_aggr (auxilary_classes.py:366-401): out = act((sum W + h) / deg).  dL/d(sum W + h) = act'(out) dL/dout
+                # / deg goes to the destination's own state as it is, and through the kernel product to the neighbour sum
+                _, agg_sum = max_src
+                ck = e.param(p.dst + "_convolution/conv_kernel")
+                ops.scale_rows_inv_degree(d_agg, graph.csr[p.adjs[0].name][0])
+                d_sum = torch.empty_like(agg_sum)
+                act = e._act(p.mp.aggregation.activation_function)
+                ops.dense_bwd(agg_sum, ck, act | ops.ACT_FROM_OUTPUT, agg, d_agg, d_sum,
+                              self.g(p.dst + "_convolution/conv_kernel"), None)     # d_agg becomes dZ in place
+                add_grad(p.dst, d_agg)
+                d_agg = d_sum
+            elif p.op == ops.OP_MEAN:
+                ops.scale_rows_inv_degree(d_agg, graph.csr[p.adjs[0].name][0])
+            elif p.op == ops.OP_MAX:
+                a = p.adjs[0]
+                rowptr, _, perm = graph.csr[a.name]
+                rows, idx = max_src
+                d_msg = ops.segment_max_bwd(rowptr, idx, perm, rows, agg, d_agg, int(graph.t["dst_" + a.name].numel()))
+                if has_msg[0]:
+                    pending[(p.key, 0)] = d_msg                       # input edge order
+                else:
+                    rp_t, _, perm_t = graph.csr_t[a.name]
+                    reduce_into(a.src, rp_t, perm_t, d_msg)
+                return
             for k, a in enumerate(p.adjs):
                 if has_msg[k]:       # every edge's message received d_agg of its destination
                     pending[(p.key, k)] = ops.gather_concat([d_agg], [graph.t["dst_" + a.name]],
@@ -178,21 +214,52 @@ class Trainer:
                         reduce_into(p.dst, rowptr, perm, ops.slice_cols(dx, off, w_))
                     off += w_                                     # edge_params are inputs, not variables
             elif kind == "agg_ff":
-                _, p, has_msg, msg_dim, saves = entry
-                if p.op != ops.OP_SUM:
-                    raise RuntimeError("IGNNITION: training through mean/max aggregation is not built")
+                _, p, has_msg, msg_dim, saves, agg, max_src = entry
                 g_new = gstate[p.dst]
                 if g_new is None:
                     continue
                 dx = dense_chain_bwd(saves, g_new)                # [n, msg_dim + hidden]: concat([agg, h], 1)
                 gstate[p.dst] = ops.slice_cols(dx, msg_dim, dx.shape[1] - msg_dim)
-                route_aggregate_grad(p, has_msg, ops.slice_cols(dx, 0, msg_dim))
+                route_aggregate_grad(p, has_msg, ops.slice_cols(dx, 0, msg_dim), agg, max_src)
             elif kind == "readout":
-                _, op, saves = entry
-                dy = dense_chain_bwd(saves, d_pred)
-                if len(op.input) != 1:
-                    raise RuntimeError("IGNNITION: training with a multi-input readout is not built")
-                add_grad(op.input[0], dy)
+                _, op, saves, widths = entry
+                dy = d_pred if op.type == "predict" else gstate.pop(op.output_name, None)
+                if dy is None:                          # an intermediate network nothing downstream reads
+                    continue
+                dx = dense_chain_bwd(saves, dy)
+                off = 0
+                for name, w_ in zip(op.input, widths):  # inputs were concatenated along the features
+                    add_grad(name, dx if len(widths) == 1 else ops.slice_cols(dx, off, w_))
+                    off += w_
+            elif kind == "product":                     # element-wise product (auxilary_classes.py:1072-1094)
+                _, op, a_in, b_in = entry
+                dy = gstate.pop(op.output_name, None)
+                if dy is not None:
+                    add_grad(op.input[0], ops.mul(dy, b_in))
+                    add_grad(op.input[1], ops.mul(dy, a_in))
+            elif kind == "pool":                        # per-sample pooling (auxilary_classes.py:1165-1185)
+                _, op, red, offsets, x_in, pooled = entry
+                dy = gstate.pop(op.output_name, None)
+                if dy is not None:
+                    n_rows = x_in.shape[0]
+                    if red == ops.OP_MAX:               # ties share the gradient (tf.reduce_max)
+                        ident = torch.arange(n_rows, dtype=torch.int32, device=dev)
+                        add_grad(op.input[0], ops.segment_max_bwd(offsets, ident, None, x_in, pooled, dy, n_rows))
+                    else:
+                        if red == ops.OP_MEAN:
+                            dy = ops.scale_rows_inv_degree(dy.clone(), offsets)
+                        add_grad(op.input[0], ops.segment_broadcast(offsets, dy, n_rows))
+            elif kind == "extend":                      # rows gathered by an adjacency (auxilary_classes.py:1236-1265)
+                _, op = entry
+                a = [x for x in e.adjacencies if x.name == op.adj_list][0]
+                d_src = gstate.pop(op.output_name[0], None)
+                d_dst = gstate.pop(op.output_name[1], None)
+                if d_src is not None:
+                    rp_t, _, perm_t = graph.csr_t[a.name]
+                    reduce_into(op.input[0], rp_t, perm_t, d_src)
+                if d_dst is not None:
+                    rowptr, _, perm = graph.csr[a.name]
+                    reduce_into(op.input[1], rowptr, perm, d_dst)
             elif kind == "seq_gru":
                 _, p, src_states, h_old, h_seq = entry
                 g_new = gstate[p.dst]
@@ -219,9 +286,7 @@ class Trainer:
                     rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]
                     reduce_into(a.src, rp_t, perm_t, d_steps)
             elif kind in ("agg_gru", "agg_gru_unfused"):
-                _, p, has_msg, h_old, agg = entry
-                if p.op != ops.OP_SUM:
-                    raise RuntimeError("IGNNITION: training through mean/max aggregation is not built")
+                _, p, has_msg, h_old, agg, max_src = entry
                 g_new = gstate[p.dst]
                 if g_new is None:
                     continue
@@ -249,7 +314,7 @@ class Trainer:
                                      g_new, d_agg, dh, self.g(p.dst + "_update/kernel"),
                                      self.g(p.dst + "_update/recurrent_kernel"), self.g(p.dst + "_update/bias"))
                 gstate[p.dst] = dh
-                route_aggregate_grad(p, has_msg, d_agg)
+                route_aggregate_grad(p, has_msg, d_agg, agg, max_src)
             else:
                 raise RuntimeError("IGNNITION: training through '%s' is not built" % kind)
 

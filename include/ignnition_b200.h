@@ -273,6 +273,24 @@ int ign_gru_cell_bwd(const float* x, const float* h, int64_t n, int f_in, int un
                      const float* d_out, float* dx, float* dh, float* d_kernel,
                      float* d_recurrent_kernel, float* d_bias, void* stream);
 
+/* Element-wise middle of the GENERIC GRU-cell backward (any f_in, units; the fused ign_gru_cell_bwd is built for
+ * f_in == units in {16, 32}): given zx = x K + b_in and zh = h R + b_rec ([n, 3 units], from ign_dense), overwrites
+ * zx with GX = [d_az | d_ar | d_axh], zh with GH = [d_az | d_ar | d_ahh] and writes dh_direct = d_out * z; the caller
+ * finishes with ign_dense_bwd(x, K, GX) and ign_dense_bwd(h, R, GH) (tf.gradients through GRUCell,
+ * generate_model.py:791, auxilary_classes.py:752-765). */
+int ign_gru_gates_bwd(float* zx, float* zh, const float* h, const float* d_out, int64_t n, int units,
+                      float* dh_direct, void* stream);
+/* Backward of the mean / max segment aggregations (north_star extensions): d[r, :] /= max(deg r, 1) turns dL/d(mean)
+ * into dL/d(sum); segment_max_bwd writes the per-slot message gradients of a max (ties share the gradient evenly, as
+ * TensorFlow's unsorted_segment_max does) at row perm[slot] (or slot when perm is NULL) of d_msg [E, width]. */
+int ign_scale_rows_inv_degree(float* d, const int32_t* rowptr, int64_t n, int width, void* stream);
+/* out[r, :] = rows[s, :] for every r in [rowptr[s], rowptr[s + 1]): backward of a per-sample sum / mean pooling
+ * (auxilary_classes.py:1165-1185) */
+int ign_segment_broadcast(const int32_t* rowptr, const float* rows, int64_t n_seg, int width, float* out, void* stream);
+int ign_segment_max_bwd(const int32_t* rowptr, const int32_t* idx, const int32_t* perm, const float* rows,
+                        const float* agg, const float* d_agg, int64_t num_dst, int width, float* d_msg, void* stream);
+
+
 /* backward of ign_gru_seq (BPTT over every destination's sequence).  h_seq is the saved output of
  * the forward call.  d_steps [sum len, f_in] receives the gradient w.r.t. each step's message
  * (the caller reduces it per source row with ign_segment_reduce over the transposed CSR);

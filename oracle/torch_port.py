@@ -74,14 +74,30 @@ class TorchOracle:
                 for mp in st["stage_mp"]:
                     dst = mp["destination_entity"]
                     state[dst] = self._mp(mp, dst, state, inp, w)
-        for k, op in enumerate(self.m["readout"]):
-            if op["type"] == "predict":
+        for k, op in enumerate(self.m["readout"]):                               # generate_model.py:607-656
+            if op["type"] in ("predict", "neural_network"):
                 x = torch.cat([state[i] for i in op["input"]], dim=1)
                 for l in o.layer_names(op["nn_name"], "readout"):
                     x = x @ w["readout_model_%d/%s/kernel" % (k, l["name"])] + w["readout_model_%d/%s/bias" % (k, l["name"])]
                     a = l.get("activation")
                     x = _act(None if a == "None" else a, x)
-                return x
+                if op["type"] == "predict":
+                    return x
+                state[op["output_name"]] = x
+            elif op["type"] == "pooling":                                        # auxilary_classes.py:1165-1185
+                x = state[op["input"][0]]
+                red = {"sum": lambda t: t.sum(dim=0), "mean": lambda t: t.mean(dim=0),
+                       "max": lambda t: t.amax(dim=0)}[op["type_pooling"]]
+                state[op["output_name"]] = red(x).reshape(1, -1)
+            elif op["type"] == "product":                                        # auxilary_classes.py:1072-1088
+                if op["type_product"] != "element_wise":
+                    raise ValueError("torch oracle: only the element-wise product is restated")
+                state[op["output_name"]] = state[op["input"][0]] * state[op["input"][1]]
+            elif op["type"] == "extend_adjacencies":                             # auxilary_classes.py:1236-1265
+                si = torch.as_tensor(np.asarray(inp["src_" + op["adj_list"]], dtype=np.int64))
+                di = torch.as_tensor(np.asarray(inp["dst_" + op["adj_list"]], dtype=np.int64))
+                state[op["output_name_src"]] = state[op["input"][0]][si]
+                state[op["output_name_dst"]] = state[op["input"][1]][di]
         raise ValueError("torch oracle: no predict operation")
 
     def _mp(self, mp, dst, state, inp, w):
@@ -132,6 +148,22 @@ class TorchOracle:
         K, R, b = w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"], w[dst + "_update/bias"]
         if agg == "sum":
             return gru_cell(src_input.sum(dim=1), h, K, R, b)
+        if agg == "convolution":            # Conv_aggr (auxilary_classes.py:366-401), single source
+            ck = w[dst + "_convolution/conv_kernel"]
+            deg = final_len.to(dt)[:, None]
+            pre = (src_input.sum(dim=1) @ ck + h) / deg
+            a = mp["aggregation"].get("activation_function", "relu")
+            return gru_cell(_act(None if a == "None" else a, pre), h, K, R, b)
+        if agg in ("mean", "max"):          # north-star extensions: the definitions of ignnition_oracle.py, on torch
+            valid = (torch.arange(src_input.shape[1])[None, :] < final_len[:, None])[:, :, None]
+            if agg == "mean":
+                red = src_input.sum(dim=1) / torch.clamp(final_len, min=1)[:, None].to(dt)
+            elif src_input.shape[1] == 0:
+                red = torch.zeros(num_dst, src_input.shape[2], dtype=dt)
+            else:
+                neg = torch.where(valid, src_input, torch.full_like(src_input, -float("inf")))
+                red = torch.where((final_len > 0)[:, None], neg.amax(dim=1), torch.zeros((), dtype=dt))
+            return gru_cell(red, h, K, R, b)
         if agg == "interleave":
             idx = torch.as_tensor(np.concatenate(idx_all))
             tr = src_input.transpose(0, 1)

@@ -80,12 +80,70 @@ def test_adam_step_matches_keras_formula():
 
 
 def test_training_unsupported_shapes_fail_loudly():
+    """the fused BPTT walk exists for message width == units in {16, 32}; other shapes raise (the single GRU step has a
+    generic backward: test_gru_cell_bwd_generic)"""
     from ignnition_b200 import ops
     z = torch.zeros(8, 64, device="cuda")
     w = torch.zeros(64, 192, device="cuda")
     b = torch.zeros(2, 192, device="cuda")
+    rp = torch.arange(9, dtype=torch.int32, device="cuda")
+    st = torch.zeros(8, dtype=torch.int32, device="cuda")
     with pytest.raises(RuntimeError, match="IGNNITION.*backward pass is built for"):
-        ops.gru_cell_bwd(z, z, w, w, b, z, z.clone(), z.clone(), w.clone(), w.clone(), b.clone())
+        ops.gru_seq_bwd(rp, st, None, [z], z, z.clone(), w, w, b, z, z.clone(), z.clone(), w.clone(), w.clone(), b.clone())
+
+
+@pytest.mark.parametrize("n,f_in,units", [(300, 64, 64), (1000, 32, 64), (77, 48, 16), (5000, 64, 32)])
+def test_gru_cell_bwd_generic(n, f_in, units):
+    """generic GRU-cell backward (two gate GEMMs recomputed + ign_gru_gates_bwd + two Dense backwards) vs fp64
+    autograd through the same Keras GRUCell formulas: dx, dh and the weight gradients, shapes the fused kernel does
+    not cover (config 5's 64-wide model, f_in != units)"""
+    from ignnition_b200 import ops
+    from oracle.torch_port import gru_cell as t_gru
+    rng = np.random.RandomState(n + f_in)
+    x = rng.randn(n, f_in).astype(np.float32)
+    h = rng.randn(n, units).astype(np.float32)
+    K = (rng.randn(f_in, 3 * units) / np.sqrt(f_in)).astype(np.float32)
+    R = (rng.randn(units, 3 * units) / np.sqrt(units)).astype(np.float32)
+    b = (rng.randn(2, 3 * units) * 0.1).astype(np.float32)
+    d_out = rng.randn(n, units).astype(np.float32)
+    tt = [torch.tensor(a.astype(np.float64), requires_grad=True) for a in (x, h, K, R, b)]
+    (t_gru(*tt) * torch.tensor(d_out.astype(np.float64))).sum().backward()
+    c = lambda a: torch.from_numpy(a).cuda()
+    dx, dh = torch.empty(n, f_in, device="cuda"), torch.empty(n, units, device="cuda")
+    dk, dr, db = (torch.zeros_like(c(a)) for a in (K, R, b))
+    ops.gru_cell_bwd(c(x), c(h), c(K), c(R), c(b), c(d_out), dx, dh, dk, dr, db)
+    for got, want in zip((dx, dh, dk, dr, db), tt):
+        assert rel_err(got.cpu().numpy(), want.grad.numpy()) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("agg,hidden,message_nn", [("mean", 32, False), ("max", 32, False), ("max", 32, True),
+                                                   ("mean", 32, True), ("sum", 64, False), ("max", 64, False)])
+def test_gradients_mean_max_and_wide_states(agg, hidden, message_nn):
+    """tf.gradients through the mean / max aggregations (north_star extensions: reduce_mean, and unsorted_segment_max
+    with ties sharing the gradient) and through 64-wide states (BASELINE config 5's model: fused tcgen05 update in the
+    forward, generic GRU-cell backward) vs fp64 autograd on the differentiable oracle."""
+    from test_gpu_model import _mpnn_json, _mpnn_sample, make, tensors_of
+    from ignnition_b200.generator import sample_dimensions
+    from ignnition_b200.train import Trainer
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(11 + len(agg) + hidden + int(message_nn))
+    model_json = _mpnn_json(agg, hidden, "gru", message_nn)
+    samples = [_mpnn_sample(rng, n, 6, params=message_nn) for n in (40, 1, 300)]
+    dims = sample_dimensions(samples[0])
+    md, eng, o64, w = make(model_json, dims)
+    both = [tensors_of(md, s) for s in samples]
+    tens, labels = [b[0] for b in both], [np.asarray(b[1], np.float32) for b in both]
+    tr = Trainer(eng)
+    graph = eng.prepare(tens, labels=labels, training=True)
+    pred, n_local = tr.loss_and_grads(graph)
+    for name, lam in eng._reg.items():
+        ops.l2_reg(eng.param(name), lam, tr.g(name), tr.scalars[1:2])
+    mse, reg, p_ref, grads = TorchOracle(model_json, dims).loss_and_grads(tens, labels, w)
+    assert rel_err(pred.cpu().numpy().reshape(-1), p_ref) < 1e-5
+    got = tr.grads.cpu().numpy()
+    for name, (off, shape) in eng.param_table.items():
+        gn = got[off:off + int(np.prod(shape))].reshape(shape)
+        assert rel_err(gn, grads[name]) < GRAD_RTOL_SELU_KINK, name
 
 
 @pytest.mark.parametrize("update,message_nn", [("gru", True), ("ff", False), ("ff", True)])
@@ -126,7 +184,7 @@ def test_training_unbuilt_paths_fail_loudly():
     from ignnition_b200.generator import sample_dimensions
     from ignnition_b200.train import Trainer
     rng = np.random.RandomState(3)
-    for agg, msg in (("mean", False), ("ordered", True)):
+    for agg, msg in (("attention", False), ("ordered", True)):
         model_json = _mpnn_json(agg, 32, "gru", msg)
         samples = [_mpnn_sample(rng, 30, 4, params=msg)]
         for s in samples:
@@ -258,3 +316,76 @@ def test_full_size_qsize_properties_inference_and_training():
         tol = GRAD_RTOL_SELU_KINK if name.startswith("readout_model") else GRAD_RTOL
         assert rel_err(a, b_) < tol, ("tc vs fp32", name, rel_err(a, b_))
         assert rel_err(b_, c) < tol, ("replicas vs one sample", name, rel_err(b_, c))
+
+
+def _grad_check(model_json, samples, graph_level=False):
+    from test_gpu_model import make, tensors_of
+    from ignnition_b200.generator import sample_dimensions
+    from ignnition_b200.train import Trainer
+    from ignnition_b200 import ops
+    dims = sample_dimensions(samples[0])
+    md, eng, o64, w = make(model_json, dims)
+    both = [tensors_of(md, s) for s in samples]
+    tens, labels = [b[0] for b in both], [np.asarray(b[1], np.float32) for b in both]
+    tr = Trainer(eng)
+    graph = eng.prepare(tens, labels=labels, training=True)
+    pred, n_local = tr.loss_and_grads(graph)
+    for name, lam in eng._reg.items():
+        ops.l2_reg(eng.param(name), lam, tr.g(name), tr.scalars[1:2])
+    mse, reg, p_ref, grads = TorchOracle(model_json, dims).loss_and_grads(tens, labels, w)
+    assert rel_err(pred.cpu().numpy().reshape(-1), p_ref) < 1e-5
+    sc = tr.scalars.cpu().numpy()
+    assert abs(sc[0] / n_local - mse) <= 1e-5 * abs(mse)
+    got = tr.grads.cpu().numpy()
+    for name, (off, shape) in eng.param_table.items():
+        gn = got[off:off + int(np.prod(shape))].reshape(shape)
+        assert rel_err(gn, grads[name]) < GRAD_RTOL_SELU_KINK, name
+    return eng
+
+
+def test_gradients_convolution_aggregation():
+    """tf.gradients through Conv_aggr = act((sum_j W m_j + h_d) / deg_d) (auxilary_classes.py:366-401): the kernel
+    product, the division by the degree, the activation and the destination's own state, vs fp64 autograd"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample
+    rng = np.random.RandomState(5)
+    mj = _mpnn_json("convolution", 32)
+    mj["message_passing"]["stages"][0]["stage_mp"][0]["aggregation"]["activation_function"] = "tanh"
+    samples = [_mpnn_sample(rng, n, 5) for n in (30, 200)]
+    for s in samples:                       # every destination has >= 1 neighbour (degree 0 divides by zero)
+        for v in s["entities"]:
+            s["adj"].setdefault(v, [v])
+    eng = _grad_check(mj, samples)
+    assert "node_convolution/conv_kernel" in eng.param_table
+
+
+@pytest.mark.parametrize("chain", ["pool_sum", "pool_mean", "pool_max", "edges"])
+def test_gradients_readout_operations(chain):
+    """tf.gradients through the readout operations (auxilary_classes.py:1072-1265, generate_model.py:632-656) vs
+    fp64 autograd, every variable: neural_network -> per-sample pooling -> predict (one graph-level label per sample),
+    and extend_adjacencies -> element-wise product -> neural_network on [product | e_src] -> predict (one label per
+    edge; multi-input networks, gradients reduced back to the node states over the adjacency and its transpose)"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample
+    rng = np.random.RandomState(3)
+    mj = _mpnn_json("sum", 32)
+    mj["neural_networks"].append({"nn_name": "edge_nn", "nn_type": "feed_forward", "nn_architecture": [
+        {"type_layer": "Dense", "units": 20, "activation": "tanh"}]})
+    samples = [_mpnn_sample(rng, n, 4) for n in (17, 9, 120)]
+    if chain == "edges":
+        mj["readout"] = [
+            {"type": "extend_adjacencies", "adj_list": "adj", "input": ["node", "node"],
+             "output_name_src": "e_src", "output_name_dst": "e_dst"},
+            {"type": "product", "type_product": "element_wise", "input": ["e_src", "e_dst"], "output_name": "e_prod"},
+            {"type": "neural_network", "input": ["e_prod", "e_src"], "nn_name": "edge_nn", "output_name": "edge2"},
+            {"type": "predict", "input": ["edge2"], "label": "y", "nn_name": "ro"},
+        ]
+        for s in samples:
+            s["y"] = rng.randn(sum(len(v) for v in s["adj"].values())).tolist()
+    else:
+        mj["readout"] = [
+            {"type": "neural_network", "input": ["node"], "nn_name": "edge_nn", "output_name": "node2"},
+            {"type": "pooling", "type_pooling": chain[5:], "input": ["node2"], "output_name": "graph"},
+            {"type": "predict", "input": ["graph"], "label": "y", "nn_name": "ro"},
+        ]
+        for s in samples:
+            s["y"] = [float(rng.randn())]
+    _grad_check(mj, samples)
