@@ -314,6 +314,7 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
     parity = None
     if rank == 0 and not train and parity_samples:
         from oracle import ignnition_oracle as orc          # checker only
+        eng.build_graph(graph)
         pred_t, states_t = eng.forward(graph, return_states=True)
         pred = pred_t.cpu().numpy().reshape(n_samples, -1)
         states = {e: states_t[e].cpu().numpy() for e in eng.entities}

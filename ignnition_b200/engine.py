@@ -607,7 +607,8 @@ class Engine:
         # aggregating kinds
         fused = (p.kind == "agg_gru" and p.op == ops.OP_SUM and len(p.adjs) == 1 and msgs[0] is None
                  and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1])
-                 and (self.fuse_sum_gru if self.fuse_sum_gru is not None else not ops.tensor_cores_enabled()))
+                 and (self.fuse_sum_gru if self.fuse_sum_gru is not None
+                      else (not ops.tensor_cores_enabled() or n_dst < ops.SMALL_ROWS)))   # small: 1 launch, not 3
         fused_tc = (p.kind == "agg_gru" and len(p.adjs) == 1 and msgs[0] is None and not p.conv and not p.attn
                     and not fused and n_dst > 0
                     and (self.fused_tc if self.fused_tc is not None else h.shape[1] == 64)

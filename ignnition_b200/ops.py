@@ -233,12 +233,18 @@ def gru_seq_steps(plan, meta, srcs: List[torch.Tensor], h0, kernel, rkernel, bia
     return out
 
 
-def gru_seq_proj_pays(n_steps: int, srcs, units: int, meta) -> bool:
+# fewer destination rows than one 128-row tile per SM: the update is bound by launches, not by the kernels
+SMALL_ROWS = 148 * 128
+
+
+def gru_seq_proj_pays(n_steps: int, srcs, units: int, meta, n_dst: int = 1 << 30) -> bool:
     """The hoisted-projection walk (ign_gru_seq_proj) is built for 32-wide states with a walk plan, and pays when the
     source rows are walked over at least twice on average (the projected table is 3 x the source rows)."""
     if meta is None or units != 32 or srcs[0].shape[1] != 32 or not tensor_cores_enabled():
         return False
     if os.environ.get("IGN_GRU_SEQ_PROJ", "1") == "0":
+        return False
+    if n_dst < SMALL_ROWS:           # launch-bound sizes: one kernel (the plain walk) instead of two
         return False
     return sum(int(s.shape[0]) for s in srcs) * 2 <= n_steps
 
@@ -250,7 +256,7 @@ def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rk
     if out is None:
         out = torch.empty_like(h0)
     sp = _ptr_array(srcs, torch.float32)
-    if gru_seq_proj_pays(int(steps.numel()), srcs, units, meta):
+    if gru_seq_proj_pays(int(steps.numel()), srcs, units, meta, n):
         rows = (C.c_int64 * len(srcs))(*[int(s.shape[0]) for s in srcs])
         nbytes = lib.ign_gru_seq_proj_ws_bytes(len(srcs), rows, srcs[0].shape[1], units)
         ws = _workspace(nbytes, h0.device)
