@@ -46,7 +46,15 @@ constexpr int AGG_THREADS = 512;
 constexpr int ROWS = 128;
 constexpr int A_IMG = ROWS * 128;                       // one [128 x 32] fp32 image
 constexpr int BATCH = 4;                                // gathered rows per cp.async group
+// -DIGN_AGG_PROBE_NB=n: profiling build for the gather-only mode (IGN_AGG_DBG=1): n batches per ring, the ring laid
+// over the (then unused) operand stages so that it fits (profiles/r2_agg_gru.md)
+#ifdef IGN_AGG_PROBE_NB
+constexpr int NB = IGN_AGG_PROBE_NB;
+constexpr bool PROBE = true;
+#else
 constexpr int NB = 5;                                   // batches in a sub-warp's ring: NB - 1 in flight
+constexpr bool PROBE = false;
+#endif
 constexpr int BAR_GATHER = 1, BAR_EPI = 2, BAR_HLOAD = 3;   // named barriers (0 = __syncthreads)
 
 struct OutMaps {
@@ -131,9 +139,10 @@ __global__ void __launch_bounds__(AGG_THREADS, 1) agg_gru_tc_kernel(
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* b_buf = smem + 2 * STAGE_A;             // ONE weight chunk (hi + lo): the tile time is the gather's
   unsigned char* out_stage = b_buf + 2 * B_IMG;          // NC boxes of [128 x 32] fp32, SWIZZLE_128B
-  unsigned char* ring = out_stage + NC * A_IMG;          // gathered rows in flight: NG rings of NB x BATCH rows
+  unsigned char* ring = PROBE ? smem : out_stage + NC * A_IMG;   // gathered rows in flight: NG rings of NB x BATCH rows
   // [128][U] fp32 aggregated rows of the tile being reduced: its own region at U = 32, the staging tile's at U = 64
-  float* xraw = reinterpret_cast<float*>(U == 32 ? ring + NG * (NB * BATCH * U * 4) : out_stage);
+  float* xraw = reinterpret_cast<float*>(PROBE ? smem + NG * (NB * BATCH * U * 4)
+                                               : U == 32 ? ring + NG * (NB * BATCH * U * 4) : out_stage);
   constexpr int RING_GROUP = NB * BATCH * U * 4;
   // bar_mma[c]: the UMMAs of chunk c of a tile are done (phase = tile count of the CTA).  One barrier per chunk of
   // the tile, not per stage: a stage is used twice per tile at U = 64 (x chunk, then h chunk) and its two users wait
@@ -527,8 +536,9 @@ template <int U, int OP, bool TMA_OUT>
 int launch_v(const int* rowptr, const int* col, const float* src, const float* h, int64_t n, const float* wimg,
              const float* bias, const OutMaps& maps, int n_out, int out_row0, float* agg_out, float* out_direct,
              int grid, cudaStream_t st) {
-  constexpr size_t smem = 1024 + 2 * (size_t)(2 * A_IMG) + 2 * (size_t)(3 * U * 128) + (size_t)(U / 32) * A_IMG +
-                          (size_t)(GATHER_THREADS / (U / 4)) * NB * BATCH * U * 4 + (U == 32 ? ROWS * U * 4 : 0);
+  constexpr size_t smem = PROBE ? 1024 + (size_t)(GATHER_THREADS / (U / 4)) * NB * BATCH * U * 4 + ROWS * U * 4 + 4096
+                                : 1024 + 2 * (size_t)(2 * A_IMG) + 2 * (size_t)(3 * U * 128) + (size_t)(U / 32) * A_IMG +
+                                      (size_t)(GATHER_THREADS / (U / 4)) * NB * BATCH * U * 4 + (U == 32 ? ROWS * U * 4 : 0);
   IGN_CUDA(cudaFuncSetAttribute(agg_gru_tc_kernel<U, OP, TMA_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
   agg_gru_tc_kernel<U, OP, TMA_OUT><<<grid, AGG_THREADS, smem, st>>>(rowptr, col, src, h, n, wimg, bias, maps, n_out,
