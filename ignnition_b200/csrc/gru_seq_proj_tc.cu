@@ -129,10 +129,10 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 constexpr int PJ_THREADS = 384;
 constexpr int PJ_XS = U + 1;                               // padded x row (floats)
 constexpr int PJ_OS = XP + 4;                              // padded output row (floats): 16-byte stores spread over the banks
-__global__ void __launch_bounds__(PJ_THREADS) project_kernel(const float* __restrict__ x, int64_t n,
-                                                             const float* __restrict__ kernel,
-                                                             const float* __restrict__ bias, float* __restrict__ xp,
-                                                             float scale_zr, float scale_c) {
+__global__ void __launch_bounds__(PJ_THREADS, 2) project_kernel(const float* __restrict__ x, int64_t n,
+                                                                const float* __restrict__ kernel,
+                                                                const float* __restrict__ bias, float* __restrict__ xp,
+                                                                float scale_zr, float scale_c) {
   extern __shared__ __align__(16) unsigned char pj_smem[];
   float* s_w = reinterpret_cast<float*>(pj_smem);                  // [32 k][96 n]
   float* s_x = s_w + U * XP;                                       // [128][33]
@@ -143,16 +143,33 @@ __global__ void __launch_bounds__(PJ_THREADS) project_kernel(const float* __rest
   if (tid < XP) s_b[tid] = bias[tid] + (tid < 2 * U ? bias[XP + tid] : 0.0f);
   const int gate = tid >> 7, r = tid & 127;
   const float gscale = gate < 2 ? scale_zr : scale_c;      // exponent scaling of the walk's gates (1 = none)
-  for (int64_t m0 = (int64_t)blockIdx.x * ROWS; m0 < n; m0 += (int64_t)gridDim.x * ROWS) {
-    __syncthreads();                                               // s_w / s_b ready; previous tile fully written out
-    for (int i = tid; i < ROWS * (U / 4); i += PJ_THREADS) {
+  constexpr int NPF = (ROWS * (U / 4) + PJ_THREADS - 1) / PJ_THREADS;     // 16-byte pieces of an x tile per thread
+  float4 pf[NPF];
+  // the x tile of the NEXT iteration travels in registers while this one is multiplied (two CTAs per SM cover the rest)
+  auto fetch = [&](int64_t m0) {
+#pragma unroll
+    for (int j = 0; j < NPF; ++j) {
+      const int i = tid + j * PJ_THREADS;
       const int rr = i >> 3, c4 = i & 7;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + rr < n) v = ldg_f4(x + (m0 + rr) * U + c4 * 4);
-      float* d = s_x + rr * PJ_XS + c4 * 4;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      pf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < ROWS * (U / 4) && m0 + rr < n) pf[j] = ldg_f4(x + (m0 + rr) * U + c4 * 4);
+    }
+  };
+  const int64_t stride = (int64_t)gridDim.x * ROWS;
+  int64_t m0 = (int64_t)blockIdx.x * ROWS;
+  if (m0 < n) fetch(m0);
+  for (; m0 < n; m0 += stride) {
+    __syncthreads();                                               // s_w / s_b ready; previous tile fully written out
+#pragma unroll
+    for (int j = 0; j < NPF; ++j) {
+      const int i = tid + j * PJ_THREADS;
+      if (i < ROWS * (U / 4)) {
+        float* d = s_x + (i >> 3) * PJ_XS + (i & 7) * 4;
+        d[0] = pf[j].x; d[1] = pf[j].y; d[2] = pf[j].z; d[3] = pf[j].w;
+      }
     }
     __syncthreads();
+    if (m0 + stride < n) fetch(m0 + stride);
     float acc[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) acc[j] = s_b[gate * U + j];
