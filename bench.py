@@ -465,6 +465,12 @@ def run_ours(args):
                                 hbm_peak, peak_src, scaling="strong", default_size=False,
                                 note="4096 samples split over the GPUs, no collective"),
                 "routenet_geant2_b4096/strong")
+            leg(lambda: compact(measure_case(ctx, "routenet_geant2_b4096", 4096 // world, False, args.steps, 3,
+                                             total_scale=(4096 // world) * world, graphed=True),
+                                hbm_peak, peak_src, scaling="strong", default_size=False,
+                                note="4096 samples split over the GPUs, no collective; the step replayed as one captured "
+                                     "CUDA graph (Engine.forward_graphed)"),
+                "routenet_geant2_b4096/strong/graphed")
         # config 2: Q-size RouteNet (links + paths + nodes, interleave aggregation)
         leg(lambda: compact(measure_case(ctx, "qsize_nsfnet_b4096", 4096, False, 10, 3, parity_samples=16), hbm_peak,
                             peak_src), "qsize_nsfnet_b4096")

@@ -67,6 +67,9 @@ SIGNATURES = {
                                      _p, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_dense_head_bwd_chain": (_int, [_p, _i64, _int, _p, _p, _int, _p, _p, _p, _p]),
     "ign_l2_reg": (_int, [_p, _i64, _f, _p, _p, _p]),
+    "ign_loss": (_int, [_int, _p, _p, _i64, C.c_float, C.c_float, _p, _p, _p]),
+    "ign_optimizer_step": (_int, [_int, _p, _p, _p, _p, _i64, C.c_float, C.c_float, C.c_float, C.c_float, _int, _p]),
+    "ign_gru_gates_fwd": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
     "ign_adam_step": (_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
     "ign_attention_ws_bytes": (_sz, [_i64, _i64, _int]),
     "ign_attention_aggregate": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),

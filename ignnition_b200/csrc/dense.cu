@@ -424,6 +424,108 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
   w[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// Keras losses by name (generate_model.py:745-751 resolves any tf.keras.losses class): per-element loss l_i, the mean
+// over all predictions is taken by the caller (acc = sum l_i in fp64); d_pred = dl_i/dp * grad_scale.
+__global__ void loss_kernel(int kind, const float* __restrict__ pred, const float* __restrict__ label, int64_t n,
+                            float grad_scale, float delta, float* __restrict__ d_pred, double* __restrict__ acc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (i < n) {
+    const float p = pred[i], y = label[i], e = p - y;
+    float d = 0.f;
+    constexpr float EPS = 1e-7f;                              // keras.backend.epsilon()
+    switch (kind) {
+      case IGN_LOSS_MSE: l = e * e; d = 2.f * e; break;
+      case IGN_LOSS_MAE: l = fabsf(e); d = e > 0.f ? 1.f : e < 0.f ? -1.f : 0.f; break;
+      case IGN_LOSS_MAPE: {
+        const float den = fmaxf(fabsf(y), EPS);
+        l = 100.f * fabsf(e) / den; d = (e > 0.f ? 100.f : e < 0.f ? -100.f : 0.f) / den; break;
+      }
+      case IGN_LOSS_MSLE: {
+        const float pc = fmaxf(p, EPS), yc = fmaxf(y, EPS);
+        const float q = log1pf(pc) - log1pf(yc);
+        l = q * q; d = p > EPS ? 2.f * q / (1.f + pc) : 0.f; break;
+      }
+      case IGN_LOSS_HUBER: {
+        const float a = fabsf(e);
+        if (a <= delta) { l = 0.5f * e * e; d = e; } else { l = delta * (a - 0.5f * delta); d = e > 0.f ? delta : -delta; }
+        break;
+      }
+      case IGN_LOSS_LOGCOSH: {
+        const float a = fabsf(e);                             // log cosh x = |x| + log1p(exp(-2|x|)) - log 2
+        l = a + log1pf(expf(-2.f * a)) - 0.69314718f; d = tanhf(e); break;
+      }
+      default: {                                              // IGN_LOSS_BCE on probabilities, clipped like Keras
+        const float pc = fminf(fmaxf(p, EPS), 1.f - EPS);
+        l = -(y * logf(pc + EPS) + (1.f - y) * logf(1.f - pc + EPS));
+        d = (p > EPS && p < 1.f - EPS) ? -(y / (pc + EPS) - (1.f - y) / (1.f - pc + EPS)) : 0.f; break;
+      }
+    }
+    if (d_pred) d_pred[i] = d * grad_scale;
+  }
+  double v = (double)l;                                       // block sum, one atomic per block
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    atomicAdd(acc, t);
+  }
+}
+
+// Keras optimisers by name (generate_model.py:796-818) [TF-2.1 fused-op semantics]; s1 / s2 are the slot buffers
+__global__ void optimizer_kernel(int kind, float* __restrict__ w, const float* __restrict__ g, float* __restrict__ s1,
+                                 float* __restrict__ s2, int64_t n, float lr, float a, float b, float eps, int flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  switch (kind) {
+    case IGN_OPT_SGD:                                         // a = momentum, flags & 1 = nesterov
+      if (a == 0.f) { w[i] -= lr * gi; break; }
+      { const float v = a * s1[i] - lr * gi; s1[i] = v; w[i] += (flags & 1) ? a * v - lr * gi : v; }
+      break;
+    case IGN_OPT_RMSPROP: {                                   // a = rho, b = momentum (ResourceApplyRMSProp)
+      const float ms = a * s1[i] + (1.f - a) * gi * gi;
+      s1[i] = ms;
+      const float mom = b * s2[i] + lr * gi * rsqrtf(ms + eps);
+      s2[i] = mom;
+      w[i] -= mom;
+      break;
+    }
+    case IGN_OPT_ADAGRAD: {                                   // s1 = accumulator (caller initialises it, Keras: 0.1)
+      const float acc = s1[i] + gi * gi;
+      s1[i] = acc;
+      w[i] -= lr * gi / (sqrtf(acc) + eps);
+      break;
+    }
+    default: {                                                // IGN_OPT_ADAMAX: a = beta1, b = beta2, lr = lr / (1 - beta1^t)
+      const float m = a * s1[i] + (1.f - a) * gi;
+      const float u = fmaxf(b * s2[i], fabsf(gi));
+      s1[i] = m; s2[i] = u;
+      w[i] -= lr * m / (u + eps);
+      break;
+    }
+  }
+}
+
+// generic GRU step (any f_in, units) from zx = x K + b_in and zh = h R + b_rec: the element-wise end of ign_dense x 2
+__global__ void gru_gates_fwd_kernel(const float* __restrict__ zx, const float* __restrict__ zh,
+                                     const float* __restrict__ h, int64_t n, int U, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * U) return;
+  const int64_t r = i / U;
+  const int u = (int)(i - r * U);
+  const float* px = zx + r * 3 * U + u;
+  const float* ph = zh + r * 3 * U + u;
+  const float z = 1.f / (1.f + expf(-(px[0] + ph[0])));
+  const float rr = 1.f / (1.f + expf(-(px[U] + ph[U])));
+  const float hh = tanhf(fmaf(rr, ph[2 * U], px[2 * U]));
+  out[i] = fmaf(z, h[i] - hh, hh);
+}
+
 }  // namespace
 
 bool ign_tensor_cores_enabled();
@@ -599,6 +701,38 @@ extern "C" int ign_mse_loss(const float* pred, const float* label, int64_t n, fl
   IGN_REQUIRE(pred && label && sse, IGN_ERR_INVALID, "IGNNITION: mse_loss: null pointer");
   mse_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(pred, label, n, grad_scale, d_pred, sse);
   IGN_CHECK_LAUNCH("mse_loss");
+  return IGN_OK;
+}
+
+extern "C" int ign_loss(int kind, const float* pred, const float* label, int64_t n, float grad_scale, float delta,
+                        float* d_pred, double* acc, void* stream) {
+  IGN_REQUIRE(kind >= IGN_LOSS_MSE && kind <= IGN_LOSS_BCE, IGN_ERR_INVALID, "IGNNITION: loss: unknown loss %d", kind);
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: loss: negative size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(pred && label && acc, IGN_ERR_INVALID, "IGNNITION: loss: null pointer");
+  loss_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(kind, pred, label, n, grad_scale, delta, d_pred, acc);
+  IGN_CHECK_LAUNCH("loss");
+  return IGN_OK;
+}
+
+extern "C" int ign_optimizer_step(int kind, float* w, const float* g, float* s1, float* s2, int64_t n, float lr, float a,
+                                  float b, float eps, int flags, void* stream) {
+  IGN_REQUIRE(kind >= IGN_OPT_SGD && kind <= IGN_OPT_ADAMAX, IGN_ERR_INVALID, "IGNNITION: optimizer_step: unknown optimiser %d", kind);
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: optimizer_step: negative size");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(w && g && s1 && s2, IGN_ERR_INVALID, "IGNNITION: optimizer_step: null pointer");
+  optimizer_kernel<<<(unsigned)ign_cdiv(n, 256), 256, 0, ign_stream(stream)>>>(kind, w, g, s1, s2, n, lr, a, b, eps, flags);
+  IGN_CHECK_LAUNCH("optimizer_step");
+  return IGN_OK;
+}
+
+extern "C" int ign_gru_gates_fwd(const float* zx, const float* zh, const float* h, int64_t n, int units, float* out,
+                                 void* stream) {
+  IGN_REQUIRE(n >= 0 && units > 0, IGN_ERR_INVALID, "IGNNITION: gru_gates_fwd: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(zx && zh && h && out, IGN_ERR_INVALID, "IGNNITION: gru_gates_fwd: null pointer");
+  gru_gates_fwd_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh, h, n, units, out);
+  IGN_CHECK_LAUNCH("gru_gates_fwd");
   return IGN_OK;
 }
 

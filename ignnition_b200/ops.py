@@ -142,12 +142,22 @@ def segment_reduce(op: int, rowptr, col, src_states, out: Optional[torch.Tensor]
     return out
 
 
+GRU_FUSED_SHAPES = {(16, 16), (32, 32), (64, 64), (16, 32), (64, 32), (32, 64), (32, 16)}     # IGN_GRU_DISPATCH
+
+
 def gru_cell(x, h, kernel, rkernel, bias, out: Optional[torch.Tensor] = None, tensor_cores: bool = True):
-    """One GRU step.  3xTF32 on tcgen05 when built for the shape (and out is not h), else fp32 FMA."""
+    """One GRU step.  3xTF32 on tcgen05 when built for the shape (and out is not h), else fp32 FMA; shapes the
+    fused kernels do not cover (hidden_state_dimension is free in the reference's schema) run as two Dense GEMMs and
+    one element-wise kernel."""
     lib = _lib.load()
     n, units = h.shape
     if out is None:
         out = torch.empty_like(h)
+    if (int(x.shape[1]), int(units)) not in GRU_FUSED_SHAPES:
+        zx = dense(x, kernel, bias[0], 0)
+        zh = dense(h, rkernel, bias[1], 0)
+        _lib.check(lib.ign_gru_gates_fwd(_f(zx), _f(zh), _f(h), n, units, _f(out), _stream()), "gru_gates_fwd")
+        return out
     ws, nbytes = None, 0
     if tensor_cores and out.data_ptr() != h.data_ptr():
         nbytes = lib.ign_gru_cell_ws_bytes(x.shape[1], units)
@@ -373,6 +383,24 @@ def mse_loss(pred, label, grad_scale: float, d_pred, sse):
     lib = _lib.load()
     _lib.check(lib.ign_mse_loss(_f(pred), _f(label), pred.numel(), grad_scale, _f(d_pred),
                                 _ptr(sse, torch.float64, "sse"), _stream()), "mse_loss")
+
+
+LOSSES = {"MeanSquaredError": 0, "MeanAbsoluteError": 1, "MeanAbsolutePercentageError": 2,
+          "MeanSquaredLogarithmicError": 3, "Huber": 4, "LogCosh": 5, "BinaryCrossentropy": 6}
+OPTIMIZERS = {"SGD": 1, "RMSprop": 2, "Adagrad": 3, "Adamax": 4}
+
+
+def loss(kind: int, pred, label, grad_scale: float, d_pred, acc, delta: float = 1.0):
+    """acc += sum of the per-prediction losses (fp64); d_pred = dl/dpred * grad_scale (ign_loss)."""
+    lib = _lib.load()
+    _lib.check(lib.ign_loss(kind, _f(pred), _f(label), pred.numel(), grad_scale, delta, _f(d_pred),
+                            _ptr(acc, torch.float64, "acc"), _stream()), "loss")
+
+
+def optimizer_step(kind: int, w, g, s1, s2, lr: float, a: float, b: float, eps: float, flags: int = 0):
+    lib = _lib.load()
+    _lib.check(lib.ign_optimizer_step(kind, _f(w), _f(g), _f(s1), _f(s2), w.numel(), lr, a, b, eps, flags, _stream()),
+               "optimizer_step")
 
 
 def dense_bwd(x, w, act: int, pre_act, dy, dx, dw, db):

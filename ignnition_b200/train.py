@@ -31,13 +31,22 @@ class LearningRate:
         self.schedule = optimizer.get("schedule")
         if self.schedule is not None:
             t = self.schedule.get("type")
-            if t not in ("ExponentialDecay", "InverseTimeDecay"):
+            if t not in ("ExponentialDecay", "InverseTimeDecay", "PolynomialDecay", "PiecewiseConstantDecay"):
                 raise RuntimeError("IGNNITION: learning-rate schedule %s is not built" % t)
 
     def __call__(self, step: int) -> float:
         s = self.schedule
         if s is None:
             return self.const
+        if s["type"] == "PiecewiseConstantDecay":
+            k = sum(1 for b in s["boundaries"] if step > float(b))       # values[i] while step <= boundaries[i]
+            return float(s["values"][k])
+        if s["type"] == "PolynomialDecay":
+            lr0, ds = float(s["initial_learning_rate"]), float(s["decay_steps"])
+            end, power = float(s.get("end_learning_rate", 0.0001)), float(s.get("power", 1.0))
+            if s.get("cycle"):
+                ds = ds * max(1.0, math.ceil(step / ds))
+            return (lr0 - end) * (1.0 - min(step, ds) / ds) ** power + end
         lr0, ds, dr = float(s["initial_learning_rate"]), float(s["decay_steps"]), float(s["decay_rate"])
         p = step / ds
         if s.get("staircase"):            # any truthy value, e.g. the string "True" of the Q-size example
@@ -56,11 +65,18 @@ class Trainer:
         self.pg = process_group
         opt = engine.model.get_optimizer()
         kind = opt.get("type", "Adam")
-        if kind != "Adam":
-            raise RuntimeError("IGNNITION: optimizer %s is not built in the B200 engine (Adam only)" % kind)
-        if engine.model.get_loss() != "MeanSquaredError":
-            raise RuntimeError("IGNNITION: loss %s is not built in the B200 engine (MeanSquaredError only)"
-                               % engine.model.get_loss())
+        if kind != "Adam" and kind not in ops.OPTIMIZERS:
+            raise RuntimeError("IGNNITION: optimizer %s is not built in the B200 engine (one of Adam, %s)"
+                               % (kind, ", ".join(sorted(ops.OPTIMIZERS))))
+        loss_name = engine.model.get_loss()
+        if loss_name not in ops.LOSSES:
+            raise RuntimeError("IGNNITION: loss %s is not built in the B200 engine (one of %s)"
+                               % (loss_name, ", ".join(sorted(ops.LOSSES))))
+        self.opt_kind = kind
+        self.opt = opt
+        self.loss_kind = ops.LOSSES[loss_name]
+        self.huber_delta = float(engine.model.get_loss_options().get("delta", 1.0)) \
+            if hasattr(engine.model, "get_loss_options") else 1.0
         self.beta1 = float(opt.get("beta_1", 0.9))
         self.beta2 = float(opt.get("beta_2", 0.999))
         self.eps = float(opt.get("epsilon", 1e-7))
@@ -70,8 +86,10 @@ class Trainer:
         self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.scalars = torch.zeros(4, dtype=torch.float64, device=dev)    # [sse, reg, n_pred, unused]
+        self.scalars = torch.zeros(4, dtype=torch.float64, device=dev)    # [sum of losses, reg, n_pred, unused]
         self.step = 0
+        if kind == "Adagrad":                       # Keras: initial_accumulator_value = 0.1
+            self.m.fill_(float(opt.get("initial_accumulator_value", 0.1)))
 
     def g(self, name: str) -> torch.Tensor:
         return self.e._pview(self.grads, name)
@@ -332,7 +350,11 @@ class Trainer:
         n_local = pred.numel()
         n_glob = global_n if global_n is not None else n_local * self.world
         d_pred = torch.empty_like(pred)
-        ops.mse_loss(pred, graph.t["labels"], 1.0 / float(n_glob), d_pred, self.scalars[0:1])
+        if self.loss_kind == 0:
+            ops.mse_loss(pred, graph.t["labels"], 1.0 / float(n_glob), d_pred, self.scalars[0:1])
+        else:                                       # any other Keras loss by name: mean over all predictions (:745-751)
+            ops.loss(self.loss_kind, pred, graph.t["labels"], 1.0 / float(n_glob), d_pred, self.scalars[0:1],
+                     self.huber_delta)
         self.backward(graph, tape, d_pred)
         return pred, n_local
 
@@ -345,8 +367,21 @@ class Trainer:
         for name, lam in e._reg.items():                            # added once, identical on every rank
             ops.l2_reg(e.param(name), lam, self.g(name), self.scalars[1:2])
         self.step += 1
-        ops.adam_step(e.weights, self.grads, self.m, self.v, self.lr(self.step - 1), self.beta1, self.beta2,
-                      self.eps, self.step)
+        lr = self.lr(self.step - 1)
+        o = self.opt
+        if self.opt_kind == "Adam":
+            ops.adam_step(e.weights, self.grads, self.m, self.v, lr, self.beta1, self.beta2, self.eps, self.step)
+        elif self.opt_kind == "SGD":
+            ops.optimizer_step(ops.OPTIMIZERS["SGD"], e.weights, self.grads, self.m, self.v, lr,
+                               float(o.get("momentum", 0.0)), 0.0, 0.0, 1 if o.get("nesterov") in (True, "True") else 0)
+        elif self.opt_kind == "RMSprop":
+            ops.optimizer_step(ops.OPTIMIZERS["RMSprop"], e.weights, self.grads, self.m, self.v, lr,
+                               float(o.get("rho", 0.9)), float(o.get("momentum", 0.0)), self.eps)
+        elif self.opt_kind == "Adagrad":
+            ops.optimizer_step(ops.OPTIMIZERS["Adagrad"], e.weights, self.grads, self.m, self.v, lr, 0.0, 0.0, self.eps)
+        else:                                       # Adamax
+            ops.optimizer_step(ops.OPTIMIZERS["Adamax"], e.weights, self.grads, self.m, self.v,
+                               lr / (1.0 - self.beta1 ** self.step), self.beta1, self.beta2, self.eps)
 
     def train_step(self, graph, global_n: Optional[int] = None):
         """One optimiser step on a prepared batch.  Returns (loss, regularisation) as device scalars

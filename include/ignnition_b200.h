@@ -327,6 +327,31 @@ int ign_dense_head_bwd_chain(const float* x, int64_t m, int k, const float* w, c
 /* l2 regulariser: reg[0] += lambda * sum(w^2) (fp64), dw += 2 lambda w (auxilary_classes.py:834). */
 int ign_l2_reg(const float* w, int64_t n, float lambda, float* dw, double* reg, void* stream);
 
+/* Keras losses by name (generate_model.py:745-751 takes any tf.keras.losses class): acc += sum_i l_i (fp64, caller
+ * zeroes; the caller divides by the global count), d_pred = dl_i/dp * grad_scale (nullable).  delta: Huber only. */
+#define IGN_LOSS_MSE 0      /* MeanSquaredError */
+#define IGN_LOSS_MAE 1      /* MeanAbsoluteError */
+#define IGN_LOSS_MAPE 2     /* MeanAbsolutePercentageError */
+#define IGN_LOSS_MSLE 3     /* MeanSquaredLogarithmicError */
+#define IGN_LOSS_HUBER 4    /* Huber(delta) */
+#define IGN_LOSS_LOGCOSH 5  /* LogCosh */
+#define IGN_LOSS_BCE 6      /* BinaryCrossentropy on probabilities */
+int ign_loss(int kind, const float* pred, const float* label, int64_t n, float grad_scale, float delta,
+             float* d_pred, double* acc, void* stream);
+/* Keras optimisers other than Adam (generate_model.py:796-818), TF-2.1 fused-op formulas on the flat buffers; s1 / s2
+ * are the slot buffers (SGD: momentum | -; RMSprop: rms | momentum; Adagrad: accumulator | -; Adamax: m | u).
+ * a, b: SGD momentum, -; RMSprop rho, momentum; Adamax beta1, beta2 (lr already divided by 1 - beta1^t).
+ * flags & 1: Nesterov momentum (SGD). */
+#define IGN_OPT_SGD 1
+#define IGN_OPT_RMSPROP 2
+#define IGN_OPT_ADAGRAD 3
+#define IGN_OPT_ADAMAX 4
+int ign_optimizer_step(int kind, float* w, const float* g, float* s1, float* s2, int64_t n, float lr, float a,
+                       float b, float eps, int flags, void* stream);
+/* Element-wise end of the GENERIC GRU step (any f_in, units): out = GRU gates of zx = x K + b_in, zh = h R + b_rec
+ * (two ign_dense calls) and the old state h (auxilary_classes.py:752-765 for widths the fused kernels do not cover) */
+int ign_gru_gates_fwd(const float* zx, const float* zh, const float* h, int64_t n, int units, float* out, void* stream);
+
 /* Keras Adam step on a flat parameter buffer (generate_model.py:796-818) [TF-2.1 semantics]:
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v moments; w -= lr_t*m/(sqrt(v)+eps).  step is 1-based. */
 int ign_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

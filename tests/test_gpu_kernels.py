@@ -187,13 +187,23 @@ def test_gru_cell(fi, u, n):
         assert rel_err(got, want) < RTOL, tc
 
 
-def test_gru_unsupported_width_fails_loudly():
+@pytest.mark.parametrize("n,fi,u", [(4, 48, 48), (700, 20, 100), (5000, 128, 24)])
+def test_gru_cell_generic_width(n, fi, u):
+    """widths the fused kernels do not cover (hidden_state_dimension is free in the reference's schema) run as two
+    Dense GEMMs + ign_gru_gates_fwd; the ordered WALK stays limited and says so"""
     from ignnition_b200 import ops
-    z = torch.zeros(4, 48, device="cuda")
-    w = torch.zeros(48, 144, device="cuda")
-    b = torch.zeros(2, 144, device="cuda")
+    rng = np.random.RandomState(n + u)
+    x = rng.randn(n, fi).astype(np.float32)
+    h = rng.randn(n, u).astype(np.float32)
+    K, R, b = gru_weights(rng, fi, u)
+    want = orc.gru_cell(x.astype(np.float64), h.astype(np.float64), K.astype(np.float64), R.astype(np.float64),
+                        b.astype(np.float64))
+    got = ops.gru_cell(dev(x), dev(h), dev(K), dev(R), dev(b)).cpu().numpy()
+    assert rel_err(got, want) < RTOL
+    rp = torch.arange(n + 1, dtype=torch.int32, device="cuda")
+    st = torch.zeros(n, dtype=torch.int32, device="cuda")
     with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
-        ops.gru_cell(z, z, w, w, b)
+        ops.gru_seq(rp, st, None, [dev(x)], dev(h), dev(K), dev(R), dev(b))
 
 
 @pytest.mark.parametrize("fi,u", [(32, 32), (64, 64), (16, 32)])

@@ -389,3 +389,97 @@ def test_gradients_readout_operations(chain):
         for s in samples:
             s["y"] = [float(rng.randn())]
     _grad_check(mj, samples)
+
+
+@pytest.mark.parametrize("name", ["MeanSquaredError", "MeanAbsoluteError", "MeanAbsolutePercentageError",
+                                  "MeanSquaredLogarithmicError", "Huber", "LogCosh", "BinaryCrossentropy"])
+def test_losses_by_name(name):
+    """tf.keras.losses by name (generate_model.py:745-751): the value against the Keras formula in NumPy fp64 and the
+    gradient against central differences of that formula"""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(len(name))
+    n = 5000
+    y = rng.rand(n) * 2 + 0.1
+    p = y + rng.randn(n) * 0.7
+    if name == "BinaryCrossentropy":
+        y = (rng.rand(n) < 0.4).astype(np.float64)
+        p = np.clip(rng.rand(n), 0.02, 0.98)
+    if name == "MeanSquaredLogarithmicError":
+        p = np.abs(p) + 0.05
+    eps = 1e-7
+
+    def f(p_):
+        e = p_ - y
+        return {"MeanSquaredError": e * e, "MeanAbsoluteError": np.abs(e),
+                "MeanAbsolutePercentageError": 100 * np.abs(e) / np.maximum(np.abs(y), eps),
+                "MeanSquaredLogarithmicError": (np.log1p(np.maximum(p_, eps)) - np.log1p(np.maximum(y, eps))) ** 2,
+                "Huber": np.where(np.abs(e) <= 1.0, 0.5 * e * e, np.abs(e) - 0.5),
+                "LogCosh": np.log(np.cosh(e)),
+                "BinaryCrossentropy": -(y * np.log(np.clip(p_, eps, 1 - eps) + eps)
+                                        + (1 - y) * np.log(1 - np.clip(p_, eps, 1 - eps) + eps))}[name]
+
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d = torch.empty(n, device="cuda")
+    pt, yt = torch.tensor(p, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    ops.loss(ops.LOSSES[name], pt, yt, 1.0 / n, d, acc)
+    p32, y = pt.cpu().numpy().astype(np.float64), yt.cpu().numpy().astype(np.float64)
+    assert abs(float(acc.item()) / n - f(p32).mean()) <= 2e-6 * abs(f(p32).mean())
+    h = 1e-5
+    num = (f(p32 + h) - f(p32 - h)) / (2 * h) / n
+    keep = np.abs(p32 - y) > 1e-3                     # away from the kinks of |e|
+    assert rel_err(d.cpu().numpy()[keep], num[keep]) < 2e-4
+
+
+@pytest.mark.parametrize("opt", [{"type": "SGD", "learning_rate": 0.05},
+                                 {"type": "SGD", "learning_rate": 0.05, "momentum": 0.9, "nesterov": True},
+                                 {"type": "RMSprop", "learning_rate": 0.01, "momentum": 0.5},
+                                 {"type": "Adagrad", "learning_rate": 0.1},
+                                 {"type": "Adamax", "learning_rate": 0.02}])
+def test_optimizers_by_name(opt):
+    """tf.keras.optimizers by name (generate_model.py:796-818): three steps of the Trainer's update on a fixed
+    gradient sequence against the TF-2.1 formulas in NumPy fp64"""
+    from test_gpu_model import _mpnn_json, make
+    from ignnition_b200.train import Trainer
+    mj = _mpnn_json("sum", 32)
+    mj["learning_options"]["optimizer"] = dict(opt)
+    md, eng, o64, w = make(mj, {"x": 3, "adj": 0})
+    tr = Trainer(eng)
+    rng = np.random.RandomState(1)
+    w0 = eng.weights.cpu().numpy().astype(np.float64)
+    n = w0.size
+    s1 = np.full(n, 0.1) if opt["type"] == "Adagrad" else np.zeros(n)
+    s2 = np.zeros(n)
+    lr, eps = opt["learning_rate"], 1e-7
+    for t in range(1, 4):
+        g = rng.randn(n) * 0.1
+        tr.grads.copy_(torch.tensor(g, dtype=torch.float32))
+        g = tr.grads.cpu().numpy().astype(np.float64)
+        tr.apply()
+        if opt["type"] == "SGD":
+            m = opt.get("momentum", 0.0)
+            if m == 0:
+                w0 -= lr * g
+            else:
+                s1 = m * s1 - lr * g
+                w0 += m * s1 - lr * g if opt.get("nesterov") else s1
+        elif opt["type"] == "RMSprop":
+            s1 = 0.9 * s1 + 0.1 * g * g
+            s2 = opt["momentum"] * s2 + lr * g / np.sqrt(s1 + eps)
+            w0 -= s2
+        elif opt["type"] == "Adagrad":
+            s1 += g * g
+            w0 -= lr * g / (np.sqrt(s1) + eps)
+        else:
+            s1 = 0.9 * s1 + 0.1 * g
+            s2 = np.maximum(0.999 * s2, np.abs(g))
+            w0 -= lr / (1 - 0.9 ** t) * s1 / (s2 + eps)
+    assert rel_err(eng.weights.cpu().numpy(), w0) < 2e-6
+
+
+def test_generic_width_trains():
+    """hidden_state_dimension is free in the reference's schema: a 48-wide model runs (two Dense GEMMs + the
+    element-wise GRU gates) and trains (generic GRU-cell backward) with parity against the oracles"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample
+    rng = np.random.RandomState(48)
+    samples = [_mpnn_sample(rng, n, 5) for n in (25, 140)]
+    _grad_check(_mpnn_json("sum", 48), samples)

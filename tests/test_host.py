@@ -594,3 +594,23 @@ def test_partition_bounds_and_split_counts():
             sizes = [b[r + 1] - b[r] for r in range(world)]
             assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
     assert split_counts([0, 3, 3, 10]) == [3, 0, 7]
+
+
+def test_learning_rate_schedules_by_name():
+    """tf.keras.optimizers.schedules by name (generate_model.py:802-809), TF-2.1 formulas"""
+    from ignnition_b200.train import LearningRate
+    lr = LearningRate({"learning_rate": 0.01})
+    assert lr(0) == lr(1000) == 0.01
+    e = LearningRate({"schedule": {"type": "ExponentialDecay", "initial_learning_rate": 0.001, "decay_steps": 100,
+                                   "decay_rate": 0.5, "staircase": "True"}})
+    assert e(99) == 0.001 and abs(e(250) - 0.00025) < 1e-12
+    p = LearningRate({"schedule": {"type": "PolynomialDecay", "initial_learning_rate": 0.1, "decay_steps": 100,
+                                   "end_learning_rate": 0.01, "power": 2.0}})
+    assert abs(p(0) - 0.1) < 1e-12 and abs(p(50) - (0.09 * 0.25 + 0.01)) < 1e-12 and abs(p(500) - 0.01) < 1e-12
+    c = LearningRate({"schedule": {"type": "PiecewiseConstantDecay", "boundaries": [10, 20], "values": [1.0, 0.5, 0.1]}})
+    assert (c(10), c(11), c(20), c(21)) == (1.0, 0.5, 0.5, 0.1)
+    i = LearningRate({"schedule": {"type": "InverseTimeDecay", "initial_learning_rate": 0.1, "decay_steps": 10,
+                                   "decay_rate": 1.0}})
+    assert abs(i(10) - 0.05) < 1e-12
+    with pytest.raises(RuntimeError, match="not built"):
+        LearningRate({"schedule": {"type": "CosineDecay"}})
