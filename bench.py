@@ -371,6 +371,54 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
     return out
 
 
+def run_ingest_leg(ctx, n_per_file=256, files=8):
+    """data.json TEXT -> predictions: the C++ ingest parses `files` dataset files of `n_per_file` GEANT2-shaped samples
+    on host threads while the GPU runs the batches that are ready (upload + adjacency build + forward + D2H per file).
+    Wall clock, rank 0's GPU; the text is built once outside the timed region."""
+    import time as _t
+    from concurrent.futures import ThreadPoolExecutor
+    torch, dev = ctx["torch"], ctx["dev"]
+    from ignnition_b200 import Engine, ModelDescription, synthetic
+    from ignnition_b200.generator import sample_dimensions
+    from ignnition_b200.ingest import NativeIngest
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "routenet_geant2.json")))
+    samples = [synthetic.routenet_sample("geant2", s % 16, s) for s in range(n_per_file)]
+    md = ModelDescription(g["model_json"], sample_dimensions(samples[0]))
+    eng = Engine(md, device=dev, seed=0)
+    text = json.dumps(samples).encode()
+    workers = max(1, min(files, (os.cpu_count() or 1)))
+
+    def parse(_):
+        ing = NativeIngest(eng, None)
+        ing.parse(text)
+        return ing.batch()
+
+    def run():
+        n = 0
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            for b in pool.map(parse, range(files)):
+                pred = eng.forward(eng.build_graph(eng.upload(b)))
+                n += int(pred.numel())
+                host = pred.cpu()
+        torch.cuda.synchronize()
+        return n
+
+    run()
+    t0 = _t.perf_counter()
+    n_pred = run()
+    dt = _t.perf_counter() - t0
+    t1 = _t.perf_counter()
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(parse, range(files)))
+    dt_parse = _t.perf_counter() - t1
+    total = n_per_file * files
+    return {"workload": "ingest_text_to_predictions_geant2", "mode": "data.json text -> C++ ingest -> upload -> forward -> host",
+            "samples": total, "json_mb": round(len(text) * files / 1e6, 1), "host_threads": workers,
+            "host_cores": os.cpu_count(), "value": total / dt, "unit": "samples/s", "predictions": n_pred,
+            "parse_only_samples_per_s": total / dt_parse,
+            "note": "host-bound: the GPU forward of the same samples runs at the default line's rate"}
+
+
 def load_json(path, default):
     try:
         return json.load(open(os.path.join(ROOT, path)))
@@ -452,6 +500,8 @@ def run_ours(args):
         if world > 1:      # SURVEY 8d variant C: 90 % of the edges stay inside the owner's rows, boundary rows only
             leg(lambda: run_mpnn(args.mpnn_nodes, args.mpnn_edges, 64, 5, 3, torch, dev, "local", rank, world,
                                  "boundary"), "mpnn_local")
+        if rank == 0:      # from dataset text to predictions, host ingest + GPU
+            leg(lambda: run_ingest_leg(ctx), "ingest_text_to_predictions")
         # config 4: RouteNet synth50 training, gradient all-reduce inside the step (weak scaling: 256 samples per GPU)
         leg(lambda: compact(measure_case(ctx, "routenet_synth50_b256", 256, True, 10, 3), hbm_peak, peak_src),
             "routenet_synth50_b256/train")

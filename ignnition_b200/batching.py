@@ -50,6 +50,63 @@ class Batch:
         self.max_seq: Dict[str, int] = {}     # adjacency -> longest per-destination list (max(seq) + 1)
         self.dst_sorted: Dict[str, bool] = {}  # adjacency -> the edge list arrives in destination order
 
+    # ---- a window of samples of a larger batch (a dataset file parsed in one go, cut into training batches)
+    def take(self, lo: int, hi: int, adjacencies: Sequence["AdjacencySpec"], label_entity: Optional[str] = None) -> "Batch":
+        """Samples [lo, hi) as a batch of their own: the same arrays ``assemble`` gives for those samples.  Edges,
+        position tables and labels of a sample are contiguous in every array (samples are concatenated in order), so
+        a window is a set of array slices with the row offsets of the first sample subtracted.  ``label_entity``: the
+        entity whose rows carry the labels (one label per row)."""
+        b = Batch()
+        b.n_samples = hi - lo
+        for e, off in self.offsets.items():
+            r0, r1 = int(off[lo]), int(off[hi])
+            b.offsets[e] = off[lo:hi + 1] - off[lo]
+            b.num[e] = r1 - r0
+            b.arrays["sample_of_" + e] = self.arrays["sample_of_" + e][r0:r1] - np.int32(lo)
+            b.arrays["offsets_" + e] = _as_i32(b.offsets[e])
+        if not hasattr(self, "_edge_bounds"):
+            self._edge_bounds = {}
+        for a in adjacencies:
+            if a.name not in self._edge_bounds:         # edges per sample, found once per file
+                es = self.arrays["sample_of_" + a.dst][self.arrays["dst_" + a.name]] if self.n_edges.get(a.name, 0) \
+                    else np.zeros(0, np.int32)
+                self._edge_bounds[a.name] = np.searchsorted(es, np.arange(self.n_samples + 1))
+            eb = self._edge_bounds[a.name]
+            e0, e1 = int(eb[lo]), int(eb[hi])
+            b.arrays["src_" + a.name] = self.arrays["src_" + a.name][e0:e1] - np.int32(self.offsets[a.src][lo])
+            b.arrays["dst_" + a.name] = self.arrays["dst_" + a.name][e0:e1] - np.int32(self.offsets[a.dst][lo])
+            b.arrays["seq_" + a.name] = seq = self.arrays["seq_" + a.name][e0:e1]
+            b.n_edges[a.name] = e1 - e0
+            b.max_seq[a.name] = int(seq.max()) + 1 if e1 > e0 else 0
+            if "params_" + a.name in self.arrays:
+                b.arrays["params_" + a.name] = self.arrays["params_" + a.name][e0:e1]
+            if a.name in self.dst_sorted:
+                b.dst_sorted[a.name] = self.dst_sorted[a.name]
+        for k, arr in self.arrays.items():
+            if k.startswith("pos_off_"):
+                key = k[len("pos_off_"):]
+                p0, p1 = int(arr[lo]), int(arr[hi])
+                b.arrays[k] = arr[lo:hi + 1] - arr[lo]
+                b.arrays["pos_src_" + key] = self.arrays["pos_src_" + key][p0:p1]
+                b.arrays["pos_col_" + key] = self.arrays["pos_col_" + key][p0:p1]
+        return b
+
+    def take_rows(self, b: "Batch", lo: int, hi: int, features: Sequence[Tuple[str, str, int]],
+                  label_entity: Optional[str] = None) -> "Batch":
+        """fills the per-row arrays (features, labels) of a window made by ``take``"""
+        for name, ent, size in features:
+            off = self.offsets[ent]
+            b.arrays["feat_" + name] = self.arrays["feat_" + name][int(off[lo]) * size:int(off[hi]) * size]
+        if "labels" in self.arrays:
+            if label_entity is None:
+                raise RuntimeError("IGNNITION: a window of a labelled batch needs the entity that carries the labels")
+            off = self.offsets[label_entity]
+            if self.arrays["labels"].size != int(off[-1]):
+                raise RuntimeError("IGNNITION: %d labels for %d rows of %s: windows need one label per row"
+                                   % (self.arrays["labels"].size, int(off[-1]), label_entity))
+            b.arrays["labels"] = self.arrays["labels"][int(off[lo]):int(off[hi])]
+        return b
+
     # ---- packing: one contiguous buffer, 256-byte aligned slices
     def pack(self, pin: bool = False, skip=()):
         """One contiguous host buffer (pinned when asked) + layout; arrays whose name starts with a

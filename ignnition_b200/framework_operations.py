@@ -17,6 +17,7 @@ import glob
 import itertools
 import os
 import sys
+import tarfile
 import time
 from typing import Callable, Dict, Iterator, List, Optional
 
@@ -134,6 +135,71 @@ def native_batches(model: ModelDescription, engine, directory: str, training: bo
         label_fn = lambda v, fn=fn: fn(v, out_name)
     return NativeIngest.batches_parallel(engine, directory, workers, out_name if training else None,
                                          feature_fns=fns, label_fn=label_fn)
+
+
+def native_train_batches(model: ModelDescription, engine, directory: str, batch_size: int,
+                         namespace: Optional[dict] = None, rank: int = 0, world: int = 1, shuffle: bool = False,
+                         seed: int = 0) -> Iterator:
+    """Endless stream of labelled training batches of ``batch_size`` samples through the C++ ingest: every
+    ``*.tar.gz`` is parsed ONCE into one big batch (a background thread parses the next file while this one is
+    consumed) and cut into windows with ``Batch.take``.  Data-parallel runs shard the FILES: rank r reads files
+    r, r + world, ... (all files when there are fewer files than ranks, then the windows are dealt round-robin), so no
+    rank parses text another rank uses.  Replaces the per-sample Python generator of the reference's input_fn
+    (generate_model.py:102-198) in the training loop."""
+    import random
+    from concurrent.futures import ThreadPoolExecutor
+
+    from .ingest import NativeIngest
+    paths = sorted(glob.glob(os.path.join(directory, "*.tar.gz")))
+    if not paths:
+        raise RuntimeError("IGNNITION: no *.tar.gz dataset files in %s" % directory)
+    deal = len(paths) < world                       # too few files: every rank reads all, windows are dealt out
+    mine = paths if deal else paths[rank::world]
+    out_name, out_norm, _ = model.get_output_info()
+    out_entity = [o for o in model.get_readout_operations() if o.type == "predict"][0].input[0]
+    fns = {}
+    for f in model.get_all_features():
+        if str(f.normalization) != "None":
+            fn = _resolve(f.normalization, namespace)
+            if fn is None:
+                raise RuntimeError("IGNNITION: The normalization function %s is not defined in the main file."
+                                   % f.normalization)
+            fns[f.name] = (lambda v, fn=fn, name=f.name: fn(v, name))
+    label_fn = None
+    if str(out_norm) != "None":
+        lf = _resolve(out_norm, namespace)
+        if lf is None:
+            raise RuntimeError("IGNNITION: The normalization function %s is not defined in the main file." % out_norm)
+        label_fn = lambda v: lf(v, out_name)
+
+    def parse(path):
+        ing = NativeIngest(engine, out_name)
+        with tarfile.open(path, "r:gz") as tar:
+            ing.parse(tar.extractfile("data.json").read())
+        return ing.batch(feature_fns=fns, label_fn=label_fn)
+
+    epoch, k = 0, 0
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        order = list(mine)
+        if shuffle:
+            random.Random(seed).shuffle(order)
+        nxt = pool.submit(parse, order[0])
+        i = 0
+        while True:
+            whole = nxt.result()
+            i += 1
+            if i == len(order):
+                i, epoch = 0, epoch + 1
+                order = list(mine)
+                if shuffle:
+                    random.Random(seed + epoch).shuffle(order)
+            nxt = pool.submit(parse, order[i])
+            for lo in range(0, whole.n_samples, batch_size):
+                k += 1
+                if deal and (k - 1) % world != rank:
+                    continue
+                hi = min(lo + batch_size, whole.n_samples)
+                yield whole.take_rows(whole.take(lo, hi, engine.adjacencies), lo, hi, engine.features, out_entity)
 
 
 def eval_metrics(labels: np.ndarray, preds: np.ndarray) -> Dict[str, float]:
@@ -266,25 +332,46 @@ def train_and_evaluate(model: ModelDescription, namespace: Optional[dict] = None
     ckpt_secs, eval_secs = float(opt.get("save_checkpoints_secs", 300)), float(opt.get("throttle_secs", 300))
     # every rank reads the SAME stream (file shuffle seeded identically on all ranks) and keeps its slice of each
     # global batch; the global prediction count is checked across ranks below
-    it = samples_of(model, cfg["PATHS"]["train_dataset"], True, opt.get("shuffle_train_samples", "True") == "True",
-                    namespace, repeat=True, seed=int(opt.get("shuffle_seed", 0)) if world > 1 else None)
+    native = opt.get("native_ingest", os.environ.get("IGNNITION_NATIVE_INGEST", "False")) in ("True", "1", "true")
+    shuffle = opt.get("shuffle_train_samples", "True") == "True"
+    if native:
+        # data.json text -> batch arrays in C++, one file ahead, files sharded over the ranks (native_train_batches)
+        stream = native_train_batches(model, engine, cfg["PATHS"]["train_dataset"], batch, namespace, rank, world,
+                                      shuffle, int(opt.get("shuffle_seed", 0)))
+        it = None
+    else:
+        it = samples_of(model, cfg["PATHS"]["train_dataset"], True, shuffle, namespace, repeat=True,
+                        seed=int(opt.get("shuffle_seed", 0)) if world > 1 else None)
     t_ckpt = t_eval = time.time()
     history = []
     for step in range(steps):
-        chunk = list(itertools.islice(it, batch * world))
-        if not chunk:
-            break
-        mine = chunk[rank::world] if world > 1 else chunk
-        n_glob = sum(c[1].size for c in chunk)
-        if world > 1 and step % 100 == 0:         # the 1/N of the loss must be the same number on every rank
+        if native:
+            b = next(stream)
+            n_loc = int(b.arrays["labels"].size)
+            n_glob = n_loc
+            if world > 1:                         # ranks read different files: the global count is their sum
+                cnt = torch.tensor([n_loc], dtype=torch.int64, device=engine.device)
+                torch.distributed.all_reduce(cnt)
+                n_glob = int(cnt.item())
+            graph = engine.build_graph(engine.upload(b), training=True)
+            trainer.train_step(graph, global_n=n_glob)
+            chunk = mine = None
+        else:
+            chunk = list(itertools.islice(it, batch * world))
+            if not chunk:
+                break
+            mine = chunk[rank::world] if world > 1 else chunk
+            n_glob = sum(c[1].size for c in chunk)
+        if not native and world > 1 and step % 100 == 0:         # the 1/N of the loss must be the same number on every rank
             chk = torch.tensor([n_glob, -n_glob], dtype=torch.int64, device=engine.device)
             torch.distributed.all_reduce(chk, op=torch.distributed.ReduceOp.MAX)
             if int(chk[0]) != n_glob or int(-chk[1]) != n_glob:
                 raise RuntimeError("IGNNITION: the ranks of the data-parallel run read different sample streams "
                                    "(global batch of %d predictions here, %d..%d across ranks)"
                                    % (n_glob, int(-chk[1]), int(chk[0])))
-        graph = engine.prepare([c[0] for c in mine], labels=[c[1] for c in mine], training=True)
-        trainer.train_step(graph, global_n=n_glob)
+        if not native:
+            graph = engine.prepare([c[0] for c in mine], labels=[c[1] for c in mine], training=True)
+            trainer.train_step(graph, global_n=n_glob)
         if step % 10 == 0:                        # LoggingTensorHook every 10 iterations (:820-824)
             l = trainer.losses()
             history.append((step, l["loss"]))

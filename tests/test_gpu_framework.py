@@ -70,3 +70,38 @@ execute_gpu: True
     m2 = ignnition.evaluate(model, engine, str(tmp_path / "eval"), 6, namespace=ns, native_ingest=True)
     for k in m:
         assert abs(m2[k] - m[k]) <= 1e-5 * max(abs(m[k]), 1e-12), k
+
+
+def test_training_loop_through_native_ingest(tmp_path):
+    """train_and_evaluate with native_ingest: data.json text -> batch arrays in C++ (one file ahead, windows of
+    batch_size samples) gives the same weights as the per-sample Python generator on the same unshuffled dataset"""
+    import json
+    from ignnition_b200 import framework_operations as ignnition
+    ns = {"normalization_routenet": normalization_routenet, "log": lambda f, n: np.log(f), "exp": lambda f, n: np.exp(f)}
+    g = load_golden("routenet_nsfnet")
+    (tmp_path / "model_description.json").write_text(json.dumps(g["model_json"]))
+    train = [synthetic.routenet_sample("nsfnet", k % 3, k) for k in range(24)]
+    synthetic.write_dataset(str(tmp_path / "train"), train, per_file=8)         # 8 = 2 x batch_size 4: whole windows
+    weights = {}
+    for native in ("False", "True"):
+        ini = tmp_path / ("train_options_%s.ini" % native)
+        ini.write_text("""[PATHS]
+train_dataset: %(d)s/train
+json_path: %(d)s/model_description.json
+model_dir: %(d)s/CheckPoints_%(n)s
+debug_dir: %(d)s/
+[TRAINING_OPTIONS]
+batch_size: 4
+train_steps: 9
+shuffle_train_samples: False
+native_ingest: %(n)s
+save_checkpoints_secs: 3000
+keep_checkpoint_max: 2
+throttle_secs: 3000
+execute_gpu: True
+""" % {"d": str(tmp_path), "n": native})
+        model = ignnition.create_model(str(ini))
+        engine, trainer, history = ignnition.train_and_evaluate(model, namespace=ns)
+        assert trainer.step == 9
+        weights[native] = engine.weights.cpu().numpy().copy()
+    assert np.abs(weights["True"] - weights["False"]).max() <= 1e-6 * np.abs(weights["False"]).max()

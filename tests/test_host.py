@@ -614,3 +614,34 @@ def test_learning_rate_schedules_by_name():
     assert abs(i(10) - 0.05) < 1e-12
     with pytest.raises(RuntimeError, match="not built"):
         LearningRate({"schedule": {"type": "CosineDecay"}})
+
+
+@pytest.mark.parametrize("case,qsize", [("routenet_nsfnet", False), ("qsize_nsfnet", True)])
+def test_batch_window_equals_assembling_the_window(case, qsize):
+    import json
+    """Batch.take / take_rows (a dataset file parsed once by the native ingest, cut into training batches) gives the
+    arrays assemble() gives for the same samples: entity offsets, shifted edge indices, position tables, labels"""
+    from ignnition_b200 import synthetic
+    from ignnition_b200.batching import assemble
+    from ignnition_b200.generator import sample_dimensions, sample_to_tensors
+    from ignnition_b200.ingest import NativeIngest
+    g = load_golden(case)
+    samples = [synthetic.routenet_sample("nsfnet", s, s, qsize=qsize) for s in range(9)]
+    md = ModelDescription(g["model_json"], sample_dimensions(samples[0]))
+    eng = _SpecEngine(md)
+    out_name = md.get_output_info()[0]
+    out_entity = [o for o in md.get_readout_operations() if o.type == "predict"][0].input[0]
+    ing = NativeIngest(eng, label_name=out_name)
+    assert ing.parse(json.dumps(samples)) == len(samples)
+    whole = ing.batch()
+    feats = [f[0] for f in eng.features]
+    pairs = [sample_to_tensors(s, feats, out_name, md.get_adjecency_info(), md.get_interleave_tensors(), [], True)
+             for s in samples]
+    for lo, hi in ((0, 9), (0, 3), (3, 4), (4, 9)):
+        win = whole.take_rows(whole.take(lo, hi, eng.adjacencies), lo, hi, eng.features, out_entity)
+        want = assemble([p[0] for p in pairs[lo:hi]], eng.entities, eng.features, eng.adjacencies, eng.sequences,
+                        [p[1] for p in pairs[lo:hi]])
+        assert win.n_samples == want.n_samples and win.num == want.num and win.n_edges == want.n_edges
+        assert win.max_seq == want.max_seq and set(win.arrays) == set(want.arrays)
+        for k in want.arrays:
+            assert np.array_equal(win.arrays[k], want.arrays[k]), (k, lo, hi)
