@@ -371,7 +371,7 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
     return out
 
 
-def run_ingest_leg(ctx, n_per_file=256, files=8):
+def run_ingest_leg(ctx, n_per_file=256, files=16):
     """data.json TEXT -> predictions: the C++ ingest parses `files` dataset files of `n_per_file` GEANT2-shaped samples
     on host threads while the GPU runs the batches that are ready (upload + adjacency build + forward + D2H per file).
     Wall clock, rank 0's GPU; the text is built once outside the timed region."""
