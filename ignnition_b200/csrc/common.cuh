@@ -21,6 +21,19 @@ void ign_set_error(const char* fmt, ...);
     }                                       \
   } while (0)
 
+// true the first time this call site runs on the CURRENT DEVICE in this thread: function attributes
+// (cudaFuncSetAttribute) are per device, so a process that drives a second GPU has to set them there too
+#define IGN_ONCE_PER_DEVICE()                                                    \
+  ([] {                                                                          \
+    static thread_local unsigned long long seen_ = 0;                            \
+    int d_ = 0;                                                                  \
+    cudaGetDevice(&d_);                                                          \
+    const unsigned long long bit_ = 1ull << (d_ & 63);                           \
+    if (seen_ & bit_) return false;                                              \
+    seen_ |= bit_;                                                               \
+    return true;                                                                 \
+  }())
+
 // process-wide count of kernels launched by this library (ign_launch_count)
 void ign_count_launch();
 

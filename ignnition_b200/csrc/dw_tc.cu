@@ -226,10 +226,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const float* __res
 template <int KB, int NB>
 int launch(const float* x, const float* dz, int64_t m, float* dw, cudaStream_t st) {
   using C = Cfg<KB, NB>;
-  static thread_local bool configured = false;
-  if (!configured) {
+  if (IGN_ONCE_PER_DEVICE()) {
     IGN_CUDA(cudaFuncSetAttribute(dw_tc_kernel<KB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    configured = true;
   }
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

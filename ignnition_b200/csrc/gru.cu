@@ -254,11 +254,14 @@ template <typename KernelT>
 int persistent_grid(KernelT k, size_t smem, int64_t ntiles, int* grid) {
   static thread_local const void* cached_fn[32];
   static thread_local int cached_occ[32];
+  static thread_local int cached_dev[32];
   const void* fn = reinterpret_cast<const void*>(k);
-  int occ = 0;
+  int occ = 0, cur = 0;
+  cudaGetDevice(&cur);                             // function attributes and occupancy are per device
   for (int i = 0; i < 32; ++i) {
-    if (cached_fn[i] == fn) { occ = cached_occ[i]; break; }
+    if (cached_fn[i] == fn && cached_dev[i] == cur) { occ = cached_occ[i]; break; }
     if (cached_fn[i] == nullptr) {
+      cached_dev[i] = cur;
       IGN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       IGN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, THREADS, smem));
       IGN_REQUIRE(occ >= 1, IGN_ERR_UNSUPPORTED, "IGNNITION: GRU kernel does not fit on an SM (smem %zu B)", smem);

@@ -373,14 +373,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_bwd_kernel(
 
 template <typename KernelT>
 int bwd_grid(KernelT k, size_t smem, int64_t ntiles, int* grid) {
-  static thread_local const void* done[8];
+  // (per template instantiation and per device: see IGN_ONCE_PER_DEVICE)
   const void* fn = reinterpret_cast<const void*>(k);
-  bool seen = false;
-  for (int i = 0; i < 8; ++i) {
-    if (done[i] == fn) { seen = true; break; }
-    if (!done[i]) { done[i] = fn; break; }
-  }
-  if (!seen) IGN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (IGN_ONCE_PER_DEVICE()) IGN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   *grid = (int)(ntiles < sms ? ntiles : sms);

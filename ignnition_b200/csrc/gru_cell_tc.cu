@@ -273,19 +273,16 @@ int ign_gru_cell_tc_launch(const float* x, const float* h, int64_t n, int units,
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = ign_cdiv(n, ROWS);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  static thread_local bool configured[2] = {false, false};
   if (units == 64) {
     const size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * 3 * 64 * 128);
-    if (!configured[1]) {
+    if (IGN_ONCE_PER_DEVICE()) {
       IGN_CUDA(cudaFuncSetAttribute(gru_cell_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[1] = true;
     }
     gru_cell_tc_kernel<64><<<grid, CELL_THREADS, smem, st>>>(x, h, n, img, bias, out);
   } else {
     const size_t smem = 1024 + 2 * (size_t)(2 * A_IMG + 2 * 3 * 32 * 128);
-    if (!configured[0]) {
+    if (IGN_ONCE_PER_DEVICE()) {
       IGN_CUDA(cudaFuncSetAttribute(gru_cell_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured[0] = true;
     }
     gru_cell_tc_kernel<32><<<grid, CELL_THREADS, smem, st>>>(x, h, n, img, bias, out);
   }

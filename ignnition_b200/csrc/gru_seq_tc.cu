@@ -385,12 +385,10 @@ int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* 
   SrcPtrs sp;
   for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
   const size_t smem = 1024 + 4 * (size_t)IMG + WALKERS * (size_t)SLOT_BYTES;
-  static thread_local bool configured = false;
   static const bool fast = getenv("IGN_GRU_TC_EXACT_MATH") == nullptr;   // default: ex2.approx-based sigmoid / tanh
-  if (!configured) {
+  if (IGN_ONCE_PER_DEVICE()) {
     IGN_CUDA(cudaFuncSetAttribute(gru_seq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IGN_CUDA(cudaFuncSetAttribute(gru_seq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -774,11 +774,9 @@ int ign_gru_step_bwd_tc_launch(int max_steps, const int* nt, const int* off, int
   float* dhs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ign_align((size_t)g_bound(num_dst) * 4 * U * sizeof(float)));
   const size_t smem_a = 1024 + 4 * (size_t)IMG + 8 * (size_t)W2IMG + 4 * (size_t)IMG + EPI_WARPS * 4096;
   const size_t smem_w = 1024 + (size_t)DW_STAGES * DW_STAGE;
-  static thread_local bool configured = false;
-  if (!configured) {
+  if (IGN_ONCE_PER_DEVICE()) {
     IGN_CUDA(cudaFuncSetAttribute(gru_step_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     IGN_CUDA(cudaFuncSetAttribute(gru_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
-    configured = true;
   }
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -270,10 +270,8 @@ int ign_gru_step_tc_launch(int t, const int* nt, const int* off, int64_t num_dst
   SrcPtrs sp;
   for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
   const size_t smem = 1024 + 4 * (size_t)IMG + 2 * (size_t)STAGE;
-  static thread_local bool configured = false;
-  if (!configured) {
+  if (IGN_ONCE_PER_DEVICE()) {
     IGN_CUDA(cudaFuncSetAttribute(gru_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

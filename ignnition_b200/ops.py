@@ -40,6 +40,11 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
         raise RuntimeError("IGNNITION: %s must be a CUDA tensor (no CPU path exists)" % name)
     if not t.is_contiguous():
         raise RuntimeError("IGNNITION: %s must be contiguous" % name)
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream: an Engine on another GPU must be driven under
+        # torch.cuda.device(engine.device) (peer-mapped buffers are passed as raw addresses, not tensors)
+        raise RuntimeError("IGNNITION: %s lives on cuda:%d but the current device is cuda:%d; wrap the call in "
+                           "torch.cuda.device(...)" % (name, t.device.index, torch.cuda.current_device()))
     if dtype is not None and t.dtype != dtype:
         raise RuntimeError("IGNNITION: %s must be %s, got %s" % (name, dtype, t.dtype))
     return t.data_ptr()
