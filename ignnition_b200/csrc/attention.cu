@@ -110,6 +110,81 @@ __global__ void attn_apply_kernel(const int* __restrict__ rowptr, const int* __r
   }
 }
 
+// ---- backward (tf.gradients through Attention_aggr).  With coef_j = exp(a_j - m_c) / den_c per slot j of column c:
+//   d_coef_j = g_out[d] . rows[idx_j]                    S_c = sum_{j in c} coef_j d_coef_j   (zero pads: d_coef = 0)
+//   d_a_j    = coef_j (d_coef_j - S_c)                   d_pre_j = d_a_j (a_j > 0 ? 1 : 0.2)  (LeakyReLU 0.2)
+//   d_msg[pos_j] = coef_j g_out[d]   (the part of dL/d rows that comes through the weighted sum, per edge)
+//   d_pre4[pos_j] = (d_pre_j, 0, 0, 0),   d_ds[d] = sum_j d_pre_j
+// pos_j = perm[j] (input edge position) or j.  The caller reduces d_msg / d_pre4 per row of `rows` and pushes d_pre
+// through the two score products (ign_dense_bwd).  Pass 1: 8 lanes per destination, d_coef into dcoef[], S_c by fp64 atomics.
+__device__ __forceinline__ float attn_coef(const AttnWs& w, int64_t c, int n_in, float a) {
+  const float m = col_shift(w, c, n_in);
+  const double den = w.colsum[c] + (double)(n_in - w.cnt[c]) * (double)expf(-m);
+  return (float)((double)expf(a - m) / den);
+}
+
+__global__ void attn_bwd_dot_kernel(const int* __restrict__ rowptr, const int* __restrict__ idx,
+                                    const float* __restrict__ rows, int F, const float* __restrict__ g_out,
+                                    const int* __restrict__ off, int n_samples, int64_t num_dst, int max_len, AttnWs w,
+                                    float* __restrict__ dcoef, double* __restrict__ colS) {
+  const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int gl = threadIdx.x & 7;
+  if (d >= num_dst) return;                               // whole 8-lane groups leave together
+  const int lo = rowptr[d], hi = rowptr[d + 1];
+  if (hi == lo) return;
+  const int s = sample_of(off, n_samples, (int)d);
+  const int n_in = off[s + 1] - off[s];
+  const int64_t base = (int64_t)s * max_len;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);
+  for (int j = lo; j < hi; ++j) {
+    float dot = 0.f;
+    for (int f = gl * 4; f < F; f += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(rows + (int64_t)idx[j] * F + f);
+      const float4 g = *reinterpret_cast<const float4*>(g_out + d * F + f);
+      dot += v.x * g.x + v.y * g.y + v.z * g.z + v.w * g.w;
+    }
+    dot += __shfl_xor_sync(gmask, dot, 1);
+    dot += __shfl_xor_sync(gmask, dot, 2);
+    dot += __shfl_xor_sync(gmask, dot, 4);
+    if (gl == 0) {
+      const int64_t c = base + (j - lo);
+      dcoef[j] = dot;
+      atomicAdd(&colS[c], (double)attn_coef(w, c, n_in, w.a[j]) * (double)dot);
+    }
+  }
+}
+
+__global__ void attn_bwd_apply_kernel(const int* __restrict__ rowptr, const int* __restrict__ perm, int F,
+                                      const float* __restrict__ g_out, const int* __restrict__ off, int n_samples,
+                                      int64_t num_dst, int max_len, AttnWs w, const float* __restrict__ dcoef,
+                                      const double* __restrict__ colS, float* __restrict__ d_msg,
+                                      float* __restrict__ d_pre4, float* __restrict__ d_ds) {
+  const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int gl = threadIdx.x & 7;
+  if (d >= num_dst) return;
+  const int lo = rowptr[d], hi = rowptr[d + 1];
+  float sum_pre = 0.f;
+  if (hi > lo) {
+    const int s = sample_of(off, n_samples, (int)d);
+    const int n_in = off[s + 1] - off[s];
+    const int64_t base = (int64_t)s * max_len;
+    for (int j = lo; j < hi; ++j) {
+      const int64_t c = base + (j - lo);
+      const float a = w.a[j];
+      const float coef = attn_coef(w, c, n_in, a);
+      const float d_pre = coef * (dcoef[j] - (float)colS[c]) * (a > 0.f ? 1.f : 0.2f);
+      sum_pre += d_pre;
+      const int64_t pos = perm ? perm[j] : j;
+      for (int f = gl * 4; f < F; f += 32) {
+        const float4 g = *reinterpret_cast<const float4*>(g_out + d * F + f);
+        *reinterpret_cast<float4*>(d_msg + pos * F + f) = make_float4(coef * g.x, coef * g.y, coef * g.z, coef * g.w);
+      }
+      if (gl == 0) *reinterpret_cast<float4*>(d_pre4 + pos * 4) = make_float4(d_pre, 0.f, 0.f, 0.f);
+    }
+  }
+  if (gl == 0) d_ds[d] = sum_pre;
+}
+
 AttnWs carve(void* ws, int64_t n_edges, int64_t n_cols) {
   AttnWs w;
   char* p = static_cast<char*>(ws);
@@ -158,5 +233,41 @@ extern "C" int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col
   attn_apply_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(rowptr, col, rows, F, sample_offsets,
                                                                           (int)n_samples, num_dst, max_len, w, out);
   IGN_CHECK_LAUNCH("attn_apply");
+  return IGN_OK;
+}
+
+extern "C" size_t ign_attention_bwd_ws_bytes(int64_t n_edges, int64_t n_samples, int max_len) {
+  const int64_t n_cols = (n_samples > 0 ? n_samples : 0) * (int64_t)(max_len > 0 ? max_len : 0);
+  return ign_align_up(n_cols * sizeof(double), 256) + ign_align_up((n_edges > 0 ? n_edges : 0) * sizeof(float), 256) + 256;
+}
+
+extern "C" int ign_attention_aggregate_bwd(const int32_t* rowptr, const int32_t* idx, const int32_t* perm,
+                                           const float* rows, int F, const float* g_out,
+                                           const int32_t* sample_offsets, int64_t n_samples, int64_t num_dst,
+                                           int64_t n_edges, int max_len, const void* fwd_ws, float* d_msg, float* d_pre4,
+                                           float* d_ds, void* ws, size_t ws_bytes, void* stream) {
+  IGN_REQUIRE(num_dst >= 0 && n_edges >= 0 && n_samples >= 0 && max_len >= 0, IGN_ERR_INVALID,
+              "IGNNITION: attention_bwd: negative size");
+  IGN_REQUIRE(F > 0 && F % 4 == 0, IGN_ERR_UNSUPPORTED, "IGNNITION: attention_bwd: message width must be a multiple of 4");
+  if (num_dst == 0) return IGN_OK;
+  IGN_REQUIRE(rowptr && g_out && sample_offsets && d_ds && fwd_ws, IGN_ERR_INVALID, "IGNNITION: attention_bwd: null pointer");
+  IGN_REQUIRE(n_edges == 0 || (idx && rows && d_msg && d_pre4), IGN_ERR_INVALID, "IGNNITION: attention_bwd: null pointer");
+  IGN_REQUIRE(ws && ws_bytes >= ign_attention_bwd_ws_bytes(n_edges, n_samples, max_len), IGN_ERR_WORKSPACE,
+              "IGNNITION: attention_bwd: workspace too small");
+  cudaStream_t st = ign_stream(stream);
+  const int64_t n_cols = n_samples * (int64_t)max_len;
+  AttnWs w = carve(const_cast<void*>(fwd_ws), n_edges, n_cols);      // column statistics and scores of the forward pass
+  double* colS = reinterpret_cast<double*>(ws);
+  float* dcoef = reinterpret_cast<float*>(static_cast<char*>(ws) + ign_align_up(n_cols * sizeof(double), 256));
+  IGN_CUDA(cudaMemsetAsync(colS, 0, (size_t)n_cols * sizeof(double), st));
+  if (n_edges > 0) {
+    attn_bwd_dot_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(rowptr, idx, rows, F, g_out, sample_offsets,
+                                                                            (int)n_samples, num_dst, max_len, w, dcoef, colS);
+    IGN_CHECK_LAUNCH("attn_bwd_dot");
+  }
+  attn_bwd_apply_kernel<<<(unsigned)ign_cdiv(num_dst * 8, 256), 256, 0, st>>>(rowptr, perm, F, g_out, sample_offsets,
+                                                                            (int)n_samples, num_dst, max_len, w, dcoef, colS,
+                                                                            d_msg, d_pre4, d_ds);
+  IGN_CHECK_LAUNCH("attn_bwd_apply");
   return IGN_OK;
 }

@@ -225,6 +225,8 @@ class Engine:
                     self._add_param(p.dst + "_attention/attn_kernel", (2 * fd, 1), "glorot")
                     p.op = ops.OP_SUM
                     p.attn = True
+                    for a_ in p.adjs:            # its backward writes per-edge gradients in input edge order
+                        self._needs_perm.add(a_.name)
                     p.kind = "agg_gru" if mp.update.type == "recurrent_nn" else "agg_ff"
                 elif agg == "convolution":
                     if p.msg_dim != fd:
@@ -630,8 +632,6 @@ class Engine:
         agg = None
         max_src = None       # (rows, index per CSR slot) the aggregation read: what the backward of a max compares
         if p.attn:      # Attention_aggr (auxilary_classes.py:278-344)
-            if tape is not None:
-                raise RuntimeError("IGNNITION: training through the attention aggregation is not built")
             a = p.adjs[0]
             rowptr, col, perm = g.csr[a.name]
             rows, idx = (state[a.src], col) if msgs[0] is None else (msgs[0], perm)
@@ -639,8 +639,12 @@ class Engine:
             ak = self.param(dst + "_attention/attn_kernel")
             v1 = ops.dense(self.param(dst + "_attention/kernel1"), ak[:F], None, 0)
             v2 = ops.dense(self.param(dst + "_attention/kernel2"), ak[F:], None, 0)
+            max_len = max(g.max_seq.get(a.name, 0), 1)
             agg = ops.attention_aggregate(rowptr, idx, rows, ops.dense(rows, v1, None, 0), ops.dense(h, v2, None, 0),
-                                          g.t["offsets_" + dst], max(g.max_seq.get(a.name, 0), 1))
+                                          g.t["offsets_" + dst], max_len, keep_ws=tape is not None)
+            if tape is not None:
+                agg, attn_ws = agg
+                max_src = ("attn", rows, idx, v1, v2, attn_ws, h, max_len)
         for k, a in enumerate(p.adjs if not p.attn else []):
             rowptr, col, perm = g.csr[a.name]
             if msgs[k] is None:

@@ -524,7 +524,8 @@ def conv_finish(nsum, self_state, rowptr, act: int, out=None):
     return out
 
 
-def attention_aggregate(rowptr, col, rows, src_score, dst_score, sample_offsets, max_len: int, out=None):
+def attention_aggregate(rowptr, col, rows, src_score, dst_score, sample_offsets, max_len: int, out=None,
+                        keep_ws: bool = False):
     lib = _lib.load()
     num_dst = rowptr.numel() - 1
     n_edges = col.numel()
@@ -537,7 +538,27 @@ def attention_aggregate(rowptr, col, rows, src_score, dst_score, sample_offsets,
     _lib.check(lib.ign_attention_aggregate(_i(rowptr), _i(col), _f(rows), F, _f(src_score), _f(dst_score),
                                            _i(sample_offsets), n_samples, num_dst, n_edges, max_len, _f(out),
                                            ws.data_ptr(), nbytes, _stream()), "attention_aggregate")
-    return out
+    return (out, ws) if keep_ws else out
+
+
+def attention_aggregate_bwd(rowptr, idx, perm, rows, g_out, sample_offsets, max_len: int, fwd_ws):
+    """(d_msg [E, F], d_pre4 [E, 4], d_ds [num_dst, 1]) of ign_attention_aggregate_bwd, per-edge arrays in input edge order"""
+    lib = _lib.load()
+    num_dst = rowptr.numel() - 1
+    n_edges = idx.numel()
+    n_samples = sample_offsets.numel() - 1
+    F = rows.shape[1]
+    dev = rows.device
+    d_msg = torch.zeros(n_edges, F, dtype=torch.float32, device=dev)
+    d_pre4 = torch.zeros(n_edges, 4, dtype=torch.float32, device=dev)
+    d_ds = torch.zeros(num_dst, 1, dtype=torch.float32, device=dev)
+    nbytes = lib.ign_attention_bwd_ws_bytes(n_edges, n_samples, max_len)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.ign_attention_aggregate_bwd(_i(rowptr), _i(idx), _i(perm), _f(rows), F, _f(g_out), _i(sample_offsets),
+                                               n_samples, num_dst, n_edges, max_len, fwd_ws.data_ptr(), _f(d_msg),
+                                               _f(d_pre4), _f(d_ds), ws.data_ptr(), nbytes, _stream()),
+               "attention_aggregate_bwd")
+    return d_msg, d_pre4, d_ds
 
 
 def partner_index(rowptr0, rowptr1, idx1, n_edges0: int):

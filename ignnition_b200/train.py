@@ -180,6 +180,39 @@ class Trainer:
             """dL/d(aggregated messages per destination) -> source states, or -> per-edge messages of a message
             network.  mean: dL/d(sum) = dL/d(mean) / degree; max: the slots that attain the maximum share the gradient
             (TensorFlow's unsorted_segment_max), written per edge and reduced per source row."""
+            if p.attn:
+                # Attention_aggr (auxilary_classes.py:278-344): through the column softmax and the LeakyReLU to the two
+                # score products, and through the weighted sum to the messages
+                _, rows, idx, v1, v2, attn_ws, h_dst, max_len = max_src
+                a = p.adjs[0]
+                rowptr, _, perm = graph.csr[a.name]
+                F = p.msg_dim
+                d_msg, d_pre4, d_ds = ops.attention_aggregate_bwd(rowptr, idx, perm, rows, d_agg,
+                                                                  graph.t["offsets_" + p.dst], max_len, attn_ws)
+                d_v1, d_v2 = torch.zeros_like(v1), torch.zeros_like(v2)
+                tmp = torch.empty_like(h_dst)
+                ops.dense_bwd(h_dst, v2, 0, None, d_ds, tmp, d_v2, None)        # dst_score = h v2
+                add_grad(p.dst, tmp)
+                if has_msg[0]:                                                  # rows = per-edge messages (edge order)
+                    tmp = torch.empty_like(rows)
+                    ops.dense_bwd(rows, v1, 0, None, ops.slice_cols(d_pre4, 0, 1), tmp, d_v1, None)
+                    ops.axpy(1.0, tmp, d_msg)
+                    pending[(p.key, 0)] = d_msg
+                else:                                                           # rows = source states: reduce per source row
+                    rp_t, _, perm_t = graph.csr_t[a.name]
+                    d_rows = ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_msg)
+                    d_ss = ops.slice_cols(ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_pre4), 0, 1)
+                    tmp = torch.empty_like(rows)
+                    ops.dense_bwd(rows, v1, 0, None, d_ss, tmp, d_v1, None)     # src_score = rows v1
+                    ops.axpy(1.0, tmp, d_rows)
+                    add_grad(a.src, d_rows)
+                ak, d_ak = e.param(p.dst + "_attention/attn_kernel"), self.g(p.dst + "_attention/attn_kernel")
+                for kname, d_v, lo_, hi_ in (("kernel1", d_v1, 0, F), ("kernel2", d_v2, F, ak.shape[0])):
+                    kmat = e.param("%s_attention/%s" % (p.dst, kname))          # v = kernel . attn_kernel[lo:hi]
+                    dk = torch.empty_like(kmat)
+                    ops.dense_bwd(kmat, ak[lo_:hi_], 0, None, d_v, dk, d_ak[lo_:hi_], None)
+                    ops.axpy(1.0, dk, self.g("%s_attention/%s" % (p.dst, kname)))
+                return
             if p.conv:
                 # Conv_aggr (auxilary_classes.py:366-401): out = act((sum W + h) / deg).  dL/d(sum W + h) = act'(out) dL/dout
                 # / deg goes to the destination's own state as it is, and through the kernel product to the neighbour sum

@@ -369,6 +369,19 @@ int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const flo
                             int64_t n_samples, int64_t num_dst, int64_t n_edges, int max_len, float* out,
                             void* ws, size_t ws_bytes, void* stream);
 
+/* Backward of ign_attention_aggregate (tf.gradients through Attention_aggr).  fwd_ws = the workspace the forward call
+ * filled (scores and column statistics; keep it).  Outputs, per edge at its input position perm[slot] (slot when perm is
+ * NULL): d_msg [E, F] = coef g_out[d] (the weighted-sum part of dL/d rows) and d_pre4 [E, 4] = (dL/d(src_score +
+ * dst_score before the LeakyReLU), 0, 0, 0); per destination d_ds [num_dst] = dL/d dst_score.  The caller reduces the
+ * per-edge arrays per row of `rows` (ign_segment_reduce over the transposed adjacency) and finishes the two score
+ * products with ign_dense_bwd. */
+size_t ign_attention_bwd_ws_bytes(int64_t n_edges, int64_t n_samples, int max_len);
+int ign_attention_aggregate_bwd(const int32_t* rowptr, const int32_t* idx, const int32_t* perm, const float* rows, int F,
+                                const float* g_out, const int32_t* sample_offsets, int64_t n_samples, int64_t num_dst,
+                                int64_t n_edges, int max_len, const void* fwd_ws, float* d_msg, float* d_pre4,
+                                float* d_ds, void* ws, size_t ws_bytes, void* stream);
+
+
 /* Concat_aggr with concat_axis = 2 (generate_model.py:496-505): for CSR position j of the first source
  * (destination d, padded column s = j - rowptr0[d]) the row of another source sitting at the same padded
  * column: out[j] = idx1[rowptr1[d] + s], or -1 where that source's block is zero padding.  Feed the index

@@ -148,6 +148,19 @@ class TorchOracle:
         K, R, b = w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"], w[dst + "_update/bias"]
         if agg == "sum":
             return gru_cell(src_input.sum(dim=1), h, K, R, b)
+        if agg == "attention":              # Attention_aggr (auxilary_classes.py:278-344), single source, as-is:
+            src0 = mp["source_entities"][0]   # softmax over the DESTINATIONS per padded column, zero pads included
+            dst_idx = torch.as_tensor(np.asarray(inp["dst_" + src0["adj_vector"]], dtype=np.int64))
+            seq = torch.as_tensor(np.asarray(inp["seq_" + src0["name"] + "_" + dst], dtype=np.int64))
+            comb = src_input[dst_idx, seq]                                       # the messages back in edge order
+            k1, k2, ak = w[dst + "_attention/kernel1"], w[dst + "_attention/kernel2"], w[dst + "_attention/attn_kernel"]
+            a_in = torch.cat([comb @ k1, h[dst_idx] @ k2], dim=1) @ ak
+            a_in = torch.where(a_in > 0, a_in, 0.2 * a_in)
+            mx = int(seq.max()) + 1
+            aux = torch.zeros(num_dst, mx, 1, dtype=dt).index_put((dst_idx, seq), a_in)
+            coef = torch.softmax(aux, dim=0)
+            red = torch.zeros(num_dst, comb.shape[1], dtype=dt).index_add(0, dst_idx, comb * coef[dst_idx, seq])
+            return gru_cell(red, h, K, R, b)
         if agg == "convolution":            # Conv_aggr (auxilary_classes.py:366-401), single source
             ck = w[dst + "_convolution/conv_kernel"]
             deg = final_len.to(dt)[:, None]

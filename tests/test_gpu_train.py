@@ -184,7 +184,7 @@ def test_training_unbuilt_paths_fail_loudly():
     from ignnition_b200.generator import sample_dimensions
     from ignnition_b200.train import Trainer
     rng = np.random.RandomState(3)
-    for agg, msg in (("attention", False), ("ordered", True)):
+    for agg, msg in (("ordered", True),):
         model_json = _mpnn_json(agg, 32, "gru", msg)
         samples = [_mpnn_sample(rng, 30, 4, params=msg)]
         for s in samples:
@@ -483,3 +483,16 @@ def test_generic_width_trains():
     rng = np.random.RandomState(48)
     samples = [_mpnn_sample(rng, n, 5) for n in (25, 140)]
     _grad_check(_mpnn_json("sum", 48), samples)
+
+
+@pytest.mark.parametrize("message_nn", [False, True])
+def test_gradients_attention_aggregation(message_nn):
+    """tf.gradients through Attention_aggr as the reference computes it (softmax over the destinations of a sample per
+    padded column, zero pads included; auxilary_classes.py:278-344): kernel1, kernel2, attn_kernel, the messages
+    (source states or message-network outputs) and the destination states, vs fp64 autograd"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample
+    rng = np.random.RandomState(8 + int(message_nn))
+    mj = _mpnn_json("attention", 32, "gru", message_nn)
+    samples = [_mpnn_sample(rng, n, 5, params=message_nn) for n in (25, 2, 150)]
+    eng = _grad_check(mj, samples)
+    assert "node_attention/attn_kernel" in eng.param_table
