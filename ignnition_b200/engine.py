@@ -579,8 +579,8 @@ class Engine:
         out = torch.empty_like(h)
         msgs = [self._messages(p, k, g, state, tape) for k in range(len(p.adjs))]
         has_msg = [m is not None for m in msgs]
-        if tape is not None and any(has_msg) and p.kind == "seq_gru":
-            raise RuntimeError("IGNNITION: training through message neural networks that feed an ordered "
+        if tape is not None and any(has_msg) and p.kind == "seq_gru" and not p.msg_rows:
+            raise RuntimeError("IGNNITION: training through message neural networks that feed a multi-source ordered "
                                "aggregation is not built")
 
         if p.kind == "seq_gru":
@@ -590,8 +590,8 @@ class Engine:
                 srcs.append(msgs[k] if msgs[k] is not None else state[a.src])
             if p.concat2:
                 srcs = [ops.gather_concat(srcs, g.partner[p.key], int(g.partner[p.key][0].numel()))]
-            if (p.concat2 or p.msg_rows) and tape is not None:
-                raise RuntimeError("IGNNITION: training through concat / message-network ordered aggregations "
+            if p.concat2 and tape is not None:
+                raise RuntimeError("IGNNITION: training through the concat aggregation along the feature axis "
                                    "is not built")
             h_seq = None
             if tape is not None:
@@ -602,8 +602,8 @@ class Engine:
             else:
                 ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq,
                             meta=g.meta.get(p.key))
-            if tape is not None:
-                tape.append(("seq_gru", p, [state[a.src] for a in p.adjs], h, h_seq))
+            if tape is not None:          # the rows the walk read: source states, or the message network's rows
+                tape.append(("seq_gru", p, list(srcs), h, h_seq))
             return out
 
         # aggregating kinds

@@ -178,24 +178,33 @@ def test_gradients_message_network_and_ff_update(update, message_nn):
         assert rel_err(gn, grads[name]) < GRAD_RTOL_SELU_KINK, name
 
 
+def test_gradients_message_network_into_ordered_aggregation():
+    """tf.gradients through a message neural network whose rows are walked by an ordered aggregation (RNN over the
+    per-edge messages): BPTT per step -> per-edge message gradients -> the message network, vs fp64 autograd"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample
+    rng = np.random.RandomState(3)
+    samples = [_mpnn_sample(rng, n, 4, params=True) for n in (30, 7, 120)]
+    for s_ in samples:                         # ordered needs >= 1 message per destination in the reference
+        for v in s_["entities"]:
+            s_["adj"].setdefault(v, [[v, [1.0, 2.0]]])
+    _grad_check(_mpnn_json("ordered", 32, "gru", True), samples)
+
+
 def test_training_unbuilt_paths_fail_loudly():
     """paths whose backward pass does not exist raise instead of dropping gradients"""
-    from test_gpu_model import _mpnn_json, _mpnn_sample, make, tensors_of
+    from test_gpu_model import _two_entity_json, _two_entity_sample, make, tensors_of
     from ignnition_b200.generator import sample_dimensions
     from ignnition_b200.train import Trainer
-    rng = np.random.RandomState(3)
-    for agg, msg in (("ordered", True),):
-        model_json = _mpnn_json(agg, 32, "gru", msg)
-        samples = [_mpnn_sample(rng, 30, 4, params=msg)]
-        for s in samples:
-            for v in s["entities"]:
-                s["adj"].setdefault(v, [[v, [1.0, 2.0]]] if msg else [v])
-        dims = sample_dimensions(samples[0])
-        md, eng, o64, w = make(model_json, dims)
-        t, y = tensors_of(md, samples[0])[:2]
-        graph = eng.prepare([t], labels=[np.asarray(y, np.float32)], training=True)
-        with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
-            Trainer(eng).loss_and_grads(graph)
+    rng = np.random.RandomState(21)
+    mj = _two_entity_json({"type": "concat", "concat_axis": 2})
+    s_ = _two_entity_sample(rng, 8, 6, 12)
+    for p_ in list(s_["lp"]):                  # equally long padded blocks (tf.concat along the features)
+        s_["np"][p_] = ["n%d" % (i % 6) for i in range(len(s_["lp"][p_]))]
+    md, eng, o64, w = make(mj, sample_dimensions(s_))
+    t, y = tensors_of(md, s_)[:2]
+    graph = eng.prepare([t], labels=[np.asarray(y, np.float32)], training=True)
+    with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
+        Trainer(eng).loss_and_grads(graph)
 
 
 def test_full_size_gradients_tensor_core_vs_fp32_backward():
