@@ -203,15 +203,18 @@ __global__ void __launch_bounds__(PJ_THREADS, 2) project_kernel(const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------- walk
-template <bool FAST>
-__global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
+// UPT = units per thread: 32 -> four warps per walker (thread = one destination), 16 -> eight warps per walker (two
+// threads per destination, the second warp of a TMEM lane quarter takes units 16..31)
+template <bool FAST, int UPT>
+__global__ void __launch_bounds__(WALKERS * 128 * (U / UPT), 1) gru_seq_proj_kernel(
     const int* __restrict__ steps, Tables xp, const float* __restrict__ h0, int64_t num_dst,
     const float* __restrict__ rkernel, const float* __restrict__ bias, float* __restrict__ out,
     float* __restrict__ h_seq, const int4* __restrict__ meta, int opt) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t hint_ns = (uint32_t)opt >> 8;             // IGN_PROJ_OPT: (suspend hint ns << 8) | 1 = direct result stores
-  const bool direct_out = opt & 1;
+  constexpr int WT = 128 * (U / UPT);                      // threads of a walker
+  constexpr int NTHREADS = WALKERS * WT;
+  const uint32_t hint_ns = (uint32_t)opt >> 8;             // IGN_PROJ_OPT: suspend hint ns << 8
   unsigned char* b_hi = smem;                              // [96 n][32 k] images of [Rz | Rr | Rh], hi and lo
   unsigned char* b_lo = b_hi + BIMG;
   unsigned char* stages = b_lo + BIMG;
@@ -226,12 +229,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
   if (tid == 0) {
     for (int g = 0; g < WALKERS; ++g) {
       mbar_init(&bar_acc[g], 1);
-      mbar_init(&bar_xp[g], WTHREADS);
+      mbar_init(&bar_xp[g], WT);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512u);
-  for (int i = tid; i < XP * U; i += THREADS) {
+  for (int i = tid; i < XP * U; i += NTHREADS) {
     const int n = i >> 5, k = i & 31;
     float hi, lo;
     tf32_split((FAST ? (n < 2 * U ? SCALE_ZR : SCALE_C) : 1.0f) * __ldg(rkernel + k * XP + n), hi, lo);
@@ -249,9 +252,12 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
   const uint32_t tmem_base = tmem_base_s;
   const int64_t ntiles = (num_dst + ROWS - 1) / ROWS;
 
-  const int g = warp >> 2;                                 // walker
-  const int q = warp & 3;                                  // TMEM lane quarter of this warp
-  const int gtid = tid & (WTHREADS - 1);
+  const int g = warp / (WT / 32);                          // walker
+  const int wq = warp % (WT / 32);
+  const int q = wq & 3;                                    // TMEM lane quarter of this warp
+  const int split = wq >> 2;                               // which half of the units (UPT = 16)
+  const int u0 = split * UPT;
+  const int gtid = tid % WT;
   const int row = q * 32 + lane;                           // this thread's destination of the tile
   unsigned char* stage = stages + g * STAGE;
   const uint32_t tD = tmem_base + g * TCOLS;               // MMA operand addresses (lane 0)
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
   const int64_t tile_stride = (int64_t)WALKERS * gridDim.x;
   uint32_t acc_phase = 0;
 
-  auto wsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(WTHREADS) : "memory"); };
+  auto wsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(WT) : "memory"); };
   auto load_plan = [&](int64_t tile) -> int4 {
     const int64_t i = tile * ROWS + row;
     if (tile < ntiles && i < num_dst) return __ldg(meta + i);
@@ -276,9 +282,10 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
   const uint32_t stage_s = smem_u32(stage);
   unsigned char* my_row = stage + row * XROW;
   auto gather_xp = [&](int e) {
+    constexpr int NIT = 8 / (WT / 128);                      // the warps of a lane quarter share its 32 rows
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + sub;
+    for (int i = 0; i < NIT; ++i) {
+      const int rl = 4 * (i + NIT * split) + sub;
       const int ev = __shfl_sync(0xffffffffu, e, rl);
       const uint32_t dst = stage_s + (uint32_t)((q * 32 + rl) * XROW + lc * 16);
       if (ev >= 0) {
@@ -291,11 +298,11 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_xp[g])) : "memory");
   };
   uint32_t xp_phase = 0;
-  float h[U];
+  float h[UPT];
   // the state as the A operand of the next MMA: hi / lo columns of this thread's TMEM lane
   auto store_a = [&]() {
 #pragma unroll
-    for (int hb = 0; hb < 2; ++hb) {
+    for (int hb = 0; hb < UPT / 16; ++hb) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
@@ -304,8 +311,8 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
         hi[k] = __float_as_uint(a);
         lo[k] = __float_as_uint(b);
       }
-      tmem_st16(tl + XP + 16 * hb, hi);
-      tmem_st16(tl + XP + U + 16 * hb, lo);
+      tmem_st16(tl + XP + u0 + 16 * hb, hi);
+      tmem_st16(tl + XP + U + u0 + 16 * hb, lo);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -335,9 +342,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
     const int wmax = __reduce_max_sync(0xffffffffu, plan.z);
     if (lane == 0) s_max[g][0][q] = wmax;
 #pragma unroll
-    for (int j = 0; j < U / 4; ++j) {
+    for (int j = 0; j < UPT / 4; ++j) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (plan.x >= 0) v = ldg_f4(h0 + (int64_t)plan.x * U + 4 * j);
+      if (plan.x >= 0) v = ldg_f4(h0 + (int64_t)plan.x * U + u0 + 4 * j);
       h[4 * j] = v.x; h[4 * j + 1] = v.y; h[4 * j + 2] = v.z; h[4 * j + 3] = v.w;
     }
   }
@@ -356,16 +363,16 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
   for (; tile < ntiles; tile += tile_stride) {
     const int s_d = plan.x, s_lo = plan.y, s_len = plan.z;
     int4 plan_n = load_plan(tile + tile_stride);           // arrives long before the last step
-    float4 h0n[U / 4];
+    float4 h0n[UPT / 4];
     int e1n = ENT_IDLE;
     // loads for the NEXT tile, issued under the wait of this tile's last step
     auto next_loads = [&]() {
       const int wmax = __reduce_max_sync(0xffffffffu, plan_n.z);
       if (lane == 0) s_max[g][par ^ 1][q] = wmax;
 #pragma unroll
-      for (int j = 0; j < U / 4; ++j) {
+      for (int j = 0; j < UPT / 4; ++j) {
         h0n[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (plan_n.x >= 0) h0n[j] = ldg_f4(h0 + (int64_t)plan_n.x * U + 4 * j);
+        if (plan_n.x >= 0) h0n[j] = ldg_f4(h0 + (int64_t)plan_n.x * U + u0 + 4 * j);
       }
       e1n = plan_n.z > 1 ? __ldg(steps + plan_n.y + 1) : ENT_IDLE;
     };
@@ -386,26 +393,36 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
         const bool act = t < s_len;                        // rows of one warp may differ in length: the TMEM loads are
         // .sync.aligned and run for every lane, only the math is guarded
         const uint32_t xr = e_cur == IGN_STEP_ZERO ? smem_u32(s_xb) : smem_u32(my_row);
-        uint32_t acc[2][24];                               // [z | r | c] pre-activations of 8 units, double-buffered
-        tmem_ld8_nowait(tl, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][0]));
-        tmem_ld8_nowait(tl + U, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][8]));
-        tmem_ld8_nowait(tl + 2 * U, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][16]));
+        // [z | r | c] pre-activations of 8 units; double-buffered where the registers allow it (four-warp walkers)
+        constexpr int NBUF = UPT == 32 ? 2 : 1;
+        uint32_t acc[NBUF][24];
+        const uint32_t tu = tl + u0;
+        if (NBUF == 2) {
+          tmem_ld8_nowait(tu, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][0]));
+          tmem_ld8_nowait(tu + U, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][8]));
+          tmem_ld8_nowait(tu + 2 * U, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][16]));
+        }
 #pragma unroll
-        for (int c = 0; c < U / 8; ++c) {                  // 8 units at a time; the loads of chunk c + 1 fly under the math
+        for (int c = 0; c < UPT / 8; ++c) {                // 8 units at a time; the loads of chunk c + 1 fly under the math
+          if (NBUF == 1) {
+            tmem_ld8_nowait(tu + 8 * c, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][0]));
+            tmem_ld8_nowait(tu + U + 8 * c, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][8]));
+            tmem_ld8_nowait(tu + 2 * U + 8 * c, *reinterpret_cast<uint32_t(*)[8]>(&acc[0][16]));
+          }
           tmem_ld_wait();
-          if (c + 1 < U / 8) {
-            tmem_ld8_nowait(tl + 8 * (c + 1), *reinterpret_cast<uint32_t(*)[8]>(&acc[(c + 1) & 1][0]));
-            tmem_ld8_nowait(tl + U + 8 * (c + 1), *reinterpret_cast<uint32_t(*)[8]>(&acc[(c + 1) & 1][8]));
-            tmem_ld8_nowait(tl + 2 * U + 8 * (c + 1), *reinterpret_cast<uint32_t(*)[8]>(&acc[(c + 1) & 1][16]));
+          if (NBUF == 2 && c + 1 < UPT / 8) {
+            tmem_ld8_nowait(tu + 8 * (c + 1), *reinterpret_cast<uint32_t(*)[8]>(&acc[(c + 1) & 1][0]));
+            tmem_ld8_nowait(tu + U + 8 * (c + 1), *reinterpret_cast<uint32_t(*)[8]>(&acc[(c + 1) & 1][8]));
+            tmem_ld8_nowait(tu + 2 * U + 8 * (c + 1), *reinterpret_cast<uint32_t(*)[8]>(&acc[(c + 1) & 1][16]));
           }
           if (act) {
-            const uint32_t* a = acc[c & 1];
+            const uint32_t* a = acc[NBUF == 2 ? (c & 1) : 0];
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
-              const float4 vz = lds_f4(xr + (8 * c + 4 * j4) * 4);
-              const float4 vr = lds_f4(xr + 128 + (8 * c + 4 * j4) * 4);
-              const float4 vc = lds_f4(xr + 256 + (8 * c + 4 * j4) * 4);
-              const float4 vb = *reinterpret_cast<const float4*>(s_bhh + 8 * c + 4 * j4);
+              const float4 vz = lds_f4(xr + (u0 + 8 * c + 4 * j4) * 4);
+              const float4 vr = lds_f4(xr + 128 + (u0 + 8 * c + 4 * j4) * 4);
+              const float4 vc = lds_f4(xr + 256 + (u0 + 8 * c + 4 * j4) * 4);
+              const float4 vb = *reinterpret_cast<const float4*>(s_bhh + u0 + 8 * c + 4 * j4);
               const float xz[4] = {vz.x, vz.y, vz.z, vz.w}, xg[4] = {vr.x, vr.y, vr.z, vr.w};
               const float xc[4] = {vc.x, vc.y, vc.z, vc.w}, bh[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
@@ -426,9 +443,9 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
           }
         }
         if (h_seq && act) {
-          float* p = h_seq + (int64_t)(s_lo + t) * U;
+          float* p = h_seq + (int64_t)(s_lo + t) * U + u0;
 #pragma unroll
-          for (int j = 0; j < U / 4; ++j) st_f4(p + 4 * j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+          for (int j = 0; j < UPT / 4; ++j) st_f4(p + 4 * j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
         }
       }
       PROF(c1 = clock64(); p_gate += c1 - c0;)
@@ -446,28 +463,18 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
     }
     PROF(c0 = clock64(); ++p_tiles;)
     // ---- tile boundary: results out, the next tile's state in, its first MMA and xp gather
-    if (s_d >= 0 && direct_out) {
-      float* p = out + (int64_t)s_d * U;
+    if (s_d >= 0) {
+      float* p = out + (int64_t)s_d * U + u0;
 #pragma unroll
-      for (int j = 0; j < U / 4; ++j) st_f4(p + 4 * j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
-    } else if (s_d >= 0) {                                 // the row's xp has been consumed: park the new state there
-#pragma unroll
-      for (int j = 0; j < U / 4; ++j)
-        *reinterpret_cast<float4*>(my_row + 16 * j) = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-      fence_async_smem();
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (int64_t)s_d * U),
-                   "r"(smem_u32(my_row)), "r"(U * 4)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      for (int j = 0; j < UPT / 4; ++j) st_f4(p + 4 * j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
     }
     if (tile + tile_stride < ntiles) {
 #pragma unroll
-      for (int j = 0; j < U / 4; ++j) {
+      for (int j = 0; j < UPT / 4; ++j) {
         h[4 * j] = h0n[j].x; h[4 * j + 1] = h0n[j].y; h[4 * j + 2] = h0n[j].z; h[4 * j + 3] = h0n[j].w;
       }
       store_a();
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the result store has read this thread's row ...
-      wsync();                                             // ... before any loader lane refills it; s_max is visible
+      wsync();                                             // every A row is written; s_max of the next tile is visible
       par ^= 1;
       maxlen = max(max(s_max[g][par][0], s_max[g][par][1]), max(s_max[g][par][2], s_max[g][par][3]));
       plan = plan_n;
@@ -485,7 +492,6 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_proj_kernel(
     for (int i = 0; i < 10; ++i) atomicAdd(&pj_prof[i], (unsigned long long)v[i]);
     atomicAdd(&pj_prof[10], 1ull);
   })
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");             // every result row has left the SM
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512u);
@@ -541,17 +547,20 @@ extern "C" int ign_gru_seq_proj(const int32_t* steps_rowptr, const int32_t* step
   }
   // 2. the walk
   const size_t smem = 1024 + 2 * (size_t)BIMG + WALKERS * (size_t)STAGE;
-  IGN_CUDA(cudaFuncSetAttribute(gru_seq_proj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  IGN_CUDA(cudaFuncSetAttribute(gru_seq_proj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int opt = getenv("IGN_PROJ_OPT") ? atoi(getenv("IGN_PROJ_OPT")) : ((500 << 8) | 1);
-  const int64_t nctas = ign_cdiv(ign_cdiv(num_dst, ROWS), WALKERS);
-  const int grid = (int)(nctas < sms ? nctas : sms);
-  if (fast)
-    gru_seq_proj_kernel<true><<<grid, THREADS, smem, st>>>(steps, tb, h0, num_dst, recurrent_kernel, bias, out, h_seq,
-                                                           reinterpret_cast<const int4*>(meta), opt);
-  else
-    gru_seq_proj_kernel<false><<<grid, THREADS, smem, st>>>(steps, tb, h0, num_dst, recurrent_kernel, bias, out, h_seq,
-                                                            reinterpret_cast<const int4*>(meta), opt);
+  static const int upt = getenv("IGN_PROJ_UPT") ? atoi(getenv("IGN_PROJ_UPT")) : 32;
+  auto launch = [&](auto kern, int threads) -> int {
+    IGN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int opt_ = getenv("IGN_PROJ_OPT") ? atoi(getenv("IGN_PROJ_OPT")) : (500 << 8);
+    const int64_t nctas_ = ign_cdiv(ign_cdiv(num_dst, ROWS), WALKERS);
+    const int grid_ = (int)(nctas_ < sms ? nctas_ : sms);
+    kern<<<grid_, threads, smem, st>>>(steps, tb, h0, num_dst, recurrent_kernel, bias, out, h_seq,
+                                       reinterpret_cast<const int4*>(meta), opt_);
+    return IGN_OK;
+  };
+  int rc;
+  if (upt == 16) rc = fast ? launch(gru_seq_proj_kernel<true, 16>, 2 * THREADS) : launch(gru_seq_proj_kernel<false, 16>, 2 * THREADS);
+  else rc = fast ? launch(gru_seq_proj_kernel<true, 32>, THREADS) : launch(gru_seq_proj_kernel<false, 32>, THREADS);
+  if (rc) return rc;
   IGN_CHECK_LAUNCH("gru_seq_proj");
   PROF({
     unsigned long long hh[12];

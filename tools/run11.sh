@@ -1,3 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_gpu_train.py tests/test_gpu_model.py -x -q -m gpu -k "attention or unbuilt" > gpurun_out/r2_t_attn.log 2>&1; echo "pytest rc=$?"; tail -30 gpurun_out/r2_t_attn.log
+for upt in 32 16; do
+  echo "UPT=$upt"
+  IGN_PROJ_UPT=$upt timeout -s KILL 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "gru_seq or write_only" 2>&1 | tail -2
+  IGN_PROJ_UPT=$upt timeout -s KILL 300 python tools/ordered_update_bench.py 2>&1 | grep -E "hoisted"
+done
