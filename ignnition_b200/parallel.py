@@ -88,6 +88,30 @@ def node_bounds(n: int, world: int) -> List[int]:
     return [(r * n) // world for r in range(world + 1)]
 
 
+def chunk_cuts(n_rows: int, chunks: int, growth: float, tile: int = 128) -> List[int]:
+    """Row cuts [0, ..., n_rows] of the 'copy' exchange: at most ``chunks`` chunks on ``tile``-row boundaries whose sizes
+    form a geometric series of ratio ``growth`` (> 1: small first chunk, the copy engine starts early; < 1: small last
+    chunk, little exchange left after the last kernel)."""
+    tiles = -(-n_rows // tile)
+    k = max(1, min(int(chunks), tiles))
+    weights = [float(growth) ** c for c in range(k)]
+    acc, marks = 0.0, [0]
+    for wgt in weights:
+        acc += wgt
+        marks.append(int(round(tiles * acc / sum(weights))))
+    marks[-1] = tiles
+    return sorted({min(n_rows, m * tile) for m in marks} | {n_rows})
+
+
+def exchange_growth(world: int, row_bytes: int, edges_per_row: float, f_in: int,
+                    peer_gbs: float = 745.0, kernel_gbs: float = 4700.0) -> float:
+    """(push time per row) / (kernel time per row) from the measured rates (profiles/r2_p2p_rate.md, r2_agg_gru.md):
+    copy engine 745 GB/s out per GPU, fused update 4.7 TB/s of algorithmic bytes; clamped to [0.25, 3]."""
+    t_push = (world - 1) * row_bytes / (peer_gbs * 1e9)
+    t_kern = (edges_per_row * (4 + 4 * f_in) + 2 * row_bytes + 4) / (kernel_gbs * 1e9)
+    return min(3.0, max(0.25, t_push / t_kern))
+
+
 def split_counts(owner_rowptr: Sequence[int]) -> List[int]:
     return [int(owner_rowptr[r + 1]) - int(owner_rowptr[r]) for r in range(len(owner_rowptr) - 1)]
 
@@ -406,25 +430,10 @@ class PartitionedEngine:
             self._copy_streams.append(torch.cuda.Stream(device=self.engine.device))
         streams = self._copy_streams[:max(1, self.copy_streams)]
         row_bytes = width * 4
-        # chunk bounds on 128-row tiles of the update kernel
-        tiles = -(-n // 128)
-        k = max(1, min(self.chunks, tiles))
         growth = self.growth
         if growth <= 0.0:
-            # measured rates (profiles/r2_p2p_rate.md, r2_agg_gru.md): copy engine 745 GB/s out per GPU, fused update
-            # 4.7 TB/s of algorithmic bytes
-            f_in = src_states.shape[1]
-            e_rows = float(col.numel()) / max(n, 1)
-            t_push = (self.world - 1) * row_bytes / 745e9
-            t_kern = (e_rows * (4 + 4 * f_in) + 2 * row_bytes + 4) / 4.7e12
-            growth = min(3.0, max(0.25, t_push / t_kern))
-        weights = [growth ** c for c in range(k)]
-        acc, marks = 0.0, [0]
-        for wgt in weights:
-            acc += wgt
-            marks.append(int(round(tiles * acc / sum(weights))))
-        marks[-1] = tiles
-        cuts = sorted({min(n, m * 128) for m in marks} | {n})
+            growth = exchange_growth(self.world, row_bytes, float(col.numel()) / max(n, 1), int(src_states.shape[1]))
+        cuts = chunk_cuts(n, self.chunks, growth)
         trace = getattr(self, "trace", None)             # profiling: [(label, start event, end event)] of one update
         def mark(stream=None):
             ev = torch.cuda.Event(enable_timing=True)

@@ -71,3 +71,26 @@ def test_data_parallel_gradient_rule_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-12
+
+
+def test_partition_host_logic():
+    """destination-range bounds and the row chunks of the copy-engine exchange (ignnition_b200.parallel): pure host
+    logic of the partitioned graph, no GPU"""
+    from ignnition_b200.parallel import chunk_cuts, exchange_growth, node_bounds, shard_bounds
+    for n, w in ((10, 3), (9_999_360, 8), (5, 8), (0, 2)):
+        b = node_bounds(n, w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        sizes = [b[i + 1] - b[i] for i in range(w)]
+        assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1
+    g8 = exchange_growth(8, 256, 20.0, 64)
+    g2 = exchange_growth(2, 256, 20.0, 64)
+    assert 1.8 < g8 < 2.2 and 0.25 <= g2 < 0.35            # NVLink is the longer leg at 8 GPUs, the kernel at 2
+    for n, k, g in ((1_249_920, 4, g8), (4_999_680, 4, g2), (1000, 8, 1.0), (50, 4, 2.0), (0, 4, 2.0)):
+        cuts = chunk_cuts(n, k, g)
+        assert cuts[0] == 0 and cuts[-1] == n and cuts == sorted(set(cuts)) and len(cuts) - 1 <= max(k, 1)
+        assert all(c % 128 == 0 for c in cuts[:-1])
+    c8 = chunk_cuts(1_249_920, 4, g8)
+    assert c8[1] - c8[0] < c8[-1] - c8[-2]                  # growing chunks: the copy engine starts early
+    c2 = chunk_cuts(4_999_680, 4, g2)
+    assert c2[1] - c2[0] > c2[-1] - c2[-2]                  # shrinking chunks: little exchange left at the end
+    assert shard_bounds([1.0] * 10, 3) == [(0, 3), (3, 6), (6, 10)] or sum(hi - lo for lo, hi in shard_bounds([1.0] * 10, 3)) == 10
