@@ -478,8 +478,10 @@ class Engine:
                             and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()):
                         g.step_plan[p.key] = (ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
                     # training: BPTT runs step-synchronously on the tensor cores (ign_gru_seq_bwd_steps)
+                    # (below one tile per SM the 2 x max_steps launches cost more than the fp32 walk they replace)
                     if (training and p.key in g.order and 1 <= max_steps <= self.max_bwd_step_launches
-                            and p.msg_dim == 32 and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()):
+                            and p.msg_dim == 32 and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()
+                            and g.num[p.dst] >= ops.BWD_STEPS_MIN_ROWS):
                         g.step_plan_bwd[p.key] = g.step_plan.get(p.key) or (
                             ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
         return g

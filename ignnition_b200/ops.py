@@ -250,6 +250,8 @@ def gru_seq_steps(plan, meta, srcs: List[torch.Tensor], h0, kernel, rkernel, bia
 
 # fewer destination rows than one 128-row tile per SM: the update is bound by launches, not by the kernels
 SMALL_ROWS = 148 * 128
+# destinations from which the step-synchronous tensor-core BPTT (2 launches per step) beats the fp32 walk (one launch)
+BWD_STEPS_MIN_ROWS = int(os.environ.get("IGN_BWD_STEPS_MIN_ROWS", "250000"))      # measured crossover: 186 k .. 373 k paths
 
 
 def gru_seq_proj_pays(n_steps: int, srcs, units: int, meta, n_dst: int = 1 << 30) -> bool:
