@@ -103,6 +103,7 @@ class Engine:
         self.adjacencies = [AdjacencySpec(a[0], a[1], a[2], a[3] == "True") for a in model.get_adjecency_info()]
         self._adj_by_name = {a.name: a for a in self.adjacencies}
         self._msg_adjacencies = list(self.adjacencies)
+        self.bwd_steps_min_rows = ops.BWD_STEPS_MIN_ROWS   # below: the fp32 BPTT walk (one launch) instead of 2 launches per step
         self._needs_perm = set()
         self.plans: List[List[_MPPlan]] = []
         self.sequences: List[SequenceSpec] = []
@@ -481,7 +482,7 @@ class Engine:
                     # (below one tile per SM the 2 x max_steps launches cost more than the fp32 walk they replace)
                     if (training and p.key in g.order and 1 <= max_steps <= self.max_bwd_step_launches
                             and p.msg_dim == 32 and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()
-                            and g.num[p.dst] >= ops.BWD_STEPS_MIN_ROWS):
+                            and g.num[p.dst] >= self.bwd_steps_min_rows):
                         g.step_plan_bwd[p.key] = g.step_plan.get(p.key) or (
                             ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
         return g

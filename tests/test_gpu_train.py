@@ -232,6 +232,7 @@ def test_full_size_gradients_tensor_core_vs_fp32_backward():
         batch = assemble_tiled(base, n, eng.entities, eng.features, eng.adjacencies, eng.sequences, fns)
         batch.arrays["labels"] = np.tile(lab, n)
         eng.max_bwd_step_launches = 64 if tensor_core_bwd else 0
+        eng.bwd_steps_min_rows = 0           # exercise the tensor-core BPTT whatever the size
         prev = ops.set_tensor_cores(True)
         try:
             graph = eng.prepare(batch, training=True)
@@ -297,6 +298,7 @@ def test_full_size_qsize_properties_inference_and_training():
         b = assemble_tiled(base, n_rep, eng.entities, eng.features, eng.adjacencies, eng.sequences, fns)
         b.arrays["labels"] = np.tile(lab, n_rep)
         eng.max_bwd_step_launches = 64 if tensor_core_bwd else 0
+        eng.bwd_steps_min_rows = 0           # exercise the tensor-core BPTT whatever the size
         prev = ops.set_tensor_cores(True)
         try:
             graph = eng.prepare(b, training=True)
