@@ -40,7 +40,10 @@ using namespace ign_tc;
 namespace {
 PROF(__device__ unsigned long long pj_prof[12];)
 
-constexpr int WALKERS = 3;
+#ifndef IGN_PROJ_WALKERS
+#define IGN_PROJ_WALKERS 3
+#endif
+constexpr int WALKERS = IGN_PROJ_WALKERS;      // (-DIGN_PROJ_WALKERS=1|2: phase-profile probes, profiles/r2_gru_seq_proj.md)
 constexpr int WTHREADS = 128;                              // 4 warps = the 4 TMEM lane quarters
 constexpr int THREADS = WALKERS * WTHREADS;
 constexpr int ROWS = 128;                                  // destinations per tile = UMMA M
