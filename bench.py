@@ -33,7 +33,7 @@ WORKLOADS = {
     "routenet_geant2_b4096": ("routenet_geant2", "geant2", False, 4096),      # BASELINE config 3 (default)
     "routenet_nsfnet_b4096": ("routenet_nsfnet", "nsfnet", False, 4096),      # config 1 shape, batched
     "qsize_nsfnet_b4096": ("qsize_nsfnet", "nsfnet", True, 4096),             # config 2
-    "routenet_synth50_b256": ("routenet_nsfnet", "synth50", False, 256),      # config 4 shape (use with --train)
+    "routenet_synth50_b256": ("routenet_synth50", "synth50", False, 256),     # config 4 shape (use with --train)
 }
 DEFAULT_WORKLOAD = "routenet_geant2_b4096"
 
@@ -41,13 +41,6 @@ DEFAULT_WORKLOAD = "routenet_geant2_b4096"
 def load_case(name):
     fixture, shape, qsize, n = WORKLOADS[name]
     g = json.load(open(os.path.join(ROOT, "tests", "golden", fixture + ".json")))
-    if shape == "synth50":            # no committed fixture: same model json, topology from the seeded generator
-        from ignnition_b200 import ModelDescription, synthetic
-        from ignnition_b200.generator import sample_to_tensors
-        md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
-        t, _ = sample_to_tensors(synthetic.routenet_sample("synth50", 0, 0), [f.name for f in md.get_all_features()],
-                                 "delay", md.get_adjecency_info(), [], [], True)
-        g = dict(g, reference_tensors=[t])
     return g, shape, qsize, n
 
 

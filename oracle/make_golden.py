@@ -125,7 +125,10 @@ def main():
         "qsize_hand": (qs_json, [HAND]),
         "qsize_nsfnet": (qs_json, [synthetic.routenet_sample("nsfnet", 0, 0, qsize=True)]),
         "routenet_geant2": (rn_json, [synthetic.routenet_sample("geant2", 0, 0)]),
+        # BASELINE config 4 shape (50 nodes, ~2.4 k paths): the training benchmark's topology
+        "routenet_synth50": (rn_json, [synthetic.routenet_sample("synth50", 0, 0)]),
     }
+    recipes = {"routenet_geant2": ["geant2", 0, 0], "routenet_synth50": ["synth50", 0, 0]}   # samples too big to store
     for name, (mj, samples) in cases.items():
         got, meta = run_reference_generator(gen, jo, mj, samples)
         assert len(got) == len(samples), (name, len(got))
@@ -136,12 +139,12 @@ def main():
             "model": os.path.relpath(mj, REF),
             "model_json": model_json,
             "reference_meta": meta,
-            "samples": samples if name != "routenet_geant2" else None,
-            "sample_recipe": None if name != "routenet_geant2" else ["geant2", 0, 0],
+            "samples": samples if name not in recipes else None,
+            "sample_recipe": recipes.get(name),
             "reference_tensors": [to_jsonable(d) for d, _ in got],
             "reference_labels": [list(map(float, y)) for _, y in got],
         }
-        if name != "routenet_geant2":
+        if name not in recipes:
             fixture["oracle_float"] = [float_golden(model_json, meta["dimensions"], d) for d, _ in got]
         path = os.path.join(out_dir, name + ".json")
         with open(path, "w") as fh:

@@ -42,7 +42,7 @@ def setup(case, n_samples=None):
     return g, dims, eng, Trainer(eng), w, tens, labels
 
 
-@pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet"])
+@pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet", "routenet_synth50"])
 def test_gradients_match_autograd(case):
     g, dims, eng, tr, w, tens, labels = setup(case)
     graph = eng.prepare(tens, labels=labels, training=True)

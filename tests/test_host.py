@@ -16,7 +16,7 @@ from ignnition_b200.generator import interleave_indices, make_indices, sample_di
 from ignnition_b200.model_description import ModelDescription, ModelDescriptionError
 from oracle import ignnition_oracle as orc
 
-CASES = ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet", "routenet_geant2"]
+CASES = ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet", "routenet_geant2", "routenet_synth50"]
 
 
 def _samples(g):

@@ -1,3 +1,5 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests -q -m gpu > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest_gpu.log
+timeout -s KILL 900 python -m pytest tests/test_gpu_train.py -x -q -m gpu -k "match_autograd" 2>&1 | tail -4
+python bench.py --workload routenet_synth50_b256 --train --no-also --steps 10 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('synth50 train', d['config'], round(d['ms_per_step'],3), round(d['value']))"
