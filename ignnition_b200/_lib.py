@@ -105,6 +105,7 @@ SIGNATURES = {
     "ign_flag_compact": (_int, [_p, _i64, _int, _p, _p, _p, _sz, _p]),
     "ign_rows_put": (_int, [_p, _p, _i64, _int, _p, _p]),
     "ign_peer_copy": (_int, [_p, _p, _sz, _p]),
+    "ign_rows_unpack": (_int, [_p, _p, _i64, _int, _p, _p]),
     "ign_index_range_check": (_int, [_p, _i64, _i64, _p, _p]),
 }
 

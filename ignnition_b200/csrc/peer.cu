@@ -57,6 +57,19 @@ __global__ void rows_put_kernel(const float* __restrict__ src, const int* __rest
   }
 }
 
+// dst[rows[i], :] = packed[i, :]: the receiving side of a packed boundary exchange
+__global__ void rows_unpack_kernel(const float* __restrict__ packed, const int* __restrict__ rows, int64_t n, int width,
+                                   float* __restrict__ dst) {
+  const int q = width / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = n * q;
+  for (int64_t j = i; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = j / q;
+    const int c = (int)(j - k * q) * 4;
+    st_f4(dst + (int64_t)rows[k] * width + c, ld_stream_f4(packed + k * width + c));
+  }
+}
+
 inline unsigned grid_for(int64_t n) { return (unsigned)(n > 0 ? ign_cdiv(n, 256) : 1); }
 
 }  // namespace
@@ -142,5 +155,18 @@ extern "C" int ign_peer_copy(void* dst, const void* src, size_t bytes, void* str
   if (bytes == 0) return IGN_OK;
   IGN_REQUIRE(dst && src, IGN_ERR_INVALID, "IGNNITION: peer_copy: null pointer");
   IGN_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ign_stream(stream)));
+  return IGN_OK;
+}
+
+extern "C" int ign_rows_unpack(const float* packed, const int32_t* rows, int64_t n_rows, int width, float* dst,
+                               void* stream) {
+  IGN_REQUIRE(n_rows >= 0 && width > 0 && width % 4 == 0, IGN_ERR_INVALID, "IGNNITION: rows_unpack: bad shape");
+  if (n_rows == 0) return IGN_OK;
+  IGN_REQUIRE(packed && rows && dst, IGN_ERR_INVALID, "IGNNITION: rows_unpack: null pointer");
+  const int64_t total = n_rows * (width / 4);
+  int64_t blocks = ign_cdiv(total, 256);
+  if (blocks > IGN_NUM_SMS * 16) blocks = IGN_NUM_SMS * 16;
+  rows_unpack_kernel<<<(unsigned)blocks, 256, 0, ign_stream(stream)>>>(packed, rows, n_rows, width, dst);
+  IGN_CHECK_LAUNCH("rows_unpack");
   return IGN_OK;
 }

@@ -640,6 +640,12 @@ def segment_max_bwd(rowptr, idx, perm, rows, agg, d_agg, n_edges: int):
     return d_msg
 
 
+def rows_unpack(packed, rows, dst):
+    """dst[rows[i]] = packed[i] (ign_rows_unpack)."""
+    lib = _lib.load()
+    _lib.check(lib.ign_rows_unpack(_f(packed), _i(rows), rows.numel(), dst.shape[1], _f(dst), _stream()), "rows_unpack")
+
+
 def peer_copy(dst_ptr: int, src_ptr: int, nbytes: int):
     """``nbytes`` from ``src_ptr`` to ``dst_ptr`` (raw device addresses; dst usually a peer-mapped buffer) by the copy
     engine, on the current stream."""

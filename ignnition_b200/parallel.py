@@ -31,8 +31,11 @@ Two ways the generated model shards:
                 the barrier that orders "all tiles landed" before the next gather.  Kept as the measured
                 counter-example: the stores starve behind the SM's own gather traffic (12.8 ms per
                 iteration at 2 GPUs against 8.3 ms of ``nccl``).
-  ``boundary``  like ``peer``, but only the rows a peer's edges actually read are sent
-                (``ign_rows_put`` per peer from lists built once): what a graph with locality needs.
+  ``boundary``  only the rows a peer's edges actually read are sent (lists built once): what a graph with
+                locality needs.  The rows for all peers are packed into one contiguous block (one
+                ``ign_gather_concat``), the copy engine moves each peer's slice into that peer's inbox
+                (``ign_peer_copy``), and after the barrier the receiver scatters its inbox
+                (``ign_rows_unpack``): two kernels and world - 1 copies per update, whatever the number of rows.
   ``nccl``      the baseline: the kernel writes the owner's rows locally, then
                 ``ncclAllGather`` (``torch.distributed.all_gather_into_tensor``) fills the rest.
 
@@ -251,6 +254,7 @@ class PartitionedEngine:
         self.cur: Dict[str, int] = {}
         self.send_rows: Dict[str, List[Optional[object]]] = {}
         self.recv_rows: Dict[str, int] = {}         # boundary exchange: rows this rank receives per update
+        self.bnd: Dict[str, dict] = {}              # boundary exchange: packed send / receive lists, inboxes, offsets
         self.n_edges: Dict[str, int] = {}
         self.exchanged_bytes = 0          # bytes this rank received over NVLink in message_passing()
         self._flag = None
@@ -357,6 +361,23 @@ class PartitionedEngine:
             for p in range(self.world):
                 self.send_rows[e][p] = got[off:off + recv[p]].contiguous() if recv[p] else None
                 off += recv[p]
+            # packed exchange: `got` is the concatenation (by peer) of the rows this rank sends, `want` the concatenation
+            # (by owner) of the rows it receives = the layout of its inbox; every sender needs the offset of its segment
+            # in every receiver's inbox
+            recv_off = [0]
+            for c_ in counts:
+                recv_off.append(recv_off[-1] + c_)
+            table = torch.tensor(recv_off[:-1], dtype=torch.int64, device=dev)
+            all_off = [torch.empty_like(table) for _ in range(self.world)]
+            dist.all_gather(all_off, table, group=self.group)
+            off_at = [int(all_off[p][self.rank].item()) for p in range(self.world)]
+            send_off = [0]
+            for c_ in recv:
+                send_off.append(send_off[-1] + c_)
+            width = self.engine.hidden[e]
+            self.bnd[e] = {"send_all": got, "send_off": send_off, "send_cnt": recv, "recv_all": want, "off_at": off_at,
+                           "inbox": [PeerBuffer(max(sum(counts), 1), width, dev, self.group) for _ in range(2)],
+                           "turn": 0}
 
     def _barrier(self):
         """Orders "every rank's stores have landed" before the next reads: a 4-byte NCCL all-reduce on the
@@ -407,12 +428,22 @@ class PartitionedEngine:
                 self._all_gather(dst, nxt)
                 self.exchanged_bytes += (self.num_global[dst] - (hi - lo)) * width * 4
             elif self.exchange == "boundary":
-                for r in range(self.world):
-                    rows = self.send_rows[dst][r]
-                    if rows is not None:
-                        ops.rows_put(bufs.tensor, rows, bufs.ptrs[r])
+                bd = self.bnd[dst]
+                inbox = bd["inbox"][bd["turn"]]
+                bd["turn"] ^= 1
+                n_send = int(bd["send_all"].numel())
+                if n_send:
+                    packed = ops.gather_concat([bufs.tensor], [bd["send_all"]], n_send)
+                    for j in range(1, self.world):
+                        r = (self.rank + j) % self.world
+                        cnt = bd["send_cnt"][r]
+                        if cnt:
+                            ops.peer_copy(inbox.ptrs[r] + bd["off_at"][r] * width * 4,
+                                          packed.data_ptr() + bd["send_off"][r] * width * 4, cnt * width * 4)
                 self.exchanged_bytes += self.recv_rows.get(dst, 0) * width * 4
                 self._barrier()
+                if int(bd["recv_all"].numel()):
+                    ops.rows_unpack(inbox.tensor, bd["recv_all"], bufs.tensor)
             else:
                 self.exchanged_bytes += (self.num_global[dst] - (hi - lo)) * width * 4
                 self._barrier()
@@ -522,5 +553,9 @@ class PartitionedEngine:
         for bufs in self.full.values():
             for b in bufs:
                 b.close()
+        for bd in self.bnd.values():
+            for b in bd["inbox"]:
+                b.close()
         self.full = {}
+        self.bnd = {}
         self.csr = {}

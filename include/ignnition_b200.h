@@ -498,6 +498,10 @@ int ign_flag_compact(const int32_t* flags, int64_t n, int add, int32_t* out, int
                      size_t ws_bytes, void* stream);
 /* dst[rows[i], :] = src[rows[i], :] for a [*, width] fp32 array; dst may be a peer-mapped buffer */
 int ign_rows_put(const float* src, const int32_t* rows, int64_t n_rows, int width, float* dst, void* stream);
+/* dst[rows[i], :] = packed[i, :]: the receiving side of the PACKED boundary exchange (the sender gathers the rows a
+ * peer reads into one contiguous block with ign_gather_concat, the copy engine moves the block with ign_peer_copy
+ * into the peer's inbox, the peer scatters it here) */
+int ign_rows_unpack(const float* packed, const int32_t* rows, int64_t n_rows, int width, float* dst, void* stream);
 /* dst[0 .. bytes) = src[0 .. bytes) by the COPY ENGINE (cudaMemcpyAsync), dst usually a peer-mapped buffer: the
  * exchange of finished row chunks while the update kernel works on the next chunk.  Stores issued by SMs whose
  * memory pipes are busy with a gather reach a peer at 30-70 GB/s, the copy engine at 750 GB/s and without slowing
