@@ -373,9 +373,22 @@ __global__ void __launch_bounds__(THREADS, 1) gru_seq_bwd_kernel(
 
 template <typename KernelT>
 int bwd_grid(KernelT k, size_t smem, int64_t ntiles, int* grid) {
-  // (per template instantiation and per device: see IGN_ONCE_PER_DEVICE)
+  // once per (kernel, device): kernels of one signature share this instantiation, and function attributes are per device
+  static thread_local const void* done_fn[16];
+  static thread_local int done_dev[16];
   const void* fn = reinterpret_cast<const void*>(k);
-  if (IGN_ONCE_PER_DEVICE()) IGN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int cur = 0;
+  cudaGetDevice(&cur);
+  bool seen = false;
+  int slot = -1;
+  for (int i = 0; i < 16; ++i) {
+    if (done_fn[i] == fn && done_dev[i] == cur) { seen = true; break; }
+    if (!done_fn[i] && slot < 0) slot = i;
+  }
+  if (!seen) {
+    IGN_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (slot >= 0) { done_fn[slot] = fn; done_dev[slot] = cur; }
+  }
   int sms = IGN_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   *grid = (int)(ntiles < sms ? ntiles : sms);

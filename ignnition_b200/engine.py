@@ -591,11 +591,13 @@ class Engine:
             srcs = []
             for k, a in enumerate(p.adjs):
                 srcs.append(msgs[k] if msgs[k] is not None else state[a.src])
+            concat_widths = None
             if p.concat2:
+                if tape is not None and any(has_msg):
+                    raise RuntimeError("IGNNITION: training through message neural networks that feed a concat "
+                                       "aggregation along the feature axis is not built")
+                concat_widths = [int(s_.shape[1]) for s_ in srcs]
                 srcs = [ops.gather_concat(srcs, g.partner[p.key], int(g.partner[p.key][0].numel()))]
-            if p.concat2 and tape is not None:
-                raise RuntimeError("IGNNITION: training through the concat aggregation along the feature axis "
-                                   "is not built")
             h_seq = None
             if tape is not None:
                 h_seq = torch.empty(steps.numel(), h.shape[1], dtype=torch.float32, device=self.device)
@@ -606,7 +608,7 @@ class Engine:
                 ops.gru_seq(rowptr_s, steps, g.order.get(p.key), srcs, h, K, R, B, out=out, h_seq=h_seq,
                             meta=g.meta.get(p.key))
             if tape is not None:          # the rows the walk read: source states, or the message network's rows
-                tape.append(("seq_gru", p, list(srcs), h, h_seq))
+                tape.append(("seq_gru", p, list(srcs), h, h_seq, concat_widths))
             return out
 
         # aggregating kinds

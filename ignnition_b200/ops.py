@@ -266,12 +266,88 @@ def gru_seq_proj_pays(n_steps: int, srcs, units: int, meta, n_dst: int = 1 << 30
     return sum(int(s.shape[0]) for s in srcs) * 2 <= n_steps
 
 
+def _seq_generic_plan(steps_rowptr, steps):
+    """Step-major plan of an ordered update for the generic (any width) path: destinations by descending length, per
+    step t the entries of the nt[t] destinations that have one (ign_length_order / ign_seq_meta / ign_seq_step_plan).
+    The per-step counts come to the host once (this path is a fallback: a sync per update)."""
+    order = length_order(steps_rowptr)
+    meta = seq_meta(steps_rowptr, steps, order)
+    n = steps_rowptr.numel() - 1
+    max_steps = int(meta[:n, 2].max().item()) if n else 0
+    if max_steps == 0:
+        return meta, 0, [], [], None
+    nt, off, steps_t = seq_step_plan(meta, steps, max_steps)
+    return meta, max_steps, nt.cpu().tolist(), off.cpu().tolist(), steps_t
+
+
+def _seq_generic_rows(srcs, entries):
+    """messages of one step: rows of the source arrays named by step entries ((source << 28) | row, -1 = zero row)"""
+    m = entries.numel()
+    if len(srcs) == 1:
+        return gather_concat([srcs[0]], [torch.where(entries >= 0, entries & 0x0FFFFFFF, entries)], m)
+    x = None
+    for k, s_k in enumerate(srcs):
+        idx = torch.where((entries >= 0) & ((entries >> 28) == k), entries & 0x0FFFFFFF, torch.full_like(entries, -1))
+        part = gather_concat([s_k], [idx], m)
+        if x is None:
+            x = part
+        else:
+            axpy(1.0, part, x)
+    return x
+
+
+def gru_seq_generic(steps_rowptr, steps, srcs, h0, kernel, rkernel, bias, out, h_seq=None):
+    """Ordered update for shapes the walk kernels do not cover (hidden_state_dimension is free in the reference's
+    schema; concat along the features makes messages wider than the state): step-synchronous, one gather + one GRU
+    step (ign_gru_cell or its generic composition) per step over the destinations that still have one."""
+    n = h0.shape[0]
+    meta, max_steps, nt, off, steps_t = _seq_generic_plan(steps_rowptr, steps)
+    dest, lo = meta[:n, 0].contiguous(), meta[:n, 1].contiguous()
+    hs = gather_concat([h0], [dest], n)
+    for t in range(max_steps):
+        m = nt[t]
+        if m == 0:
+            break
+        x = _seq_generic_rows(srcs, steps_t[off[t]:off[t] + m])
+        hn = gru_cell(x, hs[:m], kernel, rkernel, bias)
+        hs[:m].copy_(hn)
+        if h_seq is not None:
+            rows_unpack(hn, (lo[:m] + t).to(torch.int32), h_seq)
+    if n:
+        rows_unpack(hs, dest, out)
+    return out
+
+
+def gru_seq_bwd_generic(steps_rowptr, steps, srcs, h0, h_seq, kernel, rkernel, bias, d_out, d_steps, dh0, dk, drk, db):
+    """BPTT of gru_seq_generic: the steps backwards, ign_gru_cell_bwd (fused or generic) per step."""
+    n = h0.shape[0]
+    meta, max_steps, nt, off, steps_t = _seq_generic_plan(steps_rowptr, steps)
+    dest, lo = meta[:n, 0].contiguous(), meta[:n, 1].contiguous()
+    dhs = gather_concat([d_out], [dest], n)
+    for t in range(max_steps - 1, -1, -1):
+        m = nt[t]
+        if m == 0:
+            continue
+        x = _seq_generic_rows(srcs, steps_t[off[t]:off[t] + m])
+        h_prev = (gather_concat([h0], [dest[:m]], m) if t == 0
+                  else gather_concat([h_seq], [(lo[:m] + (t - 1)).to(torch.int32)], m))
+        dx = torch.empty_like(x)
+        dh = torch.empty_like(h_prev)
+        gru_cell_bwd(x, h_prev, kernel, rkernel, bias, dhs[:m].contiguous(), dx, dh, dk, drk, db)
+        dhs[:m].copy_(dh)
+        rows_unpack(dx, (lo[:m] + t).to(torch.int32), d_steps)
+    if n:
+        rows_unpack(dhs, dest, dh0)
+
+
 def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rkernel, bias, out=None,
             h_seq=None, meta=None):
     lib = _lib.load()
     n, units = h0.shape
     if out is None:
         out = torch.empty_like(h0)
+    if (int(srcs[0].shape[1]), int(units)) not in GRU_FUSED_SHAPES:
+        return gru_seq_generic(steps_rowptr, steps, srcs, h0, kernel, rkernel, bias, out, h_seq)
     sp = _ptr_array(srcs, torch.float32)
     if gru_seq_proj_pays(int(steps.numel()), srcs, units, meta, n):
         rows = (C.c_int64 * len(srcs))(*[int(s.shape[0]) for s in srcs])
@@ -461,6 +537,9 @@ def gru_seq_bwd(steps_rowptr, steps, order, srcs, h0, h_seq, kernel, rkernel, bi
                 dk, drk, db):
     lib = _lib.load()
     n, units = h0.shape
+    if not (int(srcs[0].shape[1]) == int(units) and int(units) in (16, 32)):
+        return gru_seq_bwd_generic(steps_rowptr, steps, srcs, h0, h_seq, kernel, rkernel, bias, d_out, d_steps, dh0,
+                                   dk, drk, db)
     sp = _ptr_array(srcs, torch.float32)
     _lib.check(lib.ign_gru_seq_bwd(_i(steps_rowptr), _i(steps), _i(order), len(srcs), sp, srcs[0].shape[1],
                                    _f(h0), _f(h_seq), n, units, _f(kernel), _f(rkernel), _f(bias),

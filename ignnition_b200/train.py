@@ -105,6 +105,14 @@ class Trainer:
                         key = "%s/%d" % (p.key, k)
                         if key in graph.csr_t:
                             continue
+                        if p.concat2:
+                            # concat along the features: row i of the walked array is [src_0[partner_0[i]] | src_1[...]],
+                            # so the transposed view of source k groups the rows by partner_k (-1 = zero block)
+                            n_rows = graph.num[a.src]
+                            keys = ops.steps_keys(graph.partner[p.key][k], 0, n_rows)
+                            rp, _, perm, _ = ops.csr_build(keys, keys, None, n_rows + 1, ops.CSR_SORT, want_perm=True)
+                            graph.csr_t[key] = (rp[:n_rows + 1], perm)
+                            continue
                         # rows a step entry can name: the source entity's, or one per edge when the walk reads the
                         # rows of a message network (entries are edge positions then)
                         n_rows = int(graph.t["src_" + a.name].numel()) if p.msg_rows else graph.num[a.src]
@@ -318,7 +326,7 @@ class Trainer:
                     rowptr, _, perm = graph.csr[a.name]
                     reduce_into(op.input[1], rowptr, perm, d_dst)
             elif kind == "seq_gru":
-                _, p, src_states, h_old, h_seq = entry
+                _, p, src_states, h_old, h_seq, concat_widths = entry
                 g_new = gstate[p.dst]
                 if g_new is None:                       # state never reaches the loss
                     continue
@@ -339,9 +347,13 @@ class Trainer:
                                     self.g(p.dst + "_update/kernel"), self.g(p.dst + "_update/recurrent_kernel"),
                                     self.g(p.dst + "_update/bias"))
                 gstate[p.dst] = dh0
+                col_off = 0
                 for k, a in enumerate(p.adjs):
                     rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]
-                    if p.msg_rows:        # one step per message row: its gradient goes back into the message network
+                    if concat_widths is not None:     # concat along the features: source k owns a block of columns
+                        reduce_into(a.src, rp_t, perm_t, ops.slice_cols(d_steps, col_off, concat_widths[k]))
+                        col_off += concat_widths[k]
+                    elif p.msg_rows:        # one step per message row: its gradient goes back into the message network
                         pending[(p.key, k)] = ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_steps)
                     else:
                         reduce_into(a.src, rp_t, perm_t, d_steps)

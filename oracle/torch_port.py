@@ -137,8 +137,12 @@ class TorchOracle:
             lens_all.append(torch.bincount(dst_idx, minlength=num_dst))
             if agg == "interleave":
                 idx_all.append(np.asarray(inp["indices_" + src["name"] + "_to_" + dst], dtype=np.int64))
-        src_input = torch.cat(blocks, dim=1)
-        final_len = sum(lens_all)
+        if agg == "concat" and int(mp["aggregation"].get("concat_axis", 1)) == 2:   # generate_model.py:496-505
+            src_input = torch.cat(blocks, dim=2)          # bigger messages, the first source's lengths
+            final_len = lens_all[0]
+        else:
+            src_input = torch.cat(blocks, dim=1)
+            final_len = sum(lens_all)
         h = state[dst]
         if mp["update"]["type"] != "recurrent_neural_network":                  # feed-forward update (:594-600)
             if agg != "sum":
@@ -181,7 +185,7 @@ class TorchOracle:
             idx = torch.as_tensor(np.concatenate(idx_all))
             tr = src_input.transpose(0, 1)
             src_input = torch.zeros_like(tr).index_put((idx,), tr).transpose(0, 1)
-        elif agg != "ordered":
+        elif agg not in ("ordered", "concat"):
             raise ValueError("torch oracle: aggregation " + agg + " is not restated here")
         out_prev = torch.zeros_like(h)
         outs = []

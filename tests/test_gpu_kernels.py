@@ -200,10 +200,39 @@ def test_gru_cell_generic_width(n, fi, u):
                         b.astype(np.float64))
     got = ops.gru_cell(dev(x), dev(h), dev(K), dev(R), dev(b)).cpu().numpy()
     assert rel_err(got, want) < RTOL
-    rp = torch.arange(n + 1, dtype=torch.int32, device="cuda")
-    st = torch.zeros(n, dtype=torch.int32, device="cuda")
-    with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
-        ops.gru_seq(rp, st, None, [dev(x)], dev(h), dev(K), dev(R), dev(b))
+    # the ordered walk at that width: two sources, zero messages, empty destinations, per-step states
+    lens = rng.randint(0, 6, n)
+    rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    n_steps = int(lens.sum())
+    if n_steps == 0:
+        return
+    rows = [max(2, n // 3), max(2, n // 5)]
+    e_src = rng.randint(0, 2, n_steps)
+    e_row = np.array([rng.randint(0, rows[k]) for k in e_src])
+    steps = ((e_src.astype(np.int64) << 28) | e_row).astype(np.int32)
+    zero = rng.rand(n_steps) < 0.1
+    steps[zero] = -1
+    states = [(rng.randn(r, fi) * 0.5).astype(np.float32) for r in rows]
+    h_seq = torch.zeros(n_steps, u, device="cuda")
+    got = ops.gru_seq(dev(rowptr, torch.int32), dev(steps, torch.int32), None, [dev(a) for a in states], dev(h), dev(K),
+                      dev(R), dev(b), h_seq=h_seq).cpu().numpy()
+    L = int(lens.max())
+    padded = np.zeros((n, L, fi))
+    d_of = np.repeat(np.arange(n), lens)
+    t_of = np.arange(n_steps) - rowptr[d_of]
+    msgs = np.zeros((n_steps, fi))
+    for k in range(2):
+        mk = (e_src == k) & ~zero
+        msgs[mk] = states[k][e_row[mk]]
+    padded[d_of, t_of] = msgs
+    K64, R64, b64 = K.astype(np.float64), R.astype(np.float64), b.astype(np.float64)
+    cell = lambda a_, h_: orc.gru_cell(a_, h_, K64, R64, b64)
+    nz = lens > 0
+    want = h.astype(np.float64).copy()
+    want[nz] = orc.masked_rnn_last(cell, padded[nz], h[nz].astype(np.float64), lens[nz])
+    assert rel_err(got, want) < RTOL
+    assert np.array_equal(got[~nz], h[~nz])
+    assert np.array_equal(h_seq.cpu().numpy()[rowptr[1:][nz] - 1], got[nz])
 
 
 @pytest.mark.parametrize("fi,u", [(32, 32), (64, 64), (16, 32)])

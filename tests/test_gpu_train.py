@@ -79,17 +79,16 @@ def test_adam_step_matches_keras_formula():
     assert tr.step == 21
 
 
-def test_training_unsupported_shapes_fail_loudly():
-    """the fused BPTT walk exists for message width == units in {16, 32}; other shapes raise (the single GRU step has a
-    generic backward: test_gru_cell_bwd_generic)"""
-    from ignnition_b200 import ops
-    z = torch.zeros(8, 64, device="cuda")
-    w = torch.zeros(64, 192, device="cuda")
-    b = torch.zeros(2, 192, device="cuda")
-    rp = torch.arange(9, dtype=torch.int32, device="cuda")
-    st = torch.zeros(8, dtype=torch.int32, device="cuda")
-    with pytest.raises(RuntimeError, match="IGNNITION.*backward pass is built for"):
-        ops.gru_seq_bwd(rp, st, None, [z], z, z.clone(), w, w, b, z, z.clone(), z.clone(), w.clone(), w.clone(), b.clone())
+def test_ordered_update_any_width_trains():
+    """an ordered (RNN) aggregation at a width the walk kernels are not built for (48): the step-synchronous generic
+    forward (gather + GRU step per step) and its BPTT, every variable's gradient vs fp64 autograd"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample
+    rng = np.random.RandomState(48)
+    samples = [_mpnn_sample(rng, n, 5) for n in (25, 3, 140)]
+    for s_ in samples:                         # ordered needs >= 1 message per destination in the reference
+        for v in s_["entities"]:
+            s_["adj"].setdefault(v, [v])
+    _grad_check(_mpnn_json("ordered", 48), samples)
 
 
 @pytest.mark.parametrize("n,f_in,units", [(300, 64, 64), (1000, 32, 64), (77, 48, 16), (5000, 64, 32)])
@@ -190,21 +189,41 @@ def test_gradients_message_network_into_ordered_aggregation():
     _grad_check(_mpnn_json("ordered", 32, "gru", True), samples)
 
 
+@pytest.mark.parametrize("axis", [1, 2])
+def test_gradients_concat_aggregation(axis):
+    """tf.gradients through Concat_aggr (generate_model.py:496-505): along the sequence (axis 1: the sources' blocks one
+    after the other) and along the features (axis 2: wider messages, walked by the generic ordered update), two source
+    entities, vs fp64 autograd"""
+    from test_gpu_model import _two_entity_json, _two_entity_sample
+    rng = np.random.RandomState(21 + axis)
+    mj = _two_entity_json({"type": "concat", "concat_axis": axis})
+    samples = [_two_entity_sample(rng, 8, 6, 12), _two_entity_sample(rng, 12, 7, 30)]
+    if axis == 2:
+        for s_ in samples:                     # equally long padded blocks (tf.concat along the features)
+            s_["lp"]["p0"] = ["l%d" % i for i in range(5)]
+            s_["np"]["p0"] = ["n%d" % i for i in range(5)]
+            s_["pl"] = {}
+            for p_, ls in s_["lp"].items():
+                for l in ls:
+                    s_["pl"].setdefault(l, []).append(p_)
+    _grad_check(mj, samples)
+
+
 def test_training_unbuilt_paths_fail_loudly():
     """paths whose backward pass does not exist raise instead of dropping gradients"""
-    from test_gpu_model import _two_entity_json, _two_entity_sample, make, tensors_of
+    from test_gpu_model import _mpnn_json, _mpnn_sample, make, tensors_of
     from ignnition_b200.generator import sample_dimensions
     from ignnition_b200.train import Trainer
-    rng = np.random.RandomState(21)
-    mj = _two_entity_json({"type": "concat", "concat_axis": 2})
-    s_ = _two_entity_sample(rng, 8, 6, 12)
-    for p_ in list(s_["lp"]):                  # equally long padded blocks (tf.concat along the features)
-        s_["np"][p_] = ["n%d" % (i % 6) for i in range(len(s_["lp"][p_]))]
-    md, eng, o64, w = make(mj, sample_dimensions(s_))
-    t, y = tensors_of(md, s_)[:2]
-    graph = eng.prepare([t], labels=[np.asarray(y, np.float32)], training=True)
+    mj = _mpnn_json("sum", 32)
+    mj["learning_options"]["optimizer"] = {"type": "Ftrl"}
+    md, eng, o64, w = make(mj, {"x": 3, "adj": 0})
     with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
-        Trainer(eng).loss_and_grads(graph)
+        Trainer(eng)
+    mj = _mpnn_json("sum", 32)
+    mj["learning_options"]["loss"] = "CosineSimilarity"
+    md, eng, o64, w = make(mj, {"x": 3, "adj": 0})
+    with pytest.raises(RuntimeError, match="IGNNITION.*not built"):
+        Trainer(eng)
 
 
 def test_full_size_gradients_tensor_core_vs_fp32_backward():
