@@ -72,9 +72,10 @@ SIGNATURES = {
     "ign_gru_gates_fwd": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
     "ign_adam_step": (_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
     "ign_attention_ws_bytes": (_sz, [_i64, _i64, _int]),
-    "ign_attention_aggregate": (_int, [_p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "ign_attention_aggregate": (_int, [_p, _p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "ign_attention_combine": (_int, [_int, _p, _p, _p, _i64, _int, _p, _p, _p, _p]),
     "ign_attention_bwd_ws_bytes": (_sz, [_i64, _i64, _int]),
-    "ign_attention_aggregate_bwd": (_int, [_p, _p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _p, _sz, _p]),
+    "ign_attention_aggregate_bwd": (_int, [_p, _p, _p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _p, _sz, _p]),
     "ign_partner_index": (_int, [_p, _p, _p, _i64, _p, _p]),
     "ign_ingest_create": (_p, [_int, _p, _int, _p, _p, _int, _p, _p, _p, _p, C.c_char_p]),
     "ign_ingest_add_sequence": (_int, [_p, _int, _p, _int, C.c_char_p]),

@@ -43,6 +43,8 @@ class DeviceGraph:
         self.meta: Dict[str, torch.Tensor] = {}
         self.max_seq: Dict[str, int] = {}                 # host-known longest list per adjacency
         self.partner: Dict[str, list] = {}               # concat axis 2: per-source row index per CSR position
+        self.host_offsets: Dict[str, np.ndarray] = {}    # per-sample row offsets per entity, host copy
+        self.attn_comb: Dict[str, tuple] = {}            # attention over several sources: (rowptr, perm, slot_col, max_len)
         self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
         self.step_plan_bwd: Dict[str, tuple] = {}        # the same plan for the step-synchronous backward pass
         self.status: Dict[str, torch.Tensor] = {}
@@ -215,9 +217,8 @@ class Engine:
                         self.sequences.append(p.seq)
                     p.msg_rows = has_msg_nn           # the walk reads message rows (edge order) through perm
                 elif agg == "attention":
-                    if len(p.adjs) != 1:
-                        raise RuntimeError("IGNNITION: attention over several sources is not built yet in the B200 "
-                                           "engine (the reference sums colliding padded columns, SURVEY quirk 7)")
+                    # several sources: one combined edge list, colliding padded columns add up (generate_model.py:523-543,
+                    # SURVEY quirk 7; csrc/attention.cu)
                     if p.msg_dim != fd:          # [m.kernel1 | h.kernel2] . attn_kernel[2 * fd, 1] must conform
                         raise RuntimeError("IGNNITION: attention needs messages as wide as the destination state "
                                            "(%d vs %d)" % (p.msg_dim, fd))
@@ -275,10 +276,20 @@ class Engine:
                 dims[op.output_name] = dims[op.input[0]]
                 self.readout.append((k, op))
             elif op.type == "product":                   # auxilary_classes.py:1072-1094
-                if op.type_product != "element_wise":
-                    raise RuntimeError("IGNNITION: product '%s' is not built yet in the B200 engine (the reference's "
-                                       "dot_product is tf.tensordot(axes=0), an outer product)" % op.type_product)
-                dims[op.output_name] = dims[op.input[0]]
+                if op.type_product == "dot_product":
+                    # tf.tensordot(a, b, axes=0): the outer product [n, Fa, m, Fb], registered with dimension 1
+                    # (generate_model.py:375-376).  A network built on that dimension only accepts a last axis of 1
+                    if dims[op.input[1]] != 1:
+                        raise RuntimeError("IGNNITION: dot_product is tf.tensordot(axes=0) in the reference and its "
+                                           "result is registered with dimension 1: the second input must be 1 wide "
+                                           "(got %d), any other last axis fails in the networks built on it"
+                                           % dims[op.input[1]])
+                    dims[op.output_name] = 1
+                elif op.type_product == "element_wise":
+                    dims[op.output_name] = dims[op.input[0]]
+                else:
+                    raise RuntimeError("IGNNITION: product '%s' is not a product of the reference's schema"
+                                       % op.type_product)
                 self.readout.append((k, op))
             elif op.type == "extend_adjacencies":        # auxilary_classes.py:1236-1265
                 dims[op.output_name[0]] = dims[op.input[0]]
@@ -425,6 +436,7 @@ class Engine:
         g.num = dict(batch.num)
         g.n_samples = batch.n_samples
         g.max_seq = dict(batch.max_seq)
+        g.host_offsets = {e: batch.arrays["offsets_" + e] for e in self.entities if "offsets_" + e in batch.arrays}
         return g
 
     def build_graph(self, g: DeviceGraph, training: bool = False, check: bool = False) -> DeviceGraph:
@@ -441,6 +453,14 @@ class Engine:
                 g.status[a.name] = status
         for stage in self.plans:
             for p in stage:
+                if p.attn and len(p.adjs) > 1:
+                    # the first source's columns are its seq, the others' start at the destination's edge count in
+                    # that source (generate_model.py:538-539): at most twice its longest list
+                    ms = [g.max_seq.get(a.name, 0) for a in p.adjs]
+                    max_len = max([ms[0], 1] + [2 * m for m in ms[1:]])
+                    g.attn_comb[p.key] = ops.attention_combine(
+                        [g.csr[a.name][0] for a in p.adjs], [g.csr[a.name][2] for a in p.adjs],
+                        [int(g.t["dst_" + a.name].numel()) for a in p.adjs], max_len) + (max_len,)
                 if p.kind != "seq_gru":
                     continue
                 if p.concat2:
@@ -637,16 +657,29 @@ class Engine:
         agg = None
         max_src = None       # (rows, index per CSR slot) the aggregation read: what the backward of a max compares
         if p.attn:      # Attention_aggr (auxilary_classes.py:278-344)
-            a = p.adjs[0]
-            rowptr, col, perm = g.csr[a.name]
-            rows, idx = (state[a.src], col) if msgs[0] is None else (msgs[0], perm)
             F = p.msg_dim
+            slot_col = None
+            if len(p.adjs) == 1:
+                a = p.adjs[0]
+                rowptr, col, perm = g.csr[a.name]
+                rows, idx = (state[a.src], col) if msgs[0] is None else (msgs[0], perm)
+                max_len = max(g.max_seq.get(a.name, 0), 1)
+            else:       # comb_src_states: the per-edge messages of all sources, one list (generate_model.py:531-541)
+                rowptr, idx, slot_col, max_len = g.attn_comb[p.key]
+                counts = [int(g.t["dst_" + a.name].numel()) for a in p.adjs]
+                rows = torch.empty(sum(counts), F, dtype=torch.float32, device=self.device)
+                off = 0
+                for k, a in enumerate(p.adjs):
+                    if counts[k] and msgs[k] is None:
+                        ops.gather_concat([state[a.src]], [g.t["src_" + a.name]], counts[k], out=rows[off:off + counts[k]])
+                    elif counts[k]:
+                        rows[off:off + counts[k]].copy_(msgs[k])
+                    off += counts[k]
             ak = self.param(dst + "_attention/attn_kernel")
             v1 = ops.dense(self.param(dst + "_attention/kernel1"), ak[:F], None, 0)
             v2 = ops.dense(self.param(dst + "_attention/kernel2"), ak[F:], None, 0)
-            max_len = max(g.max_seq.get(a.name, 0), 1)
             agg = ops.attention_aggregate(rowptr, idx, rows, ops.dense(rows, v1, None, 0), ops.dense(h, v2, None, 0),
-                                          g.t["offsets_" + dst], max_len, keep_ws=tape is not None)
+                                          g.t["offsets_" + dst], max_len, keep_ws=tape is not None, slot_col=slot_col)
             if tape is not None:
                 agg, attn_ws = agg
                 max_src = ("attn", rows, idx, v1, v2, attn_ws, h, max_len)
@@ -725,6 +758,29 @@ class Engine:
                 if tape is not None:
                     tape.append(("pool", op, red, g.t["offsets_" + ent], st[op.input[0]], st[op.output_name]))
                 continue
+            if op.type == "product" and op.type_product == "dot_product":
+                # per sample [n, Fa] (x) [m, 1] -> [n, Fa, m, 1], laid out as (n Fa m) rows of width 1: vec(a) b^T is a
+                # Dense product of inner width 1 (ign_dense); the samples' blocks follow one another
+                a, b = st[op.input[0]], st[op.input[1]]
+                ea, eb = owner.get(op.input[0]), owner.get(op.input[1])
+                if ea is None or eb is None or g is None:
+                    raise RuntimeError("IGNNITION: dot_product needs entity-shaped inputs")
+                oa, ob = self._host_offsets(g, ea), self._host_offsets(g, eb)
+                fa = int(a.shape[1])
+                sizes = [int(oa[i + 1] - oa[i]) * fa * int(ob[i + 1] - ob[i]) for i in range(g.n_samples)]
+                y = torch.empty(sum(sizes), 1, dtype=torch.float32, device=self.device)
+                pos = 0
+                for i, sz in enumerate(sizes):
+                    if sz:
+                        na, nb = int(oa[i + 1] - oa[i]), int(ob[i + 1] - ob[i])
+                        ops.dense(a[oa[i]:oa[i + 1]].view(na * fa, 1), b[ob[i]:ob[i + 1]].view(1, nb), None, 0,
+                                  out=y[pos:pos + sz].view(na * fa, nb), tensor_cores=False)
+                    pos += sz
+                st[op.output_name] = y
+                owner[op.output_name] = None
+                if tape is not None:
+                    tape.append(("outer", op, a, b, oa, ob))
+                continue
             if op.type == "product":
                 a, b = st[op.input[0]], st[op.input[1]]
                 if a.shape != b.shape:
@@ -762,6 +818,14 @@ class Engine:
         if return_states:
             return result, st
         return result
+
+    @staticmethod
+    def _host_offsets(g: DeviceGraph, entity: str):
+        """Per-sample row offsets of an entity on the host (kept by ``upload``; read back otherwise)."""
+        off = g.host_offsets.get(entity)
+        if off is None:
+            off = g.host_offsets[entity] = g.t["offsets_" + entity].cpu().numpy()
+        return [int(v) for v in off]
 
     def forward(self, g: DeviceGraph, training: bool = False, return_states: bool = False,
                 tape: Optional[list] = None):

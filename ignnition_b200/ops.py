@@ -605,8 +605,26 @@ def conv_finish(nsum, self_state, rowptr, act: int, out=None):
     return out
 
 
+def attention_combine(src_rowptrs, src_perms, edge_counts: Sequence[int], max_len: int):
+    """(rowptr, perm, slot_col) of the CSR over the concatenated edge lists of several sources
+    (ign_attention_combine; generate_model.py:523-543)."""
+    lib = _lib.load()
+    dev = src_rowptrs[0].device
+    num_dst = src_rowptrs[0].numel() - 1
+    total = int(sum(edge_counts))
+    rowptr = torch.empty(num_dst + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(max(total, 1), dtype=torch.int32, device=dev)[:total]
+    slot_col = torch.empty(max(total, 1), dtype=torch.int32, device=dev)[:total]
+    counts = (C.c_int64 * len(edge_counts))(*[int(c) for c in edge_counts])
+    _lib.check(lib.ign_attention_combine(len(edge_counts), _ptr_array(src_rowptrs, torch.int32),
+                                         _ptr_array(src_perms, torch.int32), counts, num_dst, max_len, _i(rowptr),
+                                         _i(perm) if total else None, _i(slot_col) if total else None, _stream()),
+               "attention_combine")
+    return rowptr, perm, slot_col
+
+
 def attention_aggregate(rowptr, col, rows, src_score, dst_score, sample_offsets, max_len: int, out=None,
-                        keep_ws: bool = False):
+                        keep_ws: bool = False, slot_col=None):
     lib = _lib.load()
     num_dst = rowptr.numel() - 1
     n_edges = col.numel()
@@ -616,13 +634,13 @@ def attention_aggregate(rowptr, col, rows, src_score, dst_score, sample_offsets,
         out = torch.empty(num_dst, F, dtype=torch.float32, device=rows.device)
     nbytes = lib.ign_attention_ws_bytes(n_edges, n_samples, max_len)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=rows.device)
-    _lib.check(lib.ign_attention_aggregate(_i(rowptr), _i(col), _f(rows), F, _f(src_score), _f(dst_score),
+    _lib.check(lib.ign_attention_aggregate(_i(rowptr), _i(col), _i(slot_col), _f(rows), F, _f(src_score), _f(dst_score),
                                            _i(sample_offsets), n_samples, num_dst, n_edges, max_len, _f(out),
                                            ws.data_ptr(), nbytes, _stream()), "attention_aggregate")
     return (out, ws) if keep_ws else out
 
 
-def attention_aggregate_bwd(rowptr, idx, perm, rows, g_out, sample_offsets, max_len: int, fwd_ws):
+def attention_aggregate_bwd(rowptr, idx, perm, rows, g_out, sample_offsets, max_len: int, fwd_ws, slot_col=None):
     """(d_msg [E, F], d_pre4 [E, 4], d_ds [num_dst, 1]) of ign_attention_aggregate_bwd, per-edge arrays in input edge order"""
     lib = _lib.load()
     num_dst = rowptr.numel() - 1
@@ -635,7 +653,8 @@ def attention_aggregate_bwd(rowptr, idx, perm, rows, g_out, sample_offsets, max_
     d_ds = torch.zeros(num_dst, 1, dtype=torch.float32, device=dev)
     nbytes = lib.ign_attention_bwd_ws_bytes(n_edges, n_samples, max_len)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    _lib.check(lib.ign_attention_aggregate_bwd(_i(rowptr), _i(idx), _i(perm), _f(rows), F, _f(g_out), _i(sample_offsets),
+    _lib.check(lib.ign_attention_aggregate_bwd(_i(rowptr), _i(idx), _i(perm), _i(slot_col), _f(rows), F, _f(g_out),
+                                               _i(sample_offsets),
                                                n_samples, num_dst, n_edges, max_len, fwd_ws.data_ptr(), _f(d_msg),
                                                _f(d_pre4), _f(d_ds), ws.data_ptr(), nbytes, _stream()),
                "attention_aggregate_bwd")

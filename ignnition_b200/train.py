@@ -198,21 +198,37 @@ class Trainer:
                 # Attention_aggr (auxilary_classes.py:278-344): through the column softmax and the LeakyReLU to the two
                 # score products, and through the weighted sum to the messages
                 _, rows, idx, v1, v2, attn_ws, h_dst, max_len = max_src
-                a = p.adjs[0]
-                rowptr, _, perm = graph.csr[a.name]
                 F = p.msg_dim
+                multi = len(p.adjs) > 1
+                if multi:        # one CSR over all sources' edges; rows = their per-edge messages, one list
+                    rowptr, perm, slot_col, _ = graph.attn_comb[p.key]
+                else:
+                    rowptr, _, perm = graph.csr[p.adjs[0].name]
+                    slot_col = None
                 d_msg, d_pre4, d_ds = ops.attention_aggregate_bwd(rowptr, idx, perm, rows, d_agg,
-                                                                  graph.t["offsets_" + p.dst], max_len, attn_ws)
+                                                                  graph.t["offsets_" + p.dst], max_len, attn_ws,
+                                                                  slot_col=slot_col)
                 d_v1, d_v2 = torch.zeros_like(v1), torch.zeros_like(v2)
                 tmp = torch.empty_like(h_dst)
                 ops.dense_bwd(h_dst, v2, 0, None, d_ds, tmp, d_v2, None)        # dst_score = h v2
                 add_grad(p.dst, tmp)
-                if has_msg[0]:                                                  # rows = per-edge messages (edge order)
-                    tmp = torch.empty_like(rows)
-                    ops.dense_bwd(rows, v1, 0, None, ops.slice_cols(d_pre4, 0, 1), tmp, d_v1, None)
-                    ops.axpy(1.0, tmp, d_msg)
-                    pending[(p.key, 0)] = d_msg
+                if multi or has_msg[0]:                                         # rows = per-edge messages (edge order)
+                    if rows.shape[0]:
+                        tmp = torch.empty_like(rows)
+                        ops.dense_bwd(rows, v1, 0, None, ops.slice_cols(d_pre4, 0, 1), tmp, d_v1, None)
+                        ops.axpy(1.0, tmp, d_msg)
+                    off = 0
+                    for k, a in enumerate(p.adjs):
+                        n_k = int(graph.t["dst_" + a.name].numel())
+                        part = d_msg[off:off + n_k]
+                        off += n_k
+                        if has_msg[k]:
+                            pending[(p.key, k)] = part
+                        elif n_k:                                               # gathered source states: per source row
+                            rp_t, _, perm_t = graph.csr_t[a.name]
+                            add_grad(a.src, ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, part))
                 else:                                                           # rows = source states: reduce per source row
+                    a = p.adjs[0]
                     rp_t, _, perm_t = graph.csr_t[a.name]
                     d_rows = ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_msg)
                     d_ss = ops.slice_cols(ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_pre4), 0, 1)
@@ -302,6 +318,22 @@ class Trainer:
                 if dy is not None:
                     add_grad(op.input[0], ops.mul(dy, b_in))
                     add_grad(op.input[1], ops.mul(dy, a_in))
+            elif kind == "outer":                       # dot_product = tf.tensordot(axes=0), per sample vec(a) b^T
+                _, op, a_in, b_in, oa, ob = entry
+                dy = gstate.pop(op.output_name, None)
+                if dy is not None:
+                    fa = int(a_in.shape[1])
+                    da, db = torch.zeros_like(a_in), torch.zeros_like(b_in)
+                    pos = 0
+                    for i in range(len(oa) - 1):
+                        na, nb = oa[i + 1] - oa[i], ob[i + 1] - ob[i]
+                        if na * nb:
+                            ops.dense_bwd(a_in[oa[i]:oa[i + 1]].view(na * fa, 1), b_in[ob[i]:ob[i + 1]].view(1, nb), 0, None,
+                                          dy[pos:pos + na * fa * nb].view(na * fa, nb),
+                                          da[oa[i]:oa[i + 1]].view(na * fa, 1), db[ob[i]:ob[i + 1]].view(1, nb), None)
+                        pos += na * fa * nb
+                    add_grad(op.input[0], da)
+                    add_grad(op.input[1], db)
             elif kind == "pool":                        # per-sample pooling (auxilary_classes.py:1165-1185)
                 _, op, red, offsets, x_in, pooled = entry
                 dy = gstate.pop(op.output_name, None)

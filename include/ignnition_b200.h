@@ -362,9 +362,12 @@ int ign_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float
  * per padded column s = j - rowptr[d] (zero pads included, as the reference's softmax over axis 0 does);
  * out[d] = sum_j coef_j * rows[col[j]].  src_score = rows . (kernel1 . attn_kernel[:F]) and
  * dst_score = h_dst . (kernel2 . attn_kernel[F:]) are ign_dense calls.  sample_offsets[n_samples+1] are
- * the destination entity's per-sample row offsets; max_len >= the longest destination list. */
+ * the destination entity's per-sample row offsets; max_len >= the longest destination list.
+ * slot_col (NULL for one source): the padded column of every CSR slot when several sources feed the aggregation
+ * (generate_model.py:525-543, ign_attention_combine); slots of one destination on the same column form one cell whose
+ * score is the SUM of their activated scores (tf.scatter_nd adds) and share its coefficient. */
 size_t ign_attention_ws_bytes(int64_t n_edges, int64_t n_samples, int max_len);
-int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const float* rows, int F,
+int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const int32_t* slot_col, const float* rows, int F,
                             const float* src_score, const float* dst_score, const int32_t* sample_offsets,
                             int64_t n_samples, int64_t num_dst, int64_t n_edges, int max_len, float* out,
                             void* ws, size_t ws_bytes, void* stream);
@@ -376,11 +379,20 @@ int ign_attention_aggregate(const int32_t* rowptr, const int32_t* col, const flo
  * per-edge arrays per row of `rows` (ign_segment_reduce over the transposed adjacency) and finishes the two score
  * products with ign_dense_bwd. */
 size_t ign_attention_bwd_ws_bytes(int64_t n_edges, int64_t n_samples, int max_len);
-int ign_attention_aggregate_bwd(const int32_t* rowptr, const int32_t* idx, const int32_t* perm, const float* rows, int F,
-                                const float* g_out, const int32_t* sample_offsets, int64_t n_samples, int64_t num_dst,
+int ign_attention_aggregate_bwd(const int32_t* rowptr, const int32_t* idx, const int32_t* perm, const int32_t* slot_col,
+                                const float* rows, int F, const float* g_out, const int32_t* sample_offsets, int64_t n_samples, int64_t num_dst,
                                 int64_t n_edges, int max_len, const void* fwd_ws, float* d_msg, float* d_pre4,
                                 float* d_ds, void* ws, size_t ws_bytes, void* stream);
 
+/* One CSR by destination over the edge lists of several sources (generate_model.py:523-543): row d = the sources'
+ * rows one after the other; perm[slot] = position of the slot's edge in the concatenation of the sources' input edge
+ * lists; slot_col[slot] = the edge's seq (its slot in the source's own row) for the first source, seq + the
+ * destination's edge count in that source for the others -- the reference gathers `lens` of the CURRENT source
+ * (generate_model.py:538-539), reproduced as it is.  src_rowptr[k] / src_perm[k] = CSR of source k alone (perm NULL =
+ * identity), edge_counts[k] on the host; rowptr [num_dst + 1], perm and slot_col [sum of edge_counts]. */
+int ign_attention_combine(int n_sources, const int32_t* const* src_rowptr, const int32_t* const* src_perm,
+                          const int64_t* edge_counts, int64_t num_dst, int max_len, int32_t* rowptr, int32_t* perm,
+                          int32_t* slot_col, void* stream);
 
 /* Concat_aggr with concat_axis = 2 (generate_model.py:496-505): for CSR position j of the first source
  * (destination d, padded column s = j - rowptr0[d]) the row of another source sitting at the same padded

@@ -287,6 +287,8 @@ class Oracle:
                 self.hs[op["output_name"]] = int(self.hs[op["input"][0]])
             elif op["type"] == "product" and op["type_product"] == "element_wise":
                 self.hs[op["output_name"]] = int(self.hs[op["input"][0]])
+            elif op["type"] == "product" and op["type_product"] == "dot_product":     # generate_model.py:375-376
+                self.hs[op["output_name"]] = 1
             elif op["type"] == "extend_adjacencies":
                 self.hs[op["output_name_src"]] = int(self.hs[op["input"][0]])
                 self.hs[op["output_name_dst"]] = int(self.hs[op["input"][1]])

@@ -90,9 +90,9 @@ class TorchOracle:
                        "max": lambda t: t.amax(dim=0)}[op["type_pooling"]]
                 state[op["output_name"]] = red(x).reshape(1, -1)
             elif op["type"] == "product":                                        # auxilary_classes.py:1072-1088
-                if op["type_product"] != "element_wise":
-                    raise ValueError("torch oracle: only the element-wise product is restated")
-                state[op["output_name"]] = state[op["input"][0]] * state[op["input"][1]]
+                a_, b_ = state[op["input"][0]], state[op["input"][1]]
+                state[op["output_name"]] = (torch.tensordot(a_, b_, dims=0) if op["type_product"] == "dot_product"
+                                            else a_ * b_)      # tf.tensordot(axes=0): the outer product
             elif op["type"] == "extend_adjacencies":                             # auxilary_classes.py:1236-1265
                 si = torch.as_tensor(np.asarray(inp["src_" + op["adj_list"]], dtype=np.int64))
                 di = torch.as_tensor(np.asarray(inp["dst_" + op["adj_list"]], dtype=np.int64))
@@ -104,7 +104,7 @@ class TorchOracle:
         dt = self.dtype
         num_dst = int(inp["num_" + dst])
         agg = mp["aggregation"]["type"]
-        blocks, lens_all, idx_all = [], [], []
+        blocks, lens_all, idx_all, edge_lists = [], [], [], []
         for src in mp["source_entities"]:
             src_idx = torch.as_tensor(np.asarray(inp["src_" + src["adj_vector"]], dtype=np.int64))
             dst_idx = torch.as_tensor(np.asarray(inp["dst_" + src["adj_vector"]], dtype=np.int64))
@@ -135,6 +135,7 @@ class TorchOracle:
             s = torch.zeros(num_dst, max_len, msgs.shape[1], dtype=dt).index_put((dst_idx, seq), msgs)  # scatter_nd
             blocks.append(s)
             lens_all.append(torch.bincount(dst_idx, minlength=num_dst))
+            edge_lists.append((msgs, dst_idx, seq))
             if agg == "interleave":
                 idx_all.append(np.asarray(inp["indices_" + src["name"] + "_to_" + dst], dtype=np.int64))
         if agg == "concat" and int(mp["aggregation"].get("concat_axis", 1)) == 2:   # generate_model.py:496-505
@@ -152,16 +153,18 @@ class TorchOracle:
         K, R, b = w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"], w[dst + "_update/bias"]
         if agg == "sum":
             return gru_cell(src_input.sum(dim=1), h, K, R, b)
-        if agg == "attention":              # Attention_aggr (auxilary_classes.py:278-344), single source, as-is:
-            src0 = mp["source_entities"][0]   # softmax over the DESTINATIONS per padded column, zero pads included
-            dst_idx = torch.as_tensor(np.asarray(inp["dst_" + src0["adj_vector"]], dtype=np.int64))
-            seq = torch.as_tensor(np.asarray(inp["seq_" + src0["name"] + "_" + dst], dtype=np.int64))
-            comb = src_input[dst_idx, seq]                                       # the messages back in edge order
+        if agg == "attention":              # Attention_aggr (auxilary_classes.py:278-344), as it is: softmax over the
+            # DESTINATIONS per padded column, zero pads included; several sources = one edge list, the columns of source
+            # k > 0 shifted by that source's own edge count per destination, colliding cells added by scatter_nd
+            # (generate_model.py:523-543)
+            comb = torch.cat([m for m, _, _ in edge_lists], dim=0)
+            dst_idx = torch.cat([d for _, d, _ in edge_lists])
+            seq = torch.cat([q if k == 0 else q + lens_all[k][d] for k, (_, d, q) in enumerate(edge_lists)])
             k1, k2, ak = w[dst + "_attention/kernel1"], w[dst + "_attention/kernel2"], w[dst + "_attention/attn_kernel"]
             a_in = torch.cat([comb @ k1, h[dst_idx] @ k2], dim=1) @ ak
             a_in = torch.where(a_in > 0, a_in, 0.2 * a_in)
             mx = int(seq.max()) + 1
-            aux = torch.zeros(num_dst, mx, 1, dtype=dt).index_put((dst_idx, seq), a_in)
+            aux = torch.zeros(num_dst, mx, 1, dtype=dt).index_put((dst_idx, seq), a_in, accumulate=True)
             coef = torch.softmax(aux, dim=0)
             red = torch.zeros(num_dst, comb.shape[1], dtype=dt).index_add(0, dst_idx, comb * coef[dst_idx, seq])
             return gru_cell(red, h, K, R, b)

@@ -317,6 +317,35 @@ def test_two_source_concat_axis1_and_ordered(agg):
     assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
 
 
+def _two_source_attention(message_nn):
+    mj = _two_entity_json({"type": "attention"})
+    if message_nn:       # the links' messages come from a network over [link, path] states, the nodes' stay their states
+        mj["message_passing"]["stages"][0]["stage_mp"][0]["source_entities"][0]["message"] = [
+            {"type": "neural_network", "nn_name": "msg", "input": ["hs_source", "hs_dest"]}]
+        mj["neural_networks"].append({"nn_name": "msg", "nn_type": "feed_forward", "nn_architecture": [
+            {"type_layer": "Dense", "units": 24, "activation": "tanh"},
+            {"type_layer": "Dense", "units": 16, "activation": "None"}]})
+    return mj
+
+
+@pytest.mark.parametrize("message_nn", [False, True])
+def test_two_source_attention(message_nn):
+    """Attention over two sources (generate_model.py:523-543 + auxilary_classes.py:278-344): one edge list, the
+    second source's padded columns start at ITS OWN edge count per destination (quirk 7), so cells collide when the
+    first source sends more messages -- scatter_nd adds the colliding scores and both edges read one coefficient."""
+    rng = np.random.RandomState(31)
+    mj = _two_source_attention(message_nn)
+    samples = [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 40)]
+    assert any(len(s["lp"][p_]) > len(s["np"][p_]) for s in samples for p_ in s["lp"])      # colliding cells exist
+    md, eng, o64, w = make(mj, sample_dimensions(samples[0]))
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred, state = eng.forward(eng.prepare(tens), return_states=True)
+    want = [o64.forward(t, w, return_states=True) for t in tens]
+    for e in ("path", "link"):
+        assert rel_err(state[e].cpu().numpy(), np.concatenate([s[e] for _, s in want])) < RTOL
+    assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
+
+
 def test_two_source_concat_axis2():
     """Concat_aggr along the feature axis (generate_model.py:496-505): step t of a path reads
     [link_t | node_t] (zeros where the node block is padding), the mask keeps the FIRST source's length."""
@@ -385,7 +414,11 @@ def test_unsupported_keywords_fail_loudly():
     mj = _mpnn_json("sum")
     mj["readout"].insert(0, {"type": "product", "type_product": "dot_product", "input": ["node", "node"],
                              "output_name": "outer"})
-    with pytest.raises(RuntimeError, match="IGNNITION.*not built yet"):
+    with pytest.raises(RuntimeError, match="IGNNITION.*1 wide"):      # the reference registers the outer product as 1 wide
+        Engine(ModelDescription(mj, {"x": 3, "adj": 0}), device="cuda:0")
+    mj = _mpnn_json("sum")
+    mj["neural_networks"][0]["recurrent_type"] = "LSTM"
+    with pytest.raises(RuntimeError, match="IGNNITION.*only GRU"):
         Engine(ModelDescription(mj, {"x": 3, "adj": 0}), device="cuda:0")
     with pytest.raises(RuntimeError, match="CUDA devices only"):
         Engine(ModelDescription(_mpnn_json(), {"x": 3, "adj": 0}), device="cpu")

@@ -388,7 +388,7 @@ def test_gradients_convolution_aggregation():
     assert "node_convolution/conv_kernel" in eng.param_table
 
 
-@pytest.mark.parametrize("chain", ["pool_sum", "pool_mean", "pool_max", "edges"])
+@pytest.mark.parametrize("chain", ["pool_sum", "pool_mean", "pool_max", "edges", "outer"])
 def test_gradients_readout_operations(chain):
     """tf.gradients through the readout operations (auxilary_classes.py:1072-1265, generate_model.py:632-656) vs
     fp64 autograd, every variable: neural_network -> per-sample pooling -> predict (one graph-level label per sample),
@@ -399,8 +399,21 @@ def test_gradients_readout_operations(chain):
     mj = _mpnn_json("sum", 32)
     mj["neural_networks"].append({"nn_name": "edge_nn", "nn_type": "feed_forward", "nn_architecture": [
         {"type_layer": "Dense", "units": 20, "activation": "tanh"}]})
-    samples = [_mpnn_sample(rng, n, 4) for n in (17, 9, 120)]
-    if chain == "edges":
+    samples = [_mpnn_sample(rng, n, 4) for n in ((17, 9, 120) if chain != "outer" else (5, 1, 9))]
+    if chain == "outer":
+        # dot_product = tf.tensordot(a, b, axes=0) (auxilary_classes.py:1082): per sample the outer product
+        # [n, 32] (x) [n, 1] -> [n, 32, n, 1], registered with dimension 1; one prediction per cell
+        mj["neural_networks"].append({"nn_name": "to1", "nn_type": "feed_forward", "nn_architecture": [
+            {"type_layer": "Dense", "units": 1, "activation": "tanh"}]})
+        mj["readout"] = [
+            {"type": "neural_network", "input": ["node"], "nn_name": "to1", "output_name": "n1"},
+            {"type": "product", "type_product": "dot_product", "input": ["node", "n1"], "output_name": "cells"},
+            {"type": "predict", "input": ["cells"], "label": "y", "nn_name": "ro"},
+        ]
+        for s in samples:
+            n = len(s["entities"])
+            s["y"] = rng.randn(n * 32 * n).tolist()
+    elif chain == "edges":
         mj["readout"] = [
             {"type": "extend_adjacencies", "adj_list": "adj", "input": ["node", "node"],
              "output_name_src": "e_src", "output_name_dst": "e_dst"},
@@ -504,6 +517,18 @@ def test_optimizers_by_name(opt):
             s2 = np.maximum(0.999 * s2, np.abs(g))
             w0 -= lr / (1 - 0.9 ** t) * s1 / (s2 + eps)
     assert rel_err(eng.weights.cpu().numpy(), w0) < 2e-6
+
+
+@pytest.mark.parametrize("message_nn", [False, True])
+def test_gradients_two_source_attention(message_nn):
+    """tf.gradients through the attention over two sources with colliding padded cells (generate_model.py:523-543):
+    the cell's coefficient is shared by the edges that collide, its score gradient reaches each of them through its
+    own LeakyReLU; messages = source states (reduced per source row) or a message network's rows, vs fp64 autograd"""
+    from test_gpu_model import _two_source_attention, _two_entity_sample
+    rng = np.random.RandomState(32 + int(message_nn))
+    samples = [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 40)]
+    eng = _grad_check(_two_source_attention(message_nn), samples)
+    assert "path_attention/kernel1" in eng.param_table
 
 
 def test_generic_width_trains():

@@ -347,11 +347,12 @@ def test_cabi_rejects_oversized_and_bad_arguments_on_the_host():
     assert lib.ign_csr_build_ws_bytes(200_000_000, 10_000_000) > 3_200_000_000   # 4 x E x 4 B of sort buffers
     assert lib.ign_dense_ws_bytes(256, 256) == 8 * 2 * 256 * 128 and lib.ign_dense_ws_bytes(65, 20) == 0
     assert lib.ign_dense_bwd_ws_bytes(32, 256) == lib.ign_dense_ws_bytes(256, 32) and lib.ign_dense_bwd_ws_bytes(256, 1) == 0
-    rc = lib.ign_attention_aggregate(one, one, one, 30, one, one, one, 1, 10, 20, 4, one, one, 1 << 20, None)
+    rc = lib.ign_attention_aggregate(one, one, None, one, 30, one, one, one, 1, 10, 20, 4, one, one, 1 << 20, None)
     assert rc == -2 and "multiple of 4" in _lib.last_error()            # message width
-    rc = lib.ign_attention_aggregate(one, one, one, 32, one, one, one, 1, 10, 20, 4, one, one, 16, None)
+    rc = lib.ign_attention_aggregate(one, one, None, one, 32, one, one, one, 1, 10, 20, 4, one, one, 16, None)
     assert rc == -1 and "workspace" in _lib.last_error()
     assert lib.ign_attention_ws_bytes(1000, 4, 8) >= 4 * 8 * 16 + 1000 * 4
+    assert lib.ign_attention_combine(9, one, one, one, 4, 2, one, one, one, None) == -2       # at most 8 sources
     assert lib.ign_mul(-1, one, one, one, None) == -1 and lib.ign_mul(0, None, None, None, None) == 0
     assert lib.ign_conv_finish(one, one, one, 0, 10, 1, one, None) == -1
     assert lib.ign_partner_index(None, None, None, 5, None, None) == -1 and lib.ign_partner_index(None, None, None, 0, None, None) == 0
