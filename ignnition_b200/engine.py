@@ -65,6 +65,7 @@ class _MPPlan:
         self.msg_dim = 0
         self.concat2 = False   # concat along the feature axis: rows gathered per CSR position of source 0
         self.msg_rows = False  # ordered walk over message-MLP rows instead of source states
+        self.msg_src: List[bool] = []   # per source: its messages come from a message network (rows in edge order)
         self.attn = False      # attention aggregation: column softmax over one sample's destinations
         self.conv = False      # convolution aggregation: (sum . conv_kernel + self) / degree, activation
 
@@ -185,8 +186,9 @@ class Engine:
                                        "the same dimension, got %s" % msg_dims)
                 p.msg_dim = msg_dims[0]
                 agg = mp.aggregation.type
-                has_msg_nn = any(op.type == "feed_forward_nn" for src in mp.source_entities
-                                 for op in src.message_formation)
+                p.msg_src = [any(op.type == "feed_forward_nn" for op in src.message_formation)
+                             for src in mp.source_entities]
+                has_msg_nn = any(p.msg_src)
                 if concat2:
                     # padded blocks side by side along the FEATURE axis, lengths of the first source
                     # (generate_model.py:496-505); one GRU walk over rows gathered per step
@@ -210,12 +212,14 @@ class Engine:
                         raise RuntimeError("IGNNITION: %s aggregation needs a recurrent update" % agg)
                     p.kind = "seq_gru"
                     if len(p.adjs) > 1 or agg == "interleave":
-                        if has_msg_nn:
-                            raise RuntimeError("IGNNITION: message neural networks feeding a multi-source ordered "
-                                               "aggregation are not built yet (step table indexes source rows)")
+                        # step entries name rows of the source states, or edge positions (perm) where a message
+                        # network produced the source's messages
                         p.seq = SequenceSpec(p.key, p.dst, p.adjs, agg == "interleave")
                         self.sequences.append(p.seq)
                     p.msg_rows = has_msg_nn           # the walk reads message rows (edge order) through perm
+                    for k_, a_ in enumerate(p.adjs):
+                        if p.msg_src[k_]:
+                            self._needs_perm.add(a_.name)
                 elif agg == "attention":
                     # several sources: one combined edge list, colliding padded columns add up (generate_model.py:523-543,
                     # SURVEY quirk 7; csrc/attention.cu)
@@ -483,7 +487,7 @@ class Engine:
                     g.steps[p.key] = (rowptr, perm if p.msg_rows else col)
                 else:
                     rps = [g.csr[a.name][0] for a in p.adjs]
-                    cols = [g.csr[a.name][1] for a in p.adjs]
+                    cols = [g.csr[a.name][2 if p.msg_src[k] else 1] for k, a in enumerate(p.adjs)]
                     total = sum(int(c.numel()) for c in cols)
                     multi = g.n_samples > 1
                     g.steps[p.key] = ops.steps_build(
@@ -602,10 +606,6 @@ class Engine:
         out = torch.empty_like(h)
         msgs = [self._messages(p, k, g, state, tape) for k in range(len(p.adjs))]
         has_msg = [m is not None for m in msgs]
-        if tape is not None and any(has_msg) and p.kind == "seq_gru" and not p.msg_rows:
-            raise RuntimeError("IGNNITION: training through message neural networks that feed a multi-source ordered "
-                               "aggregation is not built")
-
         if p.kind == "seq_gru":
             rowptr_s, steps = g.steps[p.key]
             srcs = []
@@ -613,9 +613,6 @@ class Engine:
                 srcs.append(msgs[k] if msgs[k] is not None else state[a.src])
             concat_widths = None
             if p.concat2:
-                if tape is not None and any(has_msg):
-                    raise RuntimeError("IGNNITION: training through message neural networks that feed a concat "
-                                       "aggregation along the feature axis is not built")
                 concat_widths = [int(s_.shape[1]) for s_ in srcs]
                 srcs = [ops.gather_concat(srcs, g.partner[p.key], int(g.partner[p.key][0].numel()))]
             h_seq = None

@@ -105,21 +105,18 @@ class Trainer:
                         key = "%s/%d" % (p.key, k)
                         if key in graph.csr_t:
                             continue
+                        # rows a step entry can name: the source entity's, or one per edge when the walk reads the
+                        # rows of a message network (entries are edge positions then)
+                        n_rows = int(graph.t["src_" + a.name].numel()) if p.msg_src[k] else graph.num[a.src]
                         if p.concat2:
                             # concat along the features: row i of the walked array is [src_0[partner_0[i]] | src_1[...]],
                             # so the transposed view of source k groups the rows by partner_k (-1 = zero block)
-                            n_rows = graph.num[a.src]
                             keys = ops.steps_keys(graph.partner[p.key][k], 0, n_rows)
-                            rp, _, perm, _ = ops.csr_build(keys, keys, None, n_rows + 1, ops.CSR_SORT, want_perm=True)
-                            graph.csr_t[key] = (rp[:n_rows + 1], perm)
-                            continue
-                        # rows a step entry can name: the source entity's, or one per edge when the walk reads the
-                        # rows of a message network (entries are edge positions then)
-                        n_rows = int(graph.t["src_" + a.name].numel()) if p.msg_rows else graph.num[a.src]
-                        keys = ops.steps_keys(steps, k, n_rows)
+                        else:
+                            keys = ops.steps_keys(steps, k, n_rows)
                         rp, _, perm, _ = ops.csr_build(keys, keys, None, n_rows + 1, ops.CSR_SORT, want_perm=True)
                         graph.csr_t[key] = (rp[:n_rows + 1], perm)
-                        if p.msg_rows and a.name not in graph.csr_t:     # the message network's own backward (msg_ff)
+                        if p.msg_src[k] and a.name not in graph.csr_t:   # the message network's own backward (msg_ff)
                             rp2, col_t, perm_t, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name],
                                                                   None, graph.num[a.src], ops.CSR_SORT, want_perm=True)
                             graph.csr_t[a.name] = (rp2, col_t, perm_t)
@@ -382,13 +379,14 @@ class Trainer:
                 col_off = 0
                 for k, a in enumerate(p.adjs):
                     rp_t, perm_t = graph.csr_t["%s/%d" % (p.key, k)]
+                    d_k = d_steps
                     if concat_widths is not None:     # concat along the features: source k owns a block of columns
-                        reduce_into(a.src, rp_t, perm_t, ops.slice_cols(d_steps, col_off, concat_widths[k]))
+                        d_k = ops.slice_cols(d_steps, col_off, concat_widths[k])
                         col_off += concat_widths[k]
-                    elif p.msg_rows:        # one step per message row: its gradient goes back into the message network
-                        pending[(p.key, k)] = ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_steps)
+                    if p.msg_src[k]:        # one step per message row: its gradient goes back into the message network
+                        pending[(p.key, k)] = ops.segment_reduce(ops.OP_SUM, rp_t, perm_t, d_k)
                     else:
-                        reduce_into(a.src, rp_t, perm_t, d_steps)
+                        reduce_into(a.src, rp_t, perm_t, d_k)
             elif kind in ("agg_gru", "agg_gru_unfused"):
                 _, p, has_msg, h_old, agg, max_src = entry
                 g_new = gstate[p.dst]

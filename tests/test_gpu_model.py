@@ -317,15 +317,19 @@ def test_two_source_concat_axis1_and_ordered(agg):
     assert rel_err(pred.cpu().numpy().reshape(-1), np.concatenate([p.reshape(-1) for p, _ in want])) < RTOL
 
 
+def _with_link_message_nn(mj):
+    """the links' messages come from a network over [link, path] states, the nodes' stay their states"""
+    mj["message_passing"]["stages"][0]["stage_mp"][0]["source_entities"][0]["message"] = [
+        {"type": "neural_network", "nn_name": "msg", "input": ["hs_source", "hs_dest"]}]
+    mj["neural_networks"].append({"nn_name": "msg", "nn_type": "feed_forward", "nn_architecture": [
+        {"type_layer": "Dense", "units": 24, "activation": "tanh"},
+        {"type_layer": "Dense", "units": 16, "activation": "None"}]})
+    return mj
+
+
 def _two_source_attention(message_nn):
     mj = _two_entity_json({"type": "attention"})
-    if message_nn:       # the links' messages come from a network over [link, path] states, the nodes' stay their states
-        mj["message_passing"]["stages"][0]["stage_mp"][0]["source_entities"][0]["message"] = [
-            {"type": "neural_network", "nn_name": "msg", "input": ["hs_source", "hs_dest"]}]
-        mj["neural_networks"].append({"nn_name": "msg", "nn_type": "feed_forward", "nn_architecture": [
-            {"type_layer": "Dense", "units": 24, "activation": "tanh"},
-            {"type_layer": "Dense", "units": 16, "activation": "None"}]})
-    return mj
+    return _with_link_message_nn(mj) if message_nn else mj
 
 
 @pytest.mark.parametrize("message_nn", [False, True])

@@ -189,14 +189,18 @@ def test_gradients_message_network_into_ordered_aggregation():
     _grad_check(_mpnn_json("ordered", 32, "gru", True), samples)
 
 
+@pytest.mark.parametrize("message_nn", [False, True])
 @pytest.mark.parametrize("axis", [1, 2])
-def test_gradients_concat_aggregation(axis):
+def test_gradients_concat_aggregation(axis, message_nn):
     """tf.gradients through Concat_aggr (generate_model.py:496-505): along the sequence (axis 1: the sources' blocks one
     after the other) and along the features (axis 2: wider messages, walked by the generic ordered update), two source
-    entities, vs fp64 autograd"""
-    from test_gpu_model import _two_entity_json, _two_entity_sample
+    entities, vs fp64 autograd.  With ``message_nn`` the links' messages come from a message network (step entries /
+    partner indices name edge positions, the step gradients flow back into the network per edge)"""
+    from test_gpu_model import _two_entity_json, _two_entity_sample, _with_link_message_nn
     rng = np.random.RandomState(21 + axis)
     mj = _two_entity_json({"type": "concat", "concat_axis": axis})
+    if message_nn:
+        _with_link_message_nn(mj)
     samples = [_two_entity_sample(rng, 8, 6, 12), _two_entity_sample(rng, 12, 7, 30)]
     if axis == 2:
         for s_ in samples:                     # equally long padded blocks (tf.concat along the features)
@@ -207,6 +211,15 @@ def test_gradients_concat_aggregation(axis):
                 for l in ls:
                     s_["pl"].setdefault(l, []).append(p_)
     _grad_check(mj, samples)
+
+
+def test_gradients_two_source_ordered_with_message_network():
+    """the default multi-source combine (generate_model.py:523-543) into an ordered update where one source's messages
+    come from a message network: forward parity and every gradient vs fp64 autograd"""
+    from test_gpu_model import _two_entity_json, _two_entity_sample, _with_link_message_nn
+    rng = np.random.RandomState(77)
+    mj = _with_link_message_nn(_two_entity_json({"type": "ordered"}))
+    _grad_check(mj, [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 30)])
 
 
 def test_training_unbuilt_paths_fail_loudly():
