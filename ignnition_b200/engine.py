@@ -44,6 +44,7 @@ class DeviceGraph:
         self.max_seq: Dict[str, int] = {}                 # host-known longest list per adjacency
         self.partner: Dict[str, list] = {}               # concat axis 2: per-source row index per CSR position
         self.host_offsets: Dict[str, np.ndarray] = {}    # per-sample row offsets per entity, host copy
+        self.small = False                               # built for the one-launch loop of small graphs (no walk order)
         self.attn_comb: Dict[str, tuple] = {}            # attention over several sources: (rowptr, perm, slot_col, max_len)
         self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
         self.step_plan_bwd: Dict[str, tuple] = {}        # the same plan for the step-synchronous backward pass
@@ -106,6 +107,10 @@ class Engine:
         self.adjacencies = [AdjacencySpec(a[0], a[1], a[2], a[3] == "True") for a in model.get_adjecency_info()]
         self._adj_by_name = {a.name: a for a in self.adjacencies}
         self._msg_adjacencies = list(self.adjacencies)
+        # inference of graphs whose largest entity has at most this many rows runs the whole T-iteration loop as ONE
+        # persistent launch (csrc/small_graph.cu) when every stage is an ordered or sum update of 16 / 32-wide states;
+        # 0 = never.  The reference's default batch (3 samples) is 546 paths: 16 dependent launches were all gaps
+        self.small_graph_rows = int(os.environ.get("IGN_SMALL_GRAPH_ROWS", "8192"))
         self.bwd_steps_min_rows = ops.BWD_STEPS_MIN_ROWS   # below: the fp32 BPTT walk (one launch) instead of 2 launches per step
         self._needs_perm = set()
         self.plans: List[List[_MPPlan]] = []
@@ -445,7 +450,15 @@ class Engine:
 
     def build_graph(self, g: DeviceGraph, training: bool = False, check: bool = False) -> DeviceGraph:
         """Device adjacency builder: CSR per adjacency, length order, step tables."""
-        for a in self.adjacencies:
+        g.small = (not training and self._small_program_ok() and 0 < max(g.num.values()) <= self.small_graph_rows)
+        if g.small and not check and len(self.adjacencies) <= 8:
+            # one launch for every adjacency (ign_csr_build_small) instead of a dozen launches of ~3 us each
+            specs = [(g.t["dst_" + a.name], g.t["src_" + a.name],
+                      g.t.get("seq_" + a.name) if self.csr_mode == ops.CSR_RANK else None, g.num[a.dst],
+                      a.name in self._needs_perm) for a in self.adjacencies]
+            for a, built in zip(self.adjacencies, ops.csr_build_small(specs)):
+                g.csr[a.name] = built
+        for a in ([] if g.csr else self.adjacencies):
             dst, src, seq = g.t["dst_" + a.name], g.t["src_" + a.name], g.t.get("seq_" + a.name)
             # no seq on the device (the host saw the list in destination order): stable sort, pre-sorted fast path
             mode = self.csr_mode if seq is not None else ops.CSR_SORT
@@ -493,6 +506,8 @@ class Engine:
                     g.steps[p.key] = ops.steps_build(
                         rps, cols, g.t["sample_of_" + p.dst] if multi else None, g.t["pos_off_" + p.key],
                         g.t["pos_src_" + p.key], g.t["pos_col_" + p.key], g.num[p.dst], total)
+                if g.small:          # one warp per destination in the one-launch loop: no length order, no tile table
+                    continue
                 if self.sort_by_length and g.num[p.dst] > 0:
                     g.order[p.key] = ops.length_order(g.steps[p.key][0])
                 if g.num[p.dst] > 0:
@@ -730,9 +745,48 @@ class Engine:
                                                            dtype=torch.float32, device=self.device))
         return state
 
+    def _small_program_ok(self) -> bool:
+        """Every stage is an ordered / interleave / concat-axis-1 walk or a sum + GRU update over source STATES, all
+        states and messages 16 or 32 wide: what csrc/small_graph.cu runs in one launch."""
+        ok = getattr(self, "_small_ok", None)
+        if ok is None:
+            flat = [p for stage in self.plans for p in stage]
+            widths = set(self.hidden.values())
+            ok = (len(widths) == 1 and next(iter(widths)) in (16, 32)
+                  and 1 <= len(flat) <= 8 and len(self.entities) <= 8
+                  and all(p.msg_dim == self.hidden[p.dst] and not any(p.msg_src) and len(p.adjs) <= 4
+                          and ((p.kind == "seq_gru" and not p.concat2)
+                               or (p.kind == "agg_gru" and p.op == ops.OP_SUM and not p.attn and not p.conv
+                                   and len(p.adjs) == 1)) for p in flat))
+            self._small_ok = ok
+        return ok
+
+    def _mp_small(self, g: DeviceGraph, state: Dict[str, torch.Tensor], T: int) -> Dict[str, torch.Tensor]:
+        eid = {e: i for i, e in enumerate(self.entities)}
+        buf0 = [state[e] for e in self.entities]
+        buf1 = [torch.empty_like(t) for t in buf0]
+        kinds, dsts, srcs, rowptrs, idxs, Ks, Rs, Bs = [], [], [], [], [], [], [], []
+        for stage in self.plans:
+            for p in stage:
+                seq = p.kind == "seq_gru"
+                rowptr, idx = g.steps[p.key] if seq else g.csr[p.adjs[0].name][:2]
+                kinds.append(0 if seq else 1)
+                dsts.append(eid[p.dst])
+                srcs.append([eid[a.src] for a in p.adjs])
+                rowptrs.append(rowptr)
+                idxs.append(idx)
+                Ks.append(self.param(p.dst + "_update/kernel"))
+                Rs.append(self.param(p.dst + "_update/recurrent_kernel"))
+                Bs.append(self.param(p.dst + "_update/bias"))
+        final = ops.small_graph_forward(next(iter(self.hidden.values())), [g.num[e] for e in self.entities], buf0, buf1,
+                                        kinds, dsts, srcs, rowptrs, idxs, Ks, Rs, Bs, T)
+        return {e: (buf1 if final[i] else buf0)[i] for i, e in enumerate(self.entities)}
+
     def message_passing(self, g: DeviceGraph, state: Dict[str, torch.Tensor], iterations: Optional[int] = None,
                         tape: Optional[list] = None) -> Dict[str, torch.Tensor]:
         T = self.T if iterations is None else iterations
+        if tape is None and g.small and T > 0:
+            return self._mp_small(g, state, T)
         for _ in range(T):
             for stage in self.plans:
                 for p in stage:

@@ -88,6 +88,28 @@ def csr_build(dst: torch.Tensor, src: torch.Tensor, seq: Optional[torch.Tensor],
     return rowptr, col, perm, status
 
 
+def csr_build_small(specs):
+    """CSR by destination of every adjacency of a small graph in ONE launch (ign_csr_build_small).
+    ``specs`` = [(dst, src, seq | None, num_dst, want_perm)]; returns [(rowptr, col, perm | None)]."""
+    lib = _lib.load()
+    dev = specs[0][0].device
+    out = []
+    for dst, src, seq, num_dst, want_perm in specs:
+        E = dst.numel()
+        out.append((torch.empty(num_dst + 1, dtype=torch.int32, device=dev),
+                    torch.empty(E, dtype=torch.int32, device=dev),
+                    torch.empty(E, dtype=torch.int32, device=dev) if want_perm else None))
+    n = len(specs)
+    nz = lambda t: t if t is not None and t.numel() else None
+    _lib.check(lib.ign_csr_build_small(
+        n, _ptr_array([nz(s_[0]) for s_ in specs], torch.int32), _ptr_array([nz(s_[1]) for s_ in specs], torch.int32),
+        _ptr_array([nz(s_[2]) for s_ in specs], torch.int32), (C.c_int64 * n)(*[int(s_[0].numel()) for s_ in specs]),
+        (C.c_int64 * n)(*[int(s_[3]) for s_ in specs]), _ptr_array([o[0] for o in out], torch.int32),
+        _ptr_array([nz(o[1]) for o in out], torch.int32), _ptr_array([nz(o[2]) for o in out], torch.int32), _stream()),
+        "csr_build_small")
+    return out
+
+
 def length_order(rowptr: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     n = rowptr.numel() - 1
@@ -659,6 +681,29 @@ def attention_aggregate_bwd(rowptr, idx, perm, rows, g_out, sample_offsets, max_
                                                _f(d_pre4), _f(d_ds), ws.data_ptr(), nbytes, _stream()),
                "attention_aggregate_bwd")
     return d_msg, d_pre4, d_ds
+
+
+def small_graph_forward(units: int, rows: Sequence[int], buf0, buf1, kinds: Sequence[int], dsts: Sequence[int],
+                        srcs: Sequence[Sequence[int]], rowptrs, idxs, kernels, rkernels, biases, iterations: int):
+    """All ``iterations`` of the message-passing loop of a small graph in one launch (ign_small_graph_forward).
+    Returns, per entity, which of its two buffers (0 / 1) holds the final state."""
+    lib = _lib.load()
+    n_ent, n_ops = len(rows), len(kinds)
+    dev = next(b.device for b in buf0 if b is not None)
+    flat_src = []
+    for s_ in srcs:
+        flat_src += list(s_) + [-1] * (4 - len(s_))
+    final = (C.c_int32 * n_ent)()
+    nbytes = lib.ign_small_graph_ws_bytes()
+    ws = _workspace(nbytes, dev)
+    _lib.check(lib.ign_small_graph_forward(
+        int(units), n_ent, (C.c_int64 * n_ent)(*[int(r) for r in rows]), _ptr_array(buf0, torch.float32),
+        _ptr_array(buf1, torch.float32), n_ops, (C.c_int32 * n_ops)(*[int(k) for k in kinds]),
+        (C.c_int32 * n_ops)(*[int(d) for d in dsts]), (C.c_int32 * (4 * n_ops))(*flat_src),
+        _ptr_array(rowptrs, torch.int32), _ptr_array([i if i is not None and i.numel() else None for i in idxs], torch.int32),
+        _ptr_array(kernels, torch.float32), _ptr_array(rkernels, torch.float32), _ptr_array(biases, torch.float32),
+        int(iterations), final, ws.data_ptr(), nbytes, _stream()), "small_graph_forward")
+    return [int(v) for v in final]
 
 
 def partner_index(rowptr0, rowptr1, idx1, n_edges0: int):

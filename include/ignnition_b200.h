@@ -394,6 +394,34 @@ int ign_attention_combine(int n_sources, const int32_t* const* src_rowptr, const
                           const int64_t* edge_counts, int64_t num_dst, int max_len, int32_t* rowptr, int32_t* perm,
                           int32_t* slot_col, void* stream);
 
+/* The whole message-passing loop (generate_model.py:405-602) of a SMALL graph in ONE launch: a persistent grid keeps
+ * every stage's GRU weights in shared memory for all `iterations`, a warp owns a destination row, a grid-wide barrier
+ * replaces the launch boundary between stages (csrc/small_graph.cu).  For the reference's own batch sizes (3 samples,
+ * code/train_options.ini:26) where the per-stage launches are all gaps.  fp32, bit-identical to the per-stage fp32
+ * kernels (ign_gru_seq / ign_agg_gru_cell).
+ *   units            state AND message width of every entity: 16 or 32
+ *   rows[e], buf0[e], buf1[e]   per entity: row count and two state buffers [rows, units]; buf0 holds the initial state
+ *   op_kind[o]       0 = ordered walk over step entries (IGN_STEP_* encoding, op_src = entity of each source id),
+ *                    1 = sum over the CSR row of op_src[o*4] + one GRU step
+ *   op_dst[o], op_src[o*4 .. o*4+3] (-1 = unused), op_rowptr[o], op_idx[o], op_kernel/rkernel/bias[o] (Keras GRU v2)
+ *   final_buffer[e]  (host, out) which of the two buffers holds entity e's state after the last iteration
+ *   ws               ign_small_graph_ws_bytes() of device memory (the barrier counter)
+ * All stages of one iteration run in order o = 0 .. n_ops-1, each seeing the states the previous ones wrote. */
+size_t ign_small_graph_ws_bytes(void);
+int ign_small_graph_forward(int units, int n_entities, const int64_t* rows, float* const* buf0, float* const* buf1,
+                            int n_ops, const int32_t* op_kind, const int32_t* op_dst, const int32_t* op_src,
+                            const int32_t* const* op_rowptr, const int32_t* const* op_idx,
+                            const float* const* op_kernel, const float* const* op_rkernel,
+                            const float* const* op_bias, int iterations, int32_t* final_buffer, void* ws,
+                            size_t ws_bytes, void* stream);
+
+/* ign_csr_build for all adjacencies of a SMALL graph in one launch, one CTA per adjacency (at most 8 adjacencies, 11000
+ * destinations each): seq[k] given = every edge at rowptr[dst] + seq (IGN_CSR_RANK; unclaimed slots = -1, a zero row),
+ * seq[k] NULL = stable order of the input (IGN_CSR_SORT).  perm[k] may be NULL.  Same arrays as ign_csr_build. */
+int ign_csr_build_small(int n_adj, const int32_t* const* dst, const int32_t* const* src, const int32_t* const* seq,
+                        const int64_t* n_edges, const int64_t* num_dst, int32_t* const* rowptr, int32_t* const* col,
+                        int32_t* const* perm, void* stream);
+
 /* Concat_aggr with concat_axis = 2 (generate_model.py:496-505): for CSR position j of the first source
  * (destination d, padded column s = j - rowptr0[d]) the row of another source sitting at the same padded
  * column: out[j] = idx1[rowptr1[d] + s], or -1 where that source's block is zero padding.  Feed the index

@@ -45,3 +45,64 @@ def test_forward_graphed_matches_eager_and_oracle():
     eng.reset_parameters(seed=5)
     got2 = eng.forward_graphed(batch).clone()
     assert torch.equal(got2, eng.forward(eng.prepare(tens))) and not torch.equal(got2, got)
+
+
+@pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_nsfnet", "two_entity_16"])
+def test_one_launch_loop_matches_per_stage_fp32_bitwise(case):
+    """csrc/small_graph.cu: the whole T-iteration message-passing loop of a small graph in ONE persistent launch
+    (weights resident in shared memory, grid barrier between stages) gives the SAME BITS as the per-stage fp32 kernels
+    (ign_gru_seq / ign_agg_gru_cell) -- states of every entity and predictions -- and agrees with the fp64 oracle.
+    RouteNet (ordered + sum), Q-size (interleave over three entities) and a 16-wide two-source ordered model."""
+    from ignnition_b200 import Engine, ModelDescription, ops
+    if case == "two_entity_16":
+        from test_gpu_model import _two_entity_json, _two_entity_sample, tensors_of
+        from ignnition_b200.generator import sample_dimensions
+        rng = np.random.RandomState(5)
+        mj = _two_entity_json({"type": "ordered"})
+        samples = [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 40), _two_entity_sample(rng, 3, 2, 1)]
+        dims = sample_dimensions(samples[0])
+        md = ModelDescription(mj, dims)
+        tens = [tensors_of(md, s)[0] for s in samples]
+    else:
+        g = load_golden(case)
+        mj, dims = g["model_json"], g["reference_meta"]["dimensions"]
+        md = ModelDescription(mj, dims)
+        tens = [orc.normalize_inputs(mj, t) for t in g["reference_tensors"]] * 2
+    eng = Engine(md, device="cuda:0", seed=3)
+    assert eng._small_program_ok()
+    graph = eng.prepare(tens)
+    assert graph.small and not graph.order and not graph.meta
+    state0 = eng.initial_states(graph)
+    l0 = eng.gpu_launches
+    state = eng.message_passing(graph, state0)
+    assert eng.gpu_launches - l0 == 1                       # the whole loop
+    pred = eng.readout_forward(state, g=graph)
+    ref_eng = Engine(md, device="cuda:0", seed=3)
+    ref_eng.small_graph_rows = 0
+    ops.set_tensor_cores(False)
+    try:
+        g2 = ref_eng.prepare(tens)
+        assert not g2.small
+        state2 = ref_eng.message_passing(g2, ref_eng.initial_states(g2))
+        pred2 = ref_eng.readout_forward(state2, g=g2)
+    finally:
+        ops.set_tensor_cores(True)
+    for e in eng.entities:
+        assert torch.equal(state[e], state2[e]), e
+    o64 = orc.Oracle(mj, dims, dtype=np.float64)
+    w = eng.get_weights()
+    want = [o64.forward(t, w, return_states=True) for t in tens]
+    # fp32 arithmetic against fp64: 1e-5 everywhere except the Q-size node states, where fp32 ITSELF sits at
+    # 1.0e-5 .. 1.6e-5 of the fp64 result (profiles/r2_parity.md: a NumPy fp32 run of the oracle deviates as much)
+    tol = 2e-5 if case == "qsize_nsfnet" else 1e-5
+    for e in eng.entities:
+        ref = np.concatenate([s[e] for _, s in want])
+        assert float(np.abs(state[e].cpu().numpy() - ref).max() / np.abs(ref).max()) < tol, e
+    ref = np.concatenate([p.reshape(-1) for p, _ in want])
+    assert float(np.abs(pred.cpu().numpy().reshape(-1) - ref).max() / np.abs(ref).max()) < tol
+    # through the captured graph as well (the barrier counter is reset by a memset node at every replay)
+    batch = eng.assemble(tens)
+    for _ in range(3):
+        assert torch.equal(eng.forward_graphed(batch), pred)
+    # a training graph keeps the per-stage kernels (the backward needs the walk's tables)
+    assert not eng.prepare(tens, training=True).small

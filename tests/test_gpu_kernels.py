@@ -910,3 +910,34 @@ def test_new_kernels_write_only_their_outputs():
         ops.gather_dense(parts, idx, rows, dev(rng.randn(64, 64).astype(np.float32)), dev(np.zeros(64, np.float32)), 0, out=y)
         torch.cuda.synchronize()
         assert clean(yb, rows) and not bool((y == S).any())
+
+
+def test_csr_build_small_one_launch_bit_exact():
+    """ign_csr_build_small (one CTA per adjacency, one launch for the whole graph) against the oracle's CSR: an
+    adjacency placed by seq, one grouped by destination without seq, one in random order without seq (the single-warp
+    stable placement), one without edges, and a seq with a gap (the unclaimed slot stays -1)."""
+    from ignnition_b200 import ops
+    rng = np.random.RandomState(17)
+    src_a, dst_a, seq_a = random_edges(rng, 700, 300, 9)
+    E = 5000
+    dst_b = np.sort(rng.randint(0, 3000, E))
+    src_b = rng.randint(0, 500, E)
+    dst_c = rng.randint(0, 9000, E + 77)
+    src_c = rng.randint(0, 500, E + 77)
+    empty = np.zeros(0, np.int32)
+    dst_e, seq_e, src_e = np.array([0, 0, 2]), np.array([0, 2, 0]), np.array([5, 6, 7])   # destination 0: slot 1 unclaimed
+    i32 = lambda a: dev(np.asarray(a), torch.int32)
+    specs = [(i32(dst_a), i32(src_a), i32(seq_a), 700, True), (i32(dst_b), i32(src_b), None, 3000, True),
+             (i32(dst_c), i32(src_c), None, 9000, True), (i32(empty), i32(empty), None, 12, False),
+             (i32(dst_e), i32(src_e), i32(seq_e), 3, True)]
+    l0 = ops._lib.load().ign_launch_count()
+    out = ops.csr_build_small(specs)
+    assert ops._lib.load().ign_launch_count() - l0 == 1
+    r, c, p = orc.csr_from_edges(src_a, dst_a, seq_a, 700)
+    assert all(np.array_equal(x.cpu().numpy(), y) for x, y in zip(out[0], (r, c, p)))
+    for k, (s_, d_, n_) in ((1, (src_b, dst_b, 3000)), (2, (src_c, dst_c, 9000))):
+        r, c, p = orc.stable_sort_csr(s_, d_, n_)
+        assert all(np.array_equal(x.cpu().numpy(), y) for x, y in zip(out[k], (r, c, p))), k
+    assert np.array_equal(out[3][0].cpu().numpy(), np.zeros(13)) and out[3][2] is None
+    assert np.array_equal(out[4][0].cpu().numpy(), [0, 2, 2, 3])
+    assert np.array_equal(out[4][1].cpu().numpy(), [5, -1, 7]) and np.array_equal(out[4][2].cpu().numpy(), [0, -1, 2])

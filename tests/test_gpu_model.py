@@ -36,6 +36,10 @@ def make(model_json, dims, seed=1234):
     o64 = orc.Oracle(model_json, dims, dtype=np.float64)
     w = {k: v.astype(np.float32) for k, v in o64.init_weights(seed).items()}
     eng = Engine(md, device="cuda:0")
+    # the models of this file are small: keep their tests on the per-stage kernels (what large graphs run); the
+    # one-launch loop of small graphs has its own tests (test_forward_matches_golden_and_oracle[one_launch],
+    # tests/test_gpu_graphs.py)
+    eng.small_graph_rows = 0
     assert set(eng.param_table) == set(w), set(eng.param_table) ^ set(w)
     eng.set_weights(w)
     return md, eng, o64, w
@@ -48,14 +52,19 @@ def tensors_of(md, sample):
                              md.get_additional_input_names(), True)
 
 
+@pytest.mark.parametrize("one_launch", [False, True])
 @pytest.mark.parametrize("case", ["routenet_nsfnet", "qsize_hand", "qsize_nsfnet"])
-def test_forward_matches_golden_and_oracle(case):
+def test_forward_matches_golden_and_oracle(case, one_launch):
+    """``one_launch``: the whole message-passing loop of these small graphs in one persistent launch
+    (csrc/small_graph.cu, the engine's default below 8192 rows) instead of the per-stage kernels"""
     g = load_golden(case)
     dims = g["reference_meta"]["dimensions"]
     md, eng, o64, w = make(g["model_json"], dims)
+    eng.small_graph_rows = 8192 if one_launch else 0
     for ref, fl in zip(g["reference_tensors"], g["oracle_float"]):
         tens = orc.normalize_inputs(g["model_json"], ref)
         graph = eng.prepare([tens], check=True)
+        assert graph.small == one_launch
         for st in graph.status.values():
             assert st.cpu().numpy()[0] == 0
         pred, state = eng.forward(graph, return_states=True)
@@ -65,8 +74,8 @@ def test_forward_matches_golden_and_oracle(case):
         from ignnition_b200 import ops
         tc = ops.set_tensor_cores(True)
         ops.set_tensor_cores(tc)
-        for e, v in s64.items():
-            assert rel_err(state[e].cpu().numpy(), v) < (RTOL_STATE_TC if tc else RTOL), e
+        for e, v in s64.items():       # (the one-launch loop is fp32: on Q-size node states fp32 itself sits at 1.0e-5 .. 1.6e-5)
+            assert rel_err(state[e].cpu().numpy(), v) < (RTOL_STATE_TC if tc or one_launch else RTOL), e
         # __call__ == ComnetModel.call contract: dict in, [P, 1] out
         assert eng(tens).shape == (ref["num_path"], 1)
 
@@ -81,6 +90,7 @@ def test_batch_equals_per_sample(csr_mode, sort_by_length):
     dims = g["reference_meta"]["dimensions"]
     md, eng, o64, w = make(g["model_json"], dims)
     eng = Engine(md, device="cuda:0", csr_mode=csr_mode, sort_by_length=sort_by_length)
+    eng.small_graph_rows = 0
     eng.set_weights(w)
     samples = [synthetic.routenet_sample("nsfnet", 0, 0), synthetic.routenet_sample("geant2", 3, 1),
                synthetic.routenet_sample("nsfnet", 5, 2)]
@@ -96,7 +106,7 @@ def test_forward_fp32_twin_kernels():
     from ignnition_b200 import ops
     prev = ops.set_tensor_cores(False)
     try:
-        test_forward_matches_golden_and_oracle("routenet_nsfnet")
+        test_forward_matches_golden_and_oracle("routenet_nsfnet", False)
     finally:
         ops.set_tensor_cores(prev)
 
@@ -109,6 +119,7 @@ def test_step_synchronous_engine_path():
         dims = g["reference_meta"]["dimensions"]
         md, _, o64, w = make(g["model_json"], dims)
         eng = Engine(md, device="cuda:0", max_step_launches=16)
+        eng.small_graph_rows = 0
         eng.set_weights(w)
         tens = [orc.normalize_inputs(g["model_json"], t) for t in g["reference_tensors"]]
         graph = eng.prepare(tens)

@@ -54,8 +54,11 @@ def build_engine(hidden, T, agg="sum", seed=3):
     from ignnition_b200 import Engine, ModelDescription
     md = ModelDescription(mpnn_json(hidden, T, agg), {"x": hidden, "adj": 0})
     # fuse_sum_gru=False: the single-GPU engine would take its one-launch fp32 update for graphs this small; the
-    # comparison below is bit for bit against the tensor-core update the partitioned engine runs
-    return Engine(md, device="cuda", seed=seed, fuse_sum_gru=False)
+    # comparison below is bit for bit against the tensor-core update the partitioned engine runs (small_graph_rows = 0
+    # for the same reason: no one-launch fp32 loop)
+    eng = Engine(md, device="cuda", seed=seed, fuse_sum_gru=False)
+    eng.small_graph_rows = 0
+    return eng
 
 
 @pytest.mark.parametrize("hidden,agg", [(64, "sum"), (32, "sum"), (64, "mean"), (32, "max")])
