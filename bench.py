@@ -197,6 +197,8 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
         trainer = Trainer(eng, world_size=world)
 
     def step_resident(graph):
+        if graphed and trainer is not None:   # captured: build + forward + loss + backward; then all-reduce + optimiser
+            return trainer.train_step_graphed(batch, pinned, global_n=n_pred_glob, copy=False)
         if graphed:                    # one captured CUDA graph: adjacency build + forward (Engine.forward_graphed)
             return eng.forward_graphed(batch, pinned, copy=False)
         if trainer is not None:        # model_fn train step: forward + loss + backward + all-reduce + Adam
@@ -227,6 +229,10 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
         return g_
 
     def step_e2e_graphed():
+        if trainer is not None:
+            trainer.train_step_graphed(batch, pinned, global_n=n_pred_glob, copy=True)
+            host_loss.copy_(trainer.scalars, non_blocking=True)
+            return
         pred = eng.forward_graphed(batch, pinned, copy=True)       # H2D into the graph's staging buffer + one replay
         host_pred.copy_(pred, non_blocking=True)
 
@@ -299,7 +305,9 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
 
     # per-kernel CUDA-event timing of more passes (same stream, after the timed region)
     kern = profile_kernels(eng, graph, torch, steps, trainer, n_pred_glob) if (want_kernels and not graphed) else {}
-    if graphed:                         # launches were counted at capture time: kernels inside the graph x replays
+    if graphed and trainer is not None:  # kernels inside the graph x replays + the optimiser's own launches (counted)
+        launches += list(trainer._graphs.values())[0][4] * steps
+    elif graphed:                       # launches were counted at capture time: kernels inside the graph x replays
         launches = eng.graphed_kernels(batch, pinned) * steps
 
     # parity of the timed configuration: the first samples of this rank's batch vs the fp64 CPU oracle, predictions
@@ -344,7 +352,8 @@ def measure_case(ctx, workload, n_samples, train, steps, warmup, seed_weights=0,
             parity["graph_replay_equals_eager_forward"] = bool(torch.equal(eng.forward_graphed(batch, pinned), pred_t))
 
     total = total_scale if total_scale is not None else n_samples * world
-    out = {"workload": workload, "mode": ("inference, one CUDA graph per step" if graphed else
+    out = {"workload": workload, "mode": ("train, one CUDA graph per step + optimiser update" if graphed and train else
+                                          "inference, one CUDA graph per step" if graphed else
                                           "train" if train else "inference"), "n_gpus": world,
            "samples_per_gpu": n_samples, "samples_per_step": total, "steps": steps,
            "value": total * steps / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms / steps,
@@ -529,6 +538,11 @@ def run_ours(args):
                                 note="%d samples per step; adjacency build + T = 8 iterations + readout replayed as one "
                                      "captured CUDA graph (Engine.forward_graphed)" % bsz),
                 "routenet_nsfnet_b%d/graphed" % bsz)
+            leg(lambda: compact(measure_case(ctx, "routenet_nsfnet_b4096", bsz, True, 100, 5, graphed=True), hbm_peak,
+                                peak_src, default_size=False,
+                                note="%d samples per train step; adjacency build + forward + loss + backward replayed as one "
+                                     "captured CUDA graph, optimiser update after it (Trainer.train_step_graphed)" % bsz),
+                "routenet_nsfnet_b%d/train/graphed" % bsz)
 
     if rank == 0:
         roof = roofline_of(main, hbm_peak, peak_src, n_samples == n_default)

@@ -662,7 +662,12 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
     int rc = ign_dw_tc_launch(x, dy, m, k, n, dw, st);
     if (rc != IGN_OK) return rc;
   } else if (dw) {   // dW[k,n] += X^T[k,m] dZ[m,n] : A = X stored [m,k] = [K',M'] with M'=k, K'=m
+    // a split per 4096 rows -- or, for a small batch whose few output tiles would leave the machine idle while each
+    // walks all m rows, enough splits for one CTA per SM (down to 2 BK rows per split)
     int64_t splits = ign_cdiv(m, 4096);
+    const int64_t tiles = ign_cdiv(k, BM) * ign_cdiv(n, BN);
+    const int64_t fill = ign_cdiv(IGN_NUM_SMS, tiles) < ign_cdiv(m, 2 * BK) ? ign_cdiv(IGN_NUM_SMS, tiles) : ign_cdiv(m, 2 * BK);
+    if (splits < fill) splits = fill;
     if (splits > 1024) splits = 1024;
     const int64_t per = ign_cdiv(ign_cdiv(m, splits), BK) * BK;
     splits = ign_cdiv(m, per);

@@ -325,6 +325,43 @@ int check_gru_args(const char* who, int f_in, int units, const float* k, const f
 
 }  // namespace
 
+// fp32 launchers of this compilation's tile geometry (see gru.cuh)
+int IGN_GRU_FN(ign_gru_seq_fp32)(const int* steps_rowptr, const int* steps, const int* order, int n_src,
+                                 const float* const* srcs, int f_in, const float* h0, int64_t num_dst, int units,
+                                 const float* kernel, const float* recurrent_kernel, const float* bias, float* out,
+                                 float* h_seq, cudaStream_t st) {
+  SrcPtrs sp;
+  for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
+  IGN_GRU_DISPATCH(f_in, units, return (launch_gru_seq<FI, U>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
+                                                               recurrent_kernel, bias, out, h_seq, st)));
+  return IGN_ERR_UNSUPPORTED;
+}
+
+// mode 0: gather + sum + GRU step (rowptr / col), mode 1: GRU step on a dense x
+int IGN_GRU_FN(ign_gru_cell_fp32)(int mode, const int* rowptr, const int* col, const float* src, const float* h,
+                                  int64_t num_dst, int f_in, int units, const float* kernel,
+                                  const float* recurrent_kernel, const float* bias, float* out, float* agg_out,
+                                  cudaStream_t st) {
+  if (mode == 0) {
+    IGN_GRU_DISPATCH(f_in, units, return (launch_gru_cell<FI, U, 0>(rowptr, col, src, h, num_dst, kernel,
+                                                                     recurrent_kernel, bias, out, agg_out, st)));
+  } else {
+    IGN_GRU_DISPATCH(f_in, units, return (launch_gru_cell<FI, U, 1>(nullptr, nullptr, src, h, num_dst, kernel,
+                                                                     recurrent_kernel, bias, out, nullptr, st)));
+  }
+  return IGN_ERR_UNSUPPORTED;
+}
+
+#ifndef IGN_GRU_SMALL_TILE
+int ign_gru_seq_fp32_small_tile(const int* steps_rowptr, const int* steps, const int* order, int n_src,
+                                const float* const* srcs, int f_in, const float* h0, int64_t num_dst, int units,
+                                const float* kernel, const float* recurrent_kernel, const float* bias, float* out,
+                                float* h_seq, cudaStream_t st);
+int ign_gru_cell_fp32_small_tile(int mode, const int* rowptr, const int* col, const float* src, const float* h,
+                                 int64_t num_dst, int f_in, int units, const float* kernel,
+                                 const float* recurrent_kernel, const float* bias, float* out, float* agg_out,
+                                 cudaStream_t st);
+
 // tensor-core variant (gru_seq_tc.cu), 32-wide messages and states
 int ign_gru_seq_tc_launch(const int* steps_rowptr, const int* steps, const int* order, int n_src,
                           const float* const* srcs, const float* h0, int64_t num_dst, const float* kernel,
@@ -343,18 +380,16 @@ extern "C" int ign_gru_seq(const int32_t* steps_rowptr, const int32_t* steps, co
   if (rc) return rc;
   if (num_dst == 0) return IGN_OK;
   IGN_REQUIRE(steps_rowptr && steps && h0 && out, IGN_ERR_INVALID, "IGNNITION: gru_seq: null pointer");
-  SrcPtrs sp;
-  for (int i = 0; i < IGN_MAX_SOURCES; ++i) {
-    sp.p[i] = i < n_src ? srcs[i] : nullptr;
-    IGN_REQUIRE(i >= n_src || sp.p[i], IGN_ERR_INVALID, "IGNNITION: gru_seq: null source state");
-  }
+  for (int i = 0; i < n_src; ++i)
+    IGN_REQUIRE(srcs[i], IGN_ERR_INVALID, "IGNNITION: gru_seq: null source state");
   cudaStream_t st = ign_stream(stream);
-  if (f_in == 32 && units == 32 && ign_tensor_cores_enabled())
+  // (below a few tiles per SM the tensor-core walker's fixed latency -- TMEM, barriers, weight images -- is the whole
+  // kernel: 53 us for 546 rows; the 16-row fp32 tiles take over there)
+  if (f_in == 32 && units == 32 && ign_tensor_cores_enabled() && !ign_gru_use_small_tile(num_dst))
     return ign_gru_seq_tc_launch(steps_rowptr, steps, order, n_src, srcs, h0, num_dst, kernel, recurrent_kernel,
                                  bias, out, h_seq, meta, st);
-  IGN_GRU_DISPATCH(f_in, units, return (launch_gru_seq<FI, U>(steps_rowptr, steps, order, sp, h0, num_dst, kernel,
-                                                               recurrent_kernel, bias, out, h_seq, st)));
-  return IGN_ERR_UNSUPPORTED;
+  return (ign_gru_use_small_tile(num_dst) ? ign_gru_seq_fp32_small_tile : ign_gru_seq_fp32)(
+      steps_rowptr, steps, order, n_src, srcs, f_in, h0, num_dst, units, kernel, recurrent_kernel, bias, out, h_seq, st);
 }
 
 extern "C" int ign_agg_gru_cell(const int32_t* rowptr, const int32_t* col, const float* src_states, int f_in,
@@ -367,9 +402,8 @@ extern "C" int ign_agg_gru_cell(const int32_t* rowptr, const int32_t* col, const
   if (num_dst == 0) return IGN_OK;
   IGN_REQUIRE(rowptr && src_states && h_dst && out, IGN_ERR_INVALID, "IGNNITION: agg_gru_cell: null pointer");
   cudaStream_t st = ign_stream(stream);
-  IGN_GRU_DISPATCH(f_in, units, return (launch_gru_cell<FI, U, 0>(rowptr, col, src_states, h_dst, num_dst, kernel,
-                                                                   recurrent_kernel, bias, out, agg_out, st)));
-  return IGN_ERR_UNSUPPORTED;
+  return (ign_gru_use_small_tile(num_dst) ? ign_gru_cell_fp32_small_tile : ign_gru_cell_fp32)(
+      0, rowptr, col, src_states, h_dst, num_dst, f_in, units, kernel, recurrent_kernel, bias, out, agg_out, st);
 }
 
 // step-synchronous tensor-core variant of the ordered update (gru_step_tc.cu)
@@ -418,7 +452,8 @@ extern "C" int ign_gru_cell(const float* x, const float* h, int64_t n, int f_in,
     IGN_REQUIRE(out != h, IGN_ERR_INVALID, "IGNNITION: gru_cell: out must not alias h on the tensor-core path");
     return ign_gru_cell_tc_launch(x, h, n, units, kernel, recurrent_kernel, bias, out, ws, st);
   }
-  IGN_GRU_DISPATCH(f_in, units, return (launch_gru_cell<FI, U, 1>(nullptr, nullptr, x, h, n, kernel,
-                                                                   recurrent_kernel, bias, out, nullptr, st)));
-  return IGN_ERR_UNSUPPORTED;
+  return (ign_gru_use_small_tile(n) ? ign_gru_cell_fp32_small_tile : ign_gru_cell_fp32)(
+      1, nullptr, nullptr, x, h, n, f_in, units, kernel, recurrent_kernel, bias, out, nullptr, st);
 }
+
+#endif  // IGN_GRU_SMALL_TILE

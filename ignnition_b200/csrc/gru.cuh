@@ -18,18 +18,45 @@
 
 #include "common.cuh"
 
+// gru.cu and gru_bwd.cu are compiled twice: as they are (tiles of 128 / 64 destinations per CTA, for graphs that
+// fill the machine) and with -DIGN_GRU_SMALL_TILE (16 destinations per CTA: a batch of 3 samples is 546 paths = 5 big
+// tiles on 148 SMs; small tiles spread the same rows over 35 CTAs and the kernel's latency drops with the rows per
+// thread).  The second compilation lives in its own namespace and exports its launchers with a _small_tile suffix.
+#ifdef IGN_GRU_SMALL_TILE
+#define ign_gru ign_gru_small_tile
+#define IGN_GRU_FN(name) name##_small_tile
+#else
+#define IGN_GRU_FN(name) name
+#endif
+
+// rows below which the small tiles win: up to four of them per SM
+inline bool ign_gru_use_small_tile(int64_t rows) {
+  int sms = IGN_NUM_SMS, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return rows <= (int64_t)16 * 4 * sms;
+}
+
 namespace ign_gru {
 
 constexpr int THREADS = 256;
 
 template <int U>
 struct Geo;                       // TU units x TR rows per thread, R rows per CTA tile
+#ifdef IGN_GRU_SMALL_TILE
+template <>
+struct Geo<16> { static constexpr int TU = 1, TR = 1; };
+template <>
+struct Geo<32> { static constexpr int TU = 2, TR = 1; };
+template <>
+struct Geo<64> { static constexpr int TU = 4, TR = 1; };
+#else
 template <>
 struct Geo<16> { static constexpr int TU = 1, TR = 8; };
 template <>
 struct Geo<32> { static constexpr int TU = 2, TR = 8; };
 template <>
 struct Geo<64> { static constexpr int TU = 4, TR = 4; };
+#endif
 
 template <int U>
 struct Tile {

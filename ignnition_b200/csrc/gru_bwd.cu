@@ -431,18 +431,12 @@ int check_bwd_shape(const char* who, int f_in, int units) {
 
 }  // namespace
 
-extern "C" int ign_gru_cell_bwd(const float* x, const float* h, int64_t n, int f_in, int units,
-                                const float* kernel, const float* recurrent_kernel, const float* bias,
-                                const float* d_out, float* dx, float* dh, float* d_kernel,
-                                float* d_recurrent_kernel, float* d_bias, void* stream) {
-  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: gru_cell_bwd: negative size");
-  int rc = check_bwd_shape("gru_cell_bwd", f_in, units);
-  if (rc) return rc;
-  if (n == 0) return IGN_OK;
-  IGN_REQUIRE(x && h && kernel && recurrent_kernel && bias && d_out && d_kernel && d_recurrent_kernel && d_bias,
-              IGN_ERR_INVALID, "IGNNITION: gru_cell_bwd: null pointer");
-  cudaStream_t st = ign_stream(stream);
-  int grid = 0;
+// fp32 launchers of this compilation's tile geometry (see gru.cuh)
+int IGN_GRU_FN(ign_gru_cell_bwd_fp32)(const float* x, const float* h, int64_t n, int units, const float* kernel,
+                                      const float* recurrent_kernel, const float* bias, const float* d_out, float* dx,
+                                      float* dh, float* d_kernel, float* d_recurrent_kernel, float* d_bias,
+                                      cudaStream_t st) {
+  int grid = 0, rc;
   if (units == 32) {
     rc = bwd_grid(gru_cell_bwd_kernel<32>, BSmem<32>::BYTES, ign_cdiv(n, Tile<32>::R), &grid);
     if (rc) return rc;
@@ -456,6 +450,57 @@ extern "C" int ign_gru_cell_bwd(const float* x, const float* h, int64_t n, int f
   }
   IGN_CHECK_LAUNCH("gru_cell_bwd");
   return IGN_OK;
+}
+
+int IGN_GRU_FN(ign_gru_seq_bwd_fp32)(const int* steps_rowptr, const int* steps, const int* order, int n_src,
+                                     const float* const* srcs, const float* h0, const float* h_seq, int64_t num_dst,
+                                     int units, const float* kernel, const float* recurrent_kernel, const float* bias,
+                                     const float* d_out, float* d_steps, float* dh0, float* d_kernel,
+                                     float* d_recurrent_kernel, float* d_bias, cudaStream_t st) {
+  SrcPtrs sp;
+  for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
+  int grid = 0, rc;
+  if (units == 32) {
+    rc = bwd_grid(gru_seq_bwd_kernel<32>, BSmem<32>::BYTES, ign_cdiv(num_dst, Tile<32>::R), &grid);
+    if (rc) return rc;
+    gru_seq_bwd_kernel<32><<<grid, THREADS, BSmem<32>::BYTES, st>>>(steps_rowptr, steps, order, sp, h0, h_seq, num_dst,
+                                                                     kernel, recurrent_kernel, bias, d_out, d_steps,
+                                                                     dh0, d_kernel, d_recurrent_kernel, d_bias);
+  } else {
+    rc = bwd_grid(gru_seq_bwd_kernel<16>, BSmem<16>::BYTES, ign_cdiv(num_dst, Tile<16>::R), &grid);
+    if (rc) return rc;
+    gru_seq_bwd_kernel<16><<<grid, THREADS, BSmem<16>::BYTES, st>>>(steps_rowptr, steps, order, sp, h0, h_seq, num_dst,
+                                                                     kernel, recurrent_kernel, bias, d_out, d_steps,
+                                                                     dh0, d_kernel, d_recurrent_kernel, d_bias);
+  }
+  IGN_CHECK_LAUNCH("gru_seq_bwd");
+  return IGN_OK;
+}
+
+#ifndef IGN_GRU_SMALL_TILE
+int ign_gru_cell_bwd_fp32_small_tile(const float* x, const float* h, int64_t n, int units, const float* kernel,
+                                     const float* recurrent_kernel, const float* bias, const float* d_out, float* dx,
+                                     float* dh, float* d_kernel, float* d_recurrent_kernel, float* d_bias,
+                                     cudaStream_t st);
+int ign_gru_seq_bwd_fp32_small_tile(const int* steps_rowptr, const int* steps, const int* order, int n_src,
+                                    const float* const* srcs, const float* h0, const float* h_seq, int64_t num_dst,
+                                    int units, const float* kernel, const float* recurrent_kernel, const float* bias,
+                                    const float* d_out, float* d_steps, float* dh0, float* d_kernel,
+                                    float* d_recurrent_kernel, float* d_bias, cudaStream_t st);
+
+extern "C" int ign_gru_cell_bwd(const float* x, const float* h, int64_t n, int f_in, int units,
+                                const float* kernel, const float* recurrent_kernel, const float* bias,
+                                const float* d_out, float* dx, float* dh, float* d_kernel,
+                                float* d_recurrent_kernel, float* d_bias, void* stream) {
+  IGN_REQUIRE(n >= 0, IGN_ERR_INVALID, "IGNNITION: gru_cell_bwd: negative size");
+  int rc = check_bwd_shape("gru_cell_bwd", f_in, units);
+  if (rc) return rc;
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(x && h && kernel && recurrent_kernel && bias && d_out && d_kernel && d_recurrent_kernel && d_bias,
+              IGN_ERR_INVALID, "IGNNITION: gru_cell_bwd: null pointer");
+  return (ign_gru_use_small_tile(n) ? ign_gru_cell_bwd_fp32_small_tile : ign_gru_cell_bwd_fp32)(
+      x, h, n, units, kernel, recurrent_kernel, bias, d_out, dx, dh, d_kernel, d_recurrent_kernel, d_bias,
+      ign_stream(stream));
 }
 
 extern "C" int ign_gru_gates_bwd(float* zx, float* zh, const float* h, const float* d_out, int64_t n, int units,
@@ -482,25 +527,9 @@ extern "C" int ign_gru_seq_bwd(const int32_t* steps_rowptr, const int32_t* steps
   IGN_REQUIRE(steps_rowptr && steps && h0 && h_seq && kernel && recurrent_kernel && bias && d_out && d_kernel &&
                   d_recurrent_kernel && d_bias,
               IGN_ERR_INVALID, "IGNNITION: gru_seq_bwd: null pointer");
-  SrcPtrs sp;
-  for (int i = 0; i < IGN_MAX_SOURCES; ++i) sp.p[i] = i < n_src ? srcs[i] : nullptr;
-  cudaStream_t st = ign_stream(stream);
-  int grid = 0;
-  if (units == 32) {
-    rc = bwd_grid(gru_seq_bwd_kernel<32>, BSmem<32>::BYTES, ign_cdiv(num_dst, Tile<32>::R), &grid);
-    if (rc) return rc;
-    gru_seq_bwd_kernel<32><<<grid, THREADS, BSmem<32>::BYTES, st>>>(steps_rowptr, steps, order, sp, h0, h_seq, num_dst,
-                                                                     kernel, recurrent_kernel, bias, d_out, d_steps,
-                                                                     dh0, d_kernel, d_recurrent_kernel, d_bias);
-  } else {
-    rc = bwd_grid(gru_seq_bwd_kernel<16>, BSmem<16>::BYTES, ign_cdiv(num_dst, Tile<16>::R), &grid);
-    if (rc) return rc;
-    gru_seq_bwd_kernel<16><<<grid, THREADS, BSmem<16>::BYTES, st>>>(steps_rowptr, steps, order, sp, h0, h_seq, num_dst,
-                                                                     kernel, recurrent_kernel, bias, d_out, d_steps,
-                                                                     dh0, d_kernel, d_recurrent_kernel, d_bias);
-  }
-  IGN_CHECK_LAUNCH("gru_seq_bwd");
-  return IGN_OK;
+  return (ign_gru_use_small_tile(num_dst) ? ign_gru_seq_bwd_fp32_small_tile : ign_gru_seq_bwd_fp32)(
+      steps_rowptr, steps, order, n_src, srcs, h0, h_seq, num_dst, units, kernel, recurrent_kernel, bias, d_out, d_steps,
+      dh0, d_kernel, d_recurrent_kernel, d_bias, ign_stream(stream));
 }
 
 // step-synchronous tensor-core variant (gru_step_bwd_tc.cu)
@@ -539,3 +568,5 @@ extern "C" int ign_gru_seq_bwd_steps(int max_steps, const int32_t* nt, const int
                                     recurrent_kernel, bias, d_out, d_steps, dh0, d_kernel, d_recurrent_kernel, d_bias,
                                     ws, ign_stream(stream));
 }
+
+#endif  // IGN_GRU_SMALL_TILE

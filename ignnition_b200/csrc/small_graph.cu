@@ -411,25 +411,54 @@ __global__ void __launch_bounds__(CS_THREADS) csr_small_kernel(const __grid_cons
       a.col[e] = a.src[e];
       if (a.perm) a.perm[e] = e;
     }
-  } else if (wid == 0) {
-    for (int base = 0; base < n; base += 32) {
-      const int e = base + lane;
-      const int d = e < n ? a.dst[e] : -1;
-      const bool ok = d >= 0 && d < nd;
-      const unsigned grp = __match_any_sync(0xffffffffu, ok ? d : -1 - lane);
-      const int leader = __ffs(grp) - 1;
-      int start = 0;
-      if (ok && lane == leader) {
-        start = cnt[d];
-        cnt[d] = start + __popc(grp);
+  } else {
+    // any order of the input (the transposed adjacencies of a train step).  Short rows: every edge claims a slot of
+    // its row with a shared-memory atomic, then one thread per row sorts the row's edge ids -- ids are unique, so the
+    // result is the stable order, bit for bit what the radix sort of ign_csr_build gives.  A row longer than 256
+    // would make that sort quadratic: one warp then walks the list in order (match_any groups + cursors).
+    int long_row = 0;
+    for (int i = tid; i < nd; i += CS_THREADS) long_row |= (a.rowptr[i + 1] - a.rowptr[i]) > 256;
+    long_row = __syncthreads_or(long_row);
+    int* ids = a.perm ? a.perm : a.col;
+    if (!long_row) {
+      for (int e = tid; e < n; e += CS_THREADS) {
+        const int d = a.dst[e];
+        if (d >= 0 && d < nd) ids[atomicAdd(&cnt[d], 1)] = e;
       }
-      start = __shfl_sync(0xffffffffu, start, leader);
-      if (ok) {
-        const int pos = start + __popc(grp & ((1u << lane) - 1u));
-        a.col[pos] = a.src[e];
-        if (a.perm) a.perm[pos] = e;
+      __syncthreads();
+      for (int i = tid; i < nd; i += CS_THREADS) {
+        const int lo = a.rowptr[i], hi = a.rowptr[i + 1];
+        for (int p = lo + 1; p < hi; ++p) {
+          const int v = ids[p];
+          int q = p - 1;
+          while (q >= lo && ids[q] > v) {
+            ids[q + 1] = ids[q];
+            --q;
+          }
+          ids[q + 1] = v;
+        }
+        for (int p = lo; p < hi; ++p) a.col[p] = a.src[ids[p]];
       }
-      __syncwarp();
+    } else if (wid == 0) {
+      for (int base = 0; base < n; base += 32) {
+        const int e = base + lane;
+        const int d = e < n ? a.dst[e] : -1;
+        const bool ok = d >= 0 && d < nd;
+        const unsigned grp = __match_any_sync(0xffffffffu, ok ? d : -1 - lane);
+        const int leader = __ffs(grp) - 1;
+        int start = 0;
+        if (ok && lane == leader) {
+          start = cnt[d];
+          cnt[d] = start + __popc(grp);
+        }
+        start = __shfl_sync(0xffffffffu, start, leader);
+        if (ok) {
+          const int pos = start + __popc(grp & ((1u << lane) - 1u));
+          a.col[pos] = a.src[e];
+          if (a.perm) a.perm[pos] = e;
+        }
+        __syncwarp();
+      }
     }
   }
 }

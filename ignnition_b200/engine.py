@@ -45,6 +45,7 @@ class DeviceGraph:
         self.partner: Dict[str, list] = {}               # concat axis 2: per-source row index per CSR position
         self.host_offsets: Dict[str, np.ndarray] = {}    # per-sample row offsets per entity, host copy
         self.small = False                               # built for the one-launch loop of small graphs (no walk order)
+        self.small_rows = False                          # every entity small enough for ign_csr_build_small
         self.attn_comb: Dict[str, tuple] = {}            # attention over several sources: (rowptr, perm, slot_col, max_len)
         self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
         self.step_plan_bwd: Dict[str, tuple] = {}        # the same plan for the step-synchronous backward pass
@@ -450,15 +451,20 @@ class Engine:
 
     def build_graph(self, g: DeviceGraph, training: bool = False, check: bool = False) -> DeviceGraph:
         """Device adjacency builder: CSR per adjacency, length order, step tables."""
-        g.small = (not training and self._small_program_ok() and 0 < max(g.num.values()) <= self.small_graph_rows)
-        if g.small and not check and len(self.adjacencies) <= 8:
+        small_rows = 0 < max(g.num.values()) <= self.small_graph_rows
+        g.small_rows = small_rows                  # every adjacency fits the one-launch CSR builder
+        g.small = not training and small_rows and self._small_program_ok()
+        if small_rows and not check and len(self.adjacencies) <= 8:
             # one launch for every adjacency (ign_csr_build_small) instead of a dozen launches of ~3 us each
             specs = [(g.t["dst_" + a.name], g.t["src_" + a.name],
                       g.t.get("seq_" + a.name) if self.csr_mode == ops.CSR_RANK else None, g.num[a.dst],
-                      a.name in self._needs_perm) for a in self.adjacencies]
+                      training or a.name in self._needs_perm) for a in self.adjacencies]
             for a, built in zip(self.adjacencies, ops.csr_build_small(specs)):
                 g.csr[a.name] = built
-        for a in ([] if g.csr else self.adjacencies):
+            per_adjacency = []
+        else:
+            per_adjacency = self.adjacencies
+        for a in per_adjacency:
             dst, src, seq = g.t["dst_" + a.name], g.t["src_" + a.name], g.t.get("seq_" + a.name)
             # no seq on the device (the host saw the list in destination order): stable sort, pre-sorted fast path
             mode = self.csr_mode if seq is not None else ops.CSR_SORT

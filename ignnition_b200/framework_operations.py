@@ -353,8 +353,7 @@ def train_and_evaluate(model: ModelDescription, namespace: Optional[dict] = None
                 cnt = torch.tensor([n_loc], dtype=torch.int64, device=engine.device)
                 torch.distributed.all_reduce(cnt)
                 n_glob = int(cnt.item())
-            graph = engine.build_graph(engine.upload(b), training=True)
-            trainer.train_step(graph, global_n=n_glob)
+            trainer.step_batch(b, global_n=n_glob)     # repeated small shapes replay a captured graph
             chunk = mine = None
         else:
             chunk = list(itertools.islice(it, batch * world))
@@ -370,8 +369,7 @@ def train_and_evaluate(model: ModelDescription, namespace: Optional[dict] = None
                                    "(global batch of %d predictions here, %d..%d across ranks)"
                                    % (n_glob, int(-chk[1]), int(chk[0])))
         if not native:
-            graph = engine.prepare([c[0] for c in mine], labels=[c[1] for c in mine], training=True)
-            trainer.train_step(graph, global_n=n_glob)
+            trainer.step_batch(engine.assemble([c[0] for c in mine], [c[1] for c in mine]), global_n=n_glob)
         if step % 10 == 0:                        # LoggingTensorHook every 10 iterations (:820-824)
             l = trainer.losses()
             history.append((step, l["loss"]))

@@ -18,6 +18,7 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
@@ -54,6 +55,14 @@ class LearningRate:
         if s["type"] == "ExponentialDecay":
             return lr0 * dr ** p
         return lr0 / (1.0 + dr * p)
+
+
+def _sorted_csr(graph, dst, src, num_dst: int, want_perm: bool):
+    """(rowptr, col, perm) of the stable sort by ``dst``: one launch for small graphs (ign_csr_build_small), the radix
+    sort otherwise."""
+    if getattr(graph, "small_rows", False) and num_dst <= 11000:
+        return ops.csr_build_small([(dst, src, None, num_dst, want_perm)])[0]
+    return ops.csr_build(dst, src, None, num_dst, ops.CSR_SORT, want_perm=want_perm)[:3]
 
 
 class Trainer:
@@ -114,27 +123,26 @@ class Trainer:
                             keys = ops.steps_keys(graph.partner[p.key][k], 0, n_rows)
                         else:
                             keys = ops.steps_keys(steps, k, n_rows)
-                        rp, _, perm, _ = ops.csr_build(keys, keys, None, n_rows + 1, ops.CSR_SORT, want_perm=True)
+                        rp, _, perm = _sorted_csr(graph, keys, keys, n_rows + 1, True)
                         graph.csr_t[key] = (rp[:n_rows + 1], perm)
                         if p.msg_src[k] and a.name not in graph.csr_t:   # the message network's own backward (msg_ff)
-                            rp2, col_t, perm_t, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name],
-                                                                  None, graph.num[a.src], ops.CSR_SORT, want_perm=True)
+                            rp2, col_t, perm_t = _sorted_csr(graph, graph.t["src_" + a.name], graph.t["dst_" + a.name],
+                                                             graph.num[a.src], True)
                             graph.csr_t[a.name] = (rp2, col_t, perm_t)
                 else:
                     for a in p.adjs:
                         if a.name in graph.csr_t:
                             continue
                         # perm (edge position per slot) only where per-edge rows are reduced: message networks
-                        rp, col_t, perm_t, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name], None,
-                                                             graph.num[a.src], ops.CSR_SORT,
-                                                             want_perm=a.name in e._needs_perm)
+                        rp, col_t, perm_t = _sorted_csr(graph, graph.t["src_" + a.name], graph.t["dst_" + a.name],
+                                                        graph.num[a.src], a.name in e._needs_perm)
                         graph.csr_t[a.name] = (rp, col_t, perm_t)
 
         for _, op in e.readout:
             if op.type == "extend_adjacencies" and op.adj_list not in graph.csr_t:
                 a = [x for x in e.adjacencies if x.name == op.adj_list][0]
-                rp, col_t, perm_t, _ = ops.csr_build(graph.t["src_" + a.name], graph.t["dst_" + a.name], None,
-                                                     graph.num[a.src], ops.CSR_SORT, want_perm=True)
+                rp, col_t, perm_t = _sorted_csr(graph, graph.t["src_" + a.name], graph.t["dst_" + a.name],
+                                                graph.num[a.src], True)
                 graph.csr_t[a.name] = (rp, col_t, perm_t)
 
     # ------------------------------------------------------------------ backward
@@ -474,6 +482,71 @@ class Trainer:
         self._n_glob = global_n if global_n is not None else n_local * self.world
         self.apply()
         return pred
+
+    def train_step_graphed(self, batch, pinned=None, global_n: Optional[int] = None, copy: bool = True):
+        """``train_step`` for the reference's own batch sizes (train_options.ini: batch_size 3 .. 32), where a step
+        is ~150 launches of a few microseconds each: host -> device copy into a static staging buffer, then ONE captured
+        CUDA graph per batch shape for adjacency build + transposes + forward + loss + backward.  The all-reduce, the
+        regulariser and the optimiser update run after the replay (their step count and learning rate are host
+        scalars that change every step).  Gradients are the same bits as ``train_step``'s kernels produce."""
+        e = self.e
+        if pinned is None:
+            pinned = e.pack(batch)
+        buf, layout = pinned
+        n_local = int(batch.arrays["labels"].size)
+        n_glob = global_n if global_n is not None else n_local * self.world
+        sig = (batch.n_samples, tuple(sorted(batch.num.items())), tuple(sorted(batch.max_seq.items())),
+               tuple(sorted(batch.dst_sorted.items())), n_glob,
+               tuple((k, off, str(np.dtype(dt)), tuple(shape)) for k, (off, dt, shape) in layout.items()))
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        entry = self._graphs.get(sig)
+        if entry is None:
+            dev = e.device
+            stage = torch.empty(buf.numel(), dtype=torch.uint8, device=dev)
+            dg = e.upload(batch, pinned, out=stage)
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # eager pass first: one-time kernel attributes, workspace sizes
+                e.build_graph(dg, training=True)
+                self.loss_and_grads(dg, n_glob)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            l0 = self.e.gpu_launches
+            with torch.cuda.graph(graph):
+                dg.csr_t.clear()
+                e.build_graph(dg, training=True)
+                pred, _ = self.loss_and_grads(dg, n_glob)
+            entry = (graph, stage, dg, pred, self.e.gpu_launches - l0)
+            self._graphs[sig] = entry
+            copy = True
+        graph, stage, dg, pred, _ = entry
+        if copy:
+            stage.copy_(buf, non_blocking=True)
+        graph.replay()
+        self._n_glob = n_glob
+        self.apply()
+        return pred
+
+    def step_batch(self, batch, global_n: Optional[int] = None, graph_rows: int = 8192, max_graphs: int = 32):
+        """One optimiser step on a host batch, picking the path: small batches whose shape was seen twice before go
+        through ``train_step_graphed`` (capture on the third occurrence, replay afterwards; at most ``max_graphs``
+        shapes are kept), everything else through upload + build + ``train_step``."""
+        e = self.e
+        if graph_rows > 0 and max(batch.num.values()) <= graph_rows:
+            pinned = e.pack(batch)
+            key = (batch.n_samples, tuple(sorted(batch.num.items())), tuple(sorted(batch.max_seq.items())),
+                   tuple(sorted(batch.dst_sorted.items())), global_n, pinned[0].numel())
+            if not hasattr(self, "_shape_seen"):
+                self._shape_seen, self._shape_captured = {}, set()
+            self._shape_seen[key] = self._shape_seen.get(key, 0) + 1
+            if key in self._shape_captured or (self._shape_seen[key] >= 3 and len(self._shape_captured) < max_graphs):
+                self._shape_captured.add(key)
+                return self.train_step_graphed(batch, pinned, global_n)
+            return self.train_step(e.build_graph(e.upload(batch, pinned), training=True), global_n=global_n)
+        return self.train_step(e.build_graph(e.upload(batch), training=True), global_n=global_n)
 
     def losses(self):
         s = self.scalars.cpu().numpy()

@@ -12,13 +12,17 @@ from oracle import ignnition_oracle as orc
 pytestmark = pytest.mark.gpu
 
 
-def test_forward_graphed_matches_eager_and_oracle():
+@pytest.mark.parametrize("one_launch", [True, False])
+def test_forward_graphed_matches_eager_and_oracle(one_launch):
+    """``one_launch`` False: the per-stage kernels inside the graph (what batches above 8192 rows capture)"""
     from ignnition_b200 import Engine, ModelDescription, synthetic
     from ignnition_b200.generator import sample_to_tensors
     g = load_golden("routenet_nsfnet")
     dims = g["reference_meta"]["dimensions"]
     md = ModelDescription(g["model_json"], dims)
     eng = Engine(md, device="cuda:0", seed=0)
+    if not one_launch:
+        eng.small_graph_rows = 0
     o64 = orc.Oracle(g["model_json"], dims, dtype=np.float64)
     feats = [f.name for f in md.get_all_features()]
 
@@ -106,3 +110,35 @@ def test_one_launch_loop_matches_per_stage_fp32_bitwise(case):
         assert torch.equal(eng.forward_graphed(batch), pred)
     # a training graph keeps the per-stage kernels (the backward needs the walk's tables)
     assert not eng.prepare(tens, training=True).small
+
+
+def test_train_step_graphed_matches_eager_steps():
+    """Trainer.train_step_graphed (adjacency build + forward + loss + backward as one captured graph per batch shape,
+    optimiser update outside) walks the same weights as Trainer.train_step over a stream of batches with new
+    topologies and features (the weight-gradient flush uses fp32 atomics: 1e-5, not bit for bit)"""
+    from ignnition_b200 import Engine, ModelDescription, synthetic
+    from ignnition_b200.generator import sample_to_tensors
+    from ignnition_b200.train import Trainer
+    g = load_golden("routenet_nsfnet")
+    dims = g["reference_meta"]["dimensions"]
+    md = ModelDescription(g["model_json"], dims)
+    feats = [f.name for f in md.get_all_features()]
+
+    def sample(seed):
+        t, y = sample_to_tensors(synthetic.routenet_sample("nsfnet", seed, seed), feats, "delay",
+                                 md.get_adjecency_info(), [], [], True)
+        return orc.normalize_inputs(g["model_json"], t), np.log(np.asarray(y, np.float32))
+
+    engines = [Engine(md, device="cuda:0", seed=1) for _ in range(2)]
+    trainers = [Trainer(e) for e in engines]
+    for step in range(4):
+        both = [sample(100 + 3 * step + k) for k in range(3)]
+        tens, labels = [b[0] for b in both], [b[1] for b in both]
+        batch = engines[0].assemble(tens, labels)
+        trainers[0].train_step(engines[0].prepare(batch, training=True))
+        trainers[1].train_step_graphed(engines[1].assemble(tens, labels))
+        a, b = trainers[0].losses(), trainers[1].losses()
+        assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(a["loss"])
+    w0, w1 = engines[0].weights.cpu().numpy(), engines[1].weights.cpu().numpy()
+    assert float(np.abs(w0 - w1).max() / np.abs(w0).max()) < 1e-5
+    assert 1 <= len(trainers[1]._graphs) <= 4 and trainers[1].step == 4

@@ -914,8 +914,8 @@ def test_new_kernels_write_only_their_outputs():
 
 def test_csr_build_small_one_launch_bit_exact():
     """ign_csr_build_small (one CTA per adjacency, one launch for the whole graph) against the oracle's CSR: an
-    adjacency placed by seq, one grouped by destination without seq, one in random order without seq (the single-warp
-    stable placement), one without edges, and a seq with a gap (the unclaimed slot stays -1)."""
+    adjacency placed by seq, one grouped by destination without seq, two in random order without seq (short rows: atomic placement + per-row sort of the edge ids;
+    a row of ~800 edges: one warp walking the list), one without edges, and a seq with a gap (the unclaimed slot stays -1)."""
     from ignnition_b200 import ops
     rng = np.random.RandomState(17)
     src_a, dst_a, seq_a = random_edges(rng, 700, 300, 9)
@@ -927,17 +927,22 @@ def test_csr_build_small_one_launch_bit_exact():
     empty = np.zeros(0, np.int32)
     dst_e, seq_e, src_e = np.array([0, 0, 2]), np.array([0, 2, 0]), np.array([5, 6, 7])   # destination 0: slot 1 unclaimed
     i32 = lambda a: dev(np.asarray(a), torch.int32)
+    dst_d = np.where(rng.rand(2000) < 0.4, 7, rng.randint(0, 50, 2000))          # a row of ~800 edges, any order
+    src_d = rng.randint(0, 500, 2000)
     specs = [(i32(dst_a), i32(src_a), i32(seq_a), 700, True), (i32(dst_b), i32(src_b), None, 3000, True),
              (i32(dst_c), i32(src_c), None, 9000, True), (i32(empty), i32(empty), None, 12, False),
-             (i32(dst_e), i32(src_e), i32(seq_e), 3, True)]
+             (i32(dst_e), i32(src_e), i32(seq_e), 3, True), (i32(dst_d), i32(src_d), None, 50, True),
+             (i32(dst_c), i32(src_c), None, 9000, False)]
     l0 = ops._lib.load().ign_launch_count()
     out = ops.csr_build_small(specs)
     assert ops._lib.load().ign_launch_count() - l0 == 1
     r, c, p = orc.csr_from_edges(src_a, dst_a, seq_a, 700)
     assert all(np.array_equal(x.cpu().numpy(), y) for x, y in zip(out[0], (r, c, p)))
-    for k, (s_, d_, n_) in ((1, (src_b, dst_b, 3000)), (2, (src_c, dst_c, 9000))):
+    for k, (s_, d_, n_) in ((1, (src_b, dst_b, 3000)), (2, (src_c, dst_c, 9000)), (5, (src_d, dst_d, 50))):
         r, c, p = orc.stable_sort_csr(s_, d_, n_)
         assert all(np.array_equal(x.cpu().numpy(), y) for x, y in zip(out[k], (r, c, p))), k
+    r, c, _ = orc.stable_sort_csr(src_c, dst_c, 9000)          # no perm asked for: the ids are sorted inside col
+    assert np.array_equal(out[6][0].cpu().numpy(), r) and np.array_equal(out[6][1].cpu().numpy(), c) and out[6][2] is None
     assert np.array_equal(out[3][0].cpu().numpy(), np.zeros(13)) and out[3][2] is None
     assert np.array_equal(out[4][0].cpu().numpy(), [0, 2, 2, 3])
     assert np.array_equal(out[4][1].cpu().numpy(), [5, -1, 7]) and np.array_equal(out[4][2].cpu().numpy(), [0, -1, 2])
