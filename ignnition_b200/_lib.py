@@ -75,7 +75,8 @@ SIGNATURES = {
     "ign_attention_aggregate": (_int, [_p, _p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "ign_csr_build_small": (_int, [_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ign_small_graph_ws_bytes": (_sz, []),
-    "ign_small_graph_forward": (_int, [_int, _int, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p, _int, _p, _p, _sz, _p]),
+    "ign_small_graph_forward": (_int, [_int, _int, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p,
+                                       _p, _sz, _p]),
     "ign_attention_combine": (_int, [_int, _p, _p, _p, _i64, _int, _p, _p, _p, _p]),
     "ign_attention_bwd_ws_bytes": (_sz, [_i64, _i64, _int]),
     "ign_attention_aggregate_bwd": (_int, [_p, _p, _p, _p, _p, _int, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _p, _p, _sz, _p]),

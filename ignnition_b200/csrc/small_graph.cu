@@ -23,6 +23,7 @@ namespace {
 
 constexpr int SG_MAX_OPS = 8;
 constexpr int SG_MAX_ENT = 8;
+constexpr int SG_MAX_STEPS = 64;      // stages x iterations when every stage keeps its outputs (training)
 constexpr int SG_THREADS = 512;       // 16 warps per SM: the stages are latency chains, more rows in flight is what pays
 constexpr int SG_AHEAD = 8;           // message rows of a walk in flight ahead of the step that consumes them
 
@@ -43,6 +44,13 @@ struct SgProgram {
   float* buf[SG_MAX_ENT][2];
   SgOp op[SG_MAX_OPS];
   unsigned int* barrier;
+  // training (tf.gradients needs every intermediate, generate_model.py:791): stage s = iteration * n_ops + o writes
+  // its new states to step_out[s] instead of the entity's other buffer, the state after every step of a walk to
+  // step_hseq[s] (row = position of the step entry) and the neighbour sum to step_agg[s]
+  int keep;
+  float* step_out[SG_MAX_STEPS];
+  float* step_hseq[SG_MAX_STEPS];
+  float* step_agg[SG_MAX_STEPS];
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -113,6 +121,8 @@ struct SgStage {
   const float* w;
   const float* hcur;
   float* hout;
+  float* hseq;      // training: state after every step of the walk, or nullptr
+  float* agg;       // training: the neighbour sum, or nullptr
   const float* tbl[IGN_MAX_SOURCES];
   int n;
 };
@@ -185,6 +195,11 @@ __device__ __forceinline__ void run_rows(const SgStage& sg, const int (&first)[N
             act[i] = t < len[i];
           }
           gru_step<U, NR>(sg.w, x, h, act, u);
+          if (sg.hseq) {
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+              if (act[i]) sg.hseq[(int64_t)(lo[i] + t) * U + u] = h[i];
+          }
         }
       }
     }
@@ -210,6 +225,11 @@ __device__ __forceinline__ void run_rows(const SgStage& sg, const int (&first)[N
         for (int q = 0; q < U; ++q)
           if (q < cnt && t0 + q < len[i]) x[i] += r[q];
       }
+    }
+    if (sg.agg) {
+#pragma unroll
+      for (int i = 0; i < NR; ++i)
+        if (valid[i]) sg.agg[(int64_t)(first[i] + sub) * U + u] = x[i];
     }
     gru_step<U, NR>(sg.w, x, h, act, u);
   }
@@ -243,7 +263,9 @@ __global__ void __launch_bounds__(SG_THREADS, 1) small_graph_kernel(const __grid
   const int warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int n_warps = gridDim.x * (SG_THREADS / 32);
   const int stride = n_warps * RPW;
-  unsigned cur = 0;                                // bit e: which buffer of entity e holds its current state
+  __shared__ float* s_cur[SG_MAX_ENT];             // where every entity's current state lives
+  if (threadIdx.x < SG_MAX_ENT) s_cur[threadIdx.x] = pg.buf[threadIdx.x][0];
+  __syncthreads();
   unsigned target = 0;
   const int total = pg.iterations * pg.n_ops;
   for (int step = 0; step < total; ++step) {
@@ -252,11 +274,12 @@ __global__ void __launch_bounds__(SG_THREADS, 1) small_graph_kernel(const __grid
     sg.op = &pg.op[o];
     sg.w = sw + o * WF;
     sg.n = pg.rows[sg.op->dst];
-    sg.hcur = pg.buf[sg.op->dst][(cur >> sg.op->dst) & 1u];
-    sg.hout = pg.buf[sg.op->dst][((cur >> sg.op->dst) & 1u) ^ 1u];
+    sg.hcur = s_cur[sg.op->dst];
+    sg.hout = pg.keep ? pg.step_out[step] : (sg.hcur == pg.buf[sg.op->dst][0] ? pg.buf[sg.op->dst][1] : pg.buf[sg.op->dst][0]);
+    sg.hseq = pg.keep ? pg.step_hseq[step] : nullptr;
+    sg.agg = pg.keep ? pg.step_agg[step] : nullptr;
 #pragma unroll
-    for (int k = 0; k < IGN_MAX_SOURCES; ++k)
-      sg.tbl[k] = sg.op->src[k] >= 0 ? pg.buf[sg.op->src[k]][(cur >> sg.op->src[k]) & 1u] : nullptr;
+    for (int k = 0; k < IGN_MAX_SOURCES; ++k) sg.tbl[k] = sg.op->src[k] >= 0 ? s_cur[sg.op->src[k]] : nullptr;
     int* slot_e = cache + o * (SG_THREADS + SG_THREADS / 32 * 4) + threadIdx.x;
     int* slot_ll = cache + o * (SG_THREADS + SG_THREADS / 32 * 4) + SG_THREADS + ((threadIdx.x >> 5) * 2 + sub) * 2;
     if (sg.n <= stride) {                          // at most one row (pair) per warp: its metadata stays in shared memory
@@ -273,7 +296,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) small_graph_kernel(const __grid
         run_rows<U, 1>(sg, first, u, sub, slot_e, slot_ll, false, false);
       }
     }
-    cur ^= 1u << sg.op->dst;
+    __syncthreads();                               // every warp has read this stage's pointers
+    if (threadIdx.x == 0) s_cur[sg.op->dst] = sg.hout;
 #ifdef IGN_SG_PROFILE                              // CTA 0: stage start, rows done, barrier passed (ns)
     unsigned long long* prof = reinterpret_cast<unsigned long long*>(pg.barrier) + 8;
     unsigned long long t_done = 0;
@@ -472,6 +496,7 @@ extern "C" int ign_small_graph_forward(int units, int n_entities, const int64_t*
                                        const int32_t* op_src, const int32_t* const* op_rowptr,
                                        const int32_t* const* op_idx, const float* const* op_kernel,
                                        const float* const* op_rkernel, const float* const* op_bias, int iterations,
+                                       float* const* step_out, float* const* step_hseq, float* const* step_agg,
                                        int32_t* final_buffer, void* ws, size_t ws_bytes, void* stream) {
   IGN_REQUIRE(units == 16 || units == 32, IGN_ERR_UNSUPPORTED, "IGNNITION: small_graph: 16 or 32 units, got %d", units);
   IGN_REQUIRE(n_entities >= 1 && n_entities <= SG_MAX_ENT && n_ops >= 1 && n_ops <= SG_MAX_OPS && iterations >= 0,
@@ -480,7 +505,17 @@ extern "C" int ign_small_graph_forward(int units, int n_entities, const int64_t*
                   op_bias && final_buffer,
               IGN_ERR_INVALID, "IGNNITION: small_graph: null pointer");
   IGN_REQUIRE(ws && ws_bytes >= sizeof(unsigned int), IGN_ERR_WORKSPACE, "IGNNITION: small_graph: workspace too small");
+  IGN_REQUIRE(!step_out || ((int64_t)iterations * n_ops <= SG_MAX_STEPS && step_hseq && step_agg), IGN_ERR_UNSUPPORTED,
+              "IGNNITION: small_graph: keeping every stage's outputs is built for at most %d stages x iterations",
+              SG_MAX_STEPS);
   SgProgram pg;
+  pg.keep = step_out ? 1 : 0;
+  for (int i = 0; i < SG_MAX_STEPS; ++i) {
+    const bool used = step_out && i < iterations * n_ops;
+    pg.step_out[i] = used ? step_out[i] : nullptr;
+    pg.step_hseq[i] = used ? step_hseq[i] : nullptr;
+    pg.step_agg[i] = used ? step_agg[i] : nullptr;
+  }
   pg.n_ops = n_ops;
   pg.n_ent = n_entities;
   pg.iterations = iterations;
@@ -518,6 +553,9 @@ extern "C" int ign_small_graph_forward(int units, int n_entities, const int64_t*
     op.bias = op_bias[o];
     if (pg.rows[op.dst] > max_rows) max_rows = pg.rows[op.dst];
     final_buffer[op.dst] ^= iterations & 1;
+    for (int it = 0; step_out && it < iterations; ++it)
+      IGN_REQUIRE(pg.rows[op.dst] == 0 || step_out[it * n_ops + o], IGN_ERR_INVALID,
+                  "IGNNITION: small_graph: null output buffer of stage %d", it * n_ops + o);
   }
   if (iterations == 0 || max_rows == 0) {
     for (int e = 0; e < n_entities; ++e) final_buffer[e] = 0;

@@ -767,32 +767,63 @@ class Engine:
             self._small_ok = ok
         return ok
 
-    def _mp_small(self, g: DeviceGraph, state: Dict[str, torch.Tensor], T: int) -> Dict[str, torch.Tensor]:
+    def _mp_small(self, g: DeviceGraph, state: Dict[str, torch.Tensor], T: int,
+                  tape: Optional[list] = None) -> Dict[str, torch.Tensor]:
+        """The T-iteration loop in one launch.  With a ``tape`` (training) every stage keeps what the backward pass
+        reads -- its new states, the state after every step of a walk, the neighbour sum -- and the tape gets the same
+        entries, in the same order, as the per-stage kernels would have written."""
         eid = {e: i for i, e in enumerate(self.entities)}
         buf0 = [state[e] for e in self.entities]
-        buf1 = [torch.empty_like(t) for t in buf0]
+        buf1 = [torch.empty_like(t) if tape is None else t for t in buf0]
+        flat = [p for stage in self.plans for p in stage]
         kinds, dsts, srcs, rowptrs, idxs, Ks, Rs, Bs = [], [], [], [], [], [], [], []
-        for stage in self.plans:
-            for p in stage:
-                seq = p.kind == "seq_gru"
-                rowptr, idx = g.steps[p.key] if seq else g.csr[p.adjs[0].name][:2]
-                kinds.append(0 if seq else 1)
-                dsts.append(eid[p.dst])
-                srcs.append([eid[a.src] for a in p.adjs])
-                rowptrs.append(rowptr)
-                idxs.append(idx)
-                Ks.append(self.param(p.dst + "_update/kernel"))
-                Rs.append(self.param(p.dst + "_update/recurrent_kernel"))
-                Bs.append(self.param(p.dst + "_update/bias"))
-        final = ops.small_graph_forward(next(iter(self.hidden.values())), [g.num[e] for e in self.entities], buf0, buf1,
-                                        kinds, dsts, srcs, rowptrs, idxs, Ks, Rs, Bs, T)
-        return {e: (buf1 if final[i] else buf0)[i] for i, e in enumerate(self.entities)}
+        for p in flat:
+            seq = p.kind == "seq_gru"
+            rowptr, idx = g.steps[p.key] if seq else g.csr[p.adjs[0].name][:2]
+            kinds.append(0 if seq else 1)
+            dsts.append(eid[p.dst])
+            srcs.append([eid[a.src] for a in p.adjs])
+            rowptrs.append(rowptr)
+            idxs.append(idx)
+            Ks.append(self.param(p.dst + "_update/kernel"))
+            Rs.append(self.param(p.dst + "_update/recurrent_kernel"))
+            Bs.append(self.param(p.dst + "_update/bias"))
+        U = next(iter(self.hidden.values()))
+        rows = [g.num[e] for e in self.entities]
+        if tape is None:
+            final = ops.small_graph_forward(U, rows, buf0, buf1, kinds, dsts, srcs, rowptrs, idxs, Ks, Rs, Bs, T)
+            return {e: (buf1 if final[i] else buf0)[i] for i, e in enumerate(self.entities)}
+        outs, hseqs, aggs = [], [], []
+        cur = dict(state)
+        for _ in range(T):
+            for k, p in enumerate(flat):
+                h = cur[p.dst]
+                out = torch.empty_like(h)
+                if kinds[k] == 0:
+                    h_seq = torch.empty(max(int(idxs[k].numel()), 1), U, dtype=torch.float32, device=self.device)
+                    tape.append(("seq_gru", p, [cur[a.src] for a in p.adjs], h, h_seq, None))
+                    hseqs.append(h_seq)
+                    aggs.append(None)
+                else:
+                    agg = torch.empty_like(h)
+                    tape.append(("agg_gru", p, [False], h, agg, None))
+                    hseqs.append(None)
+                    aggs.append(agg)
+                outs.append(out)
+                cur[p.dst] = out
+        ops.small_graph_forward(U, rows, buf0, buf1, kinds, dsts, srcs, rowptrs, idxs, Ks, Rs, Bs, T,
+                                step_out=outs, step_hseq=hseqs, step_agg=aggs)
+        return cur
 
     def message_passing(self, g: DeviceGraph, state: Dict[str, torch.Tensor], iterations: Optional[int] = None,
                         tape: Optional[list] = None) -> Dict[str, torch.Tensor]:
         T = self.T if iterations is None else iterations
         if tape is None and g.small and T > 0:
             return self._mp_small(g, state, T)
+        n_stages = sum(len(stage) for stage in self.plans)
+        if (tape is not None and g.small_rows and T > 0 and T * n_stages <= 64 and self.small_graph_rows > 0
+                and self._small_program_ok()):
+            return self._mp_small(g, state, T, tape)
         for _ in range(T):
             for stage in self.plans:
                 for p in stage:

@@ -684,9 +684,11 @@ def attention_aggregate_bwd(rowptr, idx, perm, rows, g_out, sample_offsets, max_
 
 
 def small_graph_forward(units: int, rows: Sequence[int], buf0, buf1, kinds: Sequence[int], dsts: Sequence[int],
-                        srcs: Sequence[Sequence[int]], rowptrs, idxs, kernels, rkernels, biases, iterations: int):
+                        srcs: Sequence[Sequence[int]], rowptrs, idxs, kernels, rkernels, biases, iterations: int,
+                        step_out=None, step_hseq=None, step_agg=None):
     """All ``iterations`` of the message-passing loop of a small graph in one launch (ign_small_graph_forward).
-    Returns, per entity, which of its two buffers (0 / 1) holds the final state."""
+    Returns, per entity, which of its two buffers (0 / 1) holds the final state.  ``step_out`` / ``step_hseq`` /
+    ``step_agg`` (lists of iterations * stages tensors or None): keep every stage's outputs, for training."""
     lib = _lib.load()
     n_ent, n_ops = len(rows), len(kinds)
     dev = next(b.device for b in buf0 if b is not None)
@@ -702,7 +704,10 @@ def small_graph_forward(units: int, rows: Sequence[int], buf0, buf1, kinds: Sequ
         (C.c_int32 * n_ops)(*[int(d) for d in dsts]), (C.c_int32 * (4 * n_ops))(*flat_src),
         _ptr_array(rowptrs, torch.int32), _ptr_array([i if i is not None and i.numel() else None for i in idxs], torch.int32),
         _ptr_array(kernels, torch.float32), _ptr_array(rkernels, torch.float32), _ptr_array(biases, torch.float32),
-        int(iterations), final, ws.data_ptr(), nbytes, _stream()), "small_graph_forward")
+        int(iterations), _ptr_array(step_out, torch.float32) if step_out is not None else None,
+        _ptr_array(step_hseq, torch.float32) if step_out is not None else None,
+        _ptr_array(step_agg, torch.float32) if step_out is not None else None,
+        final, ws.data_ptr(), nbytes, _stream()), "small_graph_forward")
     return [int(v) for v in final]
 
 

@@ -404,7 +404,12 @@ int ign_attention_combine(int n_sources, const int32_t* const* src_rowptr, const
  *   op_kind[o]       0 = ordered walk over step entries (IGN_STEP_* encoding, op_src = entity of each source id),
  *                    1 = sum over the CSR row of op_src[o*4] + one GRU step
  *   op_dst[o], op_src[o*4 .. o*4+3] (-1 = unused), op_rowptr[o], op_idx[o], op_kernel/rkernel/bias[o] (Keras GRU v2)
- *   final_buffer[e]  (host, out) which of the two buffers holds entity e's state after the last iteration
+ *   step_out / step_hseq / step_agg   NULL for inference.  Training (tf.gradients needs every intermediate,
+ *                    generate_model.py:791): arrays of iterations * n_ops pointers, stage s = iteration * n_ops + o writes
+ *                    its new states to step_out[s] ([rows, units], instead of the entity's other buffer), the state after
+ *                    every step of a walk to step_hseq[s] ([step entries, units], as ign_gru_seq's h_seq) and the neighbour
+ *                    sum of a kind-1 stage to step_agg[s] ([rows, units]); hseq / agg entries may be NULL.  At most 64 stages.
+ *   final_buffer[e]  (host, out) which of the two buffers holds entity e's state after the last iteration (inference)
  *   ws               ign_small_graph_ws_bytes() of device memory (the barrier counter)
  * All stages of one iteration run in order o = 0 .. n_ops-1, each seeing the states the previous ones wrote. */
 size_t ign_small_graph_ws_bytes(void);
@@ -412,7 +417,8 @@ int ign_small_graph_forward(int units, int n_entities, const int64_t* rows, floa
                             int n_ops, const int32_t* op_kind, const int32_t* op_dst, const int32_t* op_src,
                             const int32_t* const* op_rowptr, const int32_t* const* op_idx,
                             const float* const* op_kernel, const float* const* op_rkernel,
-                            const float* const* op_bias, int iterations, int32_t* final_buffer, void* ws,
+                            const float* const* op_bias, int iterations, float* const* step_out,
+                            float* const* step_hseq, float* const* step_agg, int32_t* final_buffer, void* ws,
                             size_t ws_bytes, void* stream);
 
 /* ign_csr_build for all adjacencies of a SMALL graph in one launch, one CTA per adjacency (at most 8 adjacencies, 11000

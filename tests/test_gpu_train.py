@@ -361,13 +361,15 @@ def test_full_size_qsize_properties_inference_and_training():
         assert rel_err(b_, c) < tol, ("replicas vs one sample", name, rel_err(b_, c))
 
 
-def _grad_check(model_json, samples, graph_level=False):
+def _grad_check(model_json, samples, graph_level=False, one_launch=False):
     from test_gpu_model import make, tensors_of
     from ignnition_b200.generator import sample_dimensions
     from ignnition_b200.train import Trainer
     from ignnition_b200 import ops
     dims = sample_dimensions(samples[0])
     md, eng, o64, w = make(model_json, dims)
+    if one_launch:          # the forward of the train step as one persistent launch that keeps every stage's outputs
+        eng.small_graph_rows = 8192
     both = [tensors_of(md, s) for s in samples]
     tens, labels = [b[0] for b in both], [np.asarray(b[1], np.float32) for b in both]
     tr = Trainer(eng)
@@ -542,6 +544,29 @@ def test_gradients_two_source_attention(message_nn):
     samples = [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 40)]
     eng = _grad_check(_two_source_attention(message_nn), samples)
     assert "path_attention/kernel1" in eng.param_table
+
+
+@pytest.mark.parametrize("model", ["two_entity_ordered_16", "sum_32", "interleave_like"])
+def test_gradients_with_one_launch_forward(model):
+    """small graphs: the forward of the train step runs as ONE launch (csrc/small_graph.cu) that keeps what the
+    backward reads -- every stage's new states, the state after every step of a walk, the neighbour sums; every
+    gradient vs fp64 autograd, as for the per-stage kernels"""
+    from test_gpu_model import _mpnn_json, _mpnn_sample, _two_entity_json, _two_entity_sample
+    rng = np.random.RandomState(91)
+    if model == "sum_32":
+        mj, samples = _mpnn_json("sum", 32), [_mpnn_sample(rng, n, 5) for n in (25, 140)]
+    else:
+        mj = _two_entity_json({"type": "ordered"} if model == "two_entity_ordered_16" else {"type": "concat", "concat_axis": 1})
+        samples = [_two_entity_sample(rng, 6, 5, 9), _two_entity_sample(rng, 12, 7, 30)]
+    launches = []
+    from ignnition_b200 import ops
+    orig = ops.small_graph_forward
+    ops.small_graph_forward = lambda *a, **k: (launches.append(k.get("step_out") is not None), orig(*a, **k))[1]
+    try:
+        _grad_check(mj, samples, one_launch=True)
+    finally:
+        ops.small_graph_forward = orig
+    assert launches == [True]
 
 
 def test_generic_width_trains():

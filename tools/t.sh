@@ -8,7 +8,7 @@ import json
 l=json.loads(open('gpurun_out/r2_bench_n1.json').read().strip().splitlines()[-1])
 print({k:l[k] for k in ('value','ms_per_step','gpu_launches')}, l['e2e']['value'], l['roofline']['frac'])
 for a in l.get('also',[]):
-    print(a.get('workload'), a.get('samples_per_gpu'), a.get('mode'), a.get('ms_per_step'), a.get('value'), a.get('error'))
+    print(a.get('workload'), a.get('samples_per_gpu'), a.get('mode'), a.get('ms_per_step'), a.get('value'), a.get('launches_per_step'), a.get('error'))
     if 'train' in str(a.get('mode')) and a.get('samples_per_gpu') in (3, 32):
-        for k in a.get('top_kernels',[])[:5]: print('      ',k)
+        for k in a.get('top_kernels',[])[:6]: print('      ',k)
 PY
