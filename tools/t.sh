@@ -1,14 +1,10 @@
 #!/bin/sh
-timeout 900 python -m pytest tests -q -m gpu > gpurun_out/r2_pytest_gpu.log 2>&1
-tail -4 gpurun_out/r2_pytest_gpu.log
-timeout 900 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err
-tail -c 600 gpurun_out/r2_bench_n1.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
+tail -c 400 gpurun_out/r2_bench_n2.err
 python - <<'PY'
 import json
-l=json.loads(open('gpurun_out/r2_bench_n1.json').read().strip().splitlines()[-1])
-print({k:l[k] for k in ('value','ms_per_step','gpu_launches')}, l['e2e']['value'], l['roofline']['frac'])
+l=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1])
+print({k:l[k] for k in ('value','ms_per_step','gpu_launches','n_gpus')}, l['e2e']['value'])
 for a in l.get('also',[]):
-    print(a.get('workload'), a.get('samples_per_gpu'), a.get('mode'), a.get('ms_per_step'), a.get('value'), a.get('launches_per_step'), a.get('error'))
-    if 'train' in str(a.get('mode')) and a.get('samples_per_gpu') in (3, 32):
-        for k in a.get('top_kernels',[])[:6]: print('      ',k)
+    print(a.get('workload'), a.get('samples_per_gpu'), a.get('mode'), a.get('ms_per_step'), a.get('value'), a.get('error'))
 PY
