@@ -112,6 +112,7 @@ class Engine:
         # persistent launch (csrc/small_graph.cu) when every stage is an ordered or sum update of 16 / 32-wide states;
         # 0 = never.  The reference's default batch (3 samples) is 546 paths: 16 dependent launches were all gaps
         self.small_graph_rows = int(os.environ.get("IGN_SMALL_GRAPH_ROWS", "8192"))
+        self.max_graphs = 32            # captured CUDA graphs kept by forward_graphed (one per batch shape)
         self.bwd_steps_min_rows = ops.BWD_STEPS_MIN_ROWS   # below: the fp32 BPTT walk (one launch) instead of 2 launches per step
         self._needs_perm = set()
         self.plans: List[List[_MPPlan]] = []
@@ -395,6 +396,10 @@ class Engine:
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         entry = self._graphs.get(sig)
+        if entry is None and len(self._graphs) >= self.max_graphs:
+            # a dataset whose samples rarely share a shape: every captured graph keeps its own memory pool, so the
+            # cache is bounded; further new shapes run the same kernels launch by launch
+            return self.forward(self.build_graph(self.upload(batch, pinned)))
         if entry is None:
             stage = torch.empty(buf.numel(), dtype=torch.uint8, device=self.device)
             dg = self.upload(batch, pinned, out=stage)
