@@ -16,6 +16,7 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int GEMM_THREADS = 256;
+constexpr int64_t DENSE_TC_MIN_ROWS = 4096;     // fewer rows: the fp32 kernels (see ign_dense)
 constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
 
 // C[M,N] (+)= op(A) op(B);  TA: A is stored [K,M] (read transposed); TB: B is stored [N,K].
@@ -316,12 +317,14 @@ __global__ void __launch_bounds__(256) dense_head_fwd_kernel(const float* __rest
 // dz = dy * act'(pre), in place; db += column sums of dz (per-CTA partial, then atomics)
 __global__ void __launch_bounds__(256) act_bwd_bias_kernel(float* __restrict__ dy, const float* __restrict__ pre,
                                                            int64_t M, int N, int act, float* __restrict__ db,
-                                                           bool from_out) {
-  // each CTA covers 64 rows; thread t handles columns t, t+256, ...
-  const int64_t r0 = (int64_t)blockIdx.x * 64;
-  const int64_t r1 = min(M, r0 + 64);
+                                                           bool from_out, int rows_per_cta) {
+  // each CTA covers rows_per_cta rows (64, fewer for a small batch: the rows of a thread are one dependent chain of
+  // loads); thread t handles columns t, t+256, ...
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(M, r0 + rows_per_cta);
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float s = 0.0f;
+#pragma unroll 4
     for (int64_t r = r0; r < r1; ++r) {
       float g = dy[r * N + n];
       if (act != IGN_ACT_LINEAR) {
@@ -548,8 +551,10 @@ extern "C" int ign_dense(const float* x, int64_t m, int k, const float* w, const
   if (m == 0) return IGN_OK;
   IGN_REQUIRE(x && w && y, IGN_ERR_INVALID, "IGNNITION: dense: null pointer");
   cudaStream_t st = ign_stream(stream);
+  // (below 4096 rows the tensor-core kernel's fixed latency -- weight image, TMEM, barriers: ~30 us -- is three times
+  // the fp32 kernel's whole run: 546 rows x 256 x 256 take 8 us on the CUDA cores)
   if (ws && ign_tensor_cores_enabled() && ign_dense_tc_supported(k, n) && ws_bytes >= ign_dense_tc_ws(k, n) &&
-      m >= 128)
+      m >= DENSE_TC_MIN_ROWS)
     return ign_dense_tc_launch(x, m, k, w, bias, n, act, y, pre_act, ws, st);
   if (n <= 8) {
     if (n == 1 && (k == 128 || k == 256 || k == 512) && m >= 1024) {
@@ -630,7 +635,11 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
   cudaStream_t st = ign_stream(stream);
   if (act != IGN_ACT_LINEAR || db) {
     if (n <= 8) act_bwd_bias_small_kernel<<<(unsigned)ign_cdiv(m, 256), 256, 0, st>>>(dy, pre_act, m, n, act, db, from_out);
-    else act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, 64), 256, 0, st>>>(dy, pre_act, m, n, act, db, from_out);
+    else {
+      int64_t rows = ign_cdiv(m, 2 * IGN_NUM_SMS);          // two CTAs per SM before a CTA takes more rows
+      rows = rows < 4 ? 4 : rows > 64 ? 64 : rows;
+      act_bwd_bias_kernel<<<(unsigned)ign_cdiv(m, rows), 256, 0, st>>>(dy, pre_act, m, n, act, db, from_out, (int)rows);
+    }
     IGN_CHECK_LAUNCH("act_bwd_bias");
   }
   if (!dx && !dw) return IGN_OK;                             // only the activation / bias step was asked for
@@ -647,7 +656,7 @@ extern "C" int ign_dense_bwd(const float* x, int64_t m, int k, const float* w, i
     return IGN_OK;
   }
   if (dx && ws && ign_tensor_cores_enabled() && ign_dense_tc_supported(n, k) && ws_bytes >= ign_dense_tc_ws(n, k) &&
-      m >= 128) {
+      m >= DENSE_TC_MIN_ROWS) {
     // tensor cores (3xTF32): y[m, k] = dZ[m, n] . W^T[n, k]
     int rc = ign_dense_tc_launch(dy, m, n, w, nullptr, k, IGN_ACT_LINEAR, dx, nullptr, ws, st, nullptr, nullptr,
                                  nullptr, true);

@@ -461,7 +461,7 @@ def gather_concat(parts: List[torch.Tensor], idx: List[Optional[torch.Tensor]], 
 def gather_dense_supported(widths: Sequence[int], units: int, rows: int) -> bool:
     lib = _lib.load()
     wd = (C.c_int32 * len(widths))(*[int(v) for v in widths])
-    return (rows >= 128 and len(widths) <= 4 and tensor_cores_enabled()
+    return (rows >= 4096 and len(widths) <= 4 and tensor_cores_enabled()      # fewer rows: fp32 kernels (ign_dense)
             and os.environ.get("IGN_GATHER_DENSE", "1") != "0"
             and lib.ign_gather_dense_ws_bytes(len(widths), wd, int(units)) > 0)
 

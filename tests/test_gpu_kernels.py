@@ -822,7 +822,7 @@ def test_csr_rank_gaps_are_zero_rows():
     assert int(bad.item()) == 2
 
 
-@pytest.mark.parametrize("rows,widths,units,act", [(128, [32], 32, "linear"), (1000, [32, 64], 64, "selu"),
+@pytest.mark.parametrize("rows,widths,units,act", [(4096, [32], 32, "linear"), (4133, [32, 64], 64, "selu"),
                                                    (5000, [64, 64, 32], 128, "tanh"), (9000, [32, 32], 32, "relu"),
                                                    (4500, [64, 32, 32, 128], 256, "sigmoid")])
 def test_gather_dense(rows, widths, units, act):

@@ -206,7 +206,8 @@ def _mpnn_sample(rng, n, max_deg, feat=3, params=False):
 def test_generic_mpnn(agg, hidden, update, message_nn, monkeypatch):
     rng = np.random.RandomState(len(agg) + hidden)
     model_json = _mpnn_json(agg, hidden, update, message_nn)
-    samples = [_mpnn_sample(rng, n, 6, params=message_nn is True) for n in (40, 1, 300)]
+    # (the fused gather + GEMM takes over from 4096 edges: below, the fp32 kernels are faster than any tensor-core launch)
+    samples = [_mpnn_sample(rng, n, 6, params=message_nn is True) for n in ((40, 1, 300) if message_nn != "fused" else (40, 1, 2500))]
     if message_nn == "fused":      # the fused path must be the one that runs
         from ignnition_b200 import ops
         calls = []
