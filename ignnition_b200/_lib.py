@@ -73,6 +73,10 @@ SIGNATURES = {
     "ign_adam_step": (_int, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _p]),
     "ign_attention_ws_bytes": (_sz, [_i64, _i64, _int]),
     "ign_attention_aggregate": (_int, [_p, _p, _p, _p, _int, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "ign_gru_v1_reset": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
+    "ign_gru_v1_out": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
+    "ign_gru_v1_bwd_out": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _p]),
+    "ign_gru_v1_bwd_reset": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p]),
     "ign_csr_build_small": (_int, [_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ign_small_graph_ws_bytes": (_sz, []),
     "ign_small_graph_forward": (_int, [_int, _int, _p, _p, _p, _int, _p, _p, _p, _p, _p, _p, _p, _p, _int, _p, _p, _p, _p,

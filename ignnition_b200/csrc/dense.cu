@@ -529,6 +529,69 @@ __global__ void gru_gates_fwd_kernel(const float* __restrict__ zx, const float* 
   out[i] = fmaf(z, h[i] - hh, hh);
 }
 
+// ---- GRUCell with reset_after = False (the Keras v1 cell a model JSON can ask for through the cell parameters,
+// auxilary_classes.py:740-750): the reset gate multiplies h BEFORE the candidate's recurrent product,
+//   zx = x K + b [n, 3U]; zh2 = h R[:, :2U] [n, 2U]; z = s(zx_z + zh2_z); r = s(zx_r + zh2_r);
+//   hh = tanh(zx_h + (r * h) R[:, 2U:]);  h' = z h + (1 - z) hh
+// so one step is three Dense products with two element-wise kernels between them.
+__global__ void gru_v1_reset_kernel(const float* __restrict__ zx, const float* __restrict__ zh2,
+                                    const float* __restrict__ h, int64_t n, int U, float* __restrict__ rh) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * U) return;
+  const int64_t r = i / U;
+  const int u = (int)(i - r * U);
+  rh[i] = sigmoid_f(zx[r * 3 * U + U + u] + zh2[r * 2 * U + U + u]) * h[i];
+}
+
+__global__ void gru_v1_out_kernel(const float* __restrict__ zx, const float* __restrict__ zh2,
+                                  const float* __restrict__ zhh, const float* __restrict__ h, int64_t n, int U,
+                                  float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * U) return;
+  const int64_t r = i / U;
+  const int u = (int)(i - r * U);
+  const float z = sigmoid_f(zx[r * 3 * U + u] + zh2[r * 2 * U + u]);
+  const float hh = tanhf(zx[r * 3 * U + 2 * U + u] + zhh[i]);
+  out[i] = fmaf(z, h[i] - hh, hh);
+}
+
+// backward, first half: the z and candidate slices of zx / zh2 / zhh become their gradients in place (the r slices stay
+// as they are for the second half), dh_direct = d_out * z
+__global__ void gru_v1_bwd_out_kernel(float* __restrict__ zx, float* __restrict__ zh2, float* __restrict__ zhh,
+                                      const float* __restrict__ h, const float* __restrict__ d_out, int64_t n, int U,
+                                      float* __restrict__ dh_direct) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * U) return;
+  const int64_t r = i / U;
+  const int u = (int)(i - r * U);
+  float* px = zx + r * 3 * U + u;
+  float* ph = zh2 + r * 2 * U + u;
+  const float z = sigmoid_f(px[0] + ph[0]);
+  const float hh = tanhf(px[2 * U] + zhh[i]);
+  const float dh = d_out[i];
+  const float g_h = dh * (1.0f - z) * (1.0f - hh * hh);
+  const float g_z = dh * (h[i] - hh) * z * (1.0f - z);
+  px[0] = g_z; ph[0] = g_z;
+  px[2 * U] = g_h; zhh[i] = g_h;
+  dh_direct[i] = dh * z;
+}
+
+// second half: d(r * h) arrives from the candidate's recurrent product; the r slices become their gradient,
+// dh_direct += d_rh * r
+__global__ void gru_v1_bwd_reset_kernel(float* __restrict__ zx, float* __restrict__ zh2, const float* __restrict__ h,
+                                        const float* __restrict__ d_rh, int64_t n, int U, float* __restrict__ dh_direct) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * U) return;
+  const int64_t r = i / U;
+  const int u = (int)(i - r * U);
+  float* px = zx + r * 3 * U + U + u;
+  float* ph = zh2 + r * 2 * U + U + u;
+  const float rr = sigmoid_f(px[0] + ph[0]);
+  const float g_r = d_rh[i] * h[i] * rr * (1.0f - rr);
+  px[0] = g_r; ph[0] = g_r;
+  dh_direct[i] += d_rh[i] * rr;
+}
+
 }  // namespace
 
 bool ign_tensor_cores_enabled();
@@ -747,6 +810,48 @@ extern "C" int ign_gru_gates_fwd(const float* zx, const float* zh, const float* 
   IGN_REQUIRE(zx && zh && h && out, IGN_ERR_INVALID, "IGNNITION: gru_gates_fwd: null pointer");
   gru_gates_fwd_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh, h, n, units, out);
   IGN_CHECK_LAUNCH("gru_gates_fwd");
+  return IGN_OK;
+}
+
+extern "C" int ign_gru_v1_reset(const float* zx, const float* zh2, const float* h, int64_t n, int units, float* rh,
+                                void* stream) {
+  IGN_REQUIRE(n >= 0 && units > 0, IGN_ERR_INVALID, "IGNNITION: gru_v1_reset: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(zx && zh2 && h && rh, IGN_ERR_INVALID, "IGNNITION: gru_v1_reset: null pointer");
+  gru_v1_reset_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh2, h, n, units, rh);
+  IGN_CHECK_LAUNCH("gru_v1_reset");
+  return IGN_OK;
+}
+
+extern "C" int ign_gru_v1_out(const float* zx, const float* zh2, const float* zhh, const float* h, int64_t n, int units,
+                              float* out, void* stream) {
+  IGN_REQUIRE(n >= 0 && units > 0, IGN_ERR_INVALID, "IGNNITION: gru_v1_out: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(zx && zh2 && zhh && h && out, IGN_ERR_INVALID, "IGNNITION: gru_v1_out: null pointer");
+  gru_v1_out_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh2, zhh, h, n, units, out);
+  IGN_CHECK_LAUNCH("gru_v1_out");
+  return IGN_OK;
+}
+
+extern "C" int ign_gru_v1_bwd_out(float* zx, float* zh2, float* zhh, const float* h, const float* d_out, int64_t n,
+                                  int units, float* dh_direct, void* stream) {
+  IGN_REQUIRE(n >= 0 && units > 0, IGN_ERR_INVALID, "IGNNITION: gru_v1_bwd_out: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(zx && zh2 && zhh && h && d_out && dh_direct, IGN_ERR_INVALID, "IGNNITION: gru_v1_bwd_out: null pointer");
+  gru_v1_bwd_out_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh2, zhh, h, d_out, n,
+                                                                                           units, dh_direct);
+  IGN_CHECK_LAUNCH("gru_v1_bwd_out");
+  return IGN_OK;
+}
+
+extern "C" int ign_gru_v1_bwd_reset(float* zx, float* zh2, const float* h, const float* d_rh, int64_t n, int units,
+                                    float* dh_direct, void* stream) {
+  IGN_REQUIRE(n >= 0 && units > 0, IGN_ERR_INVALID, "IGNNITION: gru_v1_bwd_reset: bad shape");
+  if (n == 0) return IGN_OK;
+  IGN_REQUIRE(zx && zh2 && h && d_rh && dh_direct, IGN_ERR_INVALID, "IGNNITION: gru_v1_bwd_reset: null pointer");
+  gru_v1_bwd_reset_kernel<<<(unsigned)ign_cdiv(n * units, 256), 256, 0, ign_stream(stream)>>>(zx, zh2, h, d_rh, n, units,
+                                                                                             dh_direct);
+  IGN_CHECK_LAUNCH("gru_v1_bwd_reset");
   return IGN_OK;
 }
 

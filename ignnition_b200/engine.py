@@ -67,6 +67,7 @@ class _MPPlan:
         self.msg_dim = 0
         self.concat2 = False   # concat along the feature axis: rows gathered per CSR position of source 0
         self.msg_rows = False  # ordered walk over message-MLP rows instead of source states
+        self.v1 = False        # GRUCell(reset_after=False): generic composition only
         self.msg_src: List[bool] = []   # per source: its messages come from a message network (rows in edge order)
         self.attn = False      # attention aggregation: column softmax over one sample's destinations
         self.conv = False      # convolution aggregation: (sum . conv_kernel + self) / degree, activation
@@ -261,11 +262,25 @@ class Engine:
                         raise RuntimeError("IGNNITION: only GRU cells are supported (LSTM cannot run in "
                                            "the reference: single-tensor state, auxilary_classes.py:764)")
                     params = mp.update.cell_parameters
-                    if str(params.get("reset_after", True)) not in ("True", "true", "1"):
-                        raise RuntimeError("IGNNITION: GRU reset_after=False is not built")
+                    # GRUCell(reset_after=False), the Keras v1 cell: one bias vector, the reset gate applied before
+                    # the candidate's recurrent product -> three Dense products per step (ops.gru_cell_v1), none of
+                    # the fused kernels
+                    p.v1 = str(params.get("reset_after", True)) not in ("True", "true", "1")
+                    # every other key of the JSON entry goes to tf.keras.layers.GRUCell(**parameters)
+                    # (auxilary_classes.py:740-750): values that are Keras' defaults change nothing, anything else
+                    # would change the arithmetic these kernels hard-wire
+                    same = {"activation": ("tanh",), "recurrent_activation": ("sigmoid",), "use_bias": (True, "True"),
+                            "dropout": (0, 0.0, "0", "0.0"), "recurrent_dropout": (0, 0.0, "0", "0.0"),
+                            "implementation": (1, 2, "1", "2"), "kernel_initializer": None,
+                            "recurrent_initializer": None, "bias_initializer": None, "reset_after": None,
+                            "units": None, "name": None}
+                    for key, val in params.items():
+                        if key not in same or (same[key] is not None and val not in same[key]):
+                            raise RuntimeError("IGNNITION: GRUCell parameter %s = %r is not built in the B200 engine "
+                                               "(supported: reset_after, and Keras' defaults for the rest)" % (key, val))
                     self._add_param(p.dst + "_update/kernel", (p.msg_dim, 3 * fd), "glorot")
                     self._add_param(p.dst + "_update/recurrent_kernel", (fd, 3 * fd), "orthogonal")
-                    self._add_param(p.dst + "_update/bias", (2, 3 * fd), "zeros")
+                    self._add_param(p.dst + "_update/bias", (3 * fd,) if p.v1 else (2, 3 * fd), "zeros")
                 else:
                     self._add_ff(p.dst + "_ff_update", mp.update.model, p.msg_dim + fd, last_units=fd)
                 stage_plans.append(p)
@@ -526,11 +541,11 @@ class Engine:
                     # short sequences (RouteNet paths): one streaming launch per step instead of a walk
                     max_steps = sum(g.max_seq.get(a.name, 1 << 30) for a in p.adjs)
                     if (p.key in g.order and 1 <= max_steps <= self.max_step_launches and p.msg_dim == 32
-                            and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()):
+                            and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled() and not p.v1):
                         g.step_plan[p.key] = (ops.seq_step_plan(g.meta[p.key], g.steps[p.key][1], max_steps), max_steps)
                     # training: BPTT runs step-synchronously on the tensor cores (ign_gru_seq_bwd_steps)
                     # (below one tile per SM the 2 x max_steps launches cost more than the fp32 walk they replace)
-                    if (training and p.key in g.order and 1 <= max_steps <= self.max_bwd_step_launches
+                    if (training and p.key in g.order and 1 <= max_steps <= self.max_bwd_step_launches and not p.v1
                             and p.msg_dim == 32 and self.hidden[p.dst] == 32 and ops.tensor_cores_enabled()
                             and g.num[p.dst] >= self.bwd_steps_min_rows):
                         g.step_plan_bwd[p.key] = g.step_plan.get(p.key) or (
@@ -656,11 +671,11 @@ class Engine:
 
         # aggregating kinds
         fused = (p.kind == "agg_gru" and p.op == ops.OP_SUM and len(p.adjs) == 1 and msgs[0] is None
-                 and not p.conv and not p.attn and self._fusable(p.msg_dim, h.shape[1])
+                 and not p.conv and not p.attn and not p.v1 and self._fusable(p.msg_dim, h.shape[1])
                  and (self.fuse_sum_gru if self.fuse_sum_gru is not None
                       else (not ops.tensor_cores_enabled() or n_dst < ops.SMALL_ROWS)))   # small: 1 launch, not 3
         fused_tc = (p.kind == "agg_gru" and len(p.adjs) == 1 and msgs[0] is None and not p.conv and not p.attn
-                    and not fused and n_dst > 0
+                    and not fused and n_dst > 0 and not p.v1
                     and (self.fused_tc if self.fused_tc is not None else h.shape[1] == 64)
                     and ops.agg_gru_cell_tc_supported(p.msg_dim, h.shape[1]))
         if fused_tc:
@@ -765,7 +780,7 @@ class Engine:
             widths = set(self.hidden.values())
             ok = (len(widths) == 1 and next(iter(widths)) in (16, 32)
                   and 1 <= len(flat) <= 8 and len(self.entities) <= 8
-                  and all(p.msg_dim == self.hidden[p.dst] and not any(p.msg_src) and len(p.adjs) <= 4
+                  and all(p.msg_dim == self.hidden[p.dst] and not any(p.msg_src) and len(p.adjs) <= 4 and not p.v1
                           and ((p.kind == "seq_gru" and not p.concat2)
                                or (p.kind == "agg_gru" and p.op == ops.OP_SUM and not p.attn and not p.conv
                                    and len(p.adjs) == 1)) for p in flat))

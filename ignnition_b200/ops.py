@@ -180,6 +180,8 @@ def gru_cell(x, h, kernel, rkernel, bias, out: Optional[torch.Tensor] = None, te
     n, units = h.shape
     if out is None:
         out = torch.empty_like(h)
+    if bias.dim() == 1:          # GRUCell(reset_after=False): bias [3 units], see gru_cell_v1
+        return gru_cell_v1(x, h, kernel, rkernel, bias, out)
     if (int(x.shape[1]), int(units)) not in GRU_FUSED_SHAPES:
         zx = dense(x, kernel, bias[0], 0)
         zh = dense(h, rkernel, bias[1], 0)
@@ -194,6 +196,48 @@ def gru_cell(x, h, kernel, rkernel, bias, out: Optional[torch.Tensor] = None, te
                                 _f(out), ws.data_ptr() if ws is not None else None, nbytes, _stream()),
                "gru_cell")
     return out
+
+
+def gru_cell_v1(x, h, kernel, rkernel, bias, out=None):
+    """One step of GRUCell(reset_after=False) (bias [3 units]): the reset gate multiplies h before the candidate's
+    recurrent product, so the step is three Dense products around two element-wise kernels (ign_gru_v1_*)."""
+    lib = _lib.load()
+    n, u = h.shape
+    if out is None:
+        out = torch.empty_like(h)
+    zx = dense(x, kernel, bias, 0)
+    zh2 = dense(h, slice_cols(rkernel, 0, 2 * u), None, 0)
+    rh = torch.empty_like(h)
+    _lib.check(lib.ign_gru_v1_reset(_f(zx), _f(zh2), _f(h), n, u, _f(rh), _stream()), "gru_v1_reset")
+    zhh = dense(rh, slice_cols(rkernel, 2 * u, u), None, 0)
+    _lib.check(lib.ign_gru_v1_out(_f(zx), _f(zh2), _f(zhh), _f(h), n, u, _f(out), _stream()), "gru_v1_out")
+    return out
+
+
+def gru_cell_bwd_v1(x, h, kernel, rkernel, bias, d_out, dx, dh, dk, drk, db):
+    """Backward of gru_cell_v1: the gates recomputed, ign_gru_v1_bwd_out / _reset for the gate gradients, ign_dense_bwd
+    for the three products; dk / drk / db accumulate."""
+    lib = _lib.load()
+    n, u = h.shape
+    r_zr, r_h = slice_cols(rkernel, 0, 2 * u), slice_cols(rkernel, 2 * u, u)
+    zx = dense(x, kernel, bias, 0)
+    zh2 = dense(h, r_zr, None, 0)
+    rh = torch.empty_like(h)
+    _lib.check(lib.ign_gru_v1_reset(_f(zx), _f(zh2), _f(h), n, u, _f(rh), _stream()), "gru_v1_reset")
+    zhh = dense(rh, r_h, None, 0)
+    direct = torch.empty_like(h)
+    _lib.check(lib.ign_gru_v1_bwd_out(_f(zx), _f(zh2), _f(zhh), _f(h), _f(d_out), n, u, _f(direct), _stream()),
+               "gru_v1_bwd_out")
+    d_rh = torch.empty_like(h)
+    d_r_h = torch.zeros_like(r_h)
+    dense_bwd(rh, r_h, 0, None, zhh, d_rh, d_r_h, None)
+    _lib.check(lib.ign_gru_v1_bwd_reset(_f(zx), _f(zh2), _f(h), _f(d_rh), n, u, _f(direct), _stream()),
+               "gru_v1_bwd_reset")
+    d_r_zr = torch.zeros_like(r_zr)
+    dense_bwd(x, kernel, 0, None, zx, dx, dk, db)
+    dense_bwd(h, r_zr, 0, None, zh2, dh, d_r_zr, None)
+    axpy(1.0, direct, dh)
+    axpy(1.0, gather_concat([d_r_zr, d_r_h], [None, None], u), drk)
 
 
 def agg_gru_cell(rowptr, col, src_states, h_dst, kernel, rkernel, bias, out=None, agg_out=None):
@@ -368,7 +412,7 @@ def gru_seq(steps_rowptr, steps, order, srcs: List[torch.Tensor], h0, kernel, rk
     n, units = h0.shape
     if out is None:
         out = torch.empty_like(h0)
-    if (int(srcs[0].shape[1]), int(units)) not in GRU_FUSED_SHAPES:
+    if bias.dim() == 1 or (int(srcs[0].shape[1]), int(units)) not in GRU_FUSED_SHAPES:
         return gru_seq_generic(steps_rowptr, steps, srcs, h0, kernel, rkernel, bias, out, h_seq)
     sp = _ptr_array(srcs, torch.float32)
     if gru_seq_proj_pays(int(steps.numel()), srcs, units, meta, n):
@@ -538,6 +582,8 @@ def gru_cell_bwd(x, h, kernel, rkernel, bias, d_out, dx, dh, dk, drk, db):
     lib = _lib.load()
     n, units = h.shape
     f_in = x.shape[1]
+    if bias.dim() == 1:
+        return gru_cell_bwd_v1(x, h, kernel, rkernel, bias, d_out, dx, dh, dk, drk, db)
     if not (f_in == units and units in (16, 32)):
         # generic shapes (config 5's 64-wide model, f_in != units): recompute the two gate GEMMs, one element-wise
         # kernel for the gate gradients, and the Dense backward for dx / dh and the weight gradients
@@ -559,7 +605,7 @@ def gru_seq_bwd(steps_rowptr, steps, order, srcs, h0, h_seq, kernel, rkernel, bi
                 dk, drk, db):
     lib = _lib.load()
     n, units = h0.shape
-    if not (int(srcs[0].shape[1]) == int(units) and int(units) in (16, 32)):
+    if bias.dim() == 1 or not (int(srcs[0].shape[1]) == int(units) and int(units) in (16, 32)):
         return gru_seq_bwd_generic(steps_rowptr, steps, srcs, h0, h_seq, kernel, rkernel, bias, d_out, d_steps, dh0,
                                    dk, drk, db)
     sp = _ptr_array(srcs, torch.float32)

@@ -241,7 +241,7 @@ class PartitionedEngine:
         self.plans = []
         for stage in engine.plans:
             for p in stage:
-                if (p.kind != "agg_gru" or len(p.adjs) != 1 or p.conv or p.attn or
+                if (p.kind != "agg_gru" or len(p.adjs) != 1 or p.conv or p.attn or p.v1 or
                         any(op.type == "feed_forward_nn" for s in p.mp.source_entities for op in s.message_formation)):
                     raise RuntimeError("IGNNITION: partitioned graphs run sum / mean / max aggregations of source "
                                        "states with a recurrent update; message passing to '%s' is not of that "

@@ -404,7 +404,7 @@ class Trainer:
                 dh = torch.empty_like(h_old)
                 n_dst = h_old.shape[0]
                 if (ops.tensor_cores_enabled() and agg.shape[1] == 32 and h_old.shape[1] == 32 and n_dst >= 4096
-                        and e.max_bwd_step_launches >= 1):
+                        and e.max_bwd_step_launches >= 1 and not p.v1):
                     # one GRU step = a sequence of length 1 whose message is the aggregate: the tensor-core BPTT kernels
                     # with the identity plan (destination i, step i), built once per batch and entity
                     key = "cell/" + p.dst

@@ -352,6 +352,21 @@ int ign_optimizer_step(int kind, float* w, const float* g, float* s1, float* s2,
  * (two ign_dense calls) and the old state h (auxilary_classes.py:752-765 for widths the fused kernels do not cover) */
 int ign_gru_gates_fwd(const float* zx, const float* zh, const float* h, int64_t n, int units, float* out, void* stream);
 
+/* GRUCell with reset_after = False (the Keras v1 cell; a model JSON reaches it through the recurrent network's cell
+ * parameters, auxilary_classes.py:740-750, bias [3 units]): the reset gate multiplies h before the candidate's recurrent
+ * product, so one step is zx = x K + b, zh2 = h R[:, :2U], rh = sigmoid(zx_r + zh2_r) * h (ign_gru_v1_reset),
+ * zhh = rh R[:, 2U:], out = z h + (1 - z) tanh(zx_h + zhh) (ign_gru_v1_out) -- three ign_dense calls around two
+ * element-wise kernels.  Backward: ign_gru_v1_bwd_out turns the z and candidate slices of zx / zh2 and zhh into their
+ * gradients in place and writes dh_direct = d_out * z; after d_rh = d_zhh R[:, 2U:]^T (ign_dense_bwd) ign_gru_v1_bwd_reset
+ * turns the r slices into theirs and adds d_rh * r to dh_direct; ign_dense_bwd on (x, K) and (h, R[:, :2U]) finish. */
+int ign_gru_v1_reset(const float* zx, const float* zh2, const float* h, int64_t n, int units, float* rh, void* stream);
+int ign_gru_v1_out(const float* zx, const float* zh2, const float* zhh, const float* h, int64_t n, int units, float* out,
+                   void* stream);
+int ign_gru_v1_bwd_out(float* zx, float* zh2, float* zhh, const float* h, const float* d_out, int64_t n, int units,
+                       float* dh_direct, void* stream);
+int ign_gru_v1_bwd_reset(float* zx, float* zh2, const float* h, const float* d_rh, int64_t n, int units,
+                         float* dh_direct, void* stream);
+
 /* Keras Adam step on a flat parameter buffer (generate_model.py:796-818) [TF-2.1 semantics]:
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v moments; w -= lr_t*m/(sqrt(v)+eps).  step is 1-based. */
 int ign_adam_step(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

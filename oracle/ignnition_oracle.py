@@ -259,7 +259,8 @@ class Oracle:
                 if up["type"] == "recurrent_neural_network":
                     shapes[dst + "_update/kernel"] = (fin, 3 * fd)
                     shapes[dst + "_update/recurrent_kernel"] = (fd, 3 * fd)
-                    shapes[dst + "_update/bias"] = (2, 3 * fd)
+                    ra = self.nn[up["nn_name"]].get("reset_after", True)       # GRUCell kwargs come from the JSON
+                    shapes[dst + "_update/bias"] = (2, 3 * fd) if str(ra) in ("True", "true", "1") else (3 * fd,)
                 else:
                     din = fin + fd
                     ls = self.layer_names(up["nn_name"], "update")
@@ -468,7 +469,7 @@ class Oracle:
             if arch["recurrent_type"] != "GRU":
                 raise ValueError("oracle: only GRU is restated (LSTM cannot run in the reference: "
                                  "single-tensor state, auxilary_classes.py:764)")
-            ra = arch.get("reset_after", True)
+            ra = str(arch.get("reset_after", True)) in ("True", "true", "1")
             K, R, b = (w[dst + "_update/kernel"], w[dst + "_update/recurrent_kernel"],
                        w[dst + "_update/bias"])
             cell = lambda x, h: gru_cell(x, h, K, R, b, ra)

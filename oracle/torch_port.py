@@ -36,6 +36,12 @@ def _act(name, x):
 
 def gru_cell(x, h, K, R, b):
     u = h.shape[1]
+    if b.dim() == 1:                    # GRUCell(reset_after=False): one bias, r applied before the recurrent product
+        mx = x @ K + b
+        z = torch.sigmoid(mx[:, :u] + h @ R[:, :u])
+        r = torch.sigmoid(mx[:, u:2 * u] + h @ R[:, u:2 * u])
+        hh = torch.tanh(mx[:, 2 * u:] + (r * h) @ R[:, 2 * u:])
+        return z * h + (1 - z) * hh
     mx = x @ K + b[0]
     mh = h @ R + b[1]
     z = torch.sigmoid(mx[:, :u] + mh[:, :u])

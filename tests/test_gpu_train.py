@@ -569,6 +569,31 @@ def test_gradients_with_one_launch_forward(model):
     assert launches == [True]
 
 
+@pytest.mark.parametrize("agg", ["sum", "ordered"])
+def test_gru_reset_after_false_runs_and_trains(agg):
+    """GRUCell(reset_after=False), reachable through the recurrent network's JSON entry (the keys go to
+    tf.keras.layers.GRUCell(**parameters), auxilary_classes.py:740-750): one bias vector [3 units], the reset gate
+    applied before the candidate's recurrent product.  Forward parity (checked inside _grad_check against the torch
+    oracle, which agrees with the NumPy oracle's reset_after branch) and every gradient vs fp64 autograd, for the
+    aggregate-then-update and the ordered walk.  Any other non-default GRUCell keyword fails loudly."""
+    from test_gpu_model import _mpnn_json, _mpnn_sample, make
+    from ignnition_b200.generator import sample_dimensions
+    rng = np.random.RandomState(123)
+    mj = _mpnn_json(agg, 32)
+    mj["neural_networks"][0]["reset_after"] = False
+    samples = [_mpnn_sample(rng, n, 5) for n in (25, 140)]
+    if agg == "ordered":
+        for s_ in samples:
+            for v in s_["entities"]:
+                s_["adj"].setdefault(v, [v])
+    eng = _grad_check(mj, samples)
+    assert eng.param_table["node_update/bias"][1] == (96,)
+    bad = _mpnn_json(agg, 32)
+    bad["neural_networks"][0]["activation"] = "relu"
+    with pytest.raises(RuntimeError, match="IGNNITION: GRUCell parameter activation"):
+        make(bad, sample_dimensions(samples[0]))
+
+
 def test_generic_width_trains():
     """hidden_state_dimension is free in the reference's schema: a 48-wide model runs (two Dense GEMMs + the
     element-wise GRU gates) and trains (generic GRU-cell backward) with parity against the oracles"""
