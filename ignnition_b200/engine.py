@@ -116,6 +116,7 @@ class Engine:
         self.max_graphs = 32            # captured CUDA graphs kept by forward_graphed (one per batch shape)
         self.bwd_steps_min_rows = ops.BWD_STEPS_MIN_ROWS   # below: the fp32 BPTT walk (one launch) instead of 2 launches per step
         self._needs_perm = set()
+        self.has_dropout = False        # a network holds Dropout layers with a non-zero rate: inference only
         self.plans: List[List[_MPPlan]] = []
         self.sequences: List[SequenceSpec] = []
         self.param_table: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
@@ -145,10 +146,12 @@ class Engine:
 
     def _add_ff(self, prefix: str, ff: FeedForward, in_dim: int, last_units: Optional[int] = None) -> int:
         n = len(ff.layers)
+        if getattr(ff, "dropout", False):
+            self.has_dropout = True
         for j, l in enumerate(ff.layers):
             if l.type_layer != "Dense":
                 raise RuntimeError("IGNNITION: layer type %s is not supported by the B200 engine "
-                                   "(only Dense)" % l.type_layer)
+                                   "(Dense, and Dropout as the identity at inference)" % l.type_layer)
             units = last_units if (j == n - 1 and last_units is not None) else l.units
             if units is None:
                 raise RuntimeError("IGNNITION: Dense layer %s has no units" % l.name)

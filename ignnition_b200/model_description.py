@@ -68,8 +68,10 @@ class DenseLayer:
 
 @dataclass
 class FeedForward:
-    """A Dense stack (auxilary_classes.py:868-975)."""
+    """A Dense stack (auxilary_classes.py:868-975).  ``dropout``: the JSON holds Dropout layers with a non-zero rate
+    (identity at inference, so they are not kept as layers; training through them is stochastic and not built)."""
     layers: List[DenseLayer]
+    dropout: bool = False
 
 
 @dataclass
@@ -150,10 +152,14 @@ def _require(d: dict, keys, where: str):
 
 def _parse_layers(arch: list, role: str) -> FeedForward:
     layers = []
+    dropout = False
     for i, l in enumerate(arch):
         l = dict(l)
         _require(l, ["type_layer"], "a layer of the %s neural network" % role)
         t = l.pop("type_layer")
+        if t == "Dropout":                 # tf.keras.layers.Dropout: the identity outside training
+            dropout = dropout or float(l.get("rate", 0.0)) > 0.0
+            continue
         # default layer name: auxilary_classes.py:909-910
         name = l.pop("name", "layer_%d_%s_%s" % (i, t, role))
         act = l.pop("activation", None)
@@ -166,7 +172,7 @@ def _parse_layers(arch: list, role: str) -> FeedForward:
             use_bias = use_bias == "True"
         layers.append(DenseLayer(t, name, None if units is None else int(units), act, reg,
                                  bool(use_bias), l))
-    return FeedForward(layers)
+    return FeedForward(layers, dropout)
 
 
 class ModelDescription:

@@ -77,6 +77,9 @@ class Trainer:
         if kind != "Adam" and kind not in ops.OPTIMIZERS:
             raise RuntimeError("IGNNITION: optimizer %s is not built in the B200 engine (one of Adam, %s)"
                                % (kind, ", ".join(sorted(ops.OPTIMIZERS))))
+        if getattr(engine, "has_dropout", False):
+            raise RuntimeError("IGNNITION: training through Dropout layers (a random mask per step) is not built in the "
+                               "B200 engine; inference treats them as the identity, as Keras does")
         loss_name = engine.model.get_loss()
         if loss_name not in ops.LOSSES:
             raise RuntimeError("IGNNITION: loss %s is not built in the B200 engine (one of %s)"

@@ -219,6 +219,8 @@ class Oracle:
         out = []
         for i, l in enumerate(self.nn[nn_name]["nn_architecture"]):
             l = dict(l)
+            if l["type_layer"] == "Dropout":       # tf.keras.layers.Dropout: the identity outside training
+                continue
             l.setdefault("name", "layer_%d_%s_%s" % (i, l["type_layer"], role))
             out.append(l)
         return out

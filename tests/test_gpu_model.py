@@ -425,6 +425,25 @@ def test_readout_pooling_product_extend_chain(pool):
     assert rel_err(rd["e_prod"].cpu().numpy(), st0["e_prod"]) < RTOL_STATE_TC
 
 
+def test_dropout_layers_are_identity_at_inference():
+    """tf.keras.layers.Dropout in a network's JSON (any Keras layer type is accepted by the reference,
+    auxilary_classes.py:839-848): the identity outside training, and the default layer names keep counting it
+    (layer_<i>_Dense_...); a train step through it raises instead of silently skipping the mask"""
+    from ignnition_b200.train import Trainer
+    rng = np.random.RandomState(4)
+    mj = _mpnn_json("sum", 32)
+    mj["neural_networks"][1]["nn_architecture"].insert(1, {"type_layer": "Dropout", "rate": 0.5})
+    samples = [_mpnn_sample(rng, n, 5) for n in (30, 90)]
+    md, eng, o64, w = make(mj, sample_dimensions(samples[0]))
+    assert "readout_model_0/layer_2_Dense_readout/kernel" in eng.param_table
+    tens = [tensors_of(md, s)[0] for s in samples]
+    pred = eng.forward(eng.prepare(tens)).cpu().numpy().reshape(-1)
+    want = np.concatenate([o64.forward(t, w).reshape(-1) for t in tens])
+    assert rel_err(pred, want) < RTOL
+    with pytest.raises(RuntimeError, match="IGNNITION: training through Dropout"):
+        Trainer(eng)
+
+
 def test_unsupported_keywords_fail_loudly():
     from ignnition_b200 import Engine
     mj = _mpnn_json("sum")
