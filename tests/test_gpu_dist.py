@@ -37,9 +37,10 @@ def _rank_main(rank, world, port, steps, n_samples, out_dir):
                       LOCAL_RANK=str(rank))
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
-    from ignnition_b200 import Engine, ModelDescription
+    from ignnition_b200 import Engine, ModelDescription, ops
     from ignnition_b200.parallel import shard_samples
     from ignnition_b200.train import Trainer
+    ops.set_tensor_cores(False)          # see the test: the same arithmetic at every batch size
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", device_id=dev)
@@ -75,11 +76,19 @@ def test_trainer_nccl_world2_matches_single_process(tmp_path):
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "routenet_nsfnet.json")))
     md = ModelDescription(g["model_json"], g["reference_meta"]["dimensions"])
     samples, labels = _batch(md, n_samples)
-    ref = Engine(md, device="cuda", seed=7)
-    rt = Trainer(ref, world_size=1)
-    rg = ref.prepare(samples, labels=labels, training=True)
-    for _ in range(steps):
-        rt.train_step(rg)
+    # fp32 kernels in the workers and here: the engine picks kernels by batch size (3xTF32 Dense layers from 4096 rows:
+    # the 32-sample reference batch has 5824 paths, a rank's half 2912), and four Adam steps turn a 1e-6 difference of a
+    # near-zero gradient into 1e-4 of a weight; with one arithmetic only the summation order differs
+    from ignnition_b200 import ops
+    prev = ops.set_tensor_cores(False)
+    try:
+        ref = Engine(md, device="cuda", seed=7)
+        rt = Trainer(ref, world_size=1)
+        rg = ref.prepare(samples, labels=labels, training=True)
+        for _ in range(steps):
+            rt.train_step(rg)
+    finally:
+        ops.set_tensor_cores(prev)
     want = ref.weights.cpu().numpy()
     w0 = np.load(os.path.join(str(tmp_path), "w_0.npy"))
     w1 = np.load(os.path.join(str(tmp_path), "w_1.npy"))
