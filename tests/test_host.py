@@ -646,3 +646,121 @@ def test_batch_window_equals_assembling_the_window(case, qsize):
         assert win.max_seq == want.max_seq and set(win.arrays) == set(want.arrays)
         for k in want.arrays:
             assert np.array_equal(win.arrays[k], want.arrays[k]), (k, lo, hi)
+
+
+# ------------------------------------------------------------------ the two oracles on the keywords added in round 2
+def _sum_mpnn(hidden=32, agg="sum"):
+    return {
+        "entities": [{"name": "node", "hidden_state_dimension": hidden, "features": [{"name": "x", "normalization": "None"}]}],
+        "message_passing": {"num_iterations": 2, "stages": [{"stage_name": "s", "stage_mp": [{
+            "destination_entity": "node",
+            "source_entities": [{"name": "node", "adj_vector": "adj", "message": [{"type": "direct_assignation"}]}],
+            "aggregation": {"type": agg}, "update": {"type": "recurrent_neural_network", "nn_name": "rec"}}]}]},
+        "readout": [{"type": "predict", "input": ["node"], "label": "y", "nn_name": "ro"}],
+        "neural_networks": [{"nn_name": "rec", "nn_type": "recurrent_neural_network", "recurrent_type": "GRU"},
+                            {"nn_name": "ro", "nn_type": "feed_forward", "nn_architecture": [
+                                {"type_layer": "Dense", "units": 8, "activation": "relu"},
+                                {"type_layer": "Dense", "units": 1, "activation": "None"}]}],
+        "learning_options": {"loss": "MeanSquaredError", "optimizer": {"type": "Adam"}},
+    }
+
+
+def _sum_sample(rng, n):
+    adj = {"v%d" % d: ["v%d" % s for s in rng.randint(0, n, rng.randint(1, 5))] for d in range(n)}
+    return {"entities": {"v%d" % i: "node" for i in range(n)}, "adj": adj, "x": rng.randn(n, 3).tolist(),
+            "y": rng.randn(n).tolist()}
+
+
+def _both_oracles(mj, samples):
+    from oracle.torch_port import TorchOracle
+    dims = sample_dimensions(samples[0])
+    md = ModelDescription(mj, dims)
+    feats = [f.name for f in md.get_all_features()]
+    out, _, _ = md.get_output_info()
+    o64 = orc.Oracle(mj, dims, dtype=np.float64)
+    w = o64.init_weights(7)
+    to = TorchOracle(mj, dims)
+    for s in samples:
+        tens, _ = sample_to_tensors(s, feats, out, md.get_adjecency_info(), md.get_interleave_tensors(),
+                                    md.get_additional_input_names(), True)
+        p_n = o64.forward(tens, w)
+        p_t = to.forward(tens, to.params(w)).detach().numpy()
+        assert p_n.reshape(-1).shape == p_t.reshape(-1).shape
+        assert np.abs(p_t.reshape(-1) - p_n.reshape(-1)).max() < 1e-12
+    return md, o64, w
+
+
+@pytest.mark.parametrize("agg", ["sum", "ordered"])
+def test_oracles_agree_on_gru_reset_after_false(agg):
+    """GRUCell(reset_after=False) from the JSON's cell parameters: one bias vector [3 units] in both oracles, the reset
+    gate before the candidate's recurrent product; and the v1 step differs from the v2 step on the same numbers"""
+    rng = np.random.RandomState(2)
+    mj = _sum_mpnn(16, agg)
+    mj["neural_networks"][0]["reset_after"] = False
+    md, o64, w = _both_oracles(mj, [_sum_sample(rng, 12), _sum_sample(rng, 30)])
+    assert w["node_update/bias"].shape == (48,)
+    x, h = rng.randn(5, 16), rng.randn(5, 16)
+    K, R = w["node_update/kernel"], w["node_update/recurrent_kernel"]
+    v1 = orc.gru_cell(x, h, K, R, w["node_update/bias"], False)
+    v2 = orc.gru_cell(x, h, K, R, np.stack([w["node_update/bias"], np.zeros(48)]), True)
+    assert np.abs(v1 - v2).max() > 1e-3
+    u = 16                                          # Keras v1 formula, written out
+    mx = x @ K + w["node_update/bias"]
+    z = 1 / (1 + np.exp(-(mx[:, :u] + h @ R[:, :u])))
+    r = 1 / (1 + np.exp(-(mx[:, u:2 * u] + h @ R[:, u:2 * u])))
+    hh = np.tanh(mx[:, 2 * u:] + (r * h) @ R[:, 2 * u:])
+    assert np.abs(v1 - (z * h + (1 - z) * hh)).max() < 1e-12
+
+
+def test_oracles_agree_on_dot_product_and_dropout():
+    """readout `dot_product` = tf.tensordot(a, b, axes=0) registered 1 wide (generate_model.py:375-376), and Dropout
+    layers (identity outside training; the default layer names keep counting them)"""
+    rng = np.random.RandomState(3)
+    mj = _sum_mpnn(16)
+    mj["neural_networks"].append({"nn_name": "to1", "nn_type": "feed_forward", "nn_architecture": [
+        {"type_layer": "Dense", "units": 1, "activation": "tanh"}]})
+    mj["neural_networks"][1]["nn_architecture"].insert(1, {"type_layer": "Dropout", "rate": 0.3})
+    mj["readout"] = [{"type": "neural_network", "input": ["node"], "nn_name": "to1", "output_name": "n1"},
+                     {"type": "product", "type_product": "dot_product", "input": ["node", "n1"], "output_name": "cells"},
+                     {"type": "predict", "input": ["cells"], "label": "y", "nn_name": "ro"}]
+    samples = [_sum_sample(rng, 4), _sum_sample(rng, 7)]
+    md, o64, w = _both_oracles(mj, samples)
+    assert any(k.endswith("layer_2_Dense_readout/kernel") for k in w) and not any("Dropout" in k for k in w)
+    ff = md.get_readout_operations()[-1].architecture
+    assert ff.dropout and [l.type_layer for l in ff.layers] == ["Dense", "Dense"]
+
+
+def test_oracles_agree_on_attention_over_two_sources():
+    """generate_model.py:523-543: one edge list for both sources, the second source's padded columns start at ITS OWN
+    edge count per destination, colliding cells add up (quirk 7)"""
+    rng = np.random.RandomState(5)
+    da = [{"type": "direct_assignation"}]
+    upd = {"type": "recurrent_neural_network", "nn_name": "rec"}
+    ents = [{"name": n, "hidden_state_dimension": 8, "features": [{"name": f, "normalization": "None"}]}
+            for n, f in (("link", "cap"), ("node", "deg"), ("path", "tr"))]
+    mj = {"entities": ents,
+          "message_passing": {"num_iterations": 2, "stages": [
+              {"stage_name": "s1", "stage_mp": [{"destination_entity": "path",
+                                                 "source_entities": [{"name": "link", "adj_vector": "lp", "message": da},
+                                                                     {"name": "node", "adj_vector": "np", "message": da}],
+                                                 "aggregation": {"type": "attention"}, "update": upd}]},
+              {"stage_name": "s2", "stage_mp": [{"destination_entity": "link",
+                                                 "source_entities": [{"name": "path", "adj_vector": "pl", "message": da}],
+                                                 "aggregation": {"type": "sum"}, "update": upd}]}]},
+          "readout": [{"type": "predict", "input": ["path"], "label": "y", "nn_name": "ro"}],
+          "neural_networks": _sum_mpnn()["neural_networks"],
+          "learning_options": {"loss": "MeanSquaredError", "optimizer": {"type": "Adam"}}}
+    samples = []
+    for n_link, n_node, n_path in ((5, 4, 7), (9, 6, 20)):
+        lp, npth, pl = {}, {}, {}
+        for p_ in range(n_path):
+            ls = rng.choice(n_link, rng.randint(2, min(5, n_link) + 1), replace=False)      # more links than nodes: collisions
+            lp["p%d" % p_] = ["l%d" % l for l in ls]
+            npth["p%d" % p_] = ["n%d" % n for n in rng.choice(n_node, rng.randint(1, 3), replace=False)]
+            for l in ls:
+                pl.setdefault("l%d" % l, []).append("p%d" % p_)
+        ent = {**{"l%d" % i: "link" for i in range(n_link)}, **{"n%d" % i: "node" for i in range(n_node)},
+               **{"p%d" % i: "path" for i in range(n_path)}}
+        samples.append({"entities": ent, "lp": lp, "np": npth, "pl": pl, "cap": rng.rand(n_link).tolist(),
+                        "deg": rng.rand(n_node).tolist(), "tr": rng.rand(n_path).tolist(), "y": rng.rand(n_path).tolist()})
+    _both_oracles(mj, samples)
