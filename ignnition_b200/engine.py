@@ -46,6 +46,7 @@ class DeviceGraph:
         self.host_offsets: Dict[str, np.ndarray] = {}    # per-sample row offsets per entity, host copy
         self.small = False                               # built for the one-launch loop of small graphs (no walk order)
         self.small_rows = False                          # every entity small enough for ign_csr_build_small
+        self.small_fit = False                           # ... and the model and row lengths fit the one-launch loop
         self.attn_comb: Dict[str, tuple] = {}            # attention over several sources: (rowptr, perm, slot_col, max_len)
         self.step_plan: Dict[str, tuple] = {}            # step-major plan of short ordered updates
         self.step_plan_bwd: Dict[str, tuple] = {}        # the same plan for the step-synchronous backward pass
@@ -78,8 +79,12 @@ class Engine:
                  csr_mode: int = ops.CSR_RANK, sort_by_length: bool = True, max_step_launches: int = 0,
                  fuse_sum_gru: Optional[bool] = None):
         self.model = model
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        if self.device.type != "cuda":
+        # device="plan": compile the model description into kernel choices and the parameter table only -- no device, no
+        # weights, nothing can run (host-side checks and tests of the plan logic)
+        plan_only = isinstance(device, str) and device == "plan"
+        self.device = None if plan_only else (
+            torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        if not plan_only and self.device.type != "cuda":
             raise RuntimeError("IGNNITION: ignnition_b200 runs on CUDA devices only (no CPU fallback)")
         # adjacency builder: IGN_CSR_RANK places every edge at rowptr[dst] + seq (the reference's scatter_nd((dst, seq)),
         # generate_model.py:490; histogram + scan + placement = 0.12 ms for 6.1 M edges), IGN_CSR_SORT ignores seq and
@@ -124,6 +129,8 @@ class Engine:
         self._reg: Dict[str, float] = {}
         self._n_params = 0
         self._compile()
+        if plan_only:
+            return
         self.weights = torch.zeros(self._n_params, dtype=torch.float32, device=self.device)
         self.reset_parameters(seed)
 
@@ -476,7 +483,8 @@ class Engine:
         """Device adjacency builder: CSR per adjacency, length order, step tables."""
         small_rows = 0 < max(g.num.values()) <= self.small_graph_rows
         g.small_rows = small_rows                  # every adjacency fits the one-launch CSR builder
-        g.small = not training and small_rows and self._small_program_ok()
+        g.small_fit = small_rows and self._small_program_ok() and self._small_fit(g.max_seq)
+        g.small = not training and g.small_fit
         if small_rows and not check and len(self.adjacencies) <= 8:
             # one launch for every adjacency (ign_csr_build_small) instead of a dozen launches of ~3 us each
             specs = [(g.t["dst_" + a.name], g.t["src_" + a.name],
@@ -790,6 +798,20 @@ class Engine:
             self._small_ok = ok
         return ok
 
+    def _small_fit(self, max_seq: Dict[str, int]) -> bool:
+        """Row lengths the one-launch loop has been verified on (tests/test_gpu_graphs.py): every walk at most one block
+        of entries long (units per lane group), sums of any length at 32 units and up to one block at 16.  Longer
+        rows take the per-stage kernels.  ``max_seq``: the batch's longest list per adjacency (host-known)."""
+        units = next(iter(self.hidden.values()))
+        for stage in self.plans:
+            for p in stage:
+                longest = sum(int(max_seq.get(a.name, 1 << 30)) for a in p.adjs)
+                if p.kind == "seq_gru" and longest > units:
+                    return False
+                if p.kind != "seq_gru" and units < 32 and longest > units:
+                    return False
+        return True
+
     def _mp_small(self, g: DeviceGraph, state: Dict[str, torch.Tensor], T: int,
                   tape: Optional[list] = None) -> Dict[str, torch.Tensor]:
         """The T-iteration loop in one launch.  With a ``tape`` (training) every stage keeps what the backward pass
@@ -844,8 +866,7 @@ class Engine:
         if tape is None and g.small and T > 0:
             return self._mp_small(g, state, T)
         n_stages = sum(len(stage) for stage in self.plans)
-        if (tape is not None and g.small_rows and T > 0 and T * n_stages <= 64 and self.small_graph_rows > 0
-                and self._small_program_ok()):
+        if tape is not None and g.small_fit and T > 0 and T * n_stages <= 64:
             return self._mp_small(g, state, T, tape)
         for _ in range(T):
             for stage in self.plans:

@@ -764,3 +764,38 @@ def test_oracles_agree_on_attention_over_two_sources():
         samples.append({"entities": ent, "lp": lp, "np": npth, "pl": pl, "cap": rng.rand(n_link).tolist(),
                         "deg": rng.rand(n_node).tolist(), "tr": rng.rand(n_path).tolist(), "y": rng.rand(n_path).tolist()})
     _both_oracles(mj, samples)
+
+
+# ------------------------------------------------------------------ kernel choices of the Engine, without a device
+def test_engine_plan_and_one_launch_gating_on_the_host():
+    """Engine(model, device="plan") compiles the description into kernel choices and the parameter table without a GPU.
+    The one-launch loop of small graphs (csrc/small_graph.cu) is offered for models made of ordered / sum updates of
+    16 / 32-wide source states, and only for row lengths it was verified on: walks of at most one block of entries
+    (units per lane group), sums of any length at 32 units (longer rows take the per-stage kernels)."""
+    from ignnition_b200 import Engine
+    for case, ok in (("routenet_nsfnet", True), ("qsize_nsfnet", True), ("routenet_geant2", True)):
+        g = load_golden(case)
+        eng = Engine(ModelDescription(g["model_json"], g["reference_meta"]["dimensions"]), device="plan")
+        assert eng.device is None and not hasattr(eng, "weights") and eng._n_params > 0
+        assert eng._small_program_ok() == ok
+        batch = eng.assemble([orc.normalize_inputs(g["model_json"], t) for t in g["reference_tensors"][:2]])
+        assert eng._small_fit(batch.max_seq)                          # paths of <= 5 links, any number of paths per link
+        walk = [p for st in eng.plans for p in st if p.kind == "seq_gru"][0]
+        longer = dict(batch.max_seq)
+        longer[walk.adjs[0].name] = 33
+        assert not eng._small_fit(longer)
+        assert not eng._small_fit({})                                 # unknown lengths: never
+    # 16-wide states: sums are limited to one block as well; 64-wide or attention models never take the loop
+    mj = _sum_mpnn(16)
+    eng = Engine(ModelDescription(mj, {"x": 3, "adj": 0}), device="plan")
+    assert eng._small_program_ok() and eng._small_fit({"adj": 16}) and not eng._small_fit({"adj": 17})
+    eng32 = Engine(ModelDescription(_sum_mpnn(32), {"x": 3, "adj": 0}), device="plan")
+    assert eng32._small_fit({"adj": 500})
+    for bad in (_sum_mpnn(64), _sum_mpnn(32, "attention"), _sum_mpnn(32, "mean")):
+        assert not Engine(ModelDescription(bad, {"x": 3, "adj": 0}), device="plan")._small_program_ok()
+    v1 = _sum_mpnn(32)
+    v1["neural_networks"][0]["reset_after"] = False
+    e1 = Engine(ModelDescription(v1, {"x": 3, "adj": 0}), device="plan")
+    assert not e1._small_program_ok() and e1.param_table["node_update/bias"][1] == (96,)
+    with pytest.raises(RuntimeError, match="CUDA devices only"):
+        Engine(ModelDescription(_sum_mpnn(32), {"x": 3, "adj": 0}), device="cpu")
